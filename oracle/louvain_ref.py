@@ -1,0 +1,185 @@
+"""Deterministic Louvain specification (TEST INFRASTRUCTURE -- see oracle/__init__.py).
+
+Stands in for ``louvain.find_partition(g, RBConfigurationVertexPartition,
+resolution_parameter=gamma, seed=random_state)`` which ``sc.tl.louvain`` calls from
+``/root/reference/doubletdetection/doubletdetection.py:337-342``.  The
+``louvain`` / ``igraph`` packages are not in the image, so their exact move order cannot be
+reproduced: PARITY UNPINNED for this stage.  What is specified here, and what the product's C++
+implementation (``doubletdetection_b200/csrc/louvain.cpp``) must reproduce label-for-label:
+
+Quality function (RB configuration, resolution gamma, undirected, weights w):
+    Q = sum_ij (A_ij - gamma * k_i * k_j / (2m)) * delta(c_i, c_j)
+
+Algorithm (one "level"):
+  * every node starts in its own community; ``tot[c]`` = sum of weighted degrees in c;
+  * a FIFO queue is filled with all nodes in a seeded random order (SplitMix64 + Fisher-Yates,
+    ``j = next() % (i + 1)`` for i = n-1 .. 1);
+  * pop node i, remove it from its community, evaluate for its own community first and then for
+    every neighbouring community in order of first appearance in i's adjacency list
+        gain(c) = w(i, c) - ((gamma * k_i) * tot[c]) / two_m          (IEEE double, this order)
+    and move to the FIRST community with the strictly largest gain (staying wins ties);
+  * when i moves, every neighbour that is not in i's new community and not queued is appended;
+  * the level ends when the queue is empty.
+Levels: communities are renumbered by first appearance over node index, the graph is aggregated
+(neighbour lists ascending by id, internal weight kept as a self-loop counted twice), and the
+procedure repeats until a level moves no node.  Final labels are renumbered by decreasing
+community size (ties: smaller first-appearance id first), which is what louvain-igraph's
+``renumber_communities`` does.
+"""
+
+from collections import deque
+
+import numpy as np
+
+_MASK = (1 << 64) - 1
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = int(seed) & _MASK
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _MASK
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _MASK
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _MASK
+        return z ^ (z >> 31)
+
+
+def _permutation(n, rng):
+    p = list(range(n))
+    for i in range(n - 1, 0, -1):
+        j = rng.next() % (i + 1)
+        p[i], p[j] = p[j], p[i]
+    return p
+
+
+def _one_level(n, indptr, indices, weights, selfw, gamma, two_m, rng):
+    k = [0.0] * n
+    for i in range(n):
+        s = selfw[i]
+        for e in range(indptr[i], indptr[i + 1]):
+            s += weights[e]
+        k[i] = s
+    comm = list(range(n))
+    tot = list(k)
+    queue = deque(_permutation(n, rng))
+    inq = [True] * n
+    neigh_w = [0.0] * n
+    seen = [False] * n
+    moved_any = False
+    while queue:
+        i = queue.popleft()
+        inq[i] = False
+        ci = comm[i]
+        ki = k[i]
+        cands = [ci]
+        seen[ci] = True
+        neigh_w[ci] = 0.0
+        for e in range(indptr[i], indptr[i + 1]):
+            c = comm[indices[e]]
+            if not seen[c]:
+                seen[c] = True
+                neigh_w[c] = 0.0
+                cands.append(c)
+            neigh_w[c] += weights[e]
+        tot[ci] -= ki
+        best = ci
+        best_gain = neigh_w[ci] - ((gamma * ki) * tot[ci]) / two_m
+        for c in cands[1:]:
+            g = neigh_w[c] - ((gamma * ki) * tot[c]) / two_m
+            if g > best_gain:
+                best = c
+                best_gain = g
+        for c in cands:
+            seen[c] = False
+        tot[best] += ki
+        if best != ci:
+            comm[i] = best
+            moved_any = True
+            for e in range(indptr[i], indptr[i + 1]):
+                j = indices[e]
+                if comm[j] != best and not inq[j]:
+                    inq[j] = True
+                    queue.append(j)
+    return comm, moved_any
+
+
+def _aggregate(n, indptr, indices, weights, selfw, comm):
+    new_id = {}
+    for i in range(n):
+        c = comm[i]
+        if c not in new_id:
+            new_id[c] = len(new_id)
+    nc = len(new_id)
+    node2new = [new_id[comm[i]] for i in range(n)]
+    members = [[] for _ in range(nc)]
+    for i in range(n):
+        members[node2new[i]].append(i)
+    n_indptr = [0]
+    n_indices = []
+    n_weights = []
+    n_selfw = [0.0] * nc
+    for a in range(nc):
+        acc = {}
+        s = 0.0
+        for i in members[a]:
+            s += selfw[i]
+            for e in range(indptr[i], indptr[i + 1]):
+                b = node2new[indices[e]]
+                if b == a:
+                    s += weights[e]
+                else:
+                    acc[b] = acc.get(b, 0.0) + weights[e]
+        n_selfw[a] = s
+        for b in sorted(acc):
+            n_indices.append(b)
+            n_weights.append(acc[b])
+        n_indptr.append(len(n_indices))
+    return nc, n_indptr, n_indices, n_weights, n_selfw, node2new
+
+
+def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, max_levels=64):
+    """Cluster a symmetric, self-loop-free CSR graph.  Returns int64 labels, 0 = largest."""
+    indptr = [int(x) for x in indptr]
+    indices = [int(x) for x in indices]
+    n = len(indptr) - 1
+    if weights is None:
+        weights = [1.0] * len(indices)
+    else:
+        weights = [float(x) for x in weights]
+    gamma = float(resolution)
+    selfw = [0.0] * n
+    two_m = 0.0
+    for w in weights:
+        two_m += w
+    rng = SplitMix64(seed)
+    membership = list(range(n))
+    if two_m > 0.0:
+        for _ in range(max_levels):
+            comm, moved = _one_level(len(indptr) - 1, indptr, indices, weights, selfw, gamma, two_m, rng)
+            if not moved:
+                break
+            nc, indptr, indices, weights, selfw, node2new = _aggregate(
+                len(indptr) - 1, indptr, indices, weights, selfw, comm
+            )
+            membership = [node2new[c] for c in membership]
+    return relabel_by_size(np.asarray(membership, dtype=np.int64))
+
+
+def relabel_by_size(membership):
+    """Renumber by decreasing size; ties keep first-appearance order."""
+    membership = np.asarray(membership, dtype=np.int64)
+    if membership.size == 0:
+        return membership
+    _, first_idx, inv = np.unique(membership, return_index=True, return_inverse=True)
+    # ids by first appearance
+    order_fa = np.argsort(first_idx, kind="stable")
+    rank_fa = np.empty_like(order_fa)
+    rank_fa[order_fa] = np.arange(order_fa.size)
+    fa = rank_fa[inv]
+    sizes = np.bincount(fa)
+    order = np.argsort(-sizes, kind="stable")
+    new = np.empty_like(order)
+    new[order] = np.arange(order.size)
+    return new[fa].astype(np.int64)

@@ -1,0 +1,232 @@
+"""Restatements of the third-party calls the reference makes into packages that are absent from
+this image (TEST INFRASTRUCTURE -- see oracle/__init__.py).
+
+Each function names the reference call site (``/root/reference/doubletdetection/doubletdetection.py``)
+and the upstream semantics it restates (upstream sources are not available
+here, so these are semantic restatements -- the parts that bottom out in the *installed* sklearn
+(PCA, brute-force kNN) call that code directly and are therefore exact).
+"""
+
+import numpy as np
+import scipy.sparse as sp_sparse
+
+from . import louvain_ref
+
+
+class AnnDataLite:
+    """Minimal stand-in for ``anndata.AnnData`` as used at doubletdetection.py:300-301,343."""
+
+    def __init__(self, X):
+        self.X = X
+        self.obs = {}
+        self.obsm = {}
+        self.obsp = {}
+        self.uns = {}
+
+    @property
+    def shape(self):
+        return self.X.shape
+
+    @property
+    def n_obs(self):
+        return self.X.shape[0]
+
+    @property
+    def n_vars(self):
+        return self.X.shape[1]
+
+
+def pp_scale(X, max_value=None):
+    """``sc.pp.scale(adata, max_value=15)`` -- doubletdetection.py:302-303; SURVEY Appendix B4.
+
+    Per-gene mean and variance accumulated in float64 (var = E[x^2]-E[x]^2, times n/(n-1)),
+    std==0 -> 1, in-place centre and divide on the float32 array, clip to [-max, max]
+    (scanpy >= 1.10 with zero_center=True).
+    """
+    X = np.asarray(X)
+    n = X.shape[0]
+    mean = np.mean(X, axis=0, dtype=np.float64)
+    mean_sq = np.multiply(X, X).mean(axis=0, dtype=np.float64)  # squares in X's own dtype
+    var = (mean_sq - mean**2) * (n / (n - 1))
+    std = np.sqrt(var)
+    std[std == 0] = 1
+    X = X.copy()
+    # in-place ops with float64 operands: computed in float64, rounded once into X's dtype
+    np.subtract(X, mean, out=X, casting="same_kind")
+    np.divide(X, std, out=X, casting="same_kind")
+    if max_value is not None:
+        np.clip(X, -max_value, max_value, out=X)
+    return X, mean, std
+
+
+def tl_pca(X, n_comps, random_state=0, svd_solver="auto"):
+    """``sc.tl.pca(adata, n_comps, random_state, svd_solver)`` dense path --
+    doubletdetection.py:308-314; SURVEY Appendix B5.  scanpy calls
+    ``sklearn.decomposition.PCA(n_components, svd_solver, random_state).fit_transform(X)`` and
+    casts to float32; sklearn is installed, so this is the real code.
+    """
+    from sklearn.decomposition import PCA
+
+    if sp_sparse.issparse(X):
+        pca = PCA(n_components=n_comps, svd_solver="arpack", random_state=random_state)
+    else:
+        pca = PCA(n_components=n_comps, svd_solver=svd_solver, random_state=random_state)
+    emb = pca.fit_transform(X)
+    return np.ascontiguousarray(emb, dtype=np.float32), pca
+
+
+def knn_brute(rep, n_neighbors=10):
+    """Exact kNN as scanpy does it below 8192 observations:
+    ``KNeighborsTransformer(algorithm="brute", metric="euclidean")``; the result has the point
+    itself in column 0 and ``n_neighbors - 1`` others.  Returns (indices int64, distances float32).
+    """
+    from sklearn.neighbors import KNeighborsTransformer
+
+    n = rep.shape[0]
+    k = min(n_neighbors, n)
+    tr = KNeighborsTransformer(algorithm="brute", metric="euclidean", n_neighbors=k - 1, mode="distance")
+    g = tr.fit_transform(rep)  # k explicit entries per row incl. self (distance 0)
+    g.sort_indices()
+    idx = np.empty((n, k), dtype=np.int64)
+    dist = np.empty((n, k), dtype=np.float64)
+    indptr, indices, data = g.indptr, g.indices, g.data
+    for i in range(n):
+        cols = indices[indptr[i] : indptr[i + 1]]
+        d = data[indptr[i] : indptr[i + 1]]
+        # self first, then ascending distance (ties by index, as a stable sort gives)
+        is_self = cols == i
+        key = np.lexsort((cols, d, ~is_self))
+        idx[i] = cols[key][:k]
+        dist[i] = d[key][:k]
+    return idx, dist.astype(np.float32)
+
+
+def smooth_knn_dist(distances, k, n_iter=64, local_connectivity=1.0, bandwidth=1.0):
+    """umap ``smooth_knn_dist`` restated; distances has self in column 0."""
+    SMOOTH_K_TOLERANCE = 1e-5
+    MIN_K_DIST_SCALE = 1e-3
+    n = distances.shape[0]
+    target = np.log2(k) * bandwidth
+    rho = np.zeros(n, dtype=np.float32)
+    sigma = np.zeros(n, dtype=np.float32)
+    mean_distances = np.mean(distances)
+    for i in range(n):
+        lo, hi, mid = 0.0, np.inf, 1.0
+        ith = distances[i]
+        non_zero = ith[ith > 0.0]
+        if non_zero.shape[0] >= local_connectivity:
+            index = int(np.floor(local_connectivity))
+            interpolation = local_connectivity - index
+            if index > 0:
+                rho[i] = non_zero[index - 1]
+                if interpolation > SMOOTH_K_TOLERANCE:
+                    rho[i] += interpolation * (non_zero[index] - non_zero[index - 1])
+            else:
+                rho[i] = interpolation * non_zero[0]
+        elif non_zero.shape[0] > 0:
+            rho[i] = np.max(non_zero)
+        for _ in range(n_iter):
+            psum = 0.0
+            for j in range(1, distances.shape[1]):
+                d = distances[i, j] - rho[i]
+                psum += np.exp(-(d / mid)) if d > 0 else 1.0
+            if abs(psum - target) < SMOOTH_K_TOLERANCE:
+                break
+            if psum > target:
+                hi = mid
+                mid = (lo + hi) / 2.0
+            else:
+                lo = mid
+                if hi == np.inf:
+                    mid *= 2
+                else:
+                    mid = (lo + hi) / 2.0
+        sigma[i] = mid
+        if rho[i] > 0.0:
+            mean_ith = np.mean(ith)
+            if sigma[i] < MIN_K_DIST_SCALE * mean_ith:
+                sigma[i] = MIN_K_DIST_SCALE * mean_ith
+        else:
+            if sigma[i] < MIN_K_DIST_SCALE * mean_distances:
+                sigma[i] = MIN_K_DIST_SCALE * mean_distances
+    return sigma, rho
+
+
+def fuzzy_connectivities(knn_idx, knn_dist):
+    """umap ``fuzzy_simplicial_set(set_op_mix_ratio=1, local_connectivity=1)`` restated:
+    membership strengths, then W + W^T - W o W^T, zeros eliminated."""
+    n, k = knn_idx.shape
+    d = knn_dist.astype(np.float32)
+    sigma, rho = smooth_knn_dist(d, float(k))
+    rows = np.repeat(np.arange(n), k)
+    cols = knn_idx.ravel()
+    vals = np.zeros(n * k, dtype=np.float32)
+    for i in range(n):
+        for j in range(k):
+            if knn_idx[i, j] == i:
+                v = 0.0
+            elif d[i, j] - rho[i] <= 0.0 or sigma[i] == 0.0:
+                v = 1.0
+            else:
+                v = np.exp(-((d[i, j] - rho[i]) / sigma[i]))
+            vals[i * k + j] = v
+    W = sp_sparse.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+    W.eliminate_zeros()
+    T = W.T.tocsr()
+    P = W.multiply(T)
+    C = (W + T - P).tocsr()
+    C.eliminate_zeros()
+    C.sort_indices()
+    return C
+
+
+def knn_pattern_graph(knn_idx):
+    """Symmetric 0/1 pattern of the connectivities graph: i~j iff j in kNN(i)\\{i} or i in
+    kNN(j)\\{j}.  This is all ``sc.tl.louvain`` sees because it ignores weights by default
+    (``use_weights=False``)."""
+    n, k = knn_idx.shape
+    rows = np.repeat(np.arange(n, dtype=np.int64), k)
+    cols = np.asarray(knn_idx, dtype=np.int64).ravel()
+    keep = rows != cols
+    rows, cols = rows[keep], cols[keep]
+    data = np.ones(rows.size, dtype=np.float32)
+    W = sp_sparse.coo_matrix((data, (rows, cols)), shape=(n, n)).tocsr()
+    S = (W + W.T).tocsr()
+    S.data[:] = 1.0
+    S.sort_indices()
+    return S
+
+
+def pp_neighbors(adata, random_state=0, method="umap", n_neighbors=10, with_weights=False):
+    """``sc.pp.neighbors(adata, random_state, method="umap", n_neighbors=10)`` --
+    doubletdetection.py:331-336.  Representation: ``X_pca`` when n_vars > 50, else X.
+    Exact brute-force kNN is used at every size (upstream switches to approximate NN-descent at
+    >= 8192 observations; the oracle defines the reference there through the exact kNN).
+    """
+    if adata.n_vars > 50 and "X_pca" in adata.obsm:
+        rep = adata.obsm["X_pca"]
+    else:
+        rep = adata.X
+    rep = np.asarray(rep)
+    idx, dist = knn_brute(rep, n_neighbors)
+    adata.uns["knn_indices"] = idx
+    adata.uns["knn_distances"] = dist
+    if with_weights:
+        adata.obsp["connectivities"] = fuzzy_connectivities(idx, dist)
+    else:
+        adata.obsp["connectivities"] = knn_pattern_graph(idx)
+    return adata
+
+
+def tl_louvain(adata, key_added="clusters", random_state=0, directed=False, resolution=4, louvain_fn=None, **_):
+    """``sc.tl.louvain(adata, key_added="clusters", random_state, directed=False, resolution=4)``
+    -- doubletdetection.py:337-342; SURVEY Appendix B2.  Unweighted graph from
+    ``connectivities.nonzero()``; partition by the in-repo deterministic Louvain
+    (``louvain_ref``; PARITY UNPINNED, the louvain package is absent); labels by decreasing size,
+    stored as strings like scanpy's categorical."""
+    C = adata.obsp["connectivities"].tocsr()
+    C.sort_indices()
+    fn = louvain_fn or louvain_ref.louvain
+    labels = fn(C.indptr, C.indices, None, resolution=float(resolution), seed=int(random_state))
+    adata.obs[key_added] = np.asarray([str(int(x)) for x in labels])
+    return adata
