@@ -1,0 +1,341 @@
+"""ctypes binding of ``libdd_b200.so`` (C ABI declared in ``include/dd_b200.h``).
+
+There is no CPU fallback: importing this module without the built library raises ``ImportError``
+and creating a :class:`Handle` without a B200 raises ``RuntimeError`` -- the product path never
+routes around the CUDA extension.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
+
+DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
+ABI_VERSION = 1
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class FitParams(ctypes.Structure):
+    """``dd_fit_params`` of include/dd_b200.h."""
+
+    _fields_ = [
+        ("n_iters", ctypes.c_int32),
+        ("n_synth", ctypes.c_int64),
+        ("pseudocount", ctypes.c_float),
+        ("standard_scaling", ctypes.c_int32),
+        ("scale_max_value", ctypes.c_float),
+        ("n_comp", ctypes.c_int32),
+        ("n_random", ctypes.c_int32),
+        ("n_power_iter", ctypes.c_int32),
+        ("knn_k", ctypes.c_int32),
+        ("resolution", ctypes.c_double),
+        ("seed", ctypes.c_uint64),
+        ("n_host_threads", ctypes.c_int32),
+        ("iter_begin", ctypes.c_int32),
+        ("iter_end", ctypes.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/dd_b200.h declares
+SIGNATURES = {
+    "dd_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "dd_destroy": (None, [ctypes.c_void_p]),
+    "dd_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "dd_abi_version": (ctypes.c_int, []),
+    "dd_upload_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_i32p, c_i32p, c_f32p]),
+    "dd_get_lib_size": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
+    "dd_create_doublets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i64p]),
+    "dd_synth_nnz": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
+    "dd_download_synthetics": (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_f32p]),
+    "dd_get_synth_lib_size": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
+    "dd_median_lib_size": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
+    "dd_normalise_log": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float]),
+    "dd_standard_scale": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float]),
+    "dd_download_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_f32p]),
+    "dd_upload_dense": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_f32p]),
+    "dd_pca": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, c_f64p],
+    ),
+    "dd_upload_embedding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p]),
+    "dd_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_f32p]),
+    "dd_louvain_knn": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int32, c_i32p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
+    "dd_louvain_csr": (
+        ctypes.c_int,
+        [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
+    "dd_score": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, c_i32p, c_f64p, c_f64p]),
+    "dd_hypergeom_logsf": (ctypes.c_double, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]),
+    "dd_fit_iterations": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.POINTER(FitParams), c_i64p, c_f32p, c_f64p, c_f64p, c_i32p, c_i32p, c_f64p],
+    ),
+    "dd_kernel_launches": (ctypes.c_int64, [ctypes.c_void_p]),
+    "dd_last_stage_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_char_p]),
+    "dd_set_kernel_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "dd_get_kernel_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, c_f64p, c_i64p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C doubletdetection_b200/csrc`). doubletdetection_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.dd_abi_version() != ABI_VERSION:
+        raise ImportError(f"libdd_b200.so ABI {lib.dd_abi_version()} != binding ABI {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libdd_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _raise(lib, h, rc):
+    msg = lib.dd_last_error(h)
+    msg = msg.decode("utf-8", "replace") if msg else ""
+    if rc == DD_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"libdd_b200: {msg}")
+    if rc == DD_ERR_ARG:
+        raise ValueError(f"libdd_b200: {msg}")
+    if rc == DD_ERR_NOMEM:
+        raise MemoryError(f"libdd_b200: {msg}")
+    raise NativeError(rc, msg)
+
+
+# ---- handle-free host entry points --------------------------------------------------------------
+def louvain_knn(knn_idx, resolution=4.0, seed=0):
+    lib = load()
+    knn_idx = np.ascontiguousarray(knn_idx, dtype=np.int32)
+    n, k = knn_idx.shape
+    labels = np.empty(n, dtype=np.int32)
+    ncomm = ctypes.c_int32(0)
+    rc = lib.dd_louvain_knn(n, k, _ptr(knn_idx, ctypes.c_int32), float(resolution), int(seed) & (2**64 - 1),
+                            _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return labels
+
+
+def louvain_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
+    lib = load()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    n = indptr.size - 1
+    labels = np.empty(max(n, 1), dtype=np.int32)
+    ncomm = ctypes.c_int32(0)
+    rc = lib.dd_louvain_csr(n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64), _ptr(w, ctypes.c_double),
+                            float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return labels[:n]
+
+
+def score(labels, n_cells):
+    lib = load()
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    n_synth = labels.size - n_cells
+    scores = np.empty(n_cells, dtype=np.float64)
+    logp = np.empty(n_cells, dtype=np.float64)
+    rc = lib.dd_score(n_cells, n_synth, _ptr(labels, ctypes.c_int32), _ptr(scores, ctypes.c_double),
+                      _ptr(logp, ctypes.c_double))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return scores, logp
+
+
+def hypergeom_logsf(k, M, n, N):
+    return load().dd_hypergeom_logsf(int(k), int(M), int(n), int(N))
+
+
+# ---- device handle ------------------------------------------------------------------------------
+class Handle:
+    """One ``dd_handle``: a CUDA device, its stream and the resident matrices of one fit."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        self._h = ctypes.c_void_p()
+        rc = self._lib.dd_create(int(device), ctypes.byref(self._h))
+        if rc != DD_OK:
+            msg = self._lib.dd_last_error(None)
+            raise RuntimeError(
+                "libdd_b200: " + (msg.decode("utf-8", "replace") if msg else f"dd_create failed ({rc})")
+            )
+        self.device = int(device)
+        self.n_cells = self.n_genes = self.n_synth = 0
+        self._dense_rows = self._emb_rows = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dd_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != DD_OK:
+            _raise(self._lib, self._h, rc)
+
+    # fit prologue
+    def upload_counts(self, csr):
+        indptr = np.ascontiguousarray(csr.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        data = _f32(csr.data)
+        self.n_cells, self.n_genes = csr.shape
+        self._check(self._lib.dd_upload_counts(self._h, self.n_cells, self.n_genes, _ptr(indptr, ctypes.c_int32),
+                                               _ptr(indices, ctypes.c_int32), _ptr(data, ctypes.c_float)))
+
+    def lib_size(self):
+        out = np.empty(self.n_cells, dtype=np.float32)
+        self._check(self._lib.dd_get_lib_size(self._h, _ptr(out, ctypes.c_float)))
+        return out
+
+    # _createDoublets
+    def create_doublets(self, parents):
+        parents = np.ascontiguousarray(parents, dtype=np.int64).reshape(-1, 2)
+        self.n_synth = parents.shape[0]
+        self._check(self._lib.dd_create_doublets(self._h, self.n_synth, _ptr(parents, ctypes.c_int64)))
+
+    def download_synthetics(self):
+        import scipy.sparse as sp_sparse
+
+        nnz = ctypes.c_int64(0)
+        self._check(self._lib.dd_synth_nnz(self._h, ctypes.byref(nnz)))
+        indptr = np.empty(self.n_synth + 1, dtype=np.int32)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.float32)
+        self._check(self._lib.dd_download_synthetics(self._h, _ptr(indptr, ctypes.c_int32), _ptr(indices, ctypes.c_int32),
+                                                     _ptr(data, ctypes.c_float)))
+        return sp_sparse.csr_matrix((data, indices, indptr), shape=(self.n_synth, self.n_genes))
+
+    def synth_lib_size(self):
+        out = np.empty(self.n_synth, dtype=np.float32)
+        self._check(self._lib.dd_get_synth_lib_size(self._h, _ptr(out, ctypes.c_float)))
+        return out
+
+    def median_lib_size(self):
+        out = ctypes.c_float(0)
+        self._check(self._lib.dd_median_lib_size(self._h, ctypes.byref(out)))
+        return np.float32(out.value)
+
+    # normalise
+    def normalise_log(self, median, pseudocount):
+        self._check(self._lib.dd_normalise_log(self._h, float(median), float(pseudocount)))
+        self._dense_rows = self.n_cells + self.n_synth
+
+    def standard_scale(self, max_value=15.0):
+        self._check(self._lib.dd_standard_scale(self._h, float(max_value)))
+
+    def download_dense(self, row0=0, n_rows=None):
+        if n_rows is None:
+            n_rows = self.n_cells + self.n_synth - row0
+        out = np.empty((n_rows, self.n_genes), dtype=np.float32)
+        self._check(self._lib.dd_download_dense(self._h, row0, n_rows, _ptr(out, ctypes.c_float)))
+        return out
+
+    def upload_dense(self, dense):
+        dense = _f32(dense)
+        if self.n_cells == 0:
+            self.n_cells, self.n_genes = dense.shape
+            self.n_synth = 0
+        self._check(self._lib.dd_upload_dense(self._h, dense.shape[0], dense.shape[1], _ptr(dense, ctypes.c_float)))
+        self._dense_rows = dense.shape[0]
+
+    # pca / knn
+    def pca(self, n_comp, omega, n_power_iter, n_rows=None):
+        omega = _f32(omega)
+        n_rows = n_rows or self._dense_rows
+        emb = np.empty((n_rows, n_comp), dtype=np.float32)
+        sv = np.empty(n_comp, dtype=np.float64)
+        self._check(self._lib.dd_pca(self._h, n_comp, omega.shape[1], n_power_iter, _ptr(omega, ctypes.c_float),
+                                     _ptr(emb, ctypes.c_float), _ptr(sv, ctypes.c_double)))
+        self._emb_rows = n_rows
+        return emb, sv
+
+    def upload_embedding(self, emb):
+        emb = _f32(emb)
+        self._check(self._lib.dd_upload_embedding(self._h, emb.shape[0], emb.shape[1], _ptr(emb, ctypes.c_float)))
+        self._emb_rows = emb.shape[0]
+
+    def knn(self, k=10, with_dist=True):
+        n = self._emb_rows
+        idx = np.empty((n, k), dtype=np.int32)
+        dist = np.empty((n, k), dtype=np.float32) if with_dist else None
+        self._check(self._lib.dd_knn(self._h, k, _ptr(idx, ctypes.c_int32), _ptr(dist, ctypes.c_float)))
+        return idx, dist
+
+    # the loop
+    def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10,
+                       resolution=4.0, seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0):
+        parents = np.ascontiguousarray(parents, dtype=np.int64)
+        n_iters, n_synth = parents.shape[0], parents.shape[1]
+        omega = _f32(omega)
+        iter_end = n_iters if iter_end is None else iter_end
+        p = FitParams(n_iters, n_synth, float(pseudocount), int(bool(standard_scaling)), float(scale_max_value),
+                      int(n_comp), int(omega.shape[1]), int(n_power_iter), int(knn_k), float(resolution),
+                      int(seed) & (2**64 - 1), int(n_host_threads), int(iter_begin), int(iter_end))
+        N = self.n_cells
+        scores = np.zeros((n_iters, N), dtype=np.float64)
+        logp = np.zeros((n_iters, N), dtype=np.float64)
+        comm = np.zeros((n_iters, N), dtype=np.int32)
+        synth_comm = np.zeros((n_iters, max(n_synth, 1)), dtype=np.int32)
+        stage_ms = np.zeros(8, dtype=np.float64)
+        self._check(self._lib.dd_fit_iterations(
+            self._h, ctypes.byref(p), _ptr(parents, ctypes.c_int64), _ptr(omega, ctypes.c_float),
+            _ptr(scores, ctypes.c_double), _ptr(logp, ctypes.c_double), _ptr(comm, ctypes.c_int32),
+            _ptr(synth_comm, ctypes.c_int32), _ptr(stage_ms, ctypes.c_double)))
+        self.n_synth = n_synth
+        names = ["doublets", "normalise", "scale", "pca", "knn", "d2h", "device_total", "_"]
+        return dict(scores=scores, log_p=logp, communities=comm, synth_communities=synth_comm[:, :n_synth],
+                    stage_ms=dict(zip(names, stage_ms.tolist())))
+
+    # introspection
+    def kernel_launches(self):
+        return int(self._lib.dd_kernel_launches(self._h))
+
+    def last_stage_ms(self, stage):
+        return float(self._lib.dd_last_stage_ms(self._h, stage.encode()))
+
+    def set_kernel_timing(self, on):
+        self._check(self._lib.dd_set_kernel_timing(self._h, int(bool(on))))
+
+    def kernel_timing(self, kernel):
+        ms = ctypes.c_double(0)
+        n = ctypes.c_int64(0)
+        self._check(self._lib.dd_get_kernel_timing(self._h, kernel.encode(), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value

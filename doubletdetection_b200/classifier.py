@@ -1,0 +1,314 @@
+"""``BoostClassifier`` -- drop-in for ``doubletdetection.BoostClassifier``
+(reference: doubletdetection/doubletdetection.py:22-426) whose per-iteration fit loop runs on a B200
+through ``libdd_b200.so``.
+
+Same constructor arguments, defaults, warnings and errors (:73-133, :404-426), same ``fit`` /
+``predict`` / ``doublet_score`` semantics (:135-272) and the same fitted attributes.  What changes is
+where ``_one_fit`` (:274-383) executes: synthetic doublets, normalise/log, optional scaling,
+randomized PCA and the exact kNN graph are CUDA kernels, clustering (Louvain) and scoring are native
+host code overlapped with the GPU.  There is no CPU fallback: without the built library or without a
+B200 ``fit`` raises.
+
+Keyword-only extensions (not in the reference): ``device`` (CUDA device index; default
+``LOCAL_RANK`` or 0) and ``distributed`` (shard the independent iterations over the ranks of an
+initialised ``torch.distributed`` group and all-gather the per-iteration results).
+"""
+
+import os
+import warnings
+
+import numpy as np
+import scipy.sparse as sp_sparse
+from scipy.sparse import csr_matrix
+from sklearn.utils import check_array
+
+from . import _capi
+
+
+def _pca_solver(n_samples, n_features, n_components):
+    """sklearn ``PCA(svd_solver="auto")`` dispatch (sklearn/decomposition/_pca.py:524-536), which is what
+    ``sc.tl.pca(..., svd_solver="auto")`` (doubletdetection.py:308-314) ends up in."""
+    if n_features <= 1000 and n_samples >= 10 * n_features:
+        return "covariance_eigh"
+    if max(n_samples, n_features) <= 500:
+        return "full"
+    if 1 <= n_components < 0.8 * min(n_samples, n_features):
+        return "randomized"
+    return "full"
+
+
+def _pca_plan(n_samples, n_features, n_components, random_state):
+    """Test matrix and power-iteration count of sklearn's randomized SVD
+    (sklearn/utils/extmath.py:323-333, 584-587): Omega = RandomState(seed).normal((G, C + 10)) cast to
+    float32, 7 iterations when C < 0.1 * min(shape) else 4."""
+    solver = _pca_solver(n_samples, n_features, n_components)
+    if solver != "randomized":
+        raise NotImplementedError(
+            f"sklearn's PCA(svd_solver='auto') picks '{solver}' for a {n_samples} x {n_features} matrix with "
+            f"n_components={n_components}; only the 'randomized' branch is implemented on the B200 hot path"
+        )
+    if n_samples < n_features:
+        raise NotImplementedError(
+            "fewer augmented cells than genes: sklearn's randomized SVD transposes the problem; that branch "
+            "is not implemented on the B200 hot path (lower n_top_var_genes)"
+        )
+    n_power_iter = 7 if n_components < 0.1 * min(n_samples, n_features) else 4
+    omega = np.random.RandomState(random_state).normal(size=(n_features, n_components + 10)).astype(np.float32)
+    return omega, n_power_iter
+
+
+class BoostClassifier:
+    """Classifier for doublets in single-cell RNA-seq data (see the reference docstring,
+    doubletdetection.py:23-71, for parameters and attributes -- they are identical)."""
+
+    def __init__(
+        self,
+        boost_rate=0.25,
+        n_components=30,
+        n_top_var_genes=10000,
+        replace=False,
+        clustering_algorithm="phenograph",
+        clustering_kwargs=None,
+        n_iters=10,
+        normalizer=None,
+        pseudocount=0.1,
+        random_state=0,
+        verbose=False,
+        standard_scaling=False,
+        n_jobs=1,
+        *,
+        device=None,
+        distributed=False,
+    ):
+        self.boost_rate = boost_rate
+        self.replace = replace
+        self.clustering_algorithm = clustering_algorithm
+        self.n_iters = n_iters
+        self.normalizer = normalizer
+        self.random_state = random_state
+        self.verbose = verbose
+        self.standard_scaling = standard_scaling
+        self.n_jobs = n_jobs
+        self.pseudocount = pseudocount
+        self.rng = np.random.default_rng(self.random_state)  # :99 -- one stream for all fits
+        self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
+        self.distributed = bool(distributed)
+
+        if self.clustering_algorithm not in ["louvain", "phenograph", "leiden"]:  # :101-104
+            raise ValueError("Clustering algorithm needs to be one of ['louvain', 'phenograph', 'leiden']")
+        if self.clustering_algorithm == "leiden":  # :105-106
+            warnings.warn("Leiden clustering is experimental and results have not been validated.")
+
+        if n_components == 30 and n_top_var_genes > 0:  # :108-112
+            self.n_components = min(n_components, n_top_var_genes)
+        else:
+            self.n_components = n_components
+        self.n_top_var_genes = max(0, n_top_var_genes)  # :114
+
+        self.clustering_kwargs = {} if not isinstance(clustering_kwargs, dict) else clustering_kwargs
+        self._set_clustering_kwargs()
+
+        if not self.replace and self.boost_rate > 0.5:  # :121-127
+            warnings.warn(
+                "boost_rate is trimmed to 0.5 when replace=False. Set replace=True to use greater boost rates."
+            )
+            self.boost_rate = 0.5
+
+        assert (self.n_top_var_genes == 0) or (
+            self.n_components <= self.n_top_var_genes
+        ), "n_components={0} cannot be larger than n_top_var_genes={1}".format(n_components, n_top_var_genes)
+
+        self._handle = None
+        self._parents_array = None
+        self._parents_lists = None
+        self.stage_ms_ = None
+
+    # ------------------------------------------------------------------ kwargs (:404-426)
+    def _set_clustering_kwargs(self):
+        if self.clustering_algorithm == "phenograph":
+            if "prune" not in self.clustering_kwargs:
+                self.clustering_kwargs["prune"] = True
+            if (self.n_iters == 1) and (self.clustering_kwargs.get("prune") is True):
+                warnings.warn(
+                    "Using phenograph parameter prune=False is strongly recommended when "
+                    "running only one iteration. Otherwise, expect many NaN labels."
+                )
+        else:
+            if "directed" not in self.clustering_kwargs:
+                self.clustering_kwargs["directed"] = False
+            if "resolution" not in self.clustering_kwargs:
+                self.clustering_kwargs["resolution"] = 4
+            if "key_added" in self.clustering_kwargs:
+                raise ValueError("'key_added' param cannot be overriden")
+            if "random_state" in self.clustering_kwargs:
+                raise ValueError("'random_state' param cannot be overriden. Please use classifier 'random_state'.")
+
+    # ------------------------------------------------------------------ parents_ (:395, :197)
+    @property
+    def parents_(self):
+        """List (per iteration) of lists of ``[parent0, parent1]`` -- the reference's structure,
+        materialised on first access from the int64 array the fit kept."""
+        if self._parents_lists is None and self._parents_array is not None:
+            self._parents_lists = [[list(p) for p in it] for it in self._parents_array]
+        if self._parents_lists is None:
+            raise AttributeError("parents_ is set by fit()")
+        return self._parents_lists
+
+    @parents_.setter
+    def parents_(self, value):
+        self._parents_lists = value
+
+    # ------------------------------------------------------------------ fit (:135-214)
+    def _native(self):
+        if self._handle is None:
+            self._handle = _capi.Handle(self.device)
+        return self._handle
+
+    def _host_threads(self):
+        n = int(self.n_jobs) if self.n_jobs else 1
+        if n < 0:
+            n = max(1, (os.cpu_count() or 1) + 1 + n)  # joblib convention: -1 = all cores
+        return max(1, n)
+
+    def fit(self, raw_counts):
+        """Fits the classifier on raw_counts (cells x genes, dense or CSR)."""
+        if self.normalizer is not None:
+            # the reference itself raises NameError on this path in this version (:288-291 vs :301, :372)
+            raise NotImplementedError("custom `normalizer` is not supported (and is broken in the reference at this version)")
+        if self.clustering_algorithm != "louvain":
+            raise NotImplementedError(
+                f"clustering_algorithm='{self.clustering_algorithm}' needs the phenograph / leidenalg packages; "
+                "the B200 hot path clusters with Louvain (clustering_algorithm='louvain')"
+            )
+        if self.clustering_kwargs.get("directed", False):
+            raise NotImplementedError("clustering_kwargs['directed']=True is not supported (the reference default is False)")
+        extra = set(self.clustering_kwargs) - {"directed", "resolution"}
+        if extra:
+            raise NotImplementedError(f"unsupported clustering_kwargs for the native Louvain: {sorted(extra)}")
+        if self.pseudocount == 1:
+            raise NotImplementedError("pseudocount=1 selects the sparse log1p + arpack path (:296-297, :308), which is not on the B200 hot path")
+
+        raw_counts = check_array(  # :149-155
+            raw_counts, accept_sparse="csr", ensure_all_finite=True, ensure_2d=True, dtype="float32"
+        )
+        if sp_sparse.issparse(raw_counts) is not True:  # :157-160
+            if self.verbose:
+                print("Sparsifying matrix.")
+            raw_counts = csr_matrix(raw_counts)
+
+        if self.n_top_var_genes > 0 and self.n_top_var_genes < raw_counts.shape[1]:  # :165-176
+            gene_variances = (
+                np.array(raw_counts.power(2).mean(axis=0)) - (np.array(raw_counts.mean(axis=0))) ** 2
+            )[0]
+            top_var_indexes = np.argsort(gene_variances)
+            self.top_var_genes_ = top_var_indexes[-self.n_top_var_genes:]
+            raw_counts = raw_counts.tocsc()[:, self.top_var_genes_].tocsr()
+        if not raw_counts.has_canonical_format:  # the kernels merge sorted, duplicate-free rows
+            raw_counts = raw_counts.copy()
+            raw_counts.sum_duplicates()
+
+        num_cells, num_genes = raw_counts.shape
+        self._num_cells, self._num_genes = num_cells, num_genes
+        num_synths = int(self.boost_rate * num_cells)  # :391
+        n_aug = num_cells + num_synths
+        omega, n_power_iter = _pca_plan(n_aug, num_genes, self.n_components, self.random_state)
+
+        # every iteration's `choices` (:394), drawn sequentially from the classifier's stream
+        parents = np.empty((self.n_iters, num_synths, 2), dtype=np.int64)
+        for i in range(self.n_iters):
+            parents[i] = self.rng.choice(num_cells, size=(num_synths, 2), replace=self.replace)
+
+        h = self._native()
+        h.upload_counts(raw_counts)
+
+        it0, it1 = 0, self.n_iters
+        dist = None
+        if self.distributed:
+            import torch.distributed as dist_mod
+
+            if dist_mod.is_available() and dist_mod.is_initialized() and dist_mod.get_world_size() > 1:
+                dist = dist_mod
+                rank, world = dist.get_rank(), dist.get_world_size()
+                it0 = (self.n_iters * rank) // world
+                it1 = (self.n_iters * (rank + 1)) // world
+
+        if self.verbose:
+            print(f"Running iterations {it0 + 1}..{it1} of {self.n_iters} on cuda:{self.device}")
+        out = h.fit_iterations(
+            parents, omega,
+            pseudocount=self.pseudocount, standard_scaling=self.standard_scaling is True,
+            n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10,
+            resolution=float(self.clustering_kwargs["resolution"]), seed=int(self.random_state),
+            n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1,
+        )
+        if dist is not None:
+            out = _allgather_iterations(dist, out, self.n_iters, self.device)
+        self.stage_ms_ = out["stage_ms"]
+
+        self.all_scores_ = out["scores"]
+        self.all_log_p_values_ = out["log_p"]
+        self.communities_ = out["communities"].astype(np.float64)  # the reference stores them in float arrays (:188)
+        self.synth_communities_ = out["synth_communities"].astype(np.float64)
+        self._parents_array = parents
+        self._parents_lists = None
+        return self
+
+    # ------------------------------------------------------------------ predict (:216-254)
+    def predict(self, p_thresh=1e-7, voter_thresh=0.9):
+        log_p_thresh = np.log(p_thresh)
+        if self.n_iters > 1:
+            with np.errstate(invalid="ignore"):
+                self.voting_average_ = np.mean(
+                    np.ma.masked_invalid(self.all_log_p_values_) <= log_p_thresh, axis=0
+                )
+                self.labels_ = np.ma.filled((self.voting_average_ >= voter_thresh).astype(float), np.nan)
+                self.voting_average_ = np.ma.filled(self.voting_average_, np.nan)
+        else:
+            potential_cutoffs = np.unique(self.all_scores_[~np.isnan(self.all_scores_)])
+            if len(potential_cutoffs) > 1:
+                max_dropoff = np.argmax(potential_cutoffs[1:] - potential_cutoffs[:-1]) + 1
+            else:
+                max_dropoff = 0
+            self.suggested_score_cutoff_ = potential_cutoffs[max_dropoff]
+            with np.errstate(invalid="ignore"):
+                self.labels_ = self.all_scores_[0, :] >= self.suggested_score_cutoff_
+            self.labels_[np.isnan(self.all_scores_)[0, :]] = np.nan
+        return self.labels_
+
+    # ------------------------------------------------------------------ doublet_score (:256-272)
+    def doublet_score(self):
+        if self.n_iters > 1:
+            with np.errstate(invalid="ignore"):
+                avg_log_p = np.mean(np.ma.masked_invalid(self.all_log_p_values_), axis=0)
+        else:
+            avg_log_p = self.all_log_p_values_[0]
+        return -avg_log_p
+
+
+def iteration_shard(n_iters, rank, world):
+    """Contiguous block of iterations owned by ``rank`` (BASELINE config 4: 24 iterations over 8 GPUs)."""
+    return (n_iters * rank) // world, (n_iters * (rank + 1)) // world
+
+
+def _allgather_iterations(dist, out, n_iters, device):
+    """Every rank filled only its own rows of the (n_iters, .) result arrays (the rest are zero); a sum
+    all-reduce assembles them.  No data-path collective is involved -- this is result collection."""
+    import torch
+
+    backend = dist.get_backend()
+    dev = torch.device("cuda", device) if backend == "nccl" else torch.device("cpu")
+    merged = {}
+    for key in ("scores", "log_p", "communities", "synth_communities"):
+        a = out[key]
+        if key in ("scores", "log_p"):
+            # NaN / -inf entries do not survive a sum; ship them as bit patterns instead
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy()).to(dev)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a).astype(np.int64)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r = t.cpu().numpy()
+        merged[key] = r.view(np.float64) if key in ("scores", "log_p") else r.astype(np.int32)
+    stage = torch.tensor([out["stage_ms"][k] for k in sorted(out["stage_ms"])], dtype=torch.float64, device=dev)
+    dist.all_reduce(stage, op=dist.ReduceOp.MAX)
+    merged["stage_ms"] = dict(zip(sorted(out["stage_ms"]), stage.cpu().tolist()))
+    return merged

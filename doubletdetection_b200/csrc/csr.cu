@@ -1,0 +1,492 @@
+// csr.cu -- the sparse half of _one_fit: library sizes, _createDoublets (CSR row-pair add) and the
+// fused "pair-add + L1 normalise + x median + log(x + pseudocount) -> dense" build.
+//
+// Reference lines (doubletdetection/doubletdetection.py):
+//   :182-184  _lib_size, memoised L1-normalised originals      -> k_row_sums
+//   :397-399  raw[parents[:,0]] + raw[parents[:,1]]             -> k_synth_count / k_synth_fill
+//   :288-295  synth lib sizes, L1 normalise, vstack, x median, log(. + pc) dense
+//                                                                -> k_dense_rows (originals and synthetics)
+// All kernels are HBM-bound byte movers: one warp owns one row, stages it in a per-warp shared-memory
+// row buffer (scatter in, 128-bit coalesced streaming stores out) and the grid is a multiple of the
+// SM count with warps striding over rows.
+#include "dd_internal.h"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxChunk = 8192;  // columns staged per pass: 32 KB per warp
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// _lib_size (float32 row sums, :182) and the double-precision sum of |x| that sklearn's
+// inplace_csr_row_normalize_l1 divides by (:184).  Integer-valued counts make both exact in any
+// summation order.
+__global__ void k_row_sums(const int32_t *__restrict__ indptr, const float *__restrict__ data, int64_t n_rows,
+                           float *__restrict__ lib, double *__restrict__ l1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const int s = indptr[row], e = indptr[row + 1];
+        float acc = 0.f;
+        double acc1 = 0.0;
+        for (int p = s + lane; p < e; p += 32) {
+            const float v = __ldg(data + p);
+            acc += v;
+            acc1 += fabs((double)v);
+        }
+        acc = warp_sum_f(acc);
+        acc1 = warp_sum_d(acc1);
+        if (lane == 0) {
+            lib[row] = acc;
+            l1[row] = acc1;
+        }
+    }
+}
+
+// Stage columns [c0, c0+cw) of (row a + row b) into buf.  buf is per-warp shared memory.
+__device__ __forceinline__ void stage_pair_sum(float *buf, int c0, int cw, const int32_t *__restrict__ indices,
+                                               const float *__restrict__ data, int sa, int ea, int sb, int eb,
+                                               int lane) {
+    for (int j = lane; j < cw; j += 32) buf[j] = 0.f;
+    __syncwarp();
+    for (int p = sa + lane; p < ea; p += 32) {
+        const int c = __ldg(indices + p) - c0;
+        if ((unsigned)c < (unsigned)cw) buf[c] = __ldg(data + p);
+    }
+    __syncwarp();
+    for (int p = sb + lane; p < eb; p += 32) {
+        const int c = __ldg(indices + p) - c0;
+        if ((unsigned)c < (unsigned)cw) buf[c] += __ldg(data + p);  // columns are unique within a row
+    }
+    __syncwarp();
+}
+
+// Pass 1 of _createDoublets: nnz of every synthetic row (entries whose sum is non-zero, exactly the
+// entries scipy's canonical csr_plus_csr keeps) and its float32 library size (:288).
+__global__ void k_synth_count(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                              const float *__restrict__ data, const int64_t *__restrict__ parents,
+                              int64_t n_synth, int n_genes, int chunk, int32_t *__restrict__ count,
+                              float *__restrict__ slib) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *buf = smem + (size_t)w * chunk;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + w;
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t r = warp; r < n_synth; r += n_warps) {
+        const int64_t pa = parents[2 * r], pb = parents[2 * r + 1];
+        const int sa = indptr[pa], ea = indptr[pa + 1], sb = indptr[pb], eb = indptr[pb + 1];
+        int cnt = 0;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < n_genes; c0 += chunk) {
+            const int cw = min(chunk, n_genes - c0);
+            stage_pair_sum(buf, c0, cw, indices, data, sa, ea, sb, eb, lane);
+            for (int j = lane; j < cw; j += 32) {
+                const float v = buf[j];
+                cnt += (v != 0.f);
+                sum += v;
+            }
+            __syncwarp();
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        sum = warp_sum_f(sum);
+        if (lane == 0) {
+            count[r] = cnt;
+            slib[r] = sum;
+        }
+    }
+}
+
+// Exclusive scan of count[0..n) into indptr[0..n]; single CTA (n is a few 10^5 at most).
+__global__ void k_exclusive_scan(const int32_t *__restrict__ count, int64_t n, int32_t *__restrict__ indptr) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int64_t per = (n + nt - 1) / nt;
+    const int64_t b = min((int64_t)t * per, n), e = min(b + per, n);
+    long long s = 0;
+    for (int64_t i = b; i < e; i++) s += count[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        long long run = 0;
+        for (int i = 0; i < nt; i++) {
+            const long long v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        indptr[n] = (int32_t)run;
+    }
+    __syncthreads();
+    long long run = part[t];
+    for (int64_t i = b; i < e; i++) {
+        indptr[i] = (int32_t)run;
+        run += count[i];
+    }
+}
+
+// Pass 2 of _createDoublets: write the merged rows in column order (canonical CSR).
+__global__ void k_synth_fill(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                             const float *__restrict__ data, const int64_t *__restrict__ parents,
+                             int64_t n_synth, int n_genes, int chunk, const int32_t *__restrict__ sindptr,
+                             int32_t *__restrict__ sindices, float *__restrict__ sdata) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *buf = smem + (size_t)w * chunk;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + w;
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int64_t r = warp; r < n_synth; r += n_warps) {
+        const int64_t pa = parents[2 * r], pb = parents[2 * r + 1];
+        const int sa = indptr[pa], ea = indptr[pa + 1], sb = indptr[pb], eb = indptr[pb + 1];
+        int out = sindptr[r];
+        for (int c0 = 0; c0 < n_genes; c0 += chunk) {
+            const int cw = min(chunk, n_genes - c0);
+            stage_pair_sum(buf, c0, cw, indices, data, sa, ea, sb, eb, lane);
+            for (int base = 0; base < cw; base += 32) {
+                const int j = base + lane;
+                const float v = j < cw ? buf[j] : 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+                if (v != 0.f) {
+                    const int pos = out + __popc(m & lt_mask);
+                    sindices[pos] = c0 + j;
+                    sdata[pos] = v;
+                }
+                out += __popc(m);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// log( (x / l1) * median + pc ) with the reference's float32 rounding after every step:
+//   sklearn divides in double and stores float32 (sparsefuncs_fast.pyx:516-545), scipy multiplies the
+//   float32 data by the float32 median (:293), numpy adds the pseudocount and takes the float32 log (:295).
+__device__ __forceinline__ float norm_log(float x, double l1, float median, float pc) {
+    const float normed = l1 != 0.0 ? (float)((double)x / l1) : x;
+    return logf(__fadd_rn(__fmul_rn(normed, median), pc));
+}
+
+// Dense rows of the augmented matrix, originals (row < n_cells) and synthetics in one launch.
+// One warp per row: stage the row (or the sum of the two parent rows) in shared memory, turn it into
+// log-normalised values in place and stream it out with 128-bit stores.  Pad columns [G, ld) are 0.
+__global__ void k_dense_rows(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                             const float *__restrict__ data, const double *__restrict__ l1_rows,
+                             const int64_t *__restrict__ parents, int64_t n_cells, int64_t n_synth, int n_genes,
+                             int ld, int chunk, float median, float pc, float *__restrict__ dense) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float *buf = smem + (size_t)w * chunk;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + w;
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    const int64_t n_rows = n_cells + n_synth;
+    const float logpc = logf(pc);
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const bool synth = row >= n_cells;
+        int sa, ea, sb = 0, eb = 0;
+        double l1;
+        if (!synth) {
+            sa = indptr[row];
+            ea = indptr[row + 1];
+            l1 = l1_rows[row];
+        } else {
+            const int64_t r = row - n_cells;
+            const int64_t pa = parents[2 * r], pb = parents[2 * r + 1];
+            sa = indptr[pa];
+            ea = indptr[pa + 1];
+            sb = indptr[pb];
+            eb = indptr[pb + 1];
+            l1 = 0.0;
+            if (n_genes > chunk) {  // several column chunks: the L1 norm needs its own pass
+                for (int c0 = 0; c0 < n_genes; c0 += chunk) {
+                    const int cw = min(chunk, n_genes - c0);
+                    stage_pair_sum(buf, c0, cw, indices, data, sa, ea, sb, eb, lane);
+                    for (int j = lane; j < cw; j += 32) l1 += fabs((double)buf[j]);
+                    __syncwarp();
+                }
+                l1 = warp_sum_d(l1);
+            }
+        }
+        float *out_row = dense + row * (int64_t)ld;
+        for (int c0 = 0; c0 < ld; c0 += chunk) {
+            const int cw = min(chunk, ld - c0);           // multiple of 4 (ld and chunk are multiples of 32)
+            const int cg = max(0, min(cw, n_genes - c0));  // real gene columns in this chunk
+            if (!synth) {
+                for (int j = lane; j < cw; j += 32) buf[j] = 0.f;
+                __syncwarp();
+                for (int p = sa + lane; p < ea; p += 32) {
+                    const int c = __ldg(indices + p) - c0;
+                    if ((unsigned)c < (unsigned)cg) buf[c] = __ldg(data + p);
+                }
+                __syncwarp();
+            } else {
+                stage_pair_sum(buf, c0, cg, indices, data, sa, ea, sb, eb, lane);
+                for (int j = cg + lane; j < cw; j += 32) buf[j] = 0.f;
+                if (n_genes <= chunk) {
+                    double acc = 0.0;
+                    for (int j = lane; j < cg; j += 32) acc += fabs((double)buf[j]);
+                    l1 = warp_sum_d(acc);
+                }
+                __syncwarp();
+            }
+            // transform + stream out, 4 columns per lane per step
+            for (int j = 4 * lane; j < cw; j += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(buf + j);
+                float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int c = j + q;
+                    o[q] = c < cg ? (o[q] != 0.f ? norm_log(o[q], l1, median, pc) : logpc) : 0.f;
+                }
+                __stcs(reinterpret_cast<float4 *>(out_row + c0 + j), make_float4(o[0], o[1], o[2], o[3]));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int pick_chunk(int64_t ld) { return (int)std::min<int64_t>(ld, kMaxChunk); }
+
+int grid_for(dd_handle *h, size_t smem_bytes) {
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem_bytes, 1)));
+    return h->num_sms * per_sm;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32_t *indptr,
+                                const int32_t *indices, const float *data) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_upload_counts: null handle");
+    if (n_cells <= 0 || n_genes <= 0 || !indptr) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: empty matrix");
+    if (n_genes >= (1ll << 31) - 64 || n_cells >= (1ll << 31) - 64)
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_upload_counts: dimensions exceed int32 indexing");
+    const int64_t nnz = indptr[n_cells];
+    if (indptr[0] != 0 || nnz < 0) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: bad indptr");
+    if (nnz > 0 && (!indices || !data)) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: null indices/data");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    for (void *p : {(void *)h->d_indptr, (void *)h->d_indices, (void *)h->d_data, (void *)h->d_lib, (void *)h->d_l1})
+        if (p) cudaFree(p);
+    h->d_indptr = nullptr; h->d_indices = nullptr; h->d_data = nullptr; h->d_lib = nullptr; h->d_l1 = nullptr;
+    h->N = n_cells; h->G = n_genes; h->nnz = nnz;
+    h->ld = dd_round_up(n_genes, 32);
+    h->synth_csr_valid = false; h->dense_valid = false; h->emb_valid = false; h->M = 0; h->A = 0;
+    DD_CUDA(h, cudaMalloc(&h->d_indptr, sizeof(int32_t) * (n_cells + 1)));
+    DD_CUDA(h, cudaMalloc(&h->d_indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+    DD_CUDA(h, cudaMalloc(&h->d_data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+    DD_CUDA(h, cudaMalloc(&h->d_lib, sizeof(float) * n_cells));
+    DD_CUDA(h, cudaMalloc(&h->d_l1, sizeof(double) * n_cells));
+    DD_CUDA(h, cudaMemcpyAsync(h->d_indptr, indptr, sizeof(int32_t) * (n_cells + 1), cudaMemcpyHostToDevice, h->stream));
+    if (nnz > 0) {
+        DD_CUDA(h, cudaMemcpyAsync(h->d_indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
+        DD_CUDA(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->stream));
+    }
+    const int grid = h->num_sms * 8;
+    DD_LAUNCH(h, "row_sums", k_row_sums, grid, 256, 0, h->d_indptr, h->d_data, n_cells, h->d_lib, h->d_l1);
+    h->h_lib.resize(n_cells);
+    DD_CUDA(h, cudaMemcpyAsync(h->h_lib.data(), h->d_lib, sizeof(float) * n_cells, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_get_lib_size(dd_handle *h, float *out) {
+    if (!h || !out || !h->d_indptr) return dd_fail(h, DD_ERR_ARG, "dd_get_lib_size: no counts uploaded");
+    std::copy(h->h_lib.begin(), h->h_lib.end(), out);
+    return DD_OK;
+}
+
+// Upload `choices` (:394) for one iteration; validates the indices on the host.
+int dd_set_parents(dd_handle *h, int64_t n_synth, const int64_t *parents) {
+    if (!h || !h->d_indptr) return dd_fail(h, DD_ERR_ARG, "parents: no counts uploaded");
+    if (n_synth < 0 || (n_synth > 0 && !parents)) return dd_fail(h, DD_ERR_ARG, "parents: bad arguments");
+    for (int64_t i = 0; i < 2 * n_synth; i++)
+        if (parents[i] < 0 || parents[i] >= h->N) return dd_fail(h, DD_ERR_ARG, "parents: index out of range");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    if (n_synth > h->cap_M) {
+        for (void *p : {(void *)h->d_parents, (void *)h->d_sindptr, (void *)h->d_scount, (void *)h->d_slib})
+            if (p) cudaFree(p);
+        h->d_parents = nullptr; h->d_sindptr = nullptr; h->d_scount = nullptr; h->d_slib = nullptr;
+        h->cap_M = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_parents, sizeof(int64_t) * 2 * n_synth));
+        DD_CUDA(h, cudaMalloc(&h->d_sindptr, sizeof(int32_t) * (n_synth + 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_scount, sizeof(int32_t) * n_synth));
+        DD_CUDA(h, cudaMalloc(&h->d_slib, sizeof(float) * n_synth));
+        h->cap_M = n_synth;
+    }
+    h->M = n_synth;
+    h->A = h->N + n_synth;
+    h->synth_csr_valid = false; h->dense_valid = false; h->emb_valid = false;
+    if (n_synth > 0)
+        DD_CUDA(h, cudaMemcpyAsync(h->d_parents, parents, sizeof(int64_t) * 2 * n_synth, cudaMemcpyHostToDevice,
+                                   h->stream));
+    return DD_OK;
+}
+
+int dd_dev_create_doublets_csr(dd_handle *h) {
+    const int chunk = pick_chunk(h->ld);
+    const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_synth_count, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
+        cudaFuncSetAttribute(k_synth_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
+        attr_set = true;
+    }
+    const int grid = grid_for(h, smem);
+    if (h->M > 0) {
+        DD_LAUNCH(h, "synth_count", k_synth_count, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data,
+                  h->d_parents, h->M, (int)h->G, chunk, h->d_scount, h->d_slib);
+    }
+    DD_LAUNCH(h, "exclusive_scan", k_exclusive_scan, 1, 1024, 0, h->d_scount, h->M, h->d_sindptr);
+    int32_t total = 0;
+    DD_CUDA(h, cudaMemcpyAsync(&total, h->d_sindptr + h->M, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (total < 0) return dd_fail(h, DD_ERR_UNSUPPORTED, "synthetic nnz exceeds int32 indexing");
+    if (total > h->cap_snnz) {
+        if (h->d_sindices) cudaFree(h->d_sindices);
+        if (h->d_sdata) cudaFree(h->d_sdata);
+        h->d_sindices = nullptr; h->d_sdata = nullptr; h->cap_snnz = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_sindices, sizeof(int32_t) * std::max<int64_t>(total, 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_sdata, sizeof(float) * std::max<int64_t>(total, 1)));
+        h->cap_snnz = total;
+    }
+    h->snnz = total;
+    if (h->M > 0 && total > 0) {
+        DD_LAUNCH(h, "synth_fill", k_synth_fill, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data,
+                  h->d_parents, h->M, (int)h->G, chunk, h->d_sindptr, h->d_sindices, h->d_sdata);
+    }
+    h->synth_csr_valid = true;
+    return DD_OK;
+}
+
+extern "C" int dd_create_doublets(dd_handle *h, int64_t n_synth, const int64_t *parents) {
+    DD_TRY(dd_set_parents(h, n_synth, parents));
+    DD_TRY(dd_stage_begin(h));
+    DD_TRY(dd_dev_create_doublets_csr(h));
+    DD_TRY(dd_stage_end(h, "doublets"));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_synth_nnz(dd_handle *h, int64_t *nnz_out) {
+    if (!h || !nnz_out || !h->synth_csr_valid) return dd_fail(h, DD_ERR_ARG, "dd_synth_nnz: call dd_create_doublets first");
+    *nnz_out = h->snnz;
+    return DD_OK;
+}
+
+extern "C" int dd_download_synthetics(dd_handle *h, int32_t *indptr_out, int32_t *indices_out, float *data_out) {
+    if (!h || !h->synth_csr_valid) return dd_fail(h, DD_ERR_ARG, "dd_download_synthetics: call dd_create_doublets first");
+    if (!indptr_out) return dd_fail(h, DD_ERR_ARG, "dd_download_synthetics: null output");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_CUDA(h, cudaMemcpyAsync(indptr_out, h->d_sindptr, sizeof(int32_t) * (h->M + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (h->snnz > 0) {
+        if (!indices_out || !data_out) return dd_fail(h, DD_ERR_ARG, "dd_download_synthetics: null output");
+        DD_CUDA(h, cudaMemcpyAsync(indices_out, h->d_sindices, sizeof(int32_t) * h->snnz, cudaMemcpyDeviceToHost, h->stream));
+        DD_CUDA(h, cudaMemcpyAsync(data_out, h->d_sdata, sizeof(float) * h->snnz, cudaMemcpyDeviceToHost, h->stream));
+    }
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_get_synth_lib_size(dd_handle *h, float *out) {
+    if (!h || !out || !h->synth_csr_valid) return dd_fail(h, DD_ERR_ARG, "dd_get_synth_lib_size: call dd_create_doublets first");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    if (h->M > 0) DD_CUDA(h, cudaMemcpyAsync(out, h->d_slib, sizeof(float) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+// np.median(aug_lib_size) (:289, :293): float32, mean of the two middle values for even length.
+float dd_host_median(std::vector<float> &v) {
+    const size_t n = v.size();
+    if (n == 0) return nanf("");
+    const size_t mid = n / 2;
+    std::nth_element(v.begin(), v.begin() + mid, v.end());
+    const float hi = v[mid];
+    if (n & 1) return hi;
+    const float lo = *std::max_element(v.begin(), v.begin() + mid);
+    return (lo + hi) / 2.0f;
+}
+
+extern "C" int dd_median_lib_size(dd_handle *h, float *median_out) {
+    if (!h || !median_out || !h->synth_csr_valid) return dd_fail(h, DD_ERR_ARG, "dd_median_lib_size: call dd_create_doublets first");
+    std::vector<float> aug(h->N + h->M);
+    std::copy(h->h_lib.begin(), h->h_lib.end(), aug.begin());
+    DD_TRY(dd_get_synth_lib_size(h, aug.data() + h->N));
+    *median_out = dd_host_median(aug);
+    return DD_OK;
+}
+
+int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
+    if (!h->d_indptr || !h->d_parents || h->A == 0) return dd_fail(h, DD_ERR_ARG, "normalise: upload counts and parents first");
+    const int64_t need = h->A * h->ld;
+    DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, need));
+    const int chunk = pick_chunk(h->ld);
+    const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
+        attr_set = true;
+    }
+    const int grid = grid_for(h, smem);
+    DD_LAUNCH(h, "dense_rows", k_dense_rows, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
+              h->d_parents, h->N, h->M, (int)h->G, (int)h->ld, chunk, median, pseudocount, h->d_dense);
+    h->dense_valid = true;
+    h->emb_valid = false;
+    return DD_OK;
+}
+
+extern "C" int dd_normalise_log(dd_handle *h, float median, float pseudocount) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_normalise_log: null handle");
+    if (pseudocount == 1.0f)
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "pseudocount == 1 (sparse log1p + arpack path) is not on the B200 hot path");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_TRY(dd_stage_begin(h));
+    DD_TRY(dd_dev_build_dense(h, median, pseudocount));
+    DD_TRY(dd_stage_end(h, "normalise"));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_download_dense(dd_handle *h, int64_t row0, int64_t n_rows, float *out) {
+    if (!h || !h->dense_valid) return dd_fail(h, DD_ERR_ARG, "dd_download_dense: no dense matrix");
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->A || !out) return dd_fail(h, DD_ERR_ARG, "dd_download_dense: bad range");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    if (n_rows > 0)
+        DD_CUDA(h, cudaMemcpy2DAsync(out, sizeof(float) * h->G, h->d_dense + row0 * h->ld, sizeof(float) * h->ld,
+                                     sizeof(float) * h->G, n_rows, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_upload_dense(dd_handle *h, int64_t n_rows, int64_t n_genes, const float *dense) {
+    if (!h || !dense || n_rows <= 0 || n_genes <= 0) return dd_fail(h, DD_ERR_ARG, "dd_upload_dense: bad arguments");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_indptr) {  // stand-alone use (tests): no counts uploaded
+        h->G = n_genes;
+        h->ld = dd_round_up(n_genes, 32);
+        h->N = n_rows;
+        h->M = 0;
+    } else if (n_genes != h->G) {
+        return dd_fail(h, DD_ERR_ARG, "dd_upload_dense: gene count differs from the uploaded counts");
+    }
+    h->A = n_rows;
+    DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, h->A * h->ld));
+    DD_CUDA(h, cudaMemsetAsync(h->d_dense, 0, sizeof(float) * h->A * h->ld, h->stream));
+    DD_CUDA(h, cudaMemcpy2DAsync(h->d_dense, sizeof(float) * h->ld, dense, sizeof(float) * h->G, sizeof(float) * h->G,
+                                 n_rows, cudaMemcpyHostToDevice, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->dense_valid = true;
+    h->emb_valid = false;
+    return DD_OK;
+}

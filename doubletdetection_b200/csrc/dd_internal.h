@@ -1,0 +1,142 @@
+// dd_internal.h -- handle layout, error plumbing and launch accounting shared by the translation
+// units of libdd_b200.so.  Nothing here is part of the ABI (see include/dd_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dd_b200.h"
+
+#define DD_ABI_VERSION 1
+
+// padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
+static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct dd_kernel_stat {
+    double total_ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct dd_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    std::string err;
+
+    // ---- raw counts (fit prologue) ----
+    int64_t N = 0, G = 0, nnz = 0;
+    int32_t *d_indptr = nullptr, *d_indices = nullptr;
+    float *d_data = nullptr;
+    float *d_lib = nullptr;   // float32 row sums (_lib_size)
+    double *d_l1 = nullptr;   // double sums of |x| (the L1 normaliser of sklearn)
+    std::vector<float> h_lib;
+
+    // ---- synthetics ----
+    int64_t M = 0, cap_M = 0;
+    int64_t *d_parents = nullptr;
+    int32_t *d_sindptr = nullptr, *d_scount = nullptr;
+    int32_t *d_sindices = nullptr;
+    float *d_sdata = nullptr;
+    int64_t cap_snnz = 0, snnz = -1;
+    float *d_slib = nullptr;
+    bool synth_csr_valid = false;
+
+    // ---- dense log-normalised augmented matrix ----
+    int64_t A = 0, ld = 0, cap_dense = 0;  // A rows, leading dimension ld >= G (multiple of 32)
+    float *d_dense = nullptr;
+    bool dense_valid = false;
+    double *d_colsum = nullptr, *d_colsumsq = nullptr;  // G doubles each
+    int64_t cap_cols = 0;
+
+    // ---- PCA workspace ----
+    int32_t L = 0, LP = 0, C = 0;
+    int64_t cap_pca_rows = 0, cap_pca_cols = 0;
+    int32_t cap_LP = 0;
+    float *d_Qt = nullptr;     // LP x ld  (Q transposed, K-major for both GEMM flavours)
+    float *d_Y = nullptr;      // A x LP
+    double *d_Zacc = nullptr;  // G x LP accumulators of D^T Y
+    double *d_small = nullptr; // scratch for L x L matrices, sums, flags (see pca.cu)
+    float *d_emb = nullptr;    // A x KP embedding (KP = 32 or 64, zero padded)
+    int32_t KP = 0;
+    int64_t emb_rows = 0;
+    bool emb_valid = false;
+    int64_t cap_emb = 0;
+
+    // ---- kNN outputs ----
+    int32_t *d_knn_idx = nullptr;
+    float *d_knn_dist = nullptr;
+    int64_t cap_knn = 0;
+
+    // ---- accounting ----
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t stage_ev0 = nullptr, stage_ev1 = nullptr;
+    std::map<std::string, dd_kernel_stat> kstats;
+    std::map<std::string, double> stage_ms;
+};
+
+// thread-local message for failures that happen without a handle
+void dd_set_global_error(const std::string &msg);
+int dd_fail(dd_handle *h, int code, const std::string &msg);
+
+#define DD_CUDA(h, expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return dd_fail((h), _e == cudaErrorMemoryAllocation ? DD_ERR_NOMEM : DD_ERR_CUDA,  \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+    } while (0)
+
+#define DD_TRY(expr)                 \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != DD_OK) return _rc; \
+    } while (0)
+
+// Launch accounting: every kernel goes through DD_LAUNCH so that dd_kernel_launches() is exact and
+// per-kernel device time can be collected (dd_set_kernel_timing).
+void dd_launch_begin(dd_handle *h);
+int dd_launch_end(dd_handle *h, const char *name);
+
+#define DD_LAUNCH(h, name, kernel, grid, block, smem, ...)                  \
+    do {                                                                    \
+        dd_launch_begin(h);                                                 \
+        kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);      \
+        DD_TRY(dd_launch_end((h), (name)));                                 \
+    } while (0)
+
+// stage timers (CUDA events on the handle's stream)
+int dd_stage_begin(dd_handle *h);
+int dd_stage_end(dd_handle *h, const char *stage);
+
+// grow-only device buffers
+template <typename T>
+static inline int dd_reserve(dd_handle *h, T **p, int64_t *cap, int64_t need) {
+    if (need <= *cap && *p) return DD_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc((void **)p, sizeof(T) * (size_t)(need > 0 ? need : 1));
+    if (e != cudaSuccess) return dd_fail(h, DD_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cap = need;
+    return DD_OK;
+}
+
+// ---- stage entry points implemented across the .cu files (all asynchronous on h->stream) ----
+int dd_dev_create_doublets_csr(dd_handle *h);                       // csr.cu
+int dd_dev_build_dense(dd_handle *h, float median, float pseudocount);  // csr.cu (fused pair-add + normalise)
+int dd_dev_colstats(dd_handle *h, bool with_sq);                    // scale.cu
+int dd_dev_standard_scale(dd_handle *h, float max_value);           // scale.cu
+int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter,
+               const float *omega_host);                            // pca.cu
+int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
+
+// host pieces (louvain.cpp / score.cpp)
+int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
+                        int32_t *labels_out, int32_t *n_comm_out);
+float dd_host_median(std::vector<float> &v);

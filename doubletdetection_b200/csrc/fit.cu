@@ -1,0 +1,210 @@
+// fit.cu -- the loop of BoostClassifier.fit (doubletdetection.py:192-198) as one pipelined call:
+// the GPU stages of _one_fit run back to back on the handle's stream (no host synchronisation between
+// iterations), each iteration's kNN graph lands in a pinned host buffer, and a pool of host threads
+// clusters + scores finished iterations while the GPU works on the next ones.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "dd_internal.h"
+
+int dd_set_parents(dd_handle *h, int64_t n_synth, const int64_t *parents);  // csr.cu
+int dd_pca_check(dd_handle *h);                                             // pca.cu
+int dd_pca_flag_copy(dd_handle *h, double *host_flag);                      // pca.cu
+
+namespace {
+
+struct Slot {
+    int32_t *knn = nullptr;  // pinned, A * k
+    double *flag = nullptr;  // pinned, PCA breakdown flag
+    cudaEvent_t done = nullptr;
+};
+
+struct Job {
+    int iter;
+    int slot;
+};
+
+constexpr int kStages = 6;  // doublets+normalise, scale, pca, knn, d2h  (index 0 unused in the fused build)
+
+}  // namespace
+
+extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int64_t *parents, const float *omega,
+                                 double *scores_out, double *log_p_out, int32_t *communities_out,
+                                 int32_t *synth_communities_out, double *stage_ms_out) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_fit_iterations: null handle");
+    if (!p || !omega || !scores_out || !log_p_out || !communities_out)
+        return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: null argument");
+    if (!h->d_indptr) return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: call dd_upload_counts first");
+    if (p->n_iters < 1 || p->iter_begin < 0 || p->iter_end > p->n_iters || p->iter_begin > p->iter_end)
+        return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: bad iteration range");
+    if (p->n_synth < 0 || (p->n_synth > 0 && (!parents || !synth_communities_out)))
+        return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: bad n_synth / parents");
+    if (p->pseudocount == 1.0f)
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "pseudocount == 1 (sparse log1p + arpack path) is not on the B200 hot path");
+    if (p->knn_k < 2) return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: knn_k < 2");
+    DD_CUDA(h, cudaSetDevice(h->device));
+
+    const int64_t N = h->N, M = p->n_synth, A = N + M;
+    const int k = p->knn_k;
+    const int n_threads = std::max(1, p->n_host_threads);
+    const int n_slots = n_threads + 2;
+    const int n_run = p->iter_end - p->iter_begin;
+    if (stage_ms_out) std::fill(stage_ms_out, stage_ms_out + 8, 0.0);
+    if (n_run == 0) return DD_OK;
+
+    std::vector<Slot> slots(n_slots);
+    std::vector<cudaEvent_t> evs((size_t)n_run * kStages, nullptr);
+    int rc = DD_OK;
+    std::string err;
+    auto cleanup = [&]() {
+        for (Slot &s : slots) {
+            if (s.knn) cudaFreeHost(s.knn);
+            if (s.flag) cudaFreeHost(s.flag);
+            if (s.done) cudaEventDestroy(s.done);
+        }
+        for (cudaEvent_t e : evs)
+            if (e) cudaEventDestroy(e);
+    };
+    for (Slot &s : slots) {
+        if (cudaMallocHost(&s.knn, sizeof(int32_t) * A * k) != cudaSuccess ||
+            cudaMallocHost(&s.flag, sizeof(double)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+            cleanup();
+            return dd_fail(h, DD_ERR_NOMEM, "dd_fit_iterations: pinned host buffers");
+        }
+    }
+    for (cudaEvent_t &e : evs)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            cleanup();
+            return dd_fail(h, DD_ERR_CUDA, "dd_fit_iterations: event creation");
+        }
+
+    // ---- host workers: wait for an iteration's kNN graph, cluster, score
+    std::mutex mu;
+    std::condition_variable cv_job, cv_slot;
+    std::deque<Job> jobs;
+    std::deque<int> free_slots;
+    for (int s = 0; s < n_slots; s++) free_slots.push_back(s);
+    bool closing = false;
+    std::atomic<int> worker_rc{DD_OK};
+    std::string worker_err;
+
+    auto worker = [&]() {
+        std::vector<int32_t> labels((size_t)A);
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return closing || !jobs.empty(); });
+                if (jobs.empty()) return;
+                job = jobs.front();
+                jobs.pop_front();
+            }
+            Slot &s = slots[job.slot];
+            int wrc = DD_OK;
+            std::string werr;
+            if (cudaEventSynchronize(s.done) != cudaSuccess) {
+                wrc = DD_ERR_CUDA;
+                werr = "dd_fit_iterations: device error while waiting for an iteration";
+            } else if (*s.flag != 0.0) {
+                wrc = DD_ERR_UNSUPPORTED;
+                werr = "pca: rank-deficient range (Cholesky breakdown)";
+            } else {
+                int32_t n_comm = 0;
+                wrc = dd_host_louvain_knn(A, k, s.knn, p->resolution, p->seed, labels.data(), &n_comm);
+                if (wrc != DD_OK) werr = "dd_fit_iterations: clustering rejected the kNN graph (index out of range)";
+                if (wrc == DD_OK) {
+                    wrc = dd_score(N, M, labels.data(), scores_out + (size_t)job.iter * N, log_p_out + (size_t)job.iter * N);
+                    std::copy(labels.begin(), labels.begin() + N, communities_out + (size_t)job.iter * N);
+                    if (M > 0) std::copy(labels.begin() + N, labels.end(), synth_communities_out + (size_t)job.iter * M);
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (wrc != DD_OK && worker_rc.load() == DD_OK) {
+                    worker_rc.store(wrc);
+                    worker_err = werr;
+                }
+                free_slots.push_back(job.slot);
+            }
+            cv_slot.notify_one();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
+
+    // ---- GPU producer
+    std::vector<float> aug((size_t)A);
+    bool omega_sent = false;
+    int issued = 0;
+    for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && worker_rc.load() == DD_OK; it++, issued++) {
+        const int64_t *par = M > 0 ? parents + (size_t)it * M * 2 : nullptr;
+        int slot;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_slot.wait(lk, [&] { return !free_slots.empty(); });
+            slot = free_slots.front();
+            free_slots.pop_front();
+        }
+        Slot &s = slots[slot];
+        cudaEvent_t *ev = &evs[(size_t)issued * kStages];
+        rc = dd_set_parents(h, M, par);
+        if (rc != DD_OK) break;
+        // np.median(aug_lib_size): synthetic library sizes are the parents' sums (exact for counts)
+        std::copy(h->h_lib.begin(), h->h_lib.end(), aug.begin());
+        for (int64_t r = 0; r < M; r++) aug[N + r] = h->h_lib[par[2 * r]] + h->h_lib[par[2 * r + 1]];
+        std::vector<float> tmp(aug);
+        const float median = dd_host_median(tmp);
+
+        cudaEventRecord(ev[0], h->stream);
+        if ((rc = dd_dev_build_dense(h, median, p->pseudocount)) != DD_OK) break;
+        cudaEventRecord(ev[1], h->stream);
+        if (p->standard_scaling && (rc = dd_dev_standard_scale(h, p->scale_max_value)) != DD_OK) break;
+        cudaEventRecord(ev[2], h->stream);
+        if ((rc = dd_dev_pca(h, p->n_comp, p->n_random, p->n_power_iter, omega_sent ? nullptr : omega)) != DD_OK) break;
+        omega_sent = true;
+        cudaEventRecord(ev[3], h->stream);
+        if ((rc = dd_dev_knn(h, k)) != DD_OK) break;
+        cudaEventRecord(ev[4], h->stream);
+        cudaMemcpyAsync(s.knn, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, h->stream);
+        dd_pca_flag_copy(h, s.flag);
+        cudaEventRecord(ev[5], h->stream);
+        cudaEventRecord(s.done, h->stream);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobs.push_back(Job{it, slot});
+        }
+        cv_job.notify_one();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        closing = true;
+    }
+    cv_job.notify_all();
+    for (std::thread &t : pool) t.join();
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    if (rc == DD_OK && ce != cudaSuccess) rc = dd_fail(h, DD_ERR_CUDA, std::string("dd_fit_iterations: ") + cudaGetErrorString(ce));
+    if (rc == DD_OK && worker_rc.load() != DD_OK) rc = dd_fail(h, worker_rc.load(), worker_err);
+    if (rc == DD_OK && stage_ms_out) {
+        for (int i = 0; i < issued; i++) {
+            cudaEvent_t *ev = &evs[(size_t)i * kStages];
+            float ms;
+            // {doublets, normalise, scale, pca, knn, d2h}: the fused build is booked under "normalise"
+            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stage_ms_out[1] += ms;
+            if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) stage_ms_out[2] += ms;
+            if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) stage_ms_out[3] += ms;
+            if (cudaEventElapsedTime(&ms, ev[3], ev[4]) == cudaSuccess) stage_ms_out[4] += ms;
+            if (cudaEventElapsedTime(&ms, ev[4], ev[5]) == cudaSuccess) stage_ms_out[5] += ms;
+        }
+        float total = 0.f;
+        if (cudaEventElapsedTime(&total, evs[0], evs[(size_t)(issued - 1) * kStages + 5]) == cudaSuccess)
+            stage_ms_out[6] = total;  // first launch -> last copy, device time of the whole call
+    }
+    cleanup();
+    return rc;
+}

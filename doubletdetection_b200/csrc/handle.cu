@@ -1,0 +1,124 @@
+// handle.cu -- lifetime, error reporting, launch accounting and stage timers of libdd_b200.so.
+#include "dd_internal.h"
+
+#include <cstring>
+
+static thread_local std::string g_error;
+
+void dd_set_global_error(const std::string &msg) { g_error = msg; }
+
+int dd_fail(dd_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    g_error = msg;
+    return code;
+}
+
+void dd_launch_begin(dd_handle *h) {
+    if (h->timing) cudaEventRecord(h->ev0, h->stream);
+}
+
+int dd_launch_end(dd_handle *h, const char *name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("launch of ") + name + ": " + cudaGetErrorString(e));
+    h->launches++;
+    if (h->timing) {
+        cudaEventRecord(h->ev1, h->stream);
+        e = cudaEventSynchronize(h->ev1);
+        if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("kernel ") + name + ": " + cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        dd_kernel_stat &st = h->kstats[name];
+        st.total_ms += ms;
+        st.launches++;
+    }
+    return DD_OK;
+}
+
+int dd_stage_begin(dd_handle *h) {
+    DD_CUDA(h, cudaEventRecord(h->stage_ev0, h->stream));
+    return DD_OK;
+}
+
+int dd_stage_end(dd_handle *h, const char *stage) {
+    DD_CUDA(h, cudaEventRecord(h->stage_ev1, h->stream));
+    DD_CUDA(h, cudaEventSynchronize(h->stage_ev1));
+    float ms = 0.f;
+    DD_CUDA(h, cudaEventElapsedTime(&ms, h->stage_ev0, h->stage_ev1));
+    h->stage_ms[stage] = ms;
+    return DD_OK;
+}
+
+extern "C" int dd_abi_version(void) { return DD_ABI_VERSION; }
+
+extern "C" int dd_create(int device, dd_handle **out) {
+    if (!out) return dd_fail(nullptr, DD_ERR_ARG, "dd_create: null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return dd_fail(nullptr, DD_ERR_CUDA,
+                       std::string("dd_create: no CUDA device (there is no CPU fallback): ") +
+                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return dd_fail(nullptr, DD_ERR_ARG, "dd_create: device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return dd_fail(nullptr, DD_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return dd_fail(nullptr, DD_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return dd_fail(nullptr, DD_ERR_UNSUPPORTED,
+                       std::string("dd_create: device '") + prop.name + "' is not sm_100 (this library is B200-only)");
+    dd_handle *h = new dd_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->stage_ev0) != cudaSuccess || cudaEventCreate(&h->stage_ev1) != cudaSuccess) {
+        delete h;
+        return dd_fail(nullptr, DD_ERR_CUDA, "dd_create: stream/event creation failed");
+    }
+    *out = h;
+    return DD_OK;
+}
+
+extern "C" void dd_destroy(dd_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void *bufs[] = {h->d_indptr, h->d_indices, h->d_data,   h->d_lib,   h->d_l1,      h->d_parents, h->d_sindptr,
+                    h->d_scount, h->d_sindices, h->d_sdata, h->d_slib,  h->d_dense,   h->d_colsum,  h->d_colsumsq,
+                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx, h->d_knn_dist};
+    for (void *p : bufs)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stage_ev0) cudaEventDestroy(h->stage_ev0);
+    if (h->stage_ev1) cudaEventDestroy(h->stage_ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *dd_last_error(const dd_handle *h) { return h ? h->err.c_str() : g_error.c_str(); }
+
+extern "C" int64_t dd_kernel_launches(const dd_handle *h) { return h ? h->launches : -1; }
+
+extern "C" double dd_last_stage_ms(const dd_handle *h, const char *stage) {
+    if (!h || !stage) return -1.0;
+    auto it = h->stage_ms.find(stage);
+    return it == h->stage_ms.end() ? -1.0 : it->second;
+}
+
+extern "C" int dd_set_kernel_timing(dd_handle *h, int32_t on) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_set_kernel_timing: null handle");
+    h->timing = on != 0;
+    if (on) h->kstats.clear();
+    return DD_OK;
+}
+
+extern "C" int dd_get_kernel_timing(dd_handle *h, const char *kernel, double *total_ms_out, int64_t *launches_out) {
+    if (!h || !kernel) return dd_fail(h, DD_ERR_ARG, "dd_get_kernel_timing: bad arguments");
+    auto it = h->kstats.find(kernel);
+    if (total_ms_out) *total_ms_out = it == h->kstats.end() ? 0.0 : it->second.total_ms;
+    if (launches_out) *launches_out = it == h->kstats.end() ? 0 : it->second.launches;
+    return DD_OK;
+}

@@ -1,0 +1,314 @@
+// louvain.cpp -- the clustering call of _one_fit (doubletdetection.py:337-343): what
+// sc.tl.louvain(adata, resolution=4, random_state, directed=False) optimises on the symmetrised kNN
+// pattern -- RB-configuration modularity, resolution gamma, unweighted, seeded.  The louvain-igraph
+// package is not available; the move order is specified by oracle/louvain_ref.py (FIFO queue in a
+// SplitMix64-shuffled order, stay-wins-ties, first-best candidate in adjacency order, aggregation with
+// ascending neighbour lists, labels by decreasing community size) and this file reproduces it label for
+// label.  Host code on purpose: the graph has ~15 edges per node and the algorithm is a sequential
+// sweep; iterations are clustered concurrently on host threads while the GPU runs ahead
+// (dd_fit_iterations).
+#include <stdint.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "dd_internal.h"
+
+namespace {
+
+struct SplitMix64 {
+    uint64_t s;
+    uint64_t next() {
+        s += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+};
+
+struct Graph {
+    int32_t n = 0;
+    std::vector<int64_t> indptr;
+    std::vector<int32_t> indices;
+    std::vector<double> weights;  // empty = all ones
+    std::vector<double> selfw;
+    double w(int64_t e) const { return weights.empty() ? 1.0 : weights[e]; }
+};
+
+struct Scratch {
+    std::vector<double> k, tot, neigh_w;
+    std::vector<uint8_t> seen, inq;
+    std::vector<int32_t> queue, cands;
+};
+
+// one level of local moving; returns true if any node moved
+bool one_level(const Graph &g, double gamma, double two_m, SplitMix64 &rng, std::vector<int32_t> &comm, Scratch &sc) {
+    const int32_t n = g.n;
+    sc.k.assign(n, 0.0);
+    sc.tot.assign(n, 0.0);
+    sc.neigh_w.assign(n, 0.0);
+    sc.seen.assign(n, 0);
+    sc.inq.assign(n, 1);
+    sc.queue.resize(n);
+    sc.cands.resize(std::max<int32_t>(n, 1));
+    comm.resize(n);
+    const bool unit = g.weights.empty();
+    for (int32_t i = 0; i < n; i++) {
+        double s = g.selfw[i];
+        if (unit) {
+            s += (double)(g.indptr[i + 1] - g.indptr[i]);
+        } else {
+            for (int64_t e = g.indptr[i]; e < g.indptr[i + 1]; e++) s += g.weights[e];
+        }
+        sc.k[i] = s;
+        sc.tot[i] = s;
+        comm[i] = i;
+        sc.queue[i] = i;
+    }
+    for (int64_t i = (int64_t)n - 1; i >= 1; i--) {
+        const int64_t j = (int64_t)(rng.next() % (uint64_t)(i + 1));
+        std::swap(sc.queue[i], sc.queue[j]);
+    }
+    double *tot = sc.tot.data(), *neigh_w = sc.neigh_w.data();
+    uint8_t *seen = sc.seen.data(), *inq = sc.inq.data();
+    int32_t *queue = sc.queue.data(), *cands = sc.cands.data();
+    const int64_t *indptr = g.indptr.data();
+    const int32_t *indices = g.indices.data();
+    int32_t head = 0, count = n;
+    bool moved_any = false;
+    while (count > 0) {
+        const int32_t i = queue[head];
+        head = (head + 1 == n) ? 0 : head + 1;
+        count--;
+        inq[i] = 0;
+        const int32_t ci = comm[i];
+        const double ki = sc.k[i];
+        int32_t nc = 0;
+        cands[nc++] = ci;
+        seen[ci] = 1;
+        neigh_w[ci] = 0.0;
+        const int64_t e0 = indptr[i], e1 = indptr[i + 1];
+        for (int64_t e = e0; e < e1; e++) {
+            const int32_t c = comm[indices[e]];
+            if (!seen[c]) {
+                seen[c] = 1;
+                neigh_w[c] = 0.0;
+                cands[nc++] = c;
+            }
+            neigh_w[c] += unit ? 1.0 : g.weights[e];
+        }
+        tot[ci] -= ki;
+        const double gk = gamma * ki;
+        int32_t best = ci;
+        double best_gain = neigh_w[ci] - (gk * tot[ci]) / two_m;
+        for (int32_t t = 1; t < nc; t++) {
+            const int32_t c = cands[t];
+            const double gn = neigh_w[c] - (gk * tot[c]) / two_m;
+            if (gn > best_gain) {
+                best = c;
+                best_gain = gn;
+            }
+        }
+        for (int32_t t = 0; t < nc; t++) seen[cands[t]] = 0;
+        tot[best] += ki;
+        if (best != ci) {
+            comm[i] = best;
+            moved_any = true;
+            for (int64_t e = e0; e < e1; e++) {
+                const int32_t j = indices[e];
+                if (comm[j] != best && !inq[j]) {
+                    inq[j] = 1;
+                    int32_t tail = head + count;
+                    if (tail >= n) tail -= n;
+                    queue[tail] = j;
+                    count++;
+                }
+            }
+        }
+    }
+    return moved_any;
+}
+
+// aggregate g by comm; node2new renumbers communities by first appearance over node index
+void aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &out, std::vector<int32_t> &node2new) {
+    const int32_t n = g.n;
+    std::vector<int32_t> new_id(n, -1);
+    node2new.resize(n);
+    int32_t nc = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (new_id[comm[i]] < 0) new_id[comm[i]] = nc++;
+        node2new[i] = new_id[comm[i]];
+    }
+    std::vector<int64_t> mstart(nc + 1, 0);
+    for (int32_t i = 0; i < n; i++) mstart[node2new[i] + 1]++;
+    for (int32_t a = 0; a < nc; a++) mstart[a + 1] += mstart[a];
+    std::vector<int32_t> members(std::max<int32_t>(n, 1));
+    {
+        std::vector<int64_t> fill(mstart.begin(), mstart.end() - 1);
+        for (int32_t i = 0; i < n; i++) members[fill[node2new[i]]++] = i;  // ascending node order
+    }
+    out.n = nc;
+    out.indptr.assign(nc + 1, 0);
+    out.indices.clear();
+    out.weights.clear();
+    out.selfw.assign(nc, 0.0);
+    out.indices.reserve(g.indices.size());
+    out.weights.reserve(g.indices.size());
+    std::vector<double> acc(nc, 0.0);
+    std::vector<uint8_t> seen(nc, 0);
+    std::vector<int32_t> touched;
+    touched.reserve(nc);
+    for (int32_t a = 0; a < nc; a++) {
+        double s = 0.0;
+        touched.clear();
+        for (int64_t p = mstart[a]; p < mstart[a + 1]; p++) {
+            const int32_t i = members[p];
+            s += g.selfw[i];
+            for (int64_t e = g.indptr[i]; e < g.indptr[i + 1]; e++) {
+                const int32_t b = node2new[g.indices[e]];
+                const double w = g.w(e);
+                if (b == a) {
+                    s += w;
+                } else {
+                    if (!seen[b]) {
+                        seen[b] = 1;
+                        acc[b] = 0.0;
+                        touched.push_back(b);
+                    }
+                    acc[b] += w;
+                }
+            }
+        }
+        out.selfw[a] = s;
+        std::sort(touched.begin(), touched.end());
+        for (int32_t b : touched) {
+            out.indices.push_back(b);
+            out.weights.push_back(acc[b]);
+            seen[b] = 0;
+        }
+        out.indptr[a + 1] = (int64_t)out.indices.size();
+    }
+    if (out.weights.empty()) out.weights.push_back(0.0);  // keep "empty == unit weights" unambiguous
+}
+
+int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out) {
+    const int32_t n = g.n;
+    double two_m = 0.0;
+    if (g.weights.empty())
+        two_m = (double)g.indices.size();
+    else
+        for (size_t e = 0; e < g.indices.size(); e++) two_m += g.weights[e];
+    std::vector<int32_t> membership(n);
+    std::iota(membership.begin(), membership.end(), 0);
+    SplitMix64 rng{seed};
+    Scratch sc;
+    if (two_m > 0.0) {
+        std::vector<int32_t> comm, node2new;
+        for (int level = 0; level < 64; level++) {
+            const bool moved = one_level(g, resolution, two_m, rng, comm, sc);
+            if (!moved) break;
+            Graph ng;
+            aggregate(g, comm, ng, node2new);
+            for (int32_t i = 0; i < n; i++) membership[i] = node2new[membership[i]];
+            g = std::move(ng);
+        }
+    }
+    // first-appearance ids, then by decreasing size (ties: smaller first-appearance id first)
+    std::vector<int32_t> fa_of(n, -1);
+    int32_t nc = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (fa_of[membership[i]] < 0) fa_of[membership[i]] = nc++;
+        membership[i] = fa_of[membership[i]];
+    }
+    std::vector<int64_t> size(nc, 0);
+    for (int32_t i = 0; i < n; i++) size[membership[i]]++;
+    std::vector<int32_t> order(nc);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+    std::vector<int32_t> newlab(nc);
+    for (int32_t r = 0; r < nc; r++) newlab[order[r]] = r;
+    for (int32_t i = 0; i < n; i++) labels_out[i] = newlab[membership[i]];
+    if (n_comm_out) *n_comm_out = nc;
+    return DD_OK;
+}
+
+}  // namespace
+
+// Symmetric 0/1 pattern of the neighbour graph: i ~ j iff j in kNN(i)\{i} or i in kNN(j)\{j}
+// (sc.tl.louvain ignores the connectivities' weights: use_weights=False).
+int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
+                        int32_t *labels_out, int32_t *n_comm_out) {
+    if (n < 0 || k < 1 || (n > 0 && (!knn_idx || !labels_out))) return DD_ERR_ARG;
+    if (n >= (1ll << 31) - 1) return DD_ERR_UNSUPPORTED;
+    Graph g;
+    g.n = (int32_t)n;
+    std::vector<int64_t> deg(n + 1, 0);
+    for (int64_t i = 0; i < n; i++)
+        for (int32_t c = 0; c < k; c++) {
+            const int32_t j = knn_idx[i * k + c];
+            if (j < 0 || j >= n) return DD_ERR_ARG;
+            if (j == i) continue;
+            deg[i + 1]++;
+            deg[j + 1]++;
+        }
+    for (int64_t i = 0; i < n; i++) deg[i + 1] += deg[i];
+    std::vector<int32_t> adj(deg[n] > 0 ? deg[n] : 1);
+    {
+        std::vector<int64_t> fill(deg.begin(), deg.end() - 1);
+        for (int64_t i = 0; i < n; i++)
+            for (int32_t c = 0; c < k; c++) {
+                const int32_t j = knn_idx[i * k + c];
+                if (j == i) continue;
+                adj[fill[i]++] = j;
+                adj[fill[j]++] = (int32_t)i;
+            }
+    }
+    g.indptr.assign(n + 1, 0);
+    g.indices.reserve(deg[n]);
+    for (int64_t i = 0; i < n; i++) {
+        int32_t *b = adj.data() + deg[i], *e = adj.data() + deg[i + 1];
+        std::sort(b, e);
+        e = std::unique(b, e);
+        g.indices.insert(g.indices.end(), b, e);
+        g.indptr[i + 1] = (int64_t)g.indices.size();
+    }
+    g.selfw.assign(n, 0.0);
+    return run_louvain(g, resolution, seed, labels_out, n_comm_out);
+}
+
+extern "C" int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
+                              int32_t *labels_out, int32_t *n_communities_out) {
+    const int rc = dd_host_louvain_knn(n, k, knn_idx, resolution, seed, labels_out, n_communities_out);
+    if (rc != DD_OK) dd_set_global_error("dd_louvain_knn: bad arguments (null pointer, k < 1 or neighbour index out of range)");
+    return rc;
+}
+
+extern "C" int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                              double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out) {
+    if (n < 0 || !indptr || (n > 0 && !labels_out) || n >= (1ll << 31) - 1) {
+        dd_set_global_error("dd_louvain_csr: bad arguments");
+        return DD_ERR_ARG;
+    }
+    const int64_t nnz = indptr[n];
+    if (nnz > 0 && !indices) {
+        dd_set_global_error("dd_louvain_csr: null indices");
+        return DD_ERR_ARG;
+    }
+    Graph g;
+    g.n = (int32_t)n;
+    g.indptr.assign(indptr, indptr + n + 1);
+    g.indices.resize(nnz);
+    for (int64_t e = 0; e < nnz; e++) {
+        if (indices[e] < 0 || indices[e] >= n) {
+            dd_set_global_error("dd_louvain_csr: neighbour index out of range");
+            return DD_ERR_ARG;
+        }
+        g.indices[e] = (int32_t)indices[e];
+    }
+    if (weights && nnz > 0) g.weights.assign(weights, weights + nnz);
+    g.selfw.assign(n, 0.0);
+    return run_louvain(g, resolution, seed, labels_out, n_communities_out);
+}

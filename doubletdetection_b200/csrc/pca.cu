@@ -1,0 +1,722 @@
+// pca.cu -- sc.tl.pca(svd_solver="auto") on the dense augmented matrix == sklearn's randomized
+// truncated SVD (doubletdetection.py:309-314 -> sklearn/decomposition/_pca.py:726-758,
+// sklearn/utils/extmath.py:313-385, 560-633, 970-981):
+//     Q = Omega;  repeat n_iter: Q = normalise(Dc Q); Q = normalise(Dc^T Q);
+//     Q = qr(Dc Q);  B = Q^T Dc;  svd(B);  U = Q Uhat;  flip signs by Vt;  X_pca = U[:, :C] * s[:C]
+// where Dc is the column-centred dense matrix D.
+//
+// B200 design (no centred copy, no host round trips, everything on one stream):
+//   * the two tall-skinny products  Y = D Q  (A x L)  and  Z = D^T Y  (G x L)  stream D from HBM once
+//     each (HBM-bound: 2L/4 = 20 flop per byte).  This file holds the fp32 CUDA-core version (cp.async
+//     3-stage pipelines, conflict-free 128-bit shared-memory reads).
+//   * centring is implicit:  Dc Q = D Q - 1 (mean(D Q)),  and  Dc^T Y' = D^T Y' - mu (1^T Y')  where the
+//     second term is applied to the G x L result from the exactly accumulated column sums.
+//   * sklearn's LU normaliser only fixes the span and the conditioning; the span-equivalent
+//     CholeskyQR (Gram in float64 -> Cholesky -> triangular inverse) is used on both the tall and the
+//     small side.  svd(B) is taken from the float64 Jacobi eigen-decomposition of B B^T (L x L).
+#include "dd_internal.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small-workspace layout (doubles), sized for LP = 64
+constexpr int kMaxLP = 64;
+constexpr int OFF_GRAM = 0;
+constexpr int OFF_RINV = OFF_GRAM + kMaxLP * kMaxLP;
+constexpr int OFF_CSUM = OFF_RINV + kMaxLP * kMaxLP;   // column sums of Y
+constexpr int OFF_SSUM = OFF_CSUM + kMaxLP;            // column sums of the orthonormalised Y'
+constexpr int OFF_EVEC = OFF_SSUM + kMaxLP;
+constexpr int OFF_EVAL = OFF_EVEC + kMaxLP * kMaxLP;
+constexpr int OFF_T = OFF_EVAL + kMaxLP;               // L x KP embedding transform
+constexpr int OFF_FLAG = OFF_T + kMaxLP * kMaxLP;      // != 0: a factorisation broke down
+constexpr int SMALL_DOUBLES = OFF_FLAG + 8;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Y (A x LP) = D (A x ld) * Qt^T,  Qt is LP x ld (Q transposed; pad rows / columns are zero)
+constexpr int G1_BM = 128, G1_BK = 32, G1_ST = 36, G1_NS = 3;
+template <int LP>
+constexpr size_t gemm1_smem() { return sizeof(float) * G1_NS * (G1_BM + LP) * G1_ST; }
+
+template <int LP>
+__global__ void __launch_bounds__(128) k_gemm_dq(const float *__restrict__ D, const float *__restrict__ Qt,
+                                                 float *__restrict__ Y, int64_t n_rows, int ld) {
+    constexpr int CPT = LP / 8;
+    extern __shared__ __align__(16) float sm[];
+    float *As = sm;
+    float *Bs = sm + G1_NS * G1_BM * G1_ST;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, rg = lane >> 3, cg = lane & 7;
+    const int64_t row0 = (int64_t)blockIdx.x * G1_BM;
+    const int nk = ld / G1_BK;
+
+    auto load_stage = [&](int s, int kt) {
+        const int k0 = kt * G1_BK;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int c = tid + 128 * i, r = c >> 3, kc = c & 7;
+            const int64_t grow = row0 + r;
+            const bool ok = grow < n_rows;
+            cp_async16(As + (s * G1_BM + r) * G1_ST + kc * 4, D + (ok ? grow : 0) * ld + k0 + kc * 4, ok);
+        }
+        for (int c = tid; c < LP * 8; c += 128) {
+            const int r = c >> 3, kc = c & 7;
+            cp_async16(Bs + (s * LP + r) * G1_ST + kc * 4, Qt + (int64_t)r * ld + k0 + kc * 4, true);
+        }
+    };
+
+    float acc[8][CPT];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < CPT; j++) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < G1_NS - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<G1_NS - 2>();
+        __syncthreads();
+        const int nxt = kt + G1_NS - 1;
+        if (nxt < nk) load_stage(nxt % G1_NS, nxt);
+        cp_async_commit();
+        const int s = kt % G1_NS;
+        const float *a_base = As + (s * G1_BM + warp * 32 + rg) * G1_ST;
+        const float *b_base = Bs + (s * LP + cg) * G1_ST;
+#pragma unroll
+        for (int kk = 0; kk < G1_BK; kk += 4) {
+            float4 a[8], b[CPT];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const float4 *>(a_base + 4 * i * G1_ST + kk);
+#pragma unroll
+            for (int j = 0; j < CPT; j++) b[j] = *reinterpret_cast<const float4 *>(b_base + 8 * j * G1_ST + kk);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < CPT; j++) {
+                    acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int64_t row = row0 + warp * 32 + rg + 4 * i;
+        if (row < n_rows) {
+#pragma unroll
+            for (int j = 0; j < CPT; j++) Y[row * LP + cg + 8 * j] = acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zacc (ld x LP, double) += D[r_begin:r_end, :]^T * Y[r_begin:r_end, :]   (split over row ranges)
+constexpr int G2_BG = 256, G2_BK = 32, G2_NS = 3;
+template <int LP>
+constexpr size_t gemm2_smem() { return sizeof(float) * G2_NS * G2_BK * (G2_BG + LP); }
+
+template <int LP>
+__global__ void __launch_bounds__(128) k_gemm_dty(const float *__restrict__ D, const float *__restrict__ Y,
+                                                  double *__restrict__ Zacc, int64_t n_rows, int ld,
+                                                  int rows_per_split) {
+    constexpr int CPT = LP / 4;
+    constexpr int YCH = LP / 4;  // 16-byte chunks per row of Y
+    extern __shared__ __align__(16) float sm[];
+    float *As = sm;                               // [NS][BK][BG]
+    float *Bs = sm + G2_NS * G2_BK * G2_BG;       // [NS][BK][LP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane & 7, cq = lane >> 3;
+    const int g0 = blockIdx.x * G2_BG;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r_end = min(n_rows, r_begin + rows_per_split);
+    const int nk = (int)((r_end - r_begin + G2_BK - 1) / G2_BK);
+
+    auto load_stage = [&](int s, int kt) {
+        const int64_t rbase = r_begin + (int64_t)kt * G2_BK;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int c = tid + 128 * i, r = c >> 6, gc = c & 63;
+            const int64_t grow = rbase + r;
+            const int gcol = g0 + gc * 4;
+            const bool ok = grow < r_end && gcol < ld;
+            cp_async16(As + (s * G2_BK + r) * G2_BG + gc * 4, D + (ok ? grow * ld + gcol : 0), ok);
+        }
+        for (int c = tid; c < G2_BK * YCH; c += 128) {
+            const int r = c / YCH, cc = c % YCH;
+            const int64_t grow = rbase + r;
+            const bool ok = grow < r_end;
+            cp_async16(Bs + (s * G2_BK + r) * LP + cc * 4, Y + (ok ? grow * LP + cc * 4 : 0), ok);
+        }
+    };
+
+    float acc[8][CPT];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < CPT; j++) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < G2_NS - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<G2_NS - 2>();
+        __syncthreads();
+        const int nxt = kt + G2_NS - 1;
+        if (nxt < nk) load_stage(nxt % G2_NS, nxt);
+        cp_async_commit();
+        const int s = kt % G2_NS;
+        const float *a_ptr = As + s * G2_BK * G2_BG + warp * 64 + gq * 4;
+        const float *b_ptr = Bs + s * G2_BK * LP + cq * CPT;
+#pragma unroll 4
+        for (int k = 0; k < G2_BK; k++) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(a_ptr + k * G2_BG);
+            const float4 a1 = *reinterpret_cast<const float4 *>(a_ptr + k * G2_BG + 32);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 2) {
+                const float2 t = *reinterpret_cast<const float2 *>(b_ptr + k * LP + j);
+                b[j] = t.x;
+                b[j + 1] = t.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < CPT; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int gene = g0 + warp * 64 + gq * 4 + (i & 3) + (i >> 2) * 32;
+        if (gene < ld) {
+#pragma unroll
+            for (int j = 0; j < CPT; j++) atomicAdd(Zacc + (int64_t)gene * LP + cq * CPT + j, (double)acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram matrix (and column sums) of a tall matrix in float64.
+//   MODE 0: X = Y (float, n x LP).
+//   MODE 1: X = Zacc - mu * ssum^T (double, n = ld rows = genes), written back in place.
+constexpr int GR_ROWS = 64;
+template <int LP, int MODE>
+__global__ void __launch_bounds__(256) k_gram(const float *__restrict__ Yf, double *__restrict__ Zd, int64_t n_rows,
+                                              const double *__restrict__ colsum_mu, double inv_n_mu,
+                                              const double *__restrict__ ssum, double *__restrict__ gram,
+                                              double *__restrict__ csum) {
+    constexpr int BPT = LP / 8;
+    __shared__ double tile[GR_ROWS][LP + 1];
+    const int tid = threadIdx.x, grp = tid >> 6, ti = (tid & 63) >> 3, tj = tid & 7;
+    double acc[BPT][BPT];
+#pragma unroll
+    for (int a = 0; a < BPT; a++)
+#pragma unroll
+        for (int b = 0; b < BPT; b++) acc[a][b] = 0.0;
+    double cs = 0.0;
+    const int64_t n_tiles = (n_rows + GR_ROWS - 1) / GR_ROWS;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * GR_ROWS;
+        for (int e = tid; e < GR_ROWS * LP; e += 256) {
+            const int r = e / LP, c = e % LP;
+            const int64_t row = r0 + r;
+            double v = 0.0;
+            if (row < n_rows) {
+                if (MODE == 0) {
+                    v = (double)Yf[row * LP + c];
+                } else {
+                    v = Zd[row * LP + c] - (colsum_mu[row] * inv_n_mu) * ssum[c];
+                    Zd[row * LP + c] = v;
+                }
+            }
+            tile[r][c] = v;
+        }
+        __syncthreads();
+        for (int r = grp * 16; r < grp * 16 + 16; r++) {
+            double a[BPT], b[BPT];
+#pragma unroll
+            for (int x = 0; x < BPT; x++) {
+                a[x] = tile[r][ti * BPT + x];
+                b[x] = tile[r][tj * BPT + x];
+            }
+#pragma unroll
+            for (int x = 0; x < BPT; x++)
+#pragma unroll
+                for (int y = 0; y < BPT; y++) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+        }
+        if (tid < LP) {
+            for (int r = 0; r < GR_ROWS; r++) cs += tile[r][tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < BPT; x++)
+#pragma unroll
+        for (int y = 0; y < BPT; y++) atomicAdd(gram + (ti * BPT + x) * LP + tj * BPT + y, acc[x][y]);
+    if (tid < LP) atomicAdd(csum + tid, cs);
+}
+
+// Centre the Gram matrix (optional), Cholesky  Gc = R^T R,  Rinv = R^-1 (upper triangular).  One CTA of
+// 64 threads; thread j owns column j.
+__global__ void k_chol_inv(double *__restrict__ gram, const double *__restrict__ csum, double n_rows, int centre,
+                           int L, int LP, double *__restrict__ rinv, double *__restrict__ flag) {
+    __shared__ double R[kMaxLP][kMaxLP + 1];
+    const int j = threadIdx.x;
+    for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) rinv[e] = 0.0;
+    if (j < L) {
+        for (int i = 0; i < L; i++) {
+            double g = gram[i * LP + j];
+            if (centre) g -= csum[i] * csum[j] / n_rows;
+            R[i][j] = g;
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < L; k++) {
+        // row k of R from rows 0..k-1
+        if (j >= k && j < L) {
+            double s = R[k][j];
+            for (int p = 0; p < k; p++) s -= R[p][k] * R[p][j];
+            R[k][j] = s;  // un-normalised
+        }
+        __syncthreads();
+        const double d = R[k][k];
+        __syncthreads();
+        double piv;
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (j == 0) flag[0] = 1.0;
+            piv = 1.0;
+        } else {
+            piv = sqrt(d);
+        }
+        if (j >= k && j < L) R[k][j] = (j == k) ? piv : R[k][j] / piv;
+        __syncthreads();
+    }
+    // back substitution: thread j solves column j of R^-1 (kept in global memory, own column only)
+    if (j < L) {
+        for (int i = j; i >= 0; i--) {
+            if (i == j) {
+                rinv[i * LP + j] = 1.0 / R[i][i];
+            } else {
+                double s = 0.0;
+                for (int p = i + 1; p <= j; p++) s += R[i][p] * rinv[p * LP + j];
+                rinv[i * LP + j] = -s / R[i][i];
+            }
+        }
+    }
+}
+
+// Apply the triangular inverse.
+//   MODE 0 (tall): Y <- (Y - csum/n) Rinv in place (float), ssum += column sums of the new Y.
+//   MODE 1 (small): Qt[j][g] = (Z Rinv)[g][j] (float, transposed), and Zacc is cleared for the next pass.
+template <int LP, int MODE>
+__global__ void __launch_bounds__(128) k_apply(float *__restrict__ Yf, double *__restrict__ Zd, int64_t n_rows,
+                                               int L, const double *__restrict__ rinv,
+                                               const double *__restrict__ csum, double inv_n,
+                                               double *__restrict__ ssum, float *__restrict__ Qt, int ld) {
+    __shared__ double Rs[LP][LP];
+    __shared__ double ms[LP];
+    for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) Rs[e / LP][e % LP] = rinv[e];
+    if (threadIdx.x < LP) ms[threadIdx.x] = (MODE == 0) ? csum[threadIdx.x] * inv_n : 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n_rows + 31) / 32 * 32;  // keep warps converged for the shuffles
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_pad; row += stride) {
+        const bool ok = row < n_rows;
+        double y[LP];
+#pragma unroll
+        for (int i = 0; i < LP; i++) {
+            if (MODE == 0)
+                y[i] = ok ? (double)Yf[row * LP + i] - ms[i] : 0.0;
+            else
+                y[i] = ok ? Zd[row * LP + i] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < LP; j++) {
+            double o = 0.0;
+#pragma unroll
+            for (int i = 0; i <= j; i++) o = fma(y[i], Rs[i][j], o);
+            const float of = (float)o;
+            if (MODE == 0) {
+                if (ok) Yf[row * LP + j] = of;
+                double s = ok ? (double)of : 0.0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane == 0 && j < L) atomicAdd(ssum + j, s);
+            } else {
+                if (ok) {
+                    Qt[(int64_t)j * ld + row] = of;
+                    Zd[row * LP + j] = 0.0;
+                }
+            }
+        }
+    }
+}
+
+// Symmetric eigen-decomposition of the L x L Gram matrix by parallel-ordered cyclic Jacobi (float64),
+// eigenvalues sorted in decreasing order.  One CTA, 256 threads.
+__global__ void __launch_bounds__(256) k_jacobi(const double *__restrict__ gram, int L, int LP,
+                                                double *__restrict__ evec, double *__restrict__ eval) {
+    extern __shared__ double jac_sm[];
+    double (*Am)[kMaxLP + 1] = reinterpret_cast<double (*)[kMaxLP + 1]>(jac_sm);
+    double (*Vm)[kMaxLP + 1] = reinterpret_cast<double (*)[kMaxLP + 1]>(jac_sm + kMaxLP * (kMaxLP + 1));
+    __shared__ double cs_c[kMaxLP / 2], cs_s[kMaxLP / 2];
+    __shared__ int pp[kMaxLP / 2], qq[kMaxLP / 2];
+    __shared__ int pos[kMaxLP];
+    __shared__ double offmax;
+    const int tid = threadIdx.x;
+    const int n = (L + 1) & ~1;  // even number of players; index L (if padded) is a bye
+    for (int e = tid; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        Am[i][j] = (i < L && j < L) ? gram[i * LP + j] : 0.0;
+        Vm[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    if (tid < n) pos[tid] = tid;
+    __syncthreads();
+    const int half = n / 2;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        if (tid == 0) offmax = 0.0;
+        __syncthreads();
+        for (int round = 0; round < n - 1; round++) {
+            if (tid < half) {
+                int p = pos[tid], q = pos[n - 1 - tid];
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < L) {
+                    const double apq = Am[p][q];
+                    const double scale = fabs(Am[p][p]) + fabs(Am[q][q]);
+                    if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * scale) {
+                        const double tau = (Am[q][q] - Am[p][p]) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                        if (fabs(apq) > 1e-14 * scale) offmax = 1.0;  // benign race: any writer sets it
+                    }
+                }
+                pp[tid] = p; qq[tid] = q; cs_c[tid] = c; cs_s[tid] = s;
+            }
+            __syncthreads();
+            // columns p, q of A and V
+            for (int e = tid; e < half * n; e += blockDim.x) {
+                const int t = e / n, i = e % n;
+                const int p = pp[t], q = qq[t];
+                const double c = cs_c[t], s = cs_s[t];
+                const double aip = Am[i][p], aiq = Am[i][q];
+                Am[i][p] = c * aip - s * aiq;
+                Am[i][q] = s * aip + c * aiq;
+                const double vip = Vm[i][p], viq = Vm[i][q];
+                Vm[i][p] = c * vip - s * viq;
+                Vm[i][q] = s * vip + c * viq;
+            }
+            __syncthreads();
+            // rows p, q of A
+            for (int e = tid; e < half * n; e += blockDim.x) {
+                const int t = e / n, j = e % n;
+                const int p = pp[t], q = qq[t];
+                const double c = cs_c[t], s = cs_s[t];
+                const double apj = Am[p][j], aqj = Am[q][j];
+                Am[p][j] = c * apj - s * aqj;
+                Am[q][j] = s * apj + c * aqj;
+            }
+            __syncthreads();
+            // rotate the tournament: position 0 stays, the rest shift by one
+            int nxt = 0;
+            if (tid < n && tid > 0) nxt = pos[tid == 1 ? n - 1 : tid - 1];
+            __syncthreads();
+            if (tid < n && tid > 0) pos[tid] = nxt;
+            __syncthreads();
+        }
+        const bool done = offmax == 0.0;
+        __syncthreads();
+        if (done) break;
+    }
+    // sort eigenvalues (descending) by rank counting; ties by index
+    if (tid < L) {
+        const double d = Am[tid][tid];
+        int rank = 0;
+        for (int k = 0; k < L; k++) {
+            const double dk = Am[k][k];
+            rank += (dk > d) || (dk == d && k < tid);
+        }
+        eval[rank] = d;
+        for (int i = 0; i < L; i++) evec[i * LP + rank] = Vm[i][tid];
+    }
+}
+
+constexpr size_t kJacobiSmem = sizeof(double) * 2 * kMaxLP * (kMaxLP + 1);
+
+// svd_flip(u_based_decision=False) + embedding transform.  W = Z Uhat = V S; the sign of component j is
+// the sign of the largest-|.| entry of column j of W (first index wins ties).  T[i][c] = Uhat[i][c] s_c sign_c
+// for c < C, zero for the padding columns up to KP.  One CTA, 256 threads.
+template <int LP>
+__global__ void __launch_bounds__(256) k_signs_transform(const double *__restrict__ Zd, int n_genes, int L, int C,
+                                                         int KP, const double *__restrict__ evec,
+                                                         const double *__restrict__ eval, double *__restrict__ T,
+                                                         double *__restrict__ sing_out) {
+    __shared__ double Us[LP][LP + 1];
+    __shared__ double best_v[256];
+    __shared__ int best_i[256];
+    __shared__ double sign_s[LP];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < LP * LP; e += 256) Us[e / LP][e % LP] = evec[e];
+    __syncthreads();
+    for (int j = 0; j < C; j++) {
+        double bv = -1.0, bs = 0.0;
+        int bi = 0x7fffffff;
+        for (int g = tid; g < n_genes; g += 256) {
+            double w = 0.0;
+            for (int i = 0; i < L; i++) w = fma(Zd[(int64_t)g * LP + i], Us[i][j], w);
+            const double aw = fabs(w);
+            if (aw > bv) { bv = aw; bi = g; bs = w; }
+        }
+        best_v[tid] = bv;
+        best_i[tid] = bi;
+        __syncthreads();
+        // the signed value travels in a second pass to keep shared memory small
+        for (int off = 128; off > 0; off >>= 1) {
+            if (tid < off) {
+                const double ov = best_v[tid + off];
+                const int oi = best_i[tid + off];
+                if (ov > best_v[tid] || (ov == best_v[tid] && oi < best_i[tid])) {
+                    best_v[tid] = ov;
+                    best_i[tid] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        if (best_i[0] == bi && bv >= 0.0) sign_s[j] = (bs < 0.0) ? -1.0 : 1.0;
+        __syncthreads();
+    }
+    for (int e = tid; e < LP * KP; e += 256) {
+        const int i = e / KP, c = e % KP;
+        double v = 0.0;
+        if (i < L && c < C) v = Us[i][c] * sqrt(fmax(eval[c], 0.0)) * sign_s[c];
+        T[e] = v;
+    }
+    if (tid < C) sing_out[tid] = sqrt(fmax(eval[tid], 0.0));
+}
+
+// X_pca (A x KP float, zero padded beyond C) = Yq T
+template <int LP, int KP>
+__global__ void __launch_bounds__(128) k_embed(const float *__restrict__ Yq, int64_t n_rows, const double *__restrict__ T,
+                                               float *__restrict__ emb) {
+    __shared__ double Ts[LP][KP];
+    for (int e = threadIdx.x; e < LP * KP; e += blockDim.x) Ts[e / KP][e % KP] = T[e];
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double y[LP];
+#pragma unroll
+    for (int i = 0; i < LP; i++) y[i] = (double)Yq[row * LP + i];
+#pragma unroll
+    for (int c4 = 0; c4 < KP; c4 += 4) {
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < LP; i++) s = fma(y[i], Ts[i][c4 + q], s);
+            o[q] = (float)s;
+        }
+        *reinterpret_cast<float4 *>(emb + row * KP + c4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int LP>
+int run_pca(dd_handle *h, int n_power_iter) {
+    const int64_t A = h->A;
+    const int ld = (int)h->ld;
+    const int L = h->L, C = h->C, KP = h->KP;
+    double *sm = h->d_small;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_gemm_dq<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm1_smem<LP>());
+        cudaFuncSetAttribute(k_gemm_dty<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm2_smem<LP>());
+        cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJacobiSmem);
+        attr_set = true;
+    }
+    const int grid1 = (int)((A + G1_BM - 1) / G1_BM);
+    const int gblocks = (ld + G2_BG - 1) / G2_BG;
+    int splits = std::max(1, (h->num_sms * 4 + gblocks - 1) / gblocks);
+    int rows_per_split = (int)((A + splits - 1) / splits);
+    rows_per_split = std::max(G2_BK, (rows_per_split + G2_BK - 1) / G2_BK * G2_BK);
+    splits = (int)((A + rows_per_split - 1) / rows_per_split);
+    const int tall_grid = h->num_sms * 2;
+    const double inv_A = 1.0 / (double)A;
+
+    DD_CUDA(h, cudaMemsetAsync(sm, 0, sizeof(double) * SMALL_DOUBLES, h->stream));
+    DD_CUDA(h, cudaMemsetAsync(h->d_Zacc, 0, sizeof(double) * (size_t)ld * LP, h->stream));
+    DD_TRY(dd_dev_colstats(h, false));  // mu = colsum / A
+
+    for (int it = 0; it <= n_power_iter; it++) {
+        const bool last = it == n_power_iter;
+        // Y = D Q
+        DD_LAUNCH(h, "gemm_dq", k_gemm_dq<LP>, grid1, 128, gemm1_smem<LP>(), h->d_dense, h->d_Qt, h->d_Y, A, ld);
+        // Y' = orth(Y - mean)
+        DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
+        DD_CUDA(h, cudaMemsetAsync(sm + OFF_CSUM, 0, sizeof(double) * 2 * kMaxLP, h->stream));  // csum + ssum
+        DD_LAUNCH(h, "gram_tall", (k_gram<LP, 0>), tall_grid, 256, 0, h->d_Y, nullptr, A, nullptr, 0.0, nullptr,
+                  sm + OFF_GRAM, sm + OFF_CSUM);
+        DD_LAUNCH(h, "chol_inv", k_chol_inv, 1, 64, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
+                  sm + OFF_FLAG);
+        DD_LAUNCH(h, "apply_tall", (k_apply<LP, 0>), tall_grid, 128, 0, h->d_Y, nullptr, A, L, sm + OFF_RINV,
+                  sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0);
+        // Z = Dc^T Y'
+        DD_LAUNCH(h, "gemm_dty", k_gemm_dty<LP>, dim3(gblocks, splits), 128, gemm2_smem<LP>(), h->d_dense, h->d_Y,
+                  h->d_Zacc, A, ld, rows_per_split);
+        DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
+        DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
+                  h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
+        if (!last) {
+            DD_LAUNCH(h, "chol_inv", k_chol_inv, 1, 64, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV,
+                      sm + OFF_FLAG);
+            DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
+                      sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld);
+        }
+    }
+    // svd(B) with B^T = Z:  B B^T = Z^T Z = gram
+    DD_LAUNCH(h, "jacobi", k_jacobi, 1, 256, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
+    DD_LAUNCH(h, "signs_transform", k_signs_transform<LP>, 1, 256, 0, h->d_Zacc, (int)h->G, L, C, KP, sm + OFF_EVEC,
+              sm + OFF_EVAL, sm + OFF_T, sm + OFF_CSUM /* singular values */);
+    const int egrid = (int)((A + 127) / 128);
+    if (KP == 32)
+        DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, h->d_Y, A, sm + OFF_T, h->d_emb);
+    else
+        DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, h->d_Y, A, sm + OFF_T, h->d_emb);
+    return DD_OK;
+}
+
+}  // namespace
+
+// Randomized PCA of the current dense matrix.  omega_host (G x n_random, row-major float32) may be
+// NULL to reuse the matrix uploaded by the previous call.
+int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter, const float *omega_host) {
+    if (!h->dense_valid) return dd_fail(h, DD_ERR_ARG, "pca: no dense matrix (call dd_normalise_log first)");
+    if (n_comp < 1 || n_random < n_comp || n_power_iter < 0) return dd_fail(h, DD_ERR_ARG, "pca: bad n_comp / n_random / n_power_iter");
+    if (n_random > kMaxLP) return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 > 64 is outside the B200 hot path");
+    if (n_random > h->G || n_random > h->A)
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 exceeds the matrix dimensions");
+    if (h->A < h->G)
+        return dd_fail(h, DD_ERR_UNSUPPORTED,
+                       "pca: fewer augmented cells than genes (sklearn's transposed randomized SVD) is outside the B200 hot path");
+    const int LP = n_random <= 40 ? 40 : 64;
+    const int KP = n_comp <= 32 ? 32 : 64;
+    const int64_t A = h->A, ld = h->ld;
+    if (A > h->cap_pca_rows || ld > h->cap_pca_cols || LP > h->cap_LP) {
+        const int64_t rows = std::max(A, h->cap_pca_rows), cols = std::max(ld, h->cap_pca_cols);
+        const int lp = std::max(LP, (int)h->cap_LP);
+        for (void *p : {(void *)h->d_Qt, (void *)h->d_Y, (void *)h->d_Zacc, (void *)h->d_small})
+            if (p) cudaFree(p);
+        h->d_Qt = nullptr; h->d_Y = nullptr; h->d_Zacc = nullptr; h->d_small = nullptr;
+        h->cap_pca_rows = h->cap_pca_cols = 0; h->cap_LP = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_Qt, sizeof(float) * 2 * lp * cols));  // Qt and the pristine Omega^T
+        DD_CUDA(h, cudaMalloc(&h->d_Y, sizeof(float) * rows * lp));
+        DD_CUDA(h, cudaMalloc(&h->d_Zacc, sizeof(double) * cols * lp));
+        DD_CUDA(h, cudaMalloc(&h->d_small, sizeof(double) * SMALL_DOUBLES));
+        h->cap_pca_rows = rows; h->cap_pca_cols = cols; h->cap_LP = lp;
+        h->L = 0;  // forces an Omega upload
+    }
+    float *omega_dev = h->d_Qt + (size_t)h->cap_LP * h->cap_pca_cols;
+    if (omega_host) {
+        std::vector<float> qt((size_t)LP * ld, 0.f);
+        for (int64_t g = 0; g < h->G; g++)
+            for (int j = 0; j < n_random; j++) qt[(size_t)j * ld + g] = omega_host[g * n_random + j];
+        DD_CUDA(h, cudaMemcpyAsync(omega_dev, qt.data(), sizeof(float) * LP * ld, cudaMemcpyHostToDevice, h->stream));
+        DD_CUDA(h, cudaStreamSynchronize(h->stream));  // qt is a temporary
+    } else if (h->L != n_random || h->LP != LP) {
+        return dd_fail(h, DD_ERR_ARG, "pca: omega is NULL but no matching test matrix was uploaded before");
+    }
+    h->L = n_random; h->LP = LP; h->C = n_comp;
+    DD_CUDA(h, cudaMemcpyAsync(h->d_Qt, omega_dev, sizeof(float) * LP * ld, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->KP != KP || A > h->cap_emb) {
+        if (h->d_emb) cudaFree(h->d_emb);
+        h->d_emb = nullptr; h->cap_emb = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_emb, sizeof(float) * A * KP));
+        h->cap_emb = A;
+    }
+    h->KP = KP;
+    int rc = (LP == 40) ? run_pca<40>(h, n_power_iter) : run_pca<64>(h, n_power_iter);
+    if (rc != DD_OK) return rc;
+    h->emb_rows = A;
+    h->emb_valid = true;
+    return DD_OK;
+}
+
+// Checks the factorisation flag (synchronises the stream).
+int dd_pca_check(dd_handle *h) {
+    double flag = 0.0;
+    DD_CUDA(h, cudaMemcpyAsync(&flag, h->d_small + OFF_FLAG, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (flag != 0.0) {
+        h->emb_valid = false;
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: rank-deficient range (Cholesky breakdown); the matrix has fewer than n_components + 10 independent directions");
+    }
+    return DD_OK;
+}
+
+// Queue an asynchronous copy of the factorisation flag into (pinned) host memory.
+int dd_pca_flag_copy(dd_handle *h, double *host_flag) {
+    DD_CUDA(h, cudaMemcpyAsync(host_flag, h->d_small + OFF_FLAG, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter, const float *omega,
+                      float *emb_out, double *singular_values_out) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_pca: null handle");
+    if (!omega) return dd_fail(h, DD_ERR_ARG, "dd_pca: null omega");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_TRY(dd_stage_begin(h));
+    DD_TRY(dd_dev_pca(h, n_comp, n_random, n_power_iter, omega));
+    DD_TRY(dd_stage_end(h, "pca"));
+    DD_TRY(dd_pca_check(h));
+    if (emb_out)
+        DD_CUDA(h, cudaMemcpy2DAsync(emb_out, sizeof(float) * n_comp, h->d_emb, sizeof(float) * h->KP,
+                                     sizeof(float) * n_comp, h->A, cudaMemcpyDeviceToHost, h->stream));
+    if (singular_values_out)
+        DD_CUDA(h, cudaMemcpyAsync(singular_values_out, h->d_small + OFF_CSUM, sizeof(double) * n_comp,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+extern "C" int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const float *emb) {
+    if (!h || !emb || n_rows <= 0 || n_comp <= 0) return dd_fail(h, DD_ERR_ARG, "dd_upload_embedding: bad arguments");
+    if (n_comp > 64) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_upload_embedding: more than 64 components");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    const int KP = n_comp <= 32 ? 32 : 64;
+    if (h->KP != KP || n_rows > h->cap_emb) {
+        if (h->d_emb) cudaFree(h->d_emb);
+        h->d_emb = nullptr; h->cap_emb = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_emb, sizeof(float) * n_rows * KP));
+        h->cap_emb = n_rows;
+    }
+    h->KP = KP; h->C = n_comp;
+    DD_CUDA(h, cudaMemsetAsync(h->d_emb, 0, sizeof(float) * n_rows * KP, h->stream));
+    DD_CUDA(h, cudaMemcpy2DAsync(h->d_emb, sizeof(float) * KP, emb, sizeof(float) * n_comp, sizeof(float) * n_comp,
+                                 n_rows, cudaMemcpyHostToDevice, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->emb_rows = n_rows;
+    h->emb_valid = true;
+    return DD_OK;
+}

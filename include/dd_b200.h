@@ -1,0 +1,164 @@
+/* dd_b200.h -- C ABI of libdd_b200.so: the B200-native replacement for the per-iteration hot path
+ * of DoubletDetection's BoostClassifier.fit (reference: doubletdetection/doubletdetection.py).
+ *
+ * The reference is pure Python and has no FFI of its own; the seam this ABI replaces is the
+ * private pair BoostClassifier._one_fit() / _createDoublets() (doubletdetection.py:274-402) and
+ * the loop around it (doubletdetection.py:186-198).  Each entry point below names the reference
+ * lines whose arithmetic it performs.  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 on success, non-zero on error
+ *    (DD_ERR_*); the message is available from dd_last_error(h) (or dd_last_error(NULL) when
+ *    no handle exists yet).  No exceptions cross the ABI.
+ *  - host pointers unless the name says "_dev"; the caller owns every buffer it passes in and
+ *    every output buffer (the library copies what it needs to the device).
+ *  - a handle is bound to one CUDA device and is NOT thread-safe; different handles are
+ *    independent.  Long calls do not touch Python, so ctypes releases the GIL around them.
+ *  - there is no CPU fallback: without a CUDA device dd_create fails with DD_ERR_CUDA.
+ *  - matrices are row-major.  The augmented matrix has A = N + M rows: the N original cells
+ *    first, then the M synthetic doublets (doubletdetection.py:292).
+ */
+#ifndef DD_B200_H
+#define DD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_OK 0
+#define DD_ERR_ARG 1     /* bad argument / call order            */
+#define DD_ERR_CUDA 2    /* CUDA runtime or driver error         */
+#define DD_ERR_UNSUPPORTED 3 /* shape / option outside the hot path */
+#define DD_ERR_NOMEM 4
+
+typedef struct dd_handle dd_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int dd_create(int device, dd_handle **out);
+void dd_destroy(dd_handle *h);
+const char *dd_last_error(const dd_handle *h);
+/* ABI version of the loaded library (bumped on any signature change). */
+int dd_abi_version(void);
+
+/* ---- fit() prologue, doubletdetection.py:178-184 ---------------------------------------
+ * Upload the (already float32, canonical: sorted, duplicate-free) CSR count matrix
+ * `_raw_counts` (N cells x G genes).  Computes on the device `_lib_size` (:182) and keeps the
+ * raw rows resident; the memoised L1-normalised copy (:183-184) is never materialised -- the
+ * normalise kernel divides by the row sum on the fly with the same rounding. */
+int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32_t *indptr,
+                     const int32_t *indices, const float *data);
+/* `_lib_size` (float32[N]) as computed on the device. */
+int dd_get_lib_size(dd_handle *h, float *lib_size_out);
+
+/* ---- _createDoublets(), doubletdetection.py:397-399 ------------------------------------
+ * parents: int64[M*2] (the `choices` array of :394, drawn by the caller from its PCG64 stream).
+ * Builds `_raw_synthetics` = raw[parents[:,0]] + raw[parents[:,1]] as canonical CSR on the
+ * device (sorted merge, values added where both parents express a gene). */
+int dd_create_doublets(dd_handle *h, int64_t n_synth, const int64_t *parents);
+int dd_synth_nnz(dd_handle *h, int64_t *nnz_out);
+/* Copy the synthetic CSR back: indptr int32[M+1], indices int32[nnz], data float[nnz]. */
+int dd_download_synthetics(dd_handle *h, int32_t *indptr_out, int32_t *indices_out, float *data_out);
+/* Synthetic library sizes (:288), float32[M]. */
+int dd_get_synth_lib_size(dd_handle *h, float *lib_size_out);
+
+/* ---- _one_fit() normalisation, doubletdetection.py:286-295 -----------------------------
+ * Dense float32 A x G matrix  log(x / rowsum * median + pseudocount)  for originals followed by
+ * synthetics.  `median` = np.median(aug_lib_size) (:293) computed by the caller (or by
+ * dd_median_lib_size below, same value).  pseudocount == 1 (the sparse log1p branch, :296-297)
+ * is DD_ERR_UNSUPPORTED. */
+int dd_median_lib_size(dd_handle *h, float *median_out);
+int dd_normalise_log(dd_handle *h, float median, float pseudocount);
+/* optional sc.pp.scale(max_value) on the dense matrix, doubletdetection.py:302-303.
+ * max_value <= 0 means no clipping. */
+int dd_standard_scale(dd_handle *h, float max_value);
+/* Copy rows [row0, row0+n_rows) of the dense matrix back (float32, n_rows x G, row-major). */
+int dd_download_dense(dd_handle *h, int64_t row0, int64_t n_rows, float *out);
+/* Test hook: replace the dense matrix by a caller-supplied one (A x G float32). */
+int dd_upload_dense(dd_handle *h, int64_t n_rows, int64_t n_genes, const float *dense);
+
+/* ---- sc.tl.pca(..., svd_solver="auto") == sklearn randomized PCA, doubletdetection.py:309-314
+ * omega: float32[G * n_random] row-major, the Gaussian test matrix sklearn draws
+ * (RandomState(random_state).normal(size=(G, n_comp+10)) cast to float32).  n_power_iter = 7 or
+ * 4 (sklearn's "auto").  Leaves the float32 A x n_comp embedding on the device; emb_out may be
+ * NULL.  singular_values_out (float64[n_comp]) may be NULL. */
+int dd_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter, const float *omega,
+           float *emb_out, double *singular_values_out);
+/* Test hook: replace the embedding by a caller-supplied one (A x n_comp float32). */
+int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const float *emb);
+
+/* ---- sc.pp.neighbors(n_neighbors=k) exact kNN, doubletdetection.py:331-336 -------------
+ * Exact Euclidean k nearest neighbours of every augmented cell in the embedding; column 0 is
+ * the cell itself (distance 0), then the k-1 nearest others by (distance, index).
+ * idx_out int32[A*k], dist_out float32[A*k] (may be NULL). */
+int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
+
+/* ---- clustering call, doubletdetection.py:337-343 (host) -------------------------------
+ * Louvain (RB configuration null model, resolution gamma, unweighted, seeded) on the symmetrised
+ * kNN pattern -- what sc.tl.louvain(resolution, random_state, directed=False) optimises.  The
+ * louvain package is absent from the image; the algorithm is specified in oracle/louvain_ref.py.
+ * labels_out int32[n], 0 = largest community.  No handle: pure host code, thread-safe. */
+int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
+                   int32_t *labels_out, int32_t *n_communities_out);
+/* Same on an explicit symmetric CSR graph (weights may be NULL = unweighted). */
+int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                   double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
+
+/* ---- scoring, doubletdetection.py:344-383 (host) ----------------------------------------
+ * labels int32[n_cells + n_synth]; scores_out / log_p_out float64[n_cells]:
+ * synth fraction of the cell's community and hypergeom.logsf(k, A, M, size); NaN where the
+ * label is negative. */
+int dd_score(int64_t n_cells, int64_t n_synth, const int32_t *labels, double *scores_out, double *log_p_out);
+/* scipy.stats.hypergeom.logsf(k, M, n, N) for one argument tuple. */
+double dd_hypergeom_logsf(int64_t k, int64_t M, int64_t n, int64_t N);
+
+/* ---- the loop of fit(), doubletdetection.py:192-198 -------------------------------------
+ * Runs n_iters iterations of _one_fit for the uploaded counts: GPU stages back to back on the
+ * handle's stream, clustering + scoring of finished iterations on `n_host_threads` host workers
+ * concurrently with the GPU work of the next ones.
+ *   parents      int64[n_iters * M * 2]   all iterations' `choices`, drawn sequentially by the caller
+ *   omega        float32[G * n_random]
+ * outputs (caller allocated):
+ *   scores_out, log_p_out   float64[n_iters * N]
+ *   communities_out         int32[n_iters * N]
+ *   synth_communities_out   int32[n_iters * M]
+ *   stage_ms_out            float64[8] or NULL: GPU milliseconds summed over iterations for
+ *                           {doublets, normalise, scale, pca, knn, d2h, 0, 0}
+ */
+typedef struct dd_fit_params {
+    int32_t n_iters;
+    int64_t n_synth;
+    float pseudocount;
+    int32_t standard_scaling; /* 0 / 1 */
+    float scale_max_value;    /* 15 in the reference */
+    int32_t n_comp;
+    int32_t n_random;
+    int32_t n_power_iter;
+    int32_t knn_k;            /* 10 in the reference */
+    double resolution;        /* 4 in the reference  */
+    uint64_t seed;            /* random_state        */
+    int32_t n_host_threads;
+    int32_t iter_begin;       /* run iterations [iter_begin, iter_end) of the n_iters drawn */
+    int32_t iter_end;
+} dd_fit_params;
+
+int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int64_t *parents, const float *omega,
+                      double *scores_out, double *log_p_out, int32_t *communities_out,
+                      int32_t *synth_communities_out, double *stage_ms_out);
+
+/* ---- introspection used by bench.py -------------------------------------------------------
+ * Number of kernels this library has launched on the handle since creation. */
+int64_t dd_kernel_launches(const dd_handle *h);
+/* Milliseconds of the most recent call of the named stage measured with CUDA events on the
+ * handle's stream ("doublets", "normalise", "scale", "pca", "knn"); < 0 if unknown. */
+double dd_last_stage_ms(const dd_handle *h, const char *stage);
+/* Per-kernel accumulated device time (CUDA events around each launch) when profiling is on. */
+int dd_set_kernel_timing(dd_handle *h, int32_t on);
+int dd_get_kernel_timing(dd_handle *h, const char *kernel, double *total_ms_out, int64_t *launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DD_B200_H */
