@@ -84,6 +84,7 @@ SIGNATURES = {
     "dd_last_stage_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_char_p]),
     "dd_set_kernel_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "dd_get_kernel_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, c_f64p, c_i64p]),
+    "dd_kernel_timing_report": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
 }
 
 _lib = None
@@ -333,6 +334,17 @@ class Handle:
 
     def set_kernel_timing(self, on):
         self._check(self._lib.dd_set_kernel_timing(self._h, int(bool(on))))
+
+    def kernel_timing_report(self):
+        """{kernel name: (total_ms, launches)} since timing was switched on."""
+        need = self._lib.dd_kernel_timing_report(self._h, None, 0)
+        buf = ctypes.create_string_buffer(int(need) + 16)
+        self._lib.dd_kernel_timing_report(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out
 
     def kernel_timing(self, kernel):
         ms = ctypes.c_double(0)

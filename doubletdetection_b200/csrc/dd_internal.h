@@ -21,6 +21,12 @@ struct dd_kernel_stat {
     int64_t launches = 0;
 };
 
+// one timed launch: events are recorded without synchronising and resolved when the timing is queried
+struct dd_timed_launch {
+    const char *name;  // string literal
+    cudaEvent_t start, stop;
+};
+
 struct dd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -77,6 +83,8 @@ struct dd_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t stage_ev0 = nullptr, stage_ev1 = nullptr;
     std::map<std::string, dd_kernel_stat> kstats;
+    std::vector<dd_timed_launch> pending;    // recorded, not yet resolved
+    std::vector<cudaEvent_t> event_pool;     // recycled events
     std::map<std::string, double> stage_ms;
 };
 

@@ -1,6 +1,7 @@
 // handle.cu -- lifetime, error reporting, launch accounting and stage timers of libdd_b200.so.
 #include "dd_internal.h"
 
+#include <algorithm>
 #include <cstring>
 
 static thread_local std::string g_error;
@@ -13,25 +14,51 @@ int dd_fail(dd_handle *h, int code, const std::string &msg) {
     return code;
 }
 
+static cudaEvent_t pool_get(dd_handle *h) {
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Per-kernel timing records an event pair around every launch WITHOUT synchronising, so the pipeline
+// runs as it does untimed; the pairs are resolved when the numbers are read.
 void dd_launch_begin(dd_handle *h) {
-    if (h->timing) cudaEventRecord(h->ev0, h->stream);
+    if (!h->timing) return;
+    dd_timed_launch t{nullptr, pool_get(h), pool_get(h)};
+    cudaEventRecord(t.start, h->stream);
+    h->pending.push_back(t);
 }
 
 int dd_launch_end(dd_handle *h, const char *name) {
     cudaError_t e = cudaGetLastError();
+    if (h->timing && !h->pending.empty() && h->pending.back().name == nullptr) {
+        h->pending.back().name = name;
+        cudaEventRecord(h->pending.back().stop, h->stream);
+    }
     if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("launch of ") + name + ": " + cudaGetErrorString(e));
     h->launches++;
-    if (h->timing) {
-        cudaEventRecord(h->ev1, h->stream);
-        e = cudaEventSynchronize(h->ev1);
-        if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("kernel ") + name + ": " + cudaGetErrorString(e));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-        dd_kernel_stat &st = h->kstats[name];
-        st.total_ms += ms;
-        st.launches++;
-    }
     return DD_OK;
+}
+
+static void resolve_pending(dd_handle *h) {
+    if (h->pending.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (dd_timed_launch &t : h->pending) {
+        float ms = 0.f;
+        if (t.name && cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
+            dd_kernel_stat &st = h->kstats[t.name];
+            st.total_ms += ms;
+            st.launches++;
+        }
+        h->event_pool.push_back(t.start);
+        h->event_pool.push_back(t.stop);
+    }
+    h->pending.clear();
 }
 
 int dd_stage_begin(dd_handle *h) {
@@ -90,6 +117,8 @@ extern "C" void dd_destroy(dd_handle *h) {
                     h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx, h->d_knn_dist};
     for (void *p : bufs)
         if (p) cudaFree(p);
+    resolve_pending(h);
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stage_ev0) cudaEventDestroy(h->stage_ev0);
@@ -110,13 +139,31 @@ extern "C" double dd_last_stage_ms(const dd_handle *h, const char *stage) {
 
 extern "C" int dd_set_kernel_timing(dd_handle *h, int32_t on) {
     if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_set_kernel_timing: null handle");
+    resolve_pending(h);
     h->timing = on != 0;
     if (on) h->kstats.clear();
     return DD_OK;
 }
 
+// "name total_ms launches\n" for every kernel seen since timing was switched on; returns the number of
+// bytes needed (call with buf == NULL to size the buffer).
+extern "C" int64_t dd_kernel_timing_report(dd_handle *h, char *buf, int64_t buflen) {
+    if (!h) return -1;
+    resolve_pending(h);
+    std::string out;
+    for (auto &kv : h->kstats)
+        out += kv.first + " " + std::to_string(kv.second.total_ms) + " " + std::to_string(kv.second.launches) + "\n";
+    if (buf && buflen > 0) {
+        const int64_t n = std::min<int64_t>(buflen - 1, (int64_t)out.size());
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)out.size() + 1;
+}
+
 extern "C" int dd_get_kernel_timing(dd_handle *h, const char *kernel, double *total_ms_out, int64_t *launches_out) {
     if (!h || !kernel) return dd_fail(h, DD_ERR_ARG, "dd_get_kernel_timing: bad arguments");
+    resolve_pending(h);
     auto it = h->kstats.find(kernel);
     if (total_ms_out) *total_ms_out = it == h->kstats.end() ? 0.0 : it->second.total_ms;
     if (launches_out) *launches_out = it == h->kstats.end() ? 0 : it->second.launches;

@@ -154,9 +154,13 @@ int64_t dd_kernel_launches(const dd_handle *h);
 /* Milliseconds of the most recent call of the named stage measured with CUDA events on the
  * handle's stream ("doublets", "normalise", "scale", "pca", "knn"); < 0 if unknown. */
 double dd_last_stage_ms(const dd_handle *h, const char *stage);
-/* Per-kernel accumulated device time (CUDA events around each launch) when profiling is on. */
+/* Per-kernel accumulated device time when profiling is on: a CUDA event pair is recorded around each
+ * launch on the handle's stream without synchronising, and resolved when the numbers are read. */
 int dd_set_kernel_timing(dd_handle *h, int32_t on);
 int dd_get_kernel_timing(dd_handle *h, const char *kernel, double *total_ms_out, int64_t *launches_out);
+/* All kernels at once as text lines "name total_ms launches\n"; returns the buffer size needed
+ * (pass buf == NULL to query it), < 0 on error. */
+int64_t dd_kernel_timing_report(dd_handle *h, char *buf, int64_t buflen);
 
 #ifdef __cplusplus
 }

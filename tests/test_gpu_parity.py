@@ -1,0 +1,300 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the committed golden vectors.
+Every test needs a B200 (`-m gpu`); nothing here reads /root/reference."""
+
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp_sparse
+
+from conftest import GOLDEN_NAMES, golden_case, load_golden
+from oracle import datasets, louvain_c, pca_f64, reference_path, upstream
+
+pytestmark = pytest.mark.gpu
+
+STAGE_GOLDENS = ["c1_louvain", "c1_louvain_scaled", "hvg_replace", "structured_1500x300"]
+
+
+def _prologue(name):
+    counts, kw, _ = golden_case(name)
+    return reference_path.prologue(counts, max(0, kw.get("n_top_var_genes", 10000))), kw
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a, dtype=np.float64) - b).max() / np.abs(b).max()
+
+
+# ------------------------------------------------------------------------------ stage by stage
+@pytest.mark.parametrize("name", STAGE_GOLDENS)
+def test_lib_size_and_doublets_bit_exact(handle, name):
+    g = load_golden(name)
+    pro, _ = _prologue(name)
+    handle.upload_counts(pro["raw"])
+    np.testing.assert_array_equal(handle.lib_size(), pro["lib_size"])
+    handle.create_doublets(g["parents"][0])
+    syn = handle.download_synthetics()
+    np.testing.assert_array_equal(syn.indptr, g["synth0_indptr"])
+    np.testing.assert_array_equal(syn.indices, g["synth0_indices"])
+    np.testing.assert_array_equal(syn.data, g["synth0_data"])
+    n = pro["raw"].shape[0]
+    np.testing.assert_array_equal(handle.synth_lib_size(), g["n_counts0"][n:])
+    assert handle.median_lib_size() == np.median(g["n_counts0"])
+
+
+@pytest.mark.parametrize("name", STAGE_GOLDENS)
+def test_dense_normalised_matrix(handle, name):
+    g = load_golden(name)
+    pro, kw = _prologue(name)
+    handle.upload_counts(pro["raw"])
+    handle.create_doublets(g["parents"][0])
+    handle.normalise_log(handle.median_lib_size(), 0.1)
+    if kw.get("standard_scaling"):
+        raw_dense = handle.download_dense()
+        want_raw, _, _ = reference_path.normalise(
+            reference_path.create_doublets(pro["raw"], g["parents"][0]), pro["lib_size"], pro["normed"], 0.1)
+        np.testing.assert_allclose(raw_dense, want_raw, rtol=3e-6, atol=3e-7)
+        handle.standard_scale(15.0)
+        got = handle.download_dense()
+        # float32 log differs by <= 2 ulp between CUDA and numpy; scaling divides by a std of O(0.5)
+        np.testing.assert_allclose(got, g["pca_input0"], rtol=2e-5, atol=2e-5)
+    else:
+        got = handle.download_dense()
+        np.testing.assert_allclose(got, g["pca_input0"], rtol=3e-6, atol=3e-7)
+        # zeros of the count matrix all carry exactly log(pseudocount) as computed on the device
+        assert np.unique(got[g["pca_input0"] == np.log(np.float32(0.1))]).size == 1
+
+
+def test_standard_scale_on_uploaded_matrix(handle):
+    g = load_golden("c1_louvain")
+    X = g["pca_input0"]
+    handle.upload_dense(X)
+    handle.standard_scale(15.0)
+    want, _, _ = upstream.pp_scale(X, max_value=15)
+    np.testing.assert_allclose(handle.download_dense(0, X.shape[0]), want, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", STAGE_GOLDENS)
+def test_pca_embedding_vs_float64_oracle(handle, name):
+    """north_star tolerance: PCA embedding within 1e-4 relative of the reference path.  The truth is the
+    float64 restatement of sklearn's randomized SVD on the SAME float32 input; sklearn's own
+    float32 run (the golden X_pca) is reported beside it."""
+    g = load_golden(name)
+    X = g["pca_input0"]
+    C = g["X_pca0"].shape[1]
+    n_iter = pca_f64.auto_n_iter(X.shape[0], X.shape[1], C)
+    want, sv, _ = pca_f64.randomized_pca_f64(X, C, random_state=golden_case(name)[1].get("random_state", 0))
+    seed = golden_case(name)[1].get("random_state", 0)
+    omega = pca_f64.omega(X.shape[1], C, seed).astype(np.float32)
+    handle.upload_dense(X)
+    emb, got_sv = handle.pca(C, omega, n_iter)
+    err = _rel(emb, want)
+    err_sklearn = _rel(g["X_pca0"], want)
+    print(f"\n[{name}] GPU vs f64 oracle: {err:.2e}   sklearn-f32 vs f64 oracle: {err_sklearn:.2e}")
+    assert err < 1e-4
+    np.testing.assert_allclose(got_sv, sv, rtol=1e-5)
+
+
+def test_pca_unsupported_shapes_fail_loudly(handle):
+    rs = np.random.default_rng(0)
+    handle.upload_dense(rs.normal(size=(50, 80)).astype(np.float32))  # fewer rows than genes
+    with pytest.raises(NotImplementedError):
+        handle.pca(10, rs.normal(size=(80, 20)).astype(np.float32), 4)
+    h2 = type(handle)(0)
+    h2.upload_dense(np.ones((300, 64), dtype=np.float32))  # rank 0 after centring
+    with pytest.raises(NotImplementedError):
+        h2.pca(10, rs.normal(size=(64, 20)).astype(np.float32), 4)
+    h2.close()
+
+
+@pytest.mark.parametrize("name", STAGE_GOLDENS)
+def test_knn_on_reference_embedding_exact(handle, name):
+    """Same embedding in -> same neighbour indices out (bit-exact index work), distances to float32 eps."""
+    g = load_golden(name)
+    handle.upload_embedding(g["X_pca0"])
+    idx, dist = handle.knn(10)
+    np.testing.assert_array_equal(idx, g["knn_indices0"])
+    np.testing.assert_allclose(dist, g["knn_distances0"], rtol=2e-6, atol=2e-5)
+
+
+def test_knn_larger_k_and_dims(handle):
+    rs = np.random.default_rng(3)
+    emb = (rs.normal(size=(3000, 45)) * np.linspace(5, 0.5, 45)).astype(np.float32)
+    handle.upload_embedding(emb)
+    for k in (2, 10, 16, 31):
+        idx, dist = handle.knn(k)
+        want_i, want_d = upstream.knn_brute(emb, k)
+        np.testing.assert_array_equal(idx, want_i)
+        np.testing.assert_allclose(dist, want_d, rtol=2e-6, atol=2e-5)
+
+
+def test_knn_ragged_sizes(handle):
+    rs = np.random.default_rng(4)
+    for n in (11, 127, 128, 129, 1000):
+        emb = rs.normal(size=(n, 30)).astype(np.float32)
+        handle.upload_embedding(emb)
+        idx, _ = handle.knn(10)
+        want_i, _ = upstream.knn_brute(emb, 10)
+        np.testing.assert_array_equal(idx, want_i)
+    with pytest.raises(ValueError):
+        handle.upload_embedding(rs.normal(size=(5, 30)).astype(np.float32))
+        handle.knn(10)
+
+
+# ------------------------------------------------------------------------------ edge cases of the CSR path
+def test_doublets_edge_cases(handle):
+    """Empty rows, a doublet of a cell with itself (replace=True), explicit zeros, values that cancel,
+    gene counts that are not a multiple of 32."""
+    rs = np.random.default_rng(5)
+    dense = rs.poisson(0.3, (40, 77)).astype(np.float32)
+    dense[3] = 0
+    dense[9] = 0
+    dense[5] = -dense[6]  # cancels to an all-zero synthetic row
+    raw = sp_sparse.csr_matrix(dense)
+    raw.data[:5] = 0  # explicit zeros stay stored
+    parents = np.array([[3, 9], [3, 4], [7, 7], [5, 6], [0, 39], [12, 3]], dtype=np.int64)
+    handle.upload_counts(raw)
+    handle.create_doublets(parents)
+    got = handle.download_synthetics()
+    want = reference_path.create_doublets(raw, parents)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+    with pytest.raises(ValueError):
+        handle.create_doublets(np.array([[0, 40]], dtype=np.int64))
+
+
+def test_wide_matrix_column_chunking(handle):
+    """More genes than one shared-memory chunk (8192 columns): the multi-pass path of every CSR kernel."""
+    rs = np.random.default_rng(6)
+    n, g_ = 64, 20011
+    raw = sp_sparse.random(n, g_, density=0.02, format="csr", random_state=7, dtype=np.float32)
+    raw.data = np.ceil(raw.data * 9).astype(np.float32)
+    raw.sort_indices()
+    parents = rs.choice(n, size=(16, 2), replace=False).astype(np.int64)
+    handle.upload_counts(raw)
+    handle.create_doublets(parents)
+    got = handle.download_synthetics()
+    want = reference_path.create_doublets(raw, parents)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+    pro = reference_path.prologue(raw, 0)
+    handle.normalise_log(handle.median_lib_size(), 0.1)
+    want_dense, _, med = reference_path.normalise(want, pro["lib_size"], pro["normed"], 0.1)
+    assert handle.median_lib_size() == med
+    np.testing.assert_allclose(handle.download_dense(), want_dense, rtol=3e-6, atol=3e-7)
+
+
+# ------------------------------------------------------------------------------ whole classifier
+def _fit_native(name, **extra):
+    from doubletdetection_b200 import BoostClassifier
+
+    counts, kw, pkw = golden_case(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(**kw, **extra)
+        clf.fit(counts)
+        labels = np.asarray(clf.predict(**pkw), dtype=np.float64)
+    return clf, labels
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_classifier_end_to_end_vs_golden(name):
+    """north_star: parent indices and final labels bit-exact, log p-values within 1e-4 relative."""
+    g = load_golden(name)
+    clf, labels = _fit_native(name)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), g["parents"])
+    np.testing.assert_array_equal(labels, g["labels"])
+    if "top_var_genes" in g:
+        np.testing.assert_array_equal(clf.top_var_genes_, g["top_var_genes"])
+    same = (clf.communities_ == g["communities"]).all(axis=1)
+    print(f"\n[{name}] iterations with identical communities: {int(same.sum())}/{same.size}")
+    for i in np.nonzero(same)[0]:
+        np.testing.assert_array_equal(clf.synth_communities_[i], g["synth_communities"][i])
+        np.testing.assert_array_equal(clf.all_scores_[i], g["all_scores"][i])
+        np.testing.assert_allclose(clf.all_log_p_values_[i], g["all_log_p_values"][i], rtol=1e-4, atol=1e-12)
+    assert clf.all_scores_.shape == g["all_scores"].shape
+    assert clf.synth_communities_.shape == g["synth_communities"].shape
+    sc = clf.doublet_score()
+    assert np.asarray(sc).shape == g["doublet_score"].shape
+    if same.all():
+        np.testing.assert_allclose(np.ma.filled(np.ma.asarray(sc, dtype=np.float64), np.nan), g["doublet_score"],
+                                   rtol=1e-4, atol=1e-12)
+
+
+def test_classifier_is_deterministic_and_stream_continues():
+    """Reference test (tests/test_package.py:24-38): same seed, same scores; and the classifier's RNG
+    stream continues across fit() calls."""
+    a, _ = _fit_native("c1_louvain")
+    b, _ = _fit_native("c1_louvain")
+    np.testing.assert_array_equal(a.doublet_score(), b.doublet_score())
+    first = np.asarray(a.parents_, dtype=np.int64).copy()
+    counts, _, _ = golden_case("c1_louvain")
+    a.fit(counts)
+    assert not np.array_equal(first, np.asarray(a.parents_, dtype=np.int64))
+
+
+def test_pipeline_matches_stagewise_calls(handle):
+    """dd_fit_iterations == the stage-by-stage entry points chained by hand."""
+    g = load_golden("structured_1500x300")
+    pro, _ = _prologue("structured_1500x300")
+    parents = g["parents"]
+    n_cells = pro["raw"].shape[0]
+    C = 30
+    omega = pca_f64.omega(pro["raw"].shape[1], C, 0).astype(np.float32)
+    n_aug = n_cells + parents.shape[1]
+    n_iter = pca_f64.auto_n_iter(n_aug, pro["raw"].shape[1], C)
+    handle.upload_counts(pro["raw"])
+    out = handle.fit_iterations(parents, omega, pseudocount=0.1, standard_scaling=False, n_comp=C,
+                                n_power_iter=n_iter, n_host_threads=2)
+    for i in range(parents.shape[0]):
+        handle.create_doublets(parents[i])
+        handle.normalise_log(handle.median_lib_size(), 0.1)
+        handle.pca(C, omega, n_iter)
+        idx, _ = handle.knn(10)
+        labels = louvain_c.louvain(*(lambda S: (S.indptr, S.indices))(upstream.knn_pattern_graph(idx)), None,
+                                   resolution=4.0, seed=0)
+        np.testing.assert_array_equal(out["communities"][i], labels[:n_cells])
+        np.testing.assert_array_equal(out["synth_communities"][i], labels[n_cells:])
+        s, lp, _, _ = reference_path.score_communities(labels, n_cells)
+        np.testing.assert_array_equal(out["scores"][i], s)
+        np.testing.assert_allclose(out["log_p"][i], lp, rtol=1e-9, atol=1e-12)
+    assert handle.kernel_launches() > 0
+
+
+# ------------------------------------------------------------------------------ BASELINE config sizes
+def test_config2_properties_and_sampled_parity(handle):
+    """10k cells x 3k genes (BASELINE configs[1]): size-independent properties plus oracle parity on the
+    synthetic CSR (bit-exact) and on the dense matrix / embedding / kNN."""
+    raw = datasets.structured_counts(10000, 3000, seed=1234)
+    rng = np.random.default_rng(0)
+    parents = rng.choice(10000, size=(2500, 2), replace=False)
+    pro = reference_path.prologue(raw, 10000)
+    handle.upload_counts(raw)
+    np.testing.assert_array_equal(handle.lib_size(), pro["lib_size"])
+    handle.create_doublets(parents)
+    syn = handle.download_synthetics()
+    want = reference_path.create_doublets(raw, parents)
+    np.testing.assert_array_equal(syn.indptr, want.indptr)
+    np.testing.assert_array_equal(syn.indices, want.indices)
+    np.testing.assert_array_equal(syn.data, want.data)
+    # properties: sorted unique columns, row sums add up (linearity of the pair sum)
+    assert (np.diff(syn.indices)[np.setdiff1d(np.arange(syn.nnz - 1), syn.indptr[1:-1] - 1)] > 0).all()
+    np.testing.assert_array_equal(handle.synth_lib_size(), pro["lib_size"][parents[:, 0]] + pro["lib_size"][parents[:, 1]])
+    med = handle.median_lib_size()
+    handle.normalise_log(med, 0.1)
+    want_dense, _, want_med = reference_path.normalise(want, pro["lib_size"], pro["normed"], 0.1)
+    assert med == want_med
+    got_dense = handle.download_dense()
+    np.testing.assert_allclose(got_dense, want_dense, rtol=3e-6, atol=3e-7)
+    C = 30
+    omega = pca_f64.omega(3000, C, 0).astype(np.float32)
+    emb, _ = handle.pca(C, omega, 7)
+    want_emb, _, _ = pca_f64.randomized_pca_f64(got_dense, C, random_state=0)
+    err = _rel(emb, want_emb)
+    print(f"\n[config2] GPU embedding vs f64 oracle: {err:.2e}")
+    assert err < 1e-4
+    idx, dist = handle.knn(10)
+    want_i, want_d = upstream.knn_brute(emb, 10)  # oracle kNN on the SAME (GPU) embedding
+    np.testing.assert_array_equal(idx, want_i)
+    assert (idx[:, 0] == np.arange(idx.shape[0])).all() and (np.diff(dist[:, 1:], axis=1) >= 0).all()
