@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- augmented-cells/sec through BoostClassifier.fit (n_iters=25) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1]
+
+One *step* is one pass of the hot path over one batch: a 25-iteration fit loop (every iteration =
+synthetic doublets -> normalise/log -> randomized PCA -> exact kNN -> Louvain -> hypergeometric scoring)
+over the synthetic count matrix of the workload.  With N > 1 (torchrun, one rank per GPU) every rank
+runs its own block of 25 iterations of a 25 N iteration fit (iteration sharding, no data-path
+collective): weak scaling.
+
+`value`   inputs resident in HBM (counts uploaded once), timed call = the C-ABI fit loop
+`e2e`     the same metric through the public API, BoostClassifier.fit(host CSR): host->device copies,
+          parent draws and the device->host results inside the timed region
+`roofline` the dominant kernel of the timed region: algorithmic bytes / CUDA-event time vs measured peak
+`cpu_baseline` the oracle (CPU restatement of the reference path) timed on this box's host cores on a
+          bounded sample (one iteration) of the same workload -- rank 0, N == 1 only
+
+`--impl reference` times that CPU path alone (the reference itself cannot be imported in this image:
+scanpy/anndata/phenograph are absent) and prints the same JSON line.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import scipy.sparse as sp_sparse
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # BASELINE.json configs
+    "c1": dict(n_cells=500, n_genes=100, kind="poisson", desc="500 cells x 100 genes Poisson(1)"),
+    "c2": dict(n_cells=10000, n_genes=3000, kind="structured", desc="10k cells x 3k HVG synthetic"),
+    "c3": dict(n_cells=100000, n_genes=3000, kind="structured", desc="100k cells x 3k HVG synthetic"),
+}
+N_ITERS = 25
+BOOST_RATE = 0.25
+N_COMPONENTS = 30
+PSEUDOCOUNT = 0.1
+SEED = 0
+
+
+# ----------------------------------------------------------------------------------------- inputs
+def make_counts(wl):
+    """Seeded synthetic counts; same formulas as oracle/datasets.py, re-stated here so
+    the product arm does not import the oracle."""
+    n, g = wl["n_cells"], wl["n_genes"]
+    if wl["kind"] == "poisson":
+        return sp_sparse.csr_matrix(np.random.default_rng(0).poisson(1.0, (n, g)).astype(np.float32))
+    rs = np.random.default_rng(1234)
+    n_types = 8
+    base = rs.lognormal(-3.0, 1.2, g)
+    prof = base * np.exp(rs.normal(0, 0.8, (n_types, g)))
+    types = rs.integers(0, n_types, n)
+    depth = rs.lognormal(0, 0.3, n)
+    blocks = []
+    for s in range(0, n, 20000):
+        e = min(s + 20000, n)
+        blocks.append(sp_sparse.csr_matrix(rs.poisson(prof[types[s:e]] * depth[s:e, None]).astype(np.float32)))
+    x = sp_sparse.vstack(blocks).tocsr()
+    x.sort_indices()
+    return x
+
+
+def draw_parents(rng, n_cells, n_iters):
+    m = int(BOOST_RATE * n_cells)
+    out = np.empty((n_iters, m, 2), dtype=np.int64)
+    for i in range(n_iters):
+        out[i] = rng.choice(n_cells, size=(m, 2), replace=False)
+    return out
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU path (oracle)
+def cpu_one_iteration(state):
+    """One _one_fit of the reference path on the host: the reference's own lines for doublets /
+    normalise (oracle.reference_path), sklearn PCA + brute kNN (what scanpy delegates to), the C Louvain
+    specification, scipy hypergeom scoring.  Test infrastructure used as the reported CPU baseline."""
+    from oracle import reference_path, upstream
+    from oracle import louvain_c
+
+    pro, rng, n_cells = state["pro"], state["rng"], state["n_cells"]
+    choices = reference_path.draw_parents(rng, n_cells, BOOST_RATE, False)
+    synth = reference_path.create_doublets(pro["raw"], choices)
+    aug, _, _ = reference_path.normalise(synth, pro["lib_size"], pro["normed"], PSEUDOCOUNT)
+    emb, _ = upstream.tl_pca(aug, N_COMPONENTS, random_state=SEED, svd_solver="auto")
+    from sklearn.neighbors import NearestNeighbors
+
+    nn = NearestNeighbors(n_neighbors=10, algorithm="brute", metric="euclidean", n_jobs=-1).fit(emb)
+    idx = nn.kneighbors(emb, return_distance=False)
+    graph = upstream.knn_pattern_graph(idx)
+    labels = louvain_c.louvain(graph.indptr, graph.indices, None, resolution=4.0, seed=SEED)
+    reference_path.score_communities(labels, n_cells)
+    return aug.shape[0]
+
+
+def cpu_state(counts):
+    from oracle import reference_path
+
+    pro = reference_path.prologue(counts, 10000)
+    return dict(pro=pro, rng=np.random.default_rng(SEED), n_cells=counts.shape[0])
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, wl, counts):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU path is timed once, on rank 0
+    state = cpu_state(counts)
+    for _ in range(args.warmup):
+        cpu_one_iteration(state)
+    t0 = time.perf_counter()
+    cells = 0
+    for _ in range(args.steps):
+        cells += cpu_one_iteration(state)
+    dt = time.perf_counter() - t0
+    value = cells / dt
+    sample = "one _one_fit iteration per step (of the 25-iteration fit), all host cores for BLAS / kNN, 1 thread Louvain"
+    line = {
+        "impl": "reference", "metric": "augmented-cells/sec through BoostClassifier.fit (n_iters=25)", "value": value,
+        "unit": "augmented-cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, louvain", "step": sample},
+        "cpu_baseline": {"value": value, "unit": "augmented-cells/s", "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "augmented-cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference package not importable here (scanpy/anndata/phenograph absent): oracle port of its CPU path",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- roofline
+def kernel_rooflines(report, n_cells, n_synth, n_genes, nnz_orig, nnz_parents_per_iter, peaks, n_rand=40, kp=32):
+    """Algorithmic bytes / flops per launch over the mean CUDA-event duration."""
+    a = n_cells + n_synth
+    hbm, tensor = peaks["hbm_gbs"], peaks["bf16_tflops_sustained"]
+    algo = {
+        # read D once, read Q, write Y
+        "gemm_dq": ("hbm", (a * n_genes + n_genes * n_rand + a * n_rand) * 4.0),
+        # read D once, read Y, accumulate Z (float64)
+        "gemm_dty": ("hbm", (a * n_genes + a * n_rand) * 4.0 + n_genes * n_rand * 8.0),
+        # read raw rows of originals and of both parents (index + value), write the dense matrix
+        "dense_rows": ("hbm", (nnz_orig + nnz_parents_per_iter) * 8.0 + a * n_genes * 4.0),
+        "colstats": ("hbm", a * n_genes * 4.0),
+        # 2 A^2 KP flops of the distance GEMM (CUDA-core fp32 today; the tensor peak is the yardstick)
+        "knn_scan": ("tensor", 2.0 * a * a * kp),
+    }
+    out = {}
+    for name, (bound, work) in algo.items():
+        if name not in report or report[name][1] == 0:
+            continue
+        ms = report[name][0] / report[name][1]
+        if bound == "hbm":
+            ach = work / (ms * 1e-3) / 1e9
+            out[name] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                         "traffic": None, "ms_per_launch": ms, "launches": report[name][1], "algorithmic_bytes": work}
+        else:
+            ach = work / (ms * 1e-3) / 1e12
+            out[name] = {"bound": "tensor", "achieved": ach, "peak": tensor, "unit": "TFLOP/s", "frac": ach / tensor,
+                         "traffic": None, "ms_per_launch": ms, "launches": report[name][1], "algorithmic_flops": work}
+    return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        p["source"] = "measured (MEASURED_PEAKS.json)"
+        return p
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args, wl, counts):
+    import torch
+
+    from doubletdetection_b200 import BoostClassifier, _capi
+    from doubletdetection_b200.classifier import _pca_plan
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n_cells, n_genes = counts.shape
+    n_synth = int(BOOST_RATE * n_cells)
+    n_aug = n_cells + n_synth
+    host_threads = max(1, cpu_cores() // world)
+    total_iters = N_ITERS * world  # weak scaling: every rank owns 25 iterations
+    it0, it1 = rank * N_ITERS, (rank + 1) * N_ITERS
+    omega, n_power_iter = _pca_plan(n_aug, n_genes, N_COMPONENTS, SEED)
+    fit_kw = dict(pseudocount=PSEUDOCOUNT, standard_scaling=False, n_comp=N_COMPONENTS, n_power_iter=n_power_iter,
+                  knn_k=10, resolution=4.0, seed=SEED, n_host_threads=host_threads, iter_begin=it0, iter_end=it1)
+
+    # ---------------- device-resident leg (`value`)
+    h = _capi.Handle(local_rank)
+    h.upload_counts(counts)
+    rng = np.random.default_rng(SEED)
+    for _ in range(args.warmup):
+        h.fit_iterations(draw_parents(rng, n_cells, total_iters), omega, **fit_kw)
+    step_parents = [draw_parents(rng, n_cells, total_iters) for _ in range(args.steps)]
+    h.set_kernel_timing(True)
+    launches0 = h.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    stage_tot = {}
+    for s in range(args.steps):
+        out = h.fit_iterations(step_parents[s], omega, **fit_kw)
+        dev_ms += out["stage_ms"]["device_total"]
+        for k_, v_ in out["stage_ms"].items():
+            stage_tot[k_] = stage_tot.get(k_, 0.0) + v_
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    report = h.kernel_timing_report()
+    launches = sum_over_ranks(h.kernel_launches() - launches0)
+    h.set_kernel_timing(False)
+    cells_per_step = N_ITERS * n_aug * world
+    value = args.steps * cells_per_step / dt
+
+    nnz_par = float(np.diff(counts.indptr)[step_parents[0][it0]].sum()) if n_synth else 0.0
+    peaks = load_peaks()
+    roofs = kernel_rooflines(report, n_cells, n_synth, n_genes, float(counts.nnz), nnz_par, peaks)
+    kernel_ms = {k_: round(v_[0], 3) for k_, v_ in sorted(report.items(), key=lambda kv: -kv[1][0])}
+    dominant = max(roofs, key=lambda k_: report[k_][0]) if roofs else None
+    h.close()
+
+    # ---------------- end-to-end leg (`e2e`): public API, host buffers
+    clf = BoostClassifier(boost_rate=BOOST_RATE, n_components=N_COMPONENTS, n_iters=total_iters,
+                          clustering_algorithm="louvain", pseudocount=PSEUDOCOUNT, random_state=SEED,
+                          n_jobs=host_threads, device=local_rank, distributed=world > 1)
+    for _ in range(max(1, min(args.warmup, 3))):
+        clf.fit(counts)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        clf.fit(counts)
+        labels = clf.predict()
+    barrier()
+    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = args.steps * cells_per_step / dt_e2e
+    h2d = (counts.indptr.nbytes + counts.indices.nbytes + counts.data.nbytes + omega.nbytes + N_ITERS * n_synth * 2 * 8)
+    d2h = N_ITERS * (n_aug * 10 * 4 + 8) + n_cells * 4
+    n_doublets = int(np.nansum(labels))
+
+    line = {
+        "metric": "augmented-cells/sec through BoostClassifier.fit (n_iters=25)",
+        "value": value, "unit": "augmented-cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, louvain (BASELINE.json configs)",
+            "step": "one 25-iteration fit loop per GPU over the resident count matrix",
+            "cells": n_cells, "genes": n_genes, "synthetics": n_synth, "nnz": int(counts.nnz),
+            "host_threads_per_rank": host_threads, "parallelism": f"iteration-shard x{world}",
+            "l2": "dense matrix per iteration (%.2f GB) exceeds the 126 MB L2" % (n_aug * n_genes * 4 / 1e9),
+        },
+        "device_ms_per_step": dev_ms / args.steps,
+        "stage_ms_per_step": {k_: round(v_ / args.steps, 3) for k_, v_ in stage_tot.items() if k_ != "_"},
+        "kernel_ms_total": kernel_ms,
+        "roofline": roofs.get(dominant),
+        "roofline_kernel": dominant,
+        "rooflines": roofs,
+        "peaks": {k_: peaks.get(k_) for k_ in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
+        "e2e": {"value": e2e_value, "unit": "augmented-cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * dt_e2e / args.steps, "doublets_called": n_doublets},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    # ---------------- CPU baseline beside it (rank 0, N == 1)
+    if world == 1 and not args.no_cpu_baseline:
+        state = cpu_state(counts)
+        t0 = time.perf_counter()
+        cells = cpu_one_iteration(state)
+        dt_cpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": cells / dt_cpu, "unit": "augmented-cells/s", "cores": cpu_cores(), "kind": "port",
+            "sample": "one _one_fit iteration of the 25 (oracle: reference lines + sklearn PCA/brute kNN + C Louvain + scipy hypergeom)",
+            "seconds": dt_cpu,
+        }
+    # ---------------- the other single-GPU config, for reference
+    if world == 1 and args.workload == "c3" and not args.no_extra:
+        line["other_workloads"] = {"c2": quick_workload("c2", local_rank, host_threads, _capi, _pca_plan)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def quick_workload(name, device, host_threads, _capi, _pca_plan):
+    wl = WORKLOADS[name]
+    counts = make_counts(wl)
+    n_cells, n_genes = counts.shape
+    n_aug = n_cells + int(BOOST_RATE * n_cells)
+    omega, npi = _pca_plan(n_aug, n_genes, N_COMPONENTS, SEED)
+    h = _capi.Handle(device)
+    h.upload_counts(counts)
+    rng = np.random.default_rng(SEED)
+    kw = dict(pseudocount=PSEUDOCOUNT, standard_scaling=False, n_comp=N_COMPONENTS, n_power_iter=npi, n_host_threads=host_threads)
+    for _ in range(3):
+        h.fit_iterations(draw_parents(rng, n_cells, N_ITERS), omega, **kw)
+    par = [draw_parents(rng, n_cells, N_ITERS) for _ in range(5)]
+    t0 = time.perf_counter()
+    for p in par:
+        h.fit_iterations(p, omega, **kw)
+    dt = time.perf_counter() - t0
+    h.close()
+    return {"workload": wl["desc"], "value": 5 * N_ITERS * n_aug / dt, "unit": "augmented-cells/s", "ms_per_step": 1e3 * dt / 5}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return
+    counts = make_counts(wl)
+    if args.impl == "reference":
+        run_reference_arm(args, wl, counts)
+    else:
+        run_ours(args, wl, counts)
+
+
+if __name__ == "__main__":
+    main()

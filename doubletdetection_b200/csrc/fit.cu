@@ -4,6 +4,7 @@
 // clusters + scores finished iterations while the GPU works on the next ones.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -93,6 +94,9 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     bool closing = false;
     std::atomic<int> worker_rc{DD_OK};
     std::string worker_err;
+    std::atomic<int64_t> host_us{0};
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto t_call = now();
 
     auto worker = [&]() {
         std::vector<int32_t> labels((size_t)A);
@@ -115,6 +119,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
                 wrc = DD_ERR_UNSUPPORTED;
                 werr = "pca: rank-deficient range (Cholesky breakdown)";
             } else {
+                const auto t0 = now();
                 int32_t n_comm = 0;
                 wrc = dd_host_louvain_knn(A, k, s.knn, p->resolution, p->seed, labels.data(), &n_comm);
                 if (wrc != DD_OK) werr = "dd_fit_iterations: clustering rejected the kNN graph (index out of range)";
@@ -123,6 +128,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
                     std::copy(labels.begin(), labels.begin() + N, communities_out + (size_t)job.iter * N);
                     if (M > 0) std::copy(labels.begin() + N, labels.end(), synth_communities_out + (size_t)job.iter * M);
                 }
+                host_us += std::chrono::duration_cast<std::chrono::microseconds>(now() - t0).count();
             }
             {
                 std::lock_guard<std::mutex> lk(mu);
@@ -204,6 +210,8 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         float total = 0.f;
         if (cudaEventElapsedTime(&total, evs[0], evs[(size_t)(issued - 1) * kStages + 5]) == cudaSuccess)
             stage_ms_out[6] = total;  // first launch -> last copy, device time of the whole call
+        stage_ms_out[0] = host_us.load() / 1e3;  // clustering + scoring, summed over the host workers
+        stage_ms_out[7] = std::chrono::duration_cast<std::chrono::microseconds>(now() - t_call).count() / 1e3;
     }
     cleanup();
     return rc;

@@ -124,8 +124,9 @@ double dd_hypergeom_logsf(int64_t k, int64_t M, int64_t n, int64_t N);
  *   scores_out, log_p_out   float64[n_iters * N]
  *   communities_out         int32[n_iters * N]
  *   synth_communities_out   int32[n_iters * M]
- *   stage_ms_out            float64[8] or NULL: GPU milliseconds summed over iterations for
- *                           {doublets, normalise, scale, pca, knn, d2h, 0, 0}
+ *   stage_ms_out            float64[8] or NULL: milliseconds summed over iterations for
+ *                           {host clustering+scoring (summed over workers), doublets+normalise, scale,
+ *                            pca, knn, d2h, device time first launch -> last copy, wall time of the call}
  */
 typedef struct dd_fit_params {
     int32_t n_iters;

@@ -1,0 +1,63 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: iteration sharding and the collection of
+per-iteration results (no data-path collective exists on this path)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from doubletdetection_b200 import iteration_shard
+from doubletdetection_b200.classifier import _allgather_iterations
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_iters, n_cells, n_synth, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.default_rng(7)  # same "truth" on every rank
+        truth = dict(
+            scores=rs.random((n_iters, n_cells)),
+            log_p=-rs.random((n_iters, n_cells)) * 40,
+            communities=rs.integers(0, 30, (n_iters, n_cells)).astype(np.int32),
+            synth_communities=rs.integers(0, 30, (n_iters, n_synth)).astype(np.int32),
+        )
+        truth["log_p"][1, 3] = -np.inf  # values that do not survive arithmetic reductions
+        truth["log_p"][n_iters - 1, 5] = np.nan
+        truth["scores"][n_iters - 1, 5] = np.nan
+        it0, it1 = iteration_shard(n_iters, rank, world)
+        mine = {k: np.zeros_like(v) for k, v in truth.items()}
+        for k in truth:
+            mine[k][it0:it1] = truth[k][it0:it1]
+        mine["stage_ms"] = {"pca": 1.0 + rank, "knn": 5.0 - rank}
+        merged = _allgather_iterations(dist, mine, n_iters, device=0)
+        ok = all(np.array_equal(merged[k], truth[k], equal_nan=True) for k in truth)
+        ok = ok and merged["stage_ms"] == {"knn": 5.0, "pca": float(world)}
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_iteration_sharding_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 5, 40, 10, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(results) == [(0, True), (1, True)]
