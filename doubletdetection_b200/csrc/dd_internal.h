@@ -76,6 +76,8 @@ struct dd_handle {
     int32_t *d_knn_idx = nullptr;
     float *d_knn_dist = nullptr;
     int64_t cap_knn = 0;
+    uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout
+    int64_t cap_knn_ops = 0;
 
     // ---- accounting ----
     int64_t launches = 0;

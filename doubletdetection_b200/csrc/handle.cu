@@ -114,7 +114,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     cudaStreamSynchronize(h->stream);
     void *bufs[] = {h->d_indptr, h->d_indices, h->d_data,   h->d_lib,   h->d_l1,      h->d_parents, h->d_sindptr,
                     h->d_scount, h->d_sindices, h->d_sdata, h->d_slib,  h->d_dense,   h->d_colsum,  h->d_colsumsq,
-                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx, h->d_knn_dist};
+                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx, h->d_knn_dist, h->d_knn_ops};
     for (void *p : bufs)
         if (p) cudaFree(p);
     resolve_pending(h);

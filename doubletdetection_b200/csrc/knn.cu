@@ -14,6 +14,7 @@
 #include "dd_internal.h"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace {
 
@@ -270,6 +271,302 @@ __global__ void k_knn_refine(const float *__restrict__ emb, const int *__restric
     }
 }
 
+
+// =================================================================================================
+// Tensor-core path (KP == 32, TL == 16): the distance GEMM on tcgen05 / TMEM.
+//
+//   t(q, c) = q . c - |c|^2 / 2     (larger = closer; the query norm does not change a query's ranking)
+//
+// is one K = 104 TF32 GEMM with float32-class accuracy ("3xTF32"): every operand is split into a
+// TF32-exact high part and the float32 remainder, and the three significant cross products plus the
+// norm term are concatenated along K:
+//   A' (query row)     = [ q_hi(32) | q_hi(32) | q_lo(32) | 1, 1, 0...0 ]
+//   B' (candidate row) = [ c_hi(32) | c_lo(32) | c_hi(32) | n_hi, n_lo, 0...0 ],  n = -|c|^2/2
+// k_knn_prep writes both operands tile by tile (128 rows) in the canonical no-swizzle K-major UMMA
+// layout (8 x 16-byte core matrices, LBO = 128 B along K, SBO = 3328 B along rows), so that a stage is
+// ONE 53 KB bulk copy (cp.async.bulk, TMA engine) and the shared-memory descriptors are constants.
+//
+// k_knn_tc: one CTA = 256 query rows (two M=128 accumulators) x all candidate tiles.
+//   warp 0    bulk-copy producer (2-stage ring of candidate tiles, mbarrier complete_tx)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (13 K-steps x 2 query tiles per stage)
+//   warps 2-9 epilogue: tcgen05.ld 32 columns at a time, one query row per thread; a value survives only
+//             if it beats the row's current TL-th best (kept in a register), and the rare survivors are
+//             inserted into the row's sorted candidate list in global memory
+// TMEM: 512 columns = 2 (double buffer) x 2 (query tiles) x 128 fp32 accumulator columns.
+namespace tc {
+
+constexpr int KC = 26;                         // 16-byte chunks per operand row (K = 104)
+constexpr int TILE = 128;                      // rows per operand tile
+constexpr int TILE_BYTES = TILE * KC * 16;     // 53248
+constexpr int LBO = 128, SBO = KC * 128;       // bytes
+constexpr int QT = 2;                          // query tiles per CTA
+constexpr int NS = 2;                          // candidate stages
+constexpr int KSTEPS = KC / 2;                 // 13 MMAs of K = 8
+constexpr int TLc = 16;
+constexpr float kEmptyT = -1e29f;              // list filler; padded candidates score -1e30 and never pass
+constexpr size_t SMEM_BYTES = (size_t)(QT + NS) * TILE_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle: start address, LBO (K-adjacent core matrices), SBO (row-adjacent), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(LBO >> 4) << 16;
+    d |= (uint64_t)(SBO >> 4) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Operand tiles in the canonical layout + empty candidate lists.  Block = 8 rows x 26 chunks.
+__global__ void __launch_bounds__(208) k_knn_prep(const float *__restrict__ emb, int64_t n, int64_t n_pad,
+                                                  float4 *__restrict__ qa, float4 *__restrict__ cb,
+                                                  float *__restrict__ cand_t, int *__restrict__ cand_i) {
+    const int j = threadIdx.x >> 3, rr = threadIdx.x & 7;
+    const int64_t row = (int64_t)blockIdx.x * 8 + rr;
+    if (row >= n_pad) return;
+    const bool real = row < n;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (j < 24) {
+        if (real) {
+            const float4 x = *reinterpret_cast<const float4 *>(emb + row * 32 + 4 * (j & 7));
+            const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+            const float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+            a = j < 16 ? hi : lo;
+            b = (j >= 8 && j < 16) ? lo : hi;
+        }
+    } else if (j == 24) {
+        if (real) {
+            double nn = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 x = *reinterpret_cast<const float4 *>(emb + row * 32 + c);
+                nn += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
+            }
+            const double half = -0.5 * nn;
+            const float h = tf32_hi((float)half);
+            a = make_float4(1.f, 1.f, 0.f, 0.f);
+            b = make_float4(h, (float)(half - (double)h), 0.f, 0.f);
+        } else {
+            b = make_float4(tf32_hi(-1e30f), 0.f, 0.f, 0.f);
+        }
+    }
+    const int64_t tile = row / TILE;
+    const int r = (int)(row % TILE);
+    const int64_t off16 = tile * (TILE_BYTES / 16) + (int64_t)(r >> 3) * (SBO / 16) + (int64_t)j * (LBO / 16) + (r & 7);
+    qa[off16] = a;
+    cb[off16] = b;
+    if (j < 4) {  // 16 list slots per row, 4 per thread
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            cand_t[row * TLc + 4 * j + e] = kEmptyT;
+            cand_i[row * TLc + 4 * j + e] = 0x7fffffff;
+        }
+    }
+}
+
+// sorted (descending t) insertion into a row's list; returns the new TL-th best
+__device__ __noinline__ float list_insert_desc(float *__restrict__ lt, int *__restrict__ li, float t, int idx) {
+    int pos = TLc;
+#pragma unroll
+    for (int l = TLc - 1; l >= 0; l--)
+        if (lt[l] < t) pos = l;
+    if (pos == TLc) return lt[TLc - 1];
+    for (int l = TLc - 1; l > pos; l--) {
+        lt[l] = lt[l - 1];
+        li[l] = li[l - 1];
+    }
+    lt[pos] = t;
+    li[pos] = idx;
+    return lt[TLc - 1];
+}
+
+__global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb,
+                                                    int64_t n, int n_tiles, float *__restrict__ cand_t,
+                                                    int *__restrict__ cand_i) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sA = smem;                                // QT tiles
+    uint8_t *sB = smem + (size_t)QT * TILE_BYTES;      // NS stages
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(QT + NS) * TILE_BYTES);
+    uint64_t *a_full = bars;            // 1
+    uint64_t *full = bars + 1;          // NS
+    uint64_t *empty = full + NS;        // NS
+    uint64_t *tfull = empty + NS;       // 2
+    uint64_t *tempty = tfull + 2;       // 2
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile0 = blockIdx.x * QT;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < NS; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tfull + b, 1);
+            mbar_init(tempty + b, 256);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(a_full, QT * TILE_BYTES);
+            for (int qt = 0; qt < QT; qt++)
+                bulk_g2s(sA + (size_t)qt * TILE_BYTES, qa + (size_t)(tile0 + qt) * TILE_BYTES, TILE_BYTES, a_full);
+            for (int step = 0; step < n_tiles; step++) {
+                const int s = step % NS;
+                const uint32_t ph = (step / NS) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                mbar_expect_tx(full + s, TILE_BYTES);
+                bulk_g2s(sB + (size_t)s * TILE_BYTES, cb + (size_t)step * TILE_BYTES, TILE_BYTES, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(a_full, 0);
+            fence_after();
+            uint64_t a_desc[QT];
+            for (int qt = 0; qt < QT; qt++) a_desc[qt] = make_desc(smem_u32(sA + (size_t)qt * TILE_BYTES));
+            for (int step = 0; step < n_tiles; step++) {
+                const int s = step % NS;
+                const uint32_t ph = (step / NS) & 1;
+                const int buf = step & 1;
+                const uint32_t bph = (step >> 1) & 1;
+                mbar_wait(full + s, ph);
+                mbar_wait(tempty + buf, bph ^ 1);
+                fence_after();
+                const uint64_t b_desc = make_desc(smem_u32(sB + (size_t)s * TILE_BYTES));
+#pragma unroll
+                for (int qt = 0; qt < QT; qt++) {
+                    const uint32_t d = tmem_base + buf * 256 + qt * 128;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; k++)
+                        mma_tf32(d, a_desc[qt] + (uint64_t)(k * 2 * LBO / 16), b_desc + (uint64_t)(k * 2 * LBO / 16), kIdesc,
+                                 k > 0);
+                }
+                mma_commit(empty + s);     // the stage may be refilled once these MMAs have read it
+                mma_commit(tfull + buf);   // accumulators ready for the epilogue
+            }
+        }
+    } else {
+        const int e = warp - 2;          // 0..7
+        const int qt = e >> 2;
+        const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+        const int64_t qrow = (int64_t)(tile0 + qt) * TILE + quad * 32 + lane;
+        const bool active = qrow < n;
+        float *lt = cand_t + qrow * TLc;
+        int *li = cand_i + qrow * TLc;
+        float tau = active ? kEmptyT : INFINITY;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * 128;
+        for (int step = 0; step < n_tiles; step++) {
+            const int buf = step & 1;
+            const uint32_t bph = (step >> 1) & 1;
+            mbar_wait(tfull + buf, bph);
+            fence_after();
+#pragma unroll 1
+            for (int c = 0; c < TILE; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + buf * 256 + c, v);
+                tmem_ld_wait();
+                float m = __uint_as_float(v[0]);
+#pragma unroll
+                for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
+                if (m > tau) {
+                    const int cbase = step * TILE + c;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const float t = __uint_as_float(v[i]);
+                        if (t > tau && (int64_t)(cbase + i) != qrow) tau = list_insert_desc(lt, li, t, cbase + i);
+                    }
+                }
+            }
+            fence_before();
+            mbar_arrive(tempty + buf);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc
+
 template <int KP, int TL>
 int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     const int64_t n = h->emb_rows;
@@ -287,6 +584,28 @@ int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     return DD_OK;
 }
 
+int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
+    const int64_t n = h->emb_rows;
+    const int n_tiles = (int)((n + tc::TILE - 1) / tc::TILE);
+    const int n_tiles_pad = (n_tiles + tc::QT - 1) / tc::QT * tc::QT;
+    const int64_t n_pad = (int64_t)n_tiles_pad * tc::TILE;
+    const int64_t op_bytes = (int64_t)n_tiles_pad * tc::TILE_BYTES;
+    DD_TRY(dd_reserve(h, &h->d_knn_ops, &h->cap_knn_ops, 2 * op_bytes));
+    uint8_t *qa = h->d_knn_ops, *cb = h->d_knn_ops + op_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc::k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        attr_set = true;
+    }
+    DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 208, 0, h->d_emb, n, n_pad,
+              reinterpret_cast<float4 *>(qa), reinterpret_cast<float4 *>(cb), cand_t, cand_i);
+    DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(n_tiles_pad / tc::QT), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, cand_t,
+              cand_i);
+    DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, n, k,
+              h->d_knn_idx, h->d_knn_dist);
+    return DD_OK;
+}
+
 }  // namespace
 
 // scratch layout inside d_knn_dist's allocation: [n*k dist][n norms][n*TL cand_d][n*TL cand_i]
@@ -297,7 +616,8 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     if (k > n) return dd_fail(h, DD_ERR_ARG, "knn: k exceeds the number of rows");
     if (n >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: too many rows for int32 indices");
     const int TL = (k - 1 <= 12) ? 16 : 32;
-    const int64_t need = n * k + n + 2 * n * 32;
+    const int64_t n_padded = (n + 255) / 256 * 256;  // the tensor-core path keeps lists for whole 256-row CTAs
+    const int64_t need = n * k + n + 2 * n_padded * 32;
     if (need > h->cap_knn) {
         if (h->d_knn_idx) cudaFree(h->d_knn_idx);
         if (h->d_knn_dist) cudaFree(h->d_knn_dist);
@@ -308,7 +628,10 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     }
     float *norms = h->d_knn_dist + n * k;
     float *cand_d = norms + n;
-    int *cand_i = reinterpret_cast<int *>(cand_d + n * 32);
+    int *cand_i = reinterpret_cast<int *>(cand_d + n_padded * 32);
+    // default: tcgen05 distance GEMM; DD_KNN_FFMA=1 keeps the CUDA-core kernel (A/B comparison, KP=64, k>13)
+    static const bool force_ffma = getenv("DD_KNN_FFMA") != nullptr;
+    if (h->KP == 32 && TL == 16 && !force_ffma) return run_knn_tc(h, k, cand_d, cand_i);
     if (h->KP == 32)
         return TL == 16 ? run_knn<32, 16>(h, k, norms, cand_d, cand_i) : run_knn<32, 32>(h, k, norms, cand_d, cand_i);
     return TL == 16 ? run_knn<64, 16>(h, k, norms, cand_d, cand_i) : run_knn<64, 32>(h, k, norms, cand_d, cand_i);
