@@ -385,8 +385,7 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 
 // Operand tiles in the canonical layout + empty candidate lists.  Block = 8 rows x 26 chunks.
 __global__ void __launch_bounds__(208) k_knn_prep(const float *__restrict__ emb, int64_t n, int64_t n_pad,
-                                                  float4 *__restrict__ qa, float4 *__restrict__ cb,
-                                                  float *__restrict__ cand_t, int *__restrict__ cand_i) {
+                                                  float4 *__restrict__ qa, float4 *__restrict__ cb) {
     const int j = threadIdx.x >> 3, rr = threadIdx.x & 7;
     const int64_t row = (int64_t)blockIdx.x * 8 + rr;
     if (row >= n_pad) return;
@@ -421,34 +420,29 @@ __global__ void __launch_bounds__(208) k_knn_prep(const float *__restrict__ emb,
     const int64_t off16 = tile * (TILE_BYTES / 16) + (int64_t)(r >> 3) * (SBO / 16) + (int64_t)j * (LBO / 16) + (r & 7);
     qa[off16] = a;
     cb[off16] = b;
-    if (j < 4) {  // 16 list slots per row, 4 per thread
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            cand_t[row * TLc + 4 * j + e] = kEmptyT;
-            cand_i[row * TLc + 4 * j + e] = 0x7fffffff;
-        }
-    }
 }
 
-// sorted (descending t) insertion into a row's list; returns the new TL-th best
-__device__ __noinline__ float list_insert_desc(float *__restrict__ lt, int *__restrict__ li, float t, int idx) {
-    int pos = TLc;
+// The candidate list of a query row lives in the registers of its epilogue thread, sorted by
+// decreasing t.  Insertion is a fully unrolled compare-and-swap chain (no memory, no dynamic indexing).
+struct RegList {
+    float t[TLc];
+    int i[TLc];
+};
+__device__ __forceinline__ void reglist_insert(RegList &L, float t, int idx) {
 #pragma unroll
-    for (int l = TLc - 1; l >= 0; l--)
-        if (lt[l] < t) pos = l;
-    if (pos == TLc) return lt[TLc - 1];
-    for (int l = TLc - 1; l > pos; l--) {
-        lt[l] = lt[l - 1];
-        li[l] = li[l - 1];
+    for (int l = 0; l < TLc; l++) {
+        const bool gt = t > L.t[l];  // strict: an equal score keeps the earlier (smaller) index in front
+        const float nt = gt ? L.t[l] : t;
+        const int ni = gt ? L.i[l] : idx;
+        L.t[l] = gt ? t : L.t[l];
+        L.i[l] = gt ? idx : L.i[l];
+        t = nt;
+        idx = ni;
     }
-    lt[pos] = t;
-    li[pos] = idx;
-    return lt[TLc - 1];
 }
 
 __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb,
-                                                    int64_t n, int n_tiles, float *__restrict__ cand_t,
-                                                    int *__restrict__ cand_i) {
+                                                    int64_t n, int n_tiles, int *__restrict__ cand_i) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                // QT tiles
     uint8_t *sB = smem + (size_t)QT * TILE_BYTES;      // NS stages
@@ -527,8 +521,12 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
         const int quad = warp & 3;       // TMEM lane quadrant this warp may access
         const int64_t qrow = (int64_t)(tile0 + qt) * TILE + quad * 32 + lane;
         const bool active = qrow < n;
-        float *lt = cand_t + qrow * TLc;
-        int *li = cand_i + qrow * TLc;
+        RegList L;
+#pragma unroll
+        for (int l = 0; l < TLc; l++) {
+            L.t[l] = kEmptyT;
+            L.i[l] = 0x7fffffff;
+        }
         float tau = active ? kEmptyT : INFINITY;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * 128;
         for (int step = 0; step < n_tiles; step++) {
@@ -544,17 +542,33 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
                 float m = __uint_as_float(v[0]);
 #pragma unroll
                 for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
-                if (m > tau) {
-                    const int cbase = step * TILE + c;
+                // rare: some value of this row beats its TL-th best.  Peel maxima until none does.
+                while (m > tau) {
+                    int pos = 0;
+                    bool done = false;
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const float t = __uint_as_float(v[i]);
-                        if (t > tau && (int64_t)(cbase + i) != qrow) tau = list_insert_desc(lt, li, t, cbase + i);
+                    for (int i = 0; i < 32; i++) {  // peel the FIRST column holding the maximum
+                        const bool hit = !done && __uint_as_float(v[i]) == m;
+                        pos = hit ? i : pos;
+                        v[i] = hit ? 0xff800000u : v[i];  // -inf
+                        done = done || hit;
                     }
+                    const int cidx = step * TILE + c + pos;
+                    if ((int64_t)cidx != qrow) {
+                        reglist_insert(L, m, cidx);
+                        tau = L.t[TLc - 1];
+                    }
+                    m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
                 }
             }
             fence_before();
             mbar_arrive(tempty + buf);
+        }
+        if (active) {
+#pragma unroll
+            for (int l = 0; l < TLc; l++) cand_i[qrow * TLc + l] = L.i[l];
         }
     }
     fence_before();
@@ -598,9 +612,8 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
         attr_set = true;
     }
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 208, 0, h->d_emb, n, n_pad,
-              reinterpret_cast<float4 *>(qa), reinterpret_cast<float4 *>(cb), cand_t, cand_i);
-    DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(n_tiles_pad / tc::QT), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, cand_t,
-              cand_i);
+              reinterpret_cast<float4 *>(qa), reinterpret_cast<float4 *>(cb));
+    DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(n_tiles_pad / tc::QT), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, cand_i);
     DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, n, k,
               h->d_knn_idx, h->d_knn_dist);
     return DD_OK;
