@@ -201,6 +201,8 @@ def kernel_rooflines(report, n_cells, n_synth, n_genes, nnz_orig, nnz_parents_pe
     algo = {
         # read D once, read Q, write Y
         "gemm_dq": ("hbm", (a * n_genes + n_genes * n_rand + a * n_rand) * 4.0),
+        "tc_gemm_dq": ("hbm", (a * n_genes + n_genes * n_rand + a * n_rand) * 4.0),
+        "tc_gemm_dty": ("hbm", (a * n_genes + a * n_rand) * 4.0 + n_genes * n_rand * 8.0),
         # read D once, read Y, accumulate Z (float64)
         "gemm_dty": ("hbm", (a * n_genes + a * n_rand) * 4.0 + n_genes * n_rand * 8.0),
         # read raw rows of originals and of both parents (index + value), write the dense matrix
@@ -208,6 +210,8 @@ def kernel_rooflines(report, n_cells, n_synth, n_genes, nnz_orig, nnz_parents_pe
         "colstats": ("hbm", a * n_genes * 4.0),
         # 2 A^2 KP flops of the distance GEMM (CUDA-core fp32 today; the tensor peak is the yardstick)
         "knn_scan": ("tensor", 2.0 * a * a * kp),
+        # tcgen05 path: the same 2 A^2 KP useful flops (the 3xTF32 emulation issues 3.25x as many TF32 flops)
+        "knn_tc": ("tensor", 2.0 * a * a * kp),
     }
     out = {}
     for name, (bound, work) in algo.items():

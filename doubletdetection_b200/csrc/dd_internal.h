@@ -27,6 +27,8 @@ struct dd_timed_launch {
     cudaEvent_t start, stop;
 };
 
+struct dd_tc_state;
+
 struct dd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -66,6 +68,10 @@ struct dd_handle {
     float *d_Y = nullptr;      // A x LP
     double *d_Zacc = nullptr;  // G x LP accumulators of D^T Y
     double *d_small = nullptr; // scratch for L x L matrices, sums, flags (see pca.cu)
+    // tcgen05 path: small GEMM operands as canonical hi/lo UMMA tiles (see pca_tc.h) + TMA tensor maps
+    uint8_t *d_qb = nullptr, *d_yb = nullptr, *d_omega_b = nullptr;
+    int64_t cap_qb = 0, cap_yb = 0, cap_omega_b = 0;
+    dd_tc_state *tc = nullptr;
     float *d_emb = nullptr;    // A x KP embedding (KP = 32 or 64, zero padded)
     int32_t KP = 0;
     int64_t emb_rows = 0;

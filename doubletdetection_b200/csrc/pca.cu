@@ -15,6 +15,7 @@
 //     CholeskyQR (Gram in float64 -> Cholesky -> triangular inverse) is used on both the tall and the
 //     small side.  svd(B) is taken from the float64 Jacobi eigen-decomposition of B B^T (L x L).
 #include "dd_internal.h"
+#include "pca_tc.h"
 
 #include <algorithm>
 #include <cstring>
@@ -332,7 +333,8 @@ template <int LP, int MODE>
 __global__ void __launch_bounds__(128) k_apply(float *__restrict__ Yf, double *__restrict__ Zd, int64_t n_rows,
                                                int L, const double *__restrict__ rinv,
                                                const double *__restrict__ csum, double inv_n,
-                                               double *__restrict__ ssum, float *__restrict__ Qt, int ld) {
+                                               double *__restrict__ ssum, float *__restrict__ Qt, int ld,
+                                               uint8_t *__restrict__ bt) {
     __shared__ double Rs[LP][LP];
     __shared__ double ms[LP];
     for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) Rs[e / LP][e % LP] = rinv[e];
@@ -357,6 +359,11 @@ __global__ void __launch_bounds__(128) k_apply(float *__restrict__ Yf, double *_
 #pragma unroll
             for (int i = 0; i <= j; i++) o = fma(y[i], Rs[i][j], o);
             const float of = (float)o;
+            if (bt != nullptr && ok && j < L) {  // operand of the next tcgen05 GEMM: TF32-exact high part + remainder
+                const float hi = __uint_as_float(__float_as_uint(of) & 0xffffe000u);
+                *reinterpret_cast<float *>(bt + dd_tc_b_offset(row, j, 0)) = hi;
+                *reinterpret_cast<float *>(bt + dd_tc_b_offset(row, j, 1)) = of - hi;
+            }
             if (MODE == 0) {
                 if (ok) Yf[row * LP + j] = of;
                 double s = ok ? (double)of : 0.0;
@@ -564,6 +571,20 @@ int run_pca(dd_handle *h, int n_power_iter) {
     splits = (int)((A + rows_per_split - 1) / rows_per_split);
     const int tall_grid = h->num_sms * 2;
     const double inv_A = 1.0 / (double)A;
+    const bool use_tc = LP == 40 && dd_tc_pca_enabled();
+    if (use_tc) {
+        DD_TRY(dd_tc_prepare(h));
+        const int64_t q_bytes = (int64_t)(ld / 32) * 12288, y_bytes = ((A + 31) / 32) * 12288;
+        if (q_bytes > h->cap_qb || y_bytes > h->cap_yb) {
+            DD_TRY(dd_reserve(h, &h->d_qb, &h->cap_qb, q_bytes));
+            DD_TRY(dd_reserve(h, &h->d_yb, &h->cap_yb, y_bytes));
+            // pad columns (n >= L) and pad rows are never written: they must read as zero
+            DD_CUDA(h, cudaMemsetAsync(h->d_qb, 0, (size_t)h->cap_qb, h->stream));
+            DD_CUDA(h, cudaMemsetAsync(h->d_yb, 0, (size_t)h->cap_yb, h->stream));
+        }
+        DD_CUDA(h, cudaMemsetAsync(h->d_yb + (y_bytes - 12288), 0, 12288, h->stream));  // rows >= A of the last chunk
+        DD_CUDA(h, cudaMemcpyAsync(h->d_qb, h->d_omega_b, (size_t)q_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
 
     DD_CUDA(h, cudaMemsetAsync(sm, 0, sizeof(double) * SMALL_DOUBLES, h->stream));
     DD_CUDA(h, cudaMemsetAsync(h->d_Zacc, 0, sizeof(double) * (size_t)ld * LP, h->stream));
@@ -572,7 +593,10 @@ int run_pca(dd_handle *h, int n_power_iter) {
     for (int it = 0; it <= n_power_iter; it++) {
         const bool last = it == n_power_iter;
         // Y = D Q
-        DD_LAUNCH(h, "gemm_dq", k_gemm_dq<LP>, grid1, 128, gemm1_smem<LP>(), h->d_dense, h->d_Qt, h->d_Y, A, ld);
+        if (use_tc)
+            DD_TRY(dd_tc_gemm_dq(h));
+        else
+            DD_LAUNCH(h, "gemm_dq", k_gemm_dq<LP>, grid1, 128, gemm1_smem<LP>(), h->d_dense, h->d_Qt, h->d_Y, A, ld);
         // Y' = orth(Y - mean)
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_CSUM, 0, sizeof(double) * 2 * kMaxLP, h->stream));  // csum + ssum
@@ -581,10 +605,13 @@ int run_pca(dd_handle *h, int n_power_iter) {
         DD_LAUNCH(h, "chol_inv", k_chol_inv, 1, 64, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
                   sm + OFF_FLAG);
         DD_LAUNCH(h, "apply_tall", (k_apply<LP, 0>), tall_grid, 128, 0, h->d_Y, nullptr, A, L, sm + OFF_RINV,
-                  sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0);
+                  sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0, use_tc ? h->d_yb : nullptr);
         // Z = Dc^T Y'
-        DD_LAUNCH(h, "gemm_dty", k_gemm_dty<LP>, dim3(gblocks, splits), 128, gemm2_smem<LP>(), h->d_dense, h->d_Y,
-                  h->d_Zacc, A, ld, rows_per_split);
+        if (use_tc)
+            DD_TRY(dd_tc_gemm_dty(h));
+        else
+            DD_LAUNCH(h, "gemm_dty", k_gemm_dty<LP>, dim3(gblocks, splits), 128, gemm2_smem<LP>(), h->d_dense, h->d_Y,
+                      h->d_Zacc, A, ld, rows_per_split);
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
         DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
                   h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
@@ -592,7 +619,7 @@ int run_pca(dd_handle *h, int n_power_iter) {
             DD_LAUNCH(h, "chol_inv", k_chol_inv, 1, 64, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV,
                       sm + OFF_FLAG);
             DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
-                      sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld);
+                      sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, use_tc ? h->d_qb : nullptr);
         }
     }
     // svd(B) with B^T = Z:  B B^T = Z^T Z = gram
@@ -643,7 +670,13 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
         for (int64_t g = 0; g < h->G; g++)
             for (int j = 0; j < n_random; j++) qt[(size_t)j * ld + g] = omega_host[g * n_random + j];
         DD_CUDA(h, cudaMemcpyAsync(omega_dev, qt.data(), sizeof(float) * LP * ld, cudaMemcpyHostToDevice, h->stream));
-        DD_CUDA(h, cudaStreamSynchronize(h->stream));  // qt is a temporary
+        std::vector<uint8_t> packed;
+        if (LP == 40 && dd_tc_pca_enabled()) {
+            dd_tc_pack_omega(omega_host, h->G, n_random, ld, packed);
+            DD_TRY(dd_reserve(h, &h->d_omega_b, &h->cap_omega_b, (int64_t)packed.size()));
+            DD_CUDA(h, cudaMemcpyAsync(h->d_omega_b, packed.data(), packed.size(), cudaMemcpyHostToDevice, h->stream));
+        }
+        DD_CUDA(h, cudaStreamSynchronize(h->stream));  // qt / packed are temporaries
     } else if (h->L != n_random || h->LP != LP) {
         return dd_fail(h, DD_ERR_ARG, "pca: omega is NULL but no matching test matrix was uploaded before");
     }
