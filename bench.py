@@ -361,7 +361,8 @@ def run_ours(args, wl, counts):
         "rooflines": roofs,
         "peaks": {k_: peaks.get(k_) for k_ in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
         "e2e": {"value": e2e_value, "unit": "augmented-cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dt_e2e / args.steps, "doublets_called": n_doublets},
+                "ms_per_step": 1e3 * dt_e2e / args.steps, "doublets_called": n_doublets,
+                "host_ms_last_fit": {k_: round(v_, 1) for k_, v_ in clf.host_ms_.items()}},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -188,6 +188,9 @@ class BoostClassifier:
         if self.pseudocount == 1:
             raise NotImplementedError("pseudocount=1 selects the sparse log1p + arpack path (:296-297, :308), which is not on the B200 hot path")
 
+        import time as _time
+
+        _t = [_time.perf_counter()]
         raw_counts = check_array(  # :149-155
             raw_counts, accept_sparse="csr", ensure_all_finite=True, ensure_2d=True, dtype="float32"
         )
@@ -218,8 +221,10 @@ class BoostClassifier:
         for i in range(self.n_iters):
             parents[i] = self.rng.choice(num_cells, size=(num_synths, 2), replace=self.replace)
 
+        _t.append(_time.perf_counter())
         h = self._native()
         h.upload_counts(raw_counts)
+        _t.append(_time.perf_counter())
 
         it0, it1 = 0, self.n_iters
         dist = None
@@ -241,6 +246,7 @@ class BoostClassifier:
             resolution=float(self.clustering_kwargs["resolution"]), seed=int(self.random_state),
             n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1,
         )
+        _t.append(_time.perf_counter())
         if dist is not None:
             out = _allgather_iterations(dist, out, self.n_iters, self.device)
         self.stage_ms_ = out["stage_ms"]
@@ -251,6 +257,11 @@ class BoostClassifier:
         self.synth_communities_ = out["synth_communities"].astype(np.float64)
         self._parents_array = parents
         self._parents_lists = None
+        _t.append(_time.perf_counter())
+        # host-side wall time of the phases of this fit (ms): validation + HVG + parent draws, upload,
+        # the pipelined native loop, result collection
+        self.host_ms_ = dict(zip(("prologue", "upload", "fit_iterations", "collect"),
+                                 [1e3 * (b - a) for a, b in zip(_t[:-1], _t[1:])]))
         return self
 
     # ------------------------------------------------------------------ predict (:216-254)

@@ -276,17 +276,27 @@ extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, 
     if (indptr[0] != 0 || nnz < 0) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: bad indptr");
     if (nnz > 0 && (!indices || !data)) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: null indices/data");
     DD_CUDA(h, cudaSetDevice(h->device));
-    for (void *p : {(void *)h->d_indptr, (void *)h->d_indices, (void *)h->d_data, (void *)h->d_lib, (void *)h->d_l1})
-        if (p) cudaFree(p);
-    h->d_indptr = nullptr; h->d_indices = nullptr; h->d_data = nullptr; h->d_lib = nullptr; h->d_l1 = nullptr;
     h->N = n_cells; h->G = n_genes; h->nnz = nnz;
     h->ld = dd_round_up(n_genes, 32);
     h->synth_csr_valid = false; h->dense_valid = false; h->emb_valid = false; h->M = 0; h->A = 0;
-    DD_CUDA(h, cudaMalloc(&h->d_indptr, sizeof(int32_t) * (n_cells + 1)));
-    DD_CUDA(h, cudaMalloc(&h->d_indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-    DD_CUDA(h, cudaMalloc(&h->d_data, sizeof(float) * std::max<int64_t>(nnz, 1)));
-    DD_CUDA(h, cudaMalloc(&h->d_lib, sizeof(float) * n_cells));
-    DD_CUDA(h, cudaMalloc(&h->d_l1, sizeof(double) * n_cells));
+    // grow-only buffers: a second fit() on the same classifier re-uses the allocations
+    if (n_cells + 1 > h->cap_rows) {
+        for (void *p : {(void *)h->d_indptr, (void *)h->d_lib, (void *)h->d_l1})
+            if (p) cudaFree(p);
+        h->d_indptr = nullptr; h->d_lib = nullptr; h->d_l1 = nullptr; h->cap_rows = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_indptr, sizeof(int32_t) * (n_cells + 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_lib, sizeof(float) * n_cells));
+        DD_CUDA(h, cudaMalloc(&h->d_l1, sizeof(double) * n_cells));
+        h->cap_rows = n_cells + 1;
+    }
+    if (std::max<int64_t>(nnz, 1) > h->cap_nnz) {
+        if (h->d_indices) cudaFree(h->d_indices);
+        if (h->d_data) cudaFree(h->d_data);
+        h->d_indices = nullptr; h->d_data = nullptr; h->cap_nnz = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+        h->cap_nnz = std::max<int64_t>(nnz, 1);
+    }
     DD_CUDA(h, cudaMemcpyAsync(h->d_indptr, indptr, sizeof(int32_t) * (n_cells + 1), cudaMemcpyHostToDevice, h->stream));
     if (nnz > 0) {
         DD_CUDA(h, cudaMemcpyAsync(h->d_indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));

@@ -36,7 +36,7 @@ struct dd_handle {
     std::string err;
 
     // ---- raw counts (fit prologue) ----
-    int64_t N = 0, G = 0, nnz = 0;
+    int64_t N = 0, G = 0, nnz = 0, cap_rows = 0, cap_nnz = 0;
     int32_t *d_indptr = nullptr, *d_indices = nullptr;
     float *d_data = nullptr;
     float *d_lib = nullptr;   // float32 row sums (_lib_size)
@@ -84,6 +84,11 @@ struct dd_handle {
     int64_t cap_knn = 0;
     uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout
     int64_t cap_knn_ops = 0;
+
+    // ---- pinned host slots of the pipelined fit loop (kNN graph + PCA flag per in-flight iteration) ----
+    std::vector<int32_t *> slot_knn;
+    std::vector<double *> slot_flag;
+    int64_t slot_knn_elems = 0;
 
     // ---- accounting ----
     int64_t launches = 0;

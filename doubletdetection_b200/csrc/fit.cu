@@ -63,20 +63,35 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     int rc = DD_OK;
     std::string err;
     auto cleanup = [&]() {
-        for (Slot &s : slots) {
-            if (s.knn) cudaFreeHost(s.knn);
-            if (s.flag) cudaFreeHost(s.flag);
+        for (Slot &s : slots)
             if (s.done) cudaEventDestroy(s.done);
-        }
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
     };
-    for (Slot &s : slots) {
-        if (cudaMallocHost(&s.knn, sizeof(int32_t) * A * k) != cudaSuccess ||
-            cudaMallocHost(&s.flag, sizeof(double)) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
-            cleanup();
+    // pinned result slots live in the handle (grow-only): cudaMallocHost costs milliseconds per call
+    if (A * k > h->slot_knn_elems) {
+        for (int32_t *p : h->slot_knn) cudaFreeHost(p);
+        h->slot_knn.clear();
+        h->slot_knn_elems = A * k;
+    }
+    while ((int)h->slot_knn.size() < n_slots) {
+        int32_t *p = nullptr;
+        if (cudaMallocHost(&p, sizeof(int32_t) * h->slot_knn_elems) != cudaSuccess)
             return dd_fail(h, DD_ERR_NOMEM, "dd_fit_iterations: pinned host buffers");
+        h->slot_knn.push_back(p);
+    }
+    while ((int)h->slot_flag.size() < n_slots) {
+        double *p = nullptr;
+        if (cudaMallocHost(&p, sizeof(double)) != cudaSuccess)
+            return dd_fail(h, DD_ERR_NOMEM, "dd_fit_iterations: pinned host buffers");
+        h->slot_flag.push_back(p);
+    }
+    for (int s = 0; s < n_slots; s++) {
+        slots[s].knn = h->slot_knn[s];
+        slots[s].flag = h->slot_flag[s];
+        if (cudaEventCreateWithFlags(&slots[s].done, cudaEventDisableTiming) != cudaSuccess) {
+            cleanup();
+            return dd_fail(h, DD_ERR_CUDA, "dd_fit_iterations: event creation");
         }
     }
     for (cudaEvent_t &e : evs)

@@ -119,6 +119,8 @@ extern "C" void dd_destroy(dd_handle *h) {
     for (void *p : bufs)
         if (p) cudaFree(p);
     dd_tc_free(h);
+    for (int32_t *p : h->slot_knn) cudaFreeHost(p);
+    for (double *p : h->slot_flag) cudaFreeHost(p);
     resolve_pending(h);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -10,6 +10,9 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -79,47 +82,100 @@ bool one_level(const Graph &g, double gamma, double two_m, SplitMix64 &rng, std:
     const int32_t *indices = g.indices.data();
     int32_t head = 0, count = n;
     bool moved_any = false;
+    int32_t *comm_p = comm.data();
+    const double *kk = sc.k.data();
+    constexpr int kLocal = 48;  // low-degree nodes (every node of a kNN graph) gather their candidates on the stack
+    int32_t lc[kLocal];
+    double lw[kLocal];
     while (count > 0) {
         const int32_t i = queue[head];
+        // The queue order is a random permutation, so every pop would miss the caches on the node's adjacency
+        // list and on its neighbours' community ids; the FIFO content ahead is known -> software prefetch.
+        if (count > 24) {
+            int32_t p = head + 24;
+            if (p >= n) p -= n;
+            __builtin_prefetch(indptr + queue[p]);
+            p = head + 12;
+            if (p >= n) p -= n;
+            const int64_t pe = indptr[queue[p]];
+            __builtin_prefetch(indices + pe);
+            __builtin_prefetch(indices + pe + 16);
+            p = head + 4;
+            if (p >= n) p -= n;
+            const int32_t q4 = queue[p];
+            const int64_t qe0 = indptr[q4], qe1 = std::min<int64_t>(indptr[q4 + 1], qe0 + 32);
+            for (int64_t e = qe0; e < qe1; e++) __builtin_prefetch(comm_p + indices[e]);
+            __builtin_prefetch(comm_p + q4);
+            __builtin_prefetch(tot + q4);
+        }
         head = (head + 1 == n) ? 0 : head + 1;
         count--;
         inq[i] = 0;
-        const int32_t ci = comm[i];
-        const double ki = sc.k[i];
-        int32_t nc = 0;
-        cands[nc++] = ci;
-        seen[ci] = 1;
-        neigh_w[ci] = 0.0;
+        const int32_t ci = comm_p[i];
+        const double ki = kk[i];
         const int64_t e0 = indptr[i], e1 = indptr[i + 1];
-        for (int64_t e = e0; e < e1; e++) {
-            const int32_t c = comm[indices[e]];
-            if (!seen[c]) {
-                seen[c] = 1;
-                neigh_w[c] = 0.0;
-                cands[nc++] = c;
-            }
-            neigh_w[c] += unit ? 1.0 : g.weights[e];
-        }
-        tot[ci] -= ki;
-        const double gk = gamma * ki;
         int32_t best = ci;
-        double best_gain = neigh_w[ci] - (gk * tot[ci]) / two_m;
-        for (int32_t t = 1; t < nc; t++) {
-            const int32_t c = cands[t];
-            const double gn = neigh_w[c] - (gk * tot[c]) / two_m;
-            if (gn > best_gain) {
-                best = c;
-                best_gain = gn;
+        if (e1 - e0 < kLocal) {
+            // same candidate order (own community, then first appearance in the adjacency list) and the same
+            // arithmetic as the array-based path below, without touching the per-community scratch arrays
+            int32_t nc = 1;
+            lc[0] = ci;
+            lw[0] = 0.0;
+            for (int64_t e = e0; e < e1; e++) {
+                const int32_t c = comm_p[indices[e]];
+                int32_t t = 0;
+                while (t < nc && lc[t] != c) t++;
+                if (t == nc) {
+                    lc[nc] = c;
+                    lw[nc] = 0.0;
+                    nc++;
+                }
+                lw[t] += unit ? 1.0 : g.weights[e];
             }
+            tot[ci] -= ki;
+            const double gk = gamma * ki;
+            double best_gain = lw[0] - (gk * tot[ci]) / two_m;
+            for (int32_t t = 1; t < nc; t++) {
+                const double gn = lw[t] - (gk * tot[lc[t]]) / two_m;
+                if (gn > best_gain) {
+                    best = lc[t];
+                    best_gain = gn;
+                }
+            }
+        } else {
+            int32_t nc = 0;
+            cands[nc++] = ci;
+            seen[ci] = 1;
+            neigh_w[ci] = 0.0;
+            for (int64_t e = e0; e < e1; e++) {
+                const int32_t c = comm_p[indices[e]];
+                if (!seen[c]) {
+                    seen[c] = 1;
+                    neigh_w[c] = 0.0;
+                    cands[nc++] = c;
+                }
+                neigh_w[c] += unit ? 1.0 : g.weights[e];
+            }
+            tot[ci] -= ki;
+            const double gk = gamma * ki;
+            double best_gain = neigh_w[ci] - (gk * tot[ci]) / two_m;
+            for (int32_t t = 1; t < nc; t++) {
+                const int32_t c = cands[t];
+                const double gn = neigh_w[c] - (gk * tot[c]) / two_m;
+                if (gn > best_gain) {
+                    best = c;
+                    best_gain = gn;
+                }
+            }
+            for (int32_t t = 0; t < nc; t++) seen[cands[t]] = 0;
         }
-        for (int32_t t = 0; t < nc; t++) seen[cands[t]] = 0;
         tot[best] += ki;
         if (best != ci) {
-            comm[i] = best;
+            comm_p[i] = best;
             moved_any = true;
             for (int64_t e = e0; e < e1; e++) {
                 const int32_t j = indices[e];
-                if (comm[j] != best && !inq[j]) {
+                if (comm_p[j] != best && !inq[j]) {
                     inq[j] = 1;
                     int32_t tail = head + count;
                     if (tail >= n) tail -= n;
@@ -207,11 +263,18 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
     Scratch sc;
     if (two_m > 0.0) {
         std::vector<int32_t> comm, node2new;
+        static const bool trace = getenv("DD_LOUVAIN_TRACE") != nullptr;
         for (int level = 0; level < 64; level++) {
+            const auto t0 = std::chrono::steady_clock::now();
             const bool moved = one_level(g, resolution, two_m, rng, comm, sc);
+            const auto t1 = std::chrono::steady_clock::now();
             if (!moved) break;
             Graph ng;
             aggregate(g, comm, ng, node2new);
+            if (trace)
+                fprintf(stderr, "louvain level %d: n=%d nnz=%zu move %.1f ms aggregate %.1f ms -> n=%d\n", level, g.n,
+                        g.indices.size(), std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), ng.n);
             for (int32_t i = 0; i < n; i++) membership[i] = node2new[membership[i]];
             g = std::move(ng);
         }
