@@ -12,12 +12,13 @@
 #include "dd_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kMaxChunk = 8192;  // columns staged per pass: 32 KB per warp
+constexpr int kMaxChunk = 8192;  // columns staged per pass (upper bound): 32 KB per warp
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -34,7 +35,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // inplace_csr_row_normalize_l1 divides by (:184).  Integer-valued counts make both exact in any
 // summation order.
 __global__ void k_row_sums(const int32_t *__restrict__ indptr, const float *__restrict__ data, int64_t n_rows,
-                           float *__restrict__ lib, double *__restrict__ l1) {
+                           float *__restrict__ lib, double *__restrict__ l1, int *__restrict__ any_negative) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -46,6 +47,7 @@ __global__ void k_row_sums(const int32_t *__restrict__ indptr, const float *__re
             const float v = __ldg(data + p);
             acc += v;
             acc1 += fabs((double)v);
+            if (v < 0.f) *any_negative = 1;
         }
         acc = warp_sum_f(acc);
         acc1 = warp_sum_d(acc1);
@@ -178,13 +180,26 @@ __device__ __forceinline__ float norm_log(float x, double l1, float median, floa
     return logf(__fadd_rn(__fmul_rn(normed, median), pc));
 }
 
+// lower_bound of `col` in the sorted index range [s, e); returns e if absent / position of first >= col
+__device__ __forceinline__ int lower_bound_idx(const int32_t *__restrict__ indices, int s, int e, int col) {
+    while (s < e) {
+        const int m = (s + e) >> 1;
+        if (__ldg(indices + m) < col) s = m + 1; else e = m;
+    }
+    return s;
+}
+
 // Dense rows of the augmented matrix, originals (row < n_cells) and synthetics in one launch.
-// One warp per row: stage the row (or the sum of the two parent rows) in shared memory, turn it into
-// log-normalised values in place and stream it out with 128-bit stores.  Pad columns [G, ld) are 0.
+// One warp per row.  The per-warp shared-memory row buffer always holds log(pc) (0 in the pad columns); the
+// warp scatters the TRANSFORMED non-zeros into it (one division + log per stored entry, all lanes busy),
+// streams the buffer out with 128-bit stores and restores the constant on the way.  A synthetic row is
+// the sorted merge of its two parent rows: every entry looks its column up in the other parent by binary
+// search (the rows sit in L1/L2), so no raw staging pass is needed.
 __global__ void k_dense_rows(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                              const float *__restrict__ data, const double *__restrict__ l1_rows,
                              const int64_t *__restrict__ parents, int64_t n_cells, int64_t n_synth, int n_genes,
-                             int ld, int chunk, float median, float pc, float *__restrict__ dense) {
+                             int ld, int chunk, float median, float pc, int l1_additive,
+                             float *__restrict__ dense) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float *buf = smem + (size_t)w * chunk;
@@ -192,6 +207,11 @@ __global__ void k_dense_rows(const int32_t *__restrict__ indptr, const int32_t *
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
     const int64_t n_rows = n_cells + n_synth;
     const float logpc = logf(pc);
+    const int n_chunks = (ld + chunk - 1) / chunk;
+    if (n_chunks == 1) {  // the buffer keeps its constant fill across rows
+        for (int j = lane; j < chunk; j += 32) buf[j] = j < n_genes ? logpc : 0.f;
+        __syncwarp();
+    }
     for (int64_t row = warp; row < n_rows; row += n_warps) {
         const bool synth = row >= n_cells;
         int sa, ea, sb = 0, eb = 0;
@@ -207,49 +227,69 @@ __global__ void k_dense_rows(const int32_t *__restrict__ indptr, const int32_t *
             ea = indptr[pa + 1];
             sb = indptr[pb];
             eb = indptr[pb + 1];
-            l1 = 0.0;
-            if (n_genes > chunk) {  // several column chunks: the L1 norm needs its own pass
-                for (int c0 = 0; c0 < n_genes; c0 += chunk) {
-                    const int cw = min(chunk, n_genes - c0);
-                    stage_pair_sum(buf, c0, cw, indices, data, sa, ea, sb, eb, lane);
-                    for (int j = lane; j < cw; j += 32) l1 += fabs((double)buf[j]);
-                    __syncwarp();
+            if (l1_additive) {
+                // non-negative counts: |a + b| = |a| + |b|, exact in double for integer-valued data
+                l1 = l1_rows[pa] + l1_rows[pb];
+            } else {
+                double acc = 0.0;
+                for (int p = sa + lane; p < ea; p += 32) {
+                    const int c = __ldg(indices + p);
+                    const int q = lower_bound_idx(indices, sb, eb, c);
+                    float v = __ldg(data + p);
+                    if (q < eb && __ldg(indices + q) == c) v += __ldg(data + q);
+                    acc += fabs((double)v);
                 }
-                l1 = warp_sum_d(l1);
+                for (int p = sb + lane; p < eb; p += 32) {
+                    const int c = __ldg(indices + p);
+                    const int q = lower_bound_idx(indices, sa, ea, c);
+                    if (!(q < ea && __ldg(indices + q) == c)) acc += fabs((double)__ldg(data + p));
+                }
+                l1 = warp_sum_d(acc);
             }
         }
         float *out_row = dense + row * (int64_t)ld;
         for (int c0 = 0; c0 < ld; c0 += chunk) {
-            const int cw = min(chunk, ld - c0);           // multiple of 4 (ld and chunk are multiples of 32)
+            const int cw = min(chunk, ld - c0);            // multiple of 32
             const int cg = max(0, min(cw, n_genes - c0));  // real gene columns in this chunk
-            if (!synth) {
-                for (int j = lane; j < cw; j += 32) buf[j] = 0.f;
-                __syncwarp();
-                for (int p = sa + lane; p < ea; p += 32) {
-                    const int c = __ldg(indices + p) - c0;
-                    if ((unsigned)c < (unsigned)cg) buf[c] = __ldg(data + p);
-                }
-                __syncwarp();
-            } else {
-                stage_pair_sum(buf, c0, cg, indices, data, sa, ea, sb, eb, lane);
-                for (int j = cg + lane; j < cw; j += 32) buf[j] = 0.f;
-                if (n_genes <= chunk) {
-                    double acc = 0.0;
-                    for (int j = lane; j < cg; j += 32) acc += fabs((double)buf[j]);
-                    l1 = warp_sum_d(acc);
-                }
+            if (n_chunks > 1) {
+                for (int j = lane; j < cw; j += 32) buf[j] = j < cg ? logpc : 0.f;
                 __syncwarp();
             }
-            // transform + stream out, 4 columns per lane per step
-            for (int j = 4 * lane; j < cw; j += 128) {
-                float4 v = *reinterpret_cast<const float4 *>(buf + j);
-                float o[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int c = j + q;
-                    o[q] = c < cg ? (o[q] != 0.f ? norm_log(o[q], l1, median, pc) : logpc) : 0.f;
+            // scatter the transformed non-zeros of this column range
+            for (int p = sa + lane; p < ea; p += 32) {
+                const int col = __ldg(indices + p);
+                const int c = col - c0;
+                if ((unsigned)c < (unsigned)cg) {
+                    float v = __ldg(data + p);
+                    if (synth) {
+                        const int q = lower_bound_idx(indices, sb, eb, col);
+                        if (q < eb && __ldg(indices + q) == col) v += __ldg(data + q);
+                    }
+                    if (v != 0.f) buf[c] = norm_log(v, l1, median, pc);
                 }
-                __stcs(reinterpret_cast<float4 *>(out_row + c0 + j), make_float4(o[0], o[1], o[2], o[3]));
+            }
+            if (synth) {
+                for (int p = sb + lane; p < eb; p += 32) {
+                    const int col = __ldg(indices + p);
+                    const int c = col - c0;
+                    if ((unsigned)c < (unsigned)cg) {
+                        const int q = lower_bound_idx(indices, sa, ea, col);
+                        if (!(q < ea && __ldg(indices + q) == col)) {  // columns of both parents were done above
+                            const float v = __ldg(data + p);
+                            if (v != 0.f) buf[c] = norm_log(v, l1, median, pc);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // stream out; with a single chunk the buffer is reset to its constant fill for the next row
+            for (int j = 4 * lane; j < cw; j += 128) {
+                const float4 v = *reinterpret_cast<const float4 *>(buf + j);
+                __stcs(reinterpret_cast<float4 *>(out_row + c0 + j), v);
+                if (n_chunks == 1)
+                    *reinterpret_cast<float4 *>(buf + j) =
+                        make_float4(j < cg ? logpc : 0.f, j + 1 < cg ? logpc : 0.f, j + 2 < cg ? logpc : 0.f,
+                                    j + 3 < cg ? logpc : 0.f);
             }
             __syncwarp();
         }
@@ -258,8 +298,15 @@ __global__ void k_dense_rows(const int32_t *__restrict__ indptr, const int32_t *
 
 int pick_chunk(int64_t ld) { return (int)std::min<int64_t>(ld, kMaxChunk); }
 
+// The dense build is latency-bound with one 12 KB row buffer per warp (16 warps / SM); staging 1024 columns
+// at a time (4 KB per warp) lets 48 warps / SM overlap their gather / scatter / store phases.
+int pick_dense_chunk(int64_t ld) {
+    static const int env = getenv("DD_DENSE_CHUNK") ? atoi(getenv("DD_DENSE_CHUNK")) : 1024;
+    return (int)std::min<int64_t>(ld, std::max(32, env / 32 * 32));
+}
+
 int grid_for(dd_handle *h, size_t smem_bytes) {
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem_bytes, 1)));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / std::max<size_t>(smem_bytes + 1024, 1)));
     return h->num_sms * per_sm;
 }
 
@@ -286,7 +333,7 @@ extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, 
         h->d_indptr = nullptr; h->d_lib = nullptr; h->d_l1 = nullptr; h->cap_rows = 0;
         DD_CUDA(h, cudaMalloc(&h->d_indptr, sizeof(int32_t) * (n_cells + 1)));
         DD_CUDA(h, cudaMalloc(&h->d_lib, sizeof(float) * n_cells));
-        DD_CUDA(h, cudaMalloc(&h->d_l1, sizeof(double) * n_cells));
+        DD_CUDA(h, cudaMalloc(&h->d_l1, sizeof(double) * (n_cells + 1)));
         h->cap_rows = n_cells + 1;
     }
     if (std::max<int64_t>(nnz, 1) > h->cap_nnz) {
@@ -303,10 +350,15 @@ extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, 
         DD_CUDA(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->stream));
     }
     const int grid = h->num_sms * 8;
-    DD_LAUNCH(h, "row_sums", k_row_sums, grid, 256, 0, h->d_indptr, h->d_data, n_cells, h->d_lib, h->d_l1);
+    int *d_neg = reinterpret_cast<int *>(h->d_l1 + n_cells);  // one spare slot behind the L1 sums
+    DD_CUDA(h, cudaMemsetAsync(d_neg, 0, sizeof(int), h->stream));
+    DD_LAUNCH(h, "row_sums", k_row_sums, grid, 256, 0, h->d_indptr, h->d_data, n_cells, h->d_lib, h->d_l1, d_neg);
+    int neg = 0;
+    DD_CUDA(h, cudaMemcpyAsync(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->h_lib.resize(n_cells);
     DD_CUDA(h, cudaMemcpyAsync(h->h_lib.data(), h->d_lib, sizeof(float) * n_cells, cudaMemcpyDeviceToHost, h->stream));
     DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->nonneg = neg == 0;
     return DD_OK;
 }
 
@@ -441,7 +493,7 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
     if (!h->d_indptr || !h->d_parents || h->A == 0) return dd_fail(h, DD_ERR_ARG, "normalise: upload counts and parents first");
     const int64_t need = h->A * h->ld;
     DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, need));
-    const int chunk = pick_chunk(h->ld);
+    const int chunk = pick_dense_chunk(h->ld);
     const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
     static bool attr_set = false;
     if (!attr_set) {
@@ -450,7 +502,7 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
     }
     const int grid = grid_for(h, smem);
     DD_LAUNCH(h, "dense_rows", k_dense_rows, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
-              h->d_parents, h->N, h->M, (int)h->G, (int)h->ld, chunk, median, pseudocount, h->d_dense);
+              h->d_parents, h->N, h->M, (int)h->G, (int)h->ld, chunk, median, pseudocount, h->nonneg ? 1 : 0, h->d_dense);
     h->dense_valid = true;
     h->emb_valid = false;
     return DD_OK;

@@ -42,6 +42,7 @@ struct dd_handle {
     float *d_lib = nullptr;   // float32 row sums (_lib_size)
     double *d_l1 = nullptr;   // double sums of |x| (the L1 normaliser of sklearn)
     std::vector<float> h_lib;
+    bool nonneg = true;  // no negative value in the uploaded matrix (then L1 norms of row sums are additive)
 
     // ---- synthetics ----
     int64_t M = 0, cap_M = 0;

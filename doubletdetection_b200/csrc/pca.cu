@@ -34,7 +34,8 @@ constexpr int OFF_EVEC = OFF_SSUM + kMaxLP;
 constexpr int OFF_EVAL = OFF_EVEC + kMaxLP * kMaxLP;
 constexpr int OFF_T = OFF_EVAL + kMaxLP;               // L x KP embedding transform
 constexpr int OFF_FLAG = OFF_T + kMaxLP * kMaxLP;      // != 0: a factorisation broke down
-constexpr int SMALL_DOUBLES = OFF_FLAG + 8;
+constexpr int OFF_KEYS = OFF_FLAG + 8;                 // per component: packed (|w|, gene, sign) arg-max keys
+constexpr int SMALL_DOUBLES = OFF_KEYS + kMaxLP;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -277,58 +278,74 @@ __global__ void __launch_bounds__(256) k_gram(const float *__restrict__ Yf, doub
     if (tid < LP) atomicAdd(csum + tid, cs);
 }
 
-// Centre the Gram matrix (optional), Cholesky  Gc = R^T R,  Rinv = R^-1 (upper triangular).  One CTA of
-// 64 threads; thread j owns column j.
-__global__ void k_chol_inv(double *__restrict__ gram, const double *__restrict__ csum, double n_rows, int centre,
-                           int L, int LP, double *__restrict__ rinv, double *__restrict__ flag) {
+// Centre the Gram matrix (optional), factor it, Gc = R^T R (R upper triangular, right-looking Cholesky with the
+// trailing update spread over the whole CTA) and invert the factor.  Output: R^-1 (LP x LP, zero outside the
+// L x L upper triangle).  One CTA of 512 threads.
+__global__ void __launch_bounds__(512) k_chol(const double *__restrict__ gram, const double *__restrict__ csum,
+                                              double n_rows, int centre, int L, int LP, double *__restrict__ rout,
+                                              double *__restrict__ flag) {
     __shared__ double R[kMaxLP][kMaxLP + 1];
-    const int j = threadIdx.x;
-    for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) rinv[e] = 0.0;
-    if (j < L) {
-        for (int i = 0; i < L; i++) {
-            double g = gram[i * LP + j];
-            if (centre) g -= csum[i] * csum[j] / n_rows;
-            R[i][j] = g;
-        }
+    const int tid = threadIdx.x;
+    for (int e = tid; e < L * L; e += blockDim.x) {
+        const int i = e / L, j = e % L;
+        double g = gram[i * LP + j];
+        if (centre) g -= csum[i] * csum[j] / n_rows;
+        R[i][j] = g;
     }
     __syncthreads();
     for (int k = 0; k < L; k++) {
-        // row k of R from rows 0..k-1
-        if (j >= k && j < L) {
-            double s = R[k][j];
-            for (int p = 0; p < k; p++) s -= R[p][k] * R[p][j];
-            R[k][j] = s;  // un-normalised
-        }
-        __syncthreads();
         const double d = R[k][k];
         __syncthreads();
         double piv;
         if (!(d > 0.0) || !isfinite(d)) {
-            if (j == 0) flag[0] = 1.0;
+            if (tid == 0) flag[0] = 1.0;
             piv = 1.0;
         } else {
             piv = sqrt(d);
         }
-        if (j >= k && j < L) R[k][j] = (j == k) ? piv : R[k][j] / piv;
+        const double inv = 1.0 / piv;
+        for (int j = k + tid; j < L; j += blockDim.x) R[k][j] = (j == k) ? piv : R[k][j] * inv;
+        __syncthreads();
+        const int m = L - k - 1;  // trailing block is m x m, only j >= i is needed
+        for (int e = tid; e < m * m; e += blockDim.x) {
+            const int i = k + 1 + e / m, j = k + 1 + e % m;
+            if (j >= i) R[i][j] -= R[k][i] * R[k][j];
+        }
         __syncthreads();
     }
-    // back substitution: thread j solves column j of R^-1 (kept in global memory, own column only)
-    if (j < L) {
-        for (int i = j; i >= 0; i--) {
-            if (i == j) {
-                rinv[i * LP + j] = 1.0 / R[i][i];
-            } else {
-                double s = 0.0;
-                for (int p = i + 1; p <= j; p++) s += R[i][p] * rinv[p * LP + j];
-                rinv[i * LP + j] = -s / R[i][i];
+    // R^-1 (upper triangular) by back substitution, one column per group of 8 lanes; column j of the inverse
+    // is kept in row j of the (otherwise unused) lower triangle: X[p][j] lives in R[j][p] for p < j.
+    __shared__ double invd[kMaxLP];
+    if (tid < L) invd[tid] = 1.0 / R[tid][tid];
+    __syncthreads();
+    {
+        const int j = tid >> 3, sub = tid & 7;
+        const unsigned gmask = 0xFFu << (8 * ((tid & 31) >> 3));
+        if (j < L) {
+            for (int i = j - 1; i >= 0; i--) {
+                double part = 0.0;
+                for (int p = i + 1 + sub; p <= j; p += 8) part += R[i][p] * (p == j ? invd[j] : R[j][p]);
+                part += __shfl_xor_sync(gmask, part, 4);
+                part += __shfl_xor_sync(gmask, part, 2);
+                part += __shfl_xor_sync(gmask, part, 1);
+                if (sub == 0) R[j][i] = -part * invd[i];
+                __syncwarp(gmask);
             }
         }
     }
+    __syncthreads();
+    for (int e = tid; e < LP * LP; e += blockDim.x) {
+        const int i = e / LP, j = e % LP;
+        double v = 0.0;
+        if (i < L && j < L) v = i < j ? R[j][i] : (i == j ? invd[i] : 0.0);
+        rout[e] = v;
+    }
 }
 
-// Apply the triangular inverse.
-//   MODE 0 (tall): Y <- (Y - csum/n) Rinv in place (float), ssum += column sums of the new Y.
-//   MODE 1 (small): Qt[j][g] = (Z Rinv)[g][j] (float, transposed), and Zacc is cleared for the next pass.
+// Orthonormalise with the inverse Cholesky factor (float64 arithmetic, float32 result).
+//   MODE 0 (tall): Y <- (Y - csum/n) R^-1 in place, ssum += column sums of the new Y.
+//   MODE 1 (small): Qt[j][g] = (Z R^-1)[g][j] (transposed), and Zacc is cleared for the next pass.
+// When `bt` is given the result is also written as TF32 hi/lo operand tiles for the next tcgen05 GEMM.
 template <int LP, int MODE>
 __global__ void __launch_bounds__(128) k_apply(float *__restrict__ Yf, double *__restrict__ Zd, int64_t n_rows,
                                                int L, const double *__restrict__ rinv,
@@ -472,63 +489,55 @@ __global__ void __launch_bounds__(256) k_jacobi(const double *__restrict__ gram,
 
 constexpr size_t kJacobiSmem = sizeof(double) * 2 * kMaxLP * (kMaxLP + 1);
 
-// svd_flip(u_based_decision=False) + embedding transform.  W = Z Uhat = V S; the sign of component j is
-// the sign of the largest-|.| entry of column j of W (first index wins ties).  T[i][c] = Uhat[i][c] s_c sign_c
-// for c < C, zero for the padding columns up to KP.  One CTA, 256 threads.
+// svd_flip(u_based_decision=False): W = Z Uhat = V S; the sign of component j is the sign of the largest-|.|
+// entry of column j of W (first gene wins ties).  One thread per gene computes its row of W; the arg-max per
+// column is a 64-bit atomicMax over keys  [ |w| (float64 bits, low 21 mantissa bits dropped) | ~gene | sign ].
 template <int LP>
-__global__ void __launch_bounds__(256) k_signs_transform(const double *__restrict__ Zd, int n_genes, int L, int C,
-                                                         int KP, const double *__restrict__ evec,
-                                                         const double *__restrict__ eval, double *__restrict__ T,
-                                                         double *__restrict__ sing_out) {
+__global__ void __launch_bounds__(128) k_signs_w(const double *__restrict__ Zd, int n_genes, int L, int C,
+                                                 const double *__restrict__ evec,
+                                                 unsigned long long *__restrict__ keys) {
     __shared__ double Us[LP][LP + 1];
-    __shared__ double best_v[256];
-    __shared__ int best_i[256];
-    __shared__ double sign_s[LP];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < LP * LP; e += 256) Us[e / LP][e % LP] = evec[e];
+    for (int e = threadIdx.x; e < LP * LP; e += 128) Us[e / LP][e % LP] = evec[e];
     __syncthreads();
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    const bool ok = g < n_genes;
+    double z[LP];
+#pragma unroll
+    for (int i = 0; i < LP; i++) z[i] = ok ? Zd[(int64_t)g * LP + i] : 0.0;
+    const int lane = threadIdx.x & 31;
     for (int j = 0; j < C; j++) {
-        double bv = -1.0, bs = 0.0;
-        int bi = 0x7fffffff;
-        for (int g = tid; g < n_genes; g += 256) {
-            double w = 0.0;
-            for (int i = 0; i < L; i++) w = fma(Zd[(int64_t)g * LP + i], Us[i][j], w);
-            const double aw = fabs(w);
-            if (aw > bv) { bv = aw; bi = g; bs = w; }
+        double w = 0.0;
+#pragma unroll
+        for (int i = 0; i < LP; i++) w = fma(z[i], Us[i][j], w);
+        unsigned long long key = 0ull;
+        if (ok) {
+            const unsigned long long mag = ((unsigned long long)__double_as_longlong(fabs(w)) >> 21) << 21;
+            key = mag | ((unsigned long long)(0xFFFFFu - (unsigned)g) << 1) | (w < 0.0 ? 1ull : 0ull);
         }
-        best_v[tid] = bv;
-        best_i[tid] = bi;
-        __syncthreads();
-        // the signed value travels in a second pass to keep shared memory small
-        for (int off = 128; off > 0; off >>= 1) {
-            if (tid < off) {
-                const double ov = best_v[tid + off];
-                const int oi = best_i[tid + off];
-                if (ov > best_v[tid] || (ov == best_v[tid] && oi < best_i[tid])) {
-                    best_v[tid] = ov;
-                    best_i[tid] = oi;
-                }
-            }
-            __syncthreads();
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+            key = o > key ? o : key;
         }
-        if (best_i[0] == bi && bv >= 0.0) sign_s[j] = (bs < 0.0) ? -1.0 : 1.0;
-        __syncthreads();
+        if (lane == 0) atomicMax(keys + j, key);
     }
-    for (int e = tid; e < LP * KP; e += 256) {
-        const int i = e / KP, c = e % KP;
-        double v = 0.0;
-        if (i < L && c < C) v = Us[i][c] * sqrt(fmax(eval[c], 0.0)) * sign_s[c];
-        T[e] = v;
-    }
-    if (tid < C) sing_out[tid] = sqrt(fmax(eval[tid], 0.0));
 }
 
-// X_pca (A x KP float, zero padded beyond C) = Yq T
+// X_pca (A x KP float, zero padded beyond C) = Yq T,  T[i][c] = Uhat[i][c] s_c sign_c  (U = Q Uhat, scaled
+// by the singular values and flipped as sklearn does).  Block 0 also publishes the singular values.
 template <int LP, int KP>
-__global__ void __launch_bounds__(128) k_embed(const float *__restrict__ Yq, int64_t n_rows, const double *__restrict__ T,
-                                               float *__restrict__ emb) {
+__global__ void __launch_bounds__(128) k_embed(const float *__restrict__ Yq, int64_t n_rows, int L, int C,
+                                               const double *__restrict__ evec, const double *__restrict__ eval,
+                                               const unsigned long long *__restrict__ keys, float *__restrict__ emb,
+                                               double *__restrict__ sing_out) {
     __shared__ double Ts[LP][KP];
-    for (int e = threadIdx.x; e < LP * KP; e += blockDim.x) Ts[e / KP][e % KP] = T[e];
+    for (int e = threadIdx.x; e < LP * KP; e += blockDim.x) {
+        const int i = e / KP, c = e % KP;
+        double v = 0.0;
+        if (i < L && c < C) v = evec[i * LP + c] * sqrt(fmax(eval[c], 0.0)) * ((keys[c] & 1ull) ? -1.0 : 1.0);
+        Ts[i][c] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < C) sing_out[threadIdx.x] = sqrt(fmax(eval[threadIdx.x], 0.0));
     __syncthreads();
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
@@ -602,7 +611,7 @@ int run_pca(dd_handle *h, int n_power_iter) {
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_CSUM, 0, sizeof(double) * 2 * kMaxLP, h->stream));  // csum + ssum
         DD_LAUNCH(h, "gram_tall", (k_gram<LP, 0>), tall_grid, 256, 0, h->d_Y, nullptr, A, nullptr, 0.0, nullptr,
                   sm + OFF_GRAM, sm + OFF_CSUM);
-        DD_LAUNCH(h, "chol_inv", k_chol_inv, 1, 64, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
+        DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
                   sm + OFF_FLAG);
         DD_LAUNCH(h, "apply_tall", (k_apply<LP, 0>), tall_grid, 128, 0, h->d_Y, nullptr, A, L, sm + OFF_RINV,
                   sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0, use_tc ? h->d_yb : nullptr);
@@ -616,7 +625,7 @@ int run_pca(dd_handle *h, int n_power_iter) {
         DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
                   h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
         if (!last) {
-            DD_LAUNCH(h, "chol_inv", k_chol_inv, 1, 64, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV,
+            DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV,
                       sm + OFF_FLAG);
             DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
                       sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, use_tc ? h->d_qb : nullptr);
@@ -624,13 +633,16 @@ int run_pca(dd_handle *h, int n_power_iter) {
     }
     // svd(B) with B^T = Z:  B B^T = Z^T Z = gram
     DD_LAUNCH(h, "jacobi", k_jacobi, 1, 256, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
-    DD_LAUNCH(h, "signs_transform", k_signs_transform<LP>, 1, 256, 0, h->d_Zacc, (int)h->G, L, C, KP, sm + OFF_EVEC,
-              sm + OFF_EVAL, sm + OFF_T, sm + OFF_CSUM /* singular values */);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm + OFF_KEYS);
+    DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, h->d_Zacc, (int)h->G, L, C,
+              sm + OFF_EVEC, keys);
     const int egrid = (int)((A + 127) / 128);
     if (KP == 32)
-        DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, h->d_Y, A, sm + OFF_T, h->d_emb);
+        DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
+                  h->d_emb, sm + OFF_CSUM);
     else
-        DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, h->d_Y, A, sm + OFF_T, h->d_emb);
+        DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
+                  h->d_emb, sm + OFF_CSUM);
     return DD_OK;
 }
 
@@ -642,6 +654,7 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
     if (!h->dense_valid) return dd_fail(h, DD_ERR_ARG, "pca: no dense matrix (call dd_normalise_log first)");
     if (n_comp < 1 || n_random < n_comp || n_power_iter < 0) return dd_fail(h, DD_ERR_ARG, "pca: bad n_comp / n_random / n_power_iter");
     if (n_random > kMaxLP) return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 > 64 is outside the B200 hot path");
+    if (h->G > 0xFFFFF) return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: more than 2^20 - 1 genes");
     if (n_random > h->G || n_random > h->A)
         return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 exceeds the matrix dimensions");
     if (h->A < h->G)
