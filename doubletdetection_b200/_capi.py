@@ -321,7 +321,7 @@ class Handle:
             _ptr(scores, ctypes.c_double), _ptr(logp, ctypes.c_double), _ptr(comm, ctypes.c_int32),
             _ptr(synth_comm, ctypes.c_int32), _ptr(stage_ms, ctypes.c_double)))
         self.n_synth = n_synth
-        names = ["host_cluster_score", "normalise", "scale", "pca", "knn", "d2h", "device_total", "wall"]
+        names = ["host_cluster_score", "normalise", "scale", "pca", "knn", "cluster_gpu_d2h", "device_total", "wall"]
         return dict(scores=scores, log_p=logp, communities=comm, synth_communities=synth_comm[:, :n_synth],
                     stage_ms=dict(zip(names, stage_ms.tolist())))
 

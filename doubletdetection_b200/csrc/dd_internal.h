@@ -86,6 +86,18 @@ struct dd_handle {
     uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout
     int64_t cap_knn_ops = 0;
 
+    // ---- GPU Louvain level 0 (louvain_gpu.cu): symmetric kNN pattern as CSR + community state ----
+    int32_t *d_lv_off = nullptr, *d_lv_adj = nullptr, *d_lv_comm = nullptr, *d_lv_i32 = nullptr;
+    double *d_lv_tot = nullptr;
+    int64_t cap_lv_n = 0, cap_lv_nnz = 0;
+    int64_t lv_bucket_n = -1;
+    uint64_t lv_bucket_seed = 0;
+    std::vector<int32_t> lv_colour_off;
+    void *lv_graph_exec = nullptr;  // cudaGraphExec_t of the captured round sequence
+    int64_t lv_graph_n = -1, lv_graph_launches = 0;
+    double lv_graph_gamma = 0.0;
+    uint64_t lv_graph_seed = 0;
+
     // ---- pinned host slots of the pipelined fit loop (kNN graph + PCA flag per in-flight iteration) ----
     std::vector<int32_t *> slot_knn;
     std::vector<double *> slot_flag;
@@ -157,8 +169,12 @@ int dd_dev_standard_scale(dd_handle *h, float max_value);           // scale.cu
 int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter,
                const float *omega_host);                            // pca.cu
 int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
+int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed);  // louvain_gpu.cu
 
 // host pieces (louvain.cpp / score.cpp)
 int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
                         int32_t *labels_out, int32_t *n_comm_out);
+// upper Louvain levels from a first-level partition: off/adj = symmetric pattern CSR, comm0 = community per node
+int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *adj, const int32_t *comm0,
+                                double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
 float dd_host_median(std::vector<float> &v);

@@ -20,8 +20,8 @@ int dd_pca_flag_copy(dd_handle *h, double *host_flag);                      // p
 namespace {
 
 struct Slot {
-    int32_t *knn = nullptr;  // pinned, A * k
-    double *flag = nullptr;  // pinned, PCA breakdown flag
+    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1))]
+    double *flag = nullptr;    // pinned, PCA breakdown flag
     cudaEvent_t done = nullptr;
 };
 
@@ -52,8 +52,12 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
 
     const int64_t N = h->N, M = p->n_synth, A = N + M;
     const int k = p->knn_k;
-    const int n_threads = std::max(1, p->n_host_threads);
+    // the host side of an iteration (aggregate ~10^2 communities, upper Louvain levels, scoring) is tens of
+    // milliseconds, so a few workers keep up with the GPU
+    const int n_threads = std::max(1, std::min(p->n_host_threads, 8));
     const int n_slots = n_threads + 2;
+    const int64_t max_nnz = A * 2 * (k - 1);
+    const int64_t slot_elems = (A + 1) + A + max_nnz;
     const int n_run = p->iter_end - p->iter_begin;
     if (stage_ms_out) std::fill(stage_ms_out, stage_ms_out + 8, 0.0);
     if (n_run == 0) return DD_OK;
@@ -69,10 +73,10 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             if (e) cudaEventDestroy(e);
     };
     // pinned result slots live in the handle (grow-only): cudaMallocHost costs milliseconds per call
-    if (A * k > h->slot_knn_elems) {
+    if (slot_elems > h->slot_knn_elems) {
         for (int32_t *p : h->slot_knn) cudaFreeHost(p);
         h->slot_knn.clear();
-        h->slot_knn_elems = A * k;
+        h->slot_knn_elems = slot_elems;
     }
     while ((int)h->slot_knn.size() < n_slots) {
         int32_t *p = nullptr;
@@ -87,7 +91,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         h->slot_flag.push_back(p);
     }
     for (int s = 0; s < n_slots; s++) {
-        slots[s].knn = h->slot_knn[s];
+        slots[s].graph = h->slot_knn[s];
         slots[s].flag = h->slot_flag[s];
         if (cudaEventCreateWithFlags(&slots[s].done, cudaEventDisableTiming) != cudaSuccess) {
             cleanup();
@@ -136,8 +140,9 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             } else {
                 const auto t0 = now();
                 int32_t n_comm = 0;
-                wrc = dd_host_louvain_knn(A, k, s.knn, p->resolution, p->seed, labels.data(), &n_comm);
-                if (wrc != DD_OK) werr = "dd_fit_iterations: clustering rejected the kNN graph (index out of range)";
+                const int32_t *off = s.graph, *comm0 = s.graph + (A + 1), *adj = s.graph + (A + 1) + A;
+                wrc = dd_host_louvain_from_level0(A, off, adj, comm0, p->resolution, p->seed, labels.data(), &n_comm);
+                if (wrc != DD_OK) werr = "dd_fit_iterations: clustering rejected the device graph";
                 if (wrc == DD_OK) {
                     wrc = dd_score(N, M, labels.data(), scores_out + (size_t)job.iter * N, log_p_out + (size_t)job.iter * N);
                     std::copy(labels.begin(), labels.begin() + N, communities_out + (size_t)job.iter * N);
@@ -192,7 +197,11 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         cudaEventRecord(ev[3], h->stream);
         if ((rc = dd_dev_knn(h, k)) != DD_OK) break;
         cudaEventRecord(ev[4], h->stream);
-        cudaMemcpyAsync(s.knn, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, h->stream);
+        // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device
+        if ((rc = dd_dev_louvain_level0(h, k, p->resolution, p->seed)) != DD_OK) break;
+        cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(s.graph + (A + 1), h->d_lv_comm, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, h->stream);
         dd_pca_flag_copy(h, s.flag);
         cudaEventRecord(ev[5], h->stream);
         cudaEventRecord(s.done, h->stream);

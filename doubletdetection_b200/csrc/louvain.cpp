@@ -250,7 +250,73 @@ void aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &out, std
     if (out.weights.empty()) out.weights.push_back(0.0);  // keep "empty == unit weights" unambiguous
 }
 
-int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out) {
+// First level by synchronous coloured rounds on the host (the twin of louvain_gpu.cu; specification:
+// oracle/louvain_ref.py:level0_parallel).  Unweighted graphs only.
+constexpr int kColours = 8, kMaxRounds = 32;
+inline int colour_of(uint64_t seed, int32_t i) {
+    uint64_t z = seed + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (int)(z % kColours);
+}
+
+void level0_parallel_host(const Graph &g, double gamma, double two_m, uint64_t seed, std::vector<int32_t> &comm) {
+    const int32_t n = g.n;
+    comm.resize(n);
+    std::vector<double> tot(n), cnt(n, 0.0);
+    std::vector<int32_t> size(n, 1), desired(n, -1);
+    std::vector<std::vector<int32_t>> bucket(kColours);
+    for (int32_t i = 0; i < n; i++) {
+        comm[i] = i;
+        tot[i] = (double)(g.indptr[i + 1] - g.indptr[i]);
+        bucket[colour_of(seed, i)].push_back(i);
+    }
+    for (int round = 0; round < kMaxRounds; round++) {
+        int64_t moved = 0;
+        for (int c = 0; c < kColours; c++) {
+            for (int32_t i : bucket[c]) {  // decide from the frozen state
+                desired[i] = -1;
+                const int64_t e0 = g.indptr[i], e1 = g.indptr[i + 1];
+                if (e1 == e0) continue;
+                const int32_t ci = comm[i];
+                const double ki = (double)(e1 - e0), gk = gamma * ki;
+                for (int64_t e = e0; e < e1; e++) cnt[comm[g.indices[e]]] += 1.0;
+                const double gain_stay = cnt[ci] - (gk * (tot[ci] - ki)) / two_m;
+                int32_t best = -1;
+                double best_gain = 0.0;
+                for (int64_t e = e0; e < e1; e++) {
+                    const int32_t cc = comm[g.indices[e]];
+                    if (cc == ci) continue;
+                    const double gn = cnt[cc] - (gk * tot[cc]) / two_m;
+                    if (best < 0 || gn > best_gain || (gn == best_gain && cc < best)) {
+                        best = cc;
+                        best_gain = gn;
+                    }
+                }
+                for (int64_t e = e0; e < e1; e++) cnt[comm[g.indices[e]]] = 0.0;
+                if (best >= 0 && best_gain > gain_stay && !(size[ci] == 1 && size[best] == 1 && best > ci)) desired[i] = best;
+            }
+            for (int32_t i : bucket[c]) {  // apply simultaneously
+                const int32_t b = desired[i];
+                if (b < 0) continue;
+                const int32_t ci = comm[i];
+                const double ki = (double)(g.indptr[i + 1] - g.indptr[i]);
+                comm[i] = b;
+                tot[ci] -= ki;
+                tot[b] += ki;
+                size[ci]--;
+                size[b]++;
+                moved++;
+            }
+        }
+        if (moved <= (int64_t)(n >> 9)) break;  // at most n / 512 moves: the level is settled
+    }
+}
+
+// comm0: optional first-level partition (community id per node, any ids in [0, n)); parallel0: compute it here.
+int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out,
+                const int32_t *comm0 = nullptr, bool parallel0 = false) {
     const int32_t n = g.n;
     double two_m = 0.0;
     if (g.weights.empty())
@@ -261,6 +327,17 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
     std::iota(membership.begin(), membership.end(), 0);
     SplitMix64 rng{seed};
     Scratch sc;
+    if (two_m > 0.0 && (comm0 != nullptr || parallel0)) {
+        std::vector<int32_t> comm, node2new;
+        if (comm0 != nullptr)
+            comm.assign(comm0, comm0 + n);
+        else
+            level0_parallel_host(g, resolution, two_m, seed, comm);
+        Graph ng;
+        aggregate(g, comm, ng, node2new);
+        for (int32_t i = 0; i < n; i++) membership[i] = node2new[membership[i]];
+        g = std::move(ng);
+    }
     if (two_m > 0.0) {
         std::vector<int32_t> comm, node2new;
         static const bool trace = getenv("DD_LOUVAIN_TRACE") != nullptr;
@@ -339,7 +416,24 @@ int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double res
         g.indptr[i + 1] = (int64_t)g.indices.size();
     }
     g.selfw.assign(n, 0.0);
-    return run_louvain(g, resolution, seed, labels_out, n_comm_out);
+    return run_louvain(g, resolution, seed, labels_out, n_comm_out, nullptr, /*parallel0=*/true);
+}
+
+// The pipeline's path: the GPU built the pattern graph and optimised the first level; aggregate and finish here.
+int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *adj, const int32_t *comm0,
+                                double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out) {
+    if (n < 0 || (n > 0 && (!off || !comm0 || !labels_out))) return DD_ERR_ARG;
+    Graph g;
+    g.n = (int32_t)n;
+    g.indptr.resize(n + 1);
+    for (int64_t i = 0; i <= n; i++) g.indptr[i] = off[i];
+    const int64_t nnz = n > 0 ? off[n] : 0;
+    if (nnz > 0 && !adj) return DD_ERR_ARG;
+    g.indices.assign(adj, adj + nnz);
+    for (int64_t i = 0; i < n; i++)
+        if (comm0[i] < 0 || comm0[i] >= n) return DD_ERR_ARG;
+    g.selfw.assign(n, 0.0);
+    return run_louvain(g, resolution, seed, labels_out, n_comm_out, comm0, false);
 }
 
 extern "C" int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,

@@ -1,0 +1,448 @@
+// louvain_gpu.cu -- the first (and by far largest) Louvain level of the clustering call on the GPU.
+//
+// The kNN pipeline optimises the first level by synchronous coloured rounds (specification:
+// oracle/louvain_ref.py:level0_parallel; host twin: louvain.cpp:level0_parallel_host): 8 colour classes,
+// all nodes of a class decide simultaneously from the frozen state, moves are applied at once, up to 32
+// rounds.  Everything the decision needs is integer-valued (unweighted graph), so float64 atomics are exact
+// and the result does not depend on scheduling.  This file also builds the symmetrised kNN pattern
+// (i ~ j iff j in kNN(i) or i in kNN(j)) as CSR on the device; the host only aggregates the ~10^2
+// communities that come out and runs the (tiny) upper levels.
+#include "dd_internal.h"
+
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int kColours = 8;
+constexpr int kMaxRounds = 32;
+
+__host__ __device__ inline int colour_of(uint64_t seed, int i) {
+    uint64_t z = seed + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (int)(z % kColours);
+}
+
+__device__ __forceinline__ bool in_out_list(const int32_t *__restrict__ knn, int k, int j, int i) {
+    for (int c = 0; c < k; c++)
+        if (knn[(int64_t)j * k + c] == i) return true;
+    return false;
+}
+
+// deg[j] = out-neighbours of j + in-neighbours of j that are not among its out-neighbours
+__global__ void k_graph_count(const int32_t *__restrict__ knn, int n, int k, int32_t *__restrict__ deg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int out = 0;
+    for (int c = 0; c < k; c++) {
+        const int j = knn[(int64_t)i * k + c];
+        if (j == i || j < 0) continue;
+        out++;
+        if (!in_out_list(knn, k, j, i)) atomicAdd(deg + j, 1);
+    }
+    atomicAdd(deg + i, out);
+}
+
+// single CTA: exclusive scan of deg -> off[0..n], state reset
+__global__ void k_graph_scan(const int32_t *__restrict__ deg, int n, int32_t *__restrict__ off,
+                             int32_t *__restrict__ counters) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int per = (n + nt - 1) / nt;
+    const int b = min(t * per, n), e = min(b + per, n);
+    long long s = 0;
+    for (int i = b; i < e; i++) s += deg[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        long long run = 0;
+        for (int i = 0; i < nt; i++) {
+            const long long v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        off[n] = (int32_t)run;
+        counters[0] = 0;  // moved in this round
+        counters[1] = 0;  // done flag
+        counters[2] = 0;  // rounds executed
+        counters[3] = 0;  // grid barrier arrivals (cooperative kernel)
+    }
+    __syncthreads();
+    long long run = part[t];
+    for (int i = b; i < e; i++) {
+        off[i] = (int32_t)run;
+        run += deg[i];
+    }
+}
+
+// adjacency rows: the node's own out-neighbours first, then the in-neighbours that are not out-neighbours
+// (claimed with an atomic cursor: their order inside the row is irrelevant to the algorithm)
+__global__ void k_graph_fill(const int32_t *__restrict__ knn, int n, int k, const int32_t *__restrict__ off,
+                             int32_t *__restrict__ cursor, int32_t *__restrict__ adj, int32_t *__restrict__ comm,
+                             double *__restrict__ tot, int32_t *__restrict__ csize) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int out = 0;
+    for (int c = 0; c < k; c++) {
+        const int j = knn[(int64_t)i * k + c];
+        if (j == i || j < 0) continue;
+        adj[off[i] + out] = j;
+        out++;
+    }
+    for (int c = 0; c < k; c++) {
+        const int j = knn[(int64_t)i * k + c];
+        if (j == i || j < 0) continue;
+        if (!in_out_list(knn, k, j, i)) {
+            int outj = 0;
+            for (int cc = 0; cc < k; cc++) {
+                const int jj = knn[(int64_t)j * k + cc];
+                outj += (jj != j && jj >= 0);
+            }
+            const int pos = atomicAdd(cursor + j, 1);
+            adj[off[j] + outj + pos] = i;
+        }
+    }
+    comm[i] = i;
+    tot[i] = (double)(off[i + 1] - off[i]);
+    csize[i] = 1;
+}
+
+// per-warp open-addressing table (community -> number of neighbours in it) for nodes with more than 32
+// neighbours; kTable slots, linear probing.  Degrees above kTableMaxDeg fall back to a quadratic scan.
+constexpr int kTable = 512, kTableMaxDeg = 384;
+__device__ __forceinline__ int propose_one(const int32_t *__restrict__ off, const int32_t *__restrict__ adj,
+                                           const int32_t *comm, const double *tot, const int32_t *csize, int i,
+                                           double gamma, double two_m, int32_t *tkey, int32_t *tcnt, int lane) {
+    const int s = off[i], d = off[i + 1] - s;
+    if (d <= 0) return -1;
+    const int ci = __ldcg(comm + i);
+    const double ki = (double)d;
+    const double gk = __dmul_rn(gamma, ki);
+    double best_gain = 0.0;
+    int best = 0x7fffffff;
+    int w_stay = 0;
+    if (d <= 32) {
+        const int c = lane < d ? __ldcg(comm + adj[s + lane]) : -1 - lane;  // unique sentinels never match
+        const int wc = __popc(__match_any_sync(0xffffffffu, c));
+        w_stay = __popc(__ballot_sync(0xffffffffu, c == ci));
+        if (lane < d && c != ci) {
+            best = c;
+            best_gain = __dsub_rn((double)wc, __ddiv_rn(__dmul_rn(gk, __ldcg(tot + c)), two_m));
+        }
+    } else if (d <= kTableMaxDeg) {
+        __syncwarp();
+        for (int t = lane; t < kTable; t += 32) {
+            tkey[t] = -1;
+            tcnt[t] = 0;
+        }
+        __syncwarp();
+        for (int f = lane; f < d; f += 32) {
+            const int c = __ldcg(comm + adj[s + f]);
+            unsigned slot = ((unsigned)c * 2654435761u) >> 23;  // 9 bits
+            for (;;) {
+                const int prev = atomicCAS(tkey + slot, -1, c);
+                if (prev == -1 || prev == c) break;
+                slot = (slot + 1) & (kTable - 1);
+            }
+            atomicAdd(tcnt + slot, 1);
+        }
+        __syncwarp();
+        for (int t = lane; t < kTable; t += 32) {
+            const int c = tkey[t];
+            if (c < 0) continue;
+            const int wc = tcnt[t];
+            if (c == ci) {
+                w_stay = wc;
+                continue;
+            }
+            const double gn = __dsub_rn((double)wc, __ddiv_rn(__dmul_rn(gk, __ldcg(tot + c)), two_m));
+            if (best == 0x7fffffff || gn > best_gain || (gn == best_gain && c < best)) {
+                best = c;
+                best_gain = gn;
+            }
+        }
+        w_stay = __reduce_add_sync(0xffffffffu, w_stay);  // at most one lane holds the own-community count
+    } else {
+        for (int f = lane; f < d; f += 32) w_stay += (__ldcg(comm + adj[s + f]) == ci);
+        w_stay = __reduce_add_sync(0xffffffffu, w_stay);
+        for (int e = lane; e < d; e += 32) {
+            const int c = __ldcg(comm + adj[s + e]);
+            if (c == ci) continue;
+            int wc = 0;
+            for (int f = 0; f < d; f++) wc += (__ldcg(comm + adj[s + f]) == c);
+            const double gn = __dsub_rn((double)wc, __ddiv_rn(__dmul_rn(gk, __ldcg(tot + c)), two_m));
+            if (best == 0x7fffffff || gn > best_gain || (gn == best_gain && c < best)) {
+                best = c;
+                best_gain = gn;
+            }
+        }
+    }
+    const double gain_stay = __dsub_rn((double)w_stay, __ddiv_rn(__dmul_rn(gk, __dsub_rn(__ldcg(tot + ci), ki)), two_m));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ob != 0x7fffffff && (best == 0x7fffffff || og > best_gain || (og == best_gain && ob < best))) {
+            best = ob;
+            best_gain = og;
+        }
+    }
+    if (best != 0x7fffffff && best_gain > gain_stay &&
+        !(__ldcg(csize + ci) == 1 && __ldcg(csize + best) == 1 && best > ci))
+        return best;
+    return -1;
+}
+
+// one warp per node of the current colour (multi-launch / CUDA-graph variant of the rounds)
+__global__ void __launch_bounds__(256) k_lv_propose(const int32_t *__restrict__ off, const int32_t *__restrict__ adj,
+                                                    const int32_t *__restrict__ comm, const double *__restrict__ tot,
+                                                    const int32_t *__restrict__ csize,
+                                                    const int32_t *__restrict__ bucket, int b0, int b1, int n,
+                                                    double gamma, int32_t *__restrict__ desired,
+                                                    const int32_t *__restrict__ counters) {
+    __shared__ int32_t s_tab[8 * 2 * kTable];
+    if (counters[1]) return;  // converged in an earlier round
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+    if (b0 + w >= b1) return;
+    const int i = bucket[b0 + w];
+    const double two_m = (double)off[n];
+    const int res = propose_one(off, adj, comm, tot, csize, i, gamma, two_m, s_tab + wl * 2 * kTable,
+                                s_tab + wl * 2 * kTable + kTable, lane);
+    if (lane == 0) desired[i] = res;
+}
+
+__global__ void k_lv_apply(const int32_t *__restrict__ off, int32_t *__restrict__ comm, double *__restrict__ tot,
+                           int32_t *__restrict__ csize, const int32_t *__restrict__ bucket, int b0, int b1,
+                           const int32_t *__restrict__ desired, int32_t *__restrict__ counters) {
+    if (counters[1]) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b0 + t >= b1) return;
+    const int i = bucket[b0 + t];
+    const int b = desired[i];
+    if (b < 0) return;
+    const int ci = comm[i];
+    const double ki = (double)(off[i + 1] - off[i]);
+    comm[i] = b;
+    atomicAdd(tot + ci, -ki);
+    atomicAdd(tot + b, ki);
+    atomicSub(csize + ci, 1);
+    atomicAdd(csize + b, 1);
+    atomicAdd(counters, 1);
+}
+
+// a round that moved at most n / 512 nodes ends the level (the stragglers oscillate or trickle; the levels
+// above merge whole communities anyway)
+__global__ void k_lv_round_end(int32_t *__restrict__ counters, int n) {
+    if (counters[1]) return;
+    counters[2]++;
+    if (counters[0] <= (n >> 9)) counters[1] = 1;
+    counters[0] = 0;
+}
+
+// All rounds in ONE cooperative launch: the 500+ sub-round steps are separated by grid-wide barriers instead of
+// kernel boundaries (a launch per step made the level launch-bound).  Mutable state is read with ld.global.cg
+// (L1 is not coherent across SMs inside a kernel).
+struct ColourOffsets {
+    int v[kColours + 1];
+};
+
+// grid-wide barrier for a co-resident grid (cooperative launch): one arrival per CTA on a monotonically
+// increasing counter; ~2 us, where cooperative_groups' grid.sync() measured ~15 us on 592 CTAs.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int n_blocks, unsigned int &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += n_blocks;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*(volatile unsigned int *)bar < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int kRoundThreads = 1024;
+constexpr size_t kRoundSmem = sizeof(int32_t) * (kRoundThreads / 32) * 2 * kTable;  // 128 KB
+__global__ void __launch_bounds__(kRoundThreads, 1) k_lv_rounds(const int32_t *__restrict__ off,
+                                                               const int32_t *__restrict__ adj, int32_t *comm,
+                                                               double *tot, int32_t *csize,
+                                                               const int32_t *__restrict__ bucket, ColourOffsets co,
+                                                               int n, double gamma, int32_t *desired,
+                                                               int32_t *counters) {
+    extern __shared__ int32_t s_tab[];  // per warp: kTable keys + kTable counts
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    constexpr int WPB = kRoundThreads / 32;
+    int32_t *tkey = s_tab + (size_t)wl * 2 * kTable, *tcnt = tkey + kTable;
+    const int n_warps = gridDim.x * WPB, gw = blockIdx.x * WPB + wl;
+    const int n_thr = gridDim.x * kRoundThreads, gt = blockIdx.x * kRoundThreads + threadIdx.x;
+    const double two_m = (double)off[n];
+    unsigned int *bar = reinterpret_cast<unsigned int *>(counters + 3);
+    unsigned int target = 0;
+    for (int round = 0; round < kMaxRounds; round++) {
+        for (int c = 0; c < kColours; c++) {
+            const int b0 = co.v[c], b1 = co.v[c + 1];
+            for (int t = b0 + gw; t < b1; t += n_warps) {
+                const int i = bucket[t];
+                const int res = propose_one(off, adj, comm, tot, csize, i, gamma, two_m, tkey, tcnt, lane);
+                if (lane == 0) desired[i] = res;
+            }
+            grid_barrier(bar, gridDim.x, target);
+            int moved = 0;
+            for (int t = b0 + gt; t < b1; t += n_thr) {
+                const int i = bucket[t];
+                const int b = __ldcg(desired + i);
+                if (b < 0) continue;
+                const int ci = __ldcg(comm + i);
+                const double ki = (double)(off[i + 1] - off[i]);
+                comm[i] = b;
+                atomicAdd(tot + ci, -ki);
+                atomicAdd(tot + b, ki);
+                atomicSub(csize + ci, 1);
+                atomicAdd(csize + b, 1);
+                moved++;
+            }
+            if (moved) atomicAdd(counters, moved);
+            grid_barrier(bar, gridDim.x, target);
+        }
+        const int total = __ldcg(counters);
+        grid_barrier(bar, gridDim.x, target);  // everyone has read the round's move count before it is reset
+        if (gt == 0) {
+            counters[0] = 0;
+            counters[2] = round + 1;
+        }
+        if (total <= (n >> 9)) break;  // uniform across the grid
+    }
+}
+
+}  // namespace
+
+// Build the symmetric kNN pattern from h->d_knn_idx (n x k, self in column 0) and run the parallel first
+// Louvain level.  Results (device): h->d_lv_off (n + 1), h->d_lv_adj (off[n] entries), h->d_lv_comm (n).
+// Fully asynchronous on h->stream (no host read-back: the colour classes depend only on (n, seed) and are
+// bucketed on the host once).
+int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) {
+    const int64_t n64 = h->emb_rows;
+    if (n64 >= (1ll << 31) / (2 * k)) return dd_fail(h, DD_ERR_UNSUPPORTED, "louvain: graph too large for int32 offsets");
+    const int n = (int)n64;
+    const int64_t max_nnz = (int64_t)n * 2 * (k - 1);
+    if (n > h->cap_lv_n || max_nnz > h->cap_lv_nnz) {
+        for (void *p : {(void *)h->d_lv_off, (void *)h->d_lv_adj, (void *)h->d_lv_comm, (void *)h->d_lv_tot, (void *)h->d_lv_i32})
+            if (p) cudaFree(p);
+        h->d_lv_off = h->d_lv_adj = h->d_lv_comm = h->d_lv_i32 = nullptr;
+        h->d_lv_tot = nullptr;
+        h->cap_lv_n = 0; h->cap_lv_nnz = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_lv_off, sizeof(int32_t) * (n + 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_lv_adj, sizeof(int32_t) * std::max<int64_t>(max_nnz, 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_lv_comm, sizeof(int32_t) * n));
+        DD_CUDA(h, cudaMalloc(&h->d_lv_tot, sizeof(double) * n));
+        // deg | cursor | csize | desired | bucket (n each) + counters
+        DD_CUDA(h, cudaMalloc(&h->d_lv_i32, sizeof(int32_t) * (5 * (size_t)n + 16)));
+        h->cap_lv_n = n; h->cap_lv_nnz = max_nnz;
+        h->lv_bucket_n = -1;
+        h->lv_graph_n = -1;  // the captured launches hold the old pointers
+    }
+    int32_t *deg = h->d_lv_i32, *cursor = deg + h->cap_lv_n, *csize = cursor + h->cap_lv_n,
+            *desired = csize + h->cap_lv_n, *bucket = desired + h->cap_lv_n, *counters = bucket + h->cap_lv_n;
+    if (h->lv_bucket_n != n || h->lv_bucket_seed != seed) {  // colour classes: a pure function of (n, seed)
+        std::vector<int32_t> cnt(kColours + 1, 0), nodes(n);
+        for (int i = 0; i < n; i++) cnt[colour_of(seed, i) + 1]++;
+        for (int c = 0; c < kColours; c++) cnt[c + 1] += cnt[c];
+        h->lv_colour_off.assign(cnt.begin(), cnt.end());
+        std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+        for (int i = 0; i < n; i++) nodes[fill[colour_of(seed, i)]++] = i;
+        DD_CUDA(h, cudaMemcpyAsync(bucket, nodes.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+        DD_CUDA(h, cudaStreamSynchronize(h->stream));  // `nodes` is a temporary (once per fit)
+        h->lv_bucket_n = n;
+        h->lv_bucket_seed = seed;
+    }
+    DD_CUDA(h, cudaMemsetAsync(deg, 0, sizeof(int32_t) * 2 * (size_t)h->cap_lv_n, h->stream));  // deg + cursor
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    DD_LAUNCH(h, "lv_graph_count", k_graph_count, nb, 256, 0, h->d_knn_idx, n, (int)k, deg);
+    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan, 1, 1024, 0, deg, n, h->d_lv_off, counters);
+    DD_LAUNCH(h, "lv_graph_fill", k_graph_fill, nb, 256, 0, h->d_knn_idx, n, (int)k, h->d_lv_off, cursor, h->d_lv_adj,
+              h->d_lv_comm, h->d_lv_tot, csize);
+    // default: ALL rounds in one cooperative launch (one CTA per SM, hand-written grid barrier);
+    // DD_LOUVAIN_GRAPH=1: one launch per step replayed from a CUDA graph (~10 us per step: launch-latency bound).
+    static const bool use_graph = getenv("DD_LOUVAIN_GRAPH") != nullptr;
+    if (!use_graph) {
+        const int blocks_per_sm = 1;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_lv_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRoundSmem);
+            attr_set = true;
+        }
+        ColourOffsets co;
+        for (int c = 0; c <= kColours; c++) co.v[c] = h->lv_colour_off[c];
+        int n_arg = n;
+        double g_arg = gamma;
+        const int32_t *off_p = h->d_lv_off, *adj_p = h->d_lv_adj, *bucket_p = bucket;
+        int32_t *comm_p = h->d_lv_comm, *csize_p = csize, *desired_p = desired, *counters_p = counters;
+        double *tot_p = h->d_lv_tot;
+        void *args[] = {&off_p, &adj_p, &comm_p, &tot_p, &csize_p, &bucket_p, &co, &n_arg, &g_arg, &desired_p, &counters_p};
+        dd_launch_begin(h);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_lv_rounds, dim3(h->num_sms * blocks_per_sm), dim3(kRoundThreads),
+                                                    args, kRoundSmem, h->stream);
+        if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("cooperative launch of lv_rounds: ") + cudaGetErrorString(e));
+        DD_TRY(dd_launch_end(h, "lv_rounds"));
+        return DD_OK;
+    }
+    if (h->lv_graph_exec == nullptr || h->lv_graph_n != n || h->lv_graph_gamma != gamma || h->lv_graph_seed != seed) {
+        if (h->lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lv_graph_exec);
+        h->lv_graph_exec = nullptr;
+        const bool timing = h->timing;
+        const int64_t launches_before = h->launches;
+        h->timing = false;  // no event records inside the capture
+        DD_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = DD_OK;
+        for (int round = 0; round < kMaxRounds && rc == DD_OK; round++) {
+            for (int c = 0; c < kColours && rc == DD_OK; c++) {
+                const int b0 = h->lv_colour_off[c], b1 = h->lv_colour_off[c + 1];
+                if (b1 == b0) continue;
+                dd_launch_begin(h);
+                k_lv_propose<<<(unsigned)((b1 - b0 + 7) / 8), 256, 0, h->stream>>>(h->d_lv_off, h->d_lv_adj, h->d_lv_comm,
+                                                                                    h->d_lv_tot, csize, bucket, b0, b1, n,
+                                                                                    gamma, desired, counters);
+                rc = dd_launch_end(h, "lv_propose");
+                if (rc != DD_OK) break;
+                dd_launch_begin(h);
+                k_lv_apply<<<(unsigned)((b1 - b0 + 255) / 256), 256, 0, h->stream>>>(h->d_lv_off, h->d_lv_comm, h->d_lv_tot,
+                                                                                     csize, bucket, b0, b1, desired, counters);
+                rc = dd_launch_end(h, "lv_apply");
+            }
+            if (rc != DD_OK) break;
+            dd_launch_begin(h);
+            k_lv_round_end<<<1, 1, 0, h->stream>>>(counters, n);
+            rc = dd_launch_end(h, "lv_round_end");
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        h->timing = timing;
+        h->lv_graph_launches = h->launches - launches_before;
+        h->launches = launches_before;
+        if (rc != DD_OK) return rc;
+        if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("louvain graph capture: ") + cudaGetErrorString(e));
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("louvain graph instantiate: ") + cudaGetErrorString(e));
+        h->lv_graph_exec = exec;
+        h->lv_graph_n = n;
+        h->lv_graph_gamma = gamma;
+        h->lv_graph_seed = seed;
+    }
+    dd_launch_begin(h);
+    {
+        cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)h->lv_graph_exec, h->stream);
+        if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("louvain graph launch: ") + cudaGetErrorString(e));
+    }
+    DD_TRY(dd_launch_end(h, "lv_rounds_graph"));
+    h->launches += h->lv_graph_launches - 1;  // the replay runs every captured kernel
+    return DD_OK;
+}

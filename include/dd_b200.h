@@ -95,14 +95,16 @@ int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const floa
  * idx_out int32[A*k], dist_out float32[A*k] (may be NULL). */
 int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
 
-/* ---- clustering call, doubletdetection.py:337-343 (host) -------------------------------
+/* ---- clustering call, doubletdetection.py:337-343 -----------------------------------------
  * Louvain (RB configuration null model, resolution gamma, unweighted, seeded) on the symmetrised
  * kNN pattern -- what sc.tl.louvain(resolution, random_state, directed=False) optimises.  The
- * louvain package is absent from the image; the algorithm is specified in oracle/louvain_ref.py.
+ * louvain package is absent from the image; the algorithm is specified in oracle/louvain_ref.py:
+ * the first level by synchronous coloured rounds (on the GPU inside dd_fit_iterations; this host
+ * entry computes the identical partition on the CPU), the levels above sequentially.
  * labels_out int32[n], 0 = largest community.  No handle: pure host code, thread-safe. */
 int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
                    int32_t *labels_out, int32_t *n_communities_out);
-/* Same on an explicit symmetric CSR graph (weights may be NULL = unweighted). */
+/* Fully sequential Louvain on an explicit symmetric CSR graph (weights may be NULL = unweighted). */
 int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                    double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 
@@ -125,8 +127,9 @@ double dd_hypergeom_logsf(int64_t k, int64_t M, int64_t n, int64_t N);
  *   communities_out         int32[n_iters * N]
  *   synth_communities_out   int32[n_iters * M]
  *   stage_ms_out            float64[8] or NULL: milliseconds summed over iterations for
- *                           {host clustering+scoring (summed over workers), doublets+normalise, scale,
- *                            pca, knn, d2h, device time first launch -> last copy, wall time of the call}
+ *                           {host aggregation + upper Louvain levels + scoring (summed over workers),
+ *                            doublets+normalise, scale, pca, knn, first Louvain level on the device + d2h,
+ *                            device time first launch -> last copy, wall time of the call}
  */
 typedef struct dd_fit_params {
     int32_t n_iters;

@@ -18,7 +18,8 @@ def build():
 def _load():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB):
+        src = os.path.join(_HERE, "louvain_ref.c")
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
             build()
         _lib = ctypes.CDLL(_LIB)
         _lib.louvain_ref.restype = ctypes.c_int64
@@ -26,10 +27,14 @@ def _load():
             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p,
         ]
+        _lib.louvain_ref_parallel0.restype = ctypes.c_int64
+        _lib.louvain_ref_parallel0.argtypes = [
+            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p,
+        ]
     return _lib
 
 
-def louvain(indptr, indices, weights=None, resolution=1.0, seed=0):
+def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, level0="sequential"):
     """Same contract as oracle.louvain_ref.louvain."""
     lib = _load()
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
@@ -37,6 +42,12 @@ def louvain(indptr, indices, weights=None, resolution=1.0, seed=0):
     n = indptr.size - 1
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     out = np.empty(max(n, 1), dtype=np.int64)
+    if level0 == "parallel":
+        if w is not None:
+            raise ValueError("the parallel first level is defined for unweighted graphs")
+        lib.louvain_ref_parallel0(n, indptr.ctypes.data, indices.ctypes.data, float(resolution),
+                                  int(seed) & ((1 << 64) - 1), out.ctypes.data)
+        return out[:n]
     lib.louvain_ref(
         n, indptr.ctypes.data, indices.ctypes.data, None if w is None else w.ctypes.data,
         float(resolution), int(seed) & ((1 << 64) - 1), out.ctypes.data,

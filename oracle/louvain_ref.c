@@ -157,6 +157,63 @@ static void aggregate(const graph *g, const int64_t *comm, graph *out, int64_t *
     free(new_id); free(mstart); free(members); free(fill); free(acc); free(seen); free(touched);
 }
 
+/* First level by synchronous coloured rounds (unweighted graph); same statement as
+ * oracle/louvain_ref.py:level0_parallel.  comm[] out (community id = a node id). */
+#define N_COLOURS 8
+#define MAX_ROUNDS 32
+static uint64_t colour_of(uint64_t seed, int64_t i) {
+    uint64_t z = seed + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return z % N_COLOURS;
+}
+
+static void level0_parallel(const graph *g, double gamma, double two_m, uint64_t seed, int64_t *comm) {
+    int64_t n = g->n;
+    double *k = (double *)malloc(sizeof(double) * n);
+    double *tot = (double *)malloc(sizeof(double) * n);
+    int64_t *size = (int64_t *)malloc(sizeof(int64_t) * n);
+    int64_t *desired = (int64_t *)malloc(sizeof(int64_t) * n);
+    unsigned char *col = (unsigned char *)malloc(n);
+    double *cnt = (double *)calloc(n, sizeof(double)); /* w(i, c) scratch, indexed by community */
+    for (int64_t i = 0; i < n; i++) {
+        k[i] = (double)(g->indptr[i + 1] - g->indptr[i]);
+        tot[i] = k[i]; size[i] = 1; comm[i] = i; col[i] = (unsigned char)colour_of(seed, i);
+    }
+    for (int round = 0; round < MAX_ROUNDS; round++) {
+        int64_t moved = 0;
+        for (int c = 0; c < N_COLOURS; c++) {
+            /* decide from the frozen state */
+            for (int64_t i = 0; i < n; i++) {
+                desired[i] = -1;
+                if (col[i] != c || k[i] == 0.0) continue;
+                int64_t ci = comm[i];
+                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) cnt[comm[g->indices[e]]] += 1.0;
+                double gain_stay = cnt[ci] - ((gamma * k[i]) * (tot[ci] - k[i])) / two_m;
+                int64_t best = -1; double best_gain = 0.0;
+                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) {
+                    int64_t cc = comm[g->indices[e]];
+                    if (cc == ci) continue;
+                    double gn = cnt[cc] - ((gamma * k[i]) * tot[cc]) / two_m;
+                    if (best < 0 || gn > best_gain || (gn == best_gain && cc < best)) { best = cc; best_gain = gn; }
+                }
+                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) cnt[comm[g->indices[e]]] = 0.0;
+                if (best >= 0 && best_gain > gain_stay && !(size[ci] == 1 && size[best] == 1 && best > ci))
+                    desired[i] = best;
+            }
+            /* apply simultaneously */
+            for (int64_t i = 0; i < n; i++) {
+                if (desired[i] < 0) continue;
+                int64_t ci = comm[i], b = desired[i];
+                comm[i] = b; tot[ci] -= k[i]; tot[b] += k[i]; size[ci]--; size[b]++; moved++;
+            }
+        }
+        if (moved <= (n >> 9)) break; /* at most n / 512 moves: the level is settled */
+    }
+    free(k); free(tot); free(size); free(desired); free(col); free(cnt);
+}
+
 typedef struct { int64_t size; int64_t fa; } comm_rank;
 static int cmp_rank(const void *a, const void *b) {
     const comm_rank *x = (const comm_rank *)a, *y = (const comm_rank *)b;
@@ -166,8 +223,22 @@ static int cmp_rank(const void *a, const void *b) {
 
 /* indptr/indices: symmetric CSR without self loops; weights may be NULL (all 1).
  * labels_out: n int64, 0 = largest community.  Returns number of communities. */
+static int64_t louvain_impl(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                            double resolution, uint64_t seed, int64_t *labels_out, int parallel0);
+
 int64_t louvain_ref(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                     double resolution, uint64_t seed, int64_t *labels_out) {
+    return louvain_impl(n, indptr, indices, weights, resolution, seed, labels_out, 0);
+}
+
+/* kNN-pipeline flavour: parallel first level (unweighted graphs), sequential levels above. */
+int64_t louvain_ref_parallel0(int64_t n, const int64_t *indptr, const int64_t *indices, double resolution,
+                              uint64_t seed, int64_t *labels_out) {
+    return louvain_impl(n, indptr, indices, NULL, resolution, seed, labels_out, 1);
+}
+
+static int64_t louvain_impl(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                            double resolution, uint64_t seed, int64_t *labels_out, int parallel0) {
     graph g;
     int64_t nnz = indptr[n];
     g.n = n;
@@ -182,6 +253,17 @@ int64_t louvain_ref(int64_t n, const int64_t *indptr, const int64_t *indices, co
     int64_t *membership = (int64_t *)malloc(sizeof(int64_t) * (n > 0 ? n : 1));
     for (int64_t i = 0; i < n; i++) membership[i] = i;
     sm64 rng; rng.s = seed;
+    if (two_m > 0.0 && parallel0) {
+        int64_t *comm = (int64_t *)malloc(sizeof(int64_t) * (n > 0 ? n : 1));
+        level0_parallel(&g, resolution, two_m, seed, comm);
+        graph ng;
+        int64_t *node2new = (int64_t *)malloc(sizeof(int64_t) * (n > 0 ? n : 1));
+        aggregate(&g, comm, &ng, node2new);
+        for (int64_t i = 0; i < n; i++) membership[i] = node2new[membership[i]];
+        free(comm); free(node2new);
+        graph_free(&g);
+        g = ng;
+    }
     if (two_m > 0.0) {
         for (int level = 0; level < 64; level++) {
             int64_t *comm = (int64_t *)malloc(sizeof(int64_t) * (g.n > 0 ? g.n : 1));

@@ -10,7 +10,27 @@ implementation (``doubletdetection_b200/csrc/louvain.cpp``) must reproduce label
 Quality function (RB configuration, resolution gamma, undirected, weights w):
     Q = sum_ij (A_ij - gamma * k_i * k_j / (2m)) * delta(c_i, c_j)
 
-Algorithm (one "level"):
+Two flavours of the first level exist (``level0=`` argument of :func:`louvain`):
+
+* ``"sequential"`` -- the classic queue-driven sweep described below, used for every level above the first and
+  for explicit (possibly weighted) graphs (``dd_louvain_csr``);
+* ``"parallel"`` -- what the kNN pipeline uses (``dd_louvain_knn`` / ``dd_fit_iterations``): the first level of an
+  UNWEIGHTED graph is optimised by synchronous coloured rounds (:func:`level0_parallel`) so that it can run on
+  the GPU; the communities it finds are aggregated and the remaining levels are sequential.
+
+Synchronous coloured rounds (first level, unweighted, order-independent by construction):
+  * colour(i) = SplitMix64-finaliser(seed + (i + 1) * 0x9E3779B97F4A7C15) mod 8;
+  * a round visits the colours 0..7; all nodes of the current colour decide simultaneously from the state at
+    the start of the sub-round (comm, tot, community sizes): with w(i, c) = number of neighbours in c and
+    tot'(c) = tot[c] - (k_i if c == comm[i] else 0),
+        gain(c) = w(i, c) - ((gamma * k_i) * tot'(c)) / two_m            (IEEE double, this order)
+    the node moves to the neighbouring community c != comm[i] with the largest gain (ties: smallest id) iff
+    that gain is strictly larger than gain(comm[i]) -- except that a singleton never moves into a singleton
+    with a larger id (this breaks the swap oscillation of synchronous updates);
+  * all moves of the sub-round are applied at once; the level ends after a round that moved at most
+    floor(n / 512) nodes (i.e. no node for n < 512), or after 32 rounds.
+
+Sequential algorithm (one "level"):
   * every node starts in its own community; ``tot[c]`` = sum of weighted degrees in c;
   * a FIFO queue is filled with all nodes in a seeded random order (SplitMix64 + Fisher-Yates,
     ``j = next() % (i + 1)`` for i = n-1 .. 1);
@@ -139,8 +159,96 @@ def _aggregate(n, indptr, indices, weights, selfw, comm):
     return nc, n_indptr, n_indices, n_weights, n_selfw, node2new
 
 
-def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, max_levels=64):
-    """Cluster a symmetric, self-loop-free CSR graph.  Returns int64 labels, 0 = largest."""
+N_COLOURS = 8
+MAX_ROUNDS = 32
+
+
+def node_colours(n, seed):
+    """colour(i) of the synchronous rounds (uint64 arithmetic, vectorised)."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(int(seed) & _MASK) + (np.arange(n, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z % np.uint64(N_COLOURS)).astype(np.int64)
+
+
+def level0_parallel(indptr, indices, gamma, seed):
+    """First level by synchronous coloured rounds on an unweighted symmetric graph (see the module docstring).
+    Returns the community id (a node id) of every node."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    n = indptr.size - 1
+    deg = np.diff(indptr)
+    k = deg.astype(np.float64)
+    two_m = float(indices.size)
+    comm = np.arange(n, dtype=np.int64)
+    tot = k.copy()
+    size = np.ones(n, dtype=np.int64)
+    if two_m == 0.0:
+        return comm
+    colour = node_colours(n, seed)
+    by_colour = [np.nonzero((colour == c) & (deg > 0))[0] for c in range(N_COLOURS)]
+    gamma = float(gamma)
+    for _ in range(MAX_ROUNDS):
+        moved = 0
+        for act in by_colour:
+            if act.size == 0:
+                continue
+            d = deg[act]
+            local = np.repeat(np.arange(act.size, dtype=np.int64), d)
+            starts = np.repeat(indptr[act], d)
+            offs = np.arange(d.sum(), dtype=np.int64) - np.repeat(np.cumsum(d) - d, d)
+            c_nb = comm[indices[starts + offs]]
+            key, w = np.unique(local * n + c_nb, return_counts=True)
+            a = key // n  # local index of the node
+            c = key % n  # candidate community
+            node = act[a]
+            ci = comm[node]
+            ki = k[node]
+            own = c == ci
+            gain = w.astype(np.float64) - ((gamma * ki) * (tot[c] - np.where(own, ki, 0.0))) / two_m
+            # gain of staying (w(i, ci) may be 0: then the pair is absent from `key`)
+            w_stay = np.zeros(act.size, dtype=np.float64)
+            w_stay[a[own]] = w[own].astype(np.float64)
+            ci_act = comm[act]
+            k_act = k[act]
+            gain_stay = w_stay - ((gamma * k_act) * (tot[ci_act] - k_act)) / two_m
+            # best other community: largest gain, ties -> smallest id
+            oth = ~own
+            if not oth.any():
+                continue
+            ao, co, go = a[oth], c[oth], gain[oth]
+            order = np.lexsort((co, -go, ao))
+            ao, co, go = ao[order], co[order], go[order]
+            first = np.ones(ao.size, dtype=bool)
+            first[1:] = ao[1:] != ao[:-1]
+            ab, cb, gb = ao[first], co[first], go[first]
+            src = ci_act[ab]
+            move = gb > gain_stay[ab]
+            move &= ~((size[src] == 1) & (size[cb] == 1) & (cb > src))
+            if not move.any():
+                continue
+            mv_node, mv_to, mv_from = act[ab[move]], cb[move], src[move]
+            comm[mv_node] = mv_to
+            np.add.at(tot, mv_from, -k[mv_node])
+            np.add.at(tot, mv_to, k[mv_node])
+            np.add.at(size, mv_from, -1)
+            np.add.at(size, mv_to, 1)
+            moved += int(mv_node.size)
+        if moved <= (n >> 9):  # at most n / 512 moves: the level is settled
+            break
+    return comm
+
+
+def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, max_levels=64, level0="sequential"):
+    """Cluster a symmetric, self-loop-free CSR graph.  Returns int64 labels, 0 = largest.
+    ``level0="parallel"`` (unweighted graphs only) is the kNN-pipeline flavour."""
+    comm0 = None
+    if level0 == "parallel":
+        if weights is not None:
+            raise ValueError("the parallel first level is defined for unweighted graphs")
+        comm0 = [int(x) for x in level0_parallel(indptr, indices, resolution, seed)]
     indptr = [int(x) for x in indptr]
     indices = [int(x) for x in indices]
     n = len(indptr) - 1
@@ -155,6 +263,9 @@ def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, max_levels=64
         two_m += w
     rng = SplitMix64(seed)
     membership = list(range(n))
+    if two_m > 0.0 and comm0 is not None:
+        nc, indptr, indices, weights, selfw, node2new = _aggregate(n, indptr, indices, weights, selfw, comm0)
+        membership = [node2new[c] for c in membership]
     if two_m > 0.0:
         for _ in range(max_levels):
             comm, moved = _one_level(len(indptr) - 1, indptr, indices, weights, selfw, gamma, two_m, rng)

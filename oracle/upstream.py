@@ -227,6 +227,8 @@ def tl_louvain(adata, key_added="clusters", random_state=0, directed=False, reso
     C = adata.obsp["connectivities"].tocsr()
     C.sort_indices()
     fn = louvain_fn or louvain_ref.louvain
-    labels = fn(C.indptr, C.indices, None, resolution=float(resolution), seed=int(random_state))
+    # the kNN-pipeline flavour of the specification: synchronous coloured first level (GPU-friendly), then
+    # sequential levels (oracle/louvain_ref.py)
+    labels = fn(C.indptr, C.indices, None, resolution=float(resolution), seed=int(random_state), level0="parallel")
     adata.obs[key_added] = np.asarray([str(int(x)) for x in labels])
     return adata

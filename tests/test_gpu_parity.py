@@ -253,13 +253,41 @@ def test_pipeline_matches_stagewise_calls(handle):
         handle.pca(C, omega, n_iter)
         idx, _ = handle.knn(10)
         labels = louvain_c.louvain(*(lambda S: (S.indptr, S.indices))(upstream.knn_pattern_graph(idx)), None,
-                                   resolution=4.0, seed=0)
+                                   resolution=4.0, seed=0, level0="parallel")
         np.testing.assert_array_equal(out["communities"][i], labels[:n_cells])
         np.testing.assert_array_equal(out["synth_communities"][i], labels[n_cells:])
         s, lp, _, _ = reference_path.score_communities(labels, n_cells)
         np.testing.assert_array_equal(out["scores"][i], s)
         np.testing.assert_allclose(out["log_p"][i], lp, rtol=1e-9, atol=1e-12)
     assert handle.kernel_launches() > 0
+
+
+def test_gpu_louvain_level0_matches_host_twin(handle):
+    """The device first level (inside dd_fit_iterations) and the host twin (dd_louvain_knn) must give the same
+    labels: feed the same kNN graph to both on a 12.5k-node problem."""
+    raw = datasets.structured_counts(4000, 600, seed=99)
+    rng = np.random.default_rng(3)
+    parents = rng.choice(4000, size=(2, 1000, 2), replace=False)
+    C = 30
+    omega = pca_f64.omega(600, C, 0).astype(np.float32)
+    n_iter = pca_f64.auto_n_iter(5000, 600, C)
+    handle.upload_counts(raw)
+    out = handle.fit_iterations(parents, omega, pseudocount=0.1, standard_scaling=False, n_comp=C,
+                                n_power_iter=n_iter, n_host_threads=2)
+    for i in range(2):
+        handle.create_doublets(parents[i])
+        handle.normalise_log(handle.median_lib_size(), 0.1)
+        handle.pca(C, omega, n_iter)
+        idx, _ = handle.knn(10)
+        labels = handle_native_louvain(idx)
+        np.testing.assert_array_equal(out["communities"][i], labels[:4000])
+        np.testing.assert_array_equal(out["synth_communities"][i], labels[4000:])
+
+
+def handle_native_louvain(idx):
+    from doubletdetection_b200 import _capi
+
+    return _capi.louvain_knn(idx, resolution=4.0, seed=0)
 
 
 # ------------------------------------------------------------------------------ BASELINE config sizes

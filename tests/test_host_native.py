@@ -91,11 +91,14 @@ def test_louvain_knn_matches_python_spec(native, n, k, gamma, seed):
     pts = (rs.normal(size=(n, 6)) + rs.integers(0, 5, size=(n, 1)) * 2.5).astype(np.float32)
     idx, _ = upstream.knn_brute(pts, k)
     S = upstream.knn_pattern_graph(idx)
-    want = louvain_ref.louvain(S.indptr, S.indices, None, resolution=gamma, seed=seed)
+    # kNN entry: parallel (GPU-style) first level + sequential upper levels
+    want = louvain_ref.louvain(S.indptr, S.indices, None, resolution=gamma, seed=seed, level0="parallel")
     got = native.louvain_knn(idx.astype(np.int32), resolution=gamma, seed=seed)
     np.testing.assert_array_equal(got, want)
+    # explicit-graph entry: fully sequential
+    want_seq = louvain_ref.louvain(S.indptr, S.indices, None, resolution=gamma, seed=seed)
     got_csr = native.louvain_csr(S.indptr, S.indices, None, resolution=gamma, seed=seed)
-    np.testing.assert_array_equal(got_csr, want)
+    np.testing.assert_array_equal(got_csr, want_seq)
 
 
 def test_louvain_weighted_matches_spec(native):
@@ -114,8 +117,11 @@ def test_louvain_large_matches_c_oracle(native):
     pts = (rs.normal(size=(n, 8)) + rs.integers(0, 8, size=(n, 1)) * 2.0).astype(np.float32)
     idx, _ = upstream.knn_brute(pts, 10)
     S = upstream.knn_pattern_graph(idx)
-    want = louvain_c.louvain(S.indptr, S.indices, None, resolution=4.0, seed=0)
+    want = louvain_c.louvain(S.indptr, S.indices, None, resolution=4.0, seed=0, level0="parallel")
     got = native.louvain_knn(idx.astype(np.int32), resolution=4.0, seed=0)
+    np.testing.assert_array_equal(got, want)
+    want = louvain_c.louvain(S.indptr, S.indices, None, resolution=4.0, seed=0)
+    got = native.louvain_csr(S.indptr, S.indices, None, resolution=4.0, seed=0)
     np.testing.assert_array_equal(got, want)
 
 
