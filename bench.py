@@ -146,6 +146,8 @@ def cpu_one_iteration(state):
     nn = NearestNeighbors(n_neighbors=10, algorithm="brute", metric="euclidean", n_jobs=-1).fit(emb)
     idx = nn.kneighbors(emb, return_distance=False)
     graph = upstream.knn_pattern_graph(idx)
+    # the CPU path uses the classic sequential Louvain (what a CPU implementation would run; faster on a
+    # CPU than simulating the GPU's synchronous first level)
     labels = louvain_c.louvain(graph.indptr, graph.indices, None, resolution=4.0, seed=SEED)
     reference_path.score_communities(labels, n_cells)
     return aug.shape[0]
@@ -338,7 +340,8 @@ def run_ours(args, wl, counts):
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = args.steps * cells_per_step / dt_e2e
     h2d = (counts.indptr.nbytes + counts.indices.nbytes + counts.data.nbytes + omega.nbytes + N_ITERS * n_synth * 2 * 8)
-    d2h = N_ITERS * (n_aug * 10 * 4 + 8) + n_cells * 4
+    # per iteration: the pattern graph (offsets, first-level communities, adjacency upper bound) + PCA flag
+    d2h = N_ITERS * (((n_aug + 1) + n_aug + n_aug * 18) * 4 + 8) + n_cells * 4
     n_doublets = int(np.nansum(labels))
 
     line = {

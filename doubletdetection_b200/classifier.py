@@ -302,23 +302,31 @@ def iteration_shard(n_iters, rank, world):
 
 
 def _allgather_iterations(dist, out, n_iters, device):
-    """Every rank filled only its own rows of the (n_iters, .) result arrays (the rest are zero); a sum
-    all-reduce assembles them.  No data-path collective is involved -- this is result collection."""
+    """Every rank filled only its own rows of the (n_iters, .) result arrays.  With equal blocks the rows are
+    exchanged with one all-gather per array (each rank ships only what it computed); otherwise a sum
+    all-reduce of the zero-padded arrays assembles them.  No data-path collective is involved -- this is
+    result collection."""
     import torch
 
     backend = dist.get_backend()
     dev = torch.device("cuda", device) if backend == "nccl" else torch.device("cpu")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    it0, it1 = iteration_shard(n_iters, rank, world)
+    even = n_iters % world == 0
     merged = {}
     for key in ("scores", "log_p", "communities", "synth_communities"):
-        a = out[key]
-        if key in ("scores", "log_p"):
-            # NaN / -inf entries do not survive a sum; ship them as bit patterns instead
-            t = torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy()).to(dev)
+        a = np.ascontiguousarray(out[key])
+        as_bits = key in ("scores", "log_p")  # NaN / -inf entries must survive: ship float64 as bit patterns
+        src = a.view(np.int64) if as_bits else a.astype(np.int64)
+        if even:
+            mine = torch.from_numpy(np.ascontiguousarray(src[it0:it1])).to(dev)
+            full = torch.empty((n_iters,) + tuple(mine.shape[1:]), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(full, mine)
         else:
-            t = torch.from_numpy(np.ascontiguousarray(a).astype(np.int64)).to(dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        r = t.cpu().numpy()
-        merged[key] = r.view(np.float64) if key in ("scores", "log_p") else r.astype(np.int32)
+            full = torch.from_numpy(src.copy()).to(dev)
+            dist.all_reduce(full, op=dist.ReduceOp.SUM)
+        r = full.cpu().numpy()
+        merged[key] = r.view(np.float64) if as_bits else r.astype(np.int32)
     stage = torch.tensor([out["stage_ms"][k] for k in sorted(out["stage_ms"])], dtype=torch.float64, device=dev)
     dist.all_reduce(stage, op=dist.ReduceOp.MAX)
     merged["stage_ms"] = dict(zip(sorted(out["stage_ms"]), stage.cpu().tolist()))

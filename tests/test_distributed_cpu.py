@@ -48,16 +48,18 @@ def _worker(rank, world, port, n_iters, n_cells, n_synth, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(240)
 def test_iteration_sharding_gloo_world2():
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 5, 40, 10, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=100) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=30)
-    assert sorted(results) == [(0, True), (1, True)]
+    for n_iters in (5, 6):  # uneven blocks -> all-reduce path, even blocks -> all-gather path
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, n_iters, 40, 10, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        results = [q.get(timeout=100) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=30)
+        assert sorted(results) == [(0, True), (1, True)]
