@@ -19,6 +19,7 @@
 // TMEM: 256 columns per CTA (2 x 48 accumulator + 2 x 64 operand), two CTAs per SM.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -139,7 +140,7 @@ template <bool TR, int LP>
 __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUtensorMap tmap,
                                                     const uint8_t *__restrict__ bt, float *__restrict__ Y,
                                                     double *__restrict__ Zacc, int64_t n_rows, int ld,
-                                                    int chunks_per_split) {
+                                                    int chunks_per_split, int tile_rows) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)NS * STAGE_BYTES);
@@ -161,7 +162,10 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
         chunk0 = blockIdx.y * chunks_per_split;
         nk = min(chunks_per_split, total - chunk0);
     }
-    const int tile0 = blockIdx.x * 128;  // first row (GEMM1) or first gene (GEMM2) of this CTA
+    // first row (GEMM1: tile_rows <= 128 rows per CTA, sized so that the grid fills whole waves) or first gene
+    // (GEMM2: 128 genes) of this CTA
+    const int tile0 = blockIdx.x * (TR ? 128 : tile_rows);
+    const uint32_t stage_tx = (TR ? D_TILE_BYTES : tile_rows * BK * 4) + B_TILE_BYTES;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) {
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
                     const int s = c % NS;
                     const uint32_t ph = (c / NS) & 1;
                     mbar_wait(empty + s, ph ^ 1);
-                    mbar_expect_tx(full + s, STAGE_BYTES);
+                    mbar_expect_tx(full + s, stage_tx);
                     uint8_t *sD = smem + (size_t)s * STAGE_BYTES;
                     if (!TR)
                         tma_2d(sD, &tmap, (chunk0 + c) * BK, tile0, full + s);
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
             for (int i = 0; i < 48; i++) v[i] = __float_as_uint(sum[i]);
             if (!TR) {
                 const int64_t row = (int64_t)tile0 + r;
-                if (row < n_rows) {
+                if (r < tile_rows && row < n_rows) {
 #pragma unroll
                     for (int j = 0; j < LP; j += 4)
                         *reinterpret_cast<float4 *>(Y + row * LP + j) =
@@ -349,6 +353,7 @@ struct dd_tc_state {
     CUtensorMap map_genes;  // box 128 genes x 32 rows, no swizzle    (GEMM2)
     const float *dense = nullptr;
     int64_t rows = 0, ld = 0;
+    int tile_rows = 128;  // rows per CTA of GEMM1
 };
 
 bool dd_tc_pca_enabled() {
@@ -365,7 +370,14 @@ int dd_tc_prepare(dd_handle *h) {
     const cuuint64_t dims[2] = {(cuuint64_t)h->ld, (cuuint64_t)h->A};
     const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(float)};
     const cuuint32_t estr[2] = {1, 1};
-    const cuuint32_t box_rows[2] = {32, 128};
+    // GEMM1 grid balance: ceil(A / 128) CTAs rarely fill whole waves of 2 CTAs per SM; shrink the row tile so
+    // that the same number of waves is full (the MMA still runs M = 128, the surplus lanes are ignored)
+    const int64_t slots = (int64_t)h->num_sms * 2;
+    const int64_t waves = std::max<int64_t>(1, ((h->A + 127) / 128 + slots - 1) / slots);
+    int tile_rows = (int)((h->A + slots * waves - 1) / (slots * waves));
+    tile_rows = std::min(128, std::max(8, (tile_rows + 7) / 8 * 8));
+    st->tile_rows = tile_rows;
+    const cuuint32_t box_rows[2] = {32, (cuuint32_t)tile_rows};
     const cuuint32_t box_genes[2] = {128, 32};
     CUresult r1 = enc(&st->map_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->d_dense, dims, strides, box_rows, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -395,9 +407,10 @@ void dd_tc_free(dd_handle *h) {
 
 // Y = D Q   (Q as canonical hi/lo tiles in h->d_qb)
 int dd_tc_gemm_dq(dd_handle *h) {
-    const unsigned grid = (unsigned)((h->A + 127) / 128);
+    const int tr = h->tc->tile_rows;
+    const unsigned grid = (unsigned)((h->A + tr - 1) / tr);
     DD_LAUNCH(h, "tc_gemm_dq", (tcg::k_tc_gemm<false, 40>), grid, 192, tcg::SMEM_BYTES, h->tc->map_rows, h->d_qb, h->d_Y,
-              (double *)nullptr, h->A, (int)h->ld, 0);
+              (double *)nullptr, h->A, (int)h->ld, 0, tr);
     return DD_OK;
 }
 
@@ -405,11 +418,12 @@ int dd_tc_gemm_dq(dd_handle *h) {
 int dd_tc_gemm_dty(dd_handle *h) {
     const int gblocks = (int)((h->ld + 127) / 128);
     const int total_chunks = (int)((h->A + tcg::BK - 1) / tcg::BK);
-    int splits = std::max(1, (h->num_sms * 4 + gblocks - 1) / gblocks);
+    // two CTAs per SM are resident: aim for two full waves (never a nearly empty third one)
+    int splits = std::max(1, (h->num_sms * 4) / gblocks);
     int cps = std::max(1, (total_chunks + splits - 1) / splits);
     splits = (total_chunks + cps - 1) / cps;
     DD_LAUNCH(h, "tc_gemm_dty", (tcg::k_tc_gemm<true, 40>), dim3(gblocks, splits), 192, tcg::SMEM_BYTES, h->tc->map_genes,
-              h->d_yb, (float *)nullptr, h->d_Zacc, h->A, (int)h->ld, cps);
+              h->d_yb, (float *)nullptr, h->d_Zacc, h->A, (int)h->ld, cps, 128);
     return DD_OK;
 }
 
