@@ -13,6 +13,8 @@
 // float64 distances (order: distance, then index).
 #include "dd_internal.h"
 
+#include <cuda_bf16.h>
+
 #include <cfloat>
 #include <cstdlib>
 
@@ -277,31 +279,32 @@ __global__ void k_knn_refine(const float *__restrict__ emb, const int *__restric
 //
 //   t(q, c) = q . c - |c|^2 / 2     (larger = closer; the query norm does not change a query's ranking)
 //
-// is one K = 104 TF32 GEMM with float32-class accuracy ("3xTF32"): every operand is split into a
-// TF32-exact high part and the float32 remainder, and the three significant cross products plus the
-// norm term are concatenated along K:
-//   A' (query row)     = [ q_hi(32) | q_hi(32) | q_lo(32) | 1, 1, 0...0 ]
-//   B' (candidate row) = [ c_hi(32) | c_lo(32) | c_hi(32) | n_hi, n_lo, 0...0 ],  n = -|c|^2/2
+// is one K = 112 BF16 GEMM ("3xBF16"): every coordinate is split into bf16 parts x = x1 + x2 (+ x3, dropped),
+// and the three significant cross products plus the norm term are concatenated along K:
+//   A' (query row)     = [ q1(32) | q1(32) | q2(32) | 1, 1, 1, 0...0 ]
+//   B' (candidate row) = [ c1(32) | c2(32) | c1(32) | n1, n2, n3, 0...0 ],  n = -|c|^2/2 in three bf16 parts
+// The dropped terms are 2^-17 relative: enough for a FILTER whose top 16 are re-ranked exactly in float64
+// (k_knn_refine), and half the tensor time and operand bytes of the 3xTF32 variant it replaces.
 // k_knn_prep writes both operands tile by tile (128 rows) in the canonical no-swizzle K-major UMMA
-// layout (8 x 16-byte core matrices, LBO = 128 B along K, SBO = 3328 B along rows), so that a stage is
-// ONE 53 KB bulk copy (cp.async.bulk, TMA engine) and the shared-memory descriptors are constants.
+// layout (8 x 16-byte core matrices, LBO = 128 B along K, SBO = 1792 B along rows), so that a stage is
+// ONE 28 KB bulk copy (cp.async.bulk, TMA engine) and the shared-memory descriptors are constants.
 //
 // k_knn_tc: one CTA = 256 query rows (two M=128 accumulators) x all candidate tiles.
 //   warp 0    bulk-copy producer (2-stage ring of candidate tiles, mbarrier complete_tx)
-//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (13 K-steps x 2 query tiles per stage)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (7 K-steps x 2 query tiles per stage)
 //   warps 2-9 epilogue: tcgen05.ld 32 columns at a time, one query row per thread; a value survives only
 //             if it beats the row's current TL-th best (kept in a register), and the rare survivors are
 //             inserted into the row's sorted candidate list in global memory
 // TMEM: 512 columns = 2 (double buffer) x 2 (query tiles) x 128 fp32 accumulator columns.
 namespace tc {
 
-constexpr int KC = 26;                         // 16-byte chunks per operand row (K = 104)
+constexpr int KC = 14;                         // 16-byte chunks (8 bf16) per operand row (K = 112)
 constexpr int TILE = 128;                      // rows per operand tile
-constexpr int TILE_BYTES = TILE * KC * 16;     // 53248
+constexpr int TILE_BYTES = TILE * KC * 16;     // 28672
 constexpr int LBO = 128, SBO = KC * 128;       // bytes
 constexpr int QT = 2;                          // query tiles per CTA
-constexpr int NS = 2;                          // candidate stages
-constexpr int KSTEPS = KC / 2;                 // 13 MMAs of K = 8
+constexpr int NS = 4;                          // candidate stages
+constexpr int KSTEPS = KC / 2;                 // 7 MMAs of K = 16
 constexpr int TLc = 16;
 constexpr float kEmptyT = -1e29f;              // list filler; padded candidates score -1e30 and never pass
 constexpr size_t SMEM_BYTES = (size_t)(QT + NS) * TILE_BYTES + 1024;
@@ -345,11 +348,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -378,28 +381,41 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= 1ull << 46;
     return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 with BF16 operands, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// x = b1 + b2 + b3 with bf16 parts (round to nearest at every step; the remainders are exact in float32)
+__device__ __forceinline__ void bf16_split3(float x, __nv_bfloat16 &b1, __nv_bfloat16 &b2, __nv_bfloat16 &b3) {
+    b1 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b1);
+    b2 = __float2bfloat16_rn(r1);
+    b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+}
 
-// Operand tiles in the canonical layout + empty candidate lists.  Block = 8 rows x 26 chunks.
-__global__ void __launch_bounds__(208) k_knn_prep(const float *__restrict__ emb, int64_t n, int64_t n_pad,
-                                                  float4 *__restrict__ qa, float4 *__restrict__ cb) {
+// Operand tiles in the canonical layout.  Block = 8 rows x 14 chunks (one chunk = 8 bf16 = 16 bytes).
+//   chunks 0-3: part 1 of dims 0-31 (A and B);  4-7: A part 1 / B part 2;  8-11: A part 2 / B part 1;
+//   chunk 12: A = (1, 1, 1, 0...) / B = (n1, n2, n3, 0...);  chunk 13: zero
+__global__ void __launch_bounds__(112) k_knn_prep(const float *__restrict__ emb, int64_t n, int64_t n_pad,
+                                                  uint4 *__restrict__ qa, uint4 *__restrict__ cb) {
     const int j = threadIdx.x >> 3, rr = threadIdx.x & 7;
     const int64_t row = (int64_t)blockIdx.x * 8 + rr;
     if (row >= n_pad) return;
     const bool real = row < n;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (j < 24) {
+    __nv_bfloat16 a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) a[e] = b[e] = __float2bfloat16_rn(0.f);
+    if (j < 12) {
         if (real) {
-            const float4 x = *reinterpret_cast<const float4 *>(emb + row * 32 + 4 * (j & 7));
-            const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-            const float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-            a = j < 16 ? hi : lo;
-            b = (j >= 8 && j < 16) ? lo : hi;
+            const int d0 = 8 * (j & 3);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                __nv_bfloat16 p1, p2, p3;
+                bf16_split3(emb[row * 32 + d0 + e], p1, p2, p3);
+                a[e] = j < 8 ? p1 : p2;
+                b[e] = (j >= 4 && j < 8) ? p2 : p1;
+            }
         }
-    } else if (j == 24) {
+    } else if (j == 12) {
         if (real) {
             double nn = 0.0;
 #pragma unroll
@@ -408,18 +424,23 @@ __global__ void __launch_bounds__(208) k_knn_prep(const float *__restrict__ emb,
                 nn += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
             }
             const double half = -0.5 * nn;
-            const float h = tf32_hi((float)half);
-            a = make_float4(1.f, 1.f, 0.f, 0.f);
-            b = make_float4(h, (float)(half - (double)h), 0.f, 0.f);
+            const __nv_bfloat16 n1 = __float2bfloat16_rn((float)half);
+            const double r1 = half - (double)__bfloat162float(n1);
+            const __nv_bfloat16 n2 = __float2bfloat16_rn((float)r1);
+            const __nv_bfloat16 n3 = __float2bfloat16_rn((float)(r1 - (double)__bfloat162float(n2)));
+            a[0] = a[1] = a[2] = __float2bfloat16_rn(1.f);
+            b[0] = n1;
+            b[1] = n2;
+            b[2] = n3;
         } else {
-            b = make_float4(tf32_hi(-1e30f), 0.f, 0.f, 0.f);
+            b[0] = __float2bfloat16_rn(-1e30f);  // padded candidates can never be selected
         }
     }
     const int64_t tile = row / TILE;
     const int r = (int)(row % TILE);
     const int64_t off16 = tile * (TILE_BYTES / 16) + (int64_t)(r >> 3) * (SBO / 16) + (int64_t)j * (LBO / 16) + (r & 7);
-    qa[off16] = a;
-    cb[off16] = b;
+    qa[off16] = *reinterpret_cast<const uint4 *>(a);
+    cb[off16] = *reinterpret_cast<const uint4 *>(b);
 }
 
 // The candidate list of a query row lives in the registers of its epilogue thread, sorted by
@@ -508,7 +529,7 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
                     const uint32_t d = tmem_base + buf * 256 + qt * 128;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++)
-                        mma_tf32(d, a_desc[qt] + (uint64_t)(k * 2 * LBO / 16), b_desc + (uint64_t)(k * 2 * LBO / 16), kIdesc,
+                        mma_bf16(d, a_desc[qt] + (uint64_t)(k * 2 * LBO / 16), b_desc + (uint64_t)(k * 2 * LBO / 16), kIdesc,
                                  k > 0);
                 }
                 mma_commit(empty + s);     // the stage may be refilled once these MMAs have read it
@@ -534,14 +555,18 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
             const uint32_t bph = (step >> 1) & 1;
             mbar_wait(tfull + buf, bph);
             fence_after();
-#pragma unroll 1
-            for (int c = 0; c < TILE; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + buf * 256 + c, v);
-                tmem_ld_wait();
-                float m = __uint_as_float(v[0]);
+            // software pipeline: the tcgen05.ld of the next 32 columns is in flight while this group is scanned
+            uint32_t va[32], vb[32];
+            const uint32_t col0 = lane_base + buf * 256;
+            auto scan = [&](uint32_t (&v)[32], int c) {
+                // balanced max tree (depth 5) instead of a 31-long dependent chain
+                float m8[8];
 #pragma unroll
-                for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
+                for (int i = 0; i < 8; i++)
+                    m8[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                                  fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 // rare: some value of this row beats its TL-th best.  Peel maxima until none does.
                 while (m > tau) {
                     int pos = 0;
@@ -562,7 +587,19 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
 #pragma unroll
                     for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
                 }
-            }
+            };
+            tmem_ld32(col0, va);
+            tmem_ld_wait();
+            tmem_ld32(col0 + 32, vb);
+            scan(va, 0);
+            tmem_ld_wait();
+            tmem_ld32(col0 + 64, va);
+            scan(vb, 32);
+            tmem_ld_wait();
+            tmem_ld32(col0 + 96, vb);
+            scan(va, 64);
+            tmem_ld_wait();
+            scan(vb, 96);
             fence_before();
             mbar_arrive(tempty + buf);
         }
@@ -611,8 +648,8 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
         cudaFuncSetAttribute(tc::k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         attr_set = true;
     }
-    DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 208, 0, h->d_emb, n, n_pad,
-              reinterpret_cast<float4 *>(qa), reinterpret_cast<float4 *>(cb));
+    DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
+              reinterpret_cast<uint4 *>(qa), reinterpret_cast<uint4 *>(cb));
     DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(n_tiles_pad / tc::QT), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, cand_i);
     DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, n, k,
               h->d_knn_idx, h->d_knn_dist);
