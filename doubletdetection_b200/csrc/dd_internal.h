@@ -72,6 +72,8 @@ struct dd_handle {
     // tcgen05 path: small GEMM operands as canonical hi/lo UMMA tiles (see pca_tc.h) + TMA tensor maps
     uint8_t *d_qb = nullptr, *d_yb = nullptr, *d_omega_b = nullptr;
     int64_t cap_qb = 0, cap_yb = 0, cap_omega_b = 0;
+    float *d_mu = nullptr;  // float32 column means of the dense matrix (ld entries, 0 in the pad columns)
+    int64_t cap_mu = 0;
     dd_tc_state *tc = nullptr;
     float *d_emb = nullptr;    // A x KP embedding (KP = 32 or 64, zero padded)
     int32_t KP = 0;

@@ -558,6 +558,12 @@ __global__ void __launch_bounds__(128) k_embed(const float *__restrict__ Yq, int
     }
 }
 
+// float32 column means (sklearn's mean_) from the float64 column sums
+__global__ void k_mu(const double *__restrict__ colsum, int n_genes, int ld, double inv_n, float *__restrict__ mu) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < ld) mu[g] = g < n_genes ? (float)(colsum[g] * inv_n) : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int LP>
 int run_pca(dd_handle *h, int n_power_iter) {
@@ -599,13 +605,43 @@ int run_pca(dd_handle *h, int n_power_iter) {
     DD_CUDA(h, cudaMemsetAsync(h->d_Zacc, 0, sizeof(double) * (size_t)ld * LP, h->stream));
     DD_TRY(dd_dev_colstats(h, false));  // mu = colsum / A
 
+    if (use_tc) {
+        // tcgen05 path: D is centred on the fly inside the GEMMs (x - mu_g, float32, exactly sklearn's X -= mean_),
+        // so no correction terms exist.  During the power iterations Y goes straight from the first product
+        // into the second one (as hi/lo operand tiles written by the GEMM epilogue): normalising the tall panel
+        // only re-scales the span (checked against the float64 oracle); the small side is
+        // orthonormalised every iteration, the tall side once, for the final projection.
+        DD_TRY(dd_reserve(h, &h->d_mu, &h->cap_mu, (int64_t)ld));
+        DD_LAUNCH(h, "mu", k_mu, (ld + 255) / 256, 256, 0, h->d_colsum, (int)h->G, ld, inv_A, h->d_mu);
+        for (int it = 0; it <= n_power_iter; it++) {
+            const bool last = it == n_power_iter;
+            DD_TRY(dd_tc_gemm_dq(h, /*write_y=*/last, /*write_tiles=*/!last));
+            if (last) {  // Yq = orth(Y): sklearn's qr(A @ Q)
+                DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
+                DD_CUDA(h, cudaMemsetAsync(sm + OFF_CSUM, 0, sizeof(double) * 2 * kMaxLP, h->stream));
+                DD_LAUNCH(h, "gram_tall", (k_gram<LP, 0>), tall_grid, 256, 0, h->d_Y, nullptr, A, nullptr, 0.0, nullptr,
+                          sm + OFF_GRAM, sm + OFF_CSUM);
+                DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
+                          sm + OFF_FLAG);
+                DD_LAUNCH(h, "apply_tall", (k_apply<LP, 0>), tall_grid, 128, 0, h->d_Y, nullptr, A, L, sm + OFF_RINV,
+                          sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0, h->d_yb);
+                DD_CUDA(h, cudaMemsetAsync(sm + OFF_SSUM, 0, sizeof(double) * kMaxLP, h->stream));  // no mu (x) s term
+            }
+            DD_TRY(dd_tc_gemm_dty(h));
+            DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
+            DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
+                      h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
+            if (!last) {
+                DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV, sm + OFF_FLAG);
+                DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
+                          sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, h->d_qb);
+            }
+        }
+    } else
     for (int it = 0; it <= n_power_iter; it++) {
         const bool last = it == n_power_iter;
         // Y = D Q
-        if (use_tc)
-            DD_TRY(dd_tc_gemm_dq(h));
-        else
-            DD_LAUNCH(h, "gemm_dq", k_gemm_dq<LP>, grid1, 128, gemm1_smem<LP>(), h->d_dense, h->d_Qt, h->d_Y, A, ld);
+        DD_LAUNCH(h, "gemm_dq", k_gemm_dq<LP>, grid1, 128, gemm1_smem<LP>(), h->d_dense, h->d_Qt, h->d_Y, A, ld);
         // Y' = orth(Y - mean)
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_CSUM, 0, sizeof(double) * 2 * kMaxLP, h->stream));  // csum + ssum
@@ -614,13 +650,10 @@ int run_pca(dd_handle *h, int n_power_iter) {
         DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
                   sm + OFF_FLAG);
         DD_LAUNCH(h, "apply_tall", (k_apply<LP, 0>), tall_grid, 128, 0, h->d_Y, nullptr, A, L, sm + OFF_RINV,
-                  sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0, use_tc ? h->d_yb : nullptr);
+                  sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0, nullptr);
         // Z = Dc^T Y'
-        if (use_tc)
-            DD_TRY(dd_tc_gemm_dty(h));
-        else
-            DD_LAUNCH(h, "gemm_dty", k_gemm_dty<LP>, dim3(gblocks, splits), 128, gemm2_smem<LP>(), h->d_dense, h->d_Y,
-                      h->d_Zacc, A, ld, rows_per_split);
+        DD_LAUNCH(h, "gemm_dty", k_gemm_dty<LP>, dim3(gblocks, splits), 128, gemm2_smem<LP>(), h->d_dense, h->d_Y,
+                  h->d_Zacc, A, ld, rows_per_split);
         DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
         DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
                   h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
@@ -628,7 +661,7 @@ int run_pca(dd_handle *h, int n_power_iter) {
             DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV,
                       sm + OFF_FLAG);
             DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
-                      sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, use_tc ? h->d_qb : nullptr);
+                      sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, nullptr);
         }
     }
     // svd(B) with B^T = Z:  B B^T = Z^T Z = gram

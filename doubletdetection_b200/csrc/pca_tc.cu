@@ -138,7 +138,8 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // TR == false: GEMM1 (tile = 128 rows, K runs over genes); TR == true: GEMM2 (tile = 128 genes, K over rows)
 template <bool TR, int LP>
 __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUtensorMap tmap,
-                                                    const uint8_t *__restrict__ bt, float *__restrict__ Y,
+                                                    const uint8_t *__restrict__ bt, const float *__restrict__ mu,
+                                                    float *__restrict__ Y, uint8_t *__restrict__ ytiles,
                                                     double *__restrict__ Zacc, int64_t n_rows, int ld,
                                                     int chunks_per_split, int tile_rows) {
     extern __shared__ uint8_t smem_raw[];
@@ -250,11 +251,19 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
                     sum[32 + i] += __uint_as_float(t2[i]);
                 }
             };
+            // column centring on the fly (sklearn: X -= mean_, in float32): GEMM2's thread owns one gene for the
+            // whole kernel, GEMM1's thread needs the 32 means of the current gene chunk
+            const float mu_g = (TR && tile0 + r < ld) ? __ldg(mu + tile0 + r) : 0.f;
             for (int c = 0; c < nk; c++) {
                 const int s = c % NS;
                 const uint32_t ph = (c / NS) & 1;
                 const int ab = c & 1;
                 const uint32_t aph = (c >> 1) & 1;
+                float4 m4[8];
+                if (!TR) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) m4[j] = __ldg(reinterpret_cast<const float4 *>(mu + (size_t)(chunk0 + c) * BK) + j);
+                }
                 mbar_wait(full + s, ph);
                 const uint8_t *sD = smem + (size_t)s * STAGE_BYTES;
                 uint32_t hi[32], lo[32];
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 x = *reinterpret_cast<const float4 *>(sD + r * 128 + ((j ^ (r & 7)) << 4));
-                        const float xs[4] = {x.x, x.y, x.z, x.w};
+                        const float xs[4] = {x.x - m4[j].x, x.y - m4[j].y, x.z - m4[j].z, x.w - m4[j].w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const uint32_t h = __float_as_uint(xs[e]) & 0xffffe000u;
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
                     const float *sDf = reinterpret_cast<const float *>(sD);
 #pragma unroll
                     for (int kk = 0; kk < 32; kk++) {
-                        const float x = sDf[kk * 128 + r];
+                        const float x = sDf[kk * 128 + r] - mu_g;
                         const uint32_t h = __float_as_uint(x) & 0xffffe000u;
                         hi[kk] = h;
                         lo[kk] = __float_as_uint(x - __uint_as_float(h));
@@ -307,11 +316,22 @@ __global__ void __launch_bounds__(192, 2) k_tc_gemm(const __grid_constant__ CUte
             if (!TR) {
                 const int64_t row = (int64_t)tile0 + r;
                 if (r < tile_rows && row < n_rows) {
+                    if (Y != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < LP; j += 4)
-                        *reinterpret_cast<float4 *>(Y + row * LP + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                        __uint_as_float(v[j + 3]));
+                        for (int j = 0; j < LP; j += 4)
+                            *reinterpret_cast<float4 *>(Y + row * LP + j) =
+                                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                            __uint_as_float(v[j + 3]));
+                    }
+                    if (ytiles != nullptr) {  // operand of the following D^T Y product, TF32 hi / lo parts
+#pragma unroll
+                        for (int j = 0; j < LP; j++) {
+                            const float y = __uint_as_float(v[j]);
+                            const float h = __uint_as_float(v[j] & 0xffffe000u);
+                            *reinterpret_cast<float *>(ytiles + dd_tc_b_offset(row, j, 0)) = h;
+                            *reinterpret_cast<float *>(ytiles + dd_tc_b_offset(row, j, 1)) = y - h;
+                        }
+                    }
                 }
             } else {
                 const int gene = tile0 + r;
@@ -405,12 +425,14 @@ void dd_tc_free(dd_handle *h) {
     h->tc = nullptr;
 }
 
-// Y = D Q   (Q as canonical hi/lo tiles in h->d_qb)
-int dd_tc_gemm_dq(dd_handle *h) {
+// Y = Dc Q   (Q as canonical hi/lo tiles in h->d_qb, Dc = D - mu centred on the fly).  write_y: store Y row-major
+// (h->d_Y); write_tiles: store Y as hi/lo operand tiles (h->d_yb) for the following Dc^T Y.
+int dd_tc_gemm_dq(dd_handle *h, bool write_y, bool write_tiles) {
     const int tr = h->tc->tile_rows;
     const unsigned grid = (unsigned)((h->A + tr - 1) / tr);
-    DD_LAUNCH(h, "tc_gemm_dq", (tcg::k_tc_gemm<false, 40>), grid, 192, tcg::SMEM_BYTES, h->tc->map_rows, h->d_qb, h->d_Y,
-              (double *)nullptr, h->A, (int)h->ld, 0, tr);
+    DD_LAUNCH(h, "tc_gemm_dq", (tcg::k_tc_gemm<false, 40>), grid, 192, tcg::SMEM_BYTES, h->tc->map_rows, h->d_qb, h->d_mu,
+              write_y ? h->d_Y : (float *)nullptr, write_tiles ? h->d_yb : (uint8_t *)nullptr, (double *)nullptr, h->A,
+              (int)h->ld, 0, tr);
     return DD_OK;
 }
 
@@ -423,7 +445,7 @@ int dd_tc_gemm_dty(dd_handle *h) {
     int cps = std::max(1, (total_chunks + splits - 1) / splits);
     splits = (total_chunks + cps - 1) / cps;
     DD_LAUNCH(h, "tc_gemm_dty", (tcg::k_tc_gemm<true, 40>), dim3(gblocks, splits), 192, tcg::SMEM_BYTES, h->tc->map_genes,
-              h->d_yb, (float *)nullptr, h->d_Zacc, h->A, (int)h->ld, cps, 128);
+              h->d_yb, h->d_mu, (float *)nullptr, (uint8_t *)nullptr, h->d_Zacc, h->A, (int)h->ld, cps, 128);
     return DD_OK;
 }
 

@@ -19,6 +19,6 @@ __host__ __device__ inline size_t dd_tc_b_offset(int64_t k, int n, int part) {
 bool dd_tc_pca_enabled();
 int dd_tc_prepare(dd_handle *h);
 void dd_tc_free(dd_handle *h);
-int dd_tc_gemm_dq(dd_handle *h);
+int dd_tc_gemm_dq(dd_handle *h, bool write_y, bool write_tiles);
 int dd_tc_gemm_dty(dd_handle *h);
 void dd_tc_pack_omega(const float *omega, int64_t n_genes, int n_random, int64_t ld, std::vector<uint8_t> &out);
