@@ -32,6 +32,8 @@ struct dd_tc_state;
 struct dd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // clustering (first Louvain level + result copies) overlaps the next iteration
+    cudaEvent_t ev_knn_done = nullptr, ev_lv_done = nullptr;
     int num_sms = 148;
     std::string err;
 

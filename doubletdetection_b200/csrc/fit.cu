@@ -195,16 +195,28 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         if ((rc = dd_dev_pca(h, p->n_comp, p->n_random, p->n_power_iter, omega_sent ? nullptr : omega)) != DD_OK) break;
         omega_sent = true;
         cudaEventRecord(ev[3], h->stream);
+        if (issued > 0) cudaStreamWaitEvent(h->stream, h->ev_lv_done, 0);  // previous graph build has read d_knn_idx
         if ((rc = dd_dev_knn(h, k)) != DD_OK) break;
         cudaEventRecord(ev[4], h->stream);
-        // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device
-        if ((rc = dd_dev_louvain_level0(h, k, p->resolution, p->seed)) != DD_OK) break;
-        cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, h->stream);
-        cudaMemcpyAsync(s.graph + (A + 1), h->d_lv_comm, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, h->stream);
-        cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, h->stream);
         dd_pca_flag_copy(h, s.flag);
-        cudaEventRecord(ev[5], h->stream);
-        cudaEventRecord(s.done, h->stream);
+        // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device.
+        // These are hundreds of small latency-bound kernels: they run on a second stream and overlap the
+        // HBM-bound dense build / PCA of the NEXT iteration.
+        cudaEventRecord(h->ev_knn_done, h->stream);
+        cudaStreamWaitEvent(h->stream2, h->ev_knn_done, 0);
+        {
+            cudaStream_t main_stream = h->stream;
+            h->stream = h->stream2;
+            rc = dd_dev_louvain_level0(h, k, p->resolution, p->seed);
+            h->stream = main_stream;
+        }
+        if (rc != DD_OK) break;
+        cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, h->stream2);
+        cudaMemcpyAsync(s.graph + (A + 1), h->d_lv_comm, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, h->stream2);
+        cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, h->stream2);
+        cudaEventRecord(ev[5], h->stream2);
+        cudaEventRecord(h->ev_lv_done, h->stream2);
+        cudaEventRecord(s.done, h->stream2);
         {
             std::lock_guard<std::mutex> lk(mu);
             jobs.push_back(Job{it, slot});
@@ -218,6 +230,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     cv_job.notify_all();
     for (std::thread &t : pool) t.join();
     cudaError_t ce = cudaStreamSynchronize(h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream2);
     if (rc == DD_OK && ce != cudaSuccess) rc = dd_fail(h, DD_ERR_CUDA, std::string("dd_fit_iterations: ") + cudaGetErrorString(ce));
     if (rc == DD_OK && worker_rc.load() != DD_OK) rc = dd_fail(h, worker_rc.load(), worker_err);
     if (rc == DD_OK && stage_ms_out) {

@@ -49,6 +49,7 @@ int dd_launch_end(dd_handle *h, const char *name) {
 static void resolve_pending(dd_handle *h) {
     if (h->pending.empty()) return;
     cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
     for (dd_timed_launch &t : h->pending) {
         float ms = 0.f;
         if (t.name && cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
@@ -100,6 +101,9 @@ extern "C" int dd_create(int device, dd_handle **out) {
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_knn_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_lv_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaEventCreate(&h->stage_ev0) != cudaSuccess || cudaEventCreate(&h->stage_ev1) != cudaSuccess) {
         delete h;
@@ -113,6 +117,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
     void *bufs[] = {h->d_indptr, h->d_indices, h->d_data,   h->d_lib,   h->d_l1,      h->d_parents, h->d_sindptr,
                     h->d_scount, h->d_sindices, h->d_sdata, h->d_slib,  h->d_dense,   h->d_colsum,  h->d_colsumsq,
                     h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx, h->d_knn_dist, h->d_knn_ops, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32};
@@ -128,6 +133,9 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stage_ev0) cudaEventDestroy(h->stage_ev0);
     if (h->stage_ev1) cudaEventDestroy(h->stage_ev1);
+    if (h->ev_knn_done) cudaEventDestroy(h->ev_knn_done);
+    if (h->ev_lv_done) cudaEventDestroy(h->ev_lv_done);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

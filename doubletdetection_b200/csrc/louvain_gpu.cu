@@ -368,9 +368,11 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
     DD_LAUNCH(h, "lv_graph_scan", k_graph_scan, 1, 1024, 0, deg, n, h->d_lv_off, counters);
     DD_LAUNCH(h, "lv_graph_fill", k_graph_fill, nb, 256, 0, h->d_knn_idx, n, (int)k, h->d_lv_off, cursor, h->d_lv_adj,
               h->d_lv_comm, h->d_lv_tot, csize);
-    // default: ALL rounds in one cooperative launch (one CTA per SM, hand-written grid barrier);
-    // DD_LOUVAIN_GRAPH=1: one launch per step replayed from a CUDA graph (~10 us per step: launch-latency bound).
-    static const bool use_graph = getenv("DD_LOUVAIN_GRAPH") != nullptr;
+    // default: one small launch per step, replayed from a CUDA graph -- the steps are latency-bound (~10 us each),
+    // but as ordinary kernels on the clustering stream they share the SMs with the HBM-bound kernels of the next
+    // iteration.  DD_LOUVAIN_COOP=1: all rounds in ONE cooperative launch (one CTA per SM, hand-written grid
+    // barrier) -- fewer launches, but it monopolises the SMs.
+    static const bool use_graph = getenv("DD_LOUVAIN_COOP") == nullptr;
     if (!use_graph) {
         const int blocks_per_sm = 1;
         static bool attr_set = false;
