@@ -40,20 +40,19 @@ def _pca_solver(n_samples, n_features, n_components):
 def _pca_plan(n_samples, n_features, n_components, random_state):
     """Test matrix and power-iteration count of sklearn's randomized SVD
     (sklearn/utils/extmath.py:323-333, 584-587): Omega = RandomState(seed).normal((G, C + 10)) cast to
-    float32, 7 iterations when C < 0.1 * min(shape) else 4."""
+    float32 (one row per cell instead when there are fewer augmented cells than genes), 7 iterations when
+    C < 0.1 * min(shape) else 4."""
     solver = _pca_solver(n_samples, n_features, n_components)
     if solver != "randomized":
         raise NotImplementedError(
             f"sklearn's PCA(svd_solver='auto') picks '{solver}' for a {n_samples} x {n_features} matrix with "
             f"n_components={n_components}; only the 'randomized' branch is implemented on the B200 hot path"
         )
-    if n_samples < n_features:
-        raise NotImplementedError(
-            "fewer augmented cells than genes: sklearn's randomized SVD transposes the problem; that branch "
-            "is not implemented on the B200 hot path (lower n_top_var_genes)"
-        )
     n_power_iter = 7 if n_components < 0.1 * min(n_samples, n_features) else 4
-    omega = np.random.RandomState(random_state).normal(size=(n_features, n_components + 10)).astype(np.float32)
+    # fewer samples than features: sklearn works on the transposed matrix, so Omega has one row per SAMPLE
+    # (sklearn/utils/extmath.py:589-592: transpose = n_samples < n_features)
+    rows = n_samples if n_samples < n_features else n_features
+    omega = np.random.RandomState(random_state).normal(size=(rows, n_components + 10)).astype(np.float32)
     return omega, n_power_iter
 
 

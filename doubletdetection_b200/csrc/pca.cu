@@ -493,8 +493,8 @@ constexpr size_t kJacobiSmem = sizeof(double) * 2 * kMaxLP * (kMaxLP + 1);
 // entry of column j of W (first gene wins ties).  One thread per gene computes its row of W; the arg-max per
 // column is a 64-bit atomicMax over keys  [ |w| (float64 bits, low 21 mantissa bits dropped) | ~gene | sign ].
 template <int LP>
-__global__ void __launch_bounds__(128) k_signs_w(const double *__restrict__ Zd, int n_genes, int L, int C,
-                                                 const double *__restrict__ evec,
+__global__ void __launch_bounds__(128) k_signs_w(const double *__restrict__ Zd, const float *__restrict__ Qt, int ld,
+                                                 int n_genes, int L, int C, const double *__restrict__ evec,
                                                  unsigned long long *__restrict__ keys) {
     __shared__ double Us[LP][LP + 1];
     for (int e = threadIdx.x; e < LP * LP; e += 128) Us[e / LP][e % LP] = evec[e];
@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(128) k_signs_w(const double *__restrict__ Zd, 
     const bool ok = g < n_genes;
     double z[LP];
 #pragma unroll
-    for (int i = 0; i < LP; i++) z[i] = ok ? Zd[(int64_t)g * LP + i] : 0.0;
+    for (int i = 0; i < LP; i++)  // rows of Z (float64, gene-major) or of Q given as Q^T (float32, LP x ld)
+        z[i] = ok ? (Qt != nullptr ? (double)Qt[(int64_t)i * ld + g] : Zd[(int64_t)g * LP + i]) : 0.0;
     const int lane = threadIdx.x & 31;
     for (int j = 0; j < C; j++) {
         double w = 0.0;
@@ -529,12 +530,13 @@ template <int LP, int KP>
 __global__ void __launch_bounds__(128) k_embed(const float *__restrict__ Yq, int64_t n_rows, int L, int C,
                                                const double *__restrict__ evec, const double *__restrict__ eval,
                                                const unsigned long long *__restrict__ keys, float *__restrict__ emb,
-                                               double *__restrict__ sing_out) {
+                                               double *__restrict__ sing_out, int scale_by_s) {
     __shared__ double Ts[LP][KP];
     for (int e = threadIdx.x; e < LP * KP; e += blockDim.x) {
         const int i = e / KP, c = e % KP;
         double v = 0.0;
-        if (i < L && c < C) v = evec[i * LP + c] * sqrt(fmax(eval[c], 0.0)) * ((keys[c] & 1ull) ? -1.0 : 1.0);
+        if (i < L && c < C)
+            v = evec[i * LP + c] * (scale_by_s ? sqrt(fmax(eval[c], 0.0)) : 1.0) * ((keys[c] & 1ull) ? -1.0 : 1.0);
         Ts[i][c] = v;
     }
     if (blockIdx.x == 0 && threadIdx.x < C) sing_out[threadIdx.x] = sqrt(fmax(eval[threadIdx.x], 0.0));
@@ -667,15 +669,73 @@ int run_pca(dd_handle *h, int n_power_iter) {
     // svd(B) with B^T = Z:  B B^T = Z^T Z = gram
     DD_LAUNCH(h, "jacobi", k_jacobi, 1, 256, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm + OFF_KEYS);
-    DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, h->d_Zacc, (int)h->G, L, C,
-              sm + OFF_EVEC, keys);
+    DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, h->d_Zacc, (const float *)nullptr, 0,
+              (int)h->G, L, C, sm + OFF_EVEC, keys);
     const int egrid = (int)((A + 127) / 128);
     if (KP == 32)
         DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
-                  h->d_emb, sm + OFF_CSUM);
+                  h->d_emb, sm + OFF_CSUM, 1);
     else
         DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
-                  h->d_emb, sm + OFF_CSUM);
+                  h->d_emb, sm + OFF_CSUM, 1);
+    return DD_OK;
+}
+
+// Fewer rows than columns (A < G): sklearn's randomized_svd works on the transposed problem M = Dc^T
+// (sklearn/utils/extmath.py:589-592, 618-620): Omega is A x L, the loop is
+//     Q_G = normalise(Dc^T Q_A);  Q_A = normalise(Dc Q_G)        (n_iter times)
+//     Q_G = qr(Dc^T Q_A);  B = Q_G^T Dc^T = (Dc Q_G)^T;  svd(B) = Uhat S Vt;  U_int = Q_G Uhat
+// and the roles are swapped back at the end: scores U = Vt^T = Y Uhat / S with Y = Dc Q_G, components = U_int^T.
+// Hence X_pca = U S = Y Uhat (sign from the largest-|.| entry of each column of Q_G Uhat).  Same kernels as the
+// regular path; only the gene side (G x L, the small one) is orthonormalised, in float64.
+int run_pca_transposed(dd_handle *h, int n_power_iter) {
+    constexpr int LP = 40;
+    const int64_t A = h->A;
+    const int ld = (int)h->ld;
+    const int L = h->L, C = h->C, KP = h->KP;
+    double *sm = h->d_small;
+    const int tall_grid = h->num_sms * 2;
+    const double inv_A = 1.0 / (double)A;
+    DD_TRY(dd_tc_prepare(h));
+    const int64_t q_bytes = (int64_t)(ld / 32) * 12288, y_bytes = ((A + 31) / 32) * 12288;
+    if (q_bytes > h->cap_qb || y_bytes > h->cap_yb) {
+        DD_TRY(dd_reserve(h, &h->d_qb, &h->cap_qb, q_bytes));
+        DD_TRY(dd_reserve(h, &h->d_yb, &h->cap_yb, y_bytes));
+        DD_CUDA(h, cudaMemsetAsync(h->d_qb, 0, (size_t)h->cap_qb, h->stream));
+        DD_CUDA(h, cudaMemsetAsync(h->d_yb, 0, (size_t)h->cap_yb, h->stream));
+    }
+    DD_CUDA(h, cudaMemsetAsync(sm, 0, sizeof(double) * SMALL_DOUBLES, h->stream));
+    DD_CUDA(h, cudaMemsetAsync(h->d_Zacc, 0, sizeof(double) * (size_t)ld * LP, h->stream));
+    DD_CUDA(h, cudaMemcpyAsync(h->d_yb, h->d_omega_b, (size_t)y_bytes, cudaMemcpyDeviceToDevice, h->stream));  // Q_A = Omega
+    DD_TRY(dd_dev_colstats(h, false));
+    DD_TRY(dd_reserve(h, &h->d_mu, &h->cap_mu, (int64_t)ld));
+    DD_LAUNCH(h, "mu", k_mu, (ld + 255) / 256, 256, 0, h->d_colsum, (int)h->G, ld, inv_A, h->d_mu);
+    for (int it = 0; it <= n_power_iter; it++) {
+        const bool last = it == n_power_iter;
+        DD_TRY(dd_tc_gemm_dty(h));  // Z = Dc^T Q_A
+        DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
+        DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
+                  h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
+        DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV, sm + OFF_FLAG);
+        DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
+                  sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, h->d_qb);  // Q_G (orthonormal), Zacc cleared
+        DD_TRY(dd_tc_gemm_dq(h, /*write_y=*/last, /*write_tiles=*/!last));     // Y = Dc Q_G
+    }
+    // svd(B), B^T = Y:  B B^T = Y^T Y
+    DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
+    DD_LAUNCH(h, "gram_tall", (k_gram<LP, 0>), tall_grid, 256, 0, h->d_Y, nullptr, A, nullptr, 0.0, nullptr, sm + OFF_GRAM,
+              sm + OFF_EVAL /*unused sums*/);
+    DD_LAUNCH(h, "jacobi", k_jacobi, 1, 256, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm + OFF_KEYS);
+    DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, (const double *)nullptr, h->d_Qt, ld,
+              (int)h->G, L, C, sm + OFF_EVEC, keys);
+    const int egrid = (int)((A + 127) / 128);
+    if (KP == 32)
+        DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
+                  h->d_emb, sm + OFF_CSUM, 0);
+    else
+        DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
+                  h->d_emb, sm + OFF_CSUM, 0);
     return DD_OK;
 }
 
@@ -690,9 +750,10 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
     if (h->G > 0xFFFFF) return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: more than 2^20 - 1 genes");
     if (n_random > h->G || n_random > h->A)
         return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 exceeds the matrix dimensions");
-    if (h->A < h->G)
+    const bool transposed = h->A < h->G;  // sklearn works on the transposed problem: Omega is A x n_random
+    if (transposed && (n_random > 40 || !dd_tc_pca_enabled()))
         return dd_fail(h, DD_ERR_UNSUPPORTED,
-                       "pca: fewer augmented cells than genes (sklearn's transposed randomized SVD) is outside the B200 hot path");
+                       "pca: fewer augmented cells than genes needs the tcgen05 path (n_components + 10 <= 40)");
     const int LP = n_random <= 40 ? 40 : 64;
     const int KP = n_comp <= 32 ? 32 : 64;
     const int64_t A = h->A, ld = h->ld;
@@ -711,7 +772,13 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
         h->L = 0;  // forces an Omega upload
     }
     float *omega_dev = h->d_Qt + (size_t)h->cap_LP * h->cap_pca_cols;
-    if (omega_host) {
+    if (omega_host && transposed) {
+        std::vector<uint8_t> packed;
+        dd_tc_pack_omega(omega_host, A, n_random, dd_round_up(A, 32), packed);  // rows of Omega are cells here
+        DD_TRY(dd_reserve(h, &h->d_omega_b, &h->cap_omega_b, (int64_t)packed.size()));
+        DD_CUDA(h, cudaMemcpyAsync(h->d_omega_b, packed.data(), packed.size(), cudaMemcpyHostToDevice, h->stream));
+        DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else if (omega_host) {
         std::vector<float> qt((size_t)LP * ld, 0.f);
         for (int64_t g = 0; g < h->G; g++)
             for (int j = 0; j < n_random; j++) qt[(size_t)j * ld + g] = omega_host[g * n_random + j];
@@ -727,7 +794,8 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
         return dd_fail(h, DD_ERR_ARG, "pca: omega is NULL but no matching test matrix was uploaded before");
     }
     h->L = n_random; h->LP = LP; h->C = n_comp;
-    DD_CUDA(h, cudaMemcpyAsync(h->d_Qt, omega_dev, sizeof(float) * LP * ld, cudaMemcpyDeviceToDevice, h->stream));
+    if (!transposed)
+        DD_CUDA(h, cudaMemcpyAsync(h->d_Qt, omega_dev, sizeof(float) * LP * ld, cudaMemcpyDeviceToDevice, h->stream));
     if (h->KP != KP || A > h->cap_emb) {
         if (h->d_emb) cudaFree(h->d_emb);
         h->d_emb = nullptr; h->cap_emb = 0;
@@ -735,7 +803,8 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
         h->cap_emb = A;
     }
     h->KP = KP;
-    int rc = (LP == 40) ? run_pca<40>(h, n_power_iter) : run_pca<64>(h, n_power_iter);
+    int rc = transposed ? run_pca_transposed(h, n_power_iter)
+                        : ((LP == 40) ? run_pca<40>(h, n_power_iter) : run_pca<64>(h, n_power_iter));
     if (rc != DD_OK) return rc;
     h->emb_rows = A;
     h->emb_valid = true;

@@ -80,9 +80,10 @@ int dd_download_dense(dd_handle *h, int64_t row0, int64_t n_rows, float *out);
 int dd_upload_dense(dd_handle *h, int64_t n_rows, int64_t n_genes, const float *dense);
 
 /* ---- sc.tl.pca(..., svd_solver="auto") == sklearn randomized PCA, doubletdetection.py:309-314
- * omega: float32[G * n_random] row-major, the Gaussian test matrix sklearn draws
- * (RandomState(random_state).normal(size=(G, n_comp+10)) cast to float32).  n_power_iter = 7 or
- * 4 (sklearn's "auto").  Leaves the float32 A x n_comp embedding on the device; emb_out may be
+ * omega: float32[R * n_random] row-major, the Gaussian test matrix sklearn draws
+ * (RandomState(random_state).normal(size=(R, n_comp+10)) cast to float32) with R = G, or R = A when
+ * there are fewer augmented cells than genes (sklearn then factorises the transposed matrix).
+ * n_power_iter = 7 or 4 (sklearn's "auto").  Leaves the float32 A x n_comp embedding on the device; emb_out may be
  * NULL.  singular_values_out (float64[n_comp]) may be NULL. */
 int dd_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter, const float *omega,
            float *emb_out, double *singular_values_out);

@@ -94,11 +94,46 @@ def test_pca_embedding_vs_float64_oracle(handle, name):
     np.testing.assert_allclose(got_sv, sv, rtol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(700, 1000), (333, 2051), (1200, 1250)])
+def test_pca_fewer_cells_than_genes(handle, shape):
+    """A < G: sklearn factorises the transposed matrix (Omega has one row per cell); same 1e-4 tolerance."""
+    rs = np.random.default_rng(shape[0])
+    a, g_ = shape
+    centres = rs.normal(size=(5, g_)) * 2.0
+    X = (centres[rs.integers(0, 5, a)] + rs.normal(size=(a, g_))).astype(np.float32)
+    C = 30
+    n_iter = pca_f64.auto_n_iter(a, g_, C)
+    want, sv, _ = pca_f64.randomized_pca_f64(X, C, random_state=0)
+    omega = pca_f64.omega(a, C, 0).astype(np.float32)  # rows = samples in the transposed problem
+    handle.upload_dense(X)
+    emb, got_sv = handle.pca(C, omega, n_iter)
+    err = _rel(emb, want)
+    print(f"\n[transposed {shape}] GPU vs f64 oracle: {err:.2e}")
+    assert err < 1e-4
+    np.testing.assert_allclose(got_sv, sv, rtol=1e-5)
+
+
+def test_classifier_fewer_cells_than_genes():
+    """The reference's default n_top_var_genes=10000 makes A < G the normal case for small datasets."""
+    from doubletdetection_b200 import BoostClassifier
+
+    counts = datasets.structured_counts(600, 1500, seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(n_iters=3, clustering_algorithm="louvain", random_state=2)
+        labels = clf.fit(counts).predict(p_thresh=1e-3, voter_thresh=0.5)
+        ora = reference_path.OracleClassifier(n_iters=3, random_state=2, louvain_fn=louvain_c.louvain)
+        want = ora.fit(counts).predict(p_thresh=1e-3, voter_thresh=0.5)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    np.testing.assert_array_equal(labels, want)
+    same = (clf.communities_ == ora.communities_).all(axis=1)
+    print(f"\n[A<G classifier] iterations with identical communities: {int(same.sum())}/{same.size}")
+    for i in np.nonzero(same)[0]:
+        np.testing.assert_allclose(clf.all_log_p_values_[i], ora.all_log_p_values_[i], rtol=1e-4, atol=1e-12)
+
+
 def test_pca_unsupported_shapes_fail_loudly(handle):
     rs = np.random.default_rng(0)
-    handle.upload_dense(rs.normal(size=(50, 80)).astype(np.float32))  # fewer rows than genes
-    with pytest.raises(NotImplementedError):
-        handle.pca(10, rs.normal(size=(80, 20)).astype(np.float32), 4)
     h2 = type(handle)(0)
     h2.upload_dense(np.ones((300, 64), dtype=np.float32))  # rank 0 after centring
     with pytest.raises(NotImplementedError):

@@ -93,3 +93,16 @@ def test_f64_pca_close_to_sklearn_f32():
     emb64, _, _ = pca_f64.randomized_pca_f64(X, 30, random_state=0)
     scale = np.abs(emb64).max()
     assert np.abs(emb64 - g["X_pca0"]).max() / scale < 2e-3
+
+
+def test_f64_pca_transposed_branch_matches_sklearn():
+    """Fewer samples than features: sklearn's randomized_svd transposes the problem.  The float64 restatement
+    must follow it (same Omega shape, same sign convention)."""
+    from sklearn.decomposition import PCA
+
+    rs = np.random.default_rng(3)
+    centres = rs.normal(size=(4, 900)) * 2.0
+    X = (centres[rs.integers(0, 4, 600)] + rs.normal(size=(600, 900))).astype(np.float32)
+    want = PCA(n_components=30, svd_solver="randomized", random_state=0).fit_transform(X)
+    got, _, _ = pca_f64.randomized_pca_f64(X, 30, random_state=0)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-3
