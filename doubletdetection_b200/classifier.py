@@ -11,7 +11,8 @@ B200 ``fit`` raises.
 
 Keyword-only extensions (not in the reference): ``device`` (CUDA device index; default
 ``LOCAL_RANK`` or 0) and ``distributed`` (shard the independent iterations over the ranks of an
-initialised ``torch.distributed`` group and all-gather the per-iteration results).
+initialised ``torch.distributed`` group; ``True`` gathers the per-iteration results on rank 0,
+``"allgather"`` on every rank).
 """
 
 import os
@@ -91,7 +92,7 @@ class BoostClassifier:
         self.pseudocount = pseudocount
         self.rng = np.random.default_rng(self.random_state)  # :99 -- one stream for all fits
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
-        self.distributed = bool(distributed)
+        self.distributed = distributed  # False | True (results gathered on rank 0) | "allgather" (on every rank)
 
         if self.clustering_algorithm not in ["louvain", "phenograph", "leiden"]:  # :101-104
             raise ValueError("Clustering algorithm needs to be one of ['louvain', 'phenograph', 'leiden']")
@@ -247,7 +248,7 @@ class BoostClassifier:
         )
         _t.append(_time.perf_counter())
         if dist is not None:
-            out = _allgather_iterations(dist, out, self.n_iters, self.device)
+            out = _allgather_iterations(dist, out, self.n_iters, self.device, everywhere=self.distributed == "allgather")
         self.stage_ms_ = out["stage_ms"]
 
         self.all_scores_ = out["scores"]
@@ -300,32 +301,40 @@ def iteration_shard(n_iters, rank, world):
     return (n_iters * rank) // world, (n_iters * (rank + 1)) // world
 
 
-def _allgather_iterations(dist, out, n_iters, device):
-    """Every rank filled only its own rows of the (n_iters, .) result arrays.  With equal blocks the rows are
-    exchanged with one all-gather per array (each rank ships only what it computed); otherwise a sum
-    all-reduce of the zero-padded arrays assembles them.  No data-path collective is involved -- this is
-    result collection."""
+def _allgather_iterations(dist, out, n_iters, device, everywhere=False):
+    """Collect the per-iteration result rows (every rank filled only its own block of the (n_iters, .) arrays).
+    Default: gather on rank 0, which is where ``predict`` / ``doublet_score`` are evaluated -- the other ranks
+    keep their own rows only.  ``everywhere=True`` (``distributed="allgather"``): every rank ends up with the
+    complete arrays.  No data-path collective is involved -- this is result collection."""
     import torch
 
     backend = dist.get_backend()
     dev = torch.device("cuda", device) if backend == "nccl" else torch.device("cpu")
     rank, world = dist.get_rank(), dist.get_world_size()
-    it0, it1 = iteration_shard(n_iters, rank, world)
-    even = n_iters % world == 0
+    blocks = [iteration_shard(n_iters, r, world) for r in range(world)]
+    it0, it1 = blocks[rank]
     merged = {}
     for key in ("scores", "log_p", "communities", "synth_communities"):
         a = np.ascontiguousarray(out[key])
         as_bits = key in ("scores", "log_p")  # NaN / -inf entries must survive: ship float64 as bit patterns
-        src = a.view(np.int64) if as_bits else a.astype(np.int64)
-        if even:
-            mine = torch.from_numpy(np.ascontiguousarray(src[it0:it1])).to(dev)
-            full = torch.empty((n_iters,) + tuple(mine.shape[1:]), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(full, mine)
+        src = a.view(np.int64) if as_bits else a.astype(np.int32)
+        tdtype = torch.int64 if as_bits else torch.int32
+        rows = max(b1 - b0 for b0, b1 in blocks)  # collectives want equal shapes: pad the shorter blocks
+        block = np.zeros((rows,) + src.shape[1:], dtype=src.dtype)
+        block[: it1 - it0] = src[it0:it1]
+        mine = torch.from_numpy(block).to(dev)
+        parts = None
+        if everywhere or rank == 0:
+            parts = [torch.empty_like(mine) for _ in blocks]
+        if everywhere:
+            dist.all_gather(parts, mine)
         else:
-            full = torch.from_numpy(src.copy()).to(dev)
-            dist.all_reduce(full, op=dist.ReduceOp.SUM)
-        r = full.cpu().numpy()
-        merged[key] = r.view(np.float64) if as_bits else r.astype(np.int32)
+            dist.gather(mine, gather_list=parts, dst=0)
+        if parts is not None:
+            r = torch.cat([t[: b1 - b0] for t, (b0, b1) in zip(parts, blocks)], dim=0).cpu().numpy()
+            merged[key] = r.view(np.float64) if as_bits else r
+        else:
+            merged[key] = out[key]
     stage = torch.tensor([out["stage_ms"][k] for k in sorted(out["stage_ms"])], dtype=torch.float64, device=dev)
     dist.all_reduce(stage, op=dist.ReduceOp.MAX)
     merged["stage_ms"] = dict(zip(sorted(out["stage_ms"]), stage.cpu().tolist()))

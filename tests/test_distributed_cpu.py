@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_iters, n_cells, n_synth, q):
+def _worker(rank, world, port, n_iters, n_cells, n_synth, q, everywhere=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -40,8 +40,11 @@ def _worker(rank, world, port, n_iters, n_cells, n_synth, q):
         for k in truth:
             mine[k][it0:it1] = truth[k][it0:it1]
         mine["stage_ms"] = {"pca": 1.0 + rank, "knn": 5.0 - rank}
-        merged = _allgather_iterations(dist, mine, n_iters, device=0)
-        ok = all(np.array_equal(merged[k], truth[k], equal_nan=True) for k in truth)
+        merged = _allgather_iterations(dist, mine, n_iters, device=0, everywhere=everywhere)
+        if everywhere or rank == 0:
+            ok = all(np.array_equal(merged[k], truth[k], equal_nan=True) for k in truth)
+        else:  # gather-on-rank-0 mode: the other ranks keep exactly what they computed
+            ok = all(np.array_equal(merged[k], mine[k], equal_nan=True) for k in truth)
         ok = ok and merged["stage_ms"] == {"knn": 5.0, "pca": float(world)}
         q.put((rank, bool(ok)))
     finally:
@@ -54,9 +57,9 @@ def test_iteration_sharding_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    for n_iters in (5, 6):  # uneven blocks -> all-reduce path, even blocks -> all-gather path
+    for n_iters, everywhere in ((5, True), (6, False)):  # uneven and even blocks; all-gather and gather-to-0
         port = _free_port()
-        procs = [ctx.Process(target=_worker, args=(r, world, port, n_iters, 40, 10, q)) for r in range(world)]
+        procs = [ctx.Process(target=_worker, args=(r, world, port, n_iters, 40, 10, q, everywhere)) for r in range(world)]
         for p in procs:
             p.start()
         results = [q.get(timeout=100) for _ in range(world)]
