@@ -361,3 +361,88 @@ def test_config2_properties_and_sampled_parity(handle):
     want_i, want_d = upstream.knn_brute(emb, 10)  # oracle kNN on the SAME (GPU) embedding
     np.testing.assert_array_equal(idx, want_i)
     assert (idx[:, 0] == np.arange(idx.shape[0])).all() and (np.diff(dist[:, 1:], axis=1) >= 0).all()
+
+
+def test_config3_full_size_properties():
+    """100k cells x 3k genes (BASELINE configs[2]) through the public API: size-independent properties of every
+    stage (the oracle cannot run this size in seconds)."""
+    from doubletdetection_b200 import BoostClassifier, _capi
+
+    raw = datasets.structured_counts(100000, 3000, seed=1234)
+    n, g_ = raw.shape
+    m = n // 4
+    rng = np.random.default_rng(0)
+    parents = rng.choice(n, size=(m, 2), replace=False)
+    h = _capi.Handle(0)
+    try:
+        h.upload_counts(raw)
+        lib = np.asarray(raw.sum(axis=1)).ravel().astype(np.float32)
+        np.testing.assert_array_equal(h.lib_size(), lib)
+        # CSR row-pair add: linearity of the row sums, sorted unique columns, nnz bounds, a checksum of checksums
+        h.create_doublets(parents)
+        syn = h.download_synthetics()
+        np.testing.assert_array_equal(h.synth_lib_size(), lib[parents[:, 0]] + lib[parents[:, 1]])
+        nnz_rows = np.diff(raw.indptr)
+        srows = np.diff(syn.indptr)
+        assert (srows <= nnz_rows[parents[:, 0]] + nnz_rows[parents[:, 1]]).all()
+        assert (srows >= np.maximum(nnz_rows[parents[:, 0]], nnz_rows[parents[:, 1]])).all()
+        inner = np.ones(syn.nnz - 1, dtype=bool)
+        inner[syn.indptr[1:-1] - 1] = False
+        assert (np.diff(syn.indices)[inner] > 0).all()
+        assert float(syn.data.sum(dtype=np.float64)) == float(lib[parents].sum(dtype=np.float64))
+        col_chk = np.asarray(syn.sum(axis=0)).ravel()
+        want_chk = np.asarray(raw[parents[:, 0]].sum(axis=0)).ravel() + np.asarray(raw[parents[:, 1]].sum(axis=0)).ravel()
+        np.testing.assert_array_equal(col_chk, want_chk)
+        # dense matrix: zeros of the counts carry log(pc); sampled rows equal the oracle's arithmetic
+        med = h.median_lib_size()
+        assert med == np.median(np.concatenate([lib, lib[parents[:, 0]] + lib[parents[:, 1]]]))
+        h.normalise_log(med, 0.1)
+        rows = np.array([0, 1, n - 1, n, n + 7, n + m - 1])
+        for r in rows:
+            got = h.download_dense(int(r), 1)[0]
+            if r < n:
+                x = np.asarray(raw[r].todense()).ravel()
+                tot = np.float64(np.abs(x).sum())
+            else:
+                x = np.asarray((raw[parents[r - n, 0]] + raw[parents[r - n, 1]]).todense()).ravel()
+                tot = np.float64(np.abs(x).sum())
+            want = np.log((x.astype(np.float64) / tot).astype(np.float32) * med + np.float32(0.1))
+            np.testing.assert_allclose(got, want, rtol=3e-6, atol=3e-7)
+        # PCA: components uncorrelated, singular values descending and consistent with the scores
+        C = 30
+        omega = pca_f64.omega(g_, C, 0).astype(np.float32)
+        emb, sv = h.pca(C, omega, 7)
+        assert np.all(np.diff(sv) <= 0) and np.isfinite(emb).all()
+        gram = emb.astype(np.float64).T @ emb.astype(np.float64)
+        np.testing.assert_allclose(np.sqrt(np.diag(gram)), sv, rtol=1e-5)
+        off = gram - np.diag(np.diag(gram))
+        assert np.abs(off).max() < 1e-5 * sv[0] ** 2
+        assert np.abs(emb.mean(axis=0, dtype=np.float64)).max() < 1e-3
+        # kNN: self first, ascending distances, exactness on sampled queries (brute force in float64)
+        idx, dist = h.knn(10)
+        assert (idx[:, 0] == np.arange(n + m)).all() and (dist[:, 0] == 0).all()
+        assert (np.diff(dist[:, 1:], axis=1) >= 0).all()
+        assert idx.min() >= 0 and idx.max() < n + m
+        e64 = emb.astype(np.float64)
+        for q in rng.choice(n + m, size=40, replace=False):
+            d2 = ((e64 - e64[q]) ** 2).sum(axis=1)
+            d2[q] = np.inf
+            order = np.lexsort((np.arange(n + m), d2))[:9]
+            np.testing.assert_array_equal(idx[q, 1:], order)
+    finally:
+        h.close()
+    # whole classifier: results are a valid partition / valid statistics and deterministic
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(n_iters=3, clustering_algorithm="louvain", n_jobs=8)
+        clf.fit(raw)
+        a = clf.all_log_p_values_.copy()
+        clf2 = BoostClassifier(n_iters=3, clustering_algorithm="louvain", n_jobs=8)
+        clf2.fit(raw)
+    np.testing.assert_array_equal(a, clf2.all_log_p_values_)
+    assert (a <= 1e-12).all() and ((clf.all_scores_ >= 0) & (clf.all_scores_ <= 1)).all()
+    assert clf.communities_.min() >= 0 and (clf.communities_ == np.floor(clf.communities_)).all()
+    for i in range(3):  # labels are ranked by decreasing community size over originals + synthetics
+        lab = np.concatenate([clf.communities_[i], clf.synth_communities_[i]]).astype(np.int64)
+        sizes = np.bincount(lab)
+        assert (sizes > 0).all() and (np.diff(sizes) <= 0).all()
