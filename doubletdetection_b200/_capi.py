@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
-ABI_VERSION = 1
+ABI_VERSION = 2
+COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
@@ -80,6 +81,10 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.POINTER(FitParams), c_i64p, c_f32p, c_f64p, c_f64p, c_i32p, c_i32p, c_f64p],
     ),
+    "dd_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "dd_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]),
+    "dd_comm_shard_cells": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "dd_comm_info": (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_i64p]),
     "dd_kernel_launches": (ctypes.c_int64, [ctypes.c_void_p]),
     "dd_last_stage_ms": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_char_p]),
     "dd_set_kernel_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
@@ -181,6 +186,21 @@ def score(labels, n_cells):
 
 def hypergeom_logsf(k, M, n, N):
     return load().dd_hypergeom_logsf(int(k), int(M), int(n), int(N))
+
+
+def comm_unique_id():
+    """Rendezvous token of a new NCCL communicator (call on rank 0, ship the bytes to every rank)."""
+    lib = load()
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    rc = lib.dd_comm_unique_id(buf, COMM_ID_BYTES)
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return buf.raw
+
+
+def block_of(n, rank, world):
+    """The [begin, end) share of ``n`` items rank ``rank`` of ``world`` owns (same rule as the library)."""
+    return n * rank // world, n * (rank + 1) // world
 
 
 # ---- device handle ------------------------------------------------------------------------------
@@ -324,6 +344,22 @@ class Handle:
         names = ["host_cluster_score", "normalise", "scale", "pca", "knn", "cluster_gpu_d2h", "device_total", "wall"]
         return dict(scores=scores, log_p=logp, communities=comm, synth_communities=synth_comm[:, :n_synth],
                     stage_ms=dict(zip(names, stage_ms.tolist())))
+
+    # cell-block sharding (one handle per rank / GPU)
+    def comm_init(self, rank, world, unique_id):
+        """Collective over all ranks; ``unique_id`` is rank 0's :func:`comm_unique_id` token."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(self._lib.dd_comm_init(self._h, int(rank), int(world), buf, COMM_ID_BYTES))
+
+    def shard_cells(self, on=True):
+        self._check(self._lib.dd_comm_shard_cells(self._h, int(bool(on))))
+
+    def comm_info(self):
+        rank, world = ctypes.c_int32(0), ctypes.c_int32(0)
+        block = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.dd_comm_info(self._h, ctypes.byref(rank), ctypes.byref(world), _ptr(block, ctypes.c_int64)))
+        return dict(rank=rank.value, world=world.value, first_cell=int(block[0]), n_cells=int(block[1]),
+                    first_synth=int(block[2]), n_synth=int(block[3]))
 
     # introspection
     def kernel_launches(self):

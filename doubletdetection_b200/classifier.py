@@ -10,9 +10,12 @@ host code overlapped with the GPU.  There is no CPU fallback: without the built 
 B200 ``fit`` raises.
 
 Keyword-only extensions (not in the reference): ``device`` (CUDA device index; default
-``LOCAL_RANK`` or 0) and ``distributed`` (shard the independent iterations over the ranks of an
-initialised ``torch.distributed`` group; ``True`` gathers the per-iteration results on rank 0,
-``"allgather"`` on every rank).
+``LOCAL_RANK`` or 0) and ``distributed`` (shard the work over the ranks of an initialised
+``torch.distributed`` group, one process per GPU).  ``True`` deals the independent iterations to the ranks
+and gathers the per-iteration results on rank 0, ``"allgather"`` on every rank (BASELINE config 4);
+``"cells"`` shards the CELLS of every iteration instead (BASELINE config 5): each rank builds and factorises
+its block of the augmented matrix, the PCA reductions are NCCL all-reduces and the embedding / kNN lists are
+all-gathered inside ``libdd_b200.so`` -- every rank ends up with the complete results.
 """
 
 import os
@@ -92,7 +95,11 @@ class BoostClassifier:
         self.pseudocount = pseudocount
         self.rng = np.random.default_rng(self.random_state)  # :99 -- one stream for all fits
         self.device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
-        self.distributed = distributed  # False | True (results gathered on rank 0) | "allgather" (on every rank)
+        # False | True (iterations sharded, results on rank 0) | "allgather" (same, results everywhere) |
+        # "cells" (cells of every iteration sharded, NCCL inside the library)
+        if distributed not in (False, True, "allgather", "cells"):
+            raise ValueError("distributed must be one of False, True, 'allgather', 'cells'")
+        self.distributed = distributed
 
         if self.clustering_algorithm not in ["louvain", "phenograph", "leiden"]:  # :101-104
             raise ValueError("Clustering algorithm needs to be one of ['louvain', 'phenograph', 'leiden']")
@@ -234,8 +241,17 @@ class BoostClassifier:
             if dist_mod.is_available() and dist_mod.is_initialized() and dist_mod.get_world_size() > 1:
                 dist = dist_mod
                 rank, world = dist.get_rank(), dist.get_world_size()
-                it0 = (self.n_iters * rank) // world
-                it1 = (self.n_iters * (rank + 1)) // world
+                if self.distributed == "cells":
+                    if not getattr(h, "_comm_ready", False):
+                        token = broadcast_token(dist, _capi.comm_unique_id() if rank == 0 else None, self.device)
+                        h.comm_init(rank, world, token)
+                        h._comm_ready = True
+                    h.shard_cells(True)
+                    dist = None  # every rank runs every iteration and holds the complete results
+                else:
+                    it0, it1 = iteration_shard(self.n_iters, rank, world)
+        if self.distributed != "cells" and getattr(h, "_comm_ready", False):
+            h.shard_cells(False)
 
         if self.verbose:
             print(f"Running iterations {it0 + 1}..{it1} of {self.n_iters} on cuda:{self.device}")
@@ -294,6 +310,19 @@ class BoostClassifier:
         else:
             avg_log_p = self.all_log_p_values_[0]
         return -avg_log_p
+
+
+def broadcast_token(dist, token, device):
+    """Ship rank 0's NCCL rendezvous token (bytes) to every rank over the existing process group."""
+    import torch
+
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    buf = torch.zeros(_capi.COMM_ID_BYTES, dtype=torch.uint8)
+    if token is not None:
+        buf[: len(token)] = torch.frombuffer(bytearray(token), dtype=torch.uint8)
+    buf = buf.to(dev)
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
 
 
 def iteration_shard(n_iters, rank, world):

@@ -296,6 +296,100 @@ __global__ void k_dense_rows(const int32_t *__restrict__ indptr, const int32_t *
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dense rows without shared-memory staging (the default).  The matrix is ~85-90 % the constant log(pc), so a
+// row is (1) a coalesced 128-bit fill of the constant, (2) a scatter of the transformed non-zeros on top of it.
+// Both land in L2 (the row was written a few hundred cycles earlier), which merges them before the lines are
+// evicted to HBM once: DRAM traffic stays the algorithmic 8 B per stored entry + 4 B per dense element, there is
+// no per-warp row buffer, hence no column chunking and full occupancy.
+// A synthetic row merges its two parents THROUGH the row itself instead of searching:
+//   phase 1  parent a's entries leave a tag (a NaN pattern carrying the entry's offset) at their columns;
+//   phase 2  parent b's entries read their column back: tag -> both parents have it, write T(va + vb);
+//            constant -> only b has it, write T(vb);
+//   phase 3  parent a's entries whose tag is still there are a-only: write T(va).
+// T(v) = log(v / l1 * median + pc) can be finite, +-inf or the canonical NaN, never a tag (exponent all ones,
+// quiet bit clear, non-zero payload), and the fill log(pc) cannot be one either.  __syncwarp() orders the
+// phases (the row belongs to one warp); the read-backs bypass L1 (ld.global.cg).
+// Rows are dealt synthetic-first: they are the long jobs.
+// Cell-block sharding: the launch covers originals [n0, n0 + n_loc) and synthetics [m0, m0 + m_loc) and writes
+// them as local rows [0, n_loc + m_loc).
+constexpr uint32_t kTagBits = 0x7f800000u, kTagMask = 0xffc00000u, kTagPayload = 0x003fffffu;
+__device__ __forceinline__ bool is_tag(uint32_t x) { return (x & kTagMask) == kTagBits && (x & kTagPayload) != 0u; }
+
+__global__ void __launch_bounds__(256) k_dense_rows_l2(const int32_t *__restrict__ indptr,
+                                                       const int32_t *__restrict__ indices,
+                                                       const float *__restrict__ data,
+                                                       const double *__restrict__ l1_rows,
+                                                       const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
+                                                       int64_t m0, int64_t m_loc, int n_genes, int ld, float median,
+                                                       float pc, float *__restrict__ dense) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_rows = n_loc + m_loc;
+    const float logpc = logf(pc);
+    for (int64_t w = warp; w < n_rows; w += n_warps) {
+        const bool synth = w < m_loc;
+        const int64_t row = synth ? n_loc + w : w - m_loc;  // local output row
+        float *out_row = dense + row * (int64_t)ld;
+        int sa, ea, sb = 0, eb = 0;
+        double l1;
+        if (!synth) {
+            const int64_t src = n0 + row;
+            sa = __ldg(indptr + src);
+            ea = __ldg(indptr + src + 1);
+            l1 = __ldg(l1_rows + src);
+        } else {
+            const int64_t r = m0 + w;
+            const int64_t pa = __ldg(parents + 2 * r), pb = __ldg(parents + 2 * r + 1);
+            sa = __ldg(indptr + pa);
+            ea = __ldg(indptr + pa + 1);
+            sb = __ldg(indptr + pb);
+            eb = __ldg(indptr + pb + 1);
+            l1 = __ldg(l1_rows + pa) + __ldg(l1_rows + pb);  // non-negative counts: |a + b| = |a| + |b|, exact
+        }
+        // (1) constant fill, pad columns zero
+        for (int j = 4 * lane; j < ld; j += 128) {
+            float4 v;
+            v.x = j < n_genes ? logpc : 0.f;
+            v.y = j + 1 < n_genes ? logpc : 0.f;
+            v.z = j + 2 < n_genes ? logpc : 0.f;
+            v.w = j + 3 < n_genes ? logpc : 0.f;
+            *reinterpret_cast<float4 *>(out_row + j) = v;
+        }
+        __syncwarp();
+        if (!synth) {
+#pragma unroll 4
+            for (int p = sa + lane; p < ea; p += 32) {
+                const int col = __ldg(indices + p);
+                const float v = __ldg(data + p);
+                if (v != 0.f) out_row[col] = norm_log(v, l1, median, pc);
+            }
+        } else {
+            uint32_t *out_bits = reinterpret_cast<uint32_t *>(out_row);
+#pragma unroll 4
+            for (int p = sa + lane; p < ea; p += 32) out_bits[__ldg(indices + p)] = kTagBits | (uint32_t)(p - sa + 1);
+            __syncwarp();
+#pragma unroll 4
+            for (int p = sb + lane; p < eb; p += 32) {
+                const int col = __ldg(indices + p);
+                float v = __ldg(data + p);
+                const uint32_t x = __ldcg(out_bits + col);
+                if (is_tag(x)) v += __ldg(data + sa + (int)(x & kTagPayload) - 1);
+                out_row[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int p = sa + lane; p < ea; p += 32) {
+                const int col = __ldg(indices + p);
+                const float v = __ldg(data + p);
+                if (is_tag(__ldcg(out_bits + col))) out_row[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+            }
+        }
+        // the next row of this warp touches other addresses: no barrier needed here
+    }
+}
+
 int pick_chunk(int64_t ld) { return (int)std::min<int64_t>(ld, kMaxChunk); }
 
 // The dense build is latency-bound with one 12 KB row buffer per warp (16 warps / SM); staging 1024 columns
@@ -387,7 +481,7 @@ int dd_set_parents(dd_handle *h, int64_t n_synth, const int64_t *parents) {
         h->cap_M = n_synth;
     }
     h->M = n_synth;
-    h->A = h->N + n_synth;
+    dd_set_block(h);  // A = rows of this rank's block (everything unless the handle shards cells)
     h->synth_csr_valid = false; h->dense_valid = false; h->emb_valid = false;
     if (n_synth > 0)
         DD_CUDA(h, cudaMemcpyAsync(h->d_parents, parents, sizeof(int64_t) * 2 * n_synth, cudaMemcpyHostToDevice,
@@ -493,16 +587,30 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
     if (!h->d_indptr || !h->d_parents || h->A == 0) return dd_fail(h, DD_ERR_ARG, "normalise: upload counts and parents first");
     const int64_t need = h->A * h->ld;
     DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, need));
-    const int chunk = pick_dense_chunk(h->ld);
-    const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
-        attr_set = true;
+    // DD_DENSE_V=0 keeps the shared-memory row-buffer kernel (A/B comparison; also used when the merge-through-
+    // the-row trick does not apply: negative values, or rows too long for the tag payload)
+    static const int variant = getenv("DD_DENSE_V") ? atoi(getenv("DD_DENSE_V")) : 1;
+    const bool sharded = dd_sharded(h);
+    if ((variant != 0 && h->nonneg && h->G < (int64_t)kTagPayload) || sharded) {
+        if (!h->nonneg || h->G >= (int64_t)kTagPayload)
+            return dd_fail(h, DD_ERR_UNSUPPORTED, "normalise: cell-block sharding needs non-negative counts");
+        static const int warps_per_sm = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 48;
+        const int grid = h->num_sms * std::max(1, warps_per_sm / 8);
+        DD_LAUNCH(h, "dense_rows", k_dense_rows_l2, grid, 256, 0, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
+                  h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median, pseudocount,
+                  h->d_dense);
+    } else {
+        const int chunk = pick_dense_chunk(h->ld);
+        const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
+            attr_set = true;
+        }
+        const int grid = grid_for(h, smem);
+        DD_LAUNCH(h, "dense_rows", k_dense_rows, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
+                  h->d_parents, h->N, h->M, (int)h->G, (int)h->ld, chunk, median, pseudocount, h->nonneg ? 1 : 0, h->d_dense);
     }
-    const int grid = grid_for(h, smem);
-    DD_LAUNCH(h, "dense_rows", k_dense_rows, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
-              h->d_parents, h->N, h->M, (int)h->G, (int)h->ld, chunk, median, pseudocount, h->nonneg ? 1 : 0, h->d_dense);
     h->dense_valid = true;
     h->emb_valid = false;
     return DD_OK;
@@ -533,6 +641,7 @@ extern "C" int dd_download_dense(dd_handle *h, int64_t row0, int64_t n_rows, flo
 
 extern "C" int dd_upload_dense(dd_handle *h, int64_t n_rows, int64_t n_genes, const float *dense) {
     if (!h || !dense || n_rows <= 0 || n_genes <= 0) return dd_fail(h, DD_ERR_ARG, "dd_upload_dense: bad arguments");
+    if (dd_sharded(h)) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_upload_dense: not available on a cell-sharded handle");
     DD_CUDA(h, cudaSetDevice(h->device));
     if (!h->d_indptr) {  // stand-alone use (tests): no counts uploaded
         h->G = n_genes;
@@ -542,7 +651,7 @@ extern "C" int dd_upload_dense(dd_handle *h, int64_t n_rows, int64_t n_genes, co
     } else if (n_genes != h->G) {
         return dd_fail(h, DD_ERR_ARG, "dd_upload_dense: gene count differs from the uploaded counts");
     }
-    h->A = n_rows;
+    h->A = h->A_glob = n_rows;
     DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, h->A * h->ld));
     DD_CUDA(h, cudaMemsetAsync(h->d_dense, 0, sizeof(float) * h->A * h->ld, h->stream));
     DD_CUDA(h, cudaMemcpy2DAsync(h->d_dense, sizeof(float) * h->ld, dense, sizeof(float) * h->G, sizeof(float) * h->G,

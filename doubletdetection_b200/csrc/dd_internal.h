@@ -11,7 +11,7 @@
 
 #include "../../include/dd_b200.h"
 
-#define DD_ABI_VERSION 1
+#define DD_ABI_VERSION 2
 
 // padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
 static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -56,8 +56,16 @@ struct dd_handle {
     float *d_slib = nullptr;
     bool synth_csr_valid = false;
 
+    // ---- cell-block sharding (comm.cu; config c5).  With world == 1 or sharding off the block is everything.
+    // This rank builds and factorises the dense rows of originals [blk_n0, blk_n0 + blk_n) followed by synthetics
+    // [blk_m0, blk_m0 + blk_m): A = blk_n + blk_m LOCAL rows, A_glob = N + M rows over all ranks.
+    int world = 1, rank = 0;
+    bool shard_cells = false;
+    void *nccl_comm = nullptr;  // ncclComm_t
+    int64_t blk_n0 = 0, blk_n = 0, blk_m0 = 0, blk_m = 0, A_glob = 0;
+
     // ---- dense log-normalised augmented matrix ----
-    int64_t A = 0, ld = 0, cap_dense = 0;  // A rows, leading dimension ld >= G (multiple of 32)
+    int64_t A = 0, ld = 0, cap_dense = 0;  // A (local) rows, leading dimension ld >= G (multiple of 32)
     float *d_dense = nullptr;
     bool dense_valid = false;
     double *d_colsum = nullptr, *d_colsumsq = nullptr;  // G doubles each
@@ -164,6 +172,18 @@ static inline int dd_reserve(dd_handle *h, T **p, int64_t *cap, int64_t need) {
     *cap = need;
     return DD_OK;
 }
+
+// ---- cell-block sharding helpers (comm.cu).  All are no-ops when the handle is not sharded; otherwise they
+// enqueue NCCL collectives on h->stream (every rank must issue the same sequence).
+static inline bool dd_sharded(const dd_handle *h) { return h->shard_cells && h->world > 1; }
+void dd_set_block(dd_handle *h);  // derive blk_* / A / A_glob from N, M, rank, world
+int dd_comm_allreduce_f64(dd_handle *h, double *buf, int64_t count);
+int dd_comm_bcast(dd_handle *h, void *buf, int64_t bytes, int root);
+// "all-gather" of row ranges that already sit at their final place in a replicated buffer: range r of `begin` /
+// `count` (in rows of row_bytes bytes) is owned by rank owner[r] and broadcast from there in one NCCL group
+int dd_comm_gather_ranges(dd_handle *h, void *base, int64_t row_bytes, int n_ranges, const int64_t *begin,
+                          const int64_t *count, const int *owner);
+void dd_comm_destroy(dd_handle *h);
 
 // ---- stage entry points implemented across the .cu files (all asynchronous on h->stream) ----
 int dd_dev_create_doublets_csr(dd_handle *h);                       // csr.cu

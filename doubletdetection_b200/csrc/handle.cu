@@ -124,6 +124,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     for (void *p : bufs)
         if (p) cudaFree(p);
     dd_tc_free(h);
+    dd_comm_destroy(h);
     if (h->lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lv_graph_exec);
     for (int32_t *p : h->slot_knn) cudaFreeHost(p);
     for (double *p : h->slot_flag) cudaFreeHost(p);

@@ -13,6 +13,8 @@
 // float64 distances (order: distance, then index).
 #include "dd_internal.h"
 
+#include <vector>
+
 #include <cuda_bf16.h>
 
 #include <cfloat>
@@ -239,10 +241,10 @@ __global__ void __launch_bounds__(256) k_knn_scan(const float *__restrict__ emb,
 
 // Exact float64 re-ranking of the TL candidates of every query; writes self + (k-1) neighbours.
 template <int KP, int TL>
-__global__ void k_knn_refine(const float *__restrict__ emb, const int *__restrict__ cand_i, int64_t n, int k,
+__global__ void k_knn_refine(const float *__restrict__ emb, const int *__restrict__ cand_i, int64_t q0, int64_t n, int k,
                              int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
     const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t q = q0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // queries [q0, n)
     if (q >= n) return;
     int ci = lane < TL ? cand_i[q * TL + lane] : 0x7fffffff;
     double d = INFINITY;
@@ -307,7 +309,9 @@ constexpr int NS = 4;                          // candidate stages
 constexpr int KSTEPS = KC / 2;                 // 7 MMAs of K = 16
 constexpr int TLc = 16;
 constexpr float kEmptyT = -1e29f;              // list filler; padded candidates score -1e30 and never pass
-constexpr size_t SMEM_BYTES = (size_t)(QT + NS) * TILE_BYTES + 1024;
+constexpr int PEND = 16;                       // pending (not yet inserted) survivors per query row
+constexpr size_t PEND_BYTES = (size_t)PEND * 256 * 8;
+constexpr size_t SMEM_BYTES = (size_t)(QT + NS) * TILE_BYTES + 1024 + PEND_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -463,7 +467,7 @@ __device__ __forceinline__ void reglist_insert(RegList &L, float t, int idx) {
 }
 
 __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb,
-                                                    int64_t n, int n_tiles, int *__restrict__ cand_i) {
+                                                    int64_t n, int n_tiles, int pair0, int *__restrict__ cand_i) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                // QT tiles
     uint8_t *sB = smem + (size_t)QT * TILE_BYTES;      // NS stages
@@ -474,9 +478,11 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
     uint64_t *tfull = empty + NS;       // 2
     uint64_t *tempty = tfull + 2;       // 2
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float *pend_t = reinterpret_cast<float *>(smem + (size_t)(QT + NS) * TILE_BYTES + 1024);
+    int *pend_i = reinterpret_cast<int *>(pend_t + PEND * 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile0 = blockIdx.x * QT;
+    const int tile0 = (blockIdx.x + pair0) * QT;  // pair0: first query-tile pair of this launch (cell-block sharding)
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -550,6 +556,21 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
         }
         float tau = active ? kEmptyT : INFINITY;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * 128;
+        // pending survivors of this row: PEND slots in shared memory, slot-major (conflict-free: the bank only
+        // depends on the thread), merged into the sorted register list by the whole warp together
+        const int ptid = threadIdx.x - 64;
+        int cnt = 0;
+        auto merge_pending = [&]() {
+            const int mx = __reduce_max_sync(0xffffffffu, cnt);
+            for (int s = 0; s < mx; s++) {
+                const bool have = s < cnt;
+                const float t = have ? pend_t[s * 256 + ptid] : -INFINITY;
+                const int ci = have ? pend_i[s * 256 + ptid] : 0x7fffffff;
+                reglist_insert(L, t, ci);  // arrival order is kept, so ties resolve as in a streaming insertion
+            }
+            cnt = 0;
+            tau = active ? L.t[TLc - 1] : INFINITY;
+        };
         for (int step = 0; step < n_tiles; step++) {
             const int buf = step & 1;
             const uint32_t bph = (step >> 1) & 1;
@@ -565,27 +586,28 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
                 for (int i = 0; i < 8; i++)
                     m8[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                                   fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
-                float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
-                                fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-                // rare: some value of this row beats its TL-th best.  Peel maxima until none does.
-                while (m > tau) {
-                    int pos = 0;
-                    bool done = false;
+                const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                      fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                // rare (after the first few tiles): some row of this warp sees a value above its threshold.
+                // Survivors are only APPENDED to the row's pending slots here (a few predicated stores); the
+                // sorted insertion runs for all 32 rows of the warp at once when some row runs out of slots.
+                if (__any_sync(0xffffffffu, m > tau)) {
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {  // peel the FIRST column holding the maximum
-                        const bool hit = !done && __uint_as_float(v[i]) == m;
-                        pos = hit ? i : pos;
-                        v[i] = hit ? 0xff800000u : v[i];  // -inf
-                        done = done || hit;
-                    }
-                    const int cidx = step * TILE + c + pos;
-                    if ((int64_t)cidx != qrow) {
-                        reglist_insert(L, m, cidx);
-                        tau = L.t[TLc - 1];
-                    }
-                    m = __uint_as_float(v[0]);
+                    for (int i = 0; i < 8; i++) {
+                        if (__any_sync(0xffffffffu, m8[i] > tau)) {
+                            if (__any_sync(0xffffffffu, cnt > PEND - 4)) merge_pending();
 #pragma unroll
-                    for (int i = 1; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
+                            for (int j = 0; j < 4; j++) {
+                                const float x = __uint_as_float(v[4 * i + j]);
+                                const int cidx = step * TILE + c + 4 * i + j;
+                                if (x > tau && (int64_t)cidx != qrow) {
+                                    pend_t[cnt * 256 + ptid] = x;
+                                    pend_i[cnt * 256 + ptid] = cidx;
+                                    cnt++;
+                                }
+                            }
+                        }
+                    }
                 }
             };
             tmem_ld32(col0, va);
@@ -603,6 +625,7 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
             fence_before();
             mbar_arrive(tempty + buf);
         }
+        merge_pending();
         if (active) {
 #pragma unroll
             for (int l = 0; l < TLc; l++) cand_i[qrow * TLc + l] = L.i[l];
@@ -630,7 +653,7 @@ int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     DD_LAUNCH(h, "knn_norms", k_row_norms<KP>, (unsigned)((n + 255) / 256), 256, 0, h->d_emb, n, norms);
     DD_LAUNCH(h, "knn_scan", (k_knn_scan<KP, TL>), (unsigned)((n + BQ - 1) / BQ), 256, sizeof(S), h->d_emb, norms, n,
               cand_d, cand_i);
-    DD_LAUNCH(h, "knn_refine", (k_knn_refine<KP, TL>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, n, k,
+    DD_LAUNCH(h, "knn_refine", (k_knn_refine<KP, TL>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, (int64_t)0, n, k,
               h->d_knn_idx, h->d_knn_dist);
     return DD_OK;
 }
@@ -650,9 +673,29 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
     }
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
               reinterpret_cast<uint4 *>(qa), reinterpret_cast<uint4 *>(cb));
-    DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(n_tiles_pad / tc::QT), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, cand_i);
-    DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, n, k,
-              h->d_knn_idx, h->d_knn_dist);
+    // Cell-block sharding: every rank holds the whole (all-gathered) embedding and answers the queries of its
+    // share of the 256-row query blocks against ALL candidates; the lists are then all-gathered.
+    const int n_pairs = n_tiles_pad / tc::QT;
+    const int W = dd_sharded(h) ? h->world : 1, R = dd_sharded(h) ? h->rank : 0;
+    const int pair0 = (int)((int64_t)n_pairs * R / W), pair1 = (int)((int64_t)n_pairs * (R + 1) / W);
+    const int64_t q0 = std::min<int64_t>(n, (int64_t)pair0 * tc::QT * tc::TILE);
+    const int64_t q1 = std::min<int64_t>(n, (int64_t)pair1 * tc::QT * tc::TILE);
+    if (pair1 > pair0) {
+        DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(pair1 - pair0), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, cand_i);
+        DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1, k,
+                  h->d_knn_idx, h->d_knn_dist);
+    }
+    if (W > 1) {
+        std::vector<int64_t> begin(W), count(W);
+        std::vector<int> owner(W);
+        for (int r = 0; r < W; r++) {
+            const int64_t b = std::min<int64_t>(n, (int64_t)n_pairs * r / W * tc::QT * tc::TILE);
+            const int64_t e = std::min<int64_t>(n, (int64_t)n_pairs * (r + 1) / W * tc::QT * tc::TILE);
+            begin[r] = b; count[r] = e - b; owner[r] = r;
+        }
+        DD_TRY(dd_comm_gather_ranges(h, h->d_knn_idx, (int64_t)sizeof(int32_t) * k, W, begin.data(), count.data(), owner.data()));
+        DD_TRY(dd_comm_gather_ranges(h, h->d_knn_dist, (int64_t)sizeof(float) * k, W, begin.data(), count.data(), owner.data()));
+    }
     return DD_OK;
 }
 
@@ -682,6 +725,7 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     // default: tcgen05 distance GEMM; DD_KNN_FFMA=1 keeps the CUDA-core kernel (A/B comparison, KP=64, k>13)
     static const bool force_ffma = getenv("DD_KNN_FFMA") != nullptr;
     if (h->KP == 32 && TL == 16 && !force_ffma) return run_knn_tc(h, k, cand_d, cand_i);
+    if (dd_sharded(h)) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: cell-block sharding needs the tcgen05 path (k <= 13, <= 32 components)");
     if (h->KP == 32)
         return TL == 16 ? run_knn<32, 16>(h, k, norms, cand_d, cand_i) : run_knn<32, 32>(h, k, norms, cand_d, cand_i);
     return TL == 16 ? run_knn<64, 16>(h, k, norms, cand_d, cand_i) : run_knn<64, 32>(h, k, norms, cand_d, cand_i);

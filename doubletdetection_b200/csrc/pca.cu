@@ -587,8 +587,10 @@ int run_pca(dd_handle *h, int n_power_iter) {
     rows_per_split = std::max(G2_BK, (rows_per_split + G2_BK - 1) / G2_BK * G2_BK);
     splits = (int)((A + rows_per_split - 1) / rows_per_split);
     const int tall_grid = h->num_sms * 2;
-    const double inv_A = 1.0 / (double)A;
+    const double inv_A = 1.0 / (double)h->A_glob;  // A = this rank's rows, A_glob = rows over all ranks
     const bool use_tc = LP == 40 && dd_tc_pca_enabled();
+    if (dd_sharded(h) && !use_tc)
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: cell-block sharding needs the tcgen05 path (n_components + 10 <= 40)");
     if (use_tc) {
         DD_TRY(dd_tc_prepare(h));
         const int64_t q_bytes = (int64_t)(ld / 32) * 12288, y_bytes = ((A + 31) / 32) * 12288;
@@ -615,6 +617,9 @@ int run_pca(dd_handle *h, int n_power_iter) {
         // orthonormalised every iteration, the tall side once, for the final projection.
         DD_TRY(dd_reserve(h, &h->d_mu, &h->cap_mu, (int64_t)ld));
         DD_LAUNCH(h, "mu", k_mu, (ld + 255) / 256, 256, 0, h->d_colsum, (int)h->G, ld, inv_A, h->d_mu);
+        // Cell-block sharding: every sum over cells is all-reduced (column sums above, D^T Y and the Gram matrix of
+        // the tall panel here); the L x L factorisations are replicated and rank 0's result is broadcast, so that
+        // every rank multiplies by bit-identical small matrices.
         for (int it = 0; it <= n_power_iter; it++) {
             const bool last = it == n_power_iter;
             DD_TRY(dd_tc_gemm_dq(h, /*write_y=*/last, /*write_tiles=*/!last));
@@ -623,18 +628,23 @@ int run_pca(dd_handle *h, int n_power_iter) {
                 DD_CUDA(h, cudaMemsetAsync(sm + OFF_CSUM, 0, sizeof(double) * 2 * kMaxLP, h->stream));
                 DD_LAUNCH(h, "gram_tall", (k_gram<LP, 0>), tall_grid, 256, 0, h->d_Y, nullptr, A, nullptr, 0.0, nullptr,
                           sm + OFF_GRAM, sm + OFF_CSUM);
-                DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)A, 1, L, LP, sm + OFF_RINV,
-                          sm + OFF_FLAG);
+                DD_TRY(dd_comm_allreduce_f64(h, sm + OFF_GRAM, kMaxLP * kMaxLP));
+                DD_TRY(dd_comm_allreduce_f64(h, sm + OFF_CSUM, kMaxLP));
+                DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, sm + OFF_CSUM, (double)h->A_glob, 1, L, LP,
+                          sm + OFF_RINV, sm + OFF_FLAG);
+                DD_TRY(dd_comm_bcast(h, sm + OFF_RINV, sizeof(double) * kMaxLP * kMaxLP, 0));
                 DD_LAUNCH(h, "apply_tall", (k_apply<LP, 0>), tall_grid, 128, 0, h->d_Y, nullptr, A, L, sm + OFF_RINV,
                           sm + OFF_CSUM, inv_A, sm + OFF_SSUM, nullptr, 0, h->d_yb);
                 DD_CUDA(h, cudaMemsetAsync(sm + OFF_SSUM, 0, sizeof(double) * kMaxLP, h->stream));  // no mu (x) s term
             }
             DD_TRY(dd_tc_gemm_dty(h));
+            DD_TRY(dd_comm_allreduce_f64(h, h->d_Zacc, (int64_t)ld * LP));
             DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
             DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
                       h->d_Zacc, (int64_t)ld, h->d_colsum, inv_A, sm + OFF_SSUM, sm + OFF_GRAM, sm + OFF_EVAL /*unused sums*/);
             if (!last) {
                 DD_LAUNCH(h, "chol", k_chol, 1, 512, 0, sm + OFF_GRAM, nullptr, 1.0, 0, L, LP, sm + OFF_RINV, sm + OFF_FLAG);
+                DD_TRY(dd_comm_bcast(h, sm + OFF_RINV, sizeof(double) * kMaxLP * kMaxLP, 0));
                 DD_LAUNCH(h, "apply_small", (k_apply<LP, 1>), (ld + 127) / 128, 128, 0, nullptr, h->d_Zacc, (int64_t)ld, L,
                           sm + OFF_RINV, nullptr, 0.0, nullptr, h->d_Qt, ld, h->d_qb);
             }
@@ -671,13 +681,37 @@ int run_pca(dd_handle *h, int n_power_iter) {
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm + OFF_KEYS);
     DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, h->d_Zacc, (const float *)nullptr, 0,
               (int)h->G, L, C, sm + OFF_EVEC, keys);
-    const int egrid = (int)((A + 127) / 128);
-    if (KP == 32)
-        DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
-                  h->d_emb, sm + OFF_CSUM, 1);
-    else
-        DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, h->d_Y, A, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys,
-                  h->d_emb, sm + OFF_CSUM, 1);
+    // eigenvectors, eigenvalues, flag and sign keys: rank 0's copy everywhere (no-op when not sharded)
+    DD_TRY(dd_comm_bcast(h, sm + OFF_EVEC, sizeof(double) * (SMALL_DOUBLES - OFF_EVEC), 0));
+    // the embedding rows go straight to their place in the global (originals, then synthetics) order
+    const int64_t part_rows[2] = {h->blk_n, h->blk_m};
+    const int64_t part_src[2] = {0, h->blk_n};
+    const int64_t part_dst[2] = {h->blk_n0, h->N + h->blk_m0};
+    for (int part = 0; part < 2; part++) {
+        const int64_t rows = part_rows[part];
+        if (rows <= 0) continue;
+        const int egrid = (int)((rows + 127) / 128);
+        const float *yq = h->d_Y + part_src[part] * LP;
+        float *emb = h->d_emb + part_dst[part] * KP;
+        if (KP == 32)
+            DD_LAUNCH(h, "embed", (k_embed<LP, 32>), egrid, 128, 0, yq, rows, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys, emb,
+                      sm + OFF_CSUM, 1);
+        else
+            DD_LAUNCH(h, "embed", (k_embed<LP, 64>), egrid, 128, 0, yq, rows, L, C, sm + OFF_EVEC, sm + OFF_EVAL, keys, emb,
+                      sm + OFF_CSUM, 1);
+    }
+    if (dd_sharded(h)) {  // all-gather of the low-dimensional embedding (the one data-path exchange kNN needs)
+        std::vector<int64_t> begin, count;
+        std::vector<int> owner;
+        for (int r = 0; r < h->world; r++) {
+            const int64_t n0 = h->N * r / h->world, n1 = h->N * (r + 1) / h->world;
+            const int64_t m0 = h->M * r / h->world, m1 = h->M * (r + 1) / h->world;
+            begin.push_back(n0); count.push_back(n1 - n0); owner.push_back(r);
+            begin.push_back(h->N + m0); count.push_back(m1 - m0); owner.push_back(r);
+        }
+        DD_TRY(dd_comm_gather_ranges(h, h->d_emb, (int64_t)sizeof(float) * KP, (int)begin.size(), begin.data(),
+                                     count.data(), owner.data()));
+    }
     return DD_OK;
 }
 
@@ -748,9 +782,11 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
     if (n_comp < 1 || n_random < n_comp || n_power_iter < 0) return dd_fail(h, DD_ERR_ARG, "pca: bad n_comp / n_random / n_power_iter");
     if (n_random > kMaxLP) return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 > 64 is outside the B200 hot path");
     if (h->G > 0xFFFFF) return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: more than 2^20 - 1 genes");
-    if (n_random > h->G || n_random > h->A)
+    if (n_random > h->G || n_random > h->A_glob)
         return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: n_components + 10 exceeds the matrix dimensions");
-    const bool transposed = h->A < h->G;  // sklearn works on the transposed problem: Omega is A x n_random
+    const bool transposed = h->A_glob < h->G;  // sklearn works on the transposed problem: Omega is A x n_random
+    if (transposed && dd_sharded(h))
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "pca: cell-block sharding with fewer augmented cells than genes");
     if (transposed && (n_random > 40 || !dd_tc_pca_enabled()))
         return dd_fail(h, DD_ERR_UNSUPPORTED,
                        "pca: fewer augmented cells than genes needs the tcgen05 path (n_components + 10 <= 40)");
@@ -796,17 +832,17 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
     h->L = n_random; h->LP = LP; h->C = n_comp;
     if (!transposed)
         DD_CUDA(h, cudaMemcpyAsync(h->d_Qt, omega_dev, sizeof(float) * LP * ld, cudaMemcpyDeviceToDevice, h->stream));
-    if (h->KP != KP || A > h->cap_emb) {
+    if (h->KP != KP || h->A_glob > h->cap_emb) {  // the embedding is global: every rank holds all A_glob rows
         if (h->d_emb) cudaFree(h->d_emb);
         h->d_emb = nullptr; h->cap_emb = 0;
-        DD_CUDA(h, cudaMalloc(&h->d_emb, sizeof(float) * A * KP));
-        h->cap_emb = A;
+        DD_CUDA(h, cudaMalloc(&h->d_emb, sizeof(float) * h->A_glob * KP));
+        h->cap_emb = h->A_glob;
     }
     h->KP = KP;
     int rc = transposed ? run_pca_transposed(h, n_power_iter)
                         : ((LP == 40) ? run_pca<40>(h, n_power_iter) : run_pca<64>(h, n_power_iter));
     if (rc != DD_OK) return rc;
-    h->emb_rows = A;
+    h->emb_rows = h->A_glob;
     h->emb_valid = true;
     return DD_OK;
 }
@@ -840,7 +876,7 @@ extern "C" int dd_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_
     DD_TRY(dd_pca_check(h));
     if (emb_out)
         DD_CUDA(h, cudaMemcpy2DAsync(emb_out, sizeof(float) * n_comp, h->d_emb, sizeof(float) * h->KP,
-                                     sizeof(float) * n_comp, h->A, cudaMemcpyDeviceToHost, h->stream));
+                                     sizeof(float) * n_comp, h->emb_rows, cudaMemcpyDeviceToHost, h->stream));
     if (singular_values_out)
         DD_CUDA(h, cudaMemcpyAsync(singular_values_out, h->d_small + OFF_CSUM, sizeof(double) * n_comp,
                                    cudaMemcpyDeviceToHost, h->stream));

@@ -52,13 +52,13 @@ __global__ void k_colstats(const float *__restrict__ dense, int64_t n_rows, int 
     }
 }
 
-__global__ void k_scale_apply(float *__restrict__ dense, int64_t n_rows, int n_genes, int ld,
+__global__ void k_scale_apply(float *__restrict__ dense, int64_t n_rows, int64_t n_total, int n_genes, int ld,
                               const double *__restrict__ colsum, const double *__restrict__ colsumsq,
                               float max_value) {
     const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (col >= ld) return;
     double mean[4], sd[4];
-    const double n = (double)n_rows;
+    const double n = (double)n_total;  // rows over all ranks (the statistics are all-reduced), n_rows are local
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int c = col + i;
@@ -115,14 +115,17 @@ int dd_dev_colstats(dd_handle *h, bool with_sq) {
         DD_LAUNCH(h, "colstats_sq", k_colstats<true>, grid, block, 0, h->d_dense, h->A, (int)h->ld, h->d_colsum, h->d_colsumsq);
     else
         DD_LAUNCH(h, "colstats", k_colstats<false>, grid, block, 0, h->d_dense, h->A, (int)h->ld, h->d_colsum, h->d_colsumsq);
+    // cell-block sharding: sums over the cells of all ranks
+    DD_TRY(dd_comm_allreduce_f64(h, h->d_colsum, h->ld));
+    if (with_sq) DD_TRY(dd_comm_allreduce_f64(h, h->d_colsumsq, h->ld));
     return DD_OK;
 }
 
 int dd_dev_standard_scale(dd_handle *h, float max_value) {
-    if (h->A < 2) return dd_fail(h, DD_ERR_ARG, "standard scaling needs at least two rows");
+    if (h->A_glob < 2) return dd_fail(h, DD_ERR_ARG, "standard scaling needs at least two rows");
     DD_TRY(dd_dev_colstats(h, true));
     dim3 grid((unsigned)((h->ld / 4 + 63) / 64), (unsigned)((h->A + kRowsPerCta - 1) / kRowsPerCta));
-    DD_LAUNCH(h, "scale_apply", k_scale_apply, grid, 64, 0, h->d_dense, h->A, (int)h->G, (int)h->ld, h->d_colsum,
+    DD_LAUNCH(h, "scale_apply", k_scale_apply, grid, 64, 0, h->d_dense, h->A, h->A_glob, (int)h->G, (int)h->ld, h->d_colsum,
               h->d_colsumsq, max_value);
     h->emb_valid = false;
     return DD_OK;

@@ -153,6 +153,30 @@ int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int64_t *paren
                       double *scores_out, double *log_p_out, int32_t *communities_out,
                       int32_t *synth_communities_out, double *stage_ms_out);
 
+/* ---- cell-block sharding of one fit across the GPUs of a box (SURVEY 8e level 2; BASELINE config 5) ------
+ * The reference has no multi-GPU path; this is the partition doubletdetection.py:292-336 admits: the rows of
+ * the augmented matrix (vstack of originals and synthetics, :292) are dealt to `world` ranks, one process and
+ * one handle per GPU.  Every rank uploads the SAME counts and passes the SAME parents / omega; it builds and
+ * factorises only its block of rows.  Sums over cells (column means, D^T Y, the Gram matrix of the tall panel)
+ * are NCCL all-reduces, the n_comp-dimensional embedding is all-gathered (the single exchange kNN needs), each
+ * rank answers the kNN queries of its share of rows against all cells and the lists are all-gathered; the
+ * clustering + scoring of an iteration then runs replicated, so every rank returns the full result arrays.
+ * NCCL is resolved at run time from the process (libnccl.so.2; env DD_NCCL_LIB overrides the path).
+ *   dd_comm_unique_id   rank 0 creates the rendezvous token (DD_COMM_ID_BYTES bytes) and ships it to the
+ *                       other ranks by any host channel (the Python shim uses torch.distributed.broadcast)
+ *   dd_comm_init        collective: all ranks call it with the same token
+ *   dd_comm_shard_cells 1 = shard cells across the communicator from the next dd_create_doublets /
+ *                       dd_fit_iterations on; 0 = every rank works on the whole matrix again
+ *   dd_comm_info        rank, world and this rank's block {first original, n originals, first synthetic,
+ *                       n synthetics} (int64[4]) for the parents set last
+ * On a sharded handle dd_download_dense addresses the LOCAL rows (originals of the block, then its
+ * synthetics); dd_pca / dd_knn return the global embedding / lists on every rank. */
+#define DD_COMM_ID_BYTES 128
+int dd_comm_unique_id(void *id_out, int64_t id_bytes);
+int dd_comm_init(dd_handle *h, int32_t rank, int32_t world, const void *id, int64_t id_bytes);
+int dd_comm_shard_cells(dd_handle *h, int32_t on);
+int dd_comm_info(const dd_handle *h, int32_t *rank_out, int32_t *world_out, int64_t *block_out);
+
 /* ---- introspection used by bench.py -------------------------------------------------------
  * Number of kernels this library has launched on the handle since creation. */
 int64_t dd_kernel_launches(const dd_handle *h);

@@ -10,8 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from doubletdetection_b200 import iteration_shard
-from doubletdetection_b200.classifier import _allgather_iterations
+from doubletdetection_b200 import _capi, iteration_shard
+from doubletdetection_b200.classifier import _allgather_iterations, broadcast_token
 
 
 def _free_port():
@@ -66,3 +66,43 @@ def test_iteration_sharding_gloo_world2():
         for p in procs:
             p.join(timeout=30)
         assert sorted(results) == [(0, True), (1, True)]
+
+
+def _token_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank 0 creates the NCCL rendezvous token of the cell-sharding communicator (host-only call) and ships it
+        # over the existing process group; every rank must end up with the same 128 bytes
+        token = _capi.comm_unique_id() if rank == 0 else None
+        got = broadcast_token(dist, token, device=0)
+        q.put((rank, got))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_cell_sharding_token_broadcast_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_token_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert len(results[0]) == _capi.COMM_ID_BYTES and results[0] == results[1]
+    assert any(results[0])  # a real token, not the zero padding
+
+
+def test_cell_blocks_partition_rows():
+    # the rule shared by the library (dd_set_block) and the host: contiguous, disjoint, covering
+    for n, world in ((100000, 8), (25000, 8), (7, 3), (5, 8), (1000000, 8)):
+        blocks = [_capi.block_of(n, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
+        sizes = [e - b for b, e in blocks]
+        assert max(sizes) - min(sizes) <= 1
