@@ -305,12 +305,13 @@ constexpr int TILE = 128;                      // rows per operand tile
 constexpr int TILE_BYTES = TILE * KC * 16;     // 28672
 constexpr int LBO = 128, SBO = KC * 128;       // bytes
 constexpr int QT = 2;                          // query tiles per CTA
-constexpr int NS = 4;                          // candidate stages
+constexpr int NS = 3;                          // candidate stages
 constexpr int KSTEPS = KC / 2;                 // 7 MMAs of K = 16
 constexpr int TLc = 16;
 constexpr float kEmptyT = -1e29f;              // list filler; padded candidates score -1e30 and never pass
-constexpr int PEND = 16;                       // pending (not yet inserted) survivors per query row
-constexpr size_t PEND_BYTES = (size_t)PEND * 256 * 8;
+constexpr int PEND = 40;                       // pending (not yet inserted) survivors per query row (>= 32 + slack)
+constexpr int PEND_SOFT = 8;                   // merge between steps once some row holds more than this many
+constexpr size_t PEND_BYTES = (size_t)(PEND + 1) * 256 * 8;  // + one spare slot that absorbs the misses
 constexpr size_t SMEM_BYTES = (size_t)(QT + NS) * TILE_BYTES + 1024 + PEND_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -454,18 +455,23 @@ struct RegList {
     int i[TLc];
 };
 __device__ __forceinline__ void reglist_insert(RegList &L, float t, int idx) {
+    // position-parallel form of the compare-and-swap chain: slot l takes its upper neighbour if the new score
+    // beats that neighbour (everything from the insertion point on shifts down), the new entry if it beats only
+    // slot l itself.  All 16 slots are independent, so the latency is one compare + two selects instead of a
+    // 16-long dependent chain (the epilogue warps are latency-bound: two warps per scheduler).
+    bool gt[TLc];
 #pragma unroll
-    for (int l = 0; l < TLc; l++) {
-        const bool gt = t > L.t[l];  // strict: an equal score keeps the earlier (smaller) index in front
-        const float nt = gt ? L.t[l] : t;
-        const int ni = gt ? L.i[l] : idx;
-        L.t[l] = gt ? t : L.t[l];
-        L.i[l] = gt ? idx : L.i[l];
-        t = nt;
-        idx = ni;
+    for (int l = 0; l < TLc; l++) gt[l] = t > L.t[l];  // strict: an equal score keeps the earlier entry in front
+#pragma unroll
+    for (int l = TLc - 1; l >= 1; l--) {
+        L.t[l] = gt[l - 1] ? L.t[l - 1] : (gt[l] ? t : L.t[l]);
+        L.i[l] = gt[l - 1] ? L.i[l - 1] : (gt[l] ? idx : L.i[l]);
     }
+    L.t[0] = gt[0] ? t : L.t[0];
+    L.i[0] = gt[0] ? idx : L.i[0];
 }
 
+template <int EPI>  // 0: peel maxima and insert at once; 1: append survivors to pending slots, merge in batches
 __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb,
                                                     int64_t n, int n_tiles, int pair0, int *__restrict__ cand_i) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -479,7 +485,7 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
     uint64_t *tempty = tfull + 2;       // 2
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
     float *pend_t = reinterpret_cast<float *>(smem + (size_t)(QT + NS) * TILE_BYTES + 1024);
-    int *pend_i = reinterpret_cast<int *>(pend_t + PEND * 256);
+    int *pend_i = reinterpret_cast<int *>(pend_t + (PEND + 1) * 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile0 = (blockIdx.x + pair0) * QT;  // pair0: first query-tile pair of this launch (cell-block sharding)
@@ -560,14 +566,11 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
         // depends on the thread), merged into the sorted register list by the whole warp together
         const int ptid = threadIdx.x - 64;
         int cnt = 0;
+        // per-row code (no warp collectives): callable from divergent code; when the whole warp calls it between two
+        // steps all 32 rows insert their pending survivors together
         auto merge_pending = [&]() {
-            const int mx = __reduce_max_sync(0xffffffffu, cnt);
-            for (int s = 0; s < mx; s++) {
-                const bool have = s < cnt;
-                const float t = have ? pend_t[s * 256 + ptid] : -INFINITY;
-                const int ci = have ? pend_i[s * 256 + ptid] : 0x7fffffff;
-                reglist_insert(L, t, ci);  // arrival order is kept, so ties resolve as in a streaming insertion
-            }
+            for (int s = 0; s < cnt; s++)
+                reglist_insert(L, pend_t[s * 256 + ptid], pend_i[s * 256 + ptid]);  // arrival order: ties as when streaming
             cnt = 0;
             tau = active ? L.t[TLc - 1] : INFINITY;
         };
@@ -588,22 +591,47 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
                                   fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
                 const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
                                       fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-                // rare (after the first few tiles): some row of this warp sees a value above its threshold.
-                // Survivors are only APPENDED to the row's pending slots here (a few predicated stores); the
-                // sorted insertion runs for all 32 rows of the warp at once when some row runs out of slots.
-                if (__any_sync(0xffffffffu, m > tau)) {
+                if constexpr (EPI == 0) {
+                    float mm = m;
+                    // rare: some value of this row beats its TL-th best.  Peel maxima until none does.
+                    while (mm > tau) {
+                        int pos = 0;
+                        bool done = false;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        if (__any_sync(0xffffffffu, m8[i] > tau)) {
-                            if (__any_sync(0xffffffffu, cnt > PEND - 4)) merge_pending();
+                        for (int i = 0; i < 32; i++) {  // peel the FIRST column holding the maximum
+                            const bool hit = !done && __uint_as_float(v[i]) == mm;
+                            pos = hit ? i : pos;
+                            v[i] = hit ? 0xff800000u : v[i];  // -inf
+                            done = done || hit;
+                        }
+                        const int cidx = step * TILE + c + pos;
+                        if ((int64_t)cidx != qrow) {
+                            reglist_insert(L, mm, cidx);
+                            tau = L.t[TLc - 1];
+                        }
+                        mm = __uint_as_float(v[0]);
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const float x = __uint_as_float(v[4 * i + j]);
-                                const int cidx = step * TILE + c + 4 * i + j;
-                                if (x > tau && (int64_t)cidx != qrow) {
-                                    pend_t[cnt * 256 + ptid] = x;
-                                    pend_i[cnt * 256 + ptid] = cidx;
-                                    cnt++;
+                        for (int i = 1; i < 32; i++) mm = fmaxf(mm, __uint_as_float(v[i]));
+                    }
+                } else {
+                    // Survivors are only APPENDED to the row's pending slots here (two stores each); the sorted
+                    // insertions run between steps for all rows of the warp together.  Same lean test as EPI 0 on the
+                    // common path; only rows that see a survivor enter.
+                    if (m > tau) {
+                        if (cnt > PEND - 32) merge_pending();  // rare: make room for a whole group
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (m8[i] > tau) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const float x = __uint_as_float(v[4 * i + j]);
+                                    const int cidx = step * TILE + c + 4 * i + j;
+                                    // branch-free append: a miss writes to the spare slot PEND
+                                    const bool hit = x > tau && (int64_t)cidx != qrow;
+                                    const int slot = hit ? cnt : PEND;
+                                    pend_t[slot * 256 + ptid] = x;
+                                    pend_i[slot * 256 + ptid] = cidx;
+                                    cnt += hit ? 1 : 0;
                                 }
                             }
                         }
@@ -624,8 +652,13 @@ __global__ void __launch_bounds__(320, 1) k_knn_tc(const uint8_t *__restrict__ q
             scan(vb, 96);
             fence_before();
             mbar_arrive(tempty + buf);
+            // the sorted insertions run AFTER the accumulator buffer is handed back: the variable part of a row's
+            // work no longer sits between two tensor-core steps (only a row about to run out of slots merges inside)
+            if constexpr (EPI != 0) {
+                if (__any_sync(0xffffffffu, cnt > PEND_SOFT)) merge_pending();
+            }
         }
-        merge_pending();
+        if constexpr (EPI != 0) merge_pending();
         if (active) {
 #pragma unroll
             for (int l = 0; l < TLc; l++) cand_i[qrow * TLc + l] = L.i[l];
@@ -668,7 +701,8 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
     uint8_t *qa = h->d_knn_ops, *cb = h->d_knn_ops + op_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tc::k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         attr_set = true;
     }
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
@@ -681,7 +715,11 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
     const int64_t q0 = std::min<int64_t>(n, (int64_t)pair0 * tc::QT * tc::TILE);
     const int64_t q1 = std::min<int64_t>(n, (int64_t)pair1 * tc::QT * tc::TILE);
     if (pair1 > pair0) {
-        DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(pair1 - pair0), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, cand_i);
+        static const int epi = getenv("DD_KNN_EPI") ? atoi(getenv("DD_KNN_EPI")) : 0;
+        if (epi == 0)
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<0>, (unsigned)(pair1 - pair0), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, cand_i);
+        else
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<1>, (unsigned)(pair1 - pair0), 320, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, cand_i);
         DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1, k,
                   h->d_knn_idx, h->d_knn_dist);
     }

@@ -684,9 +684,10 @@ int run_pca(dd_handle *h, int n_power_iter) {
     // eigenvectors, eigenvalues, flag and sign keys: rank 0's copy everywhere (no-op when not sharded)
     DD_TRY(dd_comm_bcast(h, sm + OFF_EVEC, sizeof(double) * (SMALL_DOUBLES - OFF_EVEC), 0));
     // the embedding rows go straight to their place in the global (originals, then synthetics) order
-    const int64_t part_rows[2] = {h->blk_n, h->blk_m};
+    const bool sh = dd_sharded(h);  // unsharded: one part, local row == global row
+    const int64_t part_rows[2] = {sh ? h->blk_n : A, sh ? h->blk_m : 0};
     const int64_t part_src[2] = {0, h->blk_n};
-    const int64_t part_dst[2] = {h->blk_n0, h->N + h->blk_m0};
+    const int64_t part_dst[2] = {sh ? h->blk_n0 : 0, h->N + h->blk_m0};
     for (int part = 0; part < 2; part++) {
         const int64_t rows = part_rows[part];
         if (rows <= 0) continue;
