@@ -40,6 +40,8 @@ WORKLOADS = {  # BASELINE.json configs
     "c1": dict(n_cells=500, n_genes=100, kind="poisson", desc="500 cells x 100 genes Poisson(1)"),
     "c2": dict(n_cells=10000, n_genes=3000, kind="structured", desc="10k cells x 3k HVG synthetic"),
     "c3": dict(n_cells=100000, n_genes=3000, kind="structured", desc="100k cells x 3k HVG synthetic"),
+    # config 5: only with --shard cells under torchrun (every rank generates a share of the rows, then all-gathers)
+    "c5": dict(n_cells=1000000, n_genes=2000, kind="structured", desc="1M cells x 2k HVG synthetic"),
 }
 N_ITERS = 25
 BOOST_RATE = 0.25
@@ -66,6 +68,49 @@ def make_counts(wl):
         e = min(s + 20000, n)
         blocks.append(sp_sparse.csr_matrix(rs.poisson(prof[types[s:e]] * depth[s:e, None]).astype(np.float32)))
     x = sp_sparse.vstack(blocks).tocsr()
+    x.sort_indices()
+    return x
+
+
+def make_counts_sharded(wl, rank, world, dist, device):
+    """The structured counts of make_counts with one seed per 20000-row block, so that rank r can draw blocks
+    r, r + world, ... and the ranks exchange them (broadcast per block): generation time / world."""
+    import torch
+
+    n, g = wl["n_cells"], wl["n_genes"]
+    rs = np.random.default_rng(1234)
+    n_types = 8
+    base = rs.lognormal(-3.0, 1.2, g)
+    prof = base * np.exp(rs.normal(0, 0.8, (n_types, g)))
+    parts = []
+    for b, s0 in enumerate(range(0, n, 20000)):
+        e0 = min(s0 + 20000, n)
+        owner = b % world
+        if owner == rank:
+            rb = np.random.default_rng([1234, b])
+            types = rb.integers(0, n_types, e0 - s0)
+            depth = rb.lognormal(0, 0.3, e0 - s0)
+            blk = sp_sparse.csr_matrix(rb.poisson(prof[types] * depth[:, None]).astype(np.float32))
+            blk.sort_indices()
+            meta = torch.tensor([blk.nnz], dtype=torch.int64, device=device)
+        else:
+            blk, meta = None, torch.zeros(1, dtype=torch.int64, device=device)
+        if world > 1:
+            dist.broadcast(meta, src=owner)
+        nnz = int(meta.item())
+        if owner == rank:
+            t_ptr = torch.from_numpy(blk.indptr.astype(np.int32)).to(device)
+            t_idx = torch.from_numpy(blk.indices.astype(np.int32)).to(device)
+            t_dat = torch.from_numpy(blk.data).to(device)
+        else:
+            t_ptr = torch.empty(e0 - s0 + 1, dtype=torch.int32, device=device)
+            t_idx = torch.empty(nnz, dtype=torch.int32, device=device)
+            t_dat = torch.empty(nnz, dtype=torch.float32, device=device)
+        if world > 1:
+            for t in (t_ptr, t_idx, t_dat):
+                dist.broadcast(t, src=owner)
+        parts.append(sp_sparse.csr_matrix((t_dat.cpu().numpy(), t_idx.cpu().numpy(), t_ptr.cpu().numpy()), shape=(e0 - s0, g)))
+    x = sp_sparse.vstack(parts).tocsr()
     x.sort_indices()
     return x
 
@@ -399,6 +444,99 @@ def run_ours(args, wl, counts):
         dist.destroy_process_group()
 
 
+def run_cells(args, wl):
+    """--shard cells: ONE fit whose cells are sharded over the ranks (BASELINE config 5; strong scaling).  Every rank
+    holds the raw counts, builds / factorises its block of the augmented matrix; NCCL all-reduces inside the PCA,
+    all-gathers of the embedding and the kNN lists (libdd_b200.so, comm.cu)."""
+    import torch
+
+    from doubletdetection_b200 import _capi
+    from doubletdetection_b200.classifier import _pca_plan, broadcast_token
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    t_gen = time.perf_counter()
+    counts = make_counts_sharded(wl, rank, world, dist, dev)
+    t_gen = time.perf_counter() - t_gen
+    n_cells, n_genes = counts.shape
+    n_synth = int(BOOST_RATE * n_cells)
+    n_aug = n_cells + n_synth
+    n_iters = args.iters
+    host_threads = max(1, cpu_cores() // world)
+    omega, n_power_iter = _pca_plan(n_aug, n_genes, N_COMPONENTS, SEED)
+    h = _capi.Handle(local_rank)
+    h.upload_counts(counts)
+    if world > 1:
+        h.comm_init(rank, world, broadcast_token(dist, _capi.comm_unique_id() if rank == 0 else None, local_rank))
+        h.shard_cells(True)
+    fit_kw = dict(pseudocount=PSEUDOCOUNT, standard_scaling=False, n_comp=N_COMPONENTS, n_power_iter=n_power_iter,
+                  knn_k=10, resolution=4.0, seed=SEED, n_host_threads=host_threads)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rng = np.random.default_rng(SEED)  # the same parents on every rank
+    for _ in range(args.warmup):
+        h.fit_iterations(draw_parents(rng, n_cells, min(n_iters, 2)), omega, **fit_kw)
+    step_parents = [draw_parents(rng, n_cells, n_iters) for _ in range(args.steps)]
+    h.set_kernel_timing(True)
+    launches0 = h.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    stage_tot = {}
+    for s_ in range(args.steps):
+        out = h.fit_iterations(step_parents[s_], omega, **fit_kw)
+        for k_, v_ in out["stage_ms"].items():
+            stage_tot[k_] = stage_tot.get(k_, 0.0) + v_
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    clocks = sampler.stop()
+    report = h.kernel_timing_report()
+    launches = h.kernel_launches() - launches0
+    if dist is not None:
+        t = torch.tensor([launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        launches = int(t.item())
+    doublet_frac = float(np.mean(out["scores"][-1] > 0.5))
+    line = {
+        "metric": "augmented-cells/sec through BoostClassifier.fit (cells of every iteration sharded)",
+        "value": args.steps * n_iters * n_aug / dt, "unit": "augmented-cells/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters={n_iters}, louvain",
+                   "step": f"one {n_iters}-iteration fit loop, cells sharded over {world} GPU(s), counts resident",
+                   "cells": n_cells, "genes": n_genes, "synthetics": n_synth, "nnz": int(counts.nnz),
+                   "host_threads_per_rank": host_threads, "parallelism": f"cell-block x{world}",
+                   "collectives": "NCCL all-reduce (column sums, D^T Y, Gram) + all-gather (embedding, kNN lists)",
+                   "data_generation_s": round(t_gen, 1)},
+        "stage_ms_per_step": {k_: round(v_ / args.steps, 3) for k_, v_ in stage_tot.items()},
+        "kernel_ms_total": {k_: round(v_[0], 3) for k_, v_ in sorted(report.items(), key=lambda kv: -kv[1][0])},
+        "gpu_launches": int(launches), "clocks": clocks, "frac_scores_above_half_last_iter": doublet_frac,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def quick_workload(name, device, host_threads, _capi, _pca_plan):
     wl = WORKLOADS[name]
     counts = make_counts(wl)
@@ -429,10 +567,18 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--shard", default="iters", choices=["iters", "cells"],
+                    help="iters: every rank runs its own 25 iterations (weak scaling, the contract's line); "
+                         "cells: one fit, the cells of every iteration sharded over the ranks (config 5)")
+    ap.add_argument("--iters", type=int, default=N_ITERS, help="iterations per fit for --shard cells")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.shard == "cells":
+        return run_cells(args, wl)
+    if args.workload == "c5":
+        raise SystemExit("bench.py: workload c5 is the cell-sharded configuration: use --shard cells under torchrun")
     counts = make_counts(wl)
     if args.impl == "reference":
         run_reference_arm(args, wl, counts)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -41,7 +41,14 @@ class FitParams(ctypes.Structure):
         ("n_host_threads", ctypes.c_int32),
         ("iter_begin", ctypes.c_int32),
         ("iter_end", ctypes.c_int32),
+        ("clustering", ctypes.c_int32),
+        ("pheno_k", ctypes.c_int32),
+        ("pheno_prune", ctypes.c_int32),
+        ("pheno_min_cluster_size", ctypes.c_int32),
     ]
+
+
+CLUSTER_LOUVAIN, CLUSTER_PHENOGRAPH = 0, 1
 
 
 # name -> (restype, argtypes); every symbol include/dd_b200.h declares
@@ -70,6 +77,14 @@ SIGNATURES = {
     "dd_louvain_knn": (
         ctypes.c_int,
         [ctypes.c_int64, ctypes.c_int32, c_i32p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
+    "dd_phenograph_knn": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
+    "dd_jaccard_graph": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i32p, c_f64p, ctypes.c_int64, c_i64p],
     ),
     "dd_louvain_csr": (
         ctypes.c_int,
@@ -154,6 +169,20 @@ def louvain_knn(knn_idx, resolution=4.0, seed=0):
     if rc != DD_OK:
         _raise(lib, None, rc)
     return labels
+
+
+def phenograph_knn(knn_idx, prune=True, min_cluster_size=10, seed=0):
+    """PhenoGraph labels from exact kNN lists with self in column 0 (host twin of the pipelined device path)."""
+    lib = load()
+    knn_idx = np.ascontiguousarray(knn_idx, dtype=np.int32)
+    n, k = knn_idx.shape
+    labels = np.empty(max(n, 1), dtype=np.int32)
+    ncomm = ctypes.c_int32(0)
+    rc = lib.dd_phenograph_knn(n, k, _ptr(knn_idx, ctypes.c_int32), int(bool(prune)), int(min_cluster_size),
+                               int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return labels[:n]
 
 
 def louvain_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
@@ -320,16 +349,39 @@ class Handle:
         self._check(self._lib.dd_knn(self._h, k, _ptr(idx, ctypes.c_int32), _ptr(dist, ctypes.c_float)))
         return idx, dist
 
+    def jaccard_graph(self, k, prune=True):
+        """PhenoGraph graph of the last ``knn(k)`` as built on the device: scipy CSR (float64, sorted rows, pruned
+        zero-weight entries dropped)."""
+        import scipy.sparse as sp_sparse
+
+        n = self._emb_rows
+        indptr = np.empty(n + 1, dtype=np.int32)
+        nnz = ctypes.c_int64(0)
+        self._check(self._lib.dd_jaccard_graph(self._h, int(k), int(bool(prune)), _ptr(indptr, ctypes.c_int32), None, None,
+                                               0, ctypes.byref(nnz)))
+        indices = np.empty(max(nnz.value, 1), dtype=np.int32)
+        weights = np.empty(max(nnz.value, 1), dtype=np.float64)
+        self._check(self._lib.dd_jaccard_graph(self._h, int(k), int(bool(prune)), _ptr(indptr, ctypes.c_int32),
+                                               _ptr(indices, ctypes.c_int32), _ptr(weights, ctypes.c_double), nnz.value,
+                                               ctypes.byref(nnz)))
+        g = sp_sparse.csr_matrix((weights[: nnz.value], indices[: nnz.value], indptr), shape=(n, n))
+        g.eliminate_zeros()
+        g.sort_indices()
+        return g
+
     # the loop
     def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10,
-                       resolution=4.0, seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0):
+                       resolution=4.0, seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0,
+                       clustering="louvain", pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10):
         parents = np.ascontiguousarray(parents, dtype=np.int64)
         n_iters, n_synth = parents.shape[0], parents.shape[1]
         omega = _f32(omega)
         iter_end = n_iters if iter_end is None else iter_end
         p = FitParams(n_iters, n_synth, float(pseudocount), int(bool(standard_scaling)), float(scale_max_value),
                       int(n_comp), int(omega.shape[1]), int(n_power_iter), int(knn_k), float(resolution),
-                      int(seed) & (2**64 - 1), int(n_host_threads), int(iter_begin), int(iter_end))
+                      int(seed) & (2**64 - 1), int(n_host_threads), int(iter_begin), int(iter_end),
+                      {"louvain": CLUSTER_LOUVAIN, "phenograph": CLUSTER_PHENOGRAPH}[clustering], int(pheno_k),
+                      int(bool(pheno_prune)), int(pheno_min_cluster_size))
         N = self.n_cells
         scores = np.zeros((n_iters, N), dtype=np.float64)
         logp = np.zeros((n_iters, N), dtype=np.float64)

@@ -6,8 +6,10 @@ Same constructor arguments, defaults, warnings and errors (:73-133, :404-426), s
 ``predict`` / ``doublet_score`` semantics (:135-272) and the same fitted attributes.  What changes is
 where ``_one_fit`` (:274-383) executes: synthetic doublets, normalise/log, optional scaling,
 randomized PCA and the exact kNN graph are CUDA kernels, clustering (Louvain) and scoring are native
-host code overlapped with the GPU.  There is no CPU fallback: without the built library or without a
-B200 ``fit`` raises.
+host code overlapped with the GPU.  ``clustering_algorithm="phenograph"`` (the reference's default) builds
+PhenoGraph's Jaccard graph of the 30 nearest neighbours on the GPU and partitions it with the in-repo Louvain
+(one seeded run; the phenograph package with its time-seeded binaries is not available); ``"leiden"`` is not
+implemented.  There is no CPU fallback: without the built library or without a B200 ``fit`` raises.
 
 Keyword-only extensions (not in the reference): ``device`` (CUDA device index; default
 ``LOCAL_RANK`` or 0) and ``distributed`` (shard the work over the ranks of an initialised
@@ -182,16 +184,32 @@ class BoostClassifier:
         if self.normalizer is not None:
             # the reference itself raises NameError on this path in this version (:288-291 vs :301, :372)
             raise NotImplementedError("custom `normalizer` is not supported (and is broken in the reference at this version)")
-        if self.clustering_algorithm != "louvain":
+        if self.clustering_algorithm == "leiden":
             raise NotImplementedError(
-                f"clustering_algorithm='{self.clustering_algorithm}' needs the phenograph / leidenalg packages; "
-                "the B200 hot path clusters with Louvain (clustering_algorithm='louvain')"
+                "clustering_algorithm='leiden' (sc.tl.leiden on the UMAP-weighted graph) is not implemented on the B200 "
+                "path; use 'louvain' or 'phenograph'"
             )
-        if self.clustering_kwargs.get("directed", False):
-            raise NotImplementedError("clustering_kwargs['directed']=True is not supported (the reference default is False)")
-        extra = set(self.clustering_kwargs) - {"directed", "resolution"}
-        if extra:
-            raise NotImplementedError(f"unsupported clustering_kwargs for the native Louvain: {sorted(extra)}")
+        cluster_kw = {}
+        if self.clustering_algorithm == "phenograph":
+            # phenograph.cluster(X_pca, n_jobs=self.n_jobs, **clustering_kwargs) (:320): the arguments that change
+            # the graph or the labels; the rest of phenograph's signature must stay at its defaults
+            allowed = {"prune", "k", "min_cluster_size", "jaccard", "directed", "primary_metric", "clustering_algo"}
+            extra = set(self.clustering_kwargs) - allowed
+            if extra:
+                raise NotImplementedError(f"unsupported clustering_kwargs for the native PhenoGraph: {sorted(extra)}")
+            kw = self.clustering_kwargs
+            if (kw.get("jaccard", True) is not True or kw.get("directed", False) is not False
+                    or kw.get("primary_metric", "euclidean") != "euclidean" or kw.get("clustering_algo", "louvain") != "louvain"):
+                raise NotImplementedError("native PhenoGraph: only jaccard=True, directed=False, euclidean, louvain")
+            cluster_kw = dict(clustering="phenograph", pheno_k=int(kw.get("k", 30)), pheno_prune=bool(kw.get("prune", True)),
+                              pheno_min_cluster_size=int(kw.get("min_cluster_size", 10)))
+        else:
+            if self.clustering_kwargs.get("directed", False):
+                raise NotImplementedError("clustering_kwargs['directed']=True is not supported (the reference default is False)")
+            extra = set(self.clustering_kwargs) - {"directed", "resolution"}
+            if extra:
+                raise NotImplementedError(f"unsupported clustering_kwargs for the native Louvain: {sorted(extra)}")
+            cluster_kw = dict(clustering="louvain", resolution=float(self.clustering_kwargs["resolution"]))
         if self.pseudocount == 1:
             raise NotImplementedError("pseudocount=1 selects the sparse log1p + arpack path (:296-297, :308), which is not on the B200 hot path")
 
@@ -258,9 +276,8 @@ class BoostClassifier:
         out = h.fit_iterations(
             parents, omega,
             pseudocount=self.pseudocount, standard_scaling=self.standard_scaling is True,
-            n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10,
-            resolution=float(self.clustering_kwargs["resolution"]), seed=int(self.random_state),
-            n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1,
+            n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10, seed=int(self.random_state),
+            n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1, **cluster_kw,
         )
         _t.append(_time.perf_counter())
         if dist is not None:

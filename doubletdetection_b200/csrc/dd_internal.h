@@ -11,7 +11,7 @@
 
 #include "../../include/dd_b200.h"
 
-#define DD_ABI_VERSION 2
+#define DD_ABI_VERSION 3
 
 // padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
 static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -101,7 +101,8 @@ struct dd_handle {
     // ---- GPU Louvain level 0 (louvain_gpu.cu): symmetric kNN pattern as CSR + community state ----
     int32_t *d_lv_off = nullptr, *d_lv_adj = nullptr, *d_lv_comm = nullptr, *d_lv_i32 = nullptr;
     double *d_lv_tot = nullptr;
-    int64_t cap_lv_n = 0, cap_lv_nnz = 0;
+    double *d_lv_w = nullptr;  // Jaccard edge weights of the PhenoGraph graph (one per adjacency entry)
+    int64_t cap_lv_n = 0, cap_lv_nnz = 0, cap_lv_w = 0;
     int64_t lv_bucket_n = -1;
     uint64_t lv_bucket_seed = 0;
     std::vector<int32_t> lv_colour_off;
@@ -194,6 +195,7 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
                const float *omega_host);                            // pca.cu
 int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
 int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed);  // louvain_gpu.cu
+int dd_dev_jaccard_graph(dd_handle *h, int32_t k, int prune);                      // louvain_gpu.cu (PhenoGraph)
 
 // host pieces (louvain.cpp / score.cpp)
 int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
@@ -201,4 +203,8 @@ int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double res
 // upper Louvain levels from a first-level partition: off/adj = symmetric pattern CSR, comm0 = community per node
 int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *adj, const int32_t *comm0,
                                 double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
+// PhenoGraph on the host from the device-built weighted graph (rows in any order, zero weights = pruned edges):
+// Louvain at resolution 1 on the weighted graph, labels by decreasing size, communities < min_cluster_size -> -1
+int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
+                                  int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out);
 float dd_host_median(std::vector<float> &v);

@@ -20,7 +20,7 @@ int dd_pca_flag_copy(dd_handle *h, double *host_flag);                      // p
 namespace {
 
 struct Slot {
-    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1))]
+    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1)) | PhenoGraph: weights (f64)]
     double *flag = nullptr;    // pinned, PCA breakdown flag
     cudaEvent_t done = nullptr;
 };
@@ -48,16 +48,23 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     if (p->pseudocount == 1.0f)
         return dd_fail(h, DD_ERR_UNSUPPORTED, "pseudocount == 1 (sparse log1p + arpack path) is not on the B200 hot path");
     if (p->knn_k < 2) return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: knn_k < 2");
+    if (p->clustering != DD_CLUSTER_LOUVAIN && p->clustering != DD_CLUSTER_PHENOGRAPH)
+        return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: unknown clustering");
+    const bool pheno = p->clustering == DD_CLUSTER_PHENOGRAPH;
+    if (pheno && (p->pheno_k < 1 || p->pheno_k > 30))
+        return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_fit_iterations: phenograph k must be in [1, 30]");
     DD_CUDA(h, cudaSetDevice(h->device));
 
     const int64_t N = h->N, M = p->n_synth, A = N + M;
-    const int k = p->knn_k;
+    // PhenoGraph looks at its own neighbourhood size (k nearest + self), not sc.pp.neighbors' 10
+    const int k = pheno ? p->pheno_k + 1 : p->knn_k;
     // the host side of an iteration (aggregate ~10^2 communities, upper Louvain levels, scoring) is tens of
     // milliseconds, so a few workers keep up with the GPU
     const int n_threads = std::max(1, std::min(p->n_host_threads, 8));
     const int n_slots = n_threads + 2;
     const int64_t max_nnz = A * 2 * (k - 1);
-    const int64_t slot_elems = (A + 1) + A + max_nnz;
+    const int64_t w_off = ((A + 1) + A + max_nnz + 1) / 2 * 2;  // weights start 8-byte aligned
+    const int64_t slot_elems = pheno ? w_off + 2 * max_nnz : (A + 1) + A + max_nnz;
     const int n_run = p->iter_end - p->iter_begin;
     if (stage_ms_out) std::fill(stage_ms_out, stage_ms_out + 8, 0.0);
     if (n_run == 0) return DD_OK;
@@ -141,7 +148,11 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
                 const auto t0 = now();
                 int32_t n_comm = 0;
                 const int32_t *off = s.graph, *comm0 = s.graph + (A + 1), *adj = s.graph + (A + 1) + A;
-                wrc = dd_host_louvain_from_level0(A, off, adj, comm0, p->resolution, p->seed, labels.data(), &n_comm);
+                if (pheno)
+                    wrc = dd_host_phenograph_from_graph(A, off, adj, reinterpret_cast<const double *>(s.graph + w_off), p->seed,
+                                                        p->pheno_min_cluster_size, labels.data(), &n_comm);
+                else
+                    wrc = dd_host_louvain_from_level0(A, off, adj, comm0, p->resolution, p->seed, labels.data(), &n_comm);
                 if (wrc != DD_OK) werr = "dd_fit_iterations: clustering rejected the device graph";
                 if (wrc == DD_OK) {
                     wrc = dd_score(N, M, labels.data(), scores_out + (size_t)job.iter * N, log_p_out + (size_t)job.iter * N);
@@ -207,13 +218,15 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         {
             cudaStream_t main_stream = h->stream;
             h->stream = h->stream2;
-            rc = dd_dev_louvain_level0(h, k, p->resolution, p->seed);
+            rc = pheno ? dd_dev_jaccard_graph(h, k, p->pheno_prune) : dd_dev_louvain_level0(h, k, p->resolution, p->seed);
             h->stream = main_stream;
         }
         if (rc != DD_OK) break;
         cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, h->stream2);
         cudaMemcpyAsync(s.graph + (A + 1), h->d_lv_comm, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, h->stream2);
         cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, h->stream2);
+        if (pheno)
+            cudaMemcpyAsync(s.graph + w_off, h->d_lv_w, sizeof(double) * max_nnz, cudaMemcpyDeviceToHost, h->stream2);
         cudaEventRecord(ev[5], h->stream2);
         cudaEventRecord(h->ev_lv_done, h->stream2);
         cudaEventRecord(s.done, h->stream2);

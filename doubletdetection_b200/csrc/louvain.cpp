@@ -436,6 +436,111 @@ int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *ad
     return run_louvain(g, resolution, seed, labels_out, n_comm_out, comm0, false);
 }
 
+// ---- PhenoGraph (doubletdetection.py:318-327 -> phenograph.cluster; specification: oracle/upstream.py
+// phenograph_cluster).  The graph arrives as CSR with rows in any order and zero weights for pruned entries.
+namespace {
+int phenograph_finish(Graph &g, uint64_t seed, int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out) {
+    const int32_t n = g.n;
+    int32_t nc = 0;
+    const int rc = run_louvain(g, 1.0, seed, labels_out, &nc);  // standard modularity; labels by decreasing size
+    if (rc != DD_OK) return rc;
+    std::vector<int64_t> size(std::max(nc, 1), 0);
+    for (int32_t i = 0; i < n; i++) size[labels_out[i]]++;
+    for (int32_t i = 0; i < n; i++)
+        if (size[labels_out[i]] < min_cluster_size) labels_out[i] = -1;  // phenograph: min_cluster_size
+    if (n_comm_out) *n_comm_out = nc;
+    return DD_OK;
+}
+}  // namespace
+
+int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
+                                  int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out) {
+    if (n < 0 || (n > 0 && (!off || !labels_out))) return DD_ERR_ARG;
+    Graph g;
+    g.n = (int32_t)n;
+    g.indptr.assign(n + 1, 0);
+    const int64_t nnz_in = n > 0 ? off[n] : 0;
+    if (nnz_in > 0 && (!adj || !w)) return DD_ERR_ARG;
+    g.indices.reserve(nnz_in);
+    g.weights.reserve(nnz_in);
+    std::vector<std::pair<int32_t, double>> row;
+    for (int64_t i = 0; i < n; i++) {
+        row.clear();
+        for (int64_t p = off[i]; p < off[i + 1]; p++) {
+            if (adj[p] < 0 || adj[p] >= n) return DD_ERR_ARG;
+            if (w[p] != 0.0) row.emplace_back(adj[p], w[p]);
+        }
+        std::sort(row.begin(), row.end(), [](const std::pair<int32_t, double> &a, const std::pair<int32_t, double> &b) {
+            return a.first < b.first;
+        });
+        for (const auto &e : row) {
+            g.indices.push_back(e.first);
+            g.weights.push_back(e.second);
+        }
+        g.indptr[i + 1] = (int64_t)g.indices.size();
+    }
+    g.selfw.assign(n, 0.0);
+    return phenograph_finish(g, seed, min_cluster_size, labels_out, n_comm_out);
+}
+
+// Host twin of the device path: the same graph from the kNN lists (n x k, self in column 0) on the CPU.
+extern "C" int dd_phenograph_knn(int64_t n, int32_t k, const int32_t *knn_idx, int32_t prune, int32_t min_cluster_size,
+                                 uint64_t seed, int32_t *labels_out, int32_t *n_communities_out) {
+    if (n < 0 || k < 2 || (n > 0 && (!knn_idx || !labels_out)) || n >= (1ll << 31) - 1) {
+        dd_set_global_error("dd_phenograph_knn: bad arguments");
+        return DD_ERR_ARG;
+    }
+    const int kk = k - 1;
+    std::vector<int32_t> sorted((size_t)n * kk);
+    for (int64_t i = 0; i < n; i++) {
+        for (int c = 0; c < kk; c++) {
+            const int32_t j = knn_idx[i * k + 1 + c];
+            if (j < 0 || j >= n) {
+                dd_set_global_error("dd_phenograph_knn: neighbour index out of range");
+                return DD_ERR_ARG;
+            }
+            sorted[i * kk + c] = j;
+        }
+        std::sort(sorted.begin() + i * kk, sorted.begin() + (i + 1) * kk);
+    }
+    auto has = [&](int64_t i, int32_t j) {
+        return std::binary_search(sorted.begin() + i * kk, sorted.begin() + (i + 1) * kk, j);
+    };
+    // symmetric pattern: out-neighbours and in-neighbours
+    std::vector<std::vector<int32_t>> nbr(n);
+    for (int64_t i = 0; i < n; i++)
+        for (int c = 0; c < kk; c++) {
+            const int32_t j = sorted[i * kk + c];
+            if (j == i) continue;
+            nbr[i].push_back(j);
+            if (!has(j, (int32_t)i)) nbr[j].push_back((int32_t)i);
+        }
+    std::vector<int32_t> off(n + 1, 0), adj;
+    std::vector<double> w;
+    for (int64_t i = 0; i < n; i++) {
+        std::sort(nbr[i].begin(), nbr[i].end());
+        nbr[i].erase(std::unique(nbr[i].begin(), nbr[i].end()), nbr[i].end());
+        for (int32_t j : nbr[i]) {
+            int s = 0;
+            const int32_t *a = sorted.data() + i * kk, *b = sorted.data() + (int64_t)j * kk;
+            for (int x = 0, y = 0; x < kk && y < kk;) {
+                if (a[x] < b[y]) x++;
+                else if (a[x] > b[y]) y++;
+                else { s++; x++; y++; }
+            }
+            const double wij = (double)s / (double)(2 * kk - s);
+            const bool mutual = has(i, j) && has(j, (int32_t)i);
+            adj.push_back(j);
+            w.push_back(prune ? (mutual ? wij * wij : 0.0) : (mutual ? wij : wij * 0.5));
+        }
+        off[i + 1] = (int32_t)adj.size();
+    }
+    const int rc = dd_host_phenograph_from_graph(n, off.data(), adj.data(), w.data(), seed, min_cluster_size, labels_out,
+                                                 n_communities_out);
+    if (rc != DD_OK) dd_set_global_error("dd_phenograph_knn: clustering failed");
+    return rc;
+}
+
 extern "C" int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
                               int32_t *labels_out, int32_t *n_communities_out) {
     const int rc = dd_host_louvain_knn(n, k, knn_idx, resolution, seed, labels_out, n_communities_out);

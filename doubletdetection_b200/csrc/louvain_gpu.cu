@@ -327,7 +327,14 @@ __global__ void __launch_bounds__(kRoundThreads, 1) k_lv_rounds(const int32_t *_
 // Louvain level.  Results (device): h->d_lv_off (n + 1), h->d_lv_adj (off[n] entries), h->d_lv_comm (n).
 // Fully asynchronous on h->stream (no host read-back: the colour classes depend only on (n, seed) and are
 // bucketed on the host once).
-int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) {
+namespace {
+struct LvBuffers {
+    int n;
+    int32_t *deg, *cursor, *csize, *desired, *bucket, *counters;
+};
+
+// (re)allocate the graph / state buffers for n nodes of out-degree <= k - 1 and build the symmetric pattern CSR
+int lv_build_graph(dd_handle *h, int32_t k, LvBuffers &b) {
     const int64_t n64 = h->emb_rows;
     if (n64 >= (1ll << 31) / (2 * k)) return dd_fail(h, DD_ERR_UNSUPPORTED, "louvain: graph too large for int32 offsets");
     const int n = (int)n64;
@@ -348,9 +355,77 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         h->lv_bucket_n = -1;
         h->lv_graph_n = -1;  // the captured launches hold the old pointers
     }
-    int32_t *deg = h->d_lv_i32, *cursor = deg + h->cap_lv_n, *csize = cursor + h->cap_lv_n,
-            *desired = csize + h->cap_lv_n, *bucket = desired + h->cap_lv_n, *counters = bucket + h->cap_lv_n;
-    if (h->lv_bucket_n != n || h->lv_bucket_seed != seed) {  // colour classes: a pure function of (n, seed)
+    b.n = n;
+    b.deg = h->d_lv_i32; b.cursor = b.deg + h->cap_lv_n; b.csize = b.cursor + h->cap_lv_n;
+    b.desired = b.csize + h->cap_lv_n; b.bucket = b.desired + h->cap_lv_n; b.counters = b.bucket + h->cap_lv_n;
+    DD_CUDA(h, cudaMemsetAsync(b.deg, 0, sizeof(int32_t) * 2 * (size_t)h->cap_lv_n, h->stream));  // deg + cursor
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    DD_LAUNCH(h, "lv_graph_count", k_graph_count, nb, 256, 0, h->d_knn_idx, n, (int)k, b.deg);
+    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan, 1, 1024, 0, b.deg, n, h->d_lv_off, b.counters);
+    DD_LAUNCH(h, "lv_graph_fill", k_graph_fill, nb, 256, 0, h->d_knn_idx, n, (int)k, h->d_lv_off, b.cursor, h->d_lv_adj,
+              h->d_lv_comm, h->d_lv_tot, b.csize);
+    return DD_OK;
+}
+
+// PhenoGraph's edge weights (phenograph/core.py jaccard_kernel; doubletdetection.py:320) on the symmetric pattern:
+// for the entry (i, j):  s = |N(i) & N(j)|,  w = s / (2 kk - s)  with N(x) the kk = k - 1 neighbours of x (self, in
+// column 0 of the kNN lists, excluded).  prune: mutual edges carry w_ij * w_ji = w^2, the others 0 (the host drops
+// them); otherwise (w_ij + w_ji) / 2 = w for mutual edges, w / 2 for one-directional ones.  One warp per node, the
+// node's list in registers (lane c holds neighbour c), every other list compared by shuffles.
+__global__ void __launch_bounds__(256) k_jaccard_weights(const int32_t *__restrict__ knn, int n, int k,
+                                                         const int32_t *__restrict__ off,
+                                                         const int32_t *__restrict__ adj, int prune,
+                                                         double *__restrict__ w_out) {
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= n) return;
+    const int kk = k - 1;
+    const int mine = lane < kk ? knn[(int64_t)i * k + 1 + lane] : -1;
+    const int b = off[i], e = off[i + 1];
+    for (int p = b; p < e; p++) {
+        const int j = adj[p];
+        const int theirs = lane < kk ? knn[(int64_t)j * k + 1 + lane] : -2;
+        bool shared = false;
+        for (int t = 0; t < kk; t++) shared |= theirs == __shfl_sync(0xffffffffu, mine, t);
+        const int s = __popc(__ballot_sync(0xffffffffu, shared && lane < kk && theirs >= 0));
+        const bool ij = __any_sync(0xffffffffu, mine == j);   // j in N(i)
+        const bool ji = __any_sync(0xffffffffu, theirs == i);  // i in N(j)
+        if (lane == 0) {
+            const double w = (double)s / (double)(2 * kk - s);
+            double out;
+            if (prune)
+                out = (ij && ji) ? w * w : 0.0;
+            else
+                out = (ij && ji) ? w : w * 0.5;
+            w_out[p] = out;
+        }
+    }
+}
+}  // namespace
+
+// Symmetric pattern of the kNN lists (k columns, self in column 0) + Jaccard weights: h->d_lv_off / d_lv_adj /
+// d_lv_w on the device (asynchronous on h->stream).
+int dd_dev_jaccard_graph(dd_handle *h, int32_t k, int prune) {
+    if (k < 2 || k > 32) return dd_fail(h, DD_ERR_UNSUPPORTED, "jaccard graph: k + 1 must be in [2, 32]");
+    LvBuffers b;
+    DD_TRY(lv_build_graph(h, k, b));
+    DD_TRY(dd_reserve(h, &h->d_lv_w, &h->cap_lv_w, h->cap_lv_nnz));
+    const unsigned nb = (unsigned)(((int64_t)b.n * 32 + 255) / 256);
+    DD_LAUNCH(h, "jaccard_weights", k_jaccard_weights, nb, 256, 0, h->d_knn_idx, b.n, (int)k, h->d_lv_off, h->d_lv_adj, prune,
+              h->d_lv_w);
+    return DD_OK;
+}
+
+int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) {
+    LvBuffers lb;
+    {   // colour classes: a pure function of (n, seed); the bucket array lives in the (possibly re-allocated) state block
+        const int64_t n64 = h->emb_rows;
+        if (n64 >= (1ll << 31) / (2 * k)) return dd_fail(h, DD_ERR_UNSUPPORTED, "louvain: graph too large for int32 offsets");
+    }
+    DD_TRY(lv_build_graph(h, k, lb));
+    const int n = lb.n;
+    int32_t *csize = lb.csize, *desired = lb.desired, *bucket = lb.bucket, *counters = lb.counters;
+    if (h->lv_bucket_n != n || h->lv_bucket_seed != seed) {
         std::vector<int32_t> cnt(kColours + 1, 0), nodes(n);
         for (int i = 0; i < n; i++) cnt[colour_of(seed, i) + 1]++;
         for (int c = 0; c < kColours; c++) cnt[c + 1] += cnt[c];
@@ -362,12 +437,6 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         h->lv_bucket_n = n;
         h->lv_bucket_seed = seed;
     }
-    DD_CUDA(h, cudaMemsetAsync(deg, 0, sizeof(int32_t) * 2 * (size_t)h->cap_lv_n, h->stream));  // deg + cursor
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    DD_LAUNCH(h, "lv_graph_count", k_graph_count, nb, 256, 0, h->d_knn_idx, n, (int)k, deg);
-    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan, 1, 1024, 0, deg, n, h->d_lv_off, counters);
-    DD_LAUNCH(h, "lv_graph_fill", k_graph_fill, nb, 256, 0, h->d_knn_idx, n, (int)k, h->d_lv_off, cursor, h->d_lv_adj,
-              h->d_lv_comm, h->d_lv_tot, csize);
     // default: one small launch per step, replayed from a CUDA graph -- the steps are latency-bound (~10 us each),
     // but as ordinary kernels on the clustering stream they share the SMs with the HBM-bound kernels of the next
     // iteration.  DD_LOUVAIN_COOP=1: all rounds in ONE cooperative launch (one CTA per SM, hand-written grid
@@ -446,5 +515,24 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
     }
     DD_TRY(dd_launch_end(h, "lv_rounds_graph"));
     h->launches += h->lv_graph_launches - 1;  // the replay runs every captured kernel
+    return DD_OK;
+}
+
+// Test / inspection hook: the PhenoGraph graph of the kNN lists computed last (dd_knn with k neighbours incl. self).
+extern "C" int dd_jaccard_graph(dd_handle *h, int32_t k, int32_t prune, int32_t *indptr_out, int32_t *indices_out,
+                                double *weights_out, int64_t capacity, int64_t *nnz_out) {
+    if (!h || !indptr_out || !nnz_out) return dd_fail(h, DD_ERR_ARG, "dd_jaccard_graph: null argument");
+    if (!h->emb_valid || !h->d_knn_idx) return dd_fail(h, DD_ERR_ARG, "dd_jaccard_graph: call dd_knn first");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_TRY(dd_dev_jaccard_graph(h, k, prune));
+    const int64_t n = h->emb_rows;
+    DD_CUDA(h, cudaMemcpyAsync(indptr_out, h->d_lv_off, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int64_t nnz = indptr_out[n];
+    *nnz_out = nnz;
+    if (nnz > capacity || !indices_out || !weights_out) return DD_OK;  // caller sizes its buffers from nnz_out and calls again
+    DD_CUDA(h, cudaMemcpyAsync(indices_out, h->d_lv_adj, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaMemcpyAsync(weights_out, h->d_lv_w, sizeof(double) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
     return DD_OK;
 }

@@ -105,6 +105,20 @@ int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
  * labels_out int32[n], 0 = largest community.  No handle: pure host code, thread-safe. */
 int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,
                    int32_t *labels_out, int32_t *n_communities_out);
+/* phenograph.cluster(X_pca, prune=...)[0], doubletdetection.py:320 (defaults k = 30, jaccard=True,
+ * min_cluster_size = 10), from the exact kNN lists knn_idx int32[n * k] (self in column 0, so k = 31 for
+ * PhenoGraph's k = 30): Jaccard graph w_ij = s / (2(k-1) - s), s = shared neighbours; prune keeps mutual edges
+ * with the product of the two directed weights, otherwise the average; Louvain at resolution 1 on the weighted
+ * graph; labels by decreasing size, communities smaller than min_cluster_size get -1.  The phenograph package
+ * (absent from the image) runs its bundled Louvain binaries repeatedly with time-based seeds; this is ONE seeded
+ * run of the in-repo Louvain (specification: oracle/upstream.py phenograph_cluster).  Pure host code: the host
+ * twin of what dd_fit_iterations does with the graph built on the device. */
+int dd_phenograph_knn(int64_t n, int32_t k, const int32_t *knn_idx, int32_t prune, int32_t min_cluster_size,
+                      uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
+/* The PhenoGraph graph of the lists of the last dd_knn(h, k, ...) as built on the device: symmetric pattern CSR
+ * (rows unordered) + weights (0 = pruned).  Call with capacity 0 to get nnz_out, then with buffers of that size. */
+int dd_jaccard_graph(dd_handle *h, int32_t k, int32_t prune, int32_t *indptr_out, int32_t *indices_out,
+                     double *weights_out, int64_t capacity, int64_t *nnz_out);
 /* Fully sequential Louvain on an explicit symmetric CSR graph (weights may be NULL = unweighted). */
 int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                    double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
@@ -147,7 +161,13 @@ typedef struct dd_fit_params {
     int32_t n_host_threads;
     int32_t iter_begin;       /* run iterations [iter_begin, iter_end) of the n_iters drawn */
     int32_t iter_end;
+    int32_t clustering;       /* DD_CLUSTER_LOUVAIN (:329-343) or DD_CLUSTER_PHENOGRAPH (:318-327) */
+    int32_t pheno_k;          /* phenograph.cluster k (30): neighbours per cell, self excluded */
+    int32_t pheno_prune;      /* 1: keep mutual edges, weight product (the reference's default); 0: average */
+    int32_t pheno_min_cluster_size; /* 10: smaller communities are labelled -1 (NaN scores, :379-381) */
 } dd_fit_params;
+#define DD_CLUSTER_LOUVAIN 0
+#define DD_CLUSTER_PHENOGRAPH 1
 
 int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int64_t *parents, const float *omega,
                       double *scores_out, double *log_p_out, int32_t *communities_out,

@@ -158,7 +158,9 @@ class OracleClassifier:
         standard_scaling=False,
         louvain_fn=None,
         keep_stages=False,
+        clustering_algorithm="louvain",
     ):
+        self.clustering_algorithm = clustering_algorithm
         self.boost_rate = boost_rate
         self.replace = replace
         self.n_iters = n_iters
@@ -172,8 +174,11 @@ class OracleClassifier:
             self.n_components = n_components
         self.n_top_var_genes = max(0, n_top_var_genes)
         kw = dict(clustering_kwargs or {})
-        kw.setdefault("directed", False)  # :417-420
-        kw.setdefault("resolution", 4)
+        if clustering_algorithm == "phenograph":
+            kw.setdefault("prune", True)  # :408-409
+        else:
+            kw.setdefault("directed", False)  # :417-420
+            kw.setdefault("resolution", 4)
         self.clustering_kwargs = kw
         if not self.replace and self.boost_rate > 0.5:  # :121-127
             self.boost_rate = 0.5
@@ -225,6 +230,14 @@ class OracleClassifier:
         emb, _ = upstream.tl_pca(aug, self.n_components, random_state=self.random_state, svd_solver=solver)
         adata.obsm["X_pca"] = emb
         st["X_pca"] = emb
+        if self.clustering_algorithm == "phenograph":  # :318-327
+            full, graph = upstream.phenograph_cluster(emb, seed=self.random_state, louvain_fn=self.louvain_fn,
+                                                      **self.clustering_kwargs)
+            st["fullcommunities"] = full
+            if self.keep_stages:
+                st["jaccard_graph"] = graph
+            st["scores"], st["log_p"], st["communities"], st["synth_communities"] = score_communities(full, num_cells)
+            return st
         upstream.pp_neighbors(adata, random_state=self.random_state, method="umap", n_neighbors=10)
         st["knn_indices"] = adata.uns["knn_indices"]
         st["knn_distances"] = adata.uns["knn_distances"]

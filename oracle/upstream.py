@@ -232,3 +232,44 @@ def tl_louvain(adata, key_added="clusters", random_state=0, directed=False, reso
     labels = fn(C.indptr, C.indices, None, resolution=float(resolution), seed=int(random_state), level0="parallel")
     adata.obs[key_added] = np.asarray([str(int(x)) for x in labels])
     return adata
+
+
+def jaccard_graph(nbr_idx, prune=True):
+    """PhenoGraph's graph (phenograph/core.py: jaccard_kernel + neighbor_graph, cluster(): prune) from the k nearest
+    neighbours WITHOUT self (n x k): directed weight w_ij = s / (2k - s) with s = |N(i) & N(j)| for j in N(i);
+    prune=True keeps mutual edges with the product of the two directed weights (``graph.multiply(graph.T)``),
+    prune=False averages (``(graph + graph.T) / 2``).  Zero weights are dropped.  float64 CSR, sorted rows.
+    **[upstream, absent -- restated from SURVEY Appendix B3]**"""
+    nbr_idx = np.asarray(nbr_idx, dtype=np.int64)
+    n, k = nbr_idx.shape
+    sets = [set(row.tolist()) for row in nbr_idx]
+    rows = np.repeat(np.arange(n, dtype=np.int64), k)
+    cols = nbr_idx.ravel()
+    w = np.empty(n * k, dtype=np.float64)
+    for i in range(n):
+        si = sets[i]
+        for c in range(k):
+            s = len(si & sets[nbr_idx[i, c]])
+            w[i * k + c] = s / (2.0 * k - s)
+    G = sp_sparse.coo_matrix((w, (rows, cols)), shape=(n, n)).tocsr()
+    S = G.multiply(G.T) if prune else (G + G.T) / 2.0
+    S = S.tocsr()
+    S.eliminate_zeros()
+    S.sort_indices()
+    return S
+
+
+def phenograph_cluster(X_pca, k=30, prune=True, min_cluster_size=10, seed=0, louvain_fn=None):
+    """``phenograph.cluster(X_pca, n_jobs=..., prune=...)[0]`` -- doubletdetection.py:320 (defaults k=30,
+    jaccard=True, min_cluster_size=10): exact k+1 nearest neighbours, self dropped; Jaccard graph; Louvain on the
+    weighted graph (standard modularity = resolution 1); communities numbered by decreasing size, those smaller
+    than ``min_cluster_size`` relabelled -1.  Upstream runs its bundled Louvain binaries repeatedly with
+    time-based seeds and keeps the best modularity, so its labels are not reproducible even against itself;
+    the oracle fixes ONE seeded run of the in-repo Louvain specification.  PARITY UNPINNED for this stage."""
+    idx, _ = knn_brute(np.asarray(X_pca), k + 1)
+    G = jaccard_graph(idx[:, 1:], prune=prune)
+    fn = louvain_fn or louvain_ref.louvain
+    labels = np.asarray(fn(G.indptr, G.indices, G.data, resolution=1.0, seed=int(seed)), dtype=np.int64).copy()
+    sizes = np.bincount(labels, minlength=labels.max() + 1 if labels.size else 0)
+    labels[sizes[labels] < min_cluster_size] = -1
+    return labels, G

@@ -69,7 +69,11 @@ def test_unsupported_paths_fail_loudly():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         with pytest.raises(NotImplementedError):
-            BoostClassifier(n_iters=2).fit(x)  # phenograph package is absent
+            BoostClassifier(n_iters=2, clustering_algorithm="leiden").fit(x)  # leidenalg path is not built
+        with pytest.raises(NotImplementedError):  # phenograph arguments the native graph does not cover
+            BoostClassifier(n_iters=2, clustering_kwargs={"primary_metric": "cosine"}).fit(x)
+        with pytest.raises(NotImplementedError):
+            BoostClassifier(n_iters=2, clustering_kwargs={"nn_method": "brute"}).fit(x)
         with pytest.raises(NotImplementedError):
             BoostClassifier(n_iters=2, clustering_algorithm="louvain", pseudocount=1).fit(x)
         with pytest.raises(NotImplementedError):

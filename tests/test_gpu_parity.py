@@ -446,3 +446,63 @@ def test_config3_full_size_properties():
         lab = np.concatenate([clf.communities_[i], clf.synth_communities_[i]]).astype(np.int64)
         sizes = np.bincount(lab)
         assert (sizes > 0).all() and (np.diff(sizes) <= 0).all()
+
+
+# ------------------------------------------------------------------------------ PhenoGraph (the reference's default)
+@pytest.mark.parametrize("prune", [True, False])
+def test_jaccard_graph_on_device_matches_oracle(handle, prune):
+    """The PhenoGraph graph built on the GPU (symmetric pattern + Jaccard weights, mutual-edge pruning) equals the
+    oracle's scipy construction entry for entry: weights are ratios / products of small integers, so bit-exact."""
+    g = load_golden("structured_1500x300")
+    emb = g["X_pca0"].astype(np.float32)
+    handle.upload_embedding(emb)
+    idx, _ = handle.knn(31)
+    want_idx, _ = upstream.knn_brute(emb, 31)
+    np.testing.assert_array_equal(idx, want_idx)
+    got = handle.jaccard_graph(31, prune=prune)
+    want = upstream.jaccard_graph(want_idx[:, 1:], prune=prune)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+
+
+@pytest.mark.parametrize("kwargs", [dict(), dict(clustering_kwargs={"prune": False}), dict(standard_scaling=True)])
+def test_classifier_phenograph_vs_oracle(kwargs):
+    """BoostClassifier with the reference's DEFAULT clustering (phenograph, doubletdetection.py:318-327) against the
+    oracle's restatement driven by the same Louvain specification: parents bit-exact, communities (incl. the -1 of
+    small clusters -> NaN scores) and labels identical, log p-values within 1e-4."""
+    from doubletdetection_b200 import BoostClassifier
+
+    counts = datasets.structured_counts(1500, 300, seed=1234)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(n_iters=3, random_state=0, n_jobs=2, **kwargs).fit(counts)
+        ora = reference_path.OracleClassifier(n_iters=3, random_state=0, louvain_fn=louvain_c.louvain,
+                                              clustering_algorithm="phenograph", **kwargs).fit(counts)
+        labels = clf.predict(p_thresh=1e-3, voter_thresh=0.5)
+        want = ora.predict(p_thresh=1e-3, voter_thresh=0.5)
+    assert clf.clustering_algorithm == "phenograph"
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    same = (clf.communities_ == ora.communities_).all(axis=1)
+    print(f"\n[phenograph {kwargs}] iterations with identical communities: {int(same.sum())}/{same.size}; "
+          f"cells labelled -1 in iteration 0: {int((clf.communities_[0] < 0).sum())}")
+    assert same.all()
+    np.testing.assert_array_equal(clf.synth_communities_, ora.synth_communities_)
+    np.testing.assert_array_equal(clf.all_scores_, ora.all_scores_)
+    np.testing.assert_allclose(clf.all_log_p_values_, ora.all_log_p_values_, rtol=1e-4, atol=1e-12)
+    np.testing.assert_array_equal(labels, want)
+    np.testing.assert_allclose(np.ma.filled(np.ma.asarray(clf.doublet_score(), dtype=np.float64), np.nan),
+                               np.ma.filled(np.ma.asarray(ora.doublet_score(), dtype=np.float64), np.nan), rtol=1e-4)
+
+
+def test_default_constructor_fits():
+    """README usage of the reference (README.md:37-44): BoostClassifier() with every default, then predict."""
+    from doubletdetection_b200 import BoostClassifier
+
+    counts = datasets.structured_counts(1200, 250, seed=99)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier()
+        labels = clf.fit(counts).predict()
+    assert labels.shape == (1200,) and clf.all_scores_.shape == (10, 1200)
+    assert np.isin(labels[~np.isnan(labels)], (0.0, 1.0)).all()

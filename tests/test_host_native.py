@@ -143,3 +143,23 @@ def test_louvain_and_score_on_golden_knn(native):
     s, lp = native.score(labels, n_cells)
     np.testing.assert_array_equal(s, g["all_scores"][0])
     np.testing.assert_allclose(lp, g["all_log_p_values"][0], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("prune", [True, False])
+def test_phenograph_host_twin_matches_oracle(native, prune):
+    """dd_phenograph_knn (the host twin of the device graph + the weighted Louvain the fit loop runs) against the
+    oracle's restatement of phenograph.cluster (oracle/upstream.py) on the same exact kNN lists."""
+    from oracle import louvain_c, upstream
+
+    rs = np.random.default_rng(3)
+    for case, (sizes, dim, spread) in enumerate([((150, 150, 150, 150), 12, 4.0), ((300, 40, 9, 200), 8, 6.0)]):
+        x = np.vstack([rs.normal(spread * c, 1.0, (m, dim)) for c, m in enumerate(sizes)]).astype(np.float32)
+        idx, _ = upstream.knn_brute(x, 31)
+        want, graph = upstream.phenograph_cluster(x, k=30, prune=prune, min_cluster_size=10, seed=case,
+                                                  louvain_fn=louvain_c.louvain)
+        got = native.phenograph_knn(idx, prune=prune, min_cluster_size=10, seed=case)
+        np.testing.assert_array_equal(got, want)
+        assert graph.nnz > 0 and (abs(graph - graph.T)).nnz == 0  # the Jaccard graph is symmetric
+    # a larger min_cluster_size sends more cells to -1 (NaN scores downstream, doubletdetection.py:379-381)
+    many = native.phenograph_knn(idx, prune=prune, min_cluster_size=100, seed=1)
+    assert (many == -1).sum() >= (got == -1).sum()
