@@ -458,9 +458,17 @@ def test_jaccard_graph_on_device_matches_oracle(handle, prune):
     handle.upload_embedding(emb)
     idx, _ = handle.knn(31)
     want_idx, _ = upstream.knn_brute(emb, 31)
-    np.testing.assert_array_equal(idx, want_idx)
+    # sklearn's brute kNN ranks by ||x||^2 - 2 x.y + ||y||^2 (rounded), the GPU re-ranks by the exact float64
+    # distance: the lists may differ where two neighbours are equidistant to ~1e-7 -- and nowhere else
+    bad = np.argwhere(idx != want_idx)
+    assert len(bad) <= 10
+    e64 = emb.astype(np.float64)
+    for r, c in bad:
+        d_gpu = np.linalg.norm(e64[r] - e64[idx[r, c]])
+        d_ref = np.linalg.norm(e64[r] - e64[want_idx[r, c]])
+        assert abs(d_gpu - d_ref) <= 1e-6 * d_ref
     got = handle.jaccard_graph(31, prune=prune)
-    want = upstream.jaccard_graph(want_idx[:, 1:], prune=prune)
+    want = upstream.jaccard_graph(idx[:, 1:], prune=prune)
     np.testing.assert_array_equal(got.indptr, want.indptr)
     np.testing.assert_array_equal(got.indices, want.indices)
     np.testing.assert_array_equal(got.data, want.data)
