@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) k_dense_rows_l2(const int32_t *__restrict
                                                        const double *__restrict__ l1_rows,
                                                        const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
                                                        int64_t m0, int64_t m_loc, int n_genes, int ld, float median,
-                                                       float pc, float *__restrict__ dense, int dbg) {
+                                                       float pc, float *__restrict__ dense) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -349,7 +349,6 @@ __global__ void __launch_bounds__(256) k_dense_rows_l2(const int32_t *__restrict
             l1 = __ldg(l1_rows + pa) + __ldg(l1_rows + pb);  // non-negative counts: |a + b| = |a| + |b|, exact
         }
         // (1) constant fill, pad columns zero
-        if (!(dbg & 1))
         for (int j = 4 * lane; j < ld; j += 128) {
             float4 v;
             v.x = j < n_genes ? logpc : 0.f;
@@ -359,7 +358,6 @@ __global__ void __launch_bounds__(256) k_dense_rows_l2(const int32_t *__restrict
             *reinterpret_cast<float4 *>(out_row + j) = v;
         }
         __syncwarp();
-        if (dbg & 2) continue;
         if (!synth) {
 #pragma unroll 4
             for (int p = sa + lane; p < ea; p += 32) {
@@ -596,12 +594,13 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
     if ((variant != 0 && h->nonneg && h->G < (int64_t)kTagPayload) || sharded) {
         if (!h->nonneg || h->G >= (int64_t)kTagPayload)
             return dd_fail(h, DD_ERR_UNSUPPORTED, "normalise: cell-block sharding needs non-negative counts");
-        static const int warps_per_sm = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 48;
+        // 48 registers x 256 threads: five CTAs fit an SM; four (32 warps) keep the grid a single full wave and the rows in
+        // flight (32 warps x 148 SMs x 12 KB = 57 MB at 3k genes) inside the 126 MB L2
+        static const int warps_per_sm = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 32;
         const int grid = h->num_sms * std::max(1, warps_per_sm / 8);
-        static const int dbg = getenv("DD_DENSE_DBG") ? atoi(getenv("DD_DENSE_DBG")) : 0;  // 1: no fill, 2: no scatter (timing experiments)
         DD_LAUNCH(h, "dense_rows", k_dense_rows_l2, grid, 256, 0, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
                   h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median, pseudocount,
-                  h->d_dense, dbg);
+                  h->d_dense);
     } else {
         const int chunk = pick_dense_chunk(h->ld);
         const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
