@@ -473,9 +473,9 @@ __device__ __forceinline__ void reglist_insert(RegList<N> &L, float t, int idx) 
 // 2048 cycles, against ~900 cycles of tensor-core time for the step's 14 MMAs.  Neither more epilogue warps (16 warps
 // with per-half lists: 7.1 ms) nor cheaper list maintenance (pending slots merged in lockstep: 5.9-7.4 ms) beat the
 // 8-warp peel-and-insert epilogue below (5.25 ms at c3, 3.4 ms TMEM-read floor, 4.1 ms with the 3.3 -> 4 wave rounding).
-constexpr int LIST = 16;   // candidates kept per query row
 constexpr int THREADS = 320;  // producer warp + MMA warp + 8 epilogue warps
 
+template <int LIST>  // candidates kept per query row: 16 (k <= 13, sc.pp.neighbors) or 32 (k <= 31, PhenoGraph)
 __global__ void __launch_bounds__(THREADS, 1)
     k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb, int64_t n, int n_tiles, int pair0,
              int *__restrict__ cand_i) {
@@ -649,7 +649,7 @@ int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     return DD_OK;
 }
 
-int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
+int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     const int64_t n = h->emb_rows;
     const int n_tiles = (int)((n + tc::TILE - 1) / tc::TILE);
     const int n_tiles_pad = (n_tiles + tc::QT - 1) / tc::QT * tc::QT;
@@ -659,7 +659,8 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
     uint8_t *qa = h->d_knn_ops, *cb = h->d_knn_ops + op_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(tc::k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         attr_set = true;
     }
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
@@ -672,10 +673,17 @@ int run_knn_tc(dd_handle *h, int k, float *cand_t, int *cand_i) {
     const int64_t q0 = std::min<int64_t>(n, (int64_t)pair0 * tc::QT * tc::TILE);
     const int64_t q1 = std::min<int64_t>(n, (int64_t)pair1 * tc::QT * tc::TILE);
     if (pair1 > pair0) {
-        DD_LAUNCH(h, "knn_tc", tc::k_knn_tc, (unsigned)(pair1 - pair0), tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0,
-                  cand_i);
-        DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1, k,
-                  h->d_knn_idx, h->d_knn_dist);
+        if (TL == 16) {
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, (unsigned)(pair1 - pair0), tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
+                      pair0, cand_i);
+            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
+                      k, h->d_knn_idx, h->d_knn_dist);
+        } else {
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<32>, (unsigned)(pair1 - pair0), tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
+                      pair0, cand_i);
+            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
+                      k, h->d_knn_idx, h->d_knn_dist);
+        }
     }
     if (W > 1) {
         std::vector<int64_t> begin(W), count(W);
@@ -716,8 +724,8 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     int *cand_i = reinterpret_cast<int *>(cand_d + n_padded * 32);
     // default: tcgen05 distance GEMM; DD_KNN_FFMA=1 keeps the CUDA-core kernel (A/B comparison, KP=64, k>13)
     static const bool force_ffma = getenv("DD_KNN_FFMA") != nullptr;
-    if (h->KP == 32 && TL == 16 && !force_ffma) return run_knn_tc(h, k, cand_d, cand_i);
-    if (dd_sharded(h)) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: cell-block sharding needs the tcgen05 path (k <= 13, <= 32 components)");
+    if (h->KP == 32 && !force_ffma) return run_knn_tc(h, k, TL, cand_d, cand_i);
+    if (dd_sharded(h)) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: cell-block sharding needs the tcgen05 path (<= 32 components)");
     if (h->KP == 32)
         return TL == 16 ? run_knn<32, 16>(h, k, norms, cand_d, cand_i) : run_knn<32, 32>(h, k, norms, cand_d, cand_i);
     return TL == 16 ? run_knn<64, 16>(h, k, norms, cand_d, cand_i) : run_knn<64, 32>(h, k, norms, cand_d, cand_i);
