@@ -33,7 +33,10 @@ struct dd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // clustering (first Louvain level + result copies) overlaps the next iteration
-    cudaEvent_t ev_knn_done = nullptr, ev_lv_done = nullptr;
+    cudaStream_t stream3 = nullptr;  // dense build of the next iteration, underneath this iteration's PCA tail and kNN
+    cudaEvent_t ev_dense_done = nullptr, ev_gemms_done = nullptr;
+    bool gemms_done_recorded = false;  // run_pca recorded ev_gemms_done right after its last pass over the matrix
+    cudaEvent_t ev_knn_done = nullptr, ev_lv_done = nullptr, ev_lv_done2 = nullptr;  // lv_done per kNN list buffer
     int num_sms = 148;
     std::string err;
 
@@ -92,7 +95,9 @@ struct dd_handle {
     int64_t cap_emb = 0;
 
     // ---- kNN outputs ----
-    int32_t *d_knn_idx = nullptr;
+    int32_t *d_knn_idx = nullptr;       // the list buffer in use: d_knn_idx_base + {0, knn_idx_stride}
+    int32_t *d_knn_idx_base = nullptr;  // two buffers (dd_knn_flip): clustering of iteration i overlaps the kNN of i + 1
+    int64_t knn_idx_stride = 0;
     float *d_knn_dist = nullptr;
     int64_t cap_knn = 0;
     uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout

@@ -30,7 +30,7 @@ struct Job {
     int slot;
 };
 
-constexpr int kStages = 6;  // doublets+normalise, scale, pca, knn, d2h  (index 0 unused in the fused build)
+constexpr int kStages = 7;  // events: build begin/end (build stream), pca begin/end, knn end, cluster end, scale begin
 
 }  // namespace
 
@@ -176,11 +176,34 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
 
     // ---- GPU producer
-    std::vector<float> aug((size_t)A);
+    // Three streams: the dense build of iteration i + 1 (HBM-bound, no shared memory / TMEM) runs on the build stream as
+    // soon as the last PCA product of iteration i has read the matrix, i.e. underneath iteration i's small PCA kernels and
+    // its TMEM-bound kNN; the clustering of iteration i runs on the clustering stream underneath iteration i + 1.
+    std::vector<float> aug((size_t)A), tmp;
     bool omega_sent = false;
     int issued = 0;
-    for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && worker_rc.load() == DD_OK; it++, issued++) {
+    auto issue_dense = [&](int it, cudaEvent_t *ev, bool wait_gemms) -> int {
         const int64_t *par = M > 0 ? parents + (size_t)it * M * 2 : nullptr;
+        // np.median(aug_lib_size): synthetic library sizes are the parents' sums (exact for counts)
+        std::copy(h->h_lib.begin(), h->h_lib.end(), aug.begin());
+        for (int64_t r = 0; r < M; r++) aug[N + r] = h->h_lib[par[2 * r]] + h->h_lib[par[2 * r + 1]];
+        tmp = aug;
+        const float median = dd_host_median(tmp);
+        cudaStream_t main_stream = h->stream;
+        h->stream = h->stream3;
+        if (wait_gemms) cudaStreamWaitEvent(h->stream3, h->ev_gemms_done, 0);  // the previous PCA still reads the matrix
+        int r = dd_set_parents(h, M, par);
+        if (r == DD_OK) {
+            cudaEventRecord(ev[0], h->stream3);
+            r = dd_dev_build_dense(h, median, p->pseudocount);
+            cudaEventRecord(ev[1], h->stream3);
+            cudaEventRecord(h->ev_dense_done, h->stream3);
+        }
+        h->stream = main_stream;
+        return r;
+    };
+    rc = issue_dense(p->iter_begin, &evs[0], false);
+    for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && worker_rc.load() == DD_OK; it++, issued++) {
         int slot;
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -190,24 +213,23 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         }
         Slot &s = slots[slot];
         cudaEvent_t *ev = &evs[(size_t)issued * kStages];
-        rc = dd_set_parents(h, M, par);
-        if (rc != DD_OK) break;
-        // np.median(aug_lib_size): synthetic library sizes are the parents' sums (exact for counts)
-        std::copy(h->h_lib.begin(), h->h_lib.end(), aug.begin());
-        for (int64_t r = 0; r < M; r++) aug[N + r] = h->h_lib[par[2 * r]] + h->h_lib[par[2 * r + 1]];
-        std::vector<float> tmp(aug);
-        const float median = dd_host_median(tmp);
-
-        cudaEventRecord(ev[0], h->stream);
-        if ((rc = dd_dev_build_dense(h, median, p->pseudocount)) != DD_OK) break;
-        cudaEventRecord(ev[1], h->stream);
+        cudaStreamWaitEvent(h->stream, h->ev_dense_done, 0);
+        cudaEventRecord(ev[6], h->stream);
         if (p->standard_scaling && (rc = dd_dev_standard_scale(h, p->scale_max_value)) != DD_OK) break;
         cudaEventRecord(ev[2], h->stream);
+        h->gemms_done_recorded = false;
         if ((rc = dd_dev_pca(h, p->n_comp, p->n_random, p->n_power_iter, omega_sent ? nullptr : omega)) != DD_OK) break;
+        if (!h->gemms_done_recorded) cudaEventRecord(h->ev_gemms_done, h->stream);
         omega_sent = true;
         cudaEventRecord(ev[3], h->stream);
-        if (issued > 0) cudaStreamWaitEvent(h->stream, h->ev_lv_done, 0);  // previous graph build has read d_knn_idx
+        // The kNN lists are double-buffered: this iteration writes buffer (issued & 1), which the clustering stream
+        // finished reading two iterations ago -- so the kNN never waits for the previous iteration's Louvain level.
+        cudaEvent_t lv_done = (issued & 1) ? h->ev_lv_done2 : h->ev_lv_done;
+        if (issued > 1) cudaStreamWaitEvent(h->stream, lv_done, 0);
+        if (h->d_knn_idx_base) h->d_knn_idx = h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride;
         if ((rc = dd_dev_knn(h, k)) != DD_OK) break;
+        if (h->d_knn_idx != h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride)  // first call allocated the buffers
+            h->d_knn_idx = h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride;
         cudaEventRecord(ev[4], h->stream);
         dd_pca_flag_copy(h, s.flag);
         // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device.
@@ -228,13 +250,14 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         if (pheno)
             cudaMemcpyAsync(s.graph + w_off, h->d_lv_w, sizeof(double) * max_nnz, cudaMemcpyDeviceToHost, h->stream2);
         cudaEventRecord(ev[5], h->stream2);
-        cudaEventRecord(h->ev_lv_done, h->stream2);
+        cudaEventRecord(lv_done, h->stream2);
         cudaEventRecord(s.done, h->stream2);
         {
             std::lock_guard<std::mutex> lk(mu);
             jobs.push_back(Job{it, slot});
         }
         cv_job.notify_one();
+        if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
     }
     {
         std::lock_guard<std::mutex> lk(mu);
@@ -244,6 +267,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     for (std::thread &t : pool) t.join();
     cudaError_t ce = cudaStreamSynchronize(h->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream2);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream3);
     if (rc == DD_OK && ce != cudaSuccess) rc = dd_fail(h, DD_ERR_CUDA, std::string("dd_fit_iterations: ") + cudaGetErrorString(ce));
     if (rc == DD_OK && worker_rc.load() != DD_OK) rc = dd_fail(h, worker_rc.load(), worker_err);
     if (rc == DD_OK && stage_ms_out) {
@@ -252,7 +276,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             float ms;
             // {doublets, normalise, scale, pca, knn, d2h}: the fused build is booked under "normalise"
             if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) stage_ms_out[1] += ms;
-            if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) stage_ms_out[2] += ms;
+            if (cudaEventElapsedTime(&ms, ev[6], ev[2]) == cudaSuccess) stage_ms_out[2] += ms;
             if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) stage_ms_out[3] += ms;
             if (cudaEventElapsedTime(&ms, ev[3], ev[4]) == cudaSuccess) stage_ms_out[4] += ms;
             if (cudaEventElapsedTime(&ms, ev[4], ev[5]) == cudaSuccess) stage_ms_out[5] += ms;

@@ -50,6 +50,7 @@ static void resolve_pending(dd_handle *h) {
     if (h->pending.empty()) return;
     cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->stream3) cudaStreamSynchronize(h->stream3);
     for (dd_timed_launch &t : h->pending) {
         float ms = 0.f;
         if (t.name && cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
@@ -100,10 +101,18 @@ extern "C" int dd_create(int device, dd_handle **out) {
     dd_handle *h = new dd_handle();
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+    // the clustering stream runs hundreds of tiny latency-bound kernels next to the main stream's HBM-bound ones: at the
+    // highest priority its CTAs are placed first whenever an SM frees resources, so it keeps pace with the main stream
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_dense_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_gemms_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_knn_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_lv_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_lv_done2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaEventCreate(&h->stage_ev0) != cudaSuccess || cudaEventCreate(&h->stage_ev1) != cudaSuccess) {
         delete h;
@@ -120,7 +129,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     void *bufs[] = {h->d_indptr, h->d_indices, h->d_data,   h->d_lib,   h->d_l1,      h->d_parents, h->d_sindptr,
                     h->d_scount, h->d_sindices, h->d_sdata, h->d_slib,  h->d_dense,   h->d_colsum,  h->d_colsumsq,
-                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx, h->d_knn_dist, h->d_knn_ops, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w};
+                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx_base, h->d_knn_dist, h->d_knn_ops, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w};
     for (void *p : bufs)
         if (p) cudaFree(p);
     dd_tc_free(h);
@@ -136,6 +145,10 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (h->stage_ev1) cudaEventDestroy(h->stage_ev1);
     if (h->ev_knn_done) cudaEventDestroy(h->ev_knn_done);
     if (h->ev_lv_done) cudaEventDestroy(h->ev_lv_done);
+    if (h->ev_lv_done2) cudaEventDestroy(h->ev_lv_done2);
+    if (h->ev_dense_done) cudaEventDestroy(h->ev_dense_done);
+    if (h->ev_gemms_done) cudaEventDestroy(h->ev_gemms_done);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

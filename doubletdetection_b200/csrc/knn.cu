@@ -712,12 +712,15 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     const int64_t n_padded = (n + 255) / 256 * 256;  // the tensor-core path keeps lists for whole 256-row CTAs
     const int64_t need = n * k + n + 2 * n_padded * 32;
     if (need > h->cap_knn) {
-        if (h->d_knn_idx) cudaFree(h->d_knn_idx);
+        if (h->d_knn_idx_base) cudaFree(h->d_knn_idx_base);
         if (h->d_knn_dist) cudaFree(h->d_knn_dist);
-        h->d_knn_idx = nullptr; h->d_knn_dist = nullptr; h->cap_knn = 0;
-        DD_CUDA(h, cudaMalloc(&h->d_knn_idx, sizeof(int32_t) * n * 32));
+        h->d_knn_idx_base = h->d_knn_idx = nullptr; h->d_knn_dist = nullptr; h->cap_knn = 0;
+        // two list buffers: the clustering stream still reads iteration i's lists while iteration i + 1 writes its own
+        DD_CUDA(h, cudaMalloc(&h->d_knn_idx_base, sizeof(int32_t) * 2 * n * 32));
         DD_CUDA(h, cudaMalloc(&h->d_knn_dist, sizeof(float) * need));
         h->cap_knn = need;
+        h->knn_idx_stride = n * 32;
+        h->d_knn_idx = h->d_knn_idx_base;
     }
     float *norms = h->d_knn_dist + n * k;
     float *cand_d = norms + n;

@@ -638,6 +638,10 @@ int run_pca(dd_handle *h, int n_power_iter) {
                 DD_CUDA(h, cudaMemsetAsync(sm + OFF_SSUM, 0, sizeof(double) * kMaxLP, h->stream));  // no mu (x) s term
             }
             DD_TRY(dd_tc_gemm_dty(h));
+            if (last && h->ev_gemms_done) {  // last pass over the dense matrix: the next iteration's build may overwrite it
+                DD_CUDA(h, cudaEventRecord(h->ev_gemms_done, h->stream));
+                h->gemms_done_recorded = true;
+            }
             DD_TRY(dd_comm_allreduce_f64(h, h->d_Zacc, (int64_t)ld * LP));
             DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
             DD_LAUNCH(h, "gram_small", (k_gram<LP, 1>), std::min<int>(tall_grid, (ld + GR_ROWS - 1) / GR_ROWS), 256, 0, nullptr,
