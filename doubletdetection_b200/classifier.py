@@ -252,7 +252,7 @@ class BoostClassifier:
         _t.append(_time.perf_counter())
 
         it0, it1 = 0, self.n_iters
-        dist = None
+        dist = cells_dist = None
         if self.distributed:
             import torch.distributed as dist_mod
 
@@ -265,7 +265,7 @@ class BoostClassifier:
                         h.comm_init(rank, world, token)
                         h._comm_ready = True
                     h.shard_cells(True)
-                    dist = None  # every rank runs every iteration and holds the complete results
+                    cells_dist, dist = dist, None  # every rank takes part in every iteration; results merged below
                 else:
                     it0, it1 = iteration_shard(self.n_iters, rank, world)
         if self.distributed != "cells" and getattr(h, "_comm_ready", False):
@@ -282,6 +282,8 @@ class BoostClassifier:
         _t.append(_time.perf_counter())
         if dist is not None:
             out = _allgather_iterations(dist, out, self.n_iters, self.device, everywhere=self.distributed == "allgather")
+        if cells_dist is not None:
+            out = merge_owned_iterations(cells_dist, out, self.device)
         self.stage_ms_ = out["stage_ms"]
 
         self.all_scores_ = out["scores"]
@@ -340,6 +342,27 @@ def broadcast_token(dist, token, device):
     buf = buf.to(dev)
     dist.broadcast(buf, src=0)
     return bytes(buf.cpu().numpy().tobytes())
+
+
+def merge_owned_iterations(dist, out, device):
+    """Cell-block sharding: the library clusters + scores iteration i on rank i % world and leaves the other ranks'
+    rows zero.  An integer SUM of the bit patterns over the ranks therefore reproduces every row exactly (NaN and
+    -inf included) on every rank."""
+    import torch
+
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    merged = {}
+    for key in ("scores", "log_p", "communities", "synth_communities"):
+        a = np.ascontiguousarray(out[key])
+        bits = a.view(np.int64) if a.dtype == np.float64 else a.astype(np.int32)
+        t = torch.from_numpy(bits.copy()).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r = t.cpu().numpy()
+        merged[key] = r.view(np.float64) if a.dtype == np.float64 else r
+    stage = torch.tensor([out["stage_ms"][k] for k in sorted(out["stage_ms"])], dtype=torch.float64, device=dev)
+    dist.all_reduce(stage, op=dist.ReduceOp.MAX)
+    merged["stage_ms"] = dict(zip(sorted(out["stage_ms"]), stage.cpu().tolist()))
+    return merged
 
 
 def iteration_shard(n_iters, rank, world):

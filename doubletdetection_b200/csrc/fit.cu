@@ -204,14 +204,17 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     };
     rc = issue_dense(p->iter_begin, &evs[0], false);
     for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && worker_rc.load() == DD_OK; it++, issued++) {
-        int slot;
-        {
+        // Cell-block sharding: every rank holds the all-gathered kNN lists of every iteration, so the clustering + scoring
+        // of the iterations is dealt round-robin to the ranks (rank it % world finishes iteration it; the caller merges the
+        // per-iteration result rows, which stay zero on the other ranks).
+        const bool cluster_here = !dd_sharded(h) || (it % h->world) == h->rank;
+        int slot = -1;
+        if (cluster_here) {
             std::unique_lock<std::mutex> lk(mu);
             cv_slot.wait(lk, [&] { return !free_slots.empty(); });
             slot = free_slots.front();
             free_slots.pop_front();
         }
-        Slot &s = slots[slot];
         cudaEvent_t *ev = &evs[(size_t)issued * kStages];
         cudaStreamWaitEvent(h->stream, h->ev_dense_done, 0);
         cudaEventRecord(ev[6], h->stream);
@@ -231,6 +234,12 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         if (h->d_knn_idx != h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride)  // first call allocated the buffers
             h->d_knn_idx = h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride;
         cudaEventRecord(ev[4], h->stream);
+        if (!cluster_here) {
+            cudaEventRecord(ev[5], h->stream);
+            if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
+            continue;
+        }
+        Slot &s = slots[slot];
         dd_pca_flag_copy(h, s.flag);
         // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device.
         // These are hundreds of small latency-bound kernels: they run on a second stream and overlap the

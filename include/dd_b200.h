@@ -180,7 +180,9 @@ int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int64_t *paren
  * factorises only its block of rows.  Sums over cells (column means, D^T Y, the Gram matrix of the tall panel)
  * are NCCL all-reduces, the n_comp-dimensional embedding is all-gathered (the single exchange kNN needs), each
  * rank answers the kNN queries of its share of rows against all cells and the lists are all-gathered; the
- * clustering + scoring of an iteration then runs replicated, so every rank returns the full result arrays.
+ * clustering + scoring of iteration i then runs on rank i % world only: dd_fit_iterations fills the result rows of
+ * the iterations a rank owns and leaves the others zero (the caller merges them, e.g. by an integer sum of the
+ * bit patterns over the ranks).
  * NCCL is resolved at run time from the process (libnccl.so.2; env DD_NCCL_LIB overrides the path).
  *   dd_comm_unique_id   rank 0 creates the rendezvous token (DD_COMM_ID_BYTES bytes) and ships it to the
  *                       other ranks by any host channel (the Python shim uses torch.distributed.broadcast)

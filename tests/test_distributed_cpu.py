@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from doubletdetection_b200 import _capi, iteration_shard
-from doubletdetection_b200.classifier import _allgather_iterations, broadcast_token
+from doubletdetection_b200.classifier import _allgather_iterations, broadcast_token, merge_owned_iterations
 
 
 def _free_port():
@@ -106,3 +106,45 @@ def test_cell_blocks_partition_rows():
         assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
         sizes = [e - b for b, e in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _merge_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_iters, n_cells, n_synth = 5, 30, 7
+        rs = np.random.default_rng(11)
+        truth = dict(scores=rs.random((n_iters, n_cells)), log_p=-rs.random((n_iters, n_cells)) * 50,
+                     communities=rs.integers(-1, 20, (n_iters, n_cells)).astype(np.int32),
+                     synth_communities=rs.integers(-1, 20, (n_iters, n_synth)).astype(np.int32))
+        truth["log_p"][0, 1] = -np.inf
+        truth["log_p"][3, 2] = np.nan
+        truth["scores"][3, 2] = np.nan
+        mine = {k: np.zeros_like(v) for k, v in truth.items()}
+        for it in range(n_iters):  # the library fills iteration i on rank i % world only
+            if it % world == rank:
+                for k in truth:
+                    mine[k][it] = truth[k][it]
+        mine["stage_ms"] = {"pca": 2.0 + rank, "knn": 1.0}
+        merged = merge_owned_iterations(dist, mine, device=0)
+        ok = all(np.array_equal(merged[k], truth[k], equal_nan=True) for k in truth)
+        ok = ok and merged["stage_ms"] == {"knn": 1.0, "pca": 1.0 + world}
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_cell_sharding_result_merge_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_merge_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(results) == [(0, True), (1, True)]
