@@ -268,8 +268,11 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int n_b
     __syncthreads();
 }
 
-constexpr int kRoundThreads = 1024;
-constexpr size_t kRoundSmem = sizeof(int32_t) * (kRoundThreads / 32) * 2 * kTable;  // 128 KB
+// kRoundThreads = 1024 (128 KB of tables): one CTA per SM on an otherwise idle GPU.  256 (32 KB): a light resident
+// grid that fits NEXT TO the main stream's kernels on the same SMs (the kNN CTA leaves 54 KB / 27 k registers free).
+template <int kRoundThreads>
+constexpr size_t round_smem() { return sizeof(int32_t) * (kRoundThreads / 32) * 2 * kTable; }
+template <int kRoundThreads>
 __global__ void __launch_bounds__(kRoundThreads, 1) k_lv_rounds(const int32_t *__restrict__ off,
                                                                const int32_t *__restrict__ adj, int32_t *comm,
                                                                double *tot, int32_t *csize,
@@ -441,12 +444,16 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
     // but as ordinary kernels on the clustering stream they share the SMs with the HBM-bound kernels of the next
     // iteration.  DD_LOUVAIN_COOP=1: all rounds in ONE cooperative launch (one CTA per SM, hand-written grid
     // barrier) -- fewer launches, but it monopolises the SMs.
-    static const bool use_graph = getenv("DD_LOUVAIN_COOP") == nullptr;
-    if (!use_graph) {
-        const int blocks_per_sm = 1;
+    // DD_LOUVAIN_COOP=2: the same single launch as a LIGHT resident grid (256 threads, 32 KB per CTA, DD_LOUVAIN_COOP_CTAS
+    // CTAs, default 128) that fits next to the main stream's CTAs on the same SMs instead of queueing ~300 tiny kernels
+    // behind them.
+    static const int coop = getenv("DD_LOUVAIN_COOP") ? atoi(getenv("DD_LOUVAIN_COOP")) : 0;
+    if (coop != 0) {
+        static const int light_ctas = getenv("DD_LOUVAIN_COOP_CTAS") ? atoi(getenv("DD_LOUVAIN_COOP_CTAS")) : 128;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(k_lv_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRoundSmem);
+            cudaFuncSetAttribute(k_lv_rounds<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<1024>());
+            cudaFuncSetAttribute(k_lv_rounds<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<256>());
             attr_set = true;
         }
         ColourOffsets co;
@@ -458,8 +465,13 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         double *tot_p = h->d_lv_tot;
         void *args[] = {&off_p, &adj_p, &comm_p, &tot_p, &csize_p, &bucket_p, &co, &n_arg, &g_arg, &desired_p, &counters_p};
         dd_launch_begin(h);
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_lv_rounds, dim3(h->num_sms * blocks_per_sm), dim3(kRoundThreads),
-                                                    args, kRoundSmem, h->stream);
+        cudaError_t e;
+        if (coop == 1)
+            e = cudaLaunchCooperativeKernel((const void *)k_lv_rounds<1024>, dim3(h->num_sms), dim3(1024), args,
+                                            round_smem<1024>(), h->stream);
+        else
+            e = cudaLaunchCooperativeKernel((const void *)k_lv_rounds<256>, dim3(std::max(1, std::min(light_ctas, h->num_sms))),
+                                            dim3(256), args, round_smem<256>(), h->stream);
         if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("cooperative launch of lv_rounds: ") + cudaGetErrorString(e));
         DD_TRY(dd_launch_end(h, "lv_rounds"));
         return DD_OK;
