@@ -478,7 +478,7 @@ constexpr int THREADS = 320;  // producer warp + MMA warp + 8 epilogue warps
 template <int LIST>  // candidates kept per query row: 16 (k <= 13, sc.pp.neighbors) or 32 (k <= 31, PhenoGraph)
 __global__ void __launch_bounds__(THREADS, 1)
     k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb, int64_t n, int n_tiles, int pair0,
-             int *__restrict__ cand_i) {
+             int n_full, int *__restrict__ cand_i) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                // QT tiles
     uint8_t *sB = smem + (size_t)QT * TILE_BYTES;      // NS stages
@@ -491,7 +491,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile0 = (blockIdx.x + pair0) * QT;  // pair0: first query-tile pair of this launch (cell-block sharding)
+    // pair0: first query-tile pair of this launch (cell-block sharding).  The first n_full CTAs own a pair of query tiles;
+    // the CTAs behind them own ONE tile each (half the work): the launch's last, partial wave is cut into half-size pieces
+    // so that it occupies twice as many SMs for half as long.
+    const bool half_cta = (int)blockIdx.x >= n_full;
+    const int n_qt = half_cta ? 1 : QT;
+    const int tile0 = half_cta ? (pair0 + n_full) * QT + ((int)blockIdx.x - n_full) : ((int)blockIdx.x + pair0) * QT;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(tfull + b, 1);
-            mbar_init(tempty + b, 256);
+            mbar_init(tempty + b, 128 * n_qt);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -513,8 +518,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(a_full, QT * TILE_BYTES);
-            for (int qt = 0; qt < QT; qt++)
+            mbar_expect_tx(a_full, n_qt * TILE_BYTES);
+            for (int qt = 0; qt < n_qt; qt++)
                 bulk_g2s(sA + (size_t)qt * TILE_BYTES, qa + (size_t)(tile0 + qt) * TILE_BYTES, TILE_BYTES, a_full);
             for (int step = 0; step < n_tiles; step++) {
                 const int s = step % NS;
@@ -541,6 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const uint64_t b_desc = make_desc(smem_u32(sB + (size_t)s * TILE_BYTES));
 #pragma unroll
                 for (int qt = 0; qt < QT; qt++) {
+                    if (qt >= n_qt) break;
                     const uint32_t d = tmem_base + buf * 256 + qt * 128;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++)
@@ -557,6 +563,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int quad = warp & 3;       // TMEM lane quadrant this warp may access (four consecutive e cover all)
         const int64_t qrow = (int64_t)(tile0 + qt) * TILE + quad * 32 + lane;
         const bool active = qrow < n;
+        const int my_tiles = qt < n_qt ? n_tiles : 0;  // the second tile's warps of a half CTA have nothing to do
         RegList<LIST> L;
 #pragma unroll
         for (int l = 0; l < LIST; l++) {
@@ -565,7 +572,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         float tau = active ? kEmptyT : INFINITY;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * 128;
-        for (int step = 0; step < n_tiles; step++) {
+        for (int step = 0; step < my_tiles; step++) {
             const int buf = step & 1;
             const uint32_t bph = (step >> 1) & 1;
             mbar_wait(tfull + buf, bph);
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             fence_before();
             mbar_arrive(tempty + buf);
         }
-        if (active) {
+        if (active && my_tiles > 0) {
 #pragma unroll
             for (int l = 0; l < LIST; l++) cand_i[qrow * LIST + l] = L.i[l];
         }
@@ -673,14 +680,17 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     const int64_t q0 = std::min<int64_t>(n, (int64_t)pair0 * tc::QT * tc::TILE);
     const int64_t q1 = std::min<int64_t>(n, (int64_t)pair1 * tc::QT * tc::TILE);
     if (pair1 > pair0) {
+        // whole waves of pair CTAs, then the remainder as single-tile CTAs (twice as many, half as long)
+        const int pairs = pair1 - pair0;
+        static const bool split_tail = getenv("DD_KNN_NO_TAIL_SPLIT") == nullptr;
+        const int n_full = split_tail ? pairs / h->num_sms * h->num_sms : pairs;
+        const unsigned grid = (unsigned)(n_full + (pairs - n_full) * tc::QT);
         if (TL == 16) {
-            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, (unsigned)(pair1 - pair0), tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
-                      pair0, cand_i);
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);
         } else {
-            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<32>, (unsigned)(pair1 - pair0), tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
-                      pair0, cand_i);
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<32>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);
         }

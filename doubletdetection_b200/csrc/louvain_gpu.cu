@@ -115,7 +115,8 @@ __global__ void k_graph_fill(const int32_t *__restrict__ knn, int n, int k, cons
 
 // per-warp open-addressing table (community -> number of neighbours in it) for nodes with more than 32
 // neighbours; kTable slots, linear probing.  Degrees above kTableMaxDeg fall back to a quadratic scan.
-constexpr int kTable = 512, kTableMaxDeg = 384;
+// 256 slots = 2 KB per warp, 16 KB per propose CTA: three of them fit next to a kNN CTA's 173 KB of shared memory.
+constexpr int kTable = 256, kTableMaxDeg = 192, kTableShift = 24;  // hash = top 8 bits
 __device__ __forceinline__ int propose_one(const int32_t *__restrict__ off, const int32_t *__restrict__ adj,
                                            const int32_t *comm, const double *tot, const int32_t *csize, int i,
                                            double gamma, double two_m, int32_t *tkey, int32_t *tcnt, int lane) {
@@ -144,7 +145,7 @@ __device__ __forceinline__ int propose_one(const int32_t *__restrict__ off, cons
         __syncwarp();
         for (int f = lane; f < d; f += 32) {
             const int c = __ldcg(comm + adj[s + f]);
-            unsigned slot = ((unsigned)c * 2654435761u) >> 23;  // 9 bits
+            unsigned slot = ((unsigned)c * 2654435761u) >> kTableShift;
             for (;;) {
                 const int prev = atomicCAS(tkey + slot, -1, c);
                 if (prev == -1 || prev == c) break;
@@ -268,7 +269,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int n_b
     __syncthreads();
 }
 
-// kRoundThreads = 1024 (128 KB of tables): one CTA per SM on an otherwise idle GPU.  256 (32 KB): a light resident
+// kRoundThreads = 1024 (64 KB of tables): one CTA per SM on an otherwise idle GPU.  256 (16 KB): a light resident
 // grid that fits NEXT TO the main stream's kernels on the same SMs (the kNN CTA leaves 54 KB / 27 k registers free).
 template <int kRoundThreads>
 constexpr size_t round_smem() { return sizeof(int32_t) * (kRoundThreads / 32) * 2 * kTable; }
