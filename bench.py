@@ -277,8 +277,8 @@ def kernel_rooflines(report, n_cells, n_synth, n_genes, nnz_orig, nnz_parents_pe
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of workload c3
-# (profiles/r1n_ncu_full_summary.md); None where no capture exists
-NCU_TRAFFIC_C3 = {"tc_gemm_dq": 1.544e9, "tc_gemm_dty": 1.561e9, "knn_tc": 5.6e7, "dense_rows": 2.642e9}
+# (profiles/r1n_ncu_full_summary.md, profiles/r1t_ncu_full_summary.md); None where no capture exists
+NCU_TRAFFIC_C3 = {"tc_gemm_dq": 1.544e9, "tc_gemm_dty": 1.561e9, "knn_tc": 5.6e7, "dense_rows": 2.431e9}
 
 
 def load_peaks():
