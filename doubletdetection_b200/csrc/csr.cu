@@ -390,6 +390,370 @@ __global__ void __launch_bounds__(256) k_dense_rows_l2(const int32_t *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dense rows with the CSR segments STAGED BY THE TMA ENGINE (DD_DENSE_V=2).  Same row algorithm as k_dense_rows_l2
+// (constant fill + scatter through L2, synthetic rows merged through the row), but the gathers that bound that
+// kernel are taken off the warps: every warp owns a ring of kTmaDepth row slots in shared memory, lane 0 issues
+// cp.async.bulk copies of the next rows' index / value segments (whole 16-byte groups around the segment) completing on
+// one mbarrier per slot, and the warp only ever waits for data that was requested kTmaDepth rows earlier.  Few warps
+// (8 per SM) keep ~60 KB of CSR reads in flight per SM; rows whose segments exceed a slot fall back to direct loads.
+constexpr int kTmaWarps = 8, kTmaDepth = 3, kTmaSeg = 520;                  // entries per staged segment (16-byte multiple)
+constexpr int kTmaSlotBytes = 4 * kTmaSeg * 4;                               // idx a | val a | idx b | val b
+constexpr int kTmaWarpBytes = kTmaDepth * kTmaSlotBytes;
+struct TmaRowDesc {
+    double l1;
+    long long row;        // local output row
+    int sa, na, sb, nb;   // global start / length of the (one or two) source segments
+    int oa, ob;           // offset of the first real entry inside the staged groups
+    int staged, synth;
+};
+constexpr int kTmaTable = 64;  // row descriptors per warp: two halves of 32, refilled by all lanes together
+constexpr size_t kTmaSmemBytes =
+    (size_t)kTmaWarps * kTmaWarpBytes + (size_t)kTmaWarps * kTmaTable * sizeof(TmaRowDesc) + kTmaWarps * kTmaDepth * 8 + 64;
+
+__device__ __forceinline__ uint32_t csr_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void csr_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(csr_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void csr_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(csr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void csr_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = csr_smem_u32(bar);
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void csr_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     csr_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(csr_smem_u32(bar))
+                 : "memory");
+}
+
+// one row from (index, value) lists that live in shared memory (staged) or in global memory (fallback)
+__device__ __forceinline__ void dense_row_from_lists(const int32_t *ia, const float *da, int na, const int32_t *ib,
+                                                     const float *db, int nb, bool synth, double l1, float median, float pc,
+                                                     float logpc, int n_genes, int ld, float *out_row, int lane, int dbg = 0) {
+    if (!(dbg & 1))  // timing experiments only (DD_DENSE_DBG): 1 = no fill, 2 = no scatter
+    for (int j = 4 * lane; j < ld; j += 128) {
+        float4 v;
+        v.x = j < n_genes ? logpc : 0.f;
+        v.y = j + 1 < n_genes ? logpc : 0.f;
+        v.z = j + 2 < n_genes ? logpc : 0.f;
+        v.w = j + 3 < n_genes ? logpc : 0.f;
+        *reinterpret_cast<float4 *>(out_row + j) = v;
+    }
+    __syncwarp();
+    if (dbg & 2) return;
+    if (!synth) {
+#pragma unroll 4
+        for (int p = lane; p < na; p += 32) {
+            const float v = da[p];
+            if (v != 0.f) out_row[ia[p]] = norm_log(v, l1, median, pc);
+        }
+        return;
+    }
+    uint32_t *out_bits = reinterpret_cast<uint32_t *>(out_row);
+#pragma unroll 4
+    for (int p = lane; p < na; p += 32) out_bits[ia[p]] = kTagBits | (uint32_t)(p + 1);
+    __syncwarp();
+#pragma unroll 4
+    for (int p = lane; p < nb; p += 32) {
+        const int col = ib[p];
+        float v = db[p];
+        const uint32_t x = __ldcg(out_bits + col);
+        if (is_tag(x)) v += da[(int)(x & kTagPayload) - 1];
+        out_row[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int p = lane; p < na; p += 32) {
+        const int col = ia[p];
+        const float v = da[p];
+        if (is_tag(__ldcg(out_bits + col))) out_row[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+    }
+}
+
+__global__ void __launch_bounds__(kTmaWarps * 32, 1)
+    k_dense_rows_tma(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+                     const double *__restrict__ l1_rows, const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
+                     int64_t m0, int64_t m_loc, int n_genes, int ld, float median, float pc, float *__restrict__ dense, int dbg) {
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    uint8_t *ring = tma_smem + (size_t)wl * kTmaWarpBytes;
+    TmaRowDesc *table = reinterpret_cast<TmaRowDesc *>(tma_smem + (size_t)kTmaWarps * kTmaWarpBytes) + wl * kTmaTable;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tma_smem + (size_t)kTmaWarps * kTmaWarpBytes +
+                                                  (size_t)kTmaWarps * kTmaTable * sizeof(TmaRowDesc)) + wl * kTmaDepth;
+    if (lane == 0) {
+        for (int d = 0; d < kTmaDepth; d++) csr_mbar_init(bars + d, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t gw = (int64_t)blockIdx.x * kTmaWarps + wl, n_warps = (int64_t)gridDim.x * kTmaWarps;
+    const int64_t n_rows = n_loc + m_loc;
+    const int64_t my_rows = gw < n_rows ? (n_rows - gw + n_warps - 1) / n_warps : 0;
+    const float logpc = logf(pc);
+
+    // all lanes: describe 32 of this warp's rows at once (the dependent parents -> indptr loads run in parallel)
+    auto describe = [&](int64_t k_first) {
+        const int64_t k = k_first + lane;
+        if (k < my_rows) {
+            const int64_t w = gw + k * n_warps;
+            TmaRowDesc d;
+            d.synth = w < m_loc;
+            d.row = d.synth ? n_loc + w : w - m_loc;
+            d.sb = 0; d.nb = 0;
+            if (!d.synth) {
+                const int64_t src = n0 + d.row;
+                d.sa = __ldg(indptr + src);
+                d.na = __ldg(indptr + src + 1) - d.sa;
+                d.l1 = __ldg(l1_rows + src);
+            } else {
+                const int64_t r = m0 + w;
+                const int64_t pa = __ldg(parents + 2 * r), pb = __ldg(parents + 2 * r + 1);
+                d.sa = __ldg(indptr + pa);
+                d.na = __ldg(indptr + pa + 1) - d.sa;
+                d.sb = __ldg(indptr + pb);
+                d.nb = __ldg(indptr + pb + 1) - d.sb;
+                d.l1 = __ldg(l1_rows + pa) + __ldg(l1_rows + pb);
+            }
+            const int a0 = d.sa & ~3, a1 = (d.sa + d.na + 3) & ~3, b0 = d.sb & ~3, b1 = (d.sb + d.nb + 3) & ~3;
+            d.oa = d.sa - a0;
+            d.ob = d.sb - b0;
+            const int ga = d.na > 0 ? a1 - a0 : 0, gb = d.nb > 0 ? b1 - b0 : 0;
+            d.staged = (ga <= kTmaSeg && gb <= kTmaSeg && ga + gb > 0) ? 1 : 0;
+            table[k % kTmaTable] = d;
+        }
+    };
+    // lane 0: request the segments of row k (its descriptor is in the table)
+    auto issue = [&](int64_t k) {
+        const TmaRowDesc &d = table[k % kTmaTable];
+        if (!d.staged) return;
+        const int slot = (int)(k % kTmaDepth);
+        const int a0 = d.sa & ~3, a1 = (d.sa + d.na + 3) & ~3, b0 = d.sb & ~3, b1 = (d.sb + d.nb + 3) & ~3;
+        const int ga = d.na > 0 ? a1 - a0 : 0, gb = d.nb > 0 ? b1 - b0 : 0;
+        uint8_t *sl = ring + (size_t)slot * kTmaSlotBytes;
+        // the slot was read with ordinary loads by the whole warp (__syncwarp before this call): order those before the
+        // async-proxy writes of the new copies
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        csr_mbar_expect_tx(bars + slot, (uint32_t)(2 * (ga + gb) * 4));
+        if (ga > 0) {
+            csr_bulk_g2s(sl, indices + a0, (uint32_t)ga * 4, bars + slot);
+            csr_bulk_g2s(sl + kTmaSeg * 4, data + a0, (uint32_t)ga * 4, bars + slot);
+        }
+        if (gb > 0) {
+            csr_bulk_g2s(sl + 2 * kTmaSeg * 4, indices + b0, (uint32_t)gb * 4, bars + slot);
+            csr_bulk_g2s(sl + 3 * kTmaSeg * 4, data + b0, (uint32_t)gb * 4, bars + slot);
+        }
+    };
+
+    describe(0);
+    describe(32);
+    __syncwarp();
+    if (lane == 0)
+        for (int64_t k = 0; k < my_rows && k < kTmaDepth; k++) issue(k);
+    uint32_t phase_bits = 0;  // per-slot parity of the next completion to wait for
+    for (int64_t k = 0; k < my_rows; k++) {
+        const int slot = (int)(k % kTmaDepth);
+        if (k > 0 && (k & 31) == 0) {  // rows [k, k + 32) are described; describe [k + 32, k + 64) into the other half
+            describe(k + 32);
+            __syncwarp();
+        }
+        const TmaRowDesc d = table[k % kTmaTable];
+        float *out_row = dense + d.row * (int64_t)ld;
+        if (d.staged) {
+            csr_mbar_wait(bars + slot, (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            const uint8_t *sl = ring + (size_t)slot * kTmaSlotBytes;
+            const int32_t *ia = reinterpret_cast<const int32_t *>(sl) + d.oa;
+            const float *da = reinterpret_cast<const float *>(sl + kTmaSeg * 4) + d.oa;
+            const int32_t *ib = reinterpret_cast<const int32_t *>(sl + 2 * kTmaSeg * 4) + d.ob;
+            const float *db = reinterpret_cast<const float *>(sl + 3 * kTmaSeg * 4) + d.ob;
+            dense_row_from_lists(ia, da, d.na, ib, db, d.nb, d.synth != 0, d.l1, median, pc, logpc, n_genes, ld, out_row, lane, dbg);
+        } else {
+            dense_row_from_lists(indices + d.sa, data + d.sa, d.na, indices + d.sb, data + d.sb, d.nb, d.synth != 0, d.l1, median,
+                                 pc, logpc, n_genes, ld, out_row, lane, dbg);
+        }
+        __syncwarp();  // every lane is done with the slot
+        if (lane == 0 && k + kTmaDepth < my_rows) issue(k + kTmaDepth);
+    }
+}
+
+// the same row algorithm on a shared-memory row buffer (no L2 round trips for the tag merge)
+__device__ __forceinline__ void dense_row_in_smem(const int32_t *ia, const float *da, int na, const int32_t *ib, const float *db,
+                                                  int nb, bool synth, double l1, float median, float pc, float logpc,
+                                                  int n_genes, int ld, float *buf, int lane) {
+    for (int j = 4 * lane; j < ld; j += 128) {
+        float4 v;
+        v.x = j < n_genes ? logpc : 0.f;
+        v.y = j + 1 < n_genes ? logpc : 0.f;
+        v.z = j + 2 < n_genes ? logpc : 0.f;
+        v.w = j + 3 < n_genes ? logpc : 0.f;
+        *reinterpret_cast<float4 *>(buf + j) = v;
+    }
+    __syncwarp();
+    if (!synth) {
+#pragma unroll 4
+        for (int p = lane; p < na; p += 32) {
+            const float v = da[p];
+            if (v != 0.f) buf[ia[p]] = norm_log(v, l1, median, pc);
+        }
+        return;
+    }
+    uint32_t *bits = reinterpret_cast<uint32_t *>(buf);
+#pragma unroll 4
+    for (int p = lane; p < na; p += 32) bits[ia[p]] = kTagBits | (uint32_t)(p + 1);
+    __syncwarp();
+#pragma unroll 4
+    for (int p = lane; p < nb; p += 32) {
+        const int col = ib[p];
+        float v = db[p];
+        const uint32_t x = bits[col];
+        if (is_tag(x)) v += da[(int)(x & kTagPayload) - 1];
+        buf[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int p = lane; p < na; p += 32) {
+        const int col = ia[p];
+        const float v = da[p];
+        if (is_tag(bits[col])) buf[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+    }
+}
+
+// DD_DENSE_V=3: as k_dense_rows_tma, but the row is assembled in a SHARED-MEMORY row buffer (constant fill, scatter and the
+// tag merge of synthetic rows all stay on chip) and leaves as ONE bulk store (cp.async.bulk shared -> global): no 4-byte
+// scatter stores reach L2 (they cost 0.44 ms of the 0.78 ms at c3), HBM sees the matrix exactly once, as full rows.  Two row
+// buffers per warp overlap a row's store with the next row's assembly; the number of warps per CTA follows from the row size.
+__global__ void __launch_bounds__(256, 1)
+    k_dense_rows_tma_smem(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+                     const double *__restrict__ l1_rows, const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
+                     int64_t m0, int64_t m_loc, int n_genes, int ld, float median, float pc, float *__restrict__ dense, int dbg) {
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const size_t row_bytes = (size_t)ld * 4;  // multiple of 128
+    const size_t warp_bytes = kTmaWarpBytes + 2 * row_bytes + kTmaTable * sizeof(TmaRowDesc) + kTmaDepth * 8 + 40;  // 16-byte multiple
+    uint8_t *wbase = tma_smem + (size_t)wl * warp_bytes;
+    uint8_t *ring = wbase;
+    float *rowbuf = reinterpret_cast<float *>(wbase + kTmaWarpBytes);
+    TmaRowDesc *table = reinterpret_cast<TmaRowDesc *>(wbase + kTmaWarpBytes + 2 * row_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + kTmaWarpBytes + 2 * row_bytes + kTmaTable * sizeof(TmaRowDesc));
+    if (lane == 0) {
+        for (int d = 0; d < kTmaDepth; d++) csr_mbar_init(bars + d, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t gw = (int64_t)blockIdx.x * nw + wl, n_warps = (int64_t)gridDim.x * nw;
+    const int64_t n_rows = n_loc + m_loc;
+    const int64_t my_rows = gw < n_rows ? (n_rows - gw + n_warps - 1) / n_warps : 0;
+    const float logpc = logf(pc);
+
+    // all lanes: describe 32 of this warp's rows at once (the dependent parents -> indptr loads run in parallel)
+    auto describe = [&](int64_t k_first) {
+        const int64_t k = k_first + lane;
+        if (k < my_rows) {
+            const int64_t w = gw + k * n_warps;
+            TmaRowDesc d;
+            d.synth = w < m_loc;
+            d.row = d.synth ? n_loc + w : w - m_loc;
+            d.sb = 0; d.nb = 0;
+            if (!d.synth) {
+                const int64_t src = n0 + d.row;
+                d.sa = __ldg(indptr + src);
+                d.na = __ldg(indptr + src + 1) - d.sa;
+                d.l1 = __ldg(l1_rows + src);
+            } else {
+                const int64_t r = m0 + w;
+                const int64_t pa = __ldg(parents + 2 * r), pb = __ldg(parents + 2 * r + 1);
+                d.sa = __ldg(indptr + pa);
+                d.na = __ldg(indptr + pa + 1) - d.sa;
+                d.sb = __ldg(indptr + pb);
+                d.nb = __ldg(indptr + pb + 1) - d.sb;
+                d.l1 = __ldg(l1_rows + pa) + __ldg(l1_rows + pb);
+            }
+            const int a0 = d.sa & ~3, a1 = (d.sa + d.na + 3) & ~3, b0 = d.sb & ~3, b1 = (d.sb + d.nb + 3) & ~3;
+            d.oa = d.sa - a0;
+            d.ob = d.sb - b0;
+            const int ga = d.na > 0 ? a1 - a0 : 0, gb = d.nb > 0 ? b1 - b0 : 0;
+            d.staged = (ga <= kTmaSeg && gb <= kTmaSeg && ga + gb > 0) ? 1 : 0;
+            table[k % kTmaTable] = d;
+        }
+    };
+    // lane 0: request the segments of row k (its descriptor is in the table)
+    auto issue = [&](int64_t k) {
+        const TmaRowDesc &d = table[k % kTmaTable];
+        if (!d.staged) return;
+        const int slot = (int)(k % kTmaDepth);
+        const int a0 = d.sa & ~3, a1 = (d.sa + d.na + 3) & ~3, b0 = d.sb & ~3, b1 = (d.sb + d.nb + 3) & ~3;
+        const int ga = d.na > 0 ? a1 - a0 : 0, gb = d.nb > 0 ? b1 - b0 : 0;
+        uint8_t *sl = ring + (size_t)slot * kTmaSlotBytes;
+        // the slot was read with ordinary loads by the whole warp (__syncwarp before this call): order those before the
+        // async-proxy writes of the new copies
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        csr_mbar_expect_tx(bars + slot, (uint32_t)(2 * (ga + gb) * 4));
+        if (ga > 0) {
+            csr_bulk_g2s(sl, indices + a0, (uint32_t)ga * 4, bars + slot);
+            csr_bulk_g2s(sl + kTmaSeg * 4, data + a0, (uint32_t)ga * 4, bars + slot);
+        }
+        if (gb > 0) {
+            csr_bulk_g2s(sl + 2 * kTmaSeg * 4, indices + b0, (uint32_t)gb * 4, bars + slot);
+            csr_bulk_g2s(sl + 3 * kTmaSeg * 4, data + b0, (uint32_t)gb * 4, bars + slot);
+        }
+    };
+
+    describe(0);
+    describe(32);
+    __syncwarp();
+    if (lane == 0)
+        for (int64_t k = 0; k < my_rows && k < kTmaDepth; k++) issue(k);
+    uint32_t phase_bits = 0;  // per-slot parity of the next completion to wait for
+    for (int64_t k = 0; k < my_rows; k++) {
+        const int slot = (int)(k % kTmaDepth);
+        if (k > 0 && (k & 31) == 0) {  // rows [k, k + 32) are described; describe [k + 32, k + 64) into the other half
+            describe(k + 32);
+            __syncwarp();
+        }
+        const TmaRowDesc d = table[k % kTmaTable];
+        float *buf = rowbuf + (size_t)(k & 1) * ld;
+        // the bulk store that last used this buffer (row k - 2) must have finished READING it: at most one younger store
+        // (row k - 1) may still be in flight
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        if (d.staged) {
+            csr_mbar_wait(bars + slot, (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            const uint8_t *sl = ring + (size_t)slot * kTmaSlotBytes;
+            const int32_t *ia = reinterpret_cast<const int32_t *>(sl) + d.oa;
+            const float *da = reinterpret_cast<const float *>(sl + kTmaSeg * 4) + d.oa;
+            const int32_t *ib = reinterpret_cast<const int32_t *>(sl + 2 * kTmaSeg * 4) + d.ob;
+            const float *db = reinterpret_cast<const float *>(sl + 3 * kTmaSeg * 4) + d.ob;
+            dense_row_in_smem(ia, da, d.na, ib, db, d.nb, d.synth != 0, d.l1, median, pc, logpc, n_genes, ld, buf, lane);
+        } else {
+            dense_row_in_smem(indices + d.sa, data + d.sa, d.na, indices + d.sb, data + d.sb, d.nb, d.synth != 0, d.l1, median, pc,
+                              logpc, n_genes, ld, buf, lane);
+        }
+        __syncwarp();  // the row is complete in shared memory
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy read
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dense + d.row * (int64_t)ld),
+                         "r"(csr_smem_u32(buf)), "r"((uint32_t)row_bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();  // every lane is done with the slot
+        if (lane == 0 && k + kTmaDepth < my_rows) issue(k + kTmaDepth);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all rows have landed before the CTA retires
+}
+
 int pick_chunk(int64_t ld) { return (int)std::min<int64_t>(ld, kMaxChunk); }
 
 // The dense build is latency-bound with one 12 KB row buffer per warp (16 warps / SM); staging 1024 columns
@@ -434,8 +798,9 @@ extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, 
         if (h->d_indices) cudaFree(h->d_indices);
         if (h->d_data) cudaFree(h->d_data);
         h->d_indices = nullptr; h->d_data = nullptr; h->cap_nnz = 0;
-        DD_CUDA(h, cudaMalloc(&h->d_indices, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-        DD_CUDA(h, cudaMalloc(&h->d_data, sizeof(float) * std::max<int64_t>(nnz, 1)));
+        // + 4 entries: the bulk-copy staging of a row reads whole 16-byte groups around it
+        DD_CUDA(h, cudaMalloc(&h->d_indices, sizeof(int32_t) * (std::max<int64_t>(nnz, 1) + 4)));
+        DD_CUDA(h, cudaMalloc(&h->d_data, sizeof(float) * (std::max<int64_t>(nnz, 1) + 4)));
         h->cap_nnz = std::max<int64_t>(nnz, 1);
     }
     DD_CUDA(h, cudaMemcpyAsync(h->d_indptr, indptr, sizeof(int32_t) * (n_cells + 1), cudaMemcpyHostToDevice, h->stream));
@@ -597,6 +962,37 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
         // 48 registers x 256 threads: five CTAs fit an SM; four (32 warps) keep the grid a single full wave and the rows in
         // flight (32 warps x 148 SMs x 12 KB = 57 MB at 3k genes) inside the 126 MB L2
         static const int warps_per_sm = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 32;
+        if (variant == 3) {  // TMA-staged CSR segments, rows assembled in shared memory, bulk-stored
+            const size_t per_warp = kTmaWarpBytes + 2 * (size_t)h->ld * 4 + kTmaTable * sizeof(TmaRowDesc) + kTmaDepth * 8 + 40;
+            const int nw = (int)std::min<size_t>(8, (220 * 1024) / per_warp);
+            if (nw >= 1) {
+                static bool attr3 = false;
+                if (!attr3) {
+                    cudaFuncSetAttribute(k_dense_rows_tma_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                    attr3 = true;
+                }
+                DD_LAUNCH(h, "dense_rows", k_dense_rows_tma_smem, h->num_sms, nw * 32, per_warp * nw, h->d_indptr, h->d_indices,
+                          h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
+                          pseudocount, h->d_dense, 0);
+                h->dense_valid = true;
+                h->emb_valid = false;
+                return DD_OK;
+            }
+        }
+        if (variant == 2) {  // TMA-staged CSR segments, one 8-warp CTA per SM
+            static const int dbg = getenv("DD_DENSE_DBG") ? atoi(getenv("DD_DENSE_DBG")) : 0;
+            static bool tma_attr = false;
+            if (!tma_attr) {
+                cudaFuncSetAttribute(k_dense_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes);
+                tma_attr = true;
+            }
+            DD_LAUNCH(h, "dense_rows", k_dense_rows_tma, h->num_sms, kTmaWarps * 32, kTmaSmemBytes, h->d_indptr, h->d_indices,
+                      h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
+                      pseudocount, h->d_dense, dbg);
+            h->dense_valid = true;
+            h->emb_valid = false;
+            return DD_OK;
+        }
         const int grid = h->num_sms * std::max(1, warps_per_sm / 8);
         DD_LAUNCH(h, "dense_rows", k_dense_rows_l2, grid, 256, 0, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
                   h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median, pseudocount,
