@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -48,7 +48,7 @@ class FitParams(ctypes.Structure):
     ]
 
 
-CLUSTER_LOUVAIN, CLUSTER_PHENOGRAPH = 0, 1
+CLUSTER_LOUVAIN, CLUSTER_PHENOGRAPH, CLUSTER_LEIDEN = 0, 1, 2
 
 
 # name -> (restype, argtypes); every symbol include/dd_b200.h declares
@@ -87,6 +87,18 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i32p, c_f64p, ctypes.c_int64, c_i64p],
     ),
     "dd_louvain_csr": (
+        ctypes.c_int,
+        [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
+    "dd_umap_connectivities": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int32, c_i32p, c_f32p, c_i64p, c_i32p, c_f32p, ctypes.c_int64, c_i64p],
+    ),
+    "dd_leiden_knn": (
+        ctypes.c_int,
+        [ctypes.c_int64, ctypes.c_int32, c_i32p, c_f32p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
+    "dd_leiden_csr": (
         ctypes.c_int,
         [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
     ),
@@ -195,6 +207,63 @@ def louvain_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
     ncomm = ctypes.c_int32(0)
     rc = lib.dd_louvain_csr(n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64), _ptr(w, ctypes.c_double),
                             float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return labels[:n]
+
+
+def umap_connectivities(knn_idx, knn_dist):
+    """umap's fuzzy simplicial set of exact kNN lists (self in column 0) as scipy CSR (float32, sorted rows)."""
+    import scipy.sparse as sp_sparse
+
+    lib = load()
+    knn_idx = np.ascontiguousarray(knn_idx, dtype=np.int32)
+    knn_dist = _f32(knn_dist)
+    n, k = knn_idx.shape
+    nnz = ctypes.c_int64(0)
+    rc = lib.dd_umap_connectivities(n, k, _ptr(knn_idx, ctypes.c_int32), _ptr(knn_dist, ctypes.c_float), None, None, None,
+                                    0, ctypes.byref(nnz))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    indices = np.empty(max(nnz.value, 1), dtype=np.int32)
+    weights = np.empty(max(nnz.value, 1), dtype=np.float32)
+    rc = lib.dd_umap_connectivities(n, k, _ptr(knn_idx, ctypes.c_int32), _ptr(knn_dist, ctypes.c_float),
+                                    _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int32),
+                                    _ptr(weights, ctypes.c_float), max(nnz.value, 1), ctypes.byref(nnz))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return sp_sparse.csr_matrix((weights[: nnz.value], indices[: nnz.value], indptr), shape=(n, n))
+
+
+def leiden_knn(knn_idx, knn_dist, resolution=4.0, seed=0):
+    """Leiden labels of the umap-weighted neighbour graph of exact kNN lists (what the fit loop's host workers run
+    for ``clustering="leiden"``)."""
+    lib = load()
+    knn_idx = np.ascontiguousarray(knn_idx, dtype=np.int32)
+    knn_dist = _f32(knn_dist)
+    n, k = knn_idx.shape
+    if knn_dist.shape != knn_idx.shape:
+        raise ValueError("knn_idx and knn_dist must have the same shape")
+    labels = np.empty(max(n, 1), dtype=np.int32)
+    ncomm = ctypes.c_int32(0)
+    rc = lib.dd_leiden_knn(n, k, _ptr(knn_idx, ctypes.c_int32), _ptr(knn_dist, ctypes.c_float), float(resolution),
+                           int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return labels[:n]
+
+
+def leiden_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
+    lib = load()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    n = indptr.size - 1
+    labels = np.empty(max(n, 1), dtype=np.int32)
+    ncomm = ctypes.c_int32(0)
+    rc = lib.dd_leiden_csr(n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64), _ptr(w, ctypes.c_double),
+                           float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
     if rc != DD_OK:
         _raise(lib, None, rc)
     return labels[:n]
@@ -380,7 +449,7 @@ class Handle:
         p = FitParams(n_iters, n_synth, float(pseudocount), int(bool(standard_scaling)), float(scale_max_value),
                       int(n_comp), int(omega.shape[1]), int(n_power_iter), int(knn_k), float(resolution),
                       int(seed) & (2**64 - 1), int(n_host_threads), int(iter_begin), int(iter_end),
-                      {"louvain": CLUSTER_LOUVAIN, "phenograph": CLUSTER_PHENOGRAPH}[clustering], int(pheno_k),
+                      {"louvain": CLUSTER_LOUVAIN, "phenograph": CLUSTER_PHENOGRAPH, "leiden": CLUSTER_LEIDEN}[clustering], int(pheno_k),
                       int(bool(pheno_prune)), int(pheno_min_cluster_size))
         N = self.n_cells
         scores = np.zeros((n_iters, N), dtype=np.float64)

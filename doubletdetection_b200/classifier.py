@@ -8,8 +8,9 @@ where ``_one_fit`` (:274-383) executes: synthetic doublets, normalise/log, optio
 randomized PCA and the exact kNN graph are CUDA kernels, clustering (Louvain) and scoring are native
 host code overlapped with the GPU.  ``clustering_algorithm="phenograph"`` (the reference's default) builds
 PhenoGraph's Jaccard graph of the 30 nearest neighbours on the GPU and partitions it with the in-repo Louvain
-(one seeded run; the phenograph package with its time-seeded binaries is not available); ``"leiden"`` is not
-implemented.  There is no CPU fallback: without the built library or without a B200 ``fit`` raises.
+(one seeded run; the phenograph package with its time-seeded binaries is not available); ``"leiden"`` takes the
+exact kNN lists and distances from the GPU and builds umap's fuzzy-simplicial-set weights and the Leiden partition
+on the native host workers (in-repo Leiden; leidenalg is not available).  There is no CPU fallback: without the built library or without a B200 ``fit`` raises.
 
 Keyword-only extensions (not in the reference): ``device`` (CUDA device index; default
 ``LOCAL_RANK`` or 0) and ``distributed`` (shard the work over the ranks of an initialised
@@ -184,11 +185,6 @@ class BoostClassifier:
         if self.normalizer is not None:
             # the reference itself raises NameError on this path in this version (:288-291 vs :301, :372)
             raise NotImplementedError("custom `normalizer` is not supported (and is broken in the reference at this version)")
-        if self.clustering_algorithm == "leiden":
-            raise NotImplementedError(
-                "clustering_algorithm='leiden' (sc.tl.leiden on the UMAP-weighted graph) is not implemented on the B200 "
-                "path; use 'louvain' or 'phenograph'"
-            )
         cluster_kw = {}
         if self.clustering_algorithm == "phenograph":
             # phenograph.cluster(X_pca, n_jobs=self.n_jobs, **clustering_kwargs) (:320): the arguments that change
@@ -208,8 +204,11 @@ class BoostClassifier:
                 raise NotImplementedError("clustering_kwargs['directed']=True is not supported (the reference default is False)")
             extra = set(self.clustering_kwargs) - {"directed", "resolution"}
             if extra:
-                raise NotImplementedError(f"unsupported clustering_kwargs for the native Louvain: {sorted(extra)}")
-            cluster_kw = dict(clustering="louvain", resolution=float(self.clustering_kwargs["resolution"]))
+                raise NotImplementedError(
+                    f"unsupported clustering_kwargs for the native {self.clustering_algorithm}: {sorted(extra)}")
+            # "louvain": unweighted pattern of the kNN graph (:337-338); "leiden": umap-weighted graph, iterated until
+            # stable (:339-340, sc.tl.leiden's use_weights=True / n_iterations=-1) on the host workers
+            cluster_kw = dict(clustering=self.clustering_algorithm, resolution=float(self.clustering_kwargs["resolution"]))
         if self.pseudocount == 1:
             raise NotImplementedError("pseudocount=1 selects the sparse log1p + arpack path (:296-297, :308), which is not on the B200 hot path")
 

@@ -11,7 +11,7 @@
 
 #include "../../include/dd_b200.h"
 
-#define DD_ABI_VERSION 3
+#define DD_ABI_VERSION 4
 
 // padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
 static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -212,4 +212,7 @@ int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *ad
 // Louvain at resolution 1 on the weighted graph, labels by decreasing size, communities < min_cluster_size -> -1
 int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
                                   int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out);
+// Leiden on the umap-weighted neighbour graph (leiden.cpp): kNN lists with self in column 0 + float32 distances
+int dd_host_leiden_knn(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist, double resolution,
+                       uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
 float dd_host_median(std::vector<float> &v);

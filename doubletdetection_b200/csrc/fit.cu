@@ -20,7 +20,8 @@ int dd_pca_flag_copy(dd_handle *h, double *host_flag);                      // p
 namespace {
 
 struct Slot {
-    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1)) | PhenoGraph: weights (f64)]
+    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1)) | PhenoGraph: weights (f64)];
+                               // Leiden: [kNN idx (A * k) | kNN dist (A * k, float32)]
     double *flag = nullptr;    // pinned, PCA breakdown flag
     cudaEvent_t done = nullptr;
 };
@@ -48,9 +49,12 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     if (p->pseudocount == 1.0f)
         return dd_fail(h, DD_ERR_UNSUPPORTED, "pseudocount == 1 (sparse log1p + arpack path) is not on the B200 hot path");
     if (p->knn_k < 2) return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: knn_k < 2");
-    if (p->clustering != DD_CLUSTER_LOUVAIN && p->clustering != DD_CLUSTER_PHENOGRAPH)
+    if (p->clustering != DD_CLUSTER_LOUVAIN && p->clustering != DD_CLUSTER_PHENOGRAPH && p->clustering != DD_CLUSTER_LEIDEN)
         return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: unknown clustering");
     const bool pheno = p->clustering == DD_CLUSTER_PHENOGRAPH;
+    // Leiden works on umap's weighted graph, whose weights come from the kNN DISTANCES: the lists + distances of every
+    // iteration go to the host workers, which build the fuzzy simplicial set and partition it (leiden.cpp)
+    const bool leiden = p->clustering == DD_CLUSTER_LEIDEN;
     if (pheno && (p->pheno_k < 1 || p->pheno_k > 30))
         return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_fit_iterations: phenograph k must be in [1, 30]");
     DD_CUDA(h, cudaSetDevice(h->device));
@@ -64,7 +68,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     const int n_slots = n_threads + 2;
     const int64_t max_nnz = A * 2 * (k - 1);
     const int64_t w_off = ((A + 1) + A + max_nnz + 1) / 2 * 2;  // weights start 8-byte aligned
-    const int64_t slot_elems = pheno ? w_off + 2 * max_nnz : (A + 1) + A + max_nnz;
+    const int64_t slot_elems = pheno ? w_off + 2 * max_nnz : leiden ? 2 * A * k : (A + 1) + A + max_nnz;
     const int n_run = p->iter_end - p->iter_begin;
     if (stage_ms_out) std::fill(stage_ms_out, stage_ms_out + 8, 0.0);
     if (n_run == 0) return DD_OK;
@@ -148,7 +152,10 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
                 const auto t0 = now();
                 int32_t n_comm = 0;
                 const int32_t *off = s.graph, *comm0 = s.graph + (A + 1), *adj = s.graph + (A + 1) + A;
-                if (pheno)
+                if (leiden)
+                    wrc = dd_host_leiden_knn(A, k, s.graph, reinterpret_cast<const float *>(s.graph + A * k), p->resolution,
+                                             p->seed, labels.data(), &n_comm);
+                else if (pheno)
                     wrc = dd_host_phenograph_from_graph(A, off, adj, reinterpret_cast<const double *>(s.graph + w_off), p->seed,
                                                         p->pheno_min_cluster_size, labels.data(), &n_comm);
                 else
@@ -241,6 +248,22 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         }
         Slot &s = slots[slot];
         dd_pca_flag_copy(h, s.flag);
+        if (leiden) {
+            // no device clustering stage: the lists and their distances leave on the main stream (the distance buffer is
+            // not double-buffered, and the next kNN is ordered behind these copies on the same stream)
+            cudaMemcpyAsync(s.graph, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, h->stream);
+            cudaMemcpyAsync(s.graph + A * k, h->d_knn_dist, sizeof(float) * A * k, cudaMemcpyDeviceToHost, h->stream);
+            cudaEventRecord(ev[5], h->stream);
+            cudaEventRecord(lv_done, h->stream);
+            cudaEventRecord(s.done, h->stream);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                jobs.push_back(Job{it, slot});
+            }
+            cv_job.notify_one();
+            if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
+            continue;
+        }
         // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device.
         // These are hundreds of small latency-bound kernels: they run on a second stream and overlap the
         // HBM-bound dense build / PCA of the NEXT iteration.

@@ -18,28 +18,12 @@
 #include <vector>
 
 #include "dd_internal.h"
+#include "louvain_host.h"
 
 namespace {
 
-struct SplitMix64 {
-    uint64_t s;
-    uint64_t next() {
-        s += 0x9E3779B97F4A7C15ULL;
-        uint64_t z = s;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-        return z ^ (z >> 31);
-    }
-};
-
-struct Graph {
-    int32_t n = 0;
-    std::vector<int64_t> indptr;
-    std::vector<int32_t> indices;
-    std::vector<double> weights;  // empty = all ones
-    std::vector<double> selfw;
-    double w(int64_t e) const { return weights.empty() ? 1.0 : weights[e]; }
-};
+using ddlv::Graph;
+using ddlv::SplitMix64;
 
 struct Scratch {
     std::vector<double> k, tot, neigh_w;
@@ -188,8 +172,10 @@ bool one_level(const Graph &g, double gamma, double two_m, SplitMix64 &rng, std:
     return moved_any;
 }
 
+}  // namespace
+
 // aggregate g by comm; node2new renumbers communities by first appearance over node index
-void aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &out, std::vector<int32_t> &node2new) {
+void ddlv::aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &out, std::vector<int32_t> &node2new) {
     const int32_t n = g.n;
     std::vector<int32_t> new_id(n, -1);
     node2new.resize(n);
@@ -249,6 +235,27 @@ void aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &out, std
     }
     if (out.weights.empty()) out.weights.push_back(0.0);  // keep "empty == unit weights" unambiguous
 }
+
+void ddlv::labels_by_size(std::vector<int32_t> &membership, int32_t *labels_out, int32_t *n_comm_out) {
+    const int32_t n = (int32_t)membership.size();
+    std::vector<int32_t> fa_of(n, -1);
+    int32_t nc = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (fa_of[membership[i]] < 0) fa_of[membership[i]] = nc++;
+        membership[i] = fa_of[membership[i]];
+    }
+    std::vector<int64_t> size(nc, 0);
+    for (int32_t i = 0; i < n; i++) size[membership[i]]++;
+    std::vector<int32_t> order(nc);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+    std::vector<int32_t> newlab(nc);
+    for (int32_t r = 0; r < nc; r++) newlab[order[r]] = r;
+    for (int32_t i = 0; i < n; i++) labels_out[i] = newlab[membership[i]];
+    if (n_comm_out) *n_comm_out = nc;
+}
+
+namespace {
 
 // First level by synchronous coloured rounds on the host (the twin of louvain_gpu.cu; specification:
 // oracle/louvain_ref.py:level0_parallel).  Unweighted graphs only.
@@ -334,7 +341,7 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
         else
             level0_parallel_host(g, resolution, two_m, seed, comm);
         Graph ng;
-        aggregate(g, comm, ng, node2new);
+        ddlv::aggregate(g, comm, ng, node2new);
         for (int32_t i = 0; i < n; i++) membership[i] = node2new[membership[i]];
         g = std::move(ng);
     }
@@ -347,7 +354,7 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
             const auto t1 = std::chrono::steady_clock::now();
             if (!moved) break;
             Graph ng;
-            aggregate(g, comm, ng, node2new);
+            ddlv::aggregate(g, comm, ng, node2new);
             if (trace)
                 fprintf(stderr, "louvain level %d: n=%d nnz=%zu move %.1f ms aggregate %.1f ms -> n=%d\n", level, g.n,
                         g.indices.size(), std::chrono::duration<double, std::milli>(t1 - t0).count(),
@@ -356,22 +363,7 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
             g = std::move(ng);
         }
     }
-    // first-appearance ids, then by decreasing size (ties: smaller first-appearance id first)
-    std::vector<int32_t> fa_of(n, -1);
-    int32_t nc = 0;
-    for (int32_t i = 0; i < n; i++) {
-        if (fa_of[membership[i]] < 0) fa_of[membership[i]] = nc++;
-        membership[i] = fa_of[membership[i]];
-    }
-    std::vector<int64_t> size(nc, 0);
-    for (int32_t i = 0; i < n; i++) size[membership[i]]++;
-    std::vector<int32_t> order(nc);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
-    std::vector<int32_t> newlab(nc);
-    for (int32_t r = 0; r < nc; r++) newlab[order[r]] = r;
-    for (int32_t i = 0; i < n; i++) labels_out[i] = newlab[membership[i]];
-    if (n_comm_out) *n_comm_out = nc;
+    ddlv::labels_by_size(membership, labels_out, n_comm_out);
     return DD_OK;
 }
 

@@ -123,6 +123,28 @@ int dd_jaccard_graph(dd_handle *h, int32_t k, int32_t prune, int32_t *indptr_out
 int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                    double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 
+/* ---- clustering_algorithm="leiden", doubletdetection.py:331-342 (host) -------------------------------------
+ * sc.pp.neighbors(method="umap", n_neighbors=k) weights + sc.tl.leiden(resolution, random_state, directed=False).
+ * dd_umap_connectivities: umap's fuzzy simplicial set of the exact kNN lists (knn_idx int32[n * k] with the cell
+ * itself in column 0, knn_dist float32[n * k]): smooth_knn_dist (rho = nearest positive distance, sigma by
+ * bisection so that the memberships of the k - 1 neighbours sum to log2(k)), membership strengths
+ * exp(-(d - rho) / sigma), fuzzy union W + W^T - W o W^T in float32, zeros dropped; CSR with ascending rows.
+ * Call with capacity 0 to get nnz_out, then with buffers of that size (indptr_out int64[n + 1]).
+ * dd_leiden_knn: that graph partitioned by the Leiden algorithm (RB-configuration quality, resolution gamma,
+ * edge weights used, iterated until stable like leidenalg's n_iterations=-1), labels by decreasing community
+ * size.  umap-learn / leidenalg are absent from the image: the arithmetic of the weights is pinned by
+ * oracle/upstream.py, the move order by oracle/leiden_ref.py (parity with leidenalg itself is unpinned).  This is
+ * what dd_fit_iterations runs on its host workers for DD_CLUSTER_LEIDEN, fed by the device kNN.
+ * dd_leiden_csr: the same partitioning of an explicit symmetric CSR graph (weights may be NULL = unweighted).
+ * No handle: pure host code, thread-safe. */
+int dd_umap_connectivities(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist,
+                           int64_t *indptr_out, int32_t *indices_out, float *weights_out, int64_t capacity,
+                           int64_t *nnz_out);
+int dd_leiden_knn(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist, double resolution,
+                  uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
+int dd_leiden_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                  double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
+
 /* ---- scoring, doubletdetection.py:344-383 (host) ----------------------------------------
  * labels int32[n_cells + n_synth]; scores_out / log_p_out float64[n_cells]:
  * synth fraction of the cell's community and hypergeom.logsf(k, A, M, size); NaN where the
@@ -161,13 +183,14 @@ typedef struct dd_fit_params {
     int32_t n_host_threads;
     int32_t iter_begin;       /* run iterations [iter_begin, iter_end) of the n_iters drawn */
     int32_t iter_end;
-    int32_t clustering;       /* DD_CLUSTER_LOUVAIN (:329-343) or DD_CLUSTER_PHENOGRAPH (:318-327) */
+    int32_t clustering;       /* DD_CLUSTER_LOUVAIN / DD_CLUSTER_LEIDEN (:329-343) or DD_CLUSTER_PHENOGRAPH (:318-327) */
     int32_t pheno_k;          /* phenograph.cluster k (30): neighbours per cell, self excluded */
     int32_t pheno_prune;      /* 1: keep mutual edges, weight product (the reference's default); 0: average */
     int32_t pheno_min_cluster_size; /* 10: smaller communities are labelled -1 (NaN scores, :379-381) */
 } dd_fit_params;
 #define DD_CLUSTER_LOUVAIN 0
 #define DD_CLUSTER_PHENOGRAPH 1
+#define DD_CLUSTER_LEIDEN 2
 
 int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int64_t *parents, const float *omega,
                       double *scores_out, double *log_p_out, int32_t *communities_out,

@@ -141,7 +141,7 @@ def doublet_score(all_log_p_values, n_iters):
 
 # --------------------------------------------------------------------------- whole classifier
 class OracleClassifier:
-    """The reference's louvain path end to end (doubletdetection.py:73-214, 274-383), with the
+    """The reference's louvain / leiden / phenograph paths end to end (doubletdetection.py:73-214, 274-383), with the
     absent upstream calls replaced by ``oracle.upstream``.  ``hooks`` lets a test capture the
     intermediate of every stage of every iteration."""
 
@@ -159,6 +159,7 @@ class OracleClassifier:
         louvain_fn=None,
         keep_stages=False,
         clustering_algorithm="louvain",
+        leiden_fn=None,
     ):
         self.clustering_algorithm = clustering_algorithm
         self.boost_rate = boost_rate
@@ -183,6 +184,7 @@ class OracleClassifier:
         if not self.replace and self.boost_rate > 0.5:  # :121-127
             self.boost_rate = 0.5
         self.louvain_fn = louvain_fn
+        self.leiden_fn = leiden_fn
         self.keep_stages = keep_stages
         self.stages = []
 
@@ -238,13 +240,20 @@ class OracleClassifier:
                 st["jaccard_graph"] = graph
             st["scores"], st["log_p"], st["communities"], st["synth_communities"] = score_communities(full, num_cells)
             return st
-        upstream.pp_neighbors(adata, random_state=self.random_state, method="umap", n_neighbors=10)
+        leiden = self.clustering_algorithm == "leiden"  # :337-340
+        upstream.pp_neighbors(adata, random_state=self.random_state, method="umap", n_neighbors=10, with_weights=leiden)
         st["knn_indices"] = adata.uns["knn_indices"]
         st["knn_distances"] = adata.uns["knn_distances"]
-        upstream.tl_louvain(
-            adata, key_added="clusters", random_state=self.random_state, louvain_fn=self.louvain_fn,
-            **self.clustering_kwargs,
-        )
+        if leiden:
+            if self.keep_stages:
+                st["connectivities"] = adata.obsp["connectivities"]
+            upstream.tl_leiden(adata, key_added="clusters", random_state=self.random_state, leiden_fn=self.leiden_fn,
+                               **self.clustering_kwargs)
+        else:
+            upstream.tl_louvain(
+                adata, key_added="clusters", random_state=self.random_state, louvain_fn=self.louvain_fn,
+                **self.clustering_kwargs,
+            )
         full = np.array(adata.obs["clusters"], dtype=int)
         st["fullcommunities"] = full
         st["scores"], st["log_p"], st["communities"], st["synth_communities"] = score_communities(full, num_cells)

@@ -10,7 +10,7 @@ here, so these are semantic restatements -- the parts that bottom out in the *in
 import numpy as np
 import scipy.sparse as sp_sparse
 
-from . import louvain_ref
+from . import leiden_ref, louvain_ref
 
 
 class AnnDataLite:
@@ -101,35 +101,45 @@ def knn_brute(rep, n_neighbors=10):
     return idx, dist.astype(np.float32)
 
 
-def smooth_knn_dist(distances, k, n_iter=64, local_connectivity=1.0, bandwidth=1.0):
-    """umap ``smooth_knn_dist`` restated; distances has self in column 0."""
+def smooth_knn_dist(distances, k, n_iter=64):
+    """umap ``smooth_knn_dist(distances, k, local_connectivity=1, bandwidth=1)`` restated (SURVEY Appendix B1);
+    ``distances`` float32 with self in column 0.  The arithmetic is pinned the way numba types the upstream code,
+    so that the product's C++ (``doubletdetection_b200/csrc/leiden.cpp:umap_weights``) reproduces it bit for bit:
+    ``rho`` and the stored ``sigma`` are float32; ``d = dist - rho`` is a float32 subtraction; the bisection
+    (``mid``, ``psum``, ``exp``) runs in float64 with libm's ``exp``; sums are sequential.  ``mean(distances)``
+    (only used as the sigma floor of rows whose neighbours all coincide with the cell) is the float64 mean of
+    the sequential float64 row sums."""
+    import math
+
     SMOOTH_K_TOLERANCE = 1e-5
     MIN_K_DIST_SCALE = 1e-3
-    n = distances.shape[0]
-    target = np.log2(k) * bandwidth
+    distances = np.asarray(distances, dtype=np.float32)
+    n, width = distances.shape
+    target = math.log2(float(k))
     rho = np.zeros(n, dtype=np.float32)
     sigma = np.zeros(n, dtype=np.float32)
-    mean_distances = np.mean(distances)
+    row_sums = []
     for i in range(n):
-        lo, hi, mid = 0.0, np.inf, 1.0
+        s = 0.0
+        for x in distances[i].tolist():
+            s += x
+        row_sums.append(s)
+    total = 0.0
+    for s in row_sums:
+        total += s
+    mean_distances = total / float(n * width) if n * width else 0.0
+    for i in range(n):
         ith = distances[i]
-        non_zero = ith[ith > 0.0]
-        if non_zero.shape[0] >= local_connectivity:
-            index = int(np.floor(local_connectivity))
-            interpolation = local_connectivity - index
-            if index > 0:
-                rho[i] = non_zero[index - 1]
-                if interpolation > SMOOTH_K_TOLERANCE:
-                    rho[i] += interpolation * (non_zero[index] - non_zero[index - 1])
-            else:
-                rho[i] = interpolation * non_zero[0]
-        elif non_zero.shape[0] > 0:
-            rho[i] = np.max(non_zero)
+        for x in ith:
+            if x > 0.0:
+                rho[i] = x  # local_connectivity = 1: the nearest neighbour at a positive distance
+                break
+        d = [float(x) for x in (ith[1:] - rho[i])]  # float32 subtraction, then exact in float64
+        lo, hi, mid = 0.0, math.inf, 1.0
         for _ in range(n_iter):
             psum = 0.0
-            for j in range(1, distances.shape[1]):
-                d = distances[i, j] - rho[i]
-                psum += np.exp(-(d / mid)) if d > 0 else 1.0
+            for x in d:
+                psum += math.exp(-(x / mid)) if x > 0.0 else 1.0
             if abs(psum - target) < SMOOTH_K_TOLERANCE:
                 break
             if psum > target:
@@ -137,39 +147,49 @@ def smooth_knn_dist(distances, k, n_iter=64, local_connectivity=1.0, bandwidth=1
                 mid = (lo + hi) / 2.0
             else:
                 lo = mid
-                if hi == np.inf:
-                    mid *= 2
+                if hi == math.inf:
+                    mid *= 2.0
                 else:
                     mid = (lo + hi) / 2.0
         sigma[i] = mid
-        if rho[i] > 0.0:
-            mean_ith = np.mean(ith)
-            if sigma[i] < MIN_K_DIST_SCALE * mean_ith:
-                sigma[i] = MIN_K_DIST_SCALE * mean_ith
-        else:
-            if sigma[i] < MIN_K_DIST_SCALE * mean_distances:
-                sigma[i] = MIN_K_DIST_SCALE * mean_distances
+        floor = MIN_K_DIST_SCALE * (row_sums[i] / float(width) if rho[i] > 0.0 else mean_distances)
+        if float(sigma[i]) < floor:
+            sigma[i] = floor
     return sigma, rho
+
+
+def membership_strengths(knn_idx, knn_dist, sigma, rho):
+    """umap ``compute_membership_strengths`` restated: float32 directed weights (n x k), 0 for the cell itself, 1 at or
+    below rho, else float32(exp(-(float64(d - rho) / float64(sigma)))) with ``d - rho`` a float32 subtraction."""
+    import math
+
+    n, k = knn_idx.shape
+    d = np.asarray(knn_dist, dtype=np.float32)
+    vals = np.zeros((n, k), dtype=np.float32)
+    for i in range(n):
+        diff = d[i] - rho[i]
+        s = float(sigma[i])
+        for j in range(k):
+            if knn_idx[i, j] == i:
+                v = 0.0
+            elif diff[j] <= 0.0 or s == 0.0:
+                v = 1.0
+            else:
+                v = math.exp(-(float(diff[j]) / s))
+            vals[i, j] = v
+    return vals
 
 
 def fuzzy_connectivities(knn_idx, knn_dist):
     """umap ``fuzzy_simplicial_set(set_op_mix_ratio=1, local_connectivity=1)`` restated:
-    membership strengths, then W + W^T - W o W^T, zeros eliminated."""
+    membership strengths, then W + W^T - W o W^T in float32, zeros eliminated."""
+    knn_idx = np.asarray(knn_idx)
     n, k = knn_idx.shape
-    d = knn_dist.astype(np.float32)
+    d = np.asarray(knn_dist, dtype=np.float32)
     sigma, rho = smooth_knn_dist(d, float(k))
+    vals = membership_strengths(knn_idx, d, sigma, rho).ravel()
     rows = np.repeat(np.arange(n), k)
     cols = knn_idx.ravel()
-    vals = np.zeros(n * k, dtype=np.float32)
-    for i in range(n):
-        for j in range(k):
-            if knn_idx[i, j] == i:
-                v = 0.0
-            elif d[i, j] - rho[i] <= 0.0 or sigma[i] == 0.0:
-                v = 1.0
-            else:
-                v = np.exp(-((d[i, j] - rho[i]) / sigma[i]))
-            vals[i * k + j] = v
     W = sp_sparse.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
     W.eliminate_zeros()
     T = W.T.tocsr()
@@ -230,6 +250,19 @@ def tl_louvain(adata, key_added="clusters", random_state=0, directed=False, reso
     # the kNN-pipeline flavour of the specification: synchronous coloured first level (GPU-friendly), then
     # sequential levels (oracle/louvain_ref.py)
     labels = fn(C.indptr, C.indices, None, resolution=float(resolution), seed=int(random_state), level0="parallel")
+    adata.obs[key_added] = np.asarray([str(int(x)) for x in labels])
+    return adata
+
+
+def tl_leiden(adata, key_added="clusters", random_state=0, directed=False, resolution=4, leiden_fn=None, **_):
+    """``sc.tl.leiden(adata, key_added="clusters", random_state, directed=False, resolution=4)`` --
+    doubletdetection.py:340-342; SURVEY Appendix B2.  Unlike ``tl.louvain`` it uses the connectivities' weights
+    (``use_weights=True``) and runs ``leidenalg`` until no iteration improves (``n_iterations=-1``).  The partition
+    comes from the in-repo deterministic Leiden (``leiden_ref``; PARITY UNPINNED, leidenalg is absent)."""
+    C = adata.obsp["connectivities"].tocsr()
+    C.sort_indices()
+    fn = leiden_fn or leiden_ref.leiden
+    labels = fn(C.indptr, C.indices, C.data.astype(np.float64), resolution=float(resolution), seed=int(random_state))
     adata.obs[key_added] = np.asarray([str(int(x)) for x in labels])
     return adata
 

@@ -69,7 +69,8 @@ def test_unsupported_paths_fail_loudly():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         with pytest.raises(NotImplementedError):
-            BoostClassifier(n_iters=2, clustering_algorithm="leiden").fit(x)  # leidenalg path is not built
+            # sc.tl.leiden arguments the native Leiden does not cover
+            BoostClassifier(n_iters=2, clustering_algorithm="leiden", clustering_kwargs={"n_iterations": 2}).fit(x)
         with pytest.raises(NotImplementedError):  # phenograph arguments the native graph does not cover
             BoostClassifier(n_iters=2, clustering_kwargs={"primary_metric": "cosine"}).fit(x)
         with pytest.raises(NotImplementedError):

@@ -10,7 +10,7 @@ import pytest
 from scipy.stats import hypergeom
 
 from conftest import ROOT, golden_case, load_golden
-from oracle import louvain_c, louvain_ref, reference_path, upstream
+from oracle import leiden_ref, louvain_c, louvain_ref, reference_path, upstream
 
 
 def test_library_exports_every_header_symbol(native):
@@ -163,3 +163,92 @@ def test_phenograph_host_twin_matches_oracle(native, prune):
     # a larger min_cluster_size sends more cells to -1 (NaN scores downstream, doubletdetection.py:379-381)
     many = native.phenograph_knn(idx, prune=prune, min_cluster_size=100, seed=1)
     assert (many == -1).sum() >= (got == -1).sum()
+
+
+# ---- clustering_algorithm="leiden": umap connectivities + Leiden on the host workers (leiden.cpp)
+def _blobs(n, dim, seed, spread=2.5, n_types=5):
+    rs = np.random.default_rng(seed)
+    return (rs.normal(size=(n, dim)) + rs.integers(0, n_types, size=(n, 1)) * spread).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,k", [(60, 4), (400, 10), (1200, 10), (700, 15)])
+def test_umap_connectivities_match_oracle_bit_for_bit(native, n, k):
+    idx, dist = upstream.knn_brute(_blobs(n, 6, n + k), k)
+    want = upstream.fuzzy_connectivities(idx, dist)
+    got = native.umap_connectivities(idx, dist)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)  # float32, same bits
+    assert got.data.dtype == np.float32 and (got.data > 0).all() and (got.data <= 1).all()
+    assert (abs(got - got.T)).nnz == 0  # the fuzzy union is symmetric
+    # every directed kNN edge survives the union (its membership strength is > 0 unless it underflows)
+    pattern = upstream.knn_pattern_graph(idx)
+    assert got.nnz <= pattern.nnz and got.nnz >= 0.99 * pattern.nnz
+
+
+def test_umap_connectivities_duplicates_and_far_neighbours(native):
+    """rho = 0 rows (all neighbours coincide with the cell: sigma floor from the global mean), exact duplicates
+    (distance 0 -> strength 1) and a neighbour so far away that its strength underflows to 0 and is dropped."""
+    x = _blobs(300, 4, 5)
+    x[10:16] = x[10]  # six coincident cells: with k = 4 all their neighbours are at distance 0
+    x[200] += 1.0e4  # an outlier: its neighbours are all ~1e4 away, and nobody lists it
+    idx, dist = upstream.knn_brute(x, 4)
+    want = upstream.fuzzy_connectivities(idx, dist)
+    got = native.umap_connectivities(idx, dist)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+    labels = native.leiden_knn(idx, dist, resolution=1.0, seed=0)
+    assert len(set(labels[10:16].tolist())) == 1  # coincident cells stay together
+
+
+@pytest.mark.parametrize("n,k,gamma,seed", [(50, 4, 1.0, 0), (300, 6, 4.0, 3), (1000, 10, 4.0, 0), (1000, 10, 0.5, 9),
+                                            (1500, 10, 4.0, 21)])
+def test_leiden_matches_python_spec(native, n, k, gamma, seed):
+    idx, dist = upstream.knn_brute(_blobs(n, 6, n + k), k)
+    C = upstream.fuzzy_connectivities(idx, dist)
+    w = C.data.astype(np.float64)
+    want = leiden_ref.leiden(C.indptr, C.indices, w, resolution=gamma, seed=seed)
+    np.testing.assert_array_equal(native.leiden_csr(C.indptr, C.indices, w, resolution=gamma, seed=seed), want)
+    np.testing.assert_array_equal(native.leiden_knn(idx, dist, resolution=gamma, seed=seed), want)
+    # unweighted flavour of the same entry
+    S = upstream.knn_pattern_graph(idx)
+    want_u = leiden_ref.leiden(S.indptr, S.indices, None, resolution=gamma, seed=seed)
+    np.testing.assert_array_equal(native.leiden_csr(S.indptr, S.indices, None, resolution=gamma, seed=seed), want_u)
+    # Leiden's guarantees: not worse than the Louvain specification on the same graph, communities connected
+    lou = louvain_ref.louvain(C.indptr, C.indices, w, resolution=gamma, seed=seed)
+    q_le = leiden_ref.quality(C.indptr, C.indices, w, want, gamma)
+    q_lo = leiden_ref.quality(C.indptr, C.indices, w, lou, gamma)
+    assert q_le >= q_lo - 1e-3
+    from scipy.sparse.csgraph import connected_components
+
+    for c in range(int(want.max()) + 1):
+        members = np.nonzero(want == c)[0]
+        ncomp, _ = connected_components(C[members][:, members], directed=False)
+        assert ncomp == 1, f"community {c} is disconnected"
+
+
+def test_leiden_degenerate_inputs(native):
+    # no edges: every node its own community
+    np.testing.assert_array_equal(native.leiden_csr(np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int64)), np.arange(5))
+    with pytest.raises(ValueError):
+        native.leiden_knn(np.array([[0, 7], [1, 0]], dtype=np.int32), np.zeros((2, 2), dtype=np.float32))
+    with pytest.raises(ValueError):
+        native.leiden_knn(np.zeros((3, 2), dtype=np.int32), np.zeros((3, 3), dtype=np.float32))
+
+
+def test_oracle_classifier_leiden_path_runs_and_matches_native_twin(native):
+    """The oracle's leiden path (reference lines + sklearn PCA / kNN + restated umap weights + Leiden spec) against
+    the native host twin fed the oracle's own kNN lists: communities, scores and log p identical."""
+    counts, _, _ = golden_case("c1_louvain")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ora = reference_path.OracleClassifier(n_iters=2, random_state=0, clustering_algorithm="leiden", keep_stages=True)
+        ora.fit(counts)
+    n_cells = counts.shape[0]
+    for i, st in enumerate(ora.stages):
+        labels = native.leiden_knn(st["knn_indices"], st["knn_distances"], resolution=4.0, seed=0)
+        np.testing.assert_array_equal(labels, st["fullcommunities"])
+        s, lp = native.score(labels, n_cells)
+        np.testing.assert_array_equal(s, ora.all_scores_[i])
+        np.testing.assert_allclose(lp, ora.all_log_p_values_[i], rtol=1e-9, atol=1e-12)
