@@ -754,6 +754,81 @@ __global__ void __launch_bounds__(256, 1)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all rows have landed before the CTA retires
 }
 
+// DD_DENSE_V=4 (experimental, written after the round's GPU budget was spent: NOT yet run on hardware): the occupancy fix
+// for variant 3.  The row is still assembled in shared memory and leaves as ONE bulk store, but a warp owns a single row
+// buffer and no staging ring (the ring cost 25 KB per warp, twice the row buffers), so 16-18 warps per SM are resident
+// instead of 4 and cover each other's per-row latency chain (descriptor loads -> list gathers -> merge -> store drain).
+// The lists are read straight from global memory (coalesced, through L1); the descriptor of the next row is loaded one row
+// ahead.  Per SM: rows in flight x 12 KB leave through the bulk-copy engine, nothing is scattered into L2.
+struct V4Desc {
+    double l1;
+    int64_t row;
+    int sa, na, sb, nb;
+    bool synth;
+};
+constexpr int kV4MaxWarps = 18;
+
+__global__ void __launch_bounds__(kV4MaxWarps * 32, 1)
+    k_dense_rows_v4(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+                    const double *__restrict__ l1_rows, const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
+                    int64_t m0, int64_t m_loc, int n_genes, int ld, float median, float pc, float *__restrict__ dense) {
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)ld * 4u;  // multiple of 128
+    float *buf = reinterpret_cast<float *>(tma_smem + (size_t)wl * row_bytes);
+    const int64_t gw = (int64_t)blockIdx.x * nw + wl, n_warps = (int64_t)gridDim.x * nw;
+    const int64_t n_rows = n_loc + m_loc;
+    const int64_t my_rows = gw < n_rows ? (n_rows - gw + n_warps - 1) / n_warps : 0;
+    const float logpc = logf(pc);
+
+    // every lane loads the same words (one broadcast transaction each)
+    auto load_desc = [&](int64_t k) {
+        V4Desc d;
+        const int64_t w = gw + k * n_warps;
+        d.synth = w < m_loc;
+        d.row = d.synth ? n_loc + w : w - m_loc;
+        d.sb = 0;
+        d.nb = 0;
+        if (!d.synth) {
+            const int64_t src = n0 + d.row;
+            d.sa = __ldg(indptr + src);
+            d.na = __ldg(indptr + src + 1) - d.sa;
+            d.l1 = __ldg(l1_rows + src);
+        } else {
+            const int64_t r = m0 + w;
+            const int64_t pa = __ldg(parents + 2 * r), pb = __ldg(parents + 2 * r + 1);
+            d.sa = __ldg(indptr + pa);
+            d.na = __ldg(indptr + pa + 1) - d.sa;
+            d.sb = __ldg(indptr + pb);
+            d.nb = __ldg(indptr + pb + 1) - d.sb;
+            d.l1 = __ldg(l1_rows + pa) + __ldg(l1_rows + pb);
+        }
+        return d;
+    };
+
+    V4Desc cur = my_rows > 0 ? load_desc(0) : V4Desc{};
+    for (int64_t k = 0; k < my_rows; k++) {
+        V4Desc nxt = cur;
+        if (k + 1 < my_rows) nxt = load_desc(k + 1);  // consumed one row later: the loads overlap this row's work
+        // the bulk store of the previous row must have finished READING the buffer before it is refilled
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        dense_row_in_smem(indices + cur.sa, data + cur.sa, cur.na, indices + cur.sb, data + cur.sb, cur.nb, cur.synth, cur.l1,
+                          median, pc, logpc, n_genes, ld, buf, lane);
+        __syncwarp();  // the row is complete in shared memory
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy read
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dense + cur.row * (int64_t)ld),
+                         "r"(csr_smem_u32(buf)), "r"(row_bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+        cur = nxt;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all rows have landed before the CTA retires
+}
+
 int pick_chunk(int64_t ld) { return (int)std::min<int64_t>(ld, kMaxChunk); }
 
 // The dense build is latency-bound with one 12 KB row buffer per warp (16 warps / SM); staging 1024 columns
@@ -974,6 +1049,24 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
                 DD_LAUNCH(h, "dense_rows", k_dense_rows_tma_smem, h->num_sms, nw * 32, per_warp * nw, h->d_indptr, h->d_indices,
                           h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
                           pseudocount, h->d_dense, 0);
+                h->dense_valid = true;
+                h->emb_valid = false;
+                return DD_OK;
+            }
+        }
+        if (variant == 4) {  // rows assembled in shared memory (one buffer per warp, no staging ring), bulk-stored
+            static const int v4_warps = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 16;
+            const size_t row_bytes = (size_t)h->ld * 4;
+            const int nw = (int)std::min<size_t>(std::min(std::max(v4_warps, 1), kV4MaxWarps), (224 * 1024) / row_bytes);
+            if (nw >= 1) {
+                static bool attr4 = false;
+                if (!attr4) {
+                    cudaFuncSetAttribute(k_dense_rows_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                    attr4 = true;
+                }
+                DD_LAUNCH(h, "dense_rows", k_dense_rows_v4, h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
+                          h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
+                          pseudocount, h->d_dense);
                 h->dense_valid = true;
                 h->emb_valid = false;
                 return DD_OK;
