@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -245,17 +246,25 @@ bool iteration(const Graph &g0, double gamma, double two_m, SplitMix64 &rng, std
     if (trace) fprintf(stderr, "leiden: iteration\n");
     for (;;) {
         const int32_t n = g->n;
+        const auto t0 = std::chrono::steady_clock::now();
         degrees(*g, w.k);
         if (move_nodes(*g, gamma, two_m, rng, part, w)) improved = true;
-        if (trace) fprintf(stderr, "leiden:   level n=%d nnz=%zu moves=%lld\n", n, g->indices.size(), (long long)w.n_moves);
+        const auto t1 = std::chrono::steady_clock::now();
         for (int32_t v = 0; v < n0; v++) membership[v] = part[node_of[v]];
         {
             std::vector<int32_t> ids = part;
             if (first_appearance(ids) == n) break;  // every node is its own community
         }
         refine(*g, gamma, two_m, rng, part, w);
+        const auto t2 = std::chrono::steady_clock::now();
         Graph ng;
         ddlv::aggregate(*g, w.refined, ng, node2new);
+        if (trace) {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "leiden:   level n=%d nnz=%zu moves=%lld: move %.1f ms, refine %.1f ms, aggregate %.1f ms -> n=%d\n", n,
+                    g->indices.size(), (long long)w.n_moves, ms(t0, t1), ms(t1, t2), ms(t2, t3), ng.n);
+        }
         if (ng.n == n) break;  // the refinement merged nothing
         part2.assign(ng.n, 0);
         for (int32_t i = 0; i < n; i++) part2[node2new[i]] = part[i];
