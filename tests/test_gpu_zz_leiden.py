@@ -88,3 +88,26 @@ def test_classifier_leiden_vs_oracle():
     assert ok.mean() > 0.9 and corr > 0.5
     assert agree >= 0.95
     assert (clf.communities_ >= 0).all()  # no -1 labels on this path
+
+
+def test_reference_package_test_mirrored():
+    """The reference's own test (tests/test_package.py:6-48) on this package: 500 x 100 Poisson counts, two iterations
+    with standard scaling for each of the three clustering algorithms, predict + doublet_score, and its one value
+    assertion -- two leiden fits with random_state=123 give equal scores.  (The plotting calls of :40-42 are out of
+    scope; the ValueError check of :45-48 lives in tests/test_api_surface.py.)"""
+    from doubletdetection_b200 import BoostClassifier
+
+    counts = np.random.default_rng(8).poisson(1.0, size=(500, 100))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for algo in ("louvain", "phenograph"):
+            clf = BoostClassifier(n_iters=2, clustering_algorithm=algo, standard_scaling=True)
+            labels = clf.fit(counts).predict(p_thresh=1e-16, voter_thresh=0.5)
+            assert labels.shape == (500,) and np.asarray(clf.doublet_score()).shape == (500,)
+        scores = []
+        for _ in range(2):
+            clf = BoostClassifier(n_iters=2, clustering_algorithm="leiden", standard_scaling=True, random_state=123)
+            clf.fit(counts).predict(p_thresh=1e-16, voter_thresh=0.5)
+            scores.append(clf.doublet_score())
+    np.testing.assert_equal(np.ma.filled(scores[0], np.nan), np.ma.filled(scores[1], np.nan))
+    assert np.isfinite(np.ma.filled(scores[0], np.nan)).any()
