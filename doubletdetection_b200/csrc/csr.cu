@@ -932,12 +932,11 @@ int dd_set_parents(dd_handle *h, int64_t n_synth, const int64_t *parents) {
 int dd_dev_create_doublets_csr(dd_handle *h) {
     const int chunk = pick_chunk(h->ld);
     const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(k_synth_count, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
         cudaFuncSetAttribute(k_synth_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
-        attr_set = true;
-    }
+    });
     const int grid = grid_for(h, smem);
     if (h->M > 0) {
         DD_LAUNCH(h, "synth_count", k_synth_count, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data,
@@ -1041,11 +1040,10 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
             const size_t per_warp = kTmaWarpBytes + 2 * (size_t)h->ld * 4 + kTmaTable * sizeof(TmaRowDesc) + kTmaDepth * 8 + 40;
             const int nw = (int)std::min<size_t>(8, (220 * 1024) / per_warp);
             if (nw >= 1) {
-                static bool attr3 = false;
-                if (!attr3) {
+                static dd_once_per_device attr3;  // function attributes are per device
+                attr3.run(h->device, [&] {
                     cudaFuncSetAttribute(k_dense_rows_tma_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-                    attr3 = true;
-                }
+                });
                 DD_LAUNCH(h, "dense_rows", k_dense_rows_tma_smem, h->num_sms, nw * 32, per_warp * nw, h->d_indptr, h->d_indices,
                           h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
                           pseudocount, h->d_dense, 0);
@@ -1059,11 +1057,10 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
             const size_t row_bytes = (size_t)h->ld * 4;
             const int nw = (int)std::min<size_t>(std::min(std::max(v4_warps, 1), kV4MaxWarps), (224 * 1024) / row_bytes);
             if (nw >= 1) {
-                static bool attr4 = false;
-                if (!attr4) {
+                static dd_once_per_device attr4;  // function attributes are per device
+                attr4.run(h->device, [&] {
                     cudaFuncSetAttribute(k_dense_rows_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-                    attr4 = true;
-                }
+                });
                 DD_LAUNCH(h, "dense_rows", k_dense_rows_v4, h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
                           h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
                           pseudocount, h->d_dense);
@@ -1074,11 +1071,10 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
         }
         if (variant == 2) {  // TMA-staged CSR segments, one 8-warp CTA per SM
             static const int dbg = getenv("DD_DENSE_DBG") ? atoi(getenv("DD_DENSE_DBG")) : 0;
-            static bool tma_attr = false;
-            if (!tma_attr) {
+            static dd_once_per_device tma_attr;  // function attributes are per device
+            tma_attr.run(h->device, [&] {
                 cudaFuncSetAttribute(k_dense_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes);
-                tma_attr = true;
-            }
+            });
             DD_LAUNCH(h, "dense_rows", k_dense_rows_tma, h->num_sms, kTmaWarps * 32, kTmaSmemBytes, h->d_indptr, h->d_indices,
                       h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
                       pseudocount, h->d_dense, dbg);
@@ -1093,11 +1089,10 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
     } else {
         const int chunk = pick_dense_chunk(h->ld);
         const size_t smem = sizeof(float) * chunk * kWarpsPerCta;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static dd_once_per_device attr_set;  // function attributes are per device
+        attr_set.run(h->device, [&] {
             cudaFuncSetAttribute(k_dense_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, sizeof(float) * kMaxChunk * kWarpsPerCta);
-            attr_set = true;
-        }
+        });
         const int grid = grid_for(h, smem);
         DD_LAUNCH(h, "dense_rows", k_dense_rows, grid, kThreads, smem, h->d_indptr, h->d_indices, h->d_data, h->d_l1,
                   h->d_parents, h->N, h->M, (int)h->G, (int)h->ld, chunk, median, pseudocount, h->nonneg ? 1 : 0, h->d_dense);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -130,6 +131,22 @@ struct dd_handle {
     std::vector<dd_timed_launch> pending;    // recorded, not yet resolved
     std::vector<cudaEvent_t> event_pool;     // recycled events
     std::map<std::string, double> stage_ms;
+};
+
+// cudaFuncSetAttribute applies to the CURRENT device only: a call site remembers per device (not per process) that it has
+// configured its kernels, so handles on several GPUs of one process all get their opt-in shared-memory sizes.  The lock is
+// held while the attributes are set (another thread must not launch on that device before they are in place).
+struct dd_once_per_device {
+    std::mutex mu;
+    uint64_t done[4] = {0, 0, 0, 0};  // device ordinals 0..255
+    template <class F>
+    void run(int device, F &&f) {
+        std::lock_guard<std::mutex> lk(mu);
+        const unsigned d = (unsigned)device & 255u;
+        if (done[d >> 6] & (1ull << (d & 63))) return;
+        f();
+        done[d >> 6] |= 1ull << (d & 63);
+    }
 };
 
 // thread-local message for failures that happen without a handle

@@ -643,11 +643,10 @@ template <int KP, int TL>
 int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     const int64_t n = h->emb_rows;
     using S = KnnSmem<KP, TL>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(k_knn_scan<KP, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S));
-        attr_set = true;
-    }
+    });
     DD_LAUNCH(h, "knn_norms", k_row_norms<KP>, (unsigned)((n + 255) / 256), 256, 0, h->d_emb, n, norms);
     DD_LAUNCH(h, "knn_scan", (k_knn_scan<KP, TL>), (unsigned)((n + BQ - 1) / BQ), 256, sizeof(S), h->d_emb, norms, n,
               cand_d, cand_i);
@@ -664,12 +663,11 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     const int64_t op_bytes = (int64_t)n_tiles_pad * tc::TILE_BYTES;
     DD_TRY(dd_reserve(h, &h->d_knn_ops, &h->cap_knn_ops, 2 * op_bytes));
     uint8_t *qa = h->d_knn_ops, *cb = h->d_knn_ops + op_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tc::k_knn_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         cudaFuncSetAttribute(tc::k_knn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-        attr_set = true;
-    }
+    });
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
               reinterpret_cast<uint4 *>(qa), reinterpret_cast<uint4 *>(cb));
     // Cell-block sharding: every rank holds the whole (all-gathered) embedding and answers the queries of its

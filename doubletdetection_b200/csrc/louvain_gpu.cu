@@ -451,12 +451,11 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
     static const int coop = getenv("DD_LOUVAIN_COOP") ? atoi(getenv("DD_LOUVAIN_COOP")) : 0;
     if (coop != 0) {
         static const int light_ctas = getenv("DD_LOUVAIN_COOP_CTAS") ? atoi(getenv("DD_LOUVAIN_COOP_CTAS")) : 128;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static dd_once_per_device attr_set;  // function attributes are per device
+        attr_set.run(h->device, [&] {
             cudaFuncSetAttribute(k_lv_rounds<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<1024>());
             cudaFuncSetAttribute(k_lv_rounds<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem<256>());
-            attr_set = true;
-        }
+        });
         ColourOffsets co;
         for (int c = 0; c <= kColours; c++) co.v[c] = h->lv_colour_off[c];
         int n_arg = n;

@@ -573,13 +573,12 @@ int run_pca(dd_handle *h, int n_power_iter) {
     const int ld = (int)h->ld;
     const int L = h->L, C = h->C, KP = h->KP;
     double *sm = h->d_small;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(k_gemm_dq<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm1_smem<LP>());
         cudaFuncSetAttribute(k_gemm_dty<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm2_smem<LP>());
         cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJacobiSmem);
-        attr_set = true;
-    }
+    });
     const int grid1 = (int)((A + G1_BM - 1) / G1_BM);
     const int gblocks = (ld + G2_BG - 1) / G2_BG;
     int splits = std::max(1, (h->num_sms * 4 + gblocks - 1) / gblocks);

@@ -411,12 +411,11 @@ int dd_tc_prepare(dd_handle *h) {
     st->dense = h->d_dense;
     st->rows = h->A;
     st->ld = h->ld;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tcg::k_tc_gemm<false, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg::SMEM_BYTES);
         cudaFuncSetAttribute(tcg::k_tc_gemm<true, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcg::SMEM_BYTES);
-        attr_set = true;
-    }
+    });
     return DD_OK;
 }
 

@@ -1,0 +1,65 @@
+"""CPU study behind DESIGN.md section 5 ("cluster-aware tile pruning"): how many (query tile, candidate tile) pairs of
+the exact kNN could be skipped with valid lower bounds on a BASELINE-shaped embedding?  No GPU, no oracle: the augmented
+matrix of one iteration is rebuilt with scipy / sklearn from bench.make_counts.
+
+    python scripts/knn_prune_study.py [c2]
+
+Points are ordered by k-means clusters of the 8 signal components (tiles never straddle clusters); a tile pair is needed
+iff the box-to-box distance^2 in the leading m components is <= the largest exact 10th-neighbour distance^2 of the query
+tile.  Result at c2 (12.5k points): 45-70 % of the tile pairs stay even with 36-64 clusters, and padding clusters to
+whole tiles eats the rest (the synthetic doublets sit BETWEEN the cell types, inflate the boxes they land in and carry
+2-3x larger neighbour distances).  Per-query (point-to-box) pruning would keep 24 %, but the tensor-core kernel scores
+256 queries x 128 candidates at a time.  So tile pruning is not pursued for this workload."""
+import os
+import sys
+
+import numpy as np
+from sklearn.cluster import KMeans
+from sklearn.decomposition import PCA
+from sklearn.neighbors import NearestNeighbors
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+counts = bench.make_counts(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c2"]).tocsr()
+n_cells = counts.shape[0]
+par = np.random.default_rng(0).choice(n_cells, size=(n_cells // 4, 2), replace=False)
+aug = np.vstack([counts.toarray(), (counts[par[:, 0]] + counts[par[:, 1]]).toarray()]).astype(np.float32)
+lib = aug.sum(1, keepdims=True)
+aug = np.log(aug / lib * np.median(lib) + 0.1)
+emb = PCA(30, random_state=0).fit_transform(aug).astype(np.float64)
+n = emb.shape[0]
+print("variance per component:", np.round(emb.var(0), 1))
+dist, _ = NearestNeighbors(n_neighbors=10, algorithm="brute").fit(emb).kneighbors(emb)
+tau = dist[:, -1] ** 2
+print("10th-neighbour distance^2: median %.1f (cells %.1f, doublets %.1f), max %.1f"
+      % (np.median(tau), np.median(tau[:n_cells]), np.median(tau[n_cells:]), tau.max()))
+
+
+def tiles(labels, size):
+    out = []
+    for c in np.unique(labels):
+        ids = np.nonzero(labels == c)[0]
+        ids = ids[np.argsort(emb[ids, 7])]
+        out += [ids[s:s + size] for s in range(0, len(ids), size)]
+    return out
+
+
+def kept(cand, query, m=8):
+    lo = np.array([emb[t, :m].min(0) for t in cand])
+    hi = np.array([emb[t, :m].max(0) for t in cand])
+    qlo = np.array([emb[t, :m].min(0) for t in query])
+    qhi = np.array([emb[t, :m].max(0) for t in query])
+    qt = np.array([tau[t].max() for t in query])
+    gap = np.maximum(0, np.maximum(lo[None] - qhi[:, None], qlo[:, None] - hi[None]))
+    need = (gap ** 2).sum(-1) <= qt[:, None]
+    pairs = (need * np.array([len(t) for t in query])[:, None] * np.array([len(t) for t in cand])[None]).sum() / (n * n)
+    slots = need.sum() * len(query[0]) * len(cand[0]) / (n * n)
+    return pairs, slots
+
+
+for kc in (8, 16, 36, 64, 128):
+    lab = KMeans(kc, n_init=2, random_state=0).fit(emb[:, :8]).labels_
+    for qt in (128, 256):
+        p, s = kept(tiles(lab, 128), tiles(lab, qt))
+        print(f"k-means {kc:3d} clusters, query tile {qt}: point pairs kept {p:.2f}, tile slots incl. padding {s:.2f} of n^2")
