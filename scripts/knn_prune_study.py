@@ -6,10 +6,15 @@ matrix of one iteration is rebuilt with scipy / sklearn from bench.make_counts.
 
 Points are ordered by k-means clusters of the 8 signal components (tiles never straddle clusters); a tile pair is needed
 iff the box-to-box distance^2 in the leading m components is <= the largest exact 10th-neighbour distance^2 of the query
-tile.  Result at c2 (12.5k points): 45-70 % of the tile pairs stay even with 36-64 clusters, and padding clusters to
-whole tiles eats the rest (the synthetic doublets sit BETWEEN the cell types, inflate the boxes they land in and carry
-2-3x larger neighbour distances).  Per-query (point-to-box) pruning would keep 24 %, but the tensor-core kernel scores
-256 queries x 128 candidates at a time.  So tile pruning is not pursued for this workload."""
+tile.  Measured (tile slots kept, padding included, 256-query x 128-candidate tiles as in k_knn_tc):
+
+    c2 (12.5k points)   8 clusters 0.90   36 clusters 0.96   64 clusters 0.86   (clusters of ~200 points: padding eats it)
+    c3 (125k points)    8 clusters 0.50   36 clusters 0.27   64 clusters 0.21   128 clusters 0.21
+
+The synthetic doublets sit BETWEEN the cell types and are what keeps pairs alive (36 % of all pairs involve one); the
+cells of different types never need each other.  With points in their natural order (what round 1 tried) every pair is
+kept.  At c3 a cluster-ordered kNN would therefore score ~1/5 of the tile pairs -- the largest remaining lever on the kNN
+kernel ("next")."""
 import os
 import sys
 
