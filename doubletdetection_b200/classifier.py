@@ -240,14 +240,18 @@ class BoostClassifier:
         n_aug = num_cells + num_synths
         omega, n_power_iter = _pca_plan(n_aug, num_genes, self.n_components, self.random_state)
 
-        # every iteration's `choices` (:394), drawn sequentially from the classifier's stream
-        parents = np.empty((self.n_iters, num_synths, 2), dtype=np.int64)
-        for i in range(self.n_iters):
-            parents[i] = self.rng.choice(num_cells, size=(num_synths, 2), replace=self.replace)
-
         _t.append(_time.perf_counter())
         h = self._native()
-        h.upload_counts(raw_counts)
+        # the host->device copy of the counts (ctypes releases the GIL) runs underneath the parent draws
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            upload = pool.submit(h.upload_counts, raw_counts)
+            # every iteration's `choices` (:394), drawn sequentially from the classifier's stream
+            parents = np.empty((self.n_iters, num_synths, 2), dtype=np.int64)
+            for i in range(self.n_iters):
+                parents[i] = self.rng.choice(num_cells, size=(num_synths, 2), replace=self.replace)
+            upload.result()  # re-raises what the upload raised
         _t.append(_time.perf_counter())
 
         it0, it1 = 0, self.n_iters
@@ -292,8 +296,8 @@ class BoostClassifier:
         self._parents_array = parents
         self._parents_lists = None
         _t.append(_time.perf_counter())
-        # host-side wall time of the phases of this fit (ms): validation + HVG + parent draws, upload,
-        # the pipelined native loop, result collection
+        # host-side wall time of the phases of this fit (ms): validation + HVG, upload (with the parent draws
+        # underneath), the pipelined native loop, result collection
         self.host_ms_ = dict(zip(("prologue", "upload", "fit_iterations", "collect"),
                                  [1e3 * (b - a) for a, b in zip(_t[:-1], _t[1:])]))
         return self
