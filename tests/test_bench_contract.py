@@ -1,0 +1,68 @@
+"""bench.py's contract, as far as it can be checked without a GPU: the reference arm (the oracle port of the
+reference's CPU path) runs and prints ONE JSON line with the keys the driver reads, the synthetic inputs are the
+seeded ones of oracle/datasets.py, and the roofline arithmetic matches DESIGN.md's algorithmic bytes."""
+
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from oracle import datasets  # noqa: E402
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "augmented-cells/s" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["metric"].startswith("augmented-cells/sec through BoostClassifier.fit")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload",
+                          "c1", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_inputs_are_the_oracle_datasets():
+    for name in ("c1", "c2"):
+        wl = bench.WORKLOADS[name]
+        a = bench.make_counts(wl)
+        b = (datasets.poisson_counts(wl["n_cells"], wl["n_genes"], seed=0) if wl["kind"] == "poisson"
+             else datasets.structured_counts(wl["n_cells"], wl["n_genes"], seed=1234))
+        import scipy.sparse as sp
+
+        b = sp.csr_matrix(b)
+        b.sort_indices()
+        assert a.shape == b.shape and a.nnz == b.nnz
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+
+
+def test_roofline_arithmetic():
+    peaks = {"hbm_gbs": 6500.0, "bf16_tflops_sustained": 1400.0}
+    n, m, g, nnz, nnz_par = 100000, 25000, 3000, 32.4e6, 16.2e6
+    a = n + m
+    report = {"dense_rows": (10 * 0.75, 10), "tc_gemm_dq": (3.0, 10), "knn_tc": (48.0, 10), "unknown": (1.0, 1)}
+    r = bench.kernel_rooflines(report, n, m, g, nnz, nnz_par, peaks)
+    assert set(r) == {"dense_rows", "tc_gemm_dq", "knn_tc"}
+    dense_bytes = (nnz + nnz_par) * 8 + a * g * 4  # CSR entries of originals + both parents, dense matrix once
+    assert r["dense_rows"]["algorithmic_bytes"] == dense_bytes and r["dense_rows"]["bound"] == "hbm"
+    assert np.isclose(r["dense_rows"]["achieved"], dense_bytes / 0.75e-3 / 1e9)
+    assert np.isclose(r["dense_rows"]["frac"], r["dense_rows"]["achieved"] / 6500.0)
+    assert r["tc_gemm_dq"]["algorithmic_bytes"] == (a * g + g * 40 + a * 40) * 4
+    assert r["knn_tc"]["bound"] == "tensor" and r["knn_tc"]["algorithmic_flops"] == 2.0 * a * a * 32
+    assert np.isclose(r["knn_tc"]["achieved"], 2.0 * a * a * 32 / 4.8e-3 / 1e12)
