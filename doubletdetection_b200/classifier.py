@@ -306,12 +306,21 @@ class BoostClassifier:
     def predict(self, p_thresh=1e-7, voter_thresh=0.9):
         log_p_thresh = np.log(p_thresh)
         if self.n_iters > 1:
-            with np.errstate(invalid="ignore"):
-                self.voting_average_ = np.mean(
-                    np.ma.masked_invalid(self.all_log_p_values_) <= log_p_thresh, axis=0
-                )
-                self.labels_ = np.ma.filled((self.voting_average_ >= voter_thresh).astype(float), np.nan)
-                self.voting_average_ = np.ma.filled(self.voting_average_, np.nan)
+            # :232-241 -- np.mean(np.ma.masked_invalid(log_p) <= thresh, axis=0), the vote >= voter_thresh, both filled
+            # with NaN where every iteration is masked.  Same values without the masked-array machinery (42 -> 6 ms at
+            # 25 x 100k): a masked mean is (number of valid votes) * 1.0 / (number of valid entries) in float64.
+            log_p = np.asarray(self.all_log_p_values_)
+            valid = np.isfinite(log_p)  # masked_invalid masks NaN, +inf and -inf (quirk Q5)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                votes = np.count_nonzero((log_p <= log_p_thresh) & valid, axis=0)
+                count = np.count_nonzero(valid, axis=0)
+                average = votes * 1.0 / count
+                labels = (average >= voter_thresh).astype(float)
+            none_valid = count == 0
+            labels[none_valid] = np.nan
+            average[none_valid] = np.nan
+            self.voting_average_ = average
+            self.labels_ = labels
         else:
             potential_cutoffs = np.unique(self.all_scores_[~np.isnan(self.all_scores_)])
             if len(potential_cutoffs) > 1:
@@ -327,8 +336,16 @@ class BoostClassifier:
     # ------------------------------------------------------------------ doublet_score (:256-272)
     def doublet_score(self):
         if self.n_iters > 1:
-            with np.errstate(invalid="ignore"):
-                avg_log_p = np.mean(np.ma.masked_invalid(self.all_log_p_values_), axis=0)
+            # :268 -- np.mean(np.ma.masked_invalid(log_p), axis=0): a MaskedArray (quirk Q5) whose values are
+            # filled(0).sum(axis=0) * 1.0 / count, masked where no iteration is valid; built directly
+            log_p = np.asarray(self.all_log_p_values_)
+            valid = np.isfinite(log_p)
+            count = np.count_nonzero(valid, axis=0)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                avg = np.where(valid, log_p, 0.0).sum(axis=0) * 1.0 / count
+            none_valid = count == 0
+            avg[none_valid] = 0.0
+            avg_log_p = np.ma.MaskedArray(avg, mask=none_valid if none_valid.any() else np.ma.nomask)
         else:
             avg_log_p = self.all_log_p_values_[0]
         return -avg_log_p

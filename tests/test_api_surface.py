@@ -134,3 +134,42 @@ def test_iteration_shard_partitions():
         assert blocks[0][0] == 0 and blocks[-1][1] == n_iters
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
     assert [b - a for a, b in (iteration_shard(24, r, 8) for r in range(8))] == [3] * 8
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fast_predict_and_score_equal_the_reference_lines(seed):
+    """predict / doublet_score avoid numpy's masked-array machinery; the literal restatement of the reference's lines
+    (oracle.reference_path.predict / doublet_score, pinned to the reference's real code by the goldens) must give the
+    same bits on inputs with NaN, +-inf, fully invalid cells and thresholds that hit votes exactly."""
+    from oracle import reference_path
+
+    rs = np.random.default_rng(seed)
+    n_iters, n = int(rs.integers(2, 12)), 4000
+    lp = -rs.exponential(8.0, (n_iters, n))
+    lp[rs.random(lp.shape) < 0.05] = -np.inf
+    lp[rs.random(lp.shape) < 0.05] = np.nan
+    lp[rs.random(lp.shape) < 0.01] = np.inf
+    lp[:, :7] = np.nan  # no valid iteration at all
+    lp[:, 7:11] = -np.inf
+    lp[0, 11] = -3.0  # exactly one valid iteration
+    lp[1:, 11] = np.nan
+    clf = BoostClassifier(n_iters=n_iters, clustering_algorithm="louvain")
+    clf.all_log_p_values_ = lp.copy()
+    clf.all_scores_ = rs.random(lp.shape)
+    for p_thresh, voter_thresh in [(1e-7, 0.9), (1e-3, 0.5), (np.exp(-3.0), 1.0), (1e-16, 0.0)]:
+        want = reference_path.predict(lp, clf.all_scores_, n_iters, p_thresh, voter_thresh)
+        got = clf.predict(p_thresh, voter_thresh)
+        assert isinstance(got, np.ndarray) and not isinstance(got, np.ma.MaskedArray) and got.dtype == np.float64
+        np.testing.assert_array_equal(got, want["labels"])
+        np.testing.assert_array_equal(clf.voting_average_, want["voting_average"])
+    want = reference_path.doublet_score(lp, n_iters)
+    got = clf.doublet_score()
+    assert isinstance(got, np.ma.MaskedArray)
+    np.testing.assert_array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(want))
+    np.testing.assert_array_equal(np.ma.filled(got, np.nan), np.ma.filled(want, np.nan))
+    # nothing invalid: still a MaskedArray, nothing masked
+    clf.all_log_p_values_ = -rs.exponential(8.0, (n_iters, 50))
+    got = clf.doublet_score()
+    want = reference_path.doublet_score(clf.all_log_p_values_, n_iters)
+    assert isinstance(got, np.ma.MaskedArray) and not np.ma.getmaskarray(got).any()
+    np.testing.assert_array_equal(np.asarray(got), np.asarray(want))
