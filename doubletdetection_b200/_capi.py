@@ -74,6 +74,7 @@ SIGNATURES = {
     ),
     "dd_upload_embedding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p]),
     "dd_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_f32p]),
+    "dd_knn_listed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p]),
     "dd_louvain_knn": (
         ctypes.c_int,
         [ctypes.c_int64, ctypes.c_int32, c_i32p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
@@ -416,6 +417,19 @@ class Handle:
         idx = np.empty((n, k), dtype=np.int32)
         dist = np.empty((n, k), dtype=np.float32) if with_dist else None
         self._check(self._lib.dd_knn(self._h, k, _ptr(idx, ctypes.c_int32), _ptr(dist, ctypes.c_float)))
+        return idx, dist
+
+    def knn_listed(self, k, list_off, list_tiles, with_dist=True):
+        """Experimental: exact kNN in which 256-row query block p only visits the 128-row candidate tiles
+        ``list_tiles[list_off[p]:list_off[p + 1]]`` (scripts/knn_listed_experiment.py)."""
+        n = self._emb_rows
+        list_off = np.ascontiguousarray(list_off, dtype=np.int32)
+        list_tiles = np.ascontiguousarray(list_tiles, dtype=np.int32)
+        idx = np.empty((n, k), dtype=np.int32)
+        dist = np.empty((n, k), dtype=np.float32) if with_dist else None
+        self._check(self._lib.dd_knn_listed(self._h, k, list_off.size - 1, _ptr(list_off, ctypes.c_int32),
+                                            _ptr(list_tiles, ctypes.c_int32), _ptr(idx, ctypes.c_int32),
+                                            _ptr(dist, ctypes.c_float)))
         return idx, dist
 
     def jaccard_graph(self, k, prune=True):

@@ -103,6 +103,10 @@ struct dd_handle {
     int64_t cap_knn = 0;
     uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout
     int64_t cap_knn_ops = 0;
+    // experimental (dd_knn_listed): candidate-tile lists per 256-row query block; knn_list_pairs > 0 while such a call runs
+    int32_t *d_knn_list_off = nullptr, *d_knn_list_tiles = nullptr;
+    int64_t cap_knn_list_off = 0, cap_knn_list_tiles = 0;
+    int knn_list_pairs = 0;
 
     // ---- GPU Louvain level 0 (louvain_gpu.cu): symmetric kNN pattern as CSR + community state ----
     int32_t *d_lv_off = nullptr, *d_lv_adj = nullptr, *d_lv_comm = nullptr, *d_lv_i32 = nullptr;

@@ -475,10 +475,14 @@ __device__ __forceinline__ void reglist_insert(RegList<N> &L, float t, int idx) 
 // 8-warp peel-and-insert epilogue below (5.25 ms at c3, 3.4 ms TMEM-read floor, 4.1 ms with the 3.3 -> 4 wave rounding).
 constexpr int THREADS = 320;  // producer warp + MMA warp + 8 epilogue warps
 
-template <int LIST>  // candidates kept per query row: 16 (k <= 13, sc.pp.neighbors) or 32 (k <= 31, PhenoGraph)
+// LISTED (experimental, dd_knn_listed): instead of ALL candidate tiles a query-tile pair visits the tiles of its own list
+// (list_tiles[list_off[pair] .. list_off[pair + 1])) -- the three roles below loop over the same step counter, so the list
+// only changes which tile a step loads and which candidate indices it stands for.
+template <int LIST, bool LISTED = false>  // LIST: candidates kept per query row, 16 (k <= 13) or 32 (k <= 31, PhenoGraph)
 __global__ void __launch_bounds__(THREADS, 1)
     k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb, int64_t n, int n_tiles, int pair0,
-             int n_full, int *__restrict__ cand_i) {
+             int n_full, int *__restrict__ cand_i, const int *__restrict__ list_off = nullptr,
+             const int *__restrict__ list_tiles = nullptr) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                // QT tiles
     uint8_t *sB = smem + (size_t)QT * TILE_BYTES;      // NS stages
@@ -497,6 +501,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     const bool half_cta = (int)blockIdx.x >= n_full;
     const int n_qt = half_cta ? 1 : QT;
     const int tile0 = half_cta ? (pair0 + n_full) * QT + ((int)blockIdx.x - n_full) : ((int)blockIdx.x + pair0) * QT;
+    const int *my_list = nullptr;
+    if constexpr (LISTED) {  // launched without half CTAs: one list per pair
+        const int off = list_off[pair0 + (int)blockIdx.x];
+        n_tiles = list_off[pair0 + (int)blockIdx.x + 1] - off;
+        my_list = list_tiles + off;
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -526,7 +536,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const uint32_t ph = (step / NS) & 1;
                 mbar_wait(empty + s, ph ^ 1);
                 mbar_expect_tx(full + s, TILE_BYTES);
-                bulk_g2s(sB + (size_t)s * TILE_BYTES, cb + (size_t)step * TILE_BYTES, TILE_BYTES, full + s);
+                int tile = step;
+                if constexpr (LISTED) tile = my_list[step];
+                bulk_g2s(sB + (size_t)s * TILE_BYTES, cb + (size_t)tile * TILE_BYTES, TILE_BYTES, full + s);
             }
         }
     } else if (warp == 1) {
@@ -580,7 +592,8 @@ __global__ void __launch_bounds__(THREADS, 1)
             // software pipeline: the tcgen05.ld of the next 32 columns is in flight while this group is scanned
             uint32_t va[32], vb[32];
             const uint32_t col0 = lane_base + buf * 256;
-            const int cand0 = step * TILE;
+            int cand0 = step * TILE;
+            if constexpr (LISTED) cand0 = my_list[step] * TILE;
             auto scan = [&](uint32_t (&v)[32], int c) {
                 // balanced max tree (depth 5) instead of a 31-long dependent chain
                 float m8[8];
@@ -667,6 +680,8 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tc::k_knn_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         cudaFuncSetAttribute(tc::k_knn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
               reinterpret_cast<uint4 *>(qa), reinterpret_cast<uint4 *>(cb));
@@ -677,6 +692,23 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     const int pair0 = (int)((int64_t)n_pairs * R / W), pair1 = (int)((int64_t)n_pairs * (R + 1) / W);
     const int64_t q0 = std::min<int64_t>(n, (int64_t)pair0 * tc::QT * tc::TILE);
     const int64_t q1 = std::min<int64_t>(n, (int64_t)pair1 * tc::QT * tc::TILE);
+    if (h->knn_list_pairs > 0) {  // experimental: per-pair candidate-tile lists (dd_knn_listed)
+        if (W > 1 || h->knn_list_pairs != n_pairs)
+            return dd_fail(h, DD_ERR_ARG, "knn: candidate lists need an unsharded handle and one list per 256-row query block");
+        if (TL == 16)
+            DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<16, true>), (unsigned)n_pairs, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
+                      0, n_pairs, cand_i, h->d_knn_list_off, h->d_knn_list_tiles);
+        else
+            DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<32, true>), (unsigned)n_pairs, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
+                      0, n_pairs, cand_i, h->d_knn_list_off, h->d_knn_list_tiles);
+        if (TL == 16)
+            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, (int64_t)0, n, k,
+                      h->d_knn_idx, h->d_knn_dist);
+        else
+            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, (int64_t)0, n, k,
+                      h->d_knn_idx, h->d_knn_dist);
+        return DD_OK;
+    }
     if (pair1 > pair0) {
         // whole waves of pair CTAs, then the remainder as single-tile CTAs (twice as many, half as long)
         const int pairs = pair1 - pair0;
@@ -750,6 +782,43 @@ extern "C" int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out
     DD_TRY(dd_dev_knn(h, k));
     DD_TRY(dd_stage_end(h, "knn"));
     const int64_t n = h->emb_rows;
+    DD_CUDA(h, cudaMemcpyAsync(idx_out, h->d_knn_idx, sizeof(int32_t) * n * k, cudaMemcpyDeviceToHost, h->stream));
+    if (dist_out)
+        DD_CUDA(h, cudaMemcpyAsync(dist_out, h->d_knn_dist, sizeof(float) * n * k, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+// Experimental test hook ("next lever"): exact kNN in which the 256-row query block p only visits the
+// candidate tiles (128 rows each) list_tiles[list_off[p] .. list_off[p + 1]).  The caller is responsible for the lists being
+// sufficient (scripts/knn_listed_experiment.py derives them from bounding boxes); rows whose lists hold fewer than k - 1
+// other points get -1 entries.  Same outputs as dd_knn.
+extern "C" int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const int32_t *list_off, const int32_t *list_tiles,
+                             int32_t *idx_out, float *dist_out) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_knn_listed: null handle");
+    if (!idx_out || !list_off || n_blocks < 1) return dd_fail(h, DD_ERR_ARG, "dd_knn_listed: null argument");
+    if (!h->emb_valid || h->KP != 32) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_knn_listed: needs an embedding of <= 32 components");
+    const int64_t n = h->emb_rows;
+    const int64_t n_tiles = (n + 127) / 128;
+    if (n_blocks != (n_tiles + 1) / 2) return dd_fail(h, DD_ERR_ARG, "dd_knn_listed: one list per 256-row query block");
+    const int64_t total = list_off[n_blocks];
+    if (list_off[0] != 0 || total < 0 || (total > 0 && !list_tiles)) return dd_fail(h, DD_ERR_ARG, "dd_knn_listed: bad list offsets");
+    for (int64_t p = 0; p < n_blocks; p++)
+        if (list_off[p + 1] < list_off[p]) return dd_fail(h, DD_ERR_ARG, "dd_knn_listed: bad list offsets");
+    for (int64_t e = 0; e < total; e++)
+        if (list_tiles[e] < 0 || list_tiles[e] >= n_tiles) return dd_fail(h, DD_ERR_ARG, "dd_knn_listed: tile index out of range");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_TRY(dd_reserve(h, &h->d_knn_list_off, &h->cap_knn_list_off, n_blocks + 1));
+    DD_TRY(dd_reserve(h, &h->d_knn_list_tiles, &h->cap_knn_list_tiles, std::max<int64_t>(total, 1)));
+    DD_CUDA(h, cudaMemcpyAsync(h->d_knn_list_off, list_off, sizeof(int32_t) * (n_blocks + 1), cudaMemcpyHostToDevice, h->stream));
+    if (total > 0)
+        DD_CUDA(h, cudaMemcpyAsync(h->d_knn_list_tiles, list_tiles, sizeof(int32_t) * total, cudaMemcpyHostToDevice, h->stream));
+    h->knn_list_pairs = (int)n_blocks;
+    int rc = dd_stage_begin(h);
+    if (rc == DD_OK) rc = dd_dev_knn(h, k);
+    if (rc == DD_OK) rc = dd_stage_end(h, "knn");
+    h->knn_list_pairs = 0;
+    DD_TRY(rc);
     DD_CUDA(h, cudaMemcpyAsync(idx_out, h->d_knn_idx, sizeof(int32_t) * n * k, cudaMemcpyDeviceToHost, h->stream));
     if (dist_out)
         DD_CUDA(h, cudaMemcpyAsync(dist_out, h->d_knn_dist, sizeof(float) * n * k, cudaMemcpyDeviceToHost, h->stream));

@@ -96,6 +96,14 @@ int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const floa
  * idx_out int32[A*k], dist_out float32[A*k] (may be NULL). */
 int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
 
+/* Experimental test hook (no counterpart in the reference): the same exact kNN, but the 256-row query block p only visits
+ * the 128-row candidate tiles list_tiles[list_off[p] .. list_off[p + 1]) (host arrays, n_blocks = ceil(ceil(A / 128) / 2)
+ * lists).  The caller guarantees that the lists are sufficient -- scripts/knn_listed_experiment.py derives them from
+ * bounding boxes of a cluster-ordered embedding; neighbours missing from a list are simply not
+ * found (-1 where fewer than k - 1 exist).  Outputs as dd_knn. */
+int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const int32_t *list_off, const int32_t *list_tiles,
+                  int32_t *idx_out, float *dist_out);
+
 /* ---- clustering call, doubletdetection.py:337-343 -----------------------------------------
  * Louvain (RB configuration null model, resolution gamma, unweighted, seeded) on the symmetrised
  * kNN pattern -- what sc.tl.louvain(resolution, random_state, directed=False) optimises.  The
