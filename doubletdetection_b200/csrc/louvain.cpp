@@ -321,6 +321,50 @@ void level0_parallel_host(const Graph &g, double gamma, double two_m, uint64_t s
     }
 }
 
+// The first aggregation of the kNN pipeline: a unit-weight graph without self-loops whose ~10^2 first-level communities fit
+// a dense count table.  Produces exactly what ddlv::aggregate produces (ids by first appearance, ascending neighbour lists,
+// integer-valued weights -- counts are exact in any order) in one tight pass over the edges instead of per-community
+// member lists.  Returns false (nothing written) when the graph does not qualify.
+bool aggregate_unit_dense(const Graph &g, const std::vector<int32_t> &comm, Graph &out, std::vector<int32_t> &node2new) {
+    constexpr int32_t kMaxDense = 1024;
+    const int32_t n = g.n;
+    if (!g.weights.empty()) return false;
+    std::vector<int32_t> new_id(n, -1);
+    node2new.resize(n);
+    int32_t nc = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (g.selfw[i] != 0.0) return false;
+        if (new_id[comm[i]] < 0) {
+            if (nc == kMaxDense) return false;
+            new_id[comm[i]] = nc++;
+        }
+        node2new[i] = new_id[comm[i]];
+    }
+    std::vector<int64_t> tab((size_t)nc * nc, 0);
+    const int32_t *n2n = node2new.data();
+    for (int32_t i = 0; i < n; i++) {
+        int64_t *row = tab.data() + (size_t)n2n[i] * nc;
+        for (int64_t e = g.indptr[i]; e < g.indptr[i + 1]; e++) row[n2n[g.indices[e]]]++;
+    }
+    out.n = nc;
+    out.indptr.assign(nc + 1, 0);
+    out.indices.clear();
+    out.weights.clear();
+    out.selfw.assign(nc, 0.0);
+    for (int32_t a = 0; a < nc; a++) {
+        const int64_t *row = tab.data() + (size_t)a * nc;
+        out.selfw[a] = (double)row[a];
+        for (int32_t b = 0; b < nc; b++)
+            if (b != a && row[b] != 0) {
+                out.indices.push_back(b);
+                out.weights.push_back((double)row[b]);
+            }
+        out.indptr[a + 1] = (int64_t)out.indices.size();
+    }
+    if (out.weights.empty()) out.weights.push_back(0.0);  // keep "empty == unit weights" unambiguous
+    return true;
+}
+
 // comm0: optional first-level partition (community id per node, any ids in [0, n)); parallel0: compute it here.
 int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out,
                 const int32_t *comm0 = nullptr, bool parallel0 = false) {
@@ -341,7 +385,13 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
         else
             level0_parallel_host(g, resolution, two_m, seed, comm);
         Graph ng;
-        ddlv::aggregate(g, comm, ng, node2new);
+        static const bool trace0 = getenv("DD_LOUVAIN_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        static const bool no_dense = getenv("DD_LOUVAIN_NO_DENSE_AGG") != nullptr;  // A/B switch
+        if (no_dense || !aggregate_unit_dense(g, comm, ng, node2new)) ddlv::aggregate(g, comm, ng, node2new);
+        if (trace0)
+            fprintf(stderr, "louvain first aggregation: n=%d nnz=%zu -> n=%d in %.1f ms\n", g.n, g.indices.size(), ng.n,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         for (int32_t i = 0; i < n; i++) membership[i] = node2new[membership[i]];
         g = std::move(ng);
     }
