@@ -338,6 +338,8 @@ def run_ours(args, wl, counts):
     omega, n_power_iter = _pca_plan(n_aug, n_genes, N_COMPONENTS, SEED)
     fit_kw = dict(pseudocount=PSEUDOCOUNT, standard_scaling=False, n_comp=N_COMPONENTS, n_power_iter=n_power_iter,
                   knn_k=10, resolution=4.0, seed=SEED, n_host_threads=host_threads, iter_begin=it0, iter_end=it1)
+    if args.clustering != "louvain":  # not the contract's line: the other two clustering algorithms of the reference
+        fit_kw.update(clustering=args.clustering, resolution=1.0 if args.clustering == "phenograph" else 4.0)
 
     # ---------------- device-resident leg (`value`)
     h = _capi.Handle(local_rank)
@@ -391,7 +393,7 @@ def run_ours(args, wl, counts):
 
     # ---------------- end-to-end leg (`e2e`): public API, host buffers
     clf = BoostClassifier(boost_rate=BOOST_RATE, n_components=N_COMPONENTS, n_iters=total_iters,
-                          clustering_algorithm="louvain", pseudocount=PSEUDOCOUNT, random_state=SEED,
+                          clustering_algorithm=args.clustering, pseudocount=PSEUDOCOUNT, random_state=SEED,
                           n_jobs=host_threads, device=local_rank, distributed=world > 1)
     # the step's inputs live in PINNED host memory (the contract's host->device leg): same CSR, page-locked buffers
     counts_host = counts
@@ -424,7 +426,7 @@ def run_ours(args, wl, counts):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, louvain (BASELINE.json configs)",
+            "workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, {args.clustering} (BASELINE.json configs)",
             "step": "one 25-iteration fit loop per GPU over the resident count matrix",
             "cells": n_cells, "genes": n_genes, "synthetics": n_synth, "nnz": int(counts.nnz),
             "host_threads_per_rank": host_threads, "parallelism": f"iteration-shard x{world}",
@@ -592,6 +594,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--clustering", default="louvain", choices=["louvain", "phenograph", "leiden"],
+                    help="clustering algorithm of the fit (the contract's line is louvain, BASELINE.json's config)")
     ap.add_argument("--shard", default="iters", choices=["iters", "cells"],
                     help="iters: every rank runs its own 25 iterations (weak scaling, the contract's line); "
                          "cells: one fit, the cells of every iteration sharded over the ranks (config 5)")
