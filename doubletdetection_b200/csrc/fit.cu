@@ -62,9 +62,10 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     const int64_t N = h->N, M = p->n_synth, A = N + M;
     // PhenoGraph looks at its own neighbourhood size (k nearest + self), not sc.pp.neighbors' 10
     const int k = pheno ? p->pheno_k + 1 : p->knn_k;
-    // the host side of an iteration (aggregate ~10^2 communities, upper Louvain levels, scoring) is tens of
-    // milliseconds, so a few workers keep up with the GPU
-    const int n_threads = std::max(1, std::min(p->n_host_threads, 8));
+    // the host side of a Louvain iteration (aggregate ~10^2 communities, upper levels, scoring) is a few milliseconds, so
+    // a few workers keep up with the GPU; PhenoGraph and Leiden partition the whole graph on the host (0.2 s and more per
+    // iteration at 100k cells) and are host-bound: they may use more workers
+    const int n_threads = std::max(1, std::min(p->n_host_threads, (pheno || leiden) ? 16 : 8));
     const int n_slots = n_threads + 2;
     const int64_t max_nnz = A * 2 * (k - 1);
     const int64_t w_off = ((A + 1) + A + max_nnz + 1) / 2 * 2;  // weights start 8-byte aligned
