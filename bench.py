@@ -182,20 +182,49 @@ def cpu_one_iteration(state):
     from oracle import louvain_c
 
     pro, rng, n_cells = state["pro"], state["rng"], state["n_cells"]
+    stage = state.setdefault("stage_s", {})
+    t = [time.perf_counter()]
+
+    def lap(name):
+        t.append(time.perf_counter())
+        stage[name] = stage.get(name, 0.0) + t[-1] - t[-2]
+
     choices = reference_path.draw_parents(rng, n_cells, BOOST_RATE, False)
     synth = reference_path.create_doublets(pro["raw"], choices)
+    lap("doublets")
     aug, _, _ = reference_path.normalise(synth, pro["lib_size"], pro["normed"], PSEUDOCOUNT)
+    lap("normalise_log")
     emb, _ = upstream.tl_pca(aug, N_COMPONENTS, random_state=SEED, svd_solver="auto")
+    lap("pca")
     from sklearn.neighbors import NearestNeighbors
 
     nn = NearestNeighbors(n_neighbors=10, algorithm="brute", metric="euclidean", n_jobs=-1).fit(emb)
     idx = nn.kneighbors(emb, return_distance=False)
+    lap("knn")
     graph = upstream.knn_pattern_graph(idx)
     # the CPU path uses the classic sequential Louvain (what a CPU implementation would run; faster on a
     # CPU than simulating the GPU's synchronous first level)
     labels = louvain_c.louvain(graph.indptr, graph.indices, None, resolution=4.0, seed=SEED)
+    lap("louvain")
     reference_path.score_communities(labels, n_cells)
+    lap("score")
     return aug.shape[0]
+
+
+def cpu_environment():
+    """Host description printed next to the CPU numbers."""
+    env = {"cpu_count": os.cpu_count(), "numpy": np.__version__}
+    try:
+        import scipy
+        import sklearn
+        from threadpoolctl import threadpool_info
+
+        env.update(scipy=scipy.__version__, sklearn=sklearn.__version__,
+                   blas=[{"api": i.get("internal_api"), "version": i.get("version"), "threads": i.get("num_threads")}
+                         for i in threadpool_info() if i.get("user_api") == "blas"])
+    except Exception as e:  # the description is optional, the measurement is not
+        env["note"] = f"threadpoolctl unavailable: {e}"
+    return env
 
 
 def cpu_state(counts):
@@ -219,6 +248,7 @@ def run_reference_arm(args, wl, counts):
     state = cpu_state(counts)
     for _ in range(args.warmup):
         cpu_one_iteration(state)
+    state["stage_s"] = {}  # per-stage seconds of the timed steps only
     t0 = time.perf_counter()
     cells = 0
     for _ in range(args.steps):
@@ -232,7 +262,9 @@ def run_reference_arm(args, wl, counts):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, louvain", "step": sample},
-        "cpu_baseline": {"value": value, "unit": "augmented-cells/s", "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "augmented-cells/s", "cores": cpu_cores(), "kind": "port", "sample": sample,
+                         "stage_seconds": {k_: round(v_, 3) for k_, v_ in state.get("stage_s", {}).items()},
+                         "host": cpu_environment()},
         "e2e": {"value": value, "unit": "augmented-cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference package not importable here (scanpy/anndata/phenograph absent): oracle port of its CPU path",
@@ -460,6 +492,8 @@ def run_ours(args, wl, counts):
             "sample": f"{n_cpu_iters} _one_fit iteration(s) of the 25 (oracle: reference lines + sklearn PCA/brute kNN + C Louvain + "
                       "scipy hypergeom)",
             "seconds": dt_cpu,
+            "stage_seconds": {k_: round(v_, 3) for k_, v_ in state.get("stage_s", {}).items()},
+            "host": cpu_environment(),
         }
     # ---------------- the other single-GPU config, for reference
     if world == 1 and args.workload == "c3" and not args.no_extra:
