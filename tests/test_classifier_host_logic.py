@@ -1,0 +1,159 @@
+"""The Python shim's orchestration (doubletdetection_b200/classifier.py) on the CPU: ``_capi.Handle`` is replaced by a
+stand-in whose ``fit_iterations`` evaluates every iteration with the ORACLE's stage functions on the parents the shim
+drew.  What is under test is therefore everything the shim itself does -- validation, HVG selection and column order,
+canonicalisation, the PCG64 parent stream (all iterations up front, continuing across fits), the mapping of constructor
+arguments to ``dd_fit_params``, iteration ranges, result attributes and their types -- against ``OracleClassifier``,
+which is pinned to the reference's real code by the goldens.  No CUDA, no libdd_b200 compute."""
+
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp_sparse
+
+from conftest import golden_case, load_golden
+from oracle import louvain_c, reference_path, upstream
+
+
+class OracleHandle:
+    """Same surface as ``_capi.Handle`` as far as ``BoostClassifier.fit`` uses it."""
+
+    calls = []
+
+    def __init__(self, device=0):
+        self.device = device
+        self.raw = None
+
+    def upload_counts(self, csr):
+        assert sp_sparse.issparse(csr) and csr.dtype == np.float32 and csr.has_canonical_format
+        self.raw = csr.copy()
+        self.n_cells, self.n_genes = csr.shape
+
+    def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10, resolution=4.0,
+                       seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0, clustering="louvain",
+                       pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10):
+        OracleHandle.calls.append(dict(n_comp=n_comp, n_power_iter=n_power_iter, omega_shape=omega.shape, seed=seed,
+                                       clustering=clustering, resolution=resolution, n_host_threads=n_host_threads,
+                                       iter_begin=iter_begin, iter_end=iter_end, standard_scaling=standard_scaling))
+        n_iters, n_synth = parents.shape[:2]
+        n = self.n_cells
+        iter_end = n_iters if iter_end is None else iter_end
+        lib = np.asarray(self.raw.sum(axis=1)).ravel()
+        normed = self.raw.copy()
+        from sklearn.utils.sparsefuncs_fast import inplace_csr_row_normalize_l1
+
+        inplace_csr_row_normalize_l1(normed)
+        out = dict(scores=np.zeros((n_iters, n)), log_p=np.zeros((n_iters, n)), communities=np.zeros((n_iters, n), np.int32),
+                   synth_communities=np.zeros((n_iters, n_synth), np.int32), stage_ms={"wall": 0.0})
+        for i in range(iter_begin, iter_end):
+            synth = reference_path.create_doublets(self.raw, parents[i])
+            aug, _, _ = reference_path.normalise(synth, lib, normed, pseudocount)
+            if standard_scaling:
+                aug, _, _ = upstream.pp_scale(aug, max_value=scale_max_value)
+            emb, _ = upstream.tl_pca(aug, n_comp, random_state=seed, svd_solver="auto")
+            if clustering == "phenograph":
+                full, _ = upstream.phenograph_cluster(emb, k=pheno_k, prune=pheno_prune, min_cluster_size=pheno_min_cluster_size,
+                                                      seed=seed, louvain_fn=louvain_c.louvain)
+            else:
+                idx, dist = upstream.knn_brute(emb, knn_k)
+                if clustering == "leiden":
+                    from oracle import leiden_ref
+
+                    C = upstream.fuzzy_connectivities(idx, dist)
+                    full = leiden_ref.leiden(C.indptr, C.indices, C.data.astype(np.float64), resolution=resolution, seed=seed)
+                else:
+                    S = upstream.knn_pattern_graph(idx)
+                    full = louvain_c.louvain(S.indptr, S.indices, None, resolution=resolution, seed=seed, level0="parallel")
+            s, lp, comm, scomm = reference_path.score_communities(np.asarray(full), n)
+            out["scores"][i], out["log_p"][i], out["communities"][i], out["synth_communities"][i] = s, lp, comm, scomm
+        return out
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def shim(monkeypatch):
+    from doubletdetection_b200 import _capi, classifier
+
+    monkeypatch.setattr(_capi, "Handle", OracleHandle)
+    OracleHandle.calls = []
+    return classifier.BoostClassifier
+
+
+@pytest.mark.parametrize("name", ["c1_louvain", "c1_louvain_scaled", "hvg_replace", "single_iter"])
+def test_shim_orchestration_reproduces_the_reference_goldens(shim, name):
+    g = load_golden(name)
+    counts, kw, pkw = golden_case(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = shim(**kw)
+        labels = np.asarray(clf.fit(counts).predict(**pkw), dtype=np.float64)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), g["parents"])
+    if "top_var_genes" in g:
+        np.testing.assert_array_equal(clf.top_var_genes_, g["top_var_genes"])
+    np.testing.assert_array_equal(clf.communities_, g["communities"])
+    np.testing.assert_array_equal(clf.synth_communities_, g["synth_communities"])
+    np.testing.assert_array_equal(clf.all_scores_, g["all_scores"])
+    np.testing.assert_allclose(clf.all_log_p_values_, g["all_log_p_values"], rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(labels, g["labels"])
+    assert clf.communities_.dtype == np.float64 and clf.synth_communities_.dtype == np.float64  # :188-190
+    assert isinstance(clf.parents_, list) and isinstance(clf.parents_[0], list) and len(clf.parents_[0][0]) == 2
+    call = OracleHandle.calls[-1]
+    n_aug = counts.shape[0] + g["parents"].shape[1]
+    n_genes = kw.get("n_top_var_genes", 10000)
+    n_genes = min(n_genes, counts.shape[1]) if n_genes > 0 else counts.shape[1]
+    assert call["omega_shape"] == (min(n_aug, n_genes) if n_aug < n_genes else n_genes, call["n_comp"] + 10)
+    assert call["n_power_iter"] == (7 if call["n_comp"] < 0.1 * min(n_aug, n_genes) else 4)
+    assert call["iter_begin"] == 0 and call["iter_end"] == kw["n_iters"] and call["resolution"] == 4.0
+
+
+def test_shim_rng_stream_continues_across_fits_and_inputs_are_untouched(shim):
+    counts, kw, _ = golden_case("c1_louvain")
+    dense = np.asarray(counts.todense() if sp_sparse.issparse(counts) else counts).astype(np.int64)
+    before = dense.copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = shim(**kw)
+        first = np.asarray(clf.fit(dense).parents_, dtype=np.int64).copy()
+        second = np.asarray(clf.fit(dense).parents_, dtype=np.int64)
+        ora = reference_path.OracleClassifier(n_iters=kw["n_iters"], random_state=0, louvain_fn=louvain_c.louvain)
+        ora.fit(dense)
+        ora.fit(dense)
+    np.testing.assert_array_equal(dense, before)
+    assert not np.array_equal(first, second)  # quirk Q2: one stream for all fits
+    np.testing.assert_array_equal(second, np.asarray(ora.parents_, dtype=np.int64))
+
+
+@pytest.mark.parametrize("algo,ckw", [("phenograph", {}), ("phenograph", {"prune": False, "k": 12, "min_cluster_size": 5}),
+                                      ("leiden", {}), ("leiden", {"resolution": 1.5}), ("louvain", {"resolution": 2})])
+def test_shim_maps_clustering_arguments(shim, algo, ckw):
+    from oracle import datasets
+
+    counts = datasets.structured_counts(600, 150, seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = shim(n_iters=2, clustering_algorithm=algo, clustering_kwargs=dict(ckw), random_state=3, n_jobs=-1).fit(counts)
+        okw = {k_: v_ for k_, v_ in ckw.items()}
+        ora = reference_path.OracleClassifier(n_iters=2, random_state=3, clustering_algorithm=algo, clustering_kwargs=okw,
+                                              louvain_fn=louvain_c.louvain).fit(counts)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    np.testing.assert_array_equal(clf.communities_, ora.communities_)
+    np.testing.assert_array_equal(clf.all_scores_, ora.all_scores_)
+    np.testing.assert_allclose(clf.all_log_p_values_, ora.all_log_p_values_, rtol=1e-12, equal_nan=True)
+    call = OracleHandle.calls[-1]
+    assert call["clustering"] == algo and call["seed"] == 3 and call["n_host_threads"] >= 1
+    if algo != "phenograph":
+        assert call["resolution"] == float(ckw.get("resolution", 4))
+
+
+def test_shim_upload_errors_surface_from_the_worker_thread(shim, monkeypatch):
+    def boom(self, csr):
+        raise MemoryError("libdd_b200: cudaMalloc: out of memory")
+
+    monkeypatch.setattr(OracleHandle, "upload_counts", boom)
+    counts, kw, _ = golden_case("c1_louvain")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(MemoryError, match="out of memory"):
+            shim(**kw).fit(counts)
