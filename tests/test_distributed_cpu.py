@@ -148,3 +148,60 @@ def test_cell_sharding_result_merge_gloo_world2():
     for p in procs:
         p.join(timeout=30)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def _fit_worker(rank, world, port, mode, q):
+    """BoostClassifier(distributed=mode).fit under gloo with the oracle-backed stand-in for the device handle
+    (tests/test_classifier_host_logic.py): the iteration blocks of the two ranks, gathered, must equal one process."""
+    import warnings
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from test_classifier_host_logic import OracleHandle
+
+        from doubletdetection_b200 import BoostClassifier
+        from oracle import datasets
+
+        _capi.Handle = OracleHandle
+        counts = datasets.poisson_counts(500, 100, seed=0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            clf = BoostClassifier(n_iters=3, clustering_algorithm="louvain", distributed=mode).fit(counts)
+        calls = list(OracleHandle.calls)
+        q.put((rank, calls[-1]["iter_begin"], calls[-1]["iter_end"], clf.all_scores_, clf.all_log_p_values_, clf.communities_,
+               np.asarray(clf.parents_, dtype=np.int64)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("mode", [True, "allgather"])
+def test_classifier_iteration_sharding_end_to_end_gloo_world2(mode):
+    from conftest import load_golden
+
+    g = load_golden("c1_louvain")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {r[0]: r[1:] for r in (q.get(timeout=200) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=30)
+    assert (results[0][0], results[0][1]) == (0, 1) and (results[1][0], results[1][1]) == (1, 3)  # blocks of 3 iterations
+    for rank in ((0, 1) if mode == "allgather" else (0,)):  # complete results: everywhere / on rank 0
+        _, _, scores, logp, comm, parents = results[rank]
+        np.testing.assert_array_equal(parents, g["parents"])  # every rank draws ALL iterations' parents (one stream)
+        np.testing.assert_array_equal(scores, g["all_scores"])
+        np.testing.assert_allclose(logp, g["all_log_p_values"], rtol=1e-12)
+        np.testing.assert_array_equal(comm, g["communities"])
+    if mode is True:  # rank 1 keeps its own rows only
+        np.testing.assert_array_equal(results[1][2][1:], g["all_scores"][1:])
+        assert not results[1][2][0].any()
