@@ -252,3 +252,40 @@ def test_oracle_classifier_leiden_path_runs_and_matches_native_twin(native):
         s, lp = native.score(labels, n_cells)
         np.testing.assert_array_equal(s, ora.all_scores_[i])
         np.testing.assert_allclose(lp, ora.all_log_p_values_[i], rtol=1e-9, atol=1e-12)
+
+
+def test_louvain_quality_against_an_independent_implementation(native):
+    """The louvain / leidenalg / igraph packages are absent, so the clustering stage has no bit-level pin.  networkx's
+    Louvain (an independent third-party implementation of the same RB-configuration objective) is the closest check
+    available: at resolution 1 on well separated data both find the same partition; at the reference's resolution 4,
+    where every cell type is split arbitrarily, the objective values must agree (ours may only be negligibly worse)."""
+    nx = pytest.importorskip("networkx")
+    from sklearn.metrics import adjusted_rand_score
+
+    rs = np.random.default_rng(5)
+    pts = (rs.normal(size=(3000, 8)) + rs.integers(0, 6, size=(3000, 1)) * 2.5).astype(np.float32)
+    idx, dist = upstream.knn_brute(pts, 10)
+    S = upstream.knn_pattern_graph(idx)
+    G = nx.from_scipy_sparse_array(S)
+    for gamma in (1.0, 4.0):
+        theirs = np.empty(3000, dtype=np.int64)
+        for c, members in enumerate(nx.community.louvain_communities(G, resolution=gamma, seed=0)):
+            theirs[list(members)] = c
+        ours = native.louvain_knn(idx.astype(np.int32), gamma, 0)
+        q_theirs = leiden_ref.quality(S.indptr, S.indices, None, theirs, gamma)
+        q_ours = leiden_ref.quality(S.indptr, S.indices, None, ours, gamma)
+        assert q_ours >= q_theirs - 0.01, (gamma, q_ours, q_theirs)
+        if gamma == 1.0:
+            assert adjusted_rand_score(theirs, ours) > 0.98
+    # the weighted objective (PhenoGraph's Jaccard graph at resolution 1, Leiden's umap graph at resolution 4)
+    C = upstream.fuzzy_connectivities(idx, dist)
+    Gw = nx.from_scipy_sparse_array(C.astype(np.float64), edge_attribute="weight")
+    w = C.data.astype(np.float64)
+    for gamma, fn in ((1.0, native.louvain_csr), (4.0, native.leiden_csr)):
+        theirs = np.empty(3000, dtype=np.int64)
+        for c, members in enumerate(nx.community.louvain_communities(Gw, weight="weight", resolution=gamma, seed=0)):
+            theirs[list(members)] = c
+        ours = fn(C.indptr, C.indices, w, resolution=gamma, seed=0)
+        q_theirs = leiden_ref.quality(C.indptr, C.indices, w, theirs, gamma)
+        q_ours = leiden_ref.quality(C.indptr, C.indices, w, ours, gamma)
+        assert q_ours >= q_theirs - 0.01, (gamma, q_ours, q_theirs)
