@@ -103,6 +103,10 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
     ),
+    "dd_louvain_csr_level0": (
+        ctypes.c_int,
+        [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
     "dd_score": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, c_i32p, c_f64p, c_f64p]),
     "dd_hypergeom_logsf": (ctypes.c_double, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]),
     "dd_fit_iterations": (
@@ -198,7 +202,8 @@ def phenograph_knn(knn_idx, prune=True, min_cluster_size=10, seed=0):
     return labels[:n]
 
 
-def louvain_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
+def louvain_csr(indptr, indices, weights=None, resolution=1.0, seed=0, level0="sequential"):
+    """``level0="parallel"``: first level by synchronous coloured rounds (fixed-point weights), as the kNN pipeline."""
     lib = load()
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
     indices = np.ascontiguousarray(indices, dtype=np.int64)
@@ -206,8 +211,9 @@ def louvain_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
     n = indptr.size - 1
     labels = np.empty(max(n, 1), dtype=np.int32)
     ncomm = ctypes.c_int32(0)
-    rc = lib.dd_louvain_csr(n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64), _ptr(w, ctypes.c_double),
-                            float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    fn = lib.dd_louvain_csr_level0 if level0 == "parallel" else lib.dd_louvain_csr
+    rc = fn(n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64), _ptr(w, ctypes.c_double),
+            float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
     if rc != DD_OK:
         _raise(lib, None, rc)
     return labels[:n]

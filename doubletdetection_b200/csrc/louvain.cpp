@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
@@ -321,6 +322,68 @@ void level0_parallel_host(const Graph &g, double gamma, double two_m, uint64_t s
     }
 }
 
+// The same level for WEIGHTED graphs (specification: oracle/louvain_ref.py, "WEIGHTED graphs"; the device counterpart is
+// round 2's work): weights in fixed point, wq = rint(w * 2^32) in int64, so that w(i, c), k_i, tot[c]
+// and two_m are exact integer sums -- identical in any summation order, which is what lets a GPU apply simultaneous moves
+// with atomics and still be bit-reproducible.  Gains: the unit formula on those integers converted to double.
+void level0_parallel_host_w(const Graph &g, double gamma, uint64_t seed, std::vector<int32_t> &comm) {
+    const int32_t n = g.n;
+    comm.resize(n);
+    const size_t nnz = g.indices.size();
+    std::vector<int64_t> wq(nnz), k(n, 0), tot(n), cnt(n, 0);
+    for (size_t e = 0; e < nnz; e++) wq[e] = (int64_t)std::nearbyint(g.weights[e] * 4294967296.0);  // ties to even, like numpy
+    int64_t two_m_q = 0;
+    std::vector<int32_t> size(n, 1), desired(n, -1);
+    std::vector<std::vector<int32_t>> bucket(kColours);
+    for (int32_t i = 0; i < n; i++) {
+        comm[i] = i;
+        for (int64_t e = g.indptr[i]; e < g.indptr[i + 1]; e++) k[i] += wq[e];
+        tot[i] = k[i];
+        two_m_q += k[i];
+        if (g.indptr[i + 1] > g.indptr[i]) bucket[colour_of(seed, i)].push_back(i);
+    }
+    if (two_m_q == 0) return;
+    const double two_m = (double)two_m_q;
+    for (int round = 0; round < kMaxRounds; round++) {
+        int64_t moved = 0;
+        for (int c = 0; c < kColours; c++) {
+            for (int32_t i : bucket[c]) {  // decide from the frozen state
+                desired[i] = -1;
+                const int64_t e0 = g.indptr[i], e1 = g.indptr[i + 1];
+                const int32_t ci = comm[i];
+                const double gk = gamma * (double)k[i];
+                for (int64_t e = e0; e < e1; e++) cnt[comm[g.indices[e]]] += wq[e];
+                const double gain_stay = (double)cnt[ci] - (gk * (double)(tot[ci] - k[i])) / two_m;
+                int32_t best = -1;
+                double best_gain = 0.0;
+                for (int64_t e = e0; e < e1; e++) {
+                    const int32_t cc = comm[g.indices[e]];
+                    if (cc == ci) continue;
+                    const double gn = (double)cnt[cc] - (gk * (double)tot[cc]) / two_m;
+                    if (best < 0 || gn > best_gain || (gn == best_gain && cc < best)) {
+                        best = cc;
+                        best_gain = gn;
+                    }
+                }
+                for (int64_t e = e0; e < e1; e++) cnt[comm[g.indices[e]]] = 0;
+                if (best >= 0 && best_gain > gain_stay && !(size[ci] == 1 && size[best] == 1 && best > ci)) desired[i] = best;
+            }
+            for (int32_t i : bucket[c]) {  // apply simultaneously
+                const int32_t b = desired[i];
+                if (b < 0) continue;
+                const int32_t ci = comm[i];
+                comm[i] = b;
+                tot[ci] -= k[i];
+                tot[b] += k[i];
+                size[ci]--;
+                size[b]++;
+                moved++;
+            }
+        }
+        if (moved <= (int64_t)(n >> 9)) break;  // at most n / 512 moves: the level is settled
+    }
+}
+
 // The first aggregation of the kNN pipeline: a unit-weight graph without self-loops whose ~10^2 first-level communities fit
 // a dense count table.  Produces exactly what ddlv::aggregate produces (ids by first appearance, ascending neighbour lists,
 // integer-valued weights -- counts are exact in any order) in one tight pass over the edges instead of per-community
@@ -382,8 +445,10 @@ int run_louvain(Graph &g, double resolution, uint64_t seed, int32_t *labels_out,
         std::vector<int32_t> comm, node2new;
         if (comm0 != nullptr)
             comm.assign(comm0, comm0 + n);
-        else
+        else if (g.weights.empty())
             level0_parallel_host(g, resolution, two_m, seed, comm);
+        else
+            level0_parallel_host_w(g, resolution, seed, comm);
         Graph ng;
         static const bool trace0 = getenv("DD_LOUVAIN_TRACE") != nullptr;
         const auto t0 = std::chrono::steady_clock::now();
@@ -590,8 +655,24 @@ extern "C" int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, doub
     return rc;
 }
 
+namespace {
+int louvain_csr_impl(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights, double resolution,
+                     uint64_t seed, int32_t *labels_out, int32_t *n_communities_out, bool parallel0);
+}
+
 extern "C" int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                               double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out) {
+    return louvain_csr_impl(n, indptr, indices, weights, resolution, seed, labels_out, n_communities_out, false);
+}
+
+extern "C" int dd_louvain_csr_level0(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                                     double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out) {
+    return louvain_csr_impl(n, indptr, indices, weights, resolution, seed, labels_out, n_communities_out, true);
+}
+
+namespace {
+int louvain_csr_impl(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights, double resolution,
+                     uint64_t seed, int32_t *labels_out, int32_t *n_communities_out, bool parallel0) {
     if (n < 0 || !indptr || (n > 0 && !labels_out) || n >= (1ll << 31) - 1) {
         dd_set_global_error("dd_louvain_csr: bad arguments");
         return DD_ERR_ARG;
@@ -614,5 +695,6 @@ extern "C" int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *i
     }
     if (weights && nnz > 0) g.weights.assign(weights, weights + nnz);
     g.selfw.assign(n, 0.0);
-    return run_louvain(g, resolution, seed, labels_out, n_communities_out);
+    return run_louvain(g, resolution, seed, labels_out, n_communities_out, nullptr, parallel0);
 }
+}  // namespace

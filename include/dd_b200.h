@@ -130,6 +130,12 @@ int dd_jaccard_graph(dd_handle *h, int32_t k, int32_t prune, int32_t *indptr_out
 /* Fully sequential Louvain on an explicit symmetric CSR graph (weights may be NULL = unweighted). */
 int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                    double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
+/* The same graph partitioned the way the kNN pipeline does it: first level by synchronous coloured rounds (the host twin
+ * of the device level), the levels above sequentially.  With weights the first level works in fixed point (multiples of
+ * 2^-32 summed in int64: exact, hence order-independent sums) -- the specification a device level for PhenoGraph's and
+ * Leiden's weighted graphs will follow (oracle/louvain_ref.py; not yet used by dd_fit_iterations). */
+int dd_louvain_csr_level0(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                          double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 
 /* ---- clustering_algorithm="leiden", doubletdetection.py:331-342 (host) -------------------------------------
  * sc.pp.neighbors(method="umap", n_neighbors=k) weights + sc.tl.leiden(resolution, random_state, directed=False).

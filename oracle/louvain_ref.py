@@ -28,7 +28,12 @@ Synchronous coloured rounds (first level, unweighted, order-independent by const
     that gain is strictly larger than gain(comm[i]) -- except that a singleton never moves into a singleton
     with a larger id (this breaks the swap oscillation of synchronous updates);
   * all moves of the sub-round are applied at once; the level ends after a round that moved at most
-    floor(n / 512) nodes (i.e. no node for n < 512), or after 32 rounds.
+    floor(n / 512) nodes (i.e. no node for n < 512), or after 32 rounds;
+  * WEIGHTED graphs (``louvain(..., weights, level0="parallel")``; not yet used by the product): the
+    level works on fixed-point weights ``wq = rint(w * 2**32)`` held in int64, so that w(i, c), k_i, tot[c] and two_m are
+    exact integer sums -- the same in any summation order, which is what makes simultaneous updates (atomics on a
+    GPU) bit-reproducible.  The gain is the expression above evaluated in double on those integers converted to double.
+    The levels above the first use the original double weights.
 
 Sequential algorithm (one "level"):
   * every node starts in its own community; ``tot[c]`` = sum of weighted degrees in c;
@@ -173,15 +178,24 @@ def node_colours(n, seed):
     return (z % np.uint64(N_COLOURS)).astype(np.int64)
 
 
-def level0_parallel(indptr, indices, gamma, seed):
-    """First level by synchronous coloured rounds on an unweighted symmetric graph (see the module docstring).
-    Returns the community id (a node id) of every node."""
+FIXED_POINT = 2.0**32
+
+
+def level0_parallel(indptr, indices, gamma, seed, weights=None):
+    """First level by synchronous coloured rounds on a symmetric graph (see the module docstring); unweighted, or with
+    ``weights`` quantised to multiples of 2**-32.  Returns the community id (a node id) of every node."""
     indptr = np.asarray(indptr, dtype=np.int64)
     indices = np.asarray(indices, dtype=np.int64)
     n = indptr.size - 1
     deg = np.diff(indptr)
-    k = deg.astype(np.float64)
-    two_m = float(indices.size)
+    if weights is None:
+        wq = np.ones(indices.size, dtype=np.int64)
+    else:
+        wq = np.rint(np.asarray(weights, dtype=np.float64) * FIXED_POINT).astype(np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), deg)
+    k = np.zeros(n, dtype=np.int64)
+    np.add.at(k, rows, wq)
+    two_m = float(int(wq.sum()))
     comm = np.arange(n, dtype=np.int64)
     tot = k.copy()
     size = np.ones(n, dtype=np.int64)
@@ -199,21 +213,24 @@ def level0_parallel(indptr, indices, gamma, seed):
             local = np.repeat(np.arange(act.size, dtype=np.int64), d)
             starts = np.repeat(indptr[act], d)
             offs = np.arange(d.sum(), dtype=np.int64) - np.repeat(np.cumsum(d) - d, d)
-            c_nb = comm[indices[starts + offs]]
-            key, w = np.unique(local * n + c_nb, return_counts=True)
+            edge = starts + offs
+            c_nb = comm[indices[edge]]
+            key, inv = np.unique(local * n + c_nb, return_inverse=True)
+            w = np.zeros(key.size, dtype=np.int64)
+            np.add.at(w, inv.ravel(), wq[edge])  # exact integer sums
             a = key // n  # local index of the node
             c = key % n  # candidate community
             node = act[a]
             ci = comm[node]
-            ki = k[node]
+            ki = k[node].astype(np.float64)
             own = c == ci
-            gain = w.astype(np.float64) - ((gamma * ki) * (tot[c] - np.where(own, ki, 0.0))) / two_m
+            gain = w.astype(np.float64) - ((gamma * ki) * (tot[c] - np.where(own, k[node], 0)).astype(np.float64)) / two_m
             # gain of staying (w(i, ci) may be 0: then the pair is absent from `key`)
             w_stay = np.zeros(act.size, dtype=np.float64)
             w_stay[a[own]] = w[own].astype(np.float64)
             ci_act = comm[act]
-            k_act = k[act]
-            gain_stay = w_stay - ((gamma * k_act) * (tot[ci_act] - k_act)) / two_m
+            k_act = k[act].astype(np.float64)
+            gain_stay = w_stay - ((gamma * k_act) * (tot[ci_act] - k[act]).astype(np.float64)) / two_m
             # best other community: largest gain, ties -> smallest id
             oth = ~own
             if not oth.any():
@@ -243,12 +260,10 @@ def level0_parallel(indptr, indices, gamma, seed):
 
 def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, max_levels=64, level0="sequential"):
     """Cluster a symmetric, self-loop-free CSR graph.  Returns int64 labels, 0 = largest.
-    ``level0="parallel"`` (unweighted graphs only) is the kNN-pipeline flavour."""
+    ``level0="parallel"`` is the kNN-pipeline flavour (weights, if any, in fixed point during that level)."""
     comm0 = None
     if level0 == "parallel":
-        if weights is not None:
-            raise ValueError("the parallel first level is defined for unweighted graphs")
-        comm0 = [int(x) for x in level0_parallel(indptr, indices, resolution, seed)]
+        comm0 = [int(x) for x in level0_parallel(indptr, indices, resolution, seed, weights)]
     indptr = [int(x) for x in indptr]
     indices = [int(x) for x in indices]
     n = len(indptr) - 1

@@ -289,3 +289,39 @@ def test_louvain_quality_against_an_independent_implementation(native):
         q_theirs = leiden_ref.quality(C.indptr, C.indices, w, theirs, gamma)
         q_ours = leiden_ref.quality(C.indptr, C.indices, w, ours, gamma)
         assert q_ours >= q_theirs - 0.01, (gamma, q_ours, q_theirs)
+
+
+@pytest.mark.parametrize("n,k,gamma,seed", [(300, 6, 1.0, 3), (1000, 10, 1.0, 0), (2000, 12, 4.0, 7), (2500, 31, 1.0, 1)])
+def test_weighted_parallel_first_level_matches_python_spec(native, n, k, gamma, seed):
+    """dd_louvain_csr_level0: synchronous coloured first level on WEIGHTED graphs with fixed-point (2^-32) weights -- the
+    specification of the device level PhenoGraph / Leiden will get.  Host twin vs the numpy
+    specification, label for label; the unweighted flavour of the same entry equals the kNN pipeline's partition."""
+    idx, dist = upstream.knn_brute(_blobs(n, 6, n), k)
+    G = upstream.jaccard_graph(idx[:, 1:], prune=True) if k == 31 else upstream.fuzzy_connectivities(idx, dist)
+    w = G.data.astype(np.float64)
+    want = louvain_ref.louvain(G.indptr, G.indices, w, resolution=gamma, seed=seed, level0="parallel")
+    got = native.louvain_csr(G.indptr, G.indices, w, gamma, seed, level0="parallel")
+    np.testing.assert_array_equal(got, want)
+    S = upstream.knn_pattern_graph(idx)
+    np.testing.assert_array_equal(native.louvain_csr(S.indptr, S.indices, None, gamma, seed, level0="parallel"),
+                                  native.louvain_knn(idx.astype(np.int32), gamma, seed))
+    # same objective value as the fully sequential sweep it is meant to replace (to within the usual Louvain scatter)
+    seq = native.louvain_csr(G.indptr, G.indices, w, gamma, seed)
+    q_par = leiden_ref.quality(G.indptr, G.indices, w, got, gamma)
+    q_seq = leiden_ref.quality(G.indptr, G.indices, w, seq, gamma)
+    assert q_par >= q_seq - 0.01
+
+
+def test_fixed_point_level_is_order_independent(native):
+    """The point of the fixed-point weights: relabelling the nodes (which permutes every summation order in the level)
+    changes nothing but the labels' names when the colour classes are permuted along."""
+    idx, dist = upstream.knn_brute(_blobs(800, 5, 17), 10)
+    G = upstream.fuzzy_connectivities(idx, dist).astype(np.float64)
+    comm = louvain_ref.level0_parallel(G.indptr, G.indices, 1.0, 0, G.data)
+    # shuffle the ORDER OF THE ENTRIES inside every row: same graph, different summation order for w(i, c), k_i, tot
+    rs = np.random.default_rng(0)
+    indptr, indices, data = G.indptr, G.indices.copy(), G.data.copy()
+    for i in range(G.shape[0]):
+        p = rs.permutation(indptr[i + 1] - indptr[i]) + indptr[i]
+        indices[indptr[i]:indptr[i + 1]], data[indptr[i]:indptr[i + 1]] = indices[p], data[p]
+    np.testing.assert_array_equal(louvain_ref.level0_parallel(indptr, indices, 1.0, 0, data), comm)
