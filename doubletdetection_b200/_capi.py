@@ -103,6 +103,10 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
     ),
+    "dd_louvain_level0_weighted": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
+    ),
     "dd_louvain_csr_level0": (
         ctypes.c_int,
         [ctypes.c_int64, c_i64p, c_i64p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
@@ -437,6 +441,19 @@ class Handle:
                                             _ptr(list_tiles, ctypes.c_int32), _ptr(idx, ctypes.c_int32),
                                             _ptr(dist, ctypes.c_float)))
         return idx, dist
+
+    def louvain_level0_weighted(self, indptr, indices, weights, resolution=1.0, seed=0):
+        """Experimental: weighted first Louvain level on the device (fixed-point weights).  Returns (comm, rounds)."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        n = indptr.size - 1
+        comm = np.empty(n, dtype=np.int32)
+        rounds = ctypes.c_int32(0)
+        self._check(self._lib.dd_louvain_level0_weighted(self._h, n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64),
+                                                         _ptr(weights, ctypes.c_double), float(resolution),
+                                                         int(seed) & (2**64 - 1), _ptr(comm, ctypes.c_int32), ctypes.byref(rounds)))
+        return comm, rounds.value
 
     def jaccard_graph(self, k, prune=True):
         """PhenoGraph graph of the last ``knn(k)`` as built on the device: scipy CSR (float64, sorted rows, pruned

@@ -1,0 +1,246 @@
+// louvain_gpu_w.cu -- EXPERIMENTAL: the first Louvain level by synchronous coloured rounds for WEIGHTED graphs (PhenoGraph's
+// Jaccard graph, Leiden's umap graph).  Written after round 1's GPU budget was spent: it has never run on hardware and
+// nothing in dd_fit_iterations calls it yet; tests/gpu_weighted_level_check.py compares it with the specification.
+//
+// Specification: oracle/louvain_ref.py:level0_parallel(..., weights); host twin: louvain.cpp:level0_parallel_host_w.  The
+// level works on fixed-point weights wq = rint(w * 2^32) held in int64: w(i, c), k_i, tot[c] and two_m are exact integer
+// sums, identical in any order, so the simultaneous moves of a sub-round can be applied with 64-bit integer atomics and
+// the result is still bit-reproducible (the float64 atomics of the unweighted kernel are exact only because degrees are
+// integers).  The gain is the unweighted formula evaluated in double on those integers (explicit _rn intrinsics: no
+// contraction), candidates are compared by (gain, smaller id), singletons never move into a larger-id singleton.
+//
+// Kept deliberately simple (one launch per step, no CUDA graph, temporary buffers): correctness first, then fold it into
+// louvain_gpu.cu's machinery.
+#include "dd_internal.h"
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int kColoursW = 8;
+constexpr int kMaxRoundsW = 32;
+constexpr int kTableW = 256, kTableMaxDegW = 192, kTableShiftW = 24;  // per-warp open addressing, hash = top 8 bits
+
+inline int colour_of_w(uint64_t seed, int i) {
+    uint64_t z = seed + (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (int)(z % kColoursW);
+}
+
+__global__ void k_lvw_init(const int32_t *__restrict__ off, const long long *__restrict__ wq, int n, int32_t *__restrict__ comm,
+                           long long *__restrict__ k, long long *__restrict__ tot, int32_t *__restrict__ csize,
+                           int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) counters[0] = counters[1] = counters[2] = 0;  // moved this round, done flag, rounds executed
+    if (i >= n) return;
+    long long s = 0;
+    for (int e = off[i]; e < off[i + 1]; e++) s += wq[e];
+    k[i] = s;
+    tot[i] = s;
+    comm[i] = i;
+    csize[i] = 1;
+}
+
+__device__ __forceinline__ double gain_of(long long w_ic, double gk, long long tot_c, double two_m) {
+    return __dsub_rn((double)w_ic, __ddiv_rn(__dmul_rn(gk, (double)tot_c), two_m));
+}
+
+// one warp per node of the current colour: the node's desired community, or -1
+__global__ void __launch_bounds__(256) k_lvw_propose(const int32_t *__restrict__ off, const int32_t *__restrict__ adj,
+                                                     const long long *__restrict__ wq, const int32_t *comm,
+                                                     const long long *__restrict__ k, const long long *tot,
+                                                     const int32_t *csize, const int32_t *__restrict__ bucket, int b0, int b1,
+                                                     double gamma, double two_m, int32_t *__restrict__ desired,
+                                                     const int32_t *__restrict__ counters) {
+    __shared__ int32_t s_key[8 * kTableW];
+    __shared__ unsigned long long s_sum[8 * kTableW];
+    if (counters[1]) return;  // the level settled in an earlier round
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+    if (b0 + w >= b1) return;  // whole warp
+    const int i = bucket[b0 + w];
+    const int s = off[i], d = off[i + 1] - s;  // buckets hold nodes with d > 0 only
+    const int ci = __ldcg(comm + i);
+    const long long ki = k[i];
+    const double gk = __dmul_rn(gamma, (double)ki);
+    double best_gain = 0.0;
+    int best = 0x7fffffff;
+    long long w_stay = 0;
+    if (d <= kTableMaxDegW) {
+        int32_t *tkey = s_key + wl * kTableW;
+        unsigned long long *tsum = s_sum + wl * kTableW;
+        for (int t = lane; t < kTableW; t += 32) {
+            tkey[t] = -1;
+            tsum[t] = 0ull;
+        }
+        __syncwarp();
+        for (int f = lane; f < d; f += 32) {
+            const int c = __ldcg(comm + adj[s + f]);
+            unsigned slot = ((unsigned)c * 2654435761u) >> kTableShiftW;
+            for (;;) {
+                const int prev = atomicCAS(tkey + slot, -1, c);
+                if (prev == -1 || prev == c) break;
+                slot = (slot + 1) & (kTableW - 1);
+            }
+            atomicAdd(tsum + slot, (unsigned long long)wq[s + f]);
+        }
+        __syncwarp();
+        for (int t = lane; t < kTableW; t += 32) {
+            const int c = tkey[t];
+            if (c < 0) continue;
+            const long long wc = (long long)tsum[t];
+            if (c == ci) {
+                w_stay = wc;
+                continue;
+            }
+            const double gn = gain_of(wc, gk, __ldcg(tot + c), two_m);
+            if (best == 0x7fffffff || gn > best_gain || (gn == best_gain && c < best)) {
+                best = c;
+                best_gain = gn;
+            }
+        }
+        __syncwarp();  // the table is reused by this warp's next node only in a later launch, but keep the phases ordered
+    } else {
+        for (int f = lane; f < d; f += 32)
+            if (__ldcg(comm + adj[s + f]) == ci) w_stay += wq[s + f];
+        for (int e = lane; e < d; e += 32) {
+            const int c = __ldcg(comm + adj[s + e]);
+            if (c == ci) continue;
+            long long wc = 0;
+            for (int f = 0; f < d; f++)
+                if (__ldcg(comm + adj[s + f]) == c) wc += wq[s + f];
+            const double gn = gain_of(wc, gk, __ldcg(tot + c), two_m);
+            if (best == 0x7fffffff || gn > best_gain || (gn == best_gain && c < best)) {
+                best = c;
+                best_gain = gn;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        w_stay += __shfl_xor_sync(0xffffffffu, w_stay, o);  // table path: one lane holds it; fallback: partial sums
+        const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ob != 0x7fffffff && (best == 0x7fffffff || og > best_gain || (og == best_gain && ob < best))) {
+            best = ob;
+            best_gain = og;
+        }
+    }
+    const double gain_stay = gain_of(w_stay, gk, __ldcg(tot + ci) - ki, two_m);
+    int res = -1;
+    if (best != 0x7fffffff && best_gain > gain_stay &&
+        !(__ldcg(csize + ci) == 1 && __ldcg(csize + best) == 1 && best > ci))
+        res = best;
+    if (lane == 0) desired[i] = res;
+}
+
+__global__ void k_lvw_apply(int32_t *__restrict__ comm, const long long *__restrict__ k, long long *__restrict__ tot,
+                            int32_t *__restrict__ csize, const int32_t *__restrict__ bucket, int b0, int b1,
+                            const int32_t *__restrict__ desired, int32_t *__restrict__ counters) {
+    if (counters[1]) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b0 + t >= b1) return;
+    const int i = bucket[b0 + t];
+    const int b = desired[i];
+    if (b < 0) return;
+    const int ci = comm[i];
+    const unsigned long long ki = (unsigned long long)k[i];
+    comm[i] = b;
+    atomicAdd(reinterpret_cast<unsigned long long *>(tot + ci), 0ull - ki);  // two's complement: exact in any order
+    atomicAdd(reinterpret_cast<unsigned long long *>(tot + b), ki);
+    atomicSub(csize + ci, 1);
+    atomicAdd(csize + b, 1);
+    atomicAdd(counters, 1);
+}
+
+__global__ void k_lvw_round_end(int32_t *__restrict__ counters, int n) {
+    if (counters[1]) return;
+    counters[2]++;
+    if (counters[0] <= (n >> 9)) counters[1] = 1;
+    counters[0] = 0;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t count) { return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1)); }
+};
+
+}  // namespace
+
+// Test hook: the weighted first level on an explicit symmetric CSR graph without self-loops and without zero weights
+// (host arrays).  comm_out int32[n]: the community (a node id) of every node after the level; rounds_out: rounds executed.
+extern "C" int dd_louvain_level0_weighted(dd_handle *h, int64_t n, const int64_t *indptr, const int64_t *indices,
+                                          const double *weights, double gamma, uint64_t seed, int32_t *comm_out,
+                                          int32_t *rounds_out) {
+    if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_louvain_level0_weighted: null handle");
+    if (n < 1 || !indptr || !comm_out) return dd_fail(h, DD_ERR_ARG, "dd_louvain_level0_weighted: null argument");
+    const int64_t nnz = indptr[n];
+    if (nnz < 0 || (nnz > 0 && (!indices || !weights)) || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1)
+        return dd_fail(h, DD_ERR_ARG, "dd_louvain_level0_weighted: bad graph");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    std::vector<int32_t> off(n + 1), adj((size_t)std::max<int64_t>(nnz, 1));
+    std::vector<long long> wq((size_t)std::max<int64_t>(nnz, 1));
+    long long two_m_q = 0;
+    for (int64_t i = 0; i <= n; i++) off[i] = (int32_t)indptr[i];
+    for (int64_t e = 0; e < nnz; e++) {
+        if (indices[e] < 0 || indices[e] >= n) return dd_fail(h, DD_ERR_ARG, "dd_louvain_level0_weighted: index out of range");
+        adj[e] = (int32_t)indices[e];
+        wq[e] = (long long)std::nearbyint(weights[e] * 4294967296.0);
+        if (wq[e] <= 0) return dd_fail(h, DD_ERR_ARG, "dd_louvain_level0_weighted: weights must be positive");
+        two_m_q += wq[e];
+    }
+    // colour classes of the nodes that have neighbours
+    std::vector<int32_t> cnt(kColoursW + 1, 0), nodes;
+    for (int64_t i = 0; i < n; i++)
+        if (off[i + 1] > off[i]) cnt[colour_of_w(seed, (int)i) + 1]++;
+    for (int c = 0; c < kColoursW; c++) cnt[c + 1] += cnt[c];
+    nodes.resize((size_t)std::max(cnt[kColoursW], 1));
+    {
+        std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+        for (int64_t i = 0; i < n; i++)
+            if (off[i + 1] > off[i]) nodes[fill[colour_of_w(seed, (int)i)]++] = (int32_t)i;
+    }
+    DevBuf<int32_t> d_off, d_adj, d_comm, d_csize, d_desired, d_bucket, d_counters;
+    DevBuf<long long> d_wq, d_k, d_tot;
+    if (d_off.alloc(n + 1) || d_adj.alloc(nnz) || d_comm.alloc(n) || d_csize.alloc(n) || d_desired.alloc(n) ||
+        d_bucket.alloc(nodes.size()) || d_counters.alloc(4) || d_wq.alloc(nnz) || d_k.alloc(n) || d_tot.alloc(n))
+        return dd_fail(h, DD_ERR_NOMEM, "dd_louvain_level0_weighted: device buffers");
+    DD_CUDA(h, cudaMemcpyAsync(d_off.p, off.data(), sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+    if (nnz > 0) {
+        DD_CUDA(h, cudaMemcpyAsync(d_adj.p, adj.data(), sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
+        DD_CUDA(h, cudaMemcpyAsync(d_wq.p, wq.data(), sizeof(long long) * nnz, cudaMemcpyHostToDevice, h->stream));
+    }
+    DD_CUDA(h, cudaMemcpyAsync(d_bucket.p, nodes.data(), sizeof(int32_t) * nodes.size(), cudaMemcpyHostToDevice, h->stream));
+    DD_CUDA(h, cudaMemsetAsync(d_desired.p, 0xff, sizeof(int32_t) * n, h->stream));
+    const int ni = (int)n;
+    DD_LAUNCH(h, "lvw_init", k_lvw_init, (unsigned)((n + 255) / 256), 256, 0, d_off.p, d_wq.p, ni, d_comm.p, d_k.p, d_tot.p,
+              d_csize.p, d_counters.p);
+    if (two_m_q > 0) {
+        const double two_m = (double)two_m_q;
+        for (int round = 0; round < kMaxRoundsW; round++) {
+            for (int c = 0; c < kColoursW; c++) {
+                const int b0 = cnt[c], b1 = cnt[c + 1];
+                if (b1 == b0) continue;
+                DD_LAUNCH(h, "lvw_propose", k_lvw_propose, (unsigned)((b1 - b0 + 7) / 8), 256, 0, d_off.p, d_adj.p, d_wq.p, d_comm.p,
+                          d_k.p, d_tot.p, d_csize.p, d_bucket.p, b0, b1, gamma, two_m, d_desired.p, d_counters.p);
+                DD_LAUNCH(h, "lvw_apply", k_lvw_apply, (unsigned)((b1 - b0 + 255) / 256), 256, 0, d_comm.p, d_k.p, d_tot.p, d_csize.p,
+                          d_bucket.p, b0, b1, d_desired.p, d_counters.p);
+            }
+            DD_LAUNCH(h, "lvw_round_end", k_lvw_round_end, 1, 1, 0, d_counters.p, ni);
+        }
+    }
+    int32_t counters[4] = {0, 0, 0, 0};
+    DD_CUDA(h, cudaMemcpyAsync(comm_out, d_comm.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaMemcpyAsync(counters, d_counters.p, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (rounds_out) *rounds_out = counters[2];
+    return DD_OK;
+}

@@ -137,6 +137,13 @@ int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, con
 int dd_louvain_csr_level0(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                           double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 
+/* Experimental test hook (never run on hardware yet, not used by dd_fit_iterations): the weighted first level of
+ * dd_louvain_csr_level0 on the DEVICE -- fixed-point weights, 64-bit integer atomics -- for an explicit symmetric CSR graph
+ * (host arrays, positive weights, no self-loops).  comm_out int32[n] = community (a node id) of every node after the level,
+ * to be compared with oracle/louvain_ref.py:level0_parallel (tests/gpu_weighted_level_check.py). */
+int dd_louvain_level0_weighted(dd_handle *h, int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                               double gamma, uint64_t seed, int32_t *comm_out, int32_t *rounds_out);
+
 /* ---- clustering_algorithm="leiden", doubletdetection.py:331-342 (host) -------------------------------------
  * sc.pp.neighbors(method="umap", n_neighbors=k) weights + sc.tl.leiden(resolution, random_state, directed=False).
  * dd_umap_connectivities: umap's fuzzy simplicial set of the exact kNN lists (knn_idx int32[n * k] with the cell

@@ -11,5 +11,6 @@ python bench.py --steps 3 --warmup 3 > gpurun_out/r2a_bench_c3.json 2> gpurun_ou
 bash scripts/gpu_dense_variants.sh > gpurun_out/r2a_dense_variants.out 2>&1
 timeout 900 python scripts/knn_listed_experiment.py c3 64 > gpurun_out/r2a_knn_listed.log 2>&1
 timeout 600 python scripts/knn_listed_experiment.py c3 128 >> gpurun_out/r2a_knn_listed.log 2>&1
-cat gpurun_out/r2a_tests.log gpurun_out/dense_variants.log gpurun_out/r2a_knn_listed.log
+timeout 600 python tests/gpu_weighted_level_check.py > gpurun_out/r2a_weighted_level.log 2>&1
+cat gpurun_out/r2a_tests.log gpurun_out/dense_variants.log gpurun_out/r2a_knn_listed.log gpurun_out/r2a_weighted_level.log
 tail -c 1500 gpurun_out/r2a_bench_c3.json
