@@ -34,4 +34,8 @@ for tool in memcheck synccheck; do
 done
 # list-driven kNN kernel
 run memcheck DD_X=0 python scripts/knn_listed_experiment.py c2
+# weighted first Louvain level (three smallest cases)
+for tool in memcheck racecheck; do
+    run $tool DD_CHECK_CASES=3 python tests/gpu_weighted_level_check.py -
+done
 grep -c "ERROR SUMMARY: 0 errors" $log; grep "ERROR SUMMARY" $log
