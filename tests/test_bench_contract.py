@@ -66,3 +66,65 @@ def test_roofline_arithmetic():
     assert r["tc_gemm_dq"]["algorithmic_bytes"] == (a * g + g * 40 + a * 40) * 4
     assert r["knn_tc"]["bound"] == "tensor" and r["knn_tc"]["algorithmic_flops"] == 2.0 * a * a * 32
     assert np.isclose(r["knn_tc"]["achieved"], 2.0 * a * a * 32 / 4.8e-3 / 1e12)
+
+
+def test_product_arm_line_with_a_stand_in_handle(monkeypatch, capsys):
+    """bench.py's own arm end to end on the CPU: CUDA and the device handle are replaced by stand-ins (the numbers mean
+    nothing), so that a typo in the measurement code cannot surface for the first time on the GPU box.  Checks every key
+    the contract names."""
+    import torch
+
+    from doubletdetection_b200 import _capi
+
+    class Handle:
+        def __init__(self, device=0):
+            self.launches = 0
+
+        def upload_counts(self, csr):
+            self.n_cells, self.n_genes = csr.shape
+
+        def fit_iterations(self, parents, omega, **kw):
+            n_iters, n_synth = parents.shape[:2]
+            self.launches += 100
+            rs = np.random.default_rng(0)
+            return dict(scores=rs.random((n_iters, self.n_cells)), log_p=-30 * rs.random((n_iters, self.n_cells)),
+                        communities=np.zeros((n_iters, self.n_cells), np.int32),
+                        synth_communities=np.zeros((n_iters, n_synth), np.int32),
+                        stage_ms=dict(host_cluster_score=1.0, normalise=1.0, scale=0.0, pca=1.0, knn=1.0, cluster_gpu_d2h=1.0,
+                                      device_total=5.0, wall=6.0))
+
+        def set_kernel_timing(self, on):
+            pass
+
+        def kernel_launches(self):
+            return self.launches
+
+        def kernel_timing_report(self):
+            return {"knn_tc": (10.0, 10), "tc_gemm_dq": (3.0, 10), "dense_rows": (7.0, 10), "lv_rounds_graph": (30.0, 10)}
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(_capi, "Handle", Handle)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "c1", "--steps", "2", "--warmup", "3"])
+    for var in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(var, raising=False)
+    bench.main()
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["unit"] == "augmented-cells/s" and d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert d["roofline"]["bound"] in ("hbm", "tensor") and d["roofline_kernel"] == "knn_tc"  # the kernel with most time
+    assert np.isclose(d["roofline"]["frac"], d["roofline"]["achieved"] / d["roofline"]["peak"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+    assert d["gpu_launches"] == 200 and set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
