@@ -21,7 +21,8 @@ def test_pipeline_leiden_matches_stagewise_calls(handle, native):
     and distances (checks the pinned-slot layout and the ordering of the copies against the next iteration's kNN)."""
     raw = datasets.structured_counts(3000, 400, seed=7)
     n_cells, n_iters, n_synth = 3000, 4, 750
-    parents = np.random.default_rng(5).choice(n_cells, size=(n_iters, n_synth, 2), replace=False)
+    rng = np.random.default_rng(5)
+    parents = np.stack([rng.choice(n_cells, size=(n_synth, 2), replace=False) for _ in range(n_iters)])
     C = 30
     omega = pca_f64.omega(400, C, 0).astype(np.float32)
     n_power = pca_f64.auto_n_iter(n_cells + n_synth, 400, C)
