@@ -325,3 +325,15 @@ def test_fixed_point_level_is_order_independent(native):
         p = rs.permutation(indptr[i + 1] - indptr[i]) + indptr[i]
         indices[indptr[i]:indptr[i + 1]], data[indptr[i]:indptr[i + 1]] = indices[p], data[p]
     np.testing.assert_array_equal(louvain_ref.level0_parallel(indptr, indices, 1.0, 0, data), comm)
+
+
+def test_leiden_medium_graph_matches_python_spec(native):
+    """A graph large enough for several Leiden iterations with long tails (6000 cells, 7 types, resolution 4)."""
+    rs = np.random.default_rng(1)
+    pts = (rs.normal(size=(6000, 8)) + rs.integers(0, 7, size=(6000, 1)) * 2.2).astype(np.float32)
+    idx, dist = upstream.knn_brute(pts, 10)
+    C = native.umap_connectivities(idx, dist)  # bit-identical to the oracle's graph (tested above), and fast
+    w = C.data.astype(np.float64)
+    want = leiden_ref.leiden(C.indptr, C.indices, w, resolution=4.0, seed=2)
+    np.testing.assert_array_equal(native.leiden_csr(C.indptr, C.indices, w, 4.0, 2), want)
+    np.testing.assert_array_equal(native.leiden_knn(idx, dist, 4.0, 2), want)
