@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU session of round 2, one call (~15 min of box time):
-#   gpurun --timeout 1500 -- 'bash scripts/gpu_r2a.sh'
+# First GPU session of round 2, one call (~20-25 min of box time):
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_r2a.sh'
 # 1. the whole GPU suite (new since the last hardware run: tests/test_gpu_zz_leiden.py, per-device kernel attributes, the
 #    upload thread in fit(), the dense first aggregation of the host Louvain);
 # 2. the bench line (e2e should move: predict() 42 -> 8 ms, upload underneath the parent draws);
