@@ -173,3 +173,27 @@ def test_fast_predict_and_score_equal_the_reference_lines(seed):
     want = reference_path.doublet_score(clf.all_log_p_values_, n_iters)
     assert isinstance(got, np.ma.MaskedArray) and not np.ma.getmaskarray(got).any()
     np.testing.assert_array_equal(np.asarray(got), np.asarray(want))
+
+
+def test_integration_stub_matches_the_abi():
+    """INTEGRATION.md's ctypes stub (what a maintainer of the reference would paste) must describe the same
+    ``dd_fit_params`` as the binding the tests run through, and only call symbols the header declares."""
+    import ctypes
+    import os
+    import re
+
+    from conftest import ROOT
+    from doubletdetection_b200 import _capi
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "_FitParams" in b)
+    struct_src = block[block.index("class _FitParams"):block.index("def _p(")]
+    ns = {"ctypes": ctypes}
+    exec(struct_src, ns)
+    assert ns["_FitParams"]._fields_ == _capi.FitParams._fields_
+    assert ctypes.sizeof(ns["_FitParams"]) == ctypes.sizeof(_capi.FitParams)
+    used = set(re.findall(r"_lib\.(dd_[a-z0-9_]+)", block))
+    assert used and used <= set(_capi.SIGNATURES), used - set(_capi.SIGNATURES)
+    header = open(os.path.join(ROOT, "include", "dd_b200.h")).read()
+    for name in re.findall(r"`(dd_[a-z0-9_]+)`", text):  # every entry point the document mentions exists
+        assert re.search(r"\b" + name + r"\s*\(", header), name
