@@ -22,7 +22,7 @@ def reference_available():
     return os.path.exists(REFERENCE_FILE)
 
 
-def _make_stub_modules(louvain_fn=None, record=None):
+def _make_stub_modules(louvain_fn=None, record=None, phenograph_seed=0):
     """``record``: optional dict; every stub call appends what it saw / produced."""
 
     def rec(key, value):
@@ -55,8 +55,12 @@ def _make_stub_modules(louvain_fn=None, record=None):
     def louvain(adata, key_added="louvain", random_state=0, **kw):
         upstream.tl_louvain(adata, key_added=key_added, random_state=random_state, louvain_fn=louvain_fn, **kw)
 
-    def leiden(adata, **kw):
-        raise NotImplementedError("leidenalg is absent from the image; no oracle restatement")
+    def leiden(adata, key_added="leiden", random_state=0, **kw):
+        # sc.pp.neighbors always builds the umap-weighted connectivities; only sc.tl.leiden uses the weights, so the
+        # neighbors stub keeps the pattern (what tl.louvain sees) and the weights are derived here from the same lists
+        adata.obsp["connectivities"] = upstream.fuzzy_connectivities(adata.uns["knn_indices"], adata.uns["knn_distances"])
+        rec("connectivities", adata.obsp["connectivities"])
+        upstream.tl_leiden(adata, key_added=key_added, random_state=random_state, **kw)
 
     pp.scale, pp.neighbors = scale, neighbors
     tl.pca, tl.louvain, tl.leiden = pca, louvain, leiden
@@ -64,18 +68,22 @@ def _make_stub_modules(louvain_fn=None, record=None):
 
     phenograph = types.ModuleType("phenograph")
 
-    def cluster(*a, **k):
-        raise NotImplementedError("phenograph is absent from the image; no oracle restatement")
+    def cluster(data, n_jobs=1, **kw):
+        # phenograph.cluster(X_pca, n_jobs=..., **clustering_kwargs) -> (communities, graph, Q); unseedable upstream, the
+        # restatement fixes seed 0 (what the classifier's default random_state passes on the native path)
+        rec("phenograph_kwargs", dict(kw, n_jobs=n_jobs))
+        labels, graph = upstream.phenograph_cluster(data, seed=phenograph_seed, louvain_fn=louvain_fn, **kw)
+        return labels, graph, None
 
     phenograph.cluster = cluster
     return {"anndata": anndata, "scanpy": sc, "phenograph": phenograph}
 
 
-def load_reference(louvain_fn=None, record=None):
+def load_reference(louvain_fn=None, record=None, phenograph_seed=0):
     """Returns the reference's ``doubletdetection.doubletdetection`` module object (real code)."""
     if not reference_available():
         raise FileNotFoundError(REFERENCE_FILE)
-    stubs = _make_stub_modules(louvain_fn, record)
+    stubs = _make_stub_modules(louvain_fn, record, phenograph_seed)
     saved = {k: sys.modules.get(k) for k in stubs}
     sys.modules.update(stubs)
     try:

@@ -38,10 +38,24 @@ def golden_case(name):
     if name == "structured_1500x300":
         st = datasets.structured_counts(1500, 300, seed=1234)
         return st, dict(n_iters=3, clustering_algorithm="louvain"), dict(p_thresh=1e-3, voter_thresh=0.5)
+    # the phenograph / leiden branches of the reference's own test (tests/test_package.py:17-28) and a PhenoGraph case
+    # with prune=False on structured counts
+    if name == "c1_phenograph_scaled":
+        return (c1, dict(n_iters=2, clustering_algorithm="phenograph", standard_scaling=True),
+                dict(p_thresh=1e-16, voter_thresh=0.5))
+    if name == "c1_leiden_scaled":
+        return (c1, dict(n_iters=2, clustering_algorithm="leiden", standard_scaling=True, random_state=123),
+                dict(p_thresh=1e-16, voter_thresh=0.5))
+    if name == "structured_900x200_phenograph":
+        st = datasets.structured_counts(900, 200, seed=77)
+        return (st, dict(n_iters=2, clustering_algorithm="phenograph", clustering_kwargs={"prune": False}),
+                dict(p_thresh=1e-3, voter_thresh=0.5))
     raise KeyError(name)
 
 
 GOLDEN_NAMES = ["c1_louvain", "c1_louvain_scaled", "hvg_replace", "single_iter", "structured_1500x300"]
+# goldens of the other two clustering branches (same generator: the reference's real code over the restated calls)
+CLUSTER_GOLDEN_NAMES = ["c1_phenograph_scaled", "c1_leiden_scaled", "structured_900x200_phenograph"]
 
 
 @pytest.fixture(scope="session")

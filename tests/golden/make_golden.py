@@ -90,6 +90,15 @@ def main():
     st = datasets.structured_counts(1500, 300, seed=1234)
     run_case("structured_1500x300", st, dict(p_thresh=1e-3, voter_thresh=0.5), n_iters=3,
              clustering_algorithm="louvain")
+    # the other two branches of the reference's own test (tests/test_package.py:17-28), through the reference's real
+    # control flow (:317-343) over the restated phenograph / umap + leiden calls
+    run_case("c1_phenograph_scaled", c1, ref_test_predict, capture_iter0=False, n_iters=2,
+             clustering_algorithm="phenograph", standard_scaling=True)
+    run_case("c1_leiden_scaled", c1, ref_test_predict, capture_iter0=False, n_iters=2, clustering_algorithm="leiden",
+             standard_scaling=True, random_state=123)
+    st2 = datasets.structured_counts(900, 200, seed=77)
+    run_case("structured_900x200_phenograph", st2, dict(p_thresh=1e-3, voter_thresh=0.5), capture_iter0=False, n_iters=2,
+             clustering_algorithm="phenograph", clustering_kwargs={"prune": False})
 
 
 if __name__ == "__main__":

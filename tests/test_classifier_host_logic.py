@@ -81,10 +81,12 @@ def shim(monkeypatch):
     return classifier.BoostClassifier
 
 
-@pytest.mark.parametrize("name", ["c1_louvain", "c1_louvain_scaled", "hvg_replace", "single_iter"])
+@pytest.mark.parametrize("name", ["c1_louvain", "c1_louvain_scaled", "hvg_replace", "single_iter", "c1_phenograph_scaled",
+                                  "c1_leiden_scaled", "structured_900x200_phenograph"])
 def test_shim_orchestration_reproduces_the_reference_goldens(shim, name):
     g = load_golden(name)
     counts, kw, pkw = golden_case(name)
+    kw = dict(kw, clustering_kwargs=dict(kw.get("clustering_kwargs") or {}))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         clf = shim(**kw)
@@ -95,7 +97,7 @@ def test_shim_orchestration_reproduces_the_reference_goldens(shim, name):
     np.testing.assert_array_equal(clf.communities_, g["communities"])
     np.testing.assert_array_equal(clf.synth_communities_, g["synth_communities"])
     np.testing.assert_array_equal(clf.all_scores_, g["all_scores"])
-    np.testing.assert_allclose(clf.all_log_p_values_, g["all_log_p_values"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(clf.all_log_p_values_, g["all_log_p_values"], rtol=1e-12, atol=0, equal_nan=True)
     np.testing.assert_array_equal(labels, g["labels"])
     assert clf.communities_.dtype == np.float64 and clf.synth_communities_.dtype == np.float64  # :188-190
     assert isinstance(clf.parents_, list) and isinstance(clf.parents_[0], list) and len(clf.parents_[0][0]) == 2
@@ -105,7 +107,9 @@ def test_shim_orchestration_reproduces_the_reference_goldens(shim, name):
     n_genes = min(n_genes, counts.shape[1]) if n_genes > 0 else counts.shape[1]
     assert call["omega_shape"] == (min(n_aug, n_genes) if n_aug < n_genes else n_genes, call["n_comp"] + 10)
     assert call["n_power_iter"] == (7 if call["n_comp"] < 0.1 * min(n_aug, n_genes) else 4)
-    assert call["iter_begin"] == 0 and call["iter_end"] == kw["n_iters"] and call["resolution"] == 4.0
+    assert call["iter_begin"] == 0 and call["iter_end"] == kw["n_iters"] and call["clustering"] == kw["clustering_algorithm"]
+    if kw["clustering_algorithm"] != "phenograph":
+        assert call["resolution"] == 4.0
 
 
 def test_shim_rng_stream_continues_across_fits_and_inputs_are_untouched(shim):

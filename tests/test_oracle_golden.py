@@ -6,14 +6,14 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_NAMES, golden_case, load_golden
+from conftest import CLUSTER_GOLDEN_NAMES, GOLDEN_NAMES, golden_case, load_golden
 from oracle import louvain_c, louvain_ref, pca_f64, reference_path, refshim, upstream
 
 
 def _oracle_fit(name):
     counts, kw, pkw = golden_case(name)
     kw = dict(kw)
-    kw.pop("clustering_algorithm")
+    kw["clustering_kwargs"] = dict(kw.get("clustering_kwargs") or {})  # the classifier adds its defaults in place
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         clf = reference_path.OracleClassifier(louvain_fn=louvain_c.louvain, keep_stages=True, **kw)
@@ -23,7 +23,7 @@ def _oracle_fit(name):
     return clf, labels, score
 
 
-@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("name", GOLDEN_NAMES + CLUSTER_GOLDEN_NAMES)
 def test_oracle_matches_reference_goldens(name):
     g = load_golden(name)
     clf, labels, score = _oracle_fit(name)
