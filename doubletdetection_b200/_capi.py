@@ -75,6 +75,7 @@ SIGNATURES = {
     "dd_upload_embedding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p]),
     "dd_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_f32p]),
     "dd_knn_listed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p]),
+    "dd_knn_pruned": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p, c_i64p]),
     "dd_louvain_knn": (
         ctypes.c_int,
         [ctypes.c_int64, ctypes.c_int32, c_i32p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
@@ -454,6 +455,18 @@ class Handle:
                                                          _ptr(weights, ctypes.c_double), float(resolution),
                                                          int(seed) & (2**64 - 1), _ptr(comm, ctypes.c_int32), ctypes.byref(rounds)))
         return comm, rounds.value
+
+    def knn_pruned(self, k, perm, block_group, n_rows, with_dist=True):
+        """Experimental: cluster-ordered exact kNN, pre-pass and both launches on the device.  ``perm``: padded position ->
+        original row or -1; ``block_group``: group of every 256-row block.  Returns (idx, dist, stats)."""
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        block_group = np.ascontiguousarray(block_group, dtype=np.int32)
+        idx = np.empty((n_rows, k), dtype=np.int32)
+        dist = np.empty((n_rows, k), dtype=np.float32) if with_dist else None
+        stats = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.dd_knn_pruned(self._h, k, perm.size, _ptr(perm, ctypes.c_int32), _ptr(block_group, ctypes.c_int32),
+                                            _ptr(idx, ctypes.c_int32), _ptr(dist, ctypes.c_float), _ptr(stats, ctypes.c_int64)))
+        return idx, dist, dict(zip(("pairs_a", "pairs_b", "blocks", "tiles"), stats.tolist()))
 
     def jaccard_graph(self, k, prune=True):
         """PhenoGraph graph of the last ``knn(k)`` as built on the device: scipy CSR (float64, sorted rows, pruned

@@ -825,3 +825,28 @@ extern "C" int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const in
     DD_CUDA(h, cudaStreamSynchronize(h->stream));
     return DD_OK;
 }
+
+// Launchers for knn_prune.cu (the experimental cluster-ordered kNN lives in its own translation unit so that the measured
+// kernels of this file stay byte-identical): operand tiles, the list-driven kernel (lists of 16), the exact re-ranking.
+int dd_knn_launch_prep(dd_handle *h, const float *emb, int64_t n, int64_t n_pad, uint8_t *qa, uint8_t *cb) {
+    DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, emb, n, n_pad, reinterpret_cast<uint4 *>(qa),
+              reinterpret_cast<uint4 *>(cb));
+    return DD_OK;
+}
+
+int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
+                           const int *list_off, const int *list_tiles) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
+        cudaFuncSetAttribute(tc::k_knn_tc<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+    });
+    DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<16, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
+              n_blocks, cand_i, list_off, list_tiles);
+    return DD_OK;
+}
+
+int dd_knn_launch_refine16(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
+    DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, (int64_t)0, n, k, idx_out,
+              dist_out);
+    return DD_OK;
+}

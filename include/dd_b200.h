@@ -104,6 +104,15 @@ int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
 int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const int32_t *list_off, const int32_t *list_tiles,
                   int32_t *idx_out, float *dist_out);
 
+/* Experimental test hook, one step further: the whole cluster-ordered kNN on the device.  perm int32[n_pad] maps a padded
+ * position to an original row or -1 (n_pad a multiple of 256; rows of a group contiguous, every group padded to whole
+ * 256-row blocks), block_group int32[n_pad / 256] names the group of every block.  Launch A (own group) bounds every
+ * query's k-th distance, launch B visits the tiles whose bounding boxes the bound cannot exclude, the result is re-ranked
+ * in the original numbering: identical to dd_knn (which must have been called once on this embedding: it sizes the output
+ * buffers).  stats_out int64[4] (may be NULL): block-tile pairs of launch A, of launch B, blocks, tiles.  k <= 13. */
+int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32_t *perm, const int32_t *block_group, int32_t *idx_out,
+                  float *dist_out, int64_t *stats_out);
+
 /* ---- clustering call, doubletdetection.py:337-343 -----------------------------------------
  * Louvain (RB configuration null model, resolution gamma, unweighted, seeded) on the symmetrised
  * kNN pattern -- what sc.tl.louvain(resolution, random_state, directed=False) optimises.  The

@@ -12,7 +12,9 @@ exactness of the scheme, not yet the device pre-pass:
   3. launch A: every block against the tiles of its own cluster -> an upper bound on each query's 10th distance;
   4. launch B: every block against the tiles whose box-to-box distance^2 (all dimensions) is within the block's
      largest bound;
-  5. the result, mapped back, must equal the dense kNN index for index; kernel times are printed next to each other.
+  5. the result, mapped back, must equal the dense kNN index for index; kernel times are printed next to each other;
+  6. the same scheme once more with steps 2-4 on the device as well (dd_knn_pruned: gather into the padded order, per-tile
+     boxes, thresholds from launch A, list construction, translation back), given only the permutation.
 """
 import os
 import sys
@@ -129,4 +131,23 @@ if not same.all():
     # equal distances can legitimately come back in another order only if their indices tie-break differently after the
     # permutation: the refine step ranks by (distance, PERMUTED index)
     print("  max |distance difference| over all rows:", float(np.abs(np.sort(dist_b[real], 1)[np.argsort(rows)] - np.sort(truth_dist, 1)).max()))
+
+# ---- the same scheme with the pre-pass on the device too (dd_knn_pruned: gather, boxes, thresholds, lists, translation)
+h.upload_embedding(emb)
+h.knn(K)  # sizes the output buffers for the original embedding
+before = h.kernel_timing_report()
+for _ in range(3):
+    idx_p, dist_p, stats = h.knn_pruned(K, perm.astype(np.int32), blocks_of_cluster.astype(np.int32), n)
+after = h.kernel_timing_report()
+print(f"dd_knn_pruned: launch A {stats['pairs_a']} + launch B {stats['pairs_b']} block-tile pairs of {stats['blocks'] * stats['tiles']} "
+      f"({(stats['pairs_a'] + stats['pairs_b']) / (stats['blocks'] * stats['tiles']):.3f}); stage {h.last_stage_ms('knn'):.3f} ms; per call:",
+      flush=True)
+for name in ("prune_gather", "knn_prep", "prune_boxes", "knn_tc_listed", "knn_refine", "prune_threshold", "prune_lists",
+             "prune_offsets", "prune_translate"):
+    a, b = after.get(name, (0.0, 0)), before.get(name, (0.0, 0))
+    if a[1] > b[1]:
+        print(f"    {name:16s} {(a[0] - b[0]) / 3:.3f} ms in {(a[1] - b[1]) // 3} launch(es)")
+same_p = (idx_p.astype(np.int64) == truth_idx).all(1)
+print(f"dd_knn_pruned rows identical to the dense kNN: {int(same_p.sum())} / {n}; lists of launch B equal to the host's: "
+      f"{stats['pairs_b'] == int(sum(len(x) for x in lists_b))}", flush=True)
 h.close()
