@@ -826,8 +826,8 @@ extern "C" int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const in
     return DD_OK;
 }
 
-// Launchers for knn_prune.cu (the experimental cluster-ordered kNN lives in its own translation unit so that the measured
-// kernels of this file stay byte-identical): operand tiles, the list-driven kernel (lists of 16), the exact re-ranking.
+// Launchers for knn_prune.cu (the experimental cluster-ordered kNN lives in its own translation unit; the measured kernels of
+// this file keep their instruction sequence): operand tiles, the list-driven kernel (lists of 16), the exact re-ranking.
 int dd_knn_launch_prep(dd_handle *h, const float *emb, int64_t n, int64_t n_pad, uint8_t *qa, uint8_t *cb) {
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, emb, n, n_pad, reinterpret_cast<uint4 *>(qa),
               reinterpret_cast<uint4 *>(cb));

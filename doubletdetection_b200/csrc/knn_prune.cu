@@ -1,6 +1,6 @@
 // knn_prune.cu -- EXPERIMENTAL (never run on hardware; DESIGN.md section 5 "next lever"): the exact kNN with cluster-ordered
-// candidate tiles, everything after the ordering on the device.  Its own translation unit: the measured kernels of knn.cu stay
-// byte-identical.
+// candidate tiles, everything after the ordering on the device.  Its own translation unit: knn.cu only gains three launchers,
+// its measured kernels keep their instruction sequence.
 #include "dd_internal.h"
 
 #include <cmath>
