@@ -337,3 +337,23 @@ def test_leiden_medium_graph_matches_python_spec(native):
     want = leiden_ref.leiden(C.indptr, C.indices, w, resolution=4.0, seed=2)
     np.testing.assert_array_equal(native.leiden_csr(C.indptr, C.indices, w, 4.0, 2), want)
     np.testing.assert_array_equal(native.leiden_knn(idx, dist, 4.0, 2), want)
+
+
+def test_phenograph_with_parallel_first_level_is_equivalent(native):
+    """PhenoGraph's clustering with the first Louvain level by synchronous rounds (the plan for the device, DESIGN.md
+    section 10) against today's fully sequential sweep on the same Jaccard graph: oracle == host twin label for label, and
+    the two flavours agree on everything but the arbitrary small clusters."""
+    from sklearn.metrics import adjusted_rand_score
+
+    rs = np.random.default_rng(9)
+    x = np.vstack([rs.normal(4.0 * c, 1.0, (m, 10)) for c, m in enumerate((700, 500, 300, 40, 8))]).astype(np.float32)
+    want, G = upstream.phenograph_cluster(x, k=30, prune=True, min_cluster_size=10, seed=0, level0="parallel")
+    w = G.data.astype(np.float64)
+    got = native.louvain_csr(G.indptr, G.indices, w, 1.0, 0, level0="parallel").astype(np.int64)
+    sizes = np.bincount(got)
+    got[sizes[got] < 10] = -1
+    np.testing.assert_array_equal(got, want)
+    seq, _ = upstream.phenograph_cluster(x, k=30, prune=True, min_cluster_size=10, seed=0, louvain_fn=louvain_c.louvain)
+    both = (seq >= 0) & (want >= 0)
+    assert both.mean() > 0.95 and adjusted_rand_score(seq[both], want[both]) > 0.95
+    assert abs(int((seq < 0).sum()) - int((want < 0).sum())) <= 0.02 * x.shape[0]
