@@ -113,6 +113,12 @@ struct dd_handle {
     double *d_lv_tot = nullptr;
     double *d_lv_w = nullptr;  // Jaccard edge weights of the PhenoGraph graph (one per adjacency entry)
     int64_t cap_lv_n = 0, cap_lv_nnz = 0, cap_lv_w = 0;
+    // experimental weighted first level (louvain_gpu_w.cu): fixed-point weights, int64 degrees / totals, buckets, state
+    long long *d_lvw_wq = nullptr, *d_lvw_i64 = nullptr;  // wq[nnz]; k | tot | two_m (2 n + 1)
+    int32_t *d_lvw_i32 = nullptr;                          // csize | desired | bucket (n each) + counters
+    int64_t cap_lvw_nnz = 0, cap_lvw_n = 0, lvw_bucket_n = -1;
+    uint64_t lvw_bucket_seed = 0;
+    std::vector<int32_t> lvw_colour_off;
     int64_t lv_bucket_n = -1;
     uint64_t lv_bucket_seed = 0;
     std::vector<int32_t> lv_colour_off;
@@ -231,8 +237,10 @@ int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *ad
                                 double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
 // PhenoGraph on the host from the device-built weighted graph (rows in any order, zero weights = pruned edges):
 // Louvain at resolution 1 on the weighted graph, labels by decreasing size, communities < min_cluster_size -> -1
+// comm0 (may be NULL): the first level already done on the device (experimental, DD_PHENO_LEVEL0)
 int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
-                                  int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out);
+                                  int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out, const int32_t *comm0);
+int dd_dev_louvain_level0_weighted(dd_handle *h, double gamma, uint64_t seed);  // louvain_gpu_w.cu (experimental)
 // Leiden on the umap-weighted neighbour graph (leiden.cpp): kNN lists with self in column 0 + float32 distances
 int dd_host_leiden_knn(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist, double resolution,
                        uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);

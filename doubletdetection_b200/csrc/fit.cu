@@ -6,6 +6,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -55,6 +56,8 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     // Leiden works on umap's weighted graph, whose weights come from the kNN DISTANCES: the lists + distances of every
     // iteration go to the host workers, which build the fuzzy simplicial set and partition it (leiden.cpp)
     const bool leiden = p->clustering == DD_CLUSTER_LEIDEN;
+    // experimental (never run on hardware): PhenoGraph's first Louvain level on the device, in fixed point (louvain_gpu_w.cu)
+    static const bool pheno_level0 = getenv("DD_PHENO_LEVEL0") != nullptr;
     if (pheno && (p->pheno_k < 1 || p->pheno_k > 30))
         return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_fit_iterations: phenograph k must be in [1, 30]");
     DD_CUDA(h, cudaSetDevice(h->device));
@@ -158,7 +161,8 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
                                              p->seed, labels.data(), &n_comm);
                 else if (pheno)
                     wrc = dd_host_phenograph_from_graph(A, off, adj, reinterpret_cast<const double *>(s.graph + w_off), p->seed,
-                                                        p->pheno_min_cluster_size, labels.data(), &n_comm);
+                                                        p->pheno_min_cluster_size, labels.data(), &n_comm,
+                                                        pheno_level0 ? comm0 : nullptr);
                 else
                     wrc = dd_host_louvain_from_level0(A, off, adj, comm0, p->resolution, p->seed, labels.data(), &n_comm);
                 if (wrc != DD_OK) werr = "dd_fit_iterations: clustering rejected the device graph";
@@ -274,6 +278,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             cudaStream_t main_stream = h->stream;
             h->stream = h->stream2;
             rc = pheno ? dd_dev_jaccard_graph(h, k, p->pheno_prune) : dd_dev_louvain_level0(h, k, p->resolution, p->seed);
+            if (rc == DD_OK && pheno && pheno_level0) rc = dd_dev_louvain_level0_weighted(h, 1.0, p->seed);
             h->stream = main_stream;
         }
         if (rc != DD_OK) break;

@@ -546,10 +546,12 @@ int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *ad
 // ---- PhenoGraph (doubletdetection.py:318-327 -> phenograph.cluster; specification: oracle/upstream.py
 // phenograph_cluster).  The graph arrives as CSR with rows in any order and zero weights for pruned entries.
 namespace {
-int phenograph_finish(Graph &g, uint64_t seed, int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out) {
+int phenograph_finish(Graph &g, uint64_t seed, int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out,
+                      const int32_t *comm0 = nullptr) {
     const int32_t n = g.n;
     int32_t nc = 0;
-    const int rc = run_louvain(g, 1.0, seed, labels_out, &nc);  // standard modularity; labels by decreasing size
+    // standard modularity; labels by decreasing size.  comm0: first level already done (device, fixed-point weights)
+    const int rc = run_louvain(g, 1.0, seed, labels_out, &nc, comm0, false);
     if (rc != DD_OK) return rc;
     std::vector<int64_t> size(std::max(nc, 1), 0);
     for (int32_t i = 0; i < n; i++) size[labels_out[i]]++;
@@ -561,7 +563,7 @@ int phenograph_finish(Graph &g, uint64_t seed, int32_t min_cluster_size, int32_t
 }  // namespace
 
 int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
-                                  int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out) {
+                                  int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out, const int32_t *comm0) {
     if (n < 0 || (n > 0 && (!off || !labels_out))) return DD_ERR_ARG;
     Graph g;
     g.n = (int32_t)n;
@@ -587,7 +589,10 @@ int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *
         g.indptr[i + 1] = (int64_t)g.indices.size();
     }
     g.selfw.assign(n, 0.0);
-    return phenograph_finish(g, seed, min_cluster_size, labels_out, n_comm_out);
+    if (comm0)
+        for (int64_t i = 0; i < n; i++)
+            if (comm0[i] < 0 || comm0[i] >= n) return DD_ERR_ARG;
+    return phenograph_finish(g, seed, min_cluster_size, labels_out, n_comm_out, comm0);
 }
 
 // Host twin of the device path: the same graph from the kNN lists (n x k, self in column 0) on the CPU.
@@ -643,7 +648,7 @@ extern "C" int dd_phenograph_knn(int64_t n, int32_t k, const int32_t *knn_idx, i
         off[i + 1] = (int32_t)adj.size();
     }
     const int rc = dd_host_phenograph_from_graph(n, off.data(), adj.data(), w.data(), seed, min_cluster_size, labels_out,
-                                                 n_communities_out);
+                                                 n_communities_out, nullptr);
     if (rc != DD_OK) dd_set_global_error("dd_phenograph_knn: clustering failed");
     return rc;
 }

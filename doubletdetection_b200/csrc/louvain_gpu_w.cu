@@ -13,6 +13,7 @@
 // louvain_gpu.cu's machinery.
 #include "dd_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -54,8 +55,8 @@ __global__ void __launch_bounds__(256) k_lvw_propose(const int32_t *__restrict__
                                                      const long long *__restrict__ wq, const int32_t *comm,
                                                      const long long *__restrict__ k, const long long *tot,
                                                      const int32_t *csize, const int32_t *__restrict__ bucket, int b0, int b1,
-                                                     double gamma, double two_m, int32_t *__restrict__ desired,
-                                                     const int32_t *__restrict__ counters) {
+                                                     double gamma, double two_m_arg, const long long *__restrict__ two_m_dev,
+                                                     int32_t *__restrict__ desired, const int32_t *__restrict__ counters) {
     __shared__ int32_t s_key[8 * kTableW];
     __shared__ unsigned long long s_sum[8 * kTableW];
     if (counters[1]) return;  // the level settled in an earlier round
@@ -63,7 +64,13 @@ __global__ void __launch_bounds__(256) k_lvw_propose(const int32_t *__restrict__
     const int w = blockIdx.x * (blockDim.x >> 5) + wl;
     if (b0 + w >= b1) return;  // whole warp
     const int i = bucket[b0 + w];
-    const int s = off[i], d = off[i + 1] - s;  // buckets hold nodes with d > 0 only
+    const int s = off[i], d = off[i + 1] - s;
+    if (d <= 0) {  // whole warp
+        if (lane == 0) desired[i] = -1;
+        return;
+    }
+    // pipeline flavour: 2m was summed on the device (k_lvw_prepare); test hook: the host passes it
+    const double two_m = two_m_dev ? (double)*two_m_dev : two_m_arg;
     const int ci = __ldcg(comm + i);
     const long long ki = k[i];
     const double gk = __dmul_rn(gamma, (double)ki);
@@ -79,6 +86,7 @@ __global__ void __launch_bounds__(256) k_lvw_propose(const int32_t *__restrict__
         }
         __syncwarp();
         for (int f = lane; f < d; f += 32) {
+            if (wq[s + f] == 0) continue;  // pruned entry of the device-built graph: not an edge
             const int c = __ldcg(comm + adj[s + f]);
             unsigned slot = ((unsigned)c * 2654435761u) >> kTableShiftW;
             for (;;) {
@@ -108,6 +116,7 @@ __global__ void __launch_bounds__(256) k_lvw_propose(const int32_t *__restrict__
         for (int f = lane; f < d; f += 32)
             if (__ldcg(comm + adj[s + f]) == ci) w_stay += wq[s + f];
         for (int e = lane; e < d; e += 32) {
+            if (wq[s + e] == 0) continue;
             const int c = __ldcg(comm + adj[s + e]);
             if (c == ci) continue;
             long long wc = 0;
@@ -230,7 +239,8 @@ extern "C" int dd_louvain_level0_weighted(dd_handle *h, int64_t n, const int64_t
                 const int b0 = cnt[c], b1 = cnt[c + 1];
                 if (b1 == b0) continue;
                 DD_LAUNCH(h, "lvw_propose", k_lvw_propose, (unsigned)((b1 - b0 + 7) / 8), 256, 0, d_off.p, d_adj.p, d_wq.p, d_comm.p,
-                          d_k.p, d_tot.p, d_csize.p, d_bucket.p, b0, b1, gamma, two_m, d_desired.p, d_counters.p);
+                          d_k.p, d_tot.p, d_csize.p, d_bucket.p, b0, b1, gamma, two_m, (const long long *)nullptr, d_desired.p,
+                          d_counters.p);
                 DD_LAUNCH(h, "lvw_apply", k_lvw_apply, (unsigned)((b1 - b0 + 255) / 256), 256, 0, d_comm.p, d_k.p, d_tot.p, d_csize.p,
                           d_bucket.p, b0, b1, d_desired.p, d_counters.p);
             }
@@ -242,5 +252,80 @@ extern "C" int dd_louvain_level0_weighted(dd_handle *h, int64_t n, const int64_t
     DD_CUDA(h, cudaMemcpyAsync(counters, d_counters.p, sizeof(int32_t) * 3, cudaMemcpyDeviceToHost, h->stream));
     DD_CUDA(h, cudaStreamSynchronize(h->stream));
     if (rounds_out) *rounds_out = counters[2];
+    return DD_OK;
+}
+
+// ---- pipeline flavour (experimental, DD_PHENO_LEVEL0): the level on the device-built PhenoGraph graph -------------------
+namespace {
+// fixed-point weights, weighted degrees, 2m and the initial state in one pass over the device graph (zero = pruned entry)
+__global__ void k_lvw_prepare(const int32_t *__restrict__ off, const double *__restrict__ w, int n, long long *__restrict__ wq,
+                              long long *__restrict__ k, long long *__restrict__ tot, long long *__restrict__ two_m,
+                              int32_t *__restrict__ comm, int32_t *__restrict__ csize, int32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) counters[0] = counters[1] = counters[2] = 0;
+    if (i >= n) return;
+    long long s = 0;
+    for (int e = off[i]; e < off[i + 1]; e++) {
+        const long long q = __double2ll_rn(__dmul_rn(w[e], 4294967296.0));  // round to nearest even, like the specification
+        wq[e] = q;
+        s += q;
+    }
+    k[i] = s;
+    tot[i] = s;
+    comm[i] = i;
+    csize[i] = 1;
+    if (s) atomicAdd(reinterpret_cast<unsigned long long *>(two_m), (unsigned long long)s);
+}
+}  // namespace
+
+// Graph: h->d_lv_off / d_lv_adj / d_lv_w as left by dd_dev_jaccard_graph (rows in any order, 0 = pruned).  Result:
+// h->d_lv_comm (community = node id), which the fit loop already copies to the host slot.  Asynchronous on h->stream.
+int dd_dev_louvain_level0_weighted(dd_handle *h, double gamma, uint64_t seed) {
+    const int64_t n64 = h->emb_rows;
+    if (!h->d_lv_off || !h->d_lv_adj || !h->d_lv_w || n64 > h->cap_lv_n)
+        return dd_fail(h, DD_ERR_ARG, "weighted louvain level: build the graph first");
+    const int n = (int)n64;
+    if (h->cap_lv_nnz > h->cap_lvw_nnz || n > h->cap_lvw_n) {
+        for (void *p : {(void *)h->d_lvw_wq, (void *)h->d_lvw_i64, (void *)h->d_lvw_i32})
+            if (p) cudaFree(p);
+        h->d_lvw_wq = h->d_lvw_i64 = nullptr;
+        h->d_lvw_i32 = nullptr;
+        h->cap_lvw_nnz = h->cap_lvw_n = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_lvw_wq, sizeof(long long) * (size_t)std::max<int64_t>(h->cap_lv_nnz, 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_lvw_i64, sizeof(long long) * (2 * (size_t)h->cap_lv_n + 1)));
+        DD_CUDA(h, cudaMalloc(&h->d_lvw_i32, sizeof(int32_t) * (3 * (size_t)h->cap_lv_n + 16)));
+        h->cap_lvw_nnz = h->cap_lv_nnz;
+        h->cap_lvw_n = h->cap_lv_n;
+        h->lvw_bucket_n = -1;
+    }
+    long long *k = h->d_lvw_i64, *tot = k + h->cap_lvw_n, *two_m = tot + h->cap_lvw_n;
+    int32_t *csize = h->d_lvw_i32, *desired = csize + h->cap_lvw_n, *bucket = desired + h->cap_lvw_n,
+            *counters = bucket + h->cap_lvw_n;
+    if (h->lvw_bucket_n != n || h->lvw_bucket_seed != seed) {  // colour classes: a pure function of (n, seed)
+        std::vector<int32_t> cnt(kColoursW + 1, 0), nodes((size_t)std::max(n, 1));
+        for (int i = 0; i < n; i++) cnt[colour_of_w(seed, i) + 1]++;
+        for (int c = 0; c < kColoursW; c++) cnt[c + 1] += cnt[c];
+        h->lvw_colour_off.assign(cnt.begin(), cnt.end());
+        std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+        for (int i = 0; i < n; i++) nodes[fill[colour_of_w(seed, i)]++] = i;
+        DD_CUDA(h, cudaMemcpyAsync(bucket, nodes.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+        DD_CUDA(h, cudaStreamSynchronize(h->stream));  // `nodes` is a temporary (once per fit)
+        h->lvw_bucket_n = n;
+        h->lvw_bucket_seed = seed;
+    }
+    DD_CUDA(h, cudaMemsetAsync(two_m, 0, sizeof(long long), h->stream));
+    DD_LAUNCH(h, "lvw_prepare", k_lvw_prepare, (unsigned)((n + 255) / 256), 256, 0, h->d_lv_off, h->d_lv_w, n, h->d_lvw_wq, k, tot,
+              two_m, h->d_lv_comm, csize, counters);
+    for (int round = 0; round < kMaxRoundsW; round++) {
+        for (int c = 0; c < kColoursW; c++) {
+            const int b0 = h->lvw_colour_off[c], b1 = h->lvw_colour_off[c + 1];
+            if (b1 == b0) continue;
+            DD_LAUNCH(h, "lvw_propose", k_lvw_propose, (unsigned)((b1 - b0 + 7) / 8), 256, 0, h->d_lv_off, h->d_lv_adj, h->d_lvw_wq,
+                      h->d_lv_comm, k, tot, csize, bucket, b0, b1, gamma, 0.0, (const long long *)two_m, desired, counters);
+            DD_LAUNCH(h, "lvw_apply", k_lvw_apply, (unsigned)((b1 - b0 + 255) / 256), 256, 0, h->d_lv_comm, k, tot, csize, bucket, b0,
+                      b1, desired, counters);
+        }
+        DD_LAUNCH(h, "lvw_round_end", k_lvw_round_end, 1, 1, 0, counters, n);
+    }
     return DD_OK;
 }

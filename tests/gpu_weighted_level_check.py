@@ -9,6 +9,9 @@ its checker.
 import os
 import sys
 import time
+import warnings
+
+os.environ["DD_PHENO_LEVEL0"] = "1"  # read once by dd_fit_iterations: PhenoGraph's first level on the device (last section)
 
 import numpy as np
 
@@ -50,3 +53,20 @@ for n, k, kind, gamma, seed in CASES[: int(os.environ.get("DD_CHECK_CASES", len(
         print("  first differences:", [(int(i), int(got[i]), int(want[i])) for i in bad[:8]], "of", bad.size)
 print("ALL EQUAL" if ok_all else "MISMATCH")
 h.close()
+
+# ---- the same level inside the fit loop (DD_PHENO_LEVEL0=1): BoostClassifier(phenograph) against the oracle's PhenoGraph
+# restatement with the parallel first level
+from doubletdetection_b200 import BoostClassifier  # noqa: E402
+from oracle import datasets, reference_path  # noqa: E402
+
+counts = datasets.structured_counts(1500, 300, seed=1234)
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    t0 = time.perf_counter()
+    clf = BoostClassifier(n_iters=3, random_state=0, n_jobs=2).fit(counts)
+    t_fit = time.perf_counter() - t0
+    ora = reference_path.OracleClassifier(n_iters=3, random_state=0, clustering_algorithm="phenograph",
+                                          clustering_kwargs={"level0": "parallel"}).fit(counts)
+same = (clf.communities_ == ora.communities_).all(axis=1)
+print(f"fit loop with the device level: iterations with communities identical to the oracle (parallel first level): "
+      f"{int(same.sum())}/{same.size}; fit {1e3 * t_fit:.0f} ms; stage ms {clf.stage_ms_}", flush=True)
