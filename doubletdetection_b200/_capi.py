@@ -344,6 +344,9 @@ class Handle:
 
     # fit prologue
     def upload_counts(self, csr):
+        # the device CSR is int32-indexed: refuse what would wrap instead of uploading garbage
+        if int(csr.indptr[-1]) >= 2**31 or max(csr.shape) >= 2**31:
+            raise ValueError(f"count matrix too large for the int32-indexed device CSR (nnz={int(csr.indptr[-1])}, shape={csr.shape})")
         indptr = np.ascontiguousarray(csr.indptr, dtype=np.int32)
         indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
         data = _f32(csr.data)

@@ -1023,7 +1023,9 @@ extern "C" int dd_median_lib_size(dd_handle *h, float *median_out) {
 }
 
 int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
-    if (!h->d_indptr || !h->d_parents || h->A == 0) return dd_fail(h, DD_ERR_ARG, "normalise: upload counts and parents first");
+    // M == 0 (int(boost_rate * n_cells) == 0, tolerated by the reference) never allocates the parents
+    if (!h->d_indptr || (h->M > 0 && !h->d_parents) || h->A == 0)
+        return dd_fail(h, DD_ERR_ARG, "normalise: upload counts and parents first");
     const int64_t need = h->A * h->ld;
     DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, need));
     // DD_DENSE_V=0 keeps the shared-memory row-buffer kernel (A/B comparison; also used when the merge-through-

@@ -236,7 +236,7 @@ int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double res
 int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *adj, const int32_t *comm0,
                                 double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
 // PhenoGraph on the host from the device-built weighted graph (rows in any order, zero weights = pruned edges):
-// Louvain at resolution 1 on the weighted graph, labels by decreasing size, communities < min_cluster_size -> -1
+// Louvain at resolution 1 on the weighted graph, labels by decreasing size, communities <= min_cluster_size -> -1
 // comm0 (may be NULL): the first level already done on the device (experimental, DD_PHENO_LEVEL0)
 int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
                                   int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out, const int32_t *comm0);

@@ -556,7 +556,7 @@ int phenograph_finish(Graph &g, uint64_t seed, int32_t min_cluster_size, int32_t
     std::vector<int64_t> size(std::max(nc, 1), 0);
     for (int32_t i = 0; i < n; i++) size[labels_out[i]]++;
     for (int32_t i = 0; i < n; i++)
-        if (size[labels_out[i]] < min_cluster_size) labels_out[i] = -1;  // phenograph: min_cluster_size
+        if (size[labels_out[i]] <= min_cluster_size) labels_out[i] = -1;  // phenograph.core.sort_by_size keeps sizes > min_size
     if (n_comm_out) *n_comm_out = nc;
     return DD_OK;
 }

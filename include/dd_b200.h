@@ -126,7 +126,7 @@ int dd_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resoluti
  * min_cluster_size = 10), from the exact kNN lists knn_idx int32[n * k] (self in column 0, so k = 31 for
  * PhenoGraph's k = 30): Jaccard graph w_ij = s / (2(k-1) - s), s = shared neighbours; prune keeps mutual edges
  * with the product of the two directed weights, otherwise the average; Louvain at resolution 1 on the weighted
- * graph; labels by decreasing size, communities smaller than min_cluster_size get -1.  The phenograph package
+ * graph; labels by decreasing size, communities of at most min_cluster_size cells get -1 (phenograph keeps sizes > min_size).  The phenograph package
  * (absent from the image) runs its bundled Louvain binaries repeatedly with time-based seeds; this is ONE seeded
  * run of the in-repo Louvain (specification: oracle/upstream.py phenograph_cluster).  Pure host code: the host
  * twin of what dd_fit_iterations does with the graph built on the device. */
@@ -216,7 +216,7 @@ typedef struct dd_fit_params {
     int32_t clustering;       /* DD_CLUSTER_LOUVAIN / DD_CLUSTER_LEIDEN (:329-343) or DD_CLUSTER_PHENOGRAPH (:318-327) */
     int32_t pheno_k;          /* phenograph.cluster k (30): neighbours per cell, self excluded */
     int32_t pheno_prune;      /* 1: keep mutual edges, weight product (the reference's default); 0: average */
-    int32_t pheno_min_cluster_size; /* 10: smaller communities are labelled -1 (NaN scores, :379-381) */
+    int32_t pheno_min_cluster_size; /* 10: communities of <= 10 cells are labelled -1 (NaN scores, :379-381) */
 } dd_fit_params;
 #define DD_CLUSTER_LOUVAIN 0
 #define DD_CLUSTER_PHENOGRAPH 1

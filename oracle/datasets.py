@@ -30,3 +30,21 @@ def structured_counts(n_cells, n_genes, seed=1234, n_types=8, chunk=20000):
     X = sp_sparse.vstack(blocks).tocsr()
     X.sort_indices()
     return X
+
+
+def structured_counts_with_doublets(n_cells, n_genes, seed=1234, doublet_frac=0.08, n_types=8):
+    """The structured counts with real doublets planted among the cells: the last ``int(doublet_frac * n_cells)`` rows are
+    replaced by the sum of two randomly chosen earlier cells (so most of them are heterotypic).  ``structured_counts`` has
+    no doublets and the classifier rightly calls none on it, which makes label parity trivial; this variant is what the
+    end-to-end label comparisons run on.  Returns (float32 CSR, bool[n_cells] is_doublet)."""
+    X = structured_counts(n_cells, n_genes, seed=seed, n_types=n_types)
+    n_dbl = int(doublet_frac * n_cells)
+    rs = np.random.default_rng([seed, 99])
+    n_single = n_cells - n_dbl
+    pa = rs.integers(0, n_single, n_dbl)
+    pb = rs.integers(0, n_single, n_dbl)
+    Y = sp_sparse.vstack([X[:n_single], X[pa] + X[pb]]).tocsr()
+    Y.sort_indices()
+    truth = np.zeros(n_cells, dtype=bool)
+    truth[n_single:] = True
+    return Y.astype(np.float32), truth

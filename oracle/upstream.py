@@ -295,8 +295,8 @@ def jaccard_graph(nbr_idx, prune=True):
 def phenograph_cluster(X_pca, k=30, prune=True, min_cluster_size=10, seed=0, louvain_fn=None, level0="sequential"):
     """``phenograph.cluster(X_pca, n_jobs=..., prune=...)[0]`` -- doubletdetection.py:320 (defaults k=30,
     jaccard=True, min_cluster_size=10): exact k+1 nearest neighbours, self dropped; Jaccard graph; Louvain on the
-    weighted graph (standard modularity = resolution 1); communities numbered by decreasing size, those smaller
-    than ``min_cluster_size`` relabelled -1.  Upstream runs its bundled Louvain binaries repeatedly with
+    weighted graph (standard modularity = resolution 1); communities numbered by decreasing size, those NOT larger
+    than ``min_cluster_size`` relabelled -1 (``sort_by_size``: ``sizes[c] > min_size`` keeps the label).  Upstream runs its bundled Louvain binaries repeatedly with
     time-based seeds and keeps the best modularity, so its labels are not reproducible even against itself;
     the oracle fixes ONE seeded run of the in-repo Louvain specification.  PARITY UNPINNED for this stage."""
     idx, _ = knn_brute(np.asarray(X_pca), k + 1)
@@ -307,5 +307,6 @@ def phenograph_cluster(X_pca, k=30, prune=True, min_cluster_size=10, seed=0, lou
     kw = {} if level0 == "sequential" else {"level0": level0}
     labels = np.asarray(fn(G.indptr, G.indices, G.data, resolution=1.0, seed=int(seed), **kw), dtype=np.int64).copy()
     sizes = np.bincount(labels, minlength=labels.max() + 1 if labels.size else 0)
-    labels[sizes[labels] < min_cluster_size] = -1
+    # phenograph.core.sort_by_size keeps a community only if its size is > min_size: exactly min_size cells -> -1
+    labels[sizes[labels] <= min_cluster_size] = -1
     return labels, G

@@ -118,8 +118,7 @@ def test_reference_package_test_mirrored():
 def test_classifier_phenograph_vs_reference_golden(name):
     """The PhenoGraph branch against goldens produced by the reference's REAL control flow (doubletdetection.py:317-327,
     tests/golden/make_golden.py) over the restated phenograph.cluster: parents bit-exact; wherever the communities of an
-    iteration are identical (they are unless a 31st-neighbour near-tie flips a Jaccard count) scores are identical and
-    log p-values agree to 1e-4; at least one iteration must be identical."""
+    iteration are identical scores are identical and log p-values agree to 1e-4; EVERY iteration must be identical."""
     from conftest import golden_case, load_golden
 
     from doubletdetection_b200 import BoostClassifier
@@ -135,10 +134,8 @@ def test_classifier_phenograph_vs_reference_golden(name):
     same = (clf.communities_ == g["communities"]).all(axis=1)
     print(f"\n[{name}] iterations with identical communities: {int(same.sum())}/{same.size}; "
           f"cells labelled -1 in iteration 0: {int((clf.communities_[0] < 0).sum())} (golden {int((g['communities'][0] < 0).sum())})")
-    assert same.any()
-    for i in np.nonzero(same)[0]:
-        np.testing.assert_array_equal(clf.synth_communities_[i], g["synth_communities"][i])
-        np.testing.assert_array_equal(clf.all_scores_[i], g["all_scores"][i])
-        np.testing.assert_allclose(clf.all_log_p_values_[i], g["all_log_p_values"][i], rtol=1e-4, atol=1e-12, equal_nan=True)
-    if same.all():
-        np.testing.assert_array_equal(labels, g["labels"])
+    assert same.all(), f"communities differ from the golden in iterations {np.nonzero(~same)[0]}"
+    np.testing.assert_array_equal(clf.synth_communities_, g["synth_communities"])
+    np.testing.assert_array_equal(clf.all_scores_, g["all_scores"])
+    np.testing.assert_allclose(clf.all_log_p_values_, g["all_log_p_values"], rtol=1e-4, atol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(labels, g["labels"])

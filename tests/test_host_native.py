@@ -165,6 +165,27 @@ def test_phenograph_host_twin_matches_oracle(native, prune):
     assert (many == -1).sum() >= (got == -1).sum()
 
 
+def test_phenograph_min_cluster_size_boundary(native):
+    """phenograph.core.sort_by_size keeps a community only if its size is > min_cluster_size: a community of EXACTLY
+    min_cluster_size cells is relabelled -1 (NaN score / log p downstream, doubletdetection.py:379-381), one of
+    min_cluster_size + 1 keeps its label.  Both the product's host code and the oracle restatement."""
+    from oracle import louvain_c, upstream
+
+    rs = np.random.default_rng(5)
+    sizes = (60, 11, 10)
+    x = np.vstack([rs.normal(40.0 * c, 1.0, (m, 6)) for c, m in enumerate(sizes)]).astype(np.float32)
+    idx, _ = upstream.knn_brute(x, 10)
+    for prune in (True, False):
+        want, _ = upstream.phenograph_cluster(x, k=9, prune=prune, min_cluster_size=10, seed=0, louvain_fn=louvain_c.louvain)
+        got = native.phenograph_knn(idx, prune=prune, min_cluster_size=10, seed=0)
+        np.testing.assert_array_equal(got, want)
+        assert (got[71:] == -1).all(), "a community of exactly min_cluster_size cells must be labelled -1"
+        assert len(set(got[60:71].tolist())) == 1 and got[60] >= 0, "a community of min_cluster_size + 1 cells keeps its label"
+        # one more cell allowed -> the 10-cell community is kept
+        loose = native.phenograph_knn(idx, prune=prune, min_cluster_size=9, seed=0)
+        assert (loose[71:] >= 0).all()
+
+
 # ---- clustering_algorithm="leiden": umap connectivities + Leiden on the host workers (leiden.cpp)
 def _blobs(n, dim, seed, spread=2.5, n_types=5):
     rs = np.random.default_rng(seed)
