@@ -44,6 +44,7 @@ WORKLOADS = {  # BASELINE.json configs
     "c5": dict(n_cells=1000000, n_genes=2000, kind="structured", desc="1M cells x 2k HVG synthetic"),
 }
 N_ITERS = 25
+STRONG_ITERS = 24  # BASELINE configs[3]: 24 iterations, 3 per GPU on 8 GPUs
 BOOST_RATE = 0.25
 N_COMPONENTS = 30
 PSEUDOCOUNT = 0.1
@@ -113,6 +114,13 @@ def make_counts_sharded(wl, rank, world, dist, device):
     x = sp_sparse.vstack(parts).tocsr()
     x.sort_indices()
     return x
+
+
+def workload_string(args, wl):
+    """config.workload -- identical on the product and the reference arm."""
+    if getattr(args, "scaling", "weak") == "strong":
+        return f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters={STRONG_ITERS} sharded over the GPUs, {args.clustering}"
+    return f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, {args.clustering}"
 
 
 def draw_parents(rng, n_cells, n_iters):
@@ -241,27 +249,37 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+def all_host_threads():
+    """Context manager: BLAS / OpenMP pools at every core this process may use.  torchrun exports OMP_NUM_THREADS=1 when
+    nproc-per-node > 1, which would make the CPU arm single-threaded; the pools are already initialised from that
+    environment when numpy was imported, so they are resized here (threadpoolctl) rather than through the environment."""
+    from threadpoolctl import threadpool_limits
+
+    return threadpool_limits(limits=cpu_cores())
+
+
 def run_reference_arm(args, wl, counts):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU path is timed once, on rank 0
     state = cpu_state(counts)
-    for _ in range(args.warmup):
-        cpu_one_iteration(state)
-    state["stage_s"] = {}  # per-stage seconds of the timed steps only
-    t0 = time.perf_counter()
-    cells = 0
-    for _ in range(args.steps):
-        cells += cpu_one_iteration(state)
-    dt = time.perf_counter() - t0
+    with all_host_threads():
+        for _ in range(args.warmup):
+            cpu_one_iteration(state)
+        state["stage_s"] = {}  # per-stage seconds of the timed steps only
+        t0 = time.perf_counter()
+        cells = 0
+        for _ in range(args.steps):
+            cells += cpu_one_iteration(state)
+        dt = time.perf_counter() - t0
     value = cells / dt
     sample = "one _one_fit iteration per step (of the 25-iteration fit), all host cores for BLAS / kNN, 1 thread Louvain"
     line = {
         "impl": "reference", "metric": "augmented-cells/sec through BoostClassifier.fit (n_iters=25)", "value": value,
         "unit": "augmented-cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, louvain", "step": sample},
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": getattr(args, "scaling", "weak"),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args, wl), "step": sample},
         "cpu_baseline": {"value": value, "unit": "augmented-cells/s", "cores": cpu_cores(), "kind": "port", "sample": sample,
                          "stage_seconds": {k_: round(v_, 3) for k_, v_ in state.get("stage_s", {}).items()},
                          "host": cpu_environment()},
@@ -365,8 +383,15 @@ def run_ours(args, wl, counts):
     n_synth = int(BOOST_RATE * n_cells)
     n_aug = n_cells + n_synth
     host_threads = max(1, cpu_cores() // world)
-    total_iters = N_ITERS * world  # weak scaling: every rank owns 25 iterations
-    it0, it1 = rank * N_ITERS, (rank + 1) * N_ITERS
+    strong = args.scaling == "strong"
+    if strong:  # BASELINE configs[3]: ONE 24-iteration fit, its iterations dealt to the GPUs (3 per GPU at N = 8)
+        from doubletdetection_b200.classifier import iteration_shard
+
+        total_iters = STRONG_ITERS
+        it0, it1 = iteration_shard(total_iters, rank, world)
+    else:  # weak scaling: every rank owns 25 iterations of a 25 N iteration fit
+        total_iters = N_ITERS * world
+        it0, it1 = rank * N_ITERS, (rank + 1) * N_ITERS
     omega, n_power_iter = _pca_plan(n_aug, n_genes, N_COMPONENTS, SEED)
     fit_kw = dict(pseudocount=PSEUDOCOUNT, standard_scaling=False, n_comp=N_COMPONENTS, n_power_iter=n_power_iter,
                   knn_k=10, resolution=4.0, seed=SEED, n_host_threads=host_threads, iter_begin=it0, iter_end=it1)
@@ -399,7 +424,7 @@ def run_ours(args, wl, counts):
     report = h.kernel_timing_report()
     launches = sum_over_ranks(h.kernel_launches() - launches0)
     h.set_kernel_timing(False)
-    cells_per_step = N_ITERS * n_aug * world
+    cells_per_step = total_iters * n_aug  # whole job: every rank's iterations
     value = args.steps * cells_per_step / dt
 
     nnz_par = float(np.diff(counts.indptr)[step_parents[0][it0]].sum()) if n_synth else 0.0
@@ -447,19 +472,22 @@ def run_ours(args, wl, counts):
     barrier()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = args.steps * cells_per_step / dt_e2e
-    h2d = (counts.indptr.nbytes + counts.indices.nbytes + counts.data.nbytes + omega.nbytes + N_ITERS * n_synth * 2 * 8)
-    # per iteration: the pattern graph (offsets, first-level communities, adjacency upper bound) + PCA flag
-    d2h = N_ITERS * (((n_aug + 1) + n_aug + n_aug * 18) * 4 + 8) + n_cells * 4
+    my_iters = it1 - it0
+    h2d = (counts.indptr.nbytes + counts.indices.nbytes + counts.data.nbytes + omega.nbytes + my_iters * n_synth * 2 * 8)
+    # per iteration: the pattern graph (offsets, first-level communities, adjacency upper bound) + PCA flag; N > 1:
+    # predict() all-reduces three N-vectors (votes, valid counts, log-p sums) instead of gathering the (n_iters, N) arrays
+    d2h = my_iters * (((n_aug + 1) + n_aug + n_aug * 18) * 4 + 8) + n_cells * 4 + (3 * 8 * n_cells if world > 1 else 0)
     n_doublets = int(np.nansum(labels))
 
     line = {
         "metric": "augmented-cells/sec through BoostClassifier.fit (n_iters=25)",
         "value": value, "unit": "augmented-cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: {wl['desc']}, boost_rate=0.25, n_iters=25, {args.clustering} (BASELINE.json configs)",
-            "step": "one 25-iteration fit loop per GPU over the resident count matrix",
+            "workload": workload_string(args, wl),
+            "step": (f"one {STRONG_ITERS}-iteration fit, {STRONG_ITERS}/N iterations per GPU (BASELINE configs[3])" if strong
+                     else "one 25-iteration fit loop per GPU over the resident count matrix"),
             "cells": n_cells, "genes": n_genes, "synthetics": n_synth, "nnz": int(counts.nnz),
             "host_threads_per_rank": host_threads, "parallelism": f"iteration-shard x{world}",
             "l2": "dense matrix per iteration (%.2f GB) exceeds the 126 MB L2" % (n_aug * n_genes * 4 / 1e9),
@@ -483,9 +511,10 @@ def run_ours(args, wl, counts):
         state = cpu_state(counts)
         t0 = time.perf_counter()
         cells, n_cpu_iters = 0, 0
-        while n_cpu_iters < N_ITERS and (n_cpu_iters == 0 or time.perf_counter() - t0 < 10.0):  # a bounded sample: >= 10 s
-            cells += cpu_one_iteration(state)
-            n_cpu_iters += 1
+        with all_host_threads():
+            while n_cpu_iters < N_ITERS and (n_cpu_iters == 0 or time.perf_counter() - t0 < 10.0):  # a bounded sample: >= 10 s
+                cells += cpu_one_iteration(state)
+                n_cpu_iters += 1
         dt_cpu = time.perf_counter() - t0
         line["cpu_baseline"] = {
             "value": cells / dt_cpu, "unit": "augmented-cells/s", "cores": cpu_cores(), "kind": "port",
@@ -634,6 +663,9 @@ def main():
                     help="iters: every rank runs its own 25 iterations (weak scaling, the contract's line); "
                          "cells: one fit, the cells of every iteration sharded over the ranks (config 5)")
     ap.add_argument("--iters", type=int, default=N_ITERS, help="iterations per fit for --shard cells")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (the contract's line): every GPU runs its own 25 iterations; strong: BASELINE configs[3], ONE "
+                         "24-iteration fit whose iterations are dealt to the GPUs (3 per GPU at N = 8)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:

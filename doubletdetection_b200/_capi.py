@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -72,6 +72,8 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_f32p, c_f32p, c_f64p],
     ),
+    "dd_centered_gram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_f64p]),
+    "dd_project": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_f64p, c_f32p]),
     "dd_upload_embedding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p]),
     "dd_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_f32p]),
     "dd_knn_listed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p]),
@@ -420,6 +422,22 @@ class Handle:
                                      _ptr(emb, ctypes.c_float), _ptr(sv, ctypes.c_double)))
         self._emb_rows = n_rows
         return emb, sv
+
+    def centered_gram(self, transposed=False):
+        """Float64 Gram matrix of the centred dense matrix: G x G (default) or A x A (transposed)."""
+        n = (self._dense_rows if transposed else self.n_genes)
+        out = np.empty((n, n), dtype=np.float64)
+        self._check(self._lib.dd_centered_gram(self._h, int(bool(transposed)), _ptr(out, ctypes.c_double)))
+        return out
+
+    def project(self, components):
+        """X_pca = (D - mean) V for float64 components V (G x n_comp); the embedding stays on the device for knn()."""
+        v = np.ascontiguousarray(components, dtype=np.float64)
+        n_comp = v.shape[1]
+        emb = np.empty((self._dense_rows, n_comp), dtype=np.float32)
+        self._check(self._lib.dd_project(self._h, n_comp, _ptr(v, ctypes.c_double), _ptr(emb, ctypes.c_float)))
+        self._emb_rows = self._dense_rows
+        return emb
 
     def upload_embedding(self, emb):
         emb = _f32(emb)

@@ -51,16 +51,42 @@ def _pca_plan(n_samples, n_features, n_components, random_state):
     C < 0.1 * min(shape) else 4."""
     solver = _pca_solver(n_samples, n_features, n_components)
     if solver != "randomized":
-        raise NotImplementedError(
-            f"sklearn's PCA(svd_solver='auto') picks '{solver}' for a {n_samples} x {n_features} matrix with "
-            f"n_components={n_components}; only the 'randomized' branch is implemented on the B200 hot path"
-        )
+        return None, 0  # exact PCA (covariance_eigh / full): _exact_pca, no test matrix
     n_power_iter = 7 if n_components < 0.1 * min(n_samples, n_features) else 4
     # fewer samples than features: sklearn works on the transposed matrix, so Omega has one row per SAMPLE
     # (sklearn/utils/extmath.py:589-592: transpose = n_samples < n_features)
     rows = n_samples if n_samples < n_features else n_features
     omega = np.random.RandomState(random_state).normal(size=(rows, n_components + 10)).astype(np.float32)
     return omega, n_power_iter
+
+
+def _exact_pca(h, n_components):
+    """sklearn's exact branches (``covariance_eigh``: <= 1000 genes and >= 10x as many augmented cells; ``full``: tiny
+    matrices or n_components >= 0.8 min(shape); sklearn/decomposition/_pca.py:524-536, 560-640) on the dense matrix the
+    handle holds: X_pca = top principal components of the centred matrix, signs by ``svd_flip(u_based_decision=False)``.
+    The device computes the float64 Gram matrix of the centred matrix on its smaller side and the projection of all
+    augmented cells; the <= 1000 x 1000 symmetric eigenproblem in between is LAPACK on the host (O(G^3), independent of
+    the number of cells -- the same routine sklearn calls).  Leaves the embedding on the device for ``knn``."""
+    n_rows, n_genes = h._dense_rows, h.n_genes
+    c = int(n_components)
+    if n_genes <= n_rows:
+        w, v = np.linalg.eigh(h.centered_gram(False))  # ascending eigenvalues of (A - 1) * covariance
+        v = np.ascontiguousarray(v[:, ::-1][:, :c])
+        top = np.argmax(np.abs(v), axis=0)
+        v *= np.sign(v[top, np.arange(v.shape[1])])[None, :]
+        return h.project(v)
+    # fewer augmented cells than genes (only reachable with <= 500 rows or n_components >= 0.8 A): eigenvectors of the
+    # A x A Gram matrix are U, X_pca = U S; the sign convention needs Vt = S^-1 U^T Dc, a (c x G) product on a tiny matrix
+    w, u = np.linalg.eigh(h.centered_gram(True))
+    u, w = u[:, ::-1][:, :c], np.maximum(w[::-1][:c], 0.0)
+    s = np.sqrt(w)
+    dense = h.download_dense().astype(np.float64)
+    dense -= dense.mean(axis=0)
+    vt = (u.T @ dense) / np.where(s > 0, s, 1.0)[:, None]
+    signs = np.sign(vt[np.arange(vt.shape[0]), np.argmax(np.abs(vt), axis=1)])
+    emb = np.ascontiguousarray(u * (s * signs)[None, :], dtype=np.float32)
+    h.upload_embedding(emb)
+    return emb
 
 
 class BoostClassifier:
@@ -132,6 +158,8 @@ class BoostClassifier:
         self._parents_array = None
         self._parents_lists = None
         self.stage_ms_ = None
+        self._fitted = {}     # all_scores_ / all_log_p_values_ / communities_ / synth_communities_ once they are complete
+        self._pending = None  # iteration-sharded fit whose per-iteration rows have not been collected yet
 
     # ------------------------------------------------------------------ kwargs (:404-426)
     def _set_clustering_kwargs(self):
@@ -167,6 +195,66 @@ class BoostClassifier:
     @parents_.setter
     def parents_(self, value):
         self._parents_lists = value
+
+    # ------------------------------------------------------------------ fitted (n_iters, .) arrays (:186-214)
+    # Plain arrays after a single-process fit.  After an ITERATION-SHARDED fit (distributed=True / "allgather") every rank
+    # holds the rows of its own iterations only: predict() and doublet_score() need per-cell sums over the iterations, so
+    # they all-reduce three N-vectors (votes, valid counts, log-p sums) instead of moving the (n_iters x N) arrays; the
+    # arrays themselves are gathered on first access (a collective: every rank must touch them, or none).
+    def _collect(self):
+        if self._pending is None:
+            return
+        pend, self._pending = self._pending, None
+        merged = _allgather_iterations(pend["dist"], pend["out"], self.n_iters, self.device,
+                                       everywhere=self.distributed == "allgather")
+        self._store(merged)
+
+    def _store(self, out):
+        self._fitted = dict(
+            all_scores_=out["scores"], all_log_p_values_=out["log_p"],
+            communities_=out["communities"].astype(np.float64),  # the reference stores them in float arrays (:188)
+            synth_communities_=out["synth_communities"].astype(np.float64))
+
+    def _get_fitted(self, name):
+        self._collect()
+        try:
+            return self._fitted[name]
+        except KeyError:
+            raise AttributeError(f"{name} is set by fit()") from None
+
+    all_scores_ = property(lambda self: self._get_fitted("all_scores_"),
+                           lambda self, v: self._fitted.__setitem__("all_scores_", v))
+    all_log_p_values_ = property(lambda self: self._get_fitted("all_log_p_values_"),
+                                 lambda self, v: self._fitted.__setitem__("all_log_p_values_", v))
+    communities_ = property(lambda self: self._get_fitted("communities_"),
+                            lambda self, v: self._fitted.__setitem__("communities_", v))
+    synth_communities_ = property(lambda self: self._get_fitted("synth_communities_"),
+                                  lambda self, v: self._fitted.__setitem__("synth_communities_", v))
+
+    def _reduced_log_p_stats(self, log_p_thresh):
+        """(votes, valid count, sum of valid log p) per cell over ALL iterations.  Pending sharded fit: from this rank's
+        rows, summed over the ranks (integers exactly; the float64 sums in rank order instead of iteration order)."""
+        if self._pending is None:
+            log_p = np.asarray(self.all_log_p_values_)
+        else:
+            log_p = np.asarray(self._pending["out"]["log_p"])[self._pending["it0"]:self._pending["it1"]]
+        valid = np.isfinite(log_p)  # masked_invalid masks NaN, +inf and -inf (quirk Q5)
+        with np.errstate(invalid="ignore"):
+            votes = np.count_nonzero((log_p <= log_p_thresh) & valid, axis=0) if log_p_thresh is not None else None
+        count = np.count_nonzero(valid, axis=0)
+        total = np.where(valid, log_p, 0.0).sum(axis=0)
+        if self._pending is not None:
+            import torch
+
+            dist = self._pending["dist"]
+            dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            ints = np.stack([votes if votes is not None else np.zeros_like(count), count]).astype(np.int64)
+            t_i, t_f = torch.from_numpy(ints).to(dev), torch.from_numpy(np.ascontiguousarray(total)).to(dev)
+            dist.all_reduce(t_i, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_f, op=dist.ReduceOp.SUM)
+            ints, total = t_i.cpu().numpy(), t_f.cpu().numpy()
+            votes, count = (ints[0] if votes is not None else None), ints[1]
+        return votes, count, total
 
     # ------------------------------------------------------------------ fit (:135-214)
     def _native(self):
@@ -276,23 +364,29 @@ class BoostClassifier:
 
         if self.verbose:
             print(f"Running iterations {it0 + 1}..{it1} of {self.n_iters} on cuda:{self.device}")
-        out = h.fit_iterations(
-            parents, omega,
-            pseudocount=self.pseudocount, standard_scaling=self.standard_scaling is True,
-            n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10, seed=int(self.random_state),
-            n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1, **cluster_kw,
-        )
+        if omega is None:
+            if cells_dist is not None:
+                raise NotImplementedError("distributed='cells' with sklearn's exact PCA branches (<= 1000 genes or a tiny matrix)")
+            out = self._fit_iterations_exact_pca(h, parents, it0, it1, cluster_kw)
+        else:
+            out = h.fit_iterations(
+                parents, omega,
+                pseudocount=self.pseudocount, standard_scaling=self.standard_scaling is True,
+                n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10, seed=int(self.random_state),
+                n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1, **cluster_kw,
+            )
         _t.append(_time.perf_counter())
-        if dist is not None:
-            out = _allgather_iterations(dist, out, self.n_iters, self.device, everywhere=self.distributed == "allgather")
+        self._pending, self._fitted = None, {}
         if cells_dist is not None:
             out = merge_owned_iterations(cells_dist, out, self.device)
         self.stage_ms_ = out["stage_ms"]
-
-        self.all_scores_ = out["scores"]
-        self.all_log_p_values_ = out["log_p"]
-        self.communities_ = out["communities"].astype(np.float64)  # the reference stores them in float arrays (:188)
-        self.synth_communities_ = out["synth_communities"].astype(np.float64)
+        if dist is not None and self.n_iters > 1:
+            # iteration-sharded: the (n_iters, .) rows stay where they were computed until somebody asks for them
+            self._pending = dict(dist=dist, out=out, it0=it0, it1=it1)
+        elif dist is not None:
+            self._store(_allgather_iterations(dist, out, self.n_iters, self.device, everywhere=self.distributed == "allgather"))
+        else:
+            self._store(out)
         self._parents_array = parents
         self._parents_lists = None
         _t.append(_time.perf_counter())
@@ -302,6 +396,43 @@ class BoostClassifier:
                                  [1e3 * (b - a) for a, b in zip(_t[:-1], _t[1:])]))
         return self
 
+    def _fit_iterations_exact_pca(self, h, parents, it0, it1, cluster_kw):
+        """``_one_fit`` (:274-383) iteration by iteration for the shapes where sklearn's "auto" PCA is EXACT (see
+        ``_exact_pca``): same device stages as the pipelined loop (fused doublets + normalise/log, optional scaling, exact
+        kNN), the exact PCA in place of the randomized one, and the native host twins of the clustering stage."""
+        import time as _time
+
+        n_cells = self._num_cells
+        n_synth = parents.shape[1]
+        scores = np.zeros((self.n_iters, n_cells))
+        log_p = np.zeros((self.n_iters, n_cells))
+        comm = np.zeros((self.n_iters, n_cells), dtype=np.int32)
+        synth_comm = np.zeros((self.n_iters, n_synth), dtype=np.int32)
+        algo = cluster_kw["clustering"]
+        seed = int(self.random_state)
+        t0 = _time.perf_counter()
+        for i in range(it0, it1):
+            h.create_doublets(parents[i])
+            h.normalise_log(h.median_lib_size(), self.pseudocount)
+            if self.standard_scaling is True:
+                h.standard_scale(15.0)
+            _exact_pca(h, self.n_components)
+            if algo == "phenograph":
+                idx, _ = h.knn(cluster_kw["pheno_k"] + 1, with_dist=False)
+                labels = _capi.phenograph_knn(idx, prune=cluster_kw["pheno_prune"],
+                                              min_cluster_size=cluster_kw["pheno_min_cluster_size"], seed=seed)
+            elif algo == "leiden":
+                idx, dist = h.knn(10)
+                labels = _capi.leiden_knn(idx, dist, resolution=cluster_kw["resolution"], seed=seed)
+            else:
+                idx, _ = h.knn(10, with_dist=False)
+                labels = _capi.louvain_knn(idx, resolution=cluster_kw["resolution"], seed=seed)
+            scores[i], log_p[i] = _capi.score(labels, n_cells)
+            comm[i], synth_comm[i] = labels[:n_cells], labels[n_cells:]
+        wall = 1e3 * (_time.perf_counter() - t0)
+        return dict(scores=scores, log_p=log_p, communities=comm, synth_communities=synth_comm,
+                    stage_ms=dict(wall=wall, device_total=wall))
+
     # ------------------------------------------------------------------ predict (:216-254)
     def predict(self, p_thresh=1e-7, voter_thresh=0.9):
         log_p_thresh = np.log(p_thresh)
@@ -309,11 +440,8 @@ class BoostClassifier:
             # :232-241 -- np.mean(np.ma.masked_invalid(log_p) <= thresh, axis=0), the vote >= voter_thresh, both filled
             # with NaN where every iteration is masked.  Same values without the masked-array machinery (42 -> 6 ms at
             # 25 x 100k): a masked mean is (number of valid votes) * 1.0 / (number of valid entries) in float64.
-            log_p = np.asarray(self.all_log_p_values_)
-            valid = np.isfinite(log_p)  # masked_invalid masks NaN, +inf and -inf (quirk Q5)
+            votes, count, _ = self._reduced_log_p_stats(log_p_thresh)
             with np.errstate(invalid="ignore", divide="ignore"):
-                votes = np.count_nonzero((log_p <= log_p_thresh) & valid, axis=0)
-                count = np.count_nonzero(valid, axis=0)
                 average = votes * 1.0 / count
                 labels = (average >= voter_thresh).astype(float)
             none_valid = count == 0
@@ -338,11 +466,9 @@ class BoostClassifier:
         if self.n_iters > 1:
             # :268 -- np.mean(np.ma.masked_invalid(log_p), axis=0): a MaskedArray (quirk Q5) whose values are
             # filled(0).sum(axis=0) * 1.0 / count, masked where no iteration is valid; built directly
-            log_p = np.asarray(self.all_log_p_values_)
-            valid = np.isfinite(log_p)
-            count = np.count_nonzero(valid, axis=0)
+            _, count, total = self._reduced_log_p_stats(None)
             with np.errstate(invalid="ignore", divide="ignore"):
-                avg = np.where(valid, log_p, 0.0).sum(axis=0) * 1.0 / count
+                avg = total * 1.0 / count
             none_valid = count == 0
             avg[none_valid] = 0.0
             avg_log_p = np.ma.MaskedArray(avg, mask=none_valid if none_valid.any() else np.ma.nomask)

@@ -12,7 +12,7 @@
 
 #include "../../include/dd_b200.h"
 
-#define DD_ABI_VERSION 4
+#define DD_ABI_VERSION 5
 
 // padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
 static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -35,6 +35,9 @@ struct dd_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // clustering (first Louvain level + result copies) overlaps the next iteration
     cudaStream_t stream3 = nullptr;  // dense build of the next iteration, underneath this iteration's PCA tail and kNN
+    cudaStream_t stream4 = nullptr;  // kNN of iteration i, concurrent with the PCA of iteration i + 1 (fit loop, unsharded)
+    cudaEvent_t ev_pca_done[2] = {nullptr, nullptr};  // per embedding buffer: the PCA has written it
+    cudaEvent_t ev_emb_free[2] = {nullptr, nullptr};  // per embedding buffer: the kNN that read it has finished
     cudaEvent_t ev_dense_done = nullptr, ev_gemms_done = nullptr;
     bool gemms_done_recorded = false;  // run_pca recorded ev_gemms_done right after its last pass over the matrix
     cudaEvent_t ev_knn_done = nullptr, ev_lv_done = nullptr, ev_lv_done2 = nullptr;  // lv_done per kNN list buffer
@@ -89,7 +92,9 @@ struct dd_handle {
     float *d_mu = nullptr;  // float32 column means of the dense matrix (ld entries, 0 in the pad columns)
     int64_t cap_mu = 0;
     dd_tc_state *tc = nullptr;
-    float *d_emb = nullptr;    // A x KP embedding (KP = 32 or 64, zero padded)
+    float *d_emb = nullptr;    // A x KP embedding (KP = 32 or 64, zero padded): the buffer in use, d_emb_base + {0, emb_stride}
+    float *d_emb_base = nullptr;  // two buffers: the kNN of iteration i reads one while the PCA of i + 1 writes the other
+    int64_t emb_stride = 0;
     int32_t KP = 0;
     int64_t emb_rows = 0;
     bool emb_valid = false;
@@ -122,6 +127,7 @@ struct dd_handle {
     int64_t lv_bucket_n = -1;
     uint64_t lv_bucket_seed = 0;
     std::vector<int32_t> lv_colour_off;
+    int32_t *h_lv_rounds = nullptr;  // pinned: rounds the last first level ran (reported as stage "lv_rounds")
     void *lv_graph_exec = nullptr;  // cudaGraphExec_t of the captured round sequence
     int64_t lv_graph_n = -1, lv_graph_launches = 0;
     double lv_graph_gamma = 0.0;
@@ -226,6 +232,7 @@ int dd_dev_standard_scale(dd_handle *h, float max_value);           // scale.cu
 int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter,
                const float *omega_host);                            // pca.cu
 int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
+int dd_emb_reserve(dd_handle *h, int64_t rows, int32_t KP);         // pca.cu: (re)allocate the two embedding buffers
 int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed);  // louvain_gpu.cu
 int dd_dev_jaccard_graph(dd_handle *h, int32_t k, int prune);                      // louvain_gpu.cu (PhenoGraph)
 

@@ -215,6 +215,16 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         return r;
     };
     rc = issue_dense(p->iter_begin, &evs[0], false);
+    // Four streams (unsharded): main = scale + PCA, build = dense matrix of the next iteration, kNN = the neighbour search of
+    // iteration i CONCURRENT with the PCA of iteration i + 1 (the kNN is bound by the TMEM read path and leaves HBM idle,
+    // the PCA products are HBM-bound and its ~2 ms of small float64 kernels leave the SMs idle), clustering = graph + first
+    // Louvain level of iteration i.  The embedding and the kNN lists are double-buffered.  Cell-block sharding keeps the kNN
+    // on the main stream: both stages enqueue NCCL collectives on the same communicator, whose order must be the same on
+    // every rank.
+    static const bool knn_inline = getenv("DD_KNN_INLINE") != nullptr;  // A/B: the round-1 order (kNN on the main stream)
+    const bool knn_own_stream = !dd_sharded(h) && !knn_inline;
+    cudaStream_t const main_stream = h->stream;
+    cudaStream_t const knn_stream = knn_own_stream ? h->stream4 : h->stream;
     for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && worker_rc.load() == DD_OK; it++, issued++) {
         // Cell-block sharding: every rank holds the all-gathered kNN lists of every iteration, so the clustering + scoring
         // of the iterations is dealt round-robin to the ranks (rank it % world finishes iteration it; the caller merges the
@@ -227,55 +237,74 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             slot = free_slots.front();
             free_slots.pop_front();
         }
+        const int eb = issued & 1;  // embedding / list buffer of this iteration
         cudaEvent_t *ev = &evs[(size_t)issued * kStages];
         cudaStreamWaitEvent(h->stream, h->ev_dense_done, 0);
         cudaEventRecord(ev[6], h->stream);
         if (p->standard_scaling && (rc = dd_dev_standard_scale(h, p->scale_max_value)) != DD_OK) break;
         cudaEventRecord(ev[2], h->stream);
         h->gemms_done_recorded = false;
+        // this PCA overwrites the embedding buffer the kNN of two iterations ago read
+        if (knn_own_stream && issued > 1) cudaStreamWaitEvent(h->stream, h->ev_emb_free[eb], 0);
+        if (h->d_emb_base) h->d_emb = h->d_emb_base + eb * h->emb_stride;
         if ((rc = dd_dev_pca(h, p->n_comp, p->n_random, p->n_power_iter, omega_sent ? nullptr : omega)) != DD_OK) break;
+        if (h->d_emb != h->d_emb_base + eb * h->emb_stride) {  // the first call allocated the buffers (and wrote buffer 0)
+            if (eb != 0) { rc = dd_fail(h, DD_ERR_CUDA, "dd_fit_iterations: embedding buffers re-allocated mid-fit"); break; }
+        }
         if (!h->gemms_done_recorded) cudaEventRecord(h->ev_gemms_done, h->stream);
         omega_sent = true;
+        if (cluster_here) dd_pca_flag_copy(h, slots[slot].flag);  // before the next PCA resets the flag
         cudaEventRecord(ev[3], h->stream);
-        // The kNN lists are double-buffered: this iteration writes buffer (issued & 1), which the clustering stream
-        // finished reading two iterations ago -- so the kNN never waits for the previous iteration's Louvain level.
-        cudaEvent_t lv_done = (issued & 1) ? h->ev_lv_done2 : h->ev_lv_done;
-        if (issued > 1) cudaStreamWaitEvent(h->stream, lv_done, 0);
-        if (h->d_knn_idx_base) h->d_knn_idx = h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride;
-        if ((rc = dd_dev_knn(h, k)) != DD_OK) break;
-        if (h->d_knn_idx != h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride)  // first call allocated the buffers
-            h->d_knn_idx = h->d_knn_idx_base + (issued & 1) * h->knn_idx_stride;
-        cudaEventRecord(ev[4], h->stream);
+        cudaEventRecord(h->ev_pca_done[eb], h->stream);
+        // the dense build of the next iteration goes out now (build stream; it waits for this PCA's last pass over the matrix)
+        if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
+
+        // ---- kNN (own stream).  The lists are double-buffered too: this iteration writes buffer eb, which the clustering
+        // stream finished reading two iterations ago -- so the kNN never waits for the previous iteration's Louvain level.
+        h->stream = knn_stream;
+        if (knn_own_stream) cudaStreamWaitEvent(knn_stream, h->ev_pca_done[eb], 0);
+        cudaEvent_t lv_done = eb ? h->ev_lv_done2 : h->ev_lv_done;
+        if (issued > 1) cudaStreamWaitEvent(knn_stream, lv_done, 0);
+        if (h->d_knn_idx_base) h->d_knn_idx = h->d_knn_idx_base + eb * h->knn_idx_stride;
+        h->emb_valid = true;  // issuing the next dense build (new parents) marked this iteration's embedding stale
+        rc = dd_dev_knn(h, k);
+        if (rc == DD_OK && h->d_knn_idx != h->d_knn_idx_base + eb * h->knn_idx_stride)  // first call allocated the buffers
+            h->d_knn_idx = h->d_knn_idx_base + eb * h->knn_idx_stride;
+        cudaEventRecord(ev[4], knn_stream);
+        if (rc == DD_OK && leiden && cluster_here) {
+            // no device clustering stage: the lists and their distances leave on the kNN stream (the distance buffer is
+            // not double-buffered, and the next kNN is ordered behind these copies on the same stream)
+            Slot &s = slots[slot];
+            cudaMemcpyAsync(s.graph, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, knn_stream);
+            cudaMemcpyAsync(s.graph + A * k, h->d_knn_dist, sizeof(float) * A * k, cudaMemcpyDeviceToHost, knn_stream);
+        }
+        cudaEventRecord(h->ev_emb_free[eb], knn_stream);
+        cudaEventRecord(h->ev_knn_done, knn_stream);
+        h->stream = main_stream;
+        if (rc != DD_OK) break;
         if (!cluster_here) {
-            cudaEventRecord(ev[5], h->stream);
-            if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
+            cudaEventRecord(ev[5], knn_stream);
             continue;
         }
         Slot &s = slots[slot];
-        dd_pca_flag_copy(h, s.flag);
         if (leiden) {
-            // no device clustering stage: the lists and their distances leave on the main stream (the distance buffer is
-            // not double-buffered, and the next kNN is ordered behind these copies on the same stream)
-            cudaMemcpyAsync(s.graph, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, h->stream);
-            cudaMemcpyAsync(s.graph + A * k, h->d_knn_dist, sizeof(float) * A * k, cudaMemcpyDeviceToHost, h->stream);
-            cudaEventRecord(ev[5], h->stream);
-            cudaEventRecord(lv_done, h->stream);
-            cudaEventRecord(s.done, h->stream);
+            cudaEventRecord(ev[5], knn_stream);
+            cudaEventRecord(lv_done, knn_stream);
+            cudaStreamWaitEvent(knn_stream, h->ev_pca_done[eb], 0);  // s.done also covers the flag copy on the main stream
+            cudaEventRecord(s.done, knn_stream);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 jobs.push_back(Job{it, slot});
             }
             cv_job.notify_one();
-            if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
             continue;
         }
         // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device.
-        // These are hundreds of small latency-bound kernels: they run on a second stream and overlap the
+        // These are hundreds of small latency-bound kernels: they run on their own stream and overlap the
         // HBM-bound dense build / PCA of the NEXT iteration.
-        cudaEventRecord(h->ev_knn_done, h->stream);
         cudaStreamWaitEvent(h->stream2, h->ev_knn_done, 0);
+        cudaStreamWaitEvent(h->stream2, h->ev_pca_done[eb], 0);  // s.done must also cover the flag copy (main stream)
         {
-            cudaStream_t main_stream = h->stream;
             h->stream = h->stream2;
             rc = pheno ? dd_dev_jaccard_graph(h, k, p->pheno_prune) : dd_dev_louvain_level0(h, k, p->resolution, p->seed);
             if (rc == DD_OK && pheno && pheno_level0) rc = dd_dev_louvain_level0_weighted(h, 1.0, p->seed);
@@ -295,8 +324,8 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             jobs.push_back(Job{it, slot});
         }
         cv_job.notify_one();
-        if (it + 1 < p->iter_end && (rc = issue_dense(it + 1, &evs[(size_t)(issued + 1) * kStages], true)) != DD_OK) break;
     }
+    h->stream = main_stream;
     {
         std::lock_guard<std::mutex> lk(mu);
         closing = true;
@@ -306,8 +335,10 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     cudaError_t ce = cudaStreamSynchronize(h->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream2);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream3);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream4);
     if (rc == DD_OK && ce != cudaSuccess) rc = dd_fail(h, DD_ERR_CUDA, std::string("dd_fit_iterations: ") + cudaGetErrorString(ce));
     if (rc == DD_OK && worker_rc.load() != DD_OK) rc = dd_fail(h, worker_rc.load(), worker_err);
+    if (rc == DD_OK && h->h_lv_rounds && !pheno && !leiden) h->stage_ms["lv_rounds"] = (double)*h->h_lv_rounds;
     if (rc == DD_OK && stage_ms_out) {
         for (int i = 0; i < issued; i++) {
             cudaEvent_t *ev = &evs[(size_t)i * kStages];

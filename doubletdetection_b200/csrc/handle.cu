@@ -108,6 +108,11 @@ extern "C" int dd_create(int device, dd_handle **out) {
     if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_pca_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_pca_done[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_emb_free[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_emb_free[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_dense_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_gemms_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_knn_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -127,9 +132,11 @@ extern "C" void dd_destroy(dd_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->stream3) cudaStreamSynchronize(h->stream3);
+    if (h->stream4) cudaStreamSynchronize(h->stream4);
     void *bufs[] = {h->d_indptr, h->d_indices, h->d_data,   h->d_lib,   h->d_l1,      h->d_parents, h->d_sindptr,
                     h->d_scount, h->d_sindices, h->d_sdata, h->d_slib,  h->d_dense,   h->d_colsum,  h->d_colsumsq,
-                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb,     h->d_knn_idx_base, h->d_knn_dist, h->d_knn_ops, h->d_knn_list_off, h->d_knn_list_tiles, h->d_lvw_wq, h->d_lvw_i64, h->d_lvw_i32, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w};
+                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb_base, h->d_knn_idx_base, h->d_knn_dist, h->d_knn_ops, h->d_knn_list_off, h->d_knn_list_tiles, h->d_lvw_wq, h->d_lvw_i64, h->d_lvw_i32, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w};
     for (void *p : bufs)
         if (p) cudaFree(p);
     dd_tc_free(h);
@@ -137,6 +144,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (h->lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lv_graph_exec);
     for (int32_t *p : h->slot_knn) cudaFreeHost(p);
     for (double *p : h->slot_flag) cudaFreeHost(p);
+    if (h->h_lv_rounds) cudaFreeHost(h->h_lv_rounds);
     resolve_pending(h);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -148,6 +156,11 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (h->ev_lv_done2) cudaEventDestroy(h->ev_lv_done2);
     if (h->ev_dense_done) cudaEventDestroy(h->ev_dense_done);
     if (h->ev_gemms_done) cudaEventDestroy(h->ev_gemms_done);
+    for (int b = 0; b < 2; b++) {
+        if (h->ev_pca_done[b]) cudaEventDestroy(h->ev_pca_done[b]);
+        if (h->ev_emb_free[b]) cudaEventDestroy(h->ev_emb_free[b]);
+    }
+    if (h->stream4) cudaStreamDestroy(h->stream4);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -49,36 +49,94 @@ __global__ void k_graph_count(const int32_t *__restrict__ knn, int n, int k, int
     atomicAdd(deg + i, out);
 }
 
-// single CTA: exclusive scan of deg -> off[0..n], state reset
-__global__ void k_graph_scan(const int32_t *__restrict__ deg, int n, int32_t *__restrict__ off,
-                             int32_t *__restrict__ counters) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x, nt = blockDim.x;
-    const int per = (n + nt - 1) / nt;
-    const int b = min(t * per, n), e = min(b + per, n);
-    long long s = 0;
-    for (int i = b; i < e; i++) s += deg[i];
-    part[t] = s;
+// Exclusive scan of deg -> off[0..n] in three small launches (the single-CTA version it replaces took 0.7-1.3 ms at 125 k
+// nodes, on the clustering stream's critical path): chunks of kScanChunk elements scanned by one CTA each, the chunk totals
+// scanned by one CTA (which also resets the level's counters), the chunk bases added back.
+constexpr int kScanChunk = 4096;  // 1024 threads x 4 elements
+__global__ void __launch_bounds__(1024) k_graph_scan_local(const int32_t *__restrict__ deg, int n, int32_t *__restrict__ off,
+                                                           int32_t *__restrict__ part) {
+    __shared__ int s_warp[32];
+    const int t = threadIdx.x, lane = t & 31, wl = t >> 5;
+    const int base = blockIdx.x * kScanChunk + t * 4;
+    int v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) v[e] = base + e < n ? deg[base + e] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[wl] = incl;
     __syncthreads();
-    if (t == 0) {
-        long long run = 0;
-        for (int i = 0; i < nt; i++) {
-            const long long v = part[i];
-            part[i] = run;
-            run += v;
+    if (wl == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
         }
-        off[n] = (int32_t)run;
+        s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - mine + (wl > 0 ? s_warp[wl - 1] : 0);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        if (base + e < n) off[base + e] = run;
+        run += v[e];
+    }
+    if (t == 1023) part[blockIdx.x] = run;  // chunk total
+}
+
+__global__ void __launch_bounds__(1024) k_graph_scan_parts(int32_t *__restrict__ part, int n_parts, int n,
+                                                           int32_t *__restrict__ off, int32_t *__restrict__ counters) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int t = threadIdx.x, lane = t & 31, wl = t >> 5;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < n_parts; p0 += 1024) {
+        const int mine = p0 + t < n_parts ? part[p0 + t] : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[wl] = incl;
+        __syncthreads();
+        if (wl == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (p0 + t < n_parts) part[p0 + t] = carry + incl - mine + (wl > 0 ? s_warp[wl - 1] : 0);  // exclusive chunk base
+        __syncthreads();
+        if (t == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (t == 0) {
+        off[n] = s_carry;
         counters[0] = 0;  // moved in this round
         counters[1] = 0;  // done flag
         counters[2] = 0;  // rounds executed
         counters[3] = 0;  // grid barrier arrivals (cooperative kernel)
     }
-    __syncthreads();
-    long long run = part[t];
-    for (int i = b; i < e; i++) {
-        off[i] = (int32_t)run;
-        run += deg[i];
-    }
+}
+
+__global__ void __launch_bounds__(1024) k_graph_scan_add(const int32_t *__restrict__ part, int n, int32_t *__restrict__ off) {
+    const int base = blockIdx.x * kScanChunk + threadIdx.x * 4;
+    const int add = part[blockIdx.x];
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+        if (base + e < n) off[base + e] += add;
 }
 
 // adjacency rows: the node's own out-neighbours first, then the in-neighbours that are not out-neighbours
@@ -219,6 +277,105 @@ __global__ void __launch_bounds__(256) k_lv_propose(const int32_t *__restrict__ 
     if (lane == 0) desired[i] = res;
 }
 
+// EIGHT LANES per node of the current colour, four nodes per warp (the default).  The warp-per-node kernel above spends 32
+// threads on the ~15 neighbours of a kNN-graph node: a colour class of 15.6 k nodes (c3) is 1950 CTAs, and next to the main
+// stream's kernels (a 173 KB kNN CTA leaves room for two of them per SM) that is ~7 waves per step, 500 steps per level --
+// the level took 11.5 ms per iteration overlapped against 3 ms alone and was the critical path of the fit loop.  (One
+// THREAD per node was measured too: a single partial wave, but the serial per-thread work made a step slower, 15 ms.)
+// Here a lane holds up to four neighbour communities in registers, multiplicities come from 32 group-wide shuffles, the
+// community totals are fetched with independent loads; the class is 488 CTAs = under two waves of the same short latency
+// chain.  Nodes with more than 32 neighbours (hubs of the in-degree tail) are handed to the whole warp afterwards
+// (propose_one).  Same arithmetic and tie-breaking as propose_one: identical results.
+constexpr int kGroupLanes = 8, kPerLane = 4, kPropWarps = 4, kNodesPerCta = kPropWarps * (32 / kGroupLanes);
+__global__ void __launch_bounds__(kPropWarps * 32, 10) k_lv_propose_g(const int32_t *__restrict__ off, const int32_t *__restrict__ adj,
+                                                      const int32_t *__restrict__ comm, const double *__restrict__ tot,
+                                                      const int32_t *__restrict__ csize,
+                                                      const int32_t *__restrict__ bucket, int b0, int b1, int n,
+                                                      double gamma, int32_t *__restrict__ desired,
+                                                      const int32_t *__restrict__ counters) {
+    __shared__ int32_t s_tab[kPropWarps * 2 * kTable];
+    if (counters[1]) return;  // converged in an earlier round
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int gl = lane & (kGroupLanes - 1), grp = lane / kGroupLanes;
+    const unsigned gmask = ((1u << kGroupLanes) - 1u) << (grp * kGroupLanes);
+    const int t = (blockIdx.x * kPropWarps + wl) * (32 / kGroupLanes) + grp;
+    const double two_m = (double)off[n];
+    int i = -1, s = 0, d = 0;
+    if (b0 + t < b1) {
+        i = bucket[b0 + t];
+        s = off[i];
+        d = off[i + 1] - s;
+    }
+    const bool big = d > kGroupLanes * kPerLane;
+    if (i >= 0 && !big) {  // uniform inside the group
+        int res = -1;
+        if (d > 0) {
+            const int ci = __ldcg(comm + i);
+            int a[kPerLane], c[kPerLane];
+#pragma unroll
+            for (int j = 0; j < kPerLane; j++) {
+                const int e = j * kGroupLanes + gl;
+                a[j] = e < d ? adj[s + e] : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < kPerLane; j++) c[j] = a[j] >= 0 ? __ldcg(comm + a[j]) : -1 - (j * kGroupLanes + gl);  // unique sentinels
+            double tt[kPerLane];
+#pragma unroll
+            for (int j = 0; j < kPerLane; j++) tt[j] = (c[j] >= 0 && c[j] != ci) ? __ldcg(tot + c[j]) : 0.0;
+            const double tot_ci = __ldcg(tot + ci);
+            const int cs_ci = __ldcg(csize + ci);
+            int wc[kPerLane] = {0, 0, 0, 0};
+            int w_stay = 0;
+#pragma unroll
+            for (int src = 0; src < kGroupLanes; src++) {
+#pragma unroll
+                for (int jj = 0; jj < kPerLane; jj++) {
+                    const int o = __shfl_sync(gmask, c[jj], grp * kGroupLanes + src);
+#pragma unroll
+                    for (int j = 0; j < kPerLane; j++) wc[j] += (o == c[j]);
+                    w_stay += (o == ci);
+                }
+            }
+            const double ki = (double)d;
+            const double gk = __dmul_rn(gamma, ki);
+            double best_gain = 0.0;
+            int best = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < kPerLane; j++) {
+                if (c[j] < 0 || c[j] == ci) continue;
+                const double gn = __dsub_rn((double)wc[j], __ddiv_rn(__dmul_rn(gk, tt[j]), two_m));
+                if (best == 0x7fffffff || gn > best_gain || (gn == best_gain && c[j] < best)) {
+                    best = c[j];
+                    best_gain = gn;
+                }
+            }
+#pragma unroll
+            for (int o = kGroupLanes / 2; o > 0; o >>= 1) {
+                const double og = __shfl_xor_sync(gmask, best_gain, o);
+                const int ob = __shfl_xor_sync(gmask, best, o);
+                if (ob != 0x7fffffff && (best == 0x7fffffff || og > best_gain || (og == best_gain && ob < best))) {
+                    best = ob;
+                    best_gain = og;
+                }
+            }
+            const double gain_stay = __dsub_rn((double)w_stay, __ddiv_rn(__dmul_rn(gk, __dsub_rn(tot_ci, ki)), two_m));
+            if (best != 0x7fffffff && best_gain > gain_stay && !(cs_ci == 1 && __ldcg(csize + best) == 1 && best > ci))
+                res = best;
+        }
+        if (gl == 0) desired[i] = res;
+    }
+    // hubs: one at a time with the whole warp
+    unsigned bigmask = __ballot_sync(0xffffffffu, big && gl == 0);
+    while (bigmask) {
+        const int src = __ffs(bigmask) - 1;
+        bigmask &= bigmask - 1;
+        const int node = __shfl_sync(0xffffffffu, i, src);
+        const int res = propose_one(off, adj, comm, tot, csize, node, gamma, two_m, s_tab + wl * 2 * kTable,
+                                    s_tab + wl * 2 * kTable + kTable, lane);
+        if (lane == 0) desired[node] = res;
+    }
+}
+
 __global__ void k_lv_apply(const int32_t *__restrict__ off, int32_t *__restrict__ comm, double *__restrict__ tot,
                            int32_t *__restrict__ csize, const int32_t *__restrict__ bucket, int b0, int b1,
                            const int32_t *__restrict__ desired, int32_t *__restrict__ counters) {
@@ -353,8 +510,8 @@ int lv_build_graph(dd_handle *h, int32_t k, LvBuffers &b) {
         DD_CUDA(h, cudaMalloc(&h->d_lv_adj, sizeof(int32_t) * std::max<int64_t>(max_nnz, 1)));
         DD_CUDA(h, cudaMalloc(&h->d_lv_comm, sizeof(int32_t) * n));
         DD_CUDA(h, cudaMalloc(&h->d_lv_tot, sizeof(double) * n));
-        // deg | cursor | csize | desired | bucket (n each) + counters
-        DD_CUDA(h, cudaMalloc(&h->d_lv_i32, sizeof(int32_t) * (5 * (size_t)n + 16)));
+        // deg | cursor | csize | desired | bucket (n each) + counters (8) + scan chunk totals
+        DD_CUDA(h, cudaMalloc(&h->d_lv_i32, sizeof(int32_t) * (5 * (size_t)n + 16 + (size_t)n / kScanChunk + 2)));
         h->cap_lv_n = n; h->cap_lv_nnz = max_nnz;
         h->lv_bucket_n = -1;
         h->lv_graph_n = -1;  // the captured launches hold the old pointers
@@ -365,7 +522,11 @@ int lv_build_graph(dd_handle *h, int32_t k, LvBuffers &b) {
     DD_CUDA(h, cudaMemsetAsync(b.deg, 0, sizeof(int32_t) * 2 * (size_t)h->cap_lv_n, h->stream));  // deg + cursor
     const unsigned nb = (unsigned)((n + 255) / 256);
     DD_LAUNCH(h, "lv_graph_count", k_graph_count, nb, 256, 0, h->d_knn_idx, n, (int)k, b.deg);
-    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan, 1, 1024, 0, b.deg, n, h->d_lv_off, b.counters);
+    const int n_parts = (n + kScanChunk - 1) / kScanChunk;
+    int32_t *part = b.counters + 8;  // chunk totals / bases live behind the counters
+    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan_local, n_parts, 1024, 0, b.deg, n, h->d_lv_off, part);
+    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan_parts, 1, 1024, 0, part, n_parts, n, h->d_lv_off, b.counters);
+    DD_LAUNCH(h, "lv_graph_scan", k_graph_scan_add, n_parts, 1024, 0, part, n, h->d_lv_off);
     DD_LAUNCH(h, "lv_graph_fill", k_graph_fill, nb, 256, 0, h->d_knn_idx, n, (int)k, h->d_lv_off, b.cursor, h->d_lv_adj,
               h->d_lv_comm, h->d_lv_tot, b.csize);
     return DD_OK;
@@ -481,6 +642,7 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         h->lv_graph_exec = nullptr;
         const bool timing = h->timing;
         const int64_t launches_before = h->launches;
+        static const bool warp_per_node = getenv("DD_LOUVAIN_WARP") != nullptr;  // A/B: the round-1 propose kernel
         h->timing = false;  // no event records inside the capture
         DD_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int rc = DD_OK;
@@ -489,9 +651,13 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
                 const int b0 = h->lv_colour_off[c], b1 = h->lv_colour_off[c + 1];
                 if (b1 == b0) continue;
                 dd_launch_begin(h);
-                k_lv_propose<<<(unsigned)((b1 - b0 + 7) / 8), 256, 0, h->stream>>>(h->d_lv_off, h->d_lv_adj, h->d_lv_comm,
-                                                                                    h->d_lv_tot, csize, bucket, b0, b1, n,
-                                                                                    gamma, desired, counters);
+                if (warp_per_node)
+                    k_lv_propose<<<(unsigned)((b1 - b0 + 7) / 8), 256, 0, h->stream>>>(h->d_lv_off, h->d_lv_adj, h->d_lv_comm,
+                                                                                        h->d_lv_tot, csize, bucket, b0, b1, n,
+                                                                                        gamma, desired, counters);
+                else
+                    k_lv_propose_g<<<(unsigned)((b1 - b0 + kNodesPerCta - 1) / kNodesPerCta), kPropWarps * 32, 0, h->stream>>>(
+                        h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, csize, bucket, b0, b1, n, gamma, desired, counters);
                 rc = dd_launch_end(h, "lv_propose");
                 if (rc != DD_OK) break;
                 dd_launch_begin(h);
@@ -527,6 +693,9 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
     }
     DD_TRY(dd_launch_end(h, "lv_rounds_graph"));
     h->launches += h->lv_graph_launches - 1;  // the replay runs every captured kernel
+    if (!h->h_lv_rounds && cudaMallocHost(&h->h_lv_rounds, sizeof(int32_t)) != cudaSuccess) h->h_lv_rounds = nullptr;
+    if (h->h_lv_rounds)  // rounds actually executed (the replay launches all kMaxRounds; converged rounds return at once)
+        cudaMemcpyAsync(h->h_lv_rounds, counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     return DD_OK;
 }
 

@@ -779,6 +779,22 @@ int run_pca_transposed(dd_handle *h, int n_power_iter) {
 
 }  // namespace
 
+// Two embedding buffers of `rows` x KP floats (grow-only): h->d_emb points at the one in use.  The fit loop flips between
+// them so that the kNN of iteration i (its own stream) reads one while the PCA of iteration i + 1 writes the other.
+int dd_emb_reserve(dd_handle *h, int64_t rows, int32_t KP) {
+    if (h->KP != KP || rows > h->cap_emb || !h->d_emb_base) {
+        if (h->d_emb_base) cudaFree(h->d_emb_base);
+        h->d_emb_base = h->d_emb = nullptr;
+        h->cap_emb = 0;
+        DD_CUDA(h, cudaMalloc(&h->d_emb_base, sizeof(float) * 2 * rows * KP));
+        h->cap_emb = rows;
+        h->emb_stride = rows * KP;
+        h->d_emb = h->d_emb_base;
+    }
+    h->KP = KP;
+    return DD_OK;
+}
+
 // Randomized PCA of the current dense matrix.  omega_host (G x n_random, row-major float32) may be
 // NULL to reuse the matrix uploaded by the previous call.
 int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter, const float *omega_host) {
@@ -836,13 +852,7 @@ int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_i
     h->L = n_random; h->LP = LP; h->C = n_comp;
     if (!transposed)
         DD_CUDA(h, cudaMemcpyAsync(h->d_Qt, omega_dev, sizeof(float) * LP * ld, cudaMemcpyDeviceToDevice, h->stream));
-    if (h->KP != KP || h->A_glob > h->cap_emb) {  // the embedding is global: every rank holds all A_glob rows
-        if (h->d_emb) cudaFree(h->d_emb);
-        h->d_emb = nullptr; h->cap_emb = 0;
-        DD_CUDA(h, cudaMalloc(&h->d_emb, sizeof(float) * h->A_glob * KP));
-        h->cap_emb = h->A_glob;
-    }
-    h->KP = KP;
+    DD_TRY(dd_emb_reserve(h, h->A_glob, KP));  // the embedding is global: every rank holds all A_glob rows
     int rc = transposed ? run_pca_transposed(h, n_power_iter)
                         : ((LP == 40) ? run_pca<40>(h, n_power_iter) : run_pca<64>(h, n_power_iter));
     if (rc != DD_OK) return rc;
@@ -893,12 +903,7 @@ extern "C" int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp,
     if (n_comp > 64) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_upload_embedding: more than 64 components");
     DD_CUDA(h, cudaSetDevice(h->device));
     const int KP = n_comp <= 32 ? 32 : 64;
-    if (h->KP != KP || n_rows > h->cap_emb) {
-        if (h->d_emb) cudaFree(h->d_emb);
-        h->d_emb = nullptr; h->cap_emb = 0;
-        DD_CUDA(h, cudaMalloc(&h->d_emb, sizeof(float) * n_rows * KP));
-        h->cap_emb = n_rows;
-    }
+    DD_TRY(dd_emb_reserve(h, n_rows, KP));
     h->KP = KP; h->C = n_comp;
     DD_CUDA(h, cudaMemsetAsync(h->d_emb, 0, sizeof(float) * n_rows * KP, h->stream));
     DD_CUDA(h, cudaMemcpy2DAsync(h->d_emb, sizeof(float) * KP, emb, sizeof(float) * n_comp, sizeof(float) * n_comp,

@@ -87,6 +87,16 @@ int dd_upload_dense(dd_handle *h, int64_t n_rows, int64_t n_genes, const float *
  * NULL.  singular_values_out (float64[n_comp]) may be NULL. */
 int dd_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter, const float *omega,
            float *emb_out, double *singular_values_out);
+/* ---- sklearn's EXACT PCA branches (svd_solver "covariance_eigh" / "full", picked by "auto" for <= 1000 genes with
+ * >= 10x as many augmented cells, for matrices with max(shape) <= 500 and for n_components >= 0.8 min(shape):
+ * sklearn/decomposition/_pca.py:524-536, 560-640; reached from doubletdetection.py:309-314).  The device does what scales
+ * with the number of cells; the caller eigendecomposes the small Gram matrix in between (numpy.linalg.eigh in the shim).
+ *   dd_centered_gram  float64 Gram matrix of the centred dense matrix: transposed == 0 -> G x G (sum over cells, i.e.
+ *                     (A - 1) x the covariance matrix), else A x A (sum over genes); out: n x n row-major, symmetric
+ *   dd_project        X_pca = (D - mean) V for sign-fixed components V (float64[G x n_comp], row-major); leaves the
+ *                     float32 embedding on the device for dd_knn like dd_pca does; emb_out (A x n_comp) may be NULL */
+int dd_centered_gram(dd_handle *h, int32_t transposed, double *out);
+int dd_project(dd_handle *h, int32_t n_comp, const double *components, float *emb_out);
 /* Test hook: replace the embedding by a caller-supplied one (A x n_comp float32). */
 int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const float *emb);
 

@@ -70,3 +70,16 @@ def randomized_pca_f64(X, n_components, random_state=0, normalizer="LU", n_iter=
     Vt = Vt * signs[:, np.newaxis]
     emb = U[:, :n_components] * s[:n_components]
     return emb, s[:n_components], Vt[:n_components]
+
+
+def exact_pca_f64(X, n_components):
+    """The float64 truth for sklearn's EXACT branches ("covariance_eigh" / "full", _pca.py:560-640): top principal
+    components of the centred matrix by a float64 SVD, signs by ``svd_flip(u_based_decision=False)``.
+    Returns (embedding A x C float64, singular values)."""
+    X = np.asarray(X, dtype=np.float64)
+    Xc = X - X.mean(axis=0)
+    U, s, Vt = linalg.svd(Xc, full_matrices=False)
+    idx = np.argmax(np.abs(Vt), axis=1)
+    signs = np.sign(Vt[np.arange(Vt.shape[0]), idx])
+    U = U * signs[np.newaxis, :]
+    return U[:, :n_components] * s[:n_components], s[:n_components]

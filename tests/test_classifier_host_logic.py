@@ -161,3 +161,55 @@ def test_shim_upload_errors_surface_from_the_worker_thread(shim, monkeypatch):
         warnings.simplefilter("ignore")
         with pytest.raises(MemoryError, match="out of memory"):
             shim(**kw).fit(counts)
+
+
+# ---- sklearn's exact PCA branches (covariance_eigh / full): the host half of _exact_pca over a numpy stand-in for the
+# two device entry points (dd_centered_gram / dd_project)
+class _NumpyDense:
+    def __init__(self, dense):
+        self.dense = np.asarray(dense, dtype=np.float32)
+        self._dense_rows, self.n_genes = self.dense.shape
+        self.emb = None
+
+    def _centred(self):
+        d = self.dense.astype(np.float64)
+        return d - d.mean(axis=0)
+
+    def centered_gram(self, transposed=False):
+        c = self._centred()
+        return c @ c.T if transposed else c.T @ c
+
+    def project(self, v):
+        self.emb = (self._centred() @ v).astype(np.float32)
+        return self.emb
+
+    def download_dense(self):
+        return self.dense
+
+    def upload_embedding(self, emb):
+        self.emb = np.asarray(emb, dtype=np.float32)
+
+
+@pytest.mark.parametrize("shape,solver", [((2600, 120), "covariance_eigh"), ((400, 90), "full"), ((60, 300), "full"),
+                                          ((36, 64), "full")])
+def test_exact_pca_branches_match_sklearn(shape, solver):
+    from sklearn.decomposition import PCA
+
+    from doubletdetection_b200.classifier import _exact_pca, _pca_plan, _pca_solver
+    from oracle import pca_f64
+
+    rs = np.random.default_rng(shape[0])
+    centres = rs.normal(size=(4, shape[1])) * 2.0
+    X = (centres[rs.integers(0, 4, shape[0])] + rs.normal(size=shape)).astype(np.float32)
+    c = 30
+    assert _pca_solver(shape[0], shape[1], c) == solver == pca_f64.auto_solver(shape[0], shape[1], c)
+    assert _pca_plan(shape[0], shape[1], c, 0) == (None, 0)
+    h = _NumpyDense(X)
+    emb = _exact_pca(h, c)
+    truth, _ = pca_f64.exact_pca_f64(X, c)
+    assert np.abs(emb - truth).max() / np.abs(truth).max() < 1e-6
+    # sklearn's own run (float32 for the eigh / svd) stays within the 1e-4 band of the same truth on the leading components
+    want = PCA(n_components=c, svd_solver="auto", random_state=0).fit_transform(X)
+    lead = slice(0, 3)
+    assert np.abs(want[:, lead] - truth[:, lead]).max() / np.abs(truth[:, lead]).max() < 1e-3
+    np.testing.assert_array_equal(h.emb, emb)

@@ -172,9 +172,15 @@ def _fit_worker(rank, world, port, mode, q):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             clf = BoostClassifier(n_iters=3, clustering_algorithm="louvain", distributed=mode).fit(counts)
+            # predict / doublet_score BEFORE anything touches the (n_iters, N) arrays: they must work from this rank's rows
+            # plus three all-reduced N-vectors (the rows are still pending), and give the complete answer on EVERY rank
+            assert clf._pending is not None
+            labels = np.asarray(clf.predict(p_thresh=1e-16, voter_thresh=0.5), dtype=np.float64)
+            score = np.ma.filled(np.ma.asarray(clf.doublet_score(), dtype=np.float64), np.nan)
+            assert clf._pending is not None
         calls = list(OracleHandle.calls)
         q.put((rank, calls[-1]["iter_begin"], calls[-1]["iter_end"], clf.all_scores_, clf.all_log_p_values_, clf.communities_,
-               np.asarray(clf.parents_, dtype=np.int64)))
+               np.asarray(clf.parents_, dtype=np.int64), labels, score))
     finally:
         dist.destroy_process_group()
 
@@ -196,8 +202,11 @@ def test_classifier_iteration_sharding_end_to_end_gloo_world2(mode):
     for p in procs:
         p.join(timeout=30)
     assert (results[0][0], results[0][1]) == (0, 1) and (results[1][0], results[1][1]) == (1, 3)  # blocks of 3 iterations
-    for rank in ((0, 1) if mode == "allgather" else (0,)):  # complete results: everywhere / on rank 0
-        _, _, scores, logp, comm, parents = results[rank]
+    for rank in (0, 1):  # labels and scores are complete on every rank in both modes (all-reduced per-cell sums)
+        np.testing.assert_array_equal(results[rank][6], g["labels"])
+        np.testing.assert_allclose(results[rank][7], g["doublet_score"], rtol=1e-12, equal_nan=True)
+    for rank in ((0, 1) if mode == "allgather" else (0,)):  # complete (n_iters, N) arrays: everywhere / on rank 0
+        _, _, scores, logp, comm, parents = results[rank][:6]
         np.testing.assert_array_equal(parents, g["parents"])  # every rank draws ALL iterations' parents (one stream)
         np.testing.assert_array_equal(scores, g["all_scores"])
         np.testing.assert_allclose(logp, g["all_log_p_values"], rtol=1e-12)

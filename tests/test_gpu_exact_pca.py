@@ -1,0 +1,108 @@
+"""sklearn's EXACT PCA branches on the B200 path (doubletdetection.py:309-314 -> PCA(svd_solver="auto") ->
+"covariance_eigh" for <= 1000 genes and >= 10x as many augmented cells, "full" for tiny matrices): device Gram matrix +
+projection around a host eigendecomposition.  Needs a B200 (`-m gpu`)."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import datasets, louvain_c, pca_f64, reference_path, upstream
+
+pytestmark = pytest.mark.gpu
+
+
+def _blobs(shape, seed):
+    rs = np.random.default_rng(seed)
+    centres = rs.normal(size=(5, shape[1])) * 2.0
+    return (centres[rs.integers(0, 5, shape[0])] + rs.normal(size=shape)).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(12500, 1000), (2600, 120), (4097, 333), (400, 90)])
+def test_centered_gram_and_projection_vs_numpy(handle, shape):
+    X = _blobs(shape, shape[0])
+    handle.upload_dense(X)
+    Xc = X.astype(np.float64) - X.astype(np.float64).mean(axis=0)
+    want = Xc.T @ Xc
+    got = handle.centered_gram(False)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-9 * np.abs(want).max())
+    assert np.array_equal(got, got.T)
+    v = np.linalg.qr(np.random.default_rng(1).normal(size=(shape[1], 30)))[0]
+    emb = handle.project(v)
+    np.testing.assert_allclose(emb, (Xc @ v).astype(np.float32), rtol=2e-6, atol=2e-6)
+    idx, _ = handle.knn(10)  # the projection left a valid embedding on the device
+    assert (idx[:, 0] == np.arange(shape[0])).all()
+
+
+@pytest.mark.parametrize("shape", [(60, 300), (36, 64), (300, 450)])
+def test_centered_gram_on_the_cell_side(handle, shape):
+    X = _blobs(shape, shape[1])
+    handle.upload_dense(X)
+    Xc = X.astype(np.float64) - X.astype(np.float64).mean(axis=0)
+    want = Xc @ Xc.T
+    np.testing.assert_allclose(handle.centered_gram(True), want, rtol=1e-11, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("shape", [(12500, 1000), (2600, 120), (400, 90), (60, 300), (36, 64)])
+def test_exact_pca_vs_float64_truth_and_sklearn(handle, shape):
+    """north_star tolerance 1e-4 against the float64 truth; sklearn's own float32 run is reported beside it."""
+    from sklearn.decomposition import PCA
+
+    from doubletdetection_b200.classifier import _exact_pca, _pca_solver
+
+    X = _blobs(shape, 7 + shape[0])
+    assert _pca_solver(shape[0], shape[1], 30) in ("covariance_eigh", "full")
+    handle.upload_dense(X)
+    emb = _exact_pca(handle, 30)
+    truth, _ = pca_f64.exact_pca_f64(X, 30)
+    err = np.abs(emb - truth).max() / np.abs(truth).max()
+    sk = PCA(n_components=30, svd_solver="auto", random_state=0).fit_transform(X)
+    err_sk = np.abs(sk - truth).max() / np.abs(truth).max()
+    print(f"\n[exact PCA {shape}] GPU vs f64 truth {err:.2e}; sklearn-f32 vs f64 truth {err_sk:.2e}")
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("algo", ["louvain", "phenograph"])
+def test_classifier_with_1000_top_var_genes(handle, algo):
+    """``n_top_var_genes=1000`` on a 10k-cell dataset (a common setting): A = 12 500 >= 10 G -> covariance_eigh.  Parents
+    bit-exact; per iteration the oracle's downstream stages run on the GPU embedding reproduce the classifier's communities
+    and scores exactly; the embedding is within 1e-4 of the float64 truth."""
+    from doubletdetection_b200 import BoostClassifier
+    from doubletdetection_b200.classifier import _exact_pca
+
+    counts = datasets.structured_counts(10000, 1500, seed=21)
+    kw = dict(n_iters=2, n_top_var_genes=1000, clustering_algorithm=algo, random_state=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(n_jobs=4, **kw).fit(counts)
+        ora = reference_path.OracleClassifier(louvain_fn=louvain_c.louvain, **kw).fit(counts)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    np.testing.assert_array_equal(clf.top_var_genes_, ora.top_var_genes_)
+    pro = reference_path.prologue(counts, 1000)
+    n = counts.shape[0]
+    handle.upload_counts(pro["raw"])
+    for i in range(2):
+        handle.create_doublets(np.asarray(clf._parents_array[i]))
+        handle.normalise_log(handle.median_lib_size(), 0.1)
+        emb = _exact_pca(handle, 30)
+        if i == 0:
+            truth, _ = pca_f64.exact_pca_f64(handle.download_dense(), 30)
+            err = np.abs(emb - truth).max() / np.abs(truth).max()
+            print(f"\n[{algo}, n_top_var_genes=1000] embedding vs f64 truth {err:.2e}")
+            assert err < 1e-4
+        if algo == "phenograph":
+            labels, _ = upstream.phenograph_cluster(emb, seed=0, louvain_fn=louvain_c.louvain, prune=True)
+        else:
+            idx, _ = upstream.knn_brute(emb, 10)
+            g = upstream.knn_pattern_graph(idx)
+            labels = louvain_c.louvain(g.indptr, g.indices, None, resolution=4.0, seed=0, level0="parallel")
+        np.testing.assert_array_equal(clf.communities_[i], labels[:n])
+        s, lp, _, _ = reference_path.score_communities(labels, n)
+        np.testing.assert_array_equal(clf.all_scores_[i], s)
+        np.testing.assert_allclose(clf.all_log_p_values_[i], lp, rtol=1e-9, atol=1e-12, equal_nan=True)
+    # drift against the oracle's own float32 covariance_eigh run
+    from sklearn.metrics import adjusted_rand_score
+
+    ari = [adjusted_rand_score(clf.communities_[i], ora.communities_[i]) for i in range(2)]
+    print(f"[{algo}] adjusted Rand vs the oracle's float32 run: {np.round(ari, 4)}")
+    assert min(ari) > 0.8
