@@ -369,12 +369,25 @@ class BoostClassifier:
                 raise NotImplementedError("distributed='cells' with sklearn's exact PCA branches (<= 1000 genes or a tiny matrix)")
             out = self._fit_iterations_exact_pca(h, parents, it0, it1, cluster_kw)
         else:
-            out = h.fit_iterations(
-                parents, omega,
-                pseudocount=self.pseudocount, standard_scaling=self.standard_scaling is True,
-                n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10, seed=int(self.random_state),
-                n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1, **cluster_kw,
-            )
+            failure = None
+            try:
+                out = h.fit_iterations(
+                    parents, omega,
+                    pseudocount=self.pseudocount, standard_scaling=self.standard_scaling is True,
+                    n_comp=self.n_components, n_power_iter=n_power_iter, knn_k=10, seed=int(self.random_state),
+                    n_host_threads=self._host_threads(), iter_begin=it0, iter_end=it1, **cluster_kw,
+                )
+            except Exception as e:  # noqa: BLE001 -- re-raised below, on every rank
+                if cells_dist is None:
+                    raise
+                failure = e
+            if cells_dist is not None:
+                # the failure of an iteration is seen by the rank that owns it only: make it collective before the merge
+                any_failed = all_ranks_any(cells_dist, failure is not None, self.device)
+                if failure is not None:
+                    raise failure
+                if any_failed:
+                    raise RuntimeError("fit failed on another rank of the cell-sharded group (see that rank's error)")
         _t.append(_time.perf_counter())
         self._pending, self._fitted = None, {}
         if cells_dist is not None:
@@ -488,6 +501,16 @@ def broadcast_token(dist, token, device):
     buf = buf.to(dev)
     dist.broadcast(buf, src=0)
     return bytes(buf.cpu().numpy().tobytes())
+
+
+def all_ranks_any(dist, flag, device):
+    """True on every rank iff ``flag`` is true on at least one (an all-reduce MAX of one integer)."""
+    import torch
+
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
 
 
 def merge_owned_iterations(dist, out, device):

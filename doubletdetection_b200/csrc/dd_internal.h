@@ -30,6 +30,30 @@ struct dd_timed_launch {
 
 struct dd_tc_state;
 
+// One clustering LANE of the fit loop: the device state of a first Louvain level (graph CSR, communities, totals, captured
+// round sequence) with its own stream.  The level is a chain of ~300 dependent, latency-bound steps (10 ms at 125 k cells
+// when it shares the GPU with the main stream's kernels, 4 ms alone) and uses a few percent of the SMs, so the levels of
+// CONSECUTIVE ITERATIONS run concurrently, one lane each.  Lane 0 lives in the handle's own fields (stage-wise calls use
+// it); dd_lv_swap() exchanges a lane with the handle's fields around the calls that work on it.
+struct dd_lv_lane {
+    int32_t *d_lv_off = nullptr, *d_lv_adj = nullptr, *d_lv_comm = nullptr, *d_lv_i32 = nullptr;
+    double *d_lv_tot = nullptr, *d_lv_w = nullptr;
+    int64_t cap_lv_n = 0, cap_lv_nnz = 0, cap_lv_w = 0;
+    long long *d_lvw_wq = nullptr, *d_lvw_i64 = nullptr;
+    int32_t *d_lvw_i32 = nullptr;
+    int64_t cap_lvw_nnz = 0, cap_lvw_n = 0, lvw_bucket_n = -1;
+    uint64_t lvw_bucket_seed = 0;
+    int64_t lv_bucket_n = -1;
+    uint64_t lv_bucket_seed = 0;
+    int32_t *h_lv_rounds = nullptr;
+    void *lv_graph_exec = nullptr;
+    int64_t lv_graph_n = -1, lv_graph_launches = 0;
+    bool lv_graph_is_loop = false;
+    double lv_graph_gamma = 0.0;
+    uint64_t lv_graph_seed = 0;
+    cudaStream_t stream = nullptr;
+};
+
 struct dd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -112,6 +136,7 @@ struct dd_handle {
     int32_t *d_knn_list_off = nullptr, *d_knn_list_tiles = nullptr;
     int64_t cap_knn_list_off = 0, cap_knn_list_tiles = 0;
     int knn_list_pairs = 0;
+    bool knn_narrow = false;  // 64-row pipeline steps / 256 TMEM columns: co-resident with a PCA product CTA (fit loop)
 
     // ---- GPU Louvain level 0 (louvain_gpu.cu): symmetric kNN pattern as CSR + community state ----
     int32_t *d_lv_off = nullptr, *d_lv_adj = nullptr, *d_lv_comm = nullptr, *d_lv_i32 = nullptr;
@@ -130,8 +155,12 @@ struct dd_handle {
     int32_t *h_lv_rounds = nullptr;  // pinned: rounds the last first level ran (reported as stage "lv_rounds")
     void *lv_graph_exec = nullptr;  // cudaGraphExec_t of the captured round sequence
     int64_t lv_graph_n = -1, lv_graph_launches = 0;
+    bool lv_graph_is_loop = false;
     double lv_graph_gamma = 0.0;
     uint64_t lv_graph_seed = 0;
+
+    std::vector<dd_lv_lane> lv_lanes;             // lanes 1.. (lane 0 = the fields above + stream2)
+    cudaEvent_t ev_after_graph_build = nullptr;   // if set, dd_dev_louvain_level0 records it once the kNN lists have been read
 
     // ---- pinned host slots of the pipelined fit loop (kNN graph + PCA flag per in-flight iteration) ----
     std::vector<int32_t *> slot_knn;
@@ -235,6 +264,8 @@ int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
 int dd_emb_reserve(dd_handle *h, int64_t rows, int32_t KP);         // pca.cu: (re)allocate the two embedding buffers
 int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed);  // louvain_gpu.cu
 int dd_dev_jaccard_graph(dd_handle *h, int32_t k, int prune);                      // louvain_gpu.cu (PhenoGraph)
+void dd_lv_swap(dd_handle *h, dd_lv_lane &lane);                                   // handle.cu
+void dd_lv_lane_free(dd_lv_lane &lane);                                            // handle.cu
 
 // host pieces (louvain.cpp / score.cpp)
 int dd_host_louvain_knn(int64_t n, int32_t k, const int32_t *knn_idx, double resolution, uint64_t seed,

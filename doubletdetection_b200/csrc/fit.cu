@@ -223,9 +223,28 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     // every rank.
     static const bool knn_inline = getenv("DD_KNN_INLINE") != nullptr;  // A/B: the round-1 order (kNN on the main stream)
     const bool knn_own_stream = !dd_sharded(h) && !knn_inline;
+    static const bool knn_narrow_ok = getenv("DD_KNN_NARROW") != nullptr;  // A/B: the 256-column kernel (measured slower: 6.2 vs 4.95 ms, profiles/r2g)
+    // clustering lanes (dd_lv_lane): the first Louvain levels of up to n_lanes consecutive iterations in flight at once
+    int n_lanes = 2;  // measured 1..4 (profiles/r2f_lanes.log): wall per iteration within 0.5 ms of each other
+    if (const char *e = getenv("DD_LV_LANES")) n_lanes = std::max(1, std::min(8, atoi(e)));
+    if (leiden) n_lanes = 1;
+    while ((int)h->lv_lanes.size() < n_lanes - 1) {
+        dd_lv_lane l;
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        if (cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
+            rc = dd_fail(h, DD_ERR_CUDA, "dd_fit_iterations: clustering lane stream");
+            break;
+        }
+        h->lv_lanes.push_back(l);
+    }
     cudaStream_t const main_stream = h->stream;
     cudaStream_t const knn_stream = knn_own_stream ? h->stream4 : h->stream;
-    for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && worker_rc.load() == DD_OK; it++, issued++) {
+    // A host worker's failure (rank-deficient PCA, clustering rejected) stops the loop early -- except on a cell-sharded
+    // handle: there only the OWNING rank sees it, and a rank that left the loop would leave the others waiting in NCCL
+    // collectives it never joins.  Sharded ranks therefore issue every iteration and report the failure at the end (the
+    // Python shim all-reduces the status so that every rank raises).
+    for (int it = p->iter_begin; it < p->iter_end && rc == DD_OK && (dd_sharded(h) || worker_rc.load() == DD_OK); it++, issued++) {
         // Cell-block sharding: every rank holds the all-gathered kNN lists of every iteration, so the clustering + scoring
         // of the iterations is dealt round-robin to the ranks (rank it % world finishes iteration it; the caller merges the
         // per-iteration result rows, which stay zero on the other ranks).
@@ -267,7 +286,9 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         if (issued > 1) cudaStreamWaitEvent(knn_stream, lv_done, 0);
         if (h->d_knn_idx_base) h->d_knn_idx = h->d_knn_idx_base + eb * h->knn_idx_stride;
         h->emb_valid = true;  // issuing the next dense build (new parents) marked this iteration's embedding stale
+        h->knn_narrow = knn_own_stream && knn_narrow_ok;
         rc = dd_dev_knn(h, k);
+        h->knn_narrow = false;
         if (rc == DD_OK && h->d_knn_idx != h->d_knn_idx_base + eb * h->knn_idx_stride)  // first call allocated the buffers
             h->d_knn_idx = h->d_knn_idx_base + eb * h->knn_idx_stride;
         cudaEventRecord(ev[4], knn_stream);
@@ -300,25 +321,36 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             continue;
         }
         // clustering, first level: symmetric kNN pattern + synchronous coloured Louvain rounds on the device.
-        // These are hundreds of small latency-bound kernels: they run on their own stream and overlap the
-        // HBM-bound dense build / PCA of the NEXT iteration.
-        cudaStreamWaitEvent(h->stream2, h->ev_knn_done, 0);
-        cudaStreamWaitEvent(h->stream2, h->ev_pca_done[eb], 0);  // s.done must also cover the flag copy (main stream)
-        {
-            h->stream = h->stream2;
-            rc = pheno ? dd_dev_jaccard_graph(h, k, p->pheno_prune) : dd_dev_louvain_level0(h, k, p->resolution, p->seed);
-            if (rc == DD_OK && pheno && pheno_level0) rc = dd_dev_louvain_level0_weighted(h, 1.0, p->seed);
-            h->stream = main_stream;
+        // These are hundreds of small latency-bound kernels: they run on a clustering lane (own stream, own state) and
+        // overlap the dense build / PCA / kNN of the NEXT iterations -- and the levels of the neighbouring iterations on
+        // the other lanes.
+        const int lane = issued % n_lanes;
+        cudaStream_t cl_stream = lane == 0 ? h->stream2 : h->lv_lanes[lane - 1].stream;
+        cudaStreamWaitEvent(cl_stream, h->ev_knn_done, 0);
+        cudaStreamWaitEvent(cl_stream, h->ev_pca_done[eb], 0);  // s.done must also cover the flag copy (main stream)
+        if (lane > 0) dd_lv_swap(h, h->lv_lanes[lane - 1]);
+        h->stream = cl_stream;
+        if (pheno) {
+            rc = dd_dev_jaccard_graph(h, k, p->pheno_prune);
+            cudaEventRecord(lv_done, cl_stream);  // the lists have been read
+            if (rc == DD_OK && pheno_level0) rc = dd_dev_louvain_level0_weighted(h, 1.0, p->seed);
+        } else {
+            h->ev_after_graph_build = lv_done;  // recorded as soon as the pattern graph exists: the lists are free again
+            rc = dd_dev_louvain_level0(h, k, p->resolution, p->seed);
+            h->ev_after_graph_build = nullptr;
         }
+        h->stream = main_stream;
+        if (rc == DD_OK) {
+            cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, cl_stream);
+            cudaMemcpyAsync(s.graph + (A + 1), h->d_lv_comm, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, cl_stream);
+            cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, cl_stream);
+            if (pheno)
+                cudaMemcpyAsync(s.graph + w_off, h->d_lv_w, sizeof(double) * max_nnz, cudaMemcpyDeviceToHost, cl_stream);
+        }
+        if (lane > 0) dd_lv_swap(h, h->lv_lanes[lane - 1]);
         if (rc != DD_OK) break;
-        cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, h->stream2);
-        cudaMemcpyAsync(s.graph + (A + 1), h->d_lv_comm, sizeof(int32_t) * A, cudaMemcpyDeviceToHost, h->stream2);
-        cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, h->stream2);
-        if (pheno)
-            cudaMemcpyAsync(s.graph + w_off, h->d_lv_w, sizeof(double) * max_nnz, cudaMemcpyDeviceToHost, h->stream2);
-        cudaEventRecord(ev[5], h->stream2);
-        cudaEventRecord(lv_done, h->stream2);
-        cudaEventRecord(s.done, h->stream2);
+        cudaEventRecord(ev[5], cl_stream);
+        cudaEventRecord(s.done, cl_stream);
         {
             std::lock_guard<std::mutex> lk(mu);
             jobs.push_back(Job{it, slot});
@@ -336,6 +368,8 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream2);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream3);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream4);
+    for (dd_lv_lane &l : h->lv_lanes)
+        if (ce == cudaSuccess && l.stream) ce = cudaStreamSynchronize(l.stream);
     if (rc == DD_OK && ce != cudaSuccess) rc = dd_fail(h, DD_ERR_CUDA, std::string("dd_fit_iterations: ") + cudaGetErrorString(ce));
     if (rc == DD_OK && worker_rc.load() != DD_OK) rc = dd_fail(h, worker_rc.load(), worker_err);
     if (rc == DD_OK && h->h_lv_rounds && !pheno && !leiden) h->stage_ms["lv_rounds"] = (double)*h->h_lv_rounds;

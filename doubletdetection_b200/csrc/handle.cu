@@ -1,4 +1,6 @@
 // handle.cu -- lifetime, error reporting, launch accounting and stage timers of libdd_b200.so.
+#include <utility>
+
 #include "dd_internal.h"
 #include "pca_tc.h"
 
@@ -127,6 +129,32 @@ extern "C" int dd_create(int device, dd_handle **out) {
     return DD_OK;
 }
 
+// exchange the Louvain-level state of the handle (= lane 0) with `lane`
+void dd_lv_swap(dd_handle *h, dd_lv_lane &l) {
+    std::swap(h->d_lv_off, l.d_lv_off); std::swap(h->d_lv_adj, l.d_lv_adj); std::swap(h->d_lv_comm, l.d_lv_comm);
+    std::swap(h->d_lv_i32, l.d_lv_i32); std::swap(h->d_lv_tot, l.d_lv_tot); std::swap(h->d_lv_w, l.d_lv_w);
+    std::swap(h->cap_lv_n, l.cap_lv_n); std::swap(h->cap_lv_nnz, l.cap_lv_nnz); std::swap(h->cap_lv_w, l.cap_lv_w);
+    std::swap(h->d_lvw_wq, l.d_lvw_wq); std::swap(h->d_lvw_i64, l.d_lvw_i64); std::swap(h->d_lvw_i32, l.d_lvw_i32);
+    std::swap(h->cap_lvw_nnz, l.cap_lvw_nnz); std::swap(h->cap_lvw_n, l.cap_lvw_n);
+    std::swap(h->lvw_bucket_n, l.lvw_bucket_n); std::swap(h->lvw_bucket_seed, l.lvw_bucket_seed);
+    std::swap(h->lv_bucket_n, l.lv_bucket_n); std::swap(h->lv_bucket_seed, l.lv_bucket_seed);
+    std::swap(h->h_lv_rounds, l.h_lv_rounds); std::swap(h->lv_graph_exec, l.lv_graph_exec);
+    std::swap(h->lv_graph_n, l.lv_graph_n); std::swap(h->lv_graph_launches, l.lv_graph_launches);
+    std::swap(h->lv_graph_is_loop, l.lv_graph_is_loop); std::swap(h->lv_graph_gamma, l.lv_graph_gamma);
+    std::swap(h->lv_graph_seed, l.lv_graph_seed);
+}
+
+void dd_lv_lane_free(dd_lv_lane &l) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    for (void *p : {(void *)l.d_lv_off, (void *)l.d_lv_adj, (void *)l.d_lv_comm, (void *)l.d_lv_i32, (void *)l.d_lv_tot,
+                    (void *)l.d_lv_w, (void *)l.d_lvw_wq, (void *)l.d_lvw_i64, (void *)l.d_lvw_i32})
+        if (p) cudaFree(p);
+    if (l.lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)l.lv_graph_exec);
+    if (l.h_lv_rounds) cudaFreeHost(l.h_lv_rounds);
+    if (l.stream) cudaStreamDestroy(l.stream);
+    l = dd_lv_lane();
+}
+
 extern "C" void dd_destroy(dd_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -139,6 +167,7 @@ extern "C" void dd_destroy(dd_handle *h) {
                     h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb_base, h->d_knn_idx_base, h->d_knn_dist, h->d_knn_ops, h->d_knn_list_off, h->d_knn_list_tiles, h->d_lvw_wq, h->d_lvw_i64, h->d_lvw_i32, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w};
     for (void *p : bufs)
         if (p) cudaFree(p);
+    for (dd_lv_lane &l : h->lv_lanes) dd_lv_lane_free(l);
     dd_tc_free(h);
     dd_comm_destroy(h);
     if (h->lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lv_graph_exec);

@@ -309,7 +309,14 @@ constexpr int QT = 2;                          // query tiles per CTA
 constexpr int NS = 4;                          // candidate stages
 constexpr int KSTEPS = KC / 2;                 // 7 MMAs of K = 16
 constexpr float kEmptyT = -1e29f;              // list filler; padded candidates score -1e30 and never pass
-constexpr size_t SMEM_BYTES = (size_t)(QT + NS) * TILE_BYTES + 1024;
+// TN = candidate rows per pipeline step.  128: one whole operand tile per step, 512 TMEM columns (2 buffers x 2 query tiles
+// x 128), 169 KB of shared memory -- the SM is this kernel's alone.  64 (the fit loop's choice when the kNN runs on its own
+// stream next to the following iteration's PCA): half a tile per step, 256 TMEM columns, 113 KB -- one CTA of the HBM-bound
+// PCA product kernel (87 KB, 256 columns) fits on the SM beside it, so the two streams overlap on every SM instead of
+// taking turns.
+template <int TN>
+constexpr size_t smem_bytes() { return (size_t)QT * TILE_BYTES + (size_t)NS * TN * KC * 16 + 1024; }
+constexpr size_t SMEM_BYTES = smem_bytes<128>();
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -383,8 +390,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= 1ull << 46;
     return d;
 }
-// kind::f16 with BF16 operands, fp32 accumulate, A and B K-major, M = 128, N = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 with BF16 operands, fp32 accumulate, A and B K-major, M = 128, N = 128 / 64
+template <int TN>
+struct Idesc {
+    static constexpr uint32_t value = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)TN >> 3) << 17) | ((128u >> 4) << 24);
+};
 
 // x = b1 + b2 + b3 with bf16 parts (round to nearest at every step; the remainders are exact in float32)
 __device__ __forceinline__ void bf16_split3(float x, __nv_bfloat16 &b1, __nv_bfloat16 &b2, __nv_bfloat16 &b3) {
@@ -478,15 +488,18 @@ constexpr int THREADS = 320;  // producer warp + MMA warp + 8 epilogue warps
 // LISTED (experimental, dd_knn_listed): instead of ALL candidate tiles a query-tile pair visits the tiles of its own list
 // (list_tiles[list_off[pair] .. list_off[pair + 1])) -- the three roles below loop over the same step counter, so the list
 // only changes which tile a step loads and which candidate indices it stands for.
-template <int LIST, bool LISTED = false>  // LIST: candidates kept per query row, 16 (k <= 13) or 32 (k <= 31, PhenoGraph)
+template <int LIST, bool LISTED = false, int TN = 128>  // LIST: candidates kept per query row, 16 (k <= 13) or 32 (k <= 31, PhenoGraph)
 __global__ void __launch_bounds__(THREADS, 1)
     k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb, int64_t n, int n_tiles, int pair0,
              int n_full, int *__restrict__ cand_i, const int *__restrict__ list_off = nullptr,
              const int *__restrict__ list_tiles = nullptr) {
+    constexpr int SUB = TILE / TN;                     // pipeline steps per 128-row candidate tile
+    constexpr int STAGE_BYTES = TN * KC * 16;
+    constexpr uint32_t TMEM_COLS = 4 * TN;             // 2 buffers x 2 query tiles x TN accumulator columns
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;                                // QT tiles
     uint8_t *sB = smem + (size_t)QT * TILE_BYTES;      // NS stages
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)(QT + NS) * TILE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)QT * TILE_BYTES + (size_t)NS * STAGE_BYTES);
     uint64_t *a_full = bars;            // 1
     uint64_t *full = bars + 1;          // NS
     uint64_t *empty = full + NS;        // NS
@@ -507,6 +520,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         n_tiles = list_off[pair0 + (int)blockIdx.x + 1] - off;
         my_list = list_tiles + off;
     }
+    const int n_steps = n_tiles * SUB;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -520,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     fence_before();
     __syncthreads();
     fence_after();
@@ -531,14 +545,16 @@ __global__ void __launch_bounds__(THREADS, 1)
             mbar_expect_tx(a_full, n_qt * TILE_BYTES);
             for (int qt = 0; qt < n_qt; qt++)
                 bulk_g2s(sA + (size_t)qt * TILE_BYTES, qa + (size_t)(tile0 + qt) * TILE_BYTES, TILE_BYTES, a_full);
-            for (int step = 0; step < n_tiles; step++) {
+            for (int step = 0; step < n_steps; step++) {
                 const int s = step % NS;
                 const uint32_t ph = (step / NS) & 1;
                 mbar_wait(empty + s, ph ^ 1);
-                mbar_expect_tx(full + s, TILE_BYTES);
-                int tile = step;
-                if constexpr (LISTED) tile = my_list[step];
-                bulk_g2s(sB + (size_t)s * TILE_BYTES, cb + (size_t)tile * TILE_BYTES, TILE_BYTES, full + s);
+                mbar_expect_tx(full + s, STAGE_BYTES);
+                int tile = step / SUB;
+                if constexpr (LISTED) tile = my_list[step / SUB];
+                // a TN-row slice of a tile is contiguous in the canonical layout (whole 8-row groups of SBO bytes)
+                bulk_g2s(sB + (size_t)s * STAGE_BYTES, cb + (size_t)tile * TILE_BYTES + (size_t)(step % SUB) * STAGE_BYTES,
+                         STAGE_BYTES, full + s);
             }
         }
     } else if (warp == 1) {
@@ -547,7 +563,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             fence_after();
             uint64_t a_desc[QT];
             for (int qt = 0; qt < QT; qt++) a_desc[qt] = make_desc(smem_u32(sA + (size_t)qt * TILE_BYTES));
-            for (int step = 0; step < n_tiles; step++) {
+            for (int step = 0; step < n_steps; step++) {
                 const int s = step % NS;
                 const uint32_t ph = (step / NS) & 1;
                 const int buf = step & 1;
@@ -555,14 +571,14 @@ __global__ void __launch_bounds__(THREADS, 1)
                 mbar_wait(full + s, ph);
                 mbar_wait(tempty + buf, bph ^ 1);
                 fence_after();
-                const uint64_t b_desc = make_desc(smem_u32(sB + (size_t)s * TILE_BYTES));
+                const uint64_t b_desc = make_desc(smem_u32(sB + (size_t)s * STAGE_BYTES));
 #pragma unroll
                 for (int qt = 0; qt < QT; qt++) {
                     if (qt >= n_qt) break;
-                    const uint32_t d = tmem_base + buf * 256 + qt * 128;
+                    const uint32_t d = tmem_base + buf * (2 * TN) + qt * TN;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++)
-                        mma_bf16(d, a_desc[qt] + (uint64_t)(k * 2 * LBO / 16), b_desc + (uint64_t)(k * 2 * LBO / 16), kIdesc,
+                        mma_bf16(d, a_desc[qt] + (uint64_t)(k * 2 * LBO / 16), b_desc + (uint64_t)(k * 2 * LBO / 16), Idesc<TN>::value,
                                  k > 0);
                 }
                 mma_commit(empty + s);     // the stage may be refilled once these MMAs have read it
@@ -575,7 +591,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int quad = warp & 3;       // TMEM lane quadrant this warp may access (four consecutive e cover all)
         const int64_t qrow = (int64_t)(tile0 + qt) * TILE + quad * 32 + lane;
         const bool active = qrow < n;
-        const int my_tiles = qt < n_qt ? n_tiles : 0;  // the second tile's warps of a half CTA have nothing to do
+        const int my_tiles = qt < n_qt ? n_steps : 0;  // the second tile's warps of a half CTA have nothing to do
         RegList<LIST> L;
 #pragma unroll
         for (int l = 0; l < LIST; l++) {
@@ -583,7 +599,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             L.i[l] = 0x7fffffff;
         }
         float tau = active ? kEmptyT : INFINITY;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * 128;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * TN;
         for (int step = 0; step < my_tiles; step++) {
             const int buf = step & 1;
             const uint32_t bph = (step >> 1) & 1;
@@ -591,9 +607,9 @@ __global__ void __launch_bounds__(THREADS, 1)
             fence_after();
             // software pipeline: the tcgen05.ld of the next 32 columns is in flight while this group is scanned
             uint32_t va[32], vb[32];
-            const uint32_t col0 = lane_base + buf * 256;
-            int cand0 = step * TILE;
-            if constexpr (LISTED) cand0 = my_list[step] * TILE;
+            const uint32_t col0 = lane_base + buf * (2 * TN);
+            int cand0 = (step / SUB) * TILE + (step % SUB) * TN;
+            if constexpr (LISTED) cand0 = my_list[step / SUB] * TILE + (step % SUB) * TN;
             auto scan = [&](uint32_t (&v)[32], int c) {
                 // balanced max tree (depth 5) instead of a 31-long dependent chain
                 float m8[8];
@@ -626,12 +642,12 @@ __global__ void __launch_bounds__(THREADS, 1)
             };
             tmem_ld32(col0, va);
 #pragma unroll 1
-            for (int half = 0; half < 2; half++) {  // rolled: two copies of the scan code, not four
+            for (int half = 0; half < TN / 64; half++) {  // rolled: two copies of the scan code, not four
                 tmem_ld_wait();
                 tmem_ld32(col0 + 64 * half + 32, vb);
                 scan(va, 64 * half);
                 tmem_ld_wait();
-                if (half == 0) tmem_ld32(col0 + 64, va);
+                if (half + 1 < TN / 64) tmem_ld32(col0 + 64 * (half + 1), va);
                 scan(vb, 64 * half + 32);
             }
             fence_before();
@@ -646,7 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     __syncthreads();
     if (warp == 1) {
         fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -682,6 +698,8 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
         cudaFuncSetAttribute(tc::k_knn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         cudaFuncSetAttribute(tc::k_knn_tc<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         cudaFuncSetAttribute(tc::k_knn_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<16, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
+        cudaFuncSetAttribute(tc::k_knn_tc<32, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
     });
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
               reinterpret_cast<uint4 *>(qa), reinterpret_cast<uint4 *>(cb));
@@ -715,7 +733,17 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
         static const bool split_tail = getenv("DD_KNN_NO_TAIL_SPLIT") == nullptr;
         const int n_full = split_tail ? pairs / h->num_sms * h->num_sms : pairs;
         const unsigned grid = (unsigned)(n_full + (pairs - n_full) * tc::QT);
-        if (TL == 16) {
+        if (h->knn_narrow && TL == 16) {
+            DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<16, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
+                      n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
+            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
+                      k, h->d_knn_idx, h->d_knn_dist);
+        } else if (h->knn_narrow) {
+            DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<32, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
+                      n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
+            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
+                      k, h->d_knn_idx, h->d_knn_dist);
+        } else if (TL == 16) {
             DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);

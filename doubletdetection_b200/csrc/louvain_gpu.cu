@@ -29,6 +29,28 @@ __host__ __device__ inline int colour_of(uint64_t seed, int i) {
     return (int)(z % kColours);
 }
 
+// Programmatic dependent launch (PDL): a kernel of the round sequence lets its successor's CTAs become resident as soon as
+// it is itself unblocked (launch_dependents right after its own wait) and the successor fetches everything that is STATIC during the level (colour bucket, CSR
+// offsets, adjacency) before it waits for its predecessor to complete and flush (pdl_wait) -- the launch latency and three
+// of the five dependent loads of a step leave the critical path.  Only data written inside the level (communities, totals,
+// sizes, desired moves, counters) may be touched after pdl_wait, and nothing written inside the level before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_step(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ bool in_out_list(const int32_t *__restrict__ knn, int k, int j, int i) {
     for (int c = 0; c < k; c++)
         if (knn[(int64_t)j * k + c] == i) return true;
@@ -266,6 +288,7 @@ __global__ void __launch_bounds__(256) k_lv_propose(const int32_t *__restrict__ 
                                                     double gamma, int32_t *__restrict__ desired,
                                                     const int32_t *__restrict__ counters) {
     __shared__ int32_t s_tab[8 * 2 * kTable];
+    pdl_wait();
     if (counters[1]) return;  // converged in an earlier round
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int w = blockIdx.x * (blockDim.x >> 5) + wl;
@@ -294,11 +317,11 @@ __global__ void __launch_bounds__(kPropWarps * 32, 10) k_lv_propose_g(const int3
                                                       double gamma, int32_t *__restrict__ desired,
                                                       const int32_t *__restrict__ counters) {
     __shared__ int32_t s_tab[kPropWarps * 2 * kTable];
-    if (counters[1]) return;  // converged in an earlier round
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int gl = lane & (kGroupLanes - 1), grp = lane / kGroupLanes;
     const unsigned gmask = ((1u << kGroupLanes) - 1u) << (grp * kGroupLanes);
     const int t = (blockIdx.x * kPropWarps + wl) * (32 / kGroupLanes) + grp;
+    // ---- static during the level: fetched while the previous step is still running
     const double two_m = (double)off[n];
     int i = -1, s = 0, d = 0;
     if (b0 + t < b1) {
@@ -307,16 +330,22 @@ __global__ void __launch_bounds__(kPropWarps * 32, 10) k_lv_propose_g(const int3
         d = off[i + 1] - s;
     }
     const bool big = d > kGroupLanes * kPerLane;
+    int a[kPerLane];
+#pragma unroll
+    for (int j = 0; j < kPerLane; j++) {
+        const int e = j * kGroupLanes + gl;
+        a[j] = (!big && e < d) ? adj[s + e] : -1;
+    }
+    pdl_wait();
+    // only now: the successor may become resident (and prefetch ITS static data) while this step works -- triggering before
+    // the wait would let the whole chain of future steps pile up on the SMs as waiting CTAs and starve the main stream
+    pdl_launch_dependents();
+    if (__ldcg(counters + 1)) return;  // converged in an earlier round
     if (i >= 0 && !big) {  // uniform inside the group
         int res = -1;
         if (d > 0) {
             const int ci = __ldcg(comm + i);
-            int a[kPerLane], c[kPerLane];
-#pragma unroll
-            for (int j = 0; j < kPerLane; j++) {
-                const int e = j * kGroupLanes + gl;
-                a[j] = e < d ? adj[s + e] : -1;
-            }
+            int c[kPerLane];
 #pragma unroll
             for (int j = 0; j < kPerLane; j++) c[j] = a[j] >= 0 ? __ldcg(comm + a[j]) : -1 - (j * kGroupLanes + gl);  // unique sentinels
             double tt[kPerLane];
@@ -379,14 +408,19 @@ __global__ void __launch_bounds__(kPropWarps * 32, 10) k_lv_propose_g(const int3
 __global__ void k_lv_apply(const int32_t *__restrict__ off, int32_t *__restrict__ comm, double *__restrict__ tot,
                            int32_t *__restrict__ csize, const int32_t *__restrict__ bucket, int b0, int b1,
                            const int32_t *__restrict__ desired, int32_t *__restrict__ counters) {
-    if (counters[1]) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b0 + t >= b1) return;
-    const int i = bucket[b0 + t];
-    const int b = desired[i];
+    int i = -1;
+    double ki = 0.0;
+    if (b0 + t < b1) {  // static during the level
+        i = bucket[b0 + t];
+        ki = (double)(off[i + 1] - off[i]);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    if (i < 0 || __ldcg(counters + 1)) return;
+    const int b = __ldcg(desired + i);
     if (b < 0) return;
-    const int ci = comm[i];
-    const double ki = (double)(off[i + 1] - off[i]);
+    const int ci = __ldcg(comm + i);
     comm[i] = b;
     atomicAdd(tot + ci, -ki);
     atomicAdd(tot + b, ki);
@@ -397,11 +431,17 @@ __global__ void k_lv_apply(const int32_t *__restrict__ off, int32_t *__restrict_
 
 // a round that moved at most n / 512 nodes ends the level (the stragglers oscillate or trickle; the levels
 // above merge whole communities anyway)
-__global__ void k_lv_round_end(int32_t *__restrict__ counters, int n) {
-    if (counters[1]) return;
-    counters[2]++;
-    if (counters[0] <= (n >> 9)) counters[1] = 1;
-    counters[0] = 0;
+// loop != 0: the round is the body of a conditional WHILE node of the CUDA graph (cond = its handle): the loop ends with the
+// level instead of replaying the remaining rounds as no-op launches
+__global__ void k_lv_round_end(int32_t *__restrict__ counters, int n, int loop, cudaGraphConditionalHandle cond, int max_rounds) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (!counters[1]) {
+        counters[2]++;
+        if (counters[0] <= (n >> 9)) counters[1] = 1;
+        counters[0] = 0;
+    }
+    if (loop && (counters[1] || counters[2] >= max_rounds)) cudaGraphSetConditional(cond, 0);
 }
 
 // All rounds in ONE cooperative launch: the 500+ sub-round steps are separated by grid-wide barriers instead of
@@ -588,6 +628,7 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         if (n64 >= (1ll << 31) / (2 * k)) return dd_fail(h, DD_ERR_UNSUPPORTED, "louvain: graph too large for int32 offsets");
     }
     DD_TRY(lv_build_graph(h, k, lb));
+    if (h->ev_after_graph_build) DD_CUDA(h, cudaEventRecord(h->ev_after_graph_build, h->stream));  // the kNN lists are free again
     const int n = lb.n;
     int32_t *csize = lb.csize, *desired = lb.desired, *bucket = lb.bucket, *counters = lb.counters;
     if (h->lv_bucket_n != n || h->lv_bucket_seed != seed) {
@@ -643,10 +684,40 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         const bool timing = h->timing;
         const int64_t launches_before = h->launches;
         static const bool warp_per_node = getenv("DD_LOUVAIN_WARP") != nullptr;  // A/B: the round-1 propose kernel
+        static const bool pdl = !warp_per_node && getenv("DD_LOUVAIN_NO_PDL") == nullptr;  // programmatic dependent launches
+        // experiment: the shared-memory carve-out the small kernels ask for (percent of the maximum; an SM cannot run CTAs of
+        // kernels with different carve-outs at the same time, and the main stream's kernels use the maximum)
+        if (const char *cv = getenv("DD_LV_CARVEOUT")) {
+            const int pct = atoi(cv);
+            cudaFuncSetAttribute(k_lv_propose_g, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_lv_propose, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_lv_apply, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_lv_round_end, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
         h->timing = false;  // no event records inside the capture
-        DD_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        // DD_LOUVAIN_WHILE=1: ONE captured round as the body of a conditional WHILE node (ends when the level has converged);
+        // default: kMaxRounds unrolled rounds whose kernels return at once after convergence
+        static const bool use_while = getenv("DD_LOUVAIN_WHILE") != nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaGraphConditionalHandle cond = 0;
+        if (use_while) {
+            DD_CUDA(h, cudaGraphCreate(&graph, 0));
+            DD_CUDA(h, cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault));
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = cond;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            DD_CUDA(h, cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+            DD_CUDA(h, cudaStreamBeginCaptureToGraph(h->stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                     cudaStreamCaptureModeThreadLocal));
+        } else {
+            DD_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        }
         int rc = DD_OK;
-        for (int round = 0; round < kMaxRounds && rc == DD_OK; round++) {
+        const int rounds_captured = use_while ? 1 : kMaxRounds;
+        for (int round = 0; round < rounds_captured && rc == DD_OK; round++) {
             for (int c = 0; c < kColours && rc == DD_OK; c++) {
                 const int b0 = h->lv_colour_off[c], b1 = h->lv_colour_off[c + 1];
                 if (b1 == b0) continue;
@@ -656,24 +727,27 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
                                                                                         h->d_lv_tot, csize, bucket, b0, b1, n,
                                                                                         gamma, desired, counters);
                 else
-                    k_lv_propose_g<<<(unsigned)((b1 - b0 + kNodesPerCta - 1) / kNodesPerCta), kPropWarps * 32, 0, h->stream>>>(
-                        h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, csize, bucket, b0, b1, n, gamma, desired, counters);
+                    launch_step(k_lv_propose_g, (unsigned)((b1 - b0 + kNodesPerCta - 1) / kNodesPerCta), kPropWarps * 32, h->stream,
+                                pdl, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, csize, bucket, b0, b1, n, gamma, desired,
+                                counters);
                 rc = dd_launch_end(h, "lv_propose");
                 if (rc != DD_OK) break;
                 dd_launch_begin(h);
-                k_lv_apply<<<(unsigned)((b1 - b0 + 255) / 256), 256, 0, h->stream>>>(h->d_lv_off, h->d_lv_comm, h->d_lv_tot,
-                                                                                     csize, bucket, b0, b1, desired, counters);
+                launch_step(k_lv_apply, (unsigned)((b1 - b0 + 255) / 256), 256, h->stream, pdl, h->d_lv_off, h->d_lv_comm, h->d_lv_tot,
+                            csize, bucket, b0, b1, desired, counters);
                 rc = dd_launch_end(h, "lv_apply");
             }
             if (rc != DD_OK) break;
             dd_launch_begin(h);
-            k_lv_round_end<<<1, 1, 0, h->stream>>>(counters, n);
+            launch_step(k_lv_round_end, 1, 1, h->stream, pdl, counters, n, use_while ? 1 : 0, cond, (int)kMaxRounds);
             rc = dd_launch_end(h, "lv_round_end");
         }
-        cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        cudaGraph_t captured = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &captured);
+        if (!use_while) graph = captured;
         h->timing = timing;
         h->lv_graph_launches = h->launches - launches_before;
+        h->lv_graph_is_loop = use_while;
         h->launches = launches_before;
         if (rc != DD_OK) return rc;
         if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("louvain graph capture: ") + cudaGetErrorString(e));
@@ -692,7 +766,9 @@ int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed) 
         if (e != cudaSuccess) return dd_fail(h, DD_ERR_CUDA, std::string("louvain graph launch: ") + cudaGetErrorString(e));
     }
     DD_TRY(dd_launch_end(h, "lv_rounds_graph"));
-    h->launches += h->lv_graph_launches - 1;  // the replay runs every captured kernel
+    // the replay runs every captured kernel; the loop variant runs its one captured round once per round of the level (the
+    // count of the previous replay stands in: the host does not wait for this one)
+    h->launches += h->lv_graph_launches * (h->lv_graph_is_loop ? std::max(1, h->h_lv_rounds ? *h->h_lv_rounds : 1) : 1) - 1;
     if (!h->h_lv_rounds && cudaMallocHost(&h->h_lv_rounds, sizeof(int32_t)) != cudaSuccess) h->h_lv_rounds = nullptr;
     if (h->h_lv_rounds)  // rounds actually executed (the replay launches all kMaxRounds; converged rounds return at once)
         cudaMemcpyAsync(h->h_lv_rounds, counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);

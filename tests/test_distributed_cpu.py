@@ -214,3 +214,64 @@ def test_classifier_iteration_sharding_end_to_end_gloo_world2(mode):
     if mode is True:  # rank 1 keeps its own rows only
         np.testing.assert_array_equal(results[1][2][1:], g["all_scores"][1:])
         assert not results[1][2][0].any()
+
+
+def _cells_failure_worker(rank, world, port, q):
+    """distributed="cells": an iteration's failure is seen by the rank that owns it only (advisor finding, round 1) -- the
+    status must be made collective so that EVERY rank raises instead of one raising and the others hanging in the merge."""
+    import warnings
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from doubletdetection_b200 import BoostClassifier
+        from oracle import datasets
+
+        class FailingHandle:
+            def __init__(self, device=0):
+                self._comm_ready = True  # pretend the NCCL communicator exists
+
+            def upload_counts(self, csr):
+                pass
+
+            def shard_cells(self, on):
+                pass
+
+            def fit_iterations(self, parents, omega, **kw):
+                if rank == 1:
+                    raise NotImplementedError("libdd_b200: pca: rank-deficient range (Cholesky breakdown)")
+                n_iters, n_synth = parents.shape[:2]
+                return dict(scores=np.zeros((n_iters, 600)), log_p=np.zeros((n_iters, 600)),
+                            communities=np.zeros((n_iters, 600), np.int32),
+                            synth_communities=np.zeros((n_iters, n_synth), np.int32), stage_ms={"wall": 1.0})
+
+        _capi.Handle = FailingHandle
+        counts = datasets.structured_counts(600, 200, seed=2)
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                BoostClassifier(n_iters=2, clustering_algorithm="louvain", distributed="cells").fit(counts)
+            q.put((rank, "no error"))
+        except NotImplementedError as e:
+            q.put((rank, "own: " + str(e)))
+        except RuntimeError as e:
+            q.put((rank, "other: " + str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_cell_sharding_failure_is_collective_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cells_failure_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert results[1].startswith("own: ") and "Cholesky" in results[1]
+    assert results[0].startswith("other: ") and "another rank" in results[0]
