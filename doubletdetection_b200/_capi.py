@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -59,6 +59,10 @@ SIGNATURES = {
     "dd_abi_version": (ctypes.c_int, []),
     "dd_upload_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_i32p, c_i32p, c_f32p]),
     "dd_get_lib_size": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
+    "dd_hvg_variances": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
+    "dd_select_genes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i64p]),
+    "dd_counts_nnz": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
+    "dd_download_counts": (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_f32p]),
     "dd_create_doublets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i64p]),
     "dd_synth_nnz": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
     "dd_download_synthetics": (ctypes.c_int, [ctypes.c_void_p, c_i32p, c_i32p, c_f32p]),
@@ -355,6 +359,31 @@ class Handle:
         self.n_cells, self.n_genes = csr.shape
         self._check(self._lib.dd_upload_counts(self._h, self.n_cells, self.n_genes, _ptr(indptr, ctypes.c_int32),
                                                _ptr(indices, ctypes.c_int32), _ptr(data, ctypes.c_float)))
+
+    def hvg_variances(self):
+        """``gene_variances`` of fit()'s prologue (:166-169), float32, computed on the device in scipy's accumulation order."""
+        out = np.empty(self.n_genes, dtype=np.float32)
+        self._check(self._lib.dd_hvg_variances(self._h, _ptr(out, ctypes.c_float)))
+        return out
+
+    def select_genes(self, genes):
+        """``raw.tocsc()[:, genes].tocsr()`` (:173-175) on the device; the handle then holds the subset."""
+        genes = np.ascontiguousarray(genes, dtype=np.int64)
+        self._check(self._lib.dd_select_genes(self._h, genes.size, _ptr(genes, ctypes.c_int64)))
+        self.n_genes = int(genes.size)
+
+    def download_counts(self):
+        """The CSR the handle holds (after ``select_genes``: the subset) -- inspection / tests."""
+        import scipy.sparse as sp_sparse
+
+        nnz = ctypes.c_int64(0)
+        self._check(self._lib.dd_counts_nnz(self._h, ctypes.byref(nnz)))
+        indptr = np.empty(self.n_cells + 1, dtype=np.int32)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        data = np.empty(nnz.value, dtype=np.float32)
+        self._check(self._lib.dd_download_counts(self._h, _ptr(indptr, ctypes.c_int32), _ptr(indices, ctypes.c_int32),
+                                                 _ptr(data, ctypes.c_float)))
+        return sp_sparse.csr_matrix((data, indices, indptr), shape=(self.n_cells, self.n_genes))
 
     def lib_size(self):
         out = np.empty(self.n_cells, dtype=np.float32)

@@ -44,12 +44,13 @@ def _pca_solver(n_samples, n_features, n_components):
     return "full"
 
 
-def _pca_plan(n_samples, n_features, n_components, random_state):
+def _pca_plan(n_samples, n_features, n_components, random_state, arpack=False):
     """Test matrix and power-iteration count of sklearn's randomized SVD
     (sklearn/utils/extmath.py:323-333, 584-587): Omega = RandomState(seed).normal((G, C + 10)) cast to
     float32 (one row per cell instead when there are fewer augmented cells than genes), 7 iterations when
-    C < 0.1 * min(shape) else 4."""
-    solver = _pca_solver(n_samples, n_features, n_components)
+    C < 0.1 * min(shape) else 4.  ``arpack``: the reference's sparse branch (pseudocount == 1 without scaling,
+    doubletdetection.py:296-297, 308) asks for the EXACT truncated SVD whatever the shape."""
+    solver = "arpack" if arpack else _pca_solver(n_samples, n_features, n_components)
     if solver != "randomized":
         return None, 0  # exact PCA (covariance_eigh / full): _exact_pca, no test matrix
     n_power_iter = 7 if n_components < 0.1 * min(n_samples, n_features) else 4
@@ -67,10 +68,14 @@ def _exact_pca(h, n_components):
     The device computes the float64 Gram matrix of the centred matrix on its smaller side and the projection of all
     augmented cells; the <= 1000 x 1000 symmetric eigenproblem in between is LAPACK on the host (O(G^3), independent of
     the number of cells -- the same routine sklearn calls).  Leaves the embedding on the device for ``knn``."""
+    from scipy.linalg import eigh
+
     n_rows, n_genes = h._dense_rows, h.n_genes
     c = int(n_components)
     if n_genes <= n_rows:
-        w, v = np.linalg.eigh(h.centered_gram(False))  # ascending eigenvalues of (A - 1) * covariance
+        # the top c eigenpairs of (A - 1) * covariance (LAPACK dsyevr; ascending order)
+        w, v = eigh(h.centered_gram(False), subset_by_index=[max(n_genes - c, 0), n_genes - 1], overwrite_a=True,
+                    check_finite=False)
         v = np.ascontiguousarray(v[:, ::-1][:, :c])
         top = np.argmax(np.abs(v), axis=0)
         v *= np.sign(v[top, np.arange(v.shape[1])])[None, :]
@@ -297,8 +302,12 @@ class BoostClassifier:
             # "louvain": unweighted pattern of the kNN graph (:337-338); "leiden": umap-weighted graph, iterated until
             # stable (:339-340, sc.tl.leiden's use_weights=True / n_iterations=-1) on the host workers
             cluster_kw = dict(clustering=self.clustering_algorithm, resolution=float(self.clustering_kwargs["resolution"]))
-        if self.pseudocount == 1:
-            raise NotImplementedError("pseudocount=1 selects the sparse log1p + arpack path (:296-297, :308), which is not on the B200 hot path")
+        # pseudocount == 1 is the reference's SPARSE branch (:296-297): log1p keeps the matrix sparse and :308 asks
+        # sc.tl.pca for svd_solver="arpack", i.e. the exact truncated SVD of the centred matrix -- unless standard_scaling
+        # densifies it first (sc.pp.scale zero-centres), which puts the dense "auto" solver back in charge.  Here the
+        # matrix is dense on the device either way (log1p(0) = 0 fills the gaps); what changes is the PCA: the exact branch
+        # (float64 Gram matrix on the smaller side + LAPACK, _exact_pca) instead of the randomized one.
+        arpack = self.pseudocount == 1 and self.standard_scaling is not True
 
         import time as _time
 
@@ -311,7 +320,12 @@ class BoostClassifier:
                 print("Sparsifying matrix.")
             raw_counts = csr_matrix(raw_counts)
 
-        if self.n_top_var_genes > 0 and self.n_top_var_genes < raw_counts.shape[1]:  # :165-176
+        # :165-176 highly variable genes.  Canonical CSR input: variances and the column subset are computed on the device
+        # from the uploaded matrix (hvg.cu reproduces scipy's float32 accumulation order; the argsort stays numpy's, so ties
+        # break as in the reference).  A matrix with duplicate or unsorted entries takes the reference's own scipy lines.
+        hvg = self.n_top_var_genes > 0 and self.n_top_var_genes < raw_counts.shape[1]
+        hvg_on_device = hvg and raw_counts.has_canonical_format and os.environ.get("DD_HVG_HOST") is None
+        if hvg and not hvg_on_device:
             gene_variances = (
                 np.array(raw_counts.power(2).mean(axis=0)) - (np.array(raw_counts.mean(axis=0))) ** 2
             )[0]
@@ -323,18 +337,33 @@ class BoostClassifier:
             raw_counts.sum_duplicates()
 
         num_cells, num_genes = raw_counts.shape
+        if hvg_on_device:
+            num_genes = int(self.n_top_var_genes)
         self._num_cells, self._num_genes = num_cells, num_genes
         num_synths = int(self.boost_rate * num_cells)  # :391
         n_aug = num_cells + num_synths
-        omega, n_power_iter = _pca_plan(n_aug, num_genes, self.n_components, self.random_state)
+        omega, n_power_iter = _pca_plan(n_aug, num_genes, self.n_components, self.random_state, arpack=arpack)
+        if omega is None and min(n_aug, num_genes) > 16384:
+            raise NotImplementedError(
+                f"exact PCA (pseudocount=1 selects svd_solver='arpack') of a {n_aug} x {num_genes} matrix: the float64 Gram "
+                "matrix on the smaller side is limited to 16384 rows; lower n_top_var_genes or use another pseudocount")
 
         _t.append(_time.perf_counter())
         h = self._native()
+
+        def upload():
+            h.upload_counts(raw_counts)
+            if hvg_on_device:
+                gene_variances = h.hvg_variances()  # :166-169
+                top_var_indexes = np.argsort(gene_variances)  # :170
+                self.top_var_genes_ = top_var_indexes[-self.n_top_var_genes:]  # :171
+                h.select_genes(self.top_var_genes_)  # :173-175
+
         # the host->device copy of the counts (ctypes releases the GIL) runs underneath the parent draws
         from concurrent.futures import ThreadPoolExecutor
 
         with ThreadPoolExecutor(max_workers=1) as pool:
-            upload = pool.submit(h.upload_counts, raw_counts)
+            upload = pool.submit(upload)
             # every iteration's `choices` (:394), drawn sequentially from the classifier's stream
             parents = np.empty((self.n_iters, num_synths, 2), dtype=np.int64)
             for i in range(self.n_iters):

@@ -177,7 +177,9 @@ __global__ void k_synth_fill(const int32_t *__restrict__ indptr, const int32_t *
 //   float32 data by the float32 median (:293), numpy adds the pseudocount and takes the float32 log (:295).
 __device__ __forceinline__ float norm_log(float x, double l1, float median, float pc) {
     const float normed = l1 != 0.0 ? (float)((double)x / l1) : x;
-    return logf(__fadd_rn(__fmul_rn(normed, median), pc));
+    const float scaled = __fmul_rn(normed, median);
+    // pseudocount == 1 is the reference's sparse branch: np.log1p on the stored entries (:296-297), log(1) = 0 elsewhere
+    return pc == 1.0f ? log1pf(scaled) : logf(__fadd_rn(scaled, pc));
 }
 
 // lower_bound of `col` in the sorted index range [s, e); returns e if absent / position of first >= col
@@ -846,6 +848,8 @@ int grid_for(dd_handle *h, size_t smem_bytes) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+int dd_finish_upload(dd_handle *h);
+
 extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32_t *indptr,
                                 const int32_t *indices, const float *data) {
     if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_upload_counts: null handle");
@@ -883,6 +887,12 @@ extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, 
         DD_CUDA(h, cudaMemcpyAsync(h->d_indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->stream));
         DD_CUDA(h, cudaMemcpyAsync(h->d_data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->stream));
     }
+    return dd_finish_upload(h);
+}
+
+// _lib_size (:182) + L1 sums + sign check of the CSR the handle holds (uploaded, or subset on the device by dd_select_genes)
+int dd_finish_upload(dd_handle *h) {
+    const int64_t n_cells = h->N;
     const int grid = h->num_sms * 8;
     int *d_neg = reinterpret_cast<int *>(h->d_l1 + n_cells);  // one spare slot behind the L1 sums
     DD_CUDA(h, cudaMemsetAsync(d_neg, 0, sizeof(int), h->stream));
@@ -1106,8 +1116,6 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
 
 extern "C" int dd_normalise_log(dd_handle *h, float median, float pseudocount) {
     if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_normalise_log: null handle");
-    if (pseudocount == 1.0f)
-        return dd_fail(h, DD_ERR_UNSUPPORTED, "pseudocount == 1 (sparse log1p + arpack path) is not on the B200 hot path");
     DD_CUDA(h, cudaSetDevice(h->device));
     DD_TRY(dd_stage_begin(h));
     DD_TRY(dd_dev_build_dense(h, median, pseudocount));

@@ -12,7 +12,7 @@
 
 #include "../../include/dd_b200.h"
 
-#define DD_ABI_VERSION 5
+#define DD_ABI_VERSION 6
 
 // padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
 static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -43,6 +43,11 @@ struct dd_lv_lane {
     int32_t *d_lvw_i32 = nullptr;
     int64_t cap_lvw_nnz = 0, cap_lvw_n = 0, lvw_bucket_n = -1;
     uint64_t lvw_bucket_seed = 0;
+    void *lvw_graph_exec = nullptr;
+    int64_t lvw_graph_n = -1, lvw_graph_launches = 0;
+    double lvw_graph_gamma = 0.0;
+    uint64_t lvw_graph_seed = 0;
+    const void *lvw_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t lv_bucket_n = -1;
     uint64_t lv_bucket_seed = 0;
     int32_t *h_lv_rounds = nullptr;
@@ -149,6 +154,11 @@ struct dd_handle {
     int64_t cap_lvw_nnz = 0, cap_lvw_n = 0, lvw_bucket_n = -1;
     uint64_t lvw_bucket_seed = 0;
     std::vector<int32_t> lvw_colour_off;
+    void *lvw_graph_exec = nullptr;  // cudaGraphExec_t of the captured weighted round sequence (louvain_gpu_w.cu)
+    int64_t lvw_graph_n = -1, lvw_graph_launches = 0;
+    double lvw_graph_gamma = 0.0;
+    uint64_t lvw_graph_seed = 0;
+    const void *lvw_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};  // buffer addresses baked into the capture
     int64_t lv_bucket_n = -1;
     uint64_t lv_bucket_seed = 0;
     std::vector<int32_t> lv_colour_off;

@@ -47,8 +47,6 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
         return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: bad iteration range");
     if (p->n_synth < 0 || (p->n_synth > 0 && (!parents || !synth_communities_out)))
         return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: bad n_synth / parents");
-    if (p->pseudocount == 1.0f)
-        return dd_fail(h, DD_ERR_UNSUPPORTED, "pseudocount == 1 (sparse log1p + arpack path) is not on the B200 hot path");
     if (p->knn_k < 2) return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: knn_k < 2");
     if (p->clustering != DD_CLUSTER_LOUVAIN && p->clustering != DD_CLUSTER_PHENOGRAPH && p->clustering != DD_CLUSTER_LEIDEN)
         return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: unknown clustering");
@@ -56,8 +54,9 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     // Leiden works on umap's weighted graph, whose weights come from the kNN DISTANCES: the lists + distances of every
     // iteration go to the host workers, which build the fuzzy simplicial set and partition it (leiden.cpp)
     const bool leiden = p->clustering == DD_CLUSTER_LEIDEN;
-    // experimental (never run on hardware): PhenoGraph's first Louvain level on the device, in fixed point (louvain_gpu_w.cu)
-    static const bool pheno_level0 = getenv("DD_PHENO_LEVEL0") != nullptr;
+    // PhenoGraph's first Louvain level on the device, in fixed point (louvain_gpu_w.cu); DD_PHENO_LEVEL0=0: the host twin
+    // of that level runs on the workers instead (same communities, A/B timing only)
+    static const bool pheno_level0 = !(getenv("DD_PHENO_LEVEL0") && atoi(getenv("DD_PHENO_LEVEL0")) == 0);
     if (pheno && (p->pheno_k < 1 || p->pheno_k > 30))
         return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_fit_iterations: phenograph k must be in [1, 30]");
     DD_CUDA(h, cudaSetDevice(h->device));
@@ -68,7 +67,8 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     // the host side of a Louvain iteration (aggregate ~10^2 communities, upper levels, scoring) is a few milliseconds, so
     // a few workers keep up with the GPU; PhenoGraph and Leiden partition the whole graph on the host (0.2 s and more per
     // iteration at 100k cells) and are host-bound: they may use more workers
-    const int n_threads = std::max(1, std::min(p->n_host_threads, (pheno || leiden) ? 16 : 8));
+    // (each worker owns a pinned result slot -- 90 MB for PhenoGraph at 125 k cells -- hence the upper bounds)
+    const int n_threads = std::max(1, std::min(p->n_host_threads, (pheno || leiden) ? 32 : 16));
     const int n_slots = n_threads + 2;
     const int64_t max_nnz = A * 2 * (k - 1);
     const int64_t w_off = ((A + 1) + A + max_nnz + 1) / 2 * 2;  // weights start 8-byte aligned

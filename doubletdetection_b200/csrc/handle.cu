@@ -142,6 +142,10 @@ void dd_lv_swap(dd_handle *h, dd_lv_lane &l) {
     std::swap(h->lv_graph_n, l.lv_graph_n); std::swap(h->lv_graph_launches, l.lv_graph_launches);
     std::swap(h->lv_graph_is_loop, l.lv_graph_is_loop); std::swap(h->lv_graph_gamma, l.lv_graph_gamma);
     std::swap(h->lv_graph_seed, l.lv_graph_seed);
+    std::swap(h->lvw_graph_exec, l.lvw_graph_exec); std::swap(h->lvw_graph_n, l.lvw_graph_n);
+    std::swap(h->lvw_graph_launches, l.lvw_graph_launches); std::swap(h->lvw_graph_gamma, l.lvw_graph_gamma);
+    std::swap(h->lvw_graph_seed, l.lvw_graph_seed);
+    for (int i = 0; i < 4; i++) std::swap(h->lvw_graph_key[i], l.lvw_graph_key[i]);
 }
 
 void dd_lv_lane_free(dd_lv_lane &l) {
@@ -150,6 +154,7 @@ void dd_lv_lane_free(dd_lv_lane &l) {
                     (void *)l.d_lv_w, (void *)l.d_lvw_wq, (void *)l.d_lvw_i64, (void *)l.d_lvw_i32})
         if (p) cudaFree(p);
     if (l.lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)l.lv_graph_exec);
+    if (l.lvw_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)l.lvw_graph_exec);
     if (l.h_lv_rounds) cudaFreeHost(l.h_lv_rounds);
     if (l.stream) cudaStreamDestroy(l.stream);
     l = dd_lv_lane();
@@ -171,6 +176,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     dd_tc_free(h);
     dd_comm_destroy(h);
     if (h->lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lv_graph_exec);
+    if (h->lvw_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lvw_graph_exec);
     for (int32_t *p : h->slot_knn) cudaFreeHost(p);
     for (double *p : h->slot_flag) cudaFreeHost(p);
     if (h->h_lv_rounds) cudaFreeHost(h->h_lv_rounds);

@@ -550,8 +550,9 @@ int phenograph_finish(Graph &g, uint64_t seed, int32_t min_cluster_size, int32_t
                       const int32_t *comm0 = nullptr) {
     const int32_t n = g.n;
     int32_t nc = 0;
-    // standard modularity; labels by decreasing size.  comm0: first level already done (device, fixed-point weights)
-    const int rc = run_louvain(g, 1.0, seed, labels_out, &nc, comm0, false);
+    // standard modularity; labels by decreasing size.  The first level is the synchronous coloured one on fixed-point
+    // weights (oracle/louvain_ref.py:level0_parallel): comm0 = already done on the device, else its host twin runs here
+    const int rc = run_louvain(g, 1.0, seed, labels_out, &nc, comm0, /*parallel0=*/comm0 == nullptr);
     if (rc != DD_OK) return rc;
     std::vector<int64_t> size(std::max(nc, 1), 0);
     for (int32_t i = 0; i < n; i++) size[labels_out[i]]++;

@@ -116,7 +116,7 @@ extern "C" int dd_centered_gram(dd_handle *h, int32_t transposed, double *out) {
     DD_CUDA(h, cudaSetDevice(h->device));
     const int64_t A = h->A, G = h->G;
     const int64_t n = transposed ? A : G, red = transposed ? G : A;
-    if (n > 4096) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_centered_gram: more than 4096 rows / columns on the Gram side");
+    if (n > 16384) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_centered_gram: more than 16384 rows / columns on the Gram side");
     DD_TRY(dd_stage_begin(h));
     DD_TRY(dd_dev_colstats(h, false));
     double *d_mean = nullptr, *d_out = nullptr;

@@ -53,6 +53,20 @@ int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32
 /* `_lib_size` (float32[N]) as computed on the device. */
 int dd_get_lib_size(dd_handle *h, float *lib_size_out);
 
+/* ---- fit() prologue, highly variable genes, doubletdetection.py:165-176 -----------------
+ * dd_hvg_variances: `gene_variances` (:166-169) of the uploaded matrix, float32[G], bit for bit what scipy's
+ * `raw.power(2).mean(axis=0) - raw.mean(axis=0) ** 2` returns (one float32 accumulator per gene, entries added in row
+ * order after the multiplication by float32(1/N)).  The caller runs `np.argsort(...)[-n_top:]` (:170-171: numpy's own
+ * sort decides ties) and hands the result to
+ * dd_select_genes: `raw = raw.tocsc()[:, top_var_genes_].tocsr()` (:173-175) on the device -- column j of the new
+ * matrix is gene genes[j], rows keep sorted column ids -- followed by `_lib_size` (:182) of the subset. */
+int dd_hvg_variances(dd_handle *h, float *variances_out);
+int dd_select_genes(dd_handle *h, int64_t n_selected, const int64_t *genes);
+/* The count matrix the handle holds (after dd_select_genes: the subset), for inspection: nnz, then indptr int32[N+1],
+ * indices int32[nnz], data float[nnz]. */
+int dd_counts_nnz(dd_handle *h, int64_t *nnz_out);
+int dd_download_counts(dd_handle *h, int32_t *indptr_out, int32_t *indices_out, float *data_out);
+
 /* ---- _createDoublets(), doubletdetection.py:397-399 ------------------------------------
  * parents: int64[M*2] (the `choices` array of :394, drawn by the caller from its PCG64 stream).
  * Builds `_raw_synthetics` = raw[parents[:,0]] + raw[parents[:,1]] as canonical CSR on the

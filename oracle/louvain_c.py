@@ -31,6 +31,10 @@ def _load():
         _lib.louvain_ref_parallel0.argtypes = [
             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p,
         ]
+        _lib.louvain_ref_parallel0_w.restype = ctypes.c_int64
+        _lib.louvain_ref_parallel0_w.argtypes = [
+            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p,
+        ]
     return _lib
 
 
@@ -43,10 +47,12 @@ def louvain(indptr, indices, weights=None, resolution=1.0, seed=0, level0="seque
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     out = np.empty(max(n, 1), dtype=np.int64)
     if level0 == "parallel":
-        if w is not None:
-            raise ValueError("the parallel first level is defined for unweighted graphs")
-        lib.louvain_ref_parallel0(n, indptr.ctypes.data, indices.ctypes.data, float(resolution),
-                                  int(seed) & ((1 << 64) - 1), out.ctypes.data)
+        if w is not None:  # fixed-point first level (oracle/louvain_ref.py:level0_parallel with weights)
+            lib.louvain_ref_parallel0_w(n, indptr.ctypes.data, indices.ctypes.data, w.ctypes.data, float(resolution),
+                                        int(seed) & ((1 << 64) - 1), out.ctypes.data)
+        else:
+            lib.louvain_ref_parallel0(n, indptr.ctypes.data, indices.ctypes.data, float(resolution),
+                                      int(seed) & ((1 << 64) - 1), out.ctypes.data)
         return out[:n]
     lib.louvain_ref(
         n, indptr.ctypes.data, indices.ctypes.data, None if w is None else w.ctypes.data,

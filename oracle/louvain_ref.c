@@ -8,6 +8,7 @@
  *
  * Build: gcc -O2 -ffp-contract=off -shared -fPIC -o oracle/_build/liblouvain_ref.so oracle/louvain_ref.c
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -169,36 +170,49 @@ static uint64_t colour_of(uint64_t seed, int64_t i) {
     return z % N_COLOURS;
 }
 
-static void level0_parallel(const graph *g, double gamma, double two_m, uint64_t seed, int64_t *comm) {
-    int64_t n = g->n;
-    double *k = (double *)malloc(sizeof(double) * n);
-    double *tot = (double *)malloc(sizeof(double) * n);
+/* weights == NULL: unit weights (two_m = number of entries); else the fixed-point flavour: wq = rint(w * 2^32) in int64,
+ * every sum exact, two_m = sum of wq (the argument is ignored). */
+static void level0_parallel(const graph *g, const double *weights, double gamma, double two_m, uint64_t seed, int64_t *comm) {
+    int64_t n = g->n, nnz = g->indptr[n];
+    int64_t *wq = (int64_t *)malloc(sizeof(int64_t) * (nnz > 0 ? nnz : 1));
+    int64_t *k = (int64_t *)malloc(sizeof(int64_t) * n);
+    int64_t *tot = (int64_t *)malloc(sizeof(int64_t) * n);
     int64_t *size = (int64_t *)malloc(sizeof(int64_t) * n);
     int64_t *desired = (int64_t *)malloc(sizeof(int64_t) * n);
     unsigned char *col = (unsigned char *)malloc(n);
-    double *cnt = (double *)calloc(n, sizeof(double)); /* w(i, c) scratch, indexed by community */
+    int64_t *cnt = (int64_t *)calloc(n, sizeof(int64_t)); /* w(i, c) scratch, indexed by community */
+    if (weights) {
+        int64_t s = 0;
+        for (int64_t e = 0; e < nnz; e++) { wq[e] = (int64_t)rint(weights[e] * 4294967296.0); s += wq[e]; }
+        two_m = (double)s;
+    } else {
+        for (int64_t e = 0; e < nnz; e++) wq[e] = 1;
+    }
     for (int64_t i = 0; i < n; i++) {
-        k[i] = (double)(g->indptr[i + 1] - g->indptr[i]);
+        int64_t s = 0;
+        for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) s += wq[e];
+        k[i] = s;
         tot[i] = k[i]; size[i] = 1; comm[i] = i; col[i] = (unsigned char)colour_of(seed, i);
     }
-    for (int round = 0; round < MAX_ROUNDS; round++) {
+    for (int round = 0; round < MAX_ROUNDS && two_m > 0.0; round++) {
         int64_t moved = 0;
         for (int c = 0; c < N_COLOURS; c++) {
             /* decide from the frozen state */
             for (int64_t i = 0; i < n; i++) {
                 desired[i] = -1;
-                if (col[i] != c || k[i] == 0.0) continue;
+                if (col[i] != c || g->indptr[i + 1] == g->indptr[i]) continue;
                 int64_t ci = comm[i];
-                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) cnt[comm[g->indices[e]]] += 1.0;
-                double gain_stay = cnt[ci] - ((gamma * k[i]) * (tot[ci] - k[i])) / two_m;
+                double gk = gamma * (double)k[i];
+                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) cnt[comm[g->indices[e]]] += wq[e];
+                double gain_stay = (double)cnt[ci] - (gk * (double)(tot[ci] - k[i])) / two_m;
                 int64_t best = -1; double best_gain = 0.0;
                 for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) {
                     int64_t cc = comm[g->indices[e]];
                     if (cc == ci) continue;
-                    double gn = cnt[cc] - ((gamma * k[i]) * tot[cc]) / two_m;
+                    double gn = (double)cnt[cc] - (gk * (double)tot[cc]) / two_m;
                     if (best < 0 || gn > best_gain || (gn == best_gain && cc < best)) { best = cc; best_gain = gn; }
                 }
-                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) cnt[comm[g->indices[e]]] = 0.0;
+                for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; e++) cnt[comm[g->indices[e]]] = 0;
                 if (best >= 0 && best_gain > gain_stay && !(size[ci] == 1 && size[best] == 1 && best > ci))
                     desired[i] = best;
             }
@@ -211,7 +225,7 @@ static void level0_parallel(const graph *g, double gamma, double two_m, uint64_t
         }
         if (moved <= (n >> 9)) break; /* at most n / 512 moves: the level is settled */
     }
-    free(k); free(tot); free(size); free(desired); free(col); free(cnt);
+    free(wq); free(k); free(tot); free(size); free(desired); free(col); free(cnt);
 }
 
 typedef struct { int64_t size; int64_t fa; } comm_rank;
@@ -237,6 +251,12 @@ int64_t louvain_ref_parallel0(int64_t n, const int64_t *indptr, const int64_t *i
     return louvain_impl(n, indptr, indices, NULL, resolution, seed, labels_out, 1);
 }
 
+/* the same with weights (PhenoGraph's Jaccard graph): fixed-point first level, double weights above it */
+int64_t louvain_ref_parallel0_w(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
+                                double resolution, uint64_t seed, int64_t *labels_out) {
+    return louvain_impl(n, indptr, indices, weights, resolution, seed, labels_out, 1);
+}
+
 static int64_t louvain_impl(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                             double resolution, uint64_t seed, int64_t *labels_out, int parallel0) {
     graph g;
@@ -255,7 +275,7 @@ static int64_t louvain_impl(int64_t n, const int64_t *indptr, const int64_t *ind
     sm64 rng; rng.s = seed;
     if (two_m > 0.0 && parallel0) {
         int64_t *comm = (int64_t *)malloc(sizeof(int64_t) * (n > 0 ? n : 1));
-        level0_parallel(&g, resolution, two_m, seed, comm);
+        level0_parallel(&g, weights, resolution, two_m, seed, comm);
         graph ng;
         int64_t *node2new = (int64_t *)malloc(sizeof(int64_t) * (n > 0 ? n : 1));
         aggregate(&g, comm, &ng, node2new);

@@ -292,7 +292,7 @@ def jaccard_graph(nbr_idx, prune=True):
     return S
 
 
-def phenograph_cluster(X_pca, k=30, prune=True, min_cluster_size=10, seed=0, louvain_fn=None, level0="sequential"):
+def phenograph_cluster(X_pca, k=30, prune=True, min_cluster_size=10, seed=0, louvain_fn=None, level0="parallel"):
     """``phenograph.cluster(X_pca, n_jobs=..., prune=...)[0]`` -- doubletdetection.py:320 (defaults k=30,
     jaccard=True, min_cluster_size=10): exact k+1 nearest neighbours, self dropped; Jaccard graph; Louvain on the
     weighted graph (standard modularity = resolution 1); communities numbered by decreasing size, those NOT larger
@@ -302,8 +302,8 @@ def phenograph_cluster(X_pca, k=30, prune=True, min_cluster_size=10, seed=0, lou
     idx, _ = knn_brute(np.asarray(X_pca), k + 1)
     G = jaccard_graph(idx[:, 1:], prune=prune)
     fn = louvain_fn or louvain_ref.louvain
-    # level0="parallel": the first level by synchronous coloured rounds on fixed-point weights -- what the fit loop will run
-    # once that level exists on the device; today's product and goldens use the sequential sweep
+    # level0="parallel" (the specification the product and the goldens follow): the first level by synchronous coloured rounds
+    # on fixed-point weights, which the fit loop runs on the device (louvain_gpu_w.cu); "sequential": the classic sweep
     kw = {} if level0 == "sequential" else {"level0": level0}
     labels = np.asarray(fn(G.indptr, G.indices, G.data, resolution=1.0, seed=int(seed), **kw), dtype=np.int64).copy()
     sizes = np.bincount(labels, minlength=labels.max() + 1 if labels.size else 0)

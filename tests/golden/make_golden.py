@@ -60,7 +60,8 @@ def run_case(name, counts, predict_kw, capture_iter0=True, **clf_kw):
         out["synth0_indptr"] = s0.indptr
         out["synth0_indices"] = s0.indices
         out["synth0_data"] = s0.data
-        out["pca_input0"] = np.asarray(record["pca_input"][0], dtype=np.float32)
+        pca_in = record["pca_input"][0]
+        out["pca_input0"] = np.asarray(pca_in.toarray() if hasattr(pca_in, "toarray") else pca_in, dtype=np.float32)
         out["n_counts0"] = np.asarray(record["n_counts"][0])
         out["X_pca0"] = record["X_pca"][0]
         out["knn_indices0"] = record["knn_indices"][0].astype(np.int32)
@@ -99,6 +100,11 @@ def main():
     st2 = datasets.structured_counts(900, 200, seed=77)
     run_case("structured_900x200_phenograph", st2, dict(p_thresh=1e-3, voter_thresh=0.5), capture_iter0=False, n_iters=2,
              clustering_algorithm="phenograph", clustering_kwargs={"prune": False})
+    # the sparse branch: pseudocount == 1 keeps the matrix sparse (np.log1p, :296-297) and sc.tl.pca gets
+    # svd_solver="arpack" (:308) -- through the reference's real control flow; PCA = the installed sklearn's arpack solver
+    st3 = datasets.structured_counts(1200, 260, seed=5)
+    run_case("structured_1200x260_pc1", st3, dict(p_thresh=1e-3, voter_thresh=0.5), n_iters=2, clustering_algorithm="louvain",
+             pseudocount=1)
 
 
 if __name__ == "__main__":

@@ -76,8 +76,6 @@ def test_unsupported_paths_fail_loudly():
         with pytest.raises(NotImplementedError):
             BoostClassifier(n_iters=2, clustering_kwargs={"nn_method": "brute"}).fit(x)
         with pytest.raises(NotImplementedError):
-            BoostClassifier(n_iters=2, clustering_algorithm="louvain", pseudocount=1).fit(x)
-        with pytest.raises(NotImplementedError):
             BoostClassifier(n_iters=2, clustering_algorithm="louvain", normalizer=lambda c: c).fit(x)
     with pytest.raises(ValueError):  # sklearn check_array, as in the reference (:149-155)
         BoostClassifier(n_iters=2, clustering_algorithm="louvain").fit(np.full((50, 20), np.nan))

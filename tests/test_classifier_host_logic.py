@@ -29,6 +29,13 @@ class OracleHandle:
         self.raw = csr.copy()
         self.n_cells, self.n_genes = csr.shape
 
+    def hvg_variances(self):  # what hvg.cu reproduces: the reference's own scipy expression (doubletdetection.py:166-169)
+        return (np.array(self.raw.power(2).mean(axis=0)) - (np.array(self.raw.mean(axis=0))) ** 2)[0]
+
+    def select_genes(self, genes):  # :173-175
+        self.raw = self.raw.tocsc()[:, np.asarray(genes)].tocsr()
+        self.n_cells, self.n_genes = self.raw.shape
+
     def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10, resolution=4.0,
                        seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0, clustering="louvain",
                        pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10):

@@ -109,3 +109,79 @@ def test_classifier_with_1000_top_var_genes(handle, algo):
     # whose mean is far from 0): its embedding is 1e-3 .. 1e-2 away from the float64 truth, so the oracle's own partition is
     # the noisy side here (measured on B200: adjusted Rand 0.68 for louvain at resolution 4)
     assert min(ari) > 0.5
+
+
+# ---------------------------------------------------------------- pseudocount == 1: the reference's sparse / arpack branch
+def test_pseudocount1_stages_vs_reference_golden(handle):
+    """doubletdetection.py:296-297, 308 through the reference's real control flow (golden ``structured_1200x260_pc1``): the
+    dense log1p matrix equals the reference's sparse one, and the exact PCA is within 1e-4 of the float64 truth (sklearn's own
+    float32 ARPACK run, the golden's X_pca, is 7e-5 away from that truth)."""
+    from conftest import golden_case, load_golden
+
+    from doubletdetection_b200.classifier import _exact_pca
+
+    g = load_golden("structured_1200x260_pc1")
+    counts, kw, _ = golden_case("structured_1200x260_pc1")
+    pro = reference_path.prologue(counts, 10000)
+    handle.upload_counts(pro["raw"])
+    handle.create_doublets(g["parents"][0])
+    handle.normalise_log(handle.median_lib_size(), 1.0)
+    dense = handle.download_dense()
+    np.testing.assert_allclose(dense, g["pca_input0"], rtol=3e-6, atol=1e-7)
+    assert (dense[g["pca_input0"] == 0] == 0).all()  # log1p(0): the sparse matrix's gaps are exact zeros
+    emb = _exact_pca(handle, 30)
+    truth, _ = pca_f64.exact_pca_f64(dense, 30)
+    err = np.abs(emb - truth).max() / np.abs(truth).max()
+    err_ref = np.abs(g["X_pca0"] - truth).max() / np.abs(truth).max()
+    print(f"\n[pseudocount=1] GPU exact PCA vs f64 truth {err:.2e}; the reference's ARPACK (float32) vs f64 truth {err_ref:.2e}")
+    assert err < 1e-4
+    np.testing.assert_allclose(emb, g["X_pca0"], atol=5e-4 * np.abs(truth).max())
+
+
+@pytest.mark.parametrize("shape,n_top", [((1200, 260), 10000), ((6000, 3000), 10000)])
+def test_classifier_pseudocount1_chain_vs_oracle(handle, shape, n_top):
+    """BoostClassifier(pseudocount=1): parents bit-exact; the oracle's downstream stages on the GPU's exact embedding
+    reproduce communities and scores of every iteration; end to end against the reference golden / the oracle's ARPACK run
+    the communities agree up to the drift of its float32 solver."""
+    from sklearn.metrics import adjusted_rand_score
+
+    from doubletdetection_b200 import BoostClassifier
+    from doubletdetection_b200.classifier import _exact_pca
+
+    counts = datasets.structured_counts(*shape, seed=5)
+    kw = dict(n_iters=2, clustering_algorithm="louvain", pseudocount=1, random_state=0, n_top_var_genes=n_top)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(**kw).fit(counts)
+        ora = reference_path.OracleClassifier(louvain_fn=louvain_c.louvain, **kw).fit(counts)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    n = counts.shape[0]
+    handle.upload_counts(reference_path.prologue(counts, n_top)["raw"])
+    for i in range(2):
+        handle.create_doublets(np.asarray(clf._parents_array[i]))
+        handle.normalise_log(handle.median_lib_size(), 1.0)
+        emb = _exact_pca(handle, 30)
+        idx, _ = upstream.knn_brute(emb, 10)
+        gph = upstream.knn_pattern_graph(idx)
+        labels = louvain_c.louvain(gph.indptr, gph.indices, None, resolution=4.0, seed=0, level0="parallel")
+        np.testing.assert_array_equal(clf.communities_[i], labels[:n])
+        s, lp, _, _ = reference_path.score_communities(labels, n)
+        np.testing.assert_array_equal(clf.all_scores_[i], s)
+        np.testing.assert_allclose(clf.all_log_p_values_[i], lp, rtol=1e-9, atol=1e-12, equal_nan=True)
+    ari = [adjusted_rand_score(clf.communities_[i], ora.communities_[i]) for i in range(2)]
+    print(f"\n[pseudocount=1 {shape}] adjusted Rand vs the oracle's float32 ARPACK run: {np.round(ari, 4)}")
+    assert min(ari) > 0.8
+
+
+def test_pseudocount1_with_scaling_takes_the_dense_solver():
+    """standard_scaling densifies the matrix (sc.pp.scale zero-centres), so :308 picks "auto" again: the pipelined loop with
+    the log1p build.  The oracle does not restate scanpy's sparse pp.scale, so this checks the path runs and is deterministic."""
+    from doubletdetection_b200 import BoostClassifier
+
+    counts = datasets.structured_counts(1500, 600, seed=9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = BoostClassifier(n_iters=2, clustering_algorithm="louvain", pseudocount=1, standard_scaling=True).fit(counts)
+        b = BoostClassifier(n_iters=2, clustering_algorithm="louvain", pseudocount=1, standard_scaling=True).fit(counts)
+    np.testing.assert_array_equal(a.communities_, b.communities_)
+    assert np.isfinite(a.all_scores_).all()

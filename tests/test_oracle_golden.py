@@ -6,7 +6,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import CLUSTER_GOLDEN_NAMES, GOLDEN_NAMES, golden_case, load_golden
+from conftest import CLUSTER_GOLDEN_NAMES, GOLDEN_NAMES, SPARSE_GOLDEN_NAMES, golden_case, load_golden
 from oracle import louvain_c, louvain_ref, pca_f64, reference_path, refshim, upstream
 
 
@@ -23,7 +23,7 @@ def _oracle_fit(name):
     return clf, labels, score
 
 
-@pytest.mark.parametrize("name", GOLDEN_NAMES + CLUSTER_GOLDEN_NAMES)
+@pytest.mark.parametrize("name", GOLDEN_NAMES + CLUSTER_GOLDEN_NAMES + SPARSE_GOLDEN_NAMES)
 def test_oracle_matches_reference_goldens(name):
     g = load_golden(name)
     clf, labels, score = _oracle_fit(name)
@@ -41,7 +41,8 @@ def test_oracle_matches_reference_goldens(name):
         np.testing.assert_array_equal(st["raw_synth"].indptr, g["synth0_indptr"])
         np.testing.assert_array_equal(st["raw_synth"].indices, g["synth0_indices"])
         np.testing.assert_array_equal(st["raw_synth"].data, g["synth0_data"])
-        np.testing.assert_array_equal(np.asarray(st["aug"], dtype=np.float32), g["pca_input0"])
+        aug = st["aug"].toarray() if hasattr(st["aug"], "toarray") else st["aug"]  # sparse on the pseudocount == 1 branch
+        np.testing.assert_array_equal(np.asarray(aug, dtype=np.float32), g["pca_input0"])
         np.testing.assert_array_equal(st["X_pca"], g["X_pca0"])
         np.testing.assert_array_equal(st["knn_indices"], g["knn_indices0"])
 
