@@ -81,6 +81,8 @@ SIGNATURES = {
     "dd_upload_embedding": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, c_f32p]),
     "dd_knn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_f32p]),
     "dd_knn_listed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p]),
+    "dd_set_knn_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
+    "dd_knn_clustered_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
     "dd_knn_pruned": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p, c_i64p]),
     "dd_louvain_knn": (
         ctypes.c_int,
@@ -479,6 +481,15 @@ class Handle:
         dist = np.empty((n, k), dtype=np.float32) if with_dist else None
         self._check(self._lib.dd_knn(self._h, k, _ptr(idx, ctypes.c_int32), _ptr(dist, ctypes.c_float)))
         return idx, dist
+
+    def set_knn_mode(self, mode):
+        """0 = cluster-ordered kNN for large embeddings (default), 1 = always the all-tiles kernel, 2 = always cluster-ordered."""
+        self._check(self._lib.dd_set_knn_mode(self._h, int(mode)))
+
+    def knn_clustered_stats(self):
+        out = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.dd_knn_clustered_stats(self._h, _ptr(out, ctypes.c_int64)))
+        return dict(pairs_a=int(out[0]), pairs_b=int(out[1]), blocks=int(out[2]), tiles=int(out[3]))
 
     def knn_listed(self, k, list_off, list_tiles, with_dist=True):
         """Experimental: exact kNN in which 256-row query block p only visits the 128-row candidate tiles

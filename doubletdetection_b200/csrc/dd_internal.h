@@ -139,8 +139,13 @@ struct dd_handle {
     int64_t cap_knn_ops = 0;
     // experimental (dd_knn_listed): candidate-tile lists per 256-row query block; knn_list_pairs > 0 while such a call runs
     int32_t *d_knn_list_off = nullptr, *d_knn_list_tiles = nullptr;
+    // cluster-ordered kNN (knn_prune.cu: dd_dev_knn_clustered): one carved allocation; the k-means centroids inside it are
+    // carried from call to call while the number of rows stays the same
+    uint8_t *d_knn_cl = nullptr;
+    int64_t cap_knn_cl = 0, knn_cl_rows = -1;
     int64_t cap_knn_list_off = 0, cap_knn_list_tiles = 0;
     int knn_list_pairs = 0;
+    int knn_mode = 0;  // dd_set_knn_mode: 0 = by size, 1 = always all tiles, 2 = always the cluster-ordered path (tests)
     bool knn_narrow = false;  // 64-row pipeline steps / 256 TMEM columns: co-resident with a PCA product CTA (fit loop)
 
     // ---- GPU Louvain level 0 (louvain_gpu.cu): symmetric kNN pattern as CSR + community state ----
@@ -271,6 +276,8 @@ int dd_dev_standard_scale(dd_handle *h, float max_value);           // scale.cu
 int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter,
                const float *omega_host);                            // pca.cu
 int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
+bool dd_knn_clustered_applies(const dd_handle *h, int32_t k);        // knn_prune.cu
+int dd_dev_knn_clustered(dd_handle *h, int32_t k);                  // knn_prune.cu
 int dd_emb_reserve(dd_handle *h, int64_t rows, int32_t KP);         // pca.cu: (re)allocate the two embedding buffers
 int dd_dev_louvain_level0(dd_handle *h, int32_t k, double gamma, uint64_t seed);  // louvain_gpu.cu
 int dd_dev_jaccard_graph(dd_handle *h, int32_t k, int prune);                      // louvain_gpu.cu (PhenoGraph)

@@ -492,7 +492,9 @@ template <int LIST, bool LISTED = false, int TN = 128>  // LIST: candidates kept
 __global__ void __launch_bounds__(THREADS, 1)
     k_knn_tc(const uint8_t *__restrict__ qa, const uint8_t *__restrict__ cb, int64_t n, int n_tiles, int pair0,
              int n_full, int *__restrict__ cand_i, const int *__restrict__ list_off = nullptr,
-             const int *__restrict__ list_tiles = nullptr) {
+             const int *__restrict__ list_tiles = nullptr, const int *__restrict__ list_len = nullptr,
+             const int *__restrict__ block_order = nullptr, const float *__restrict__ tau_init = nullptr,
+             float *__restrict__ tau_out = nullptr) {
     constexpr int SUB = TILE / TN;                     // pipeline steps per 128-row candidate tile
     constexpr int STAGE_BYTES = TN * KC * 16;
     constexpr uint32_t TMEM_COLS = 4 * TN;             // 2 buffers x 2 query tiles x TN accumulator columns
@@ -513,12 +515,17 @@ __global__ void __launch_bounds__(THREADS, 1)
     // so that it occupies twice as many SMs for half as long.
     const bool half_cta = (int)blockIdx.x >= n_full;
     const int n_qt = half_cta ? 1 : QT;
-    const int tile0 = half_cta ? (pair0 + n_full) * QT + ((int)blockIdx.x - n_full) : ((int)blockIdx.x + pair0) * QT;
+    int tile0 = half_cta ? (pair0 + n_full) * QT + ((int)blockIdx.x - n_full) : ((int)blockIdx.x + pair0) * QT;
     const int *my_list = nullptr;
     if constexpr (LISTED) {  // launched without half CTAs: one list per pair
-        const int off = list_off[pair0 + (int)blockIdx.x];
-        n_tiles = list_off[pair0 + (int)blockIdx.x + 1] - off;
+        // block_order: the pairs in order of decreasing list length (longest first: the hardware hands CTAs out in index
+        // order, so the tail of the launch is made of the short lists).  list_len: lists at fixed strides (list_off[p]) with
+        // explicit lengths, instead of packed lists delimited by list_off[p + 1]
+        const int blk = pair0 + (block_order ? block_order[blockIdx.x] : (int)blockIdx.x);
+        const int off = list_off[blk];
+        n_tiles = list_len ? list_len[blk] : list_off[blk + 1] - off;
         my_list = list_tiles + off;
+        tile0 = blk * QT;
     }
     const int n_steps = n_tiles * SUB;
 
@@ -598,7 +605,12 @@ __global__ void __launch_bounds__(THREADS, 1)
             L.t[l] = kEmptyT;
             L.i[l] = 0x7fffffff;
         }
-        float tau = active ? kEmptyT : INFINITY;
+        // tau_init (cluster-ordered kNN, second launch): the row's LIST-th best score of the first launch -- only candidates
+        // that beat it can still belong to the row's LIST best overall (the two lists are merged by the re-ranking)
+        float tau0 = kEmptyT;
+        if constexpr (LISTED)
+            if (tau_init && active) tau0 = tau_init[qrow];
+        float tau = active ? tau0 : INFINITY;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + qt * TN;
         for (int step = 0; step < my_tiles; step++) {
             const int buf = step & 1;
@@ -633,7 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const int cidx = cand0 + c + pos;
                     if ((int64_t)cidx != qrow) {
                         reglist_insert(L, m, cidx);
-                        tau = L.t[LIST - 1];
+                        tau = LISTED ? fmaxf(tau0, L.t[LIST - 1]) : L.t[LIST - 1];
                     }
                     m = __uint_as_float(v[0]);
 #pragma unroll
@@ -653,9 +665,11 @@ __global__ void __launch_bounds__(THREADS, 1)
             fence_before();
             mbar_arrive(tempty + buf);
         }
-        if (active && my_tiles > 0) {
+        if (active && (LISTED || my_tiles > 0)) {  // a listed pair with an empty list still owns its rows: all "none"
 #pragma unroll
             for (int l = 0; l < LIST; l++) cand_i[qrow * LIST + l] = L.i[l];
+            if constexpr (LISTED)
+                if (tau_out) tau_out[qrow] = fmaxf(tau0, L.t[LIST - 1]);
         }
     }
     fence_before();
@@ -795,6 +809,8 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     int *cand_i = reinterpret_cast<int *>(cand_d + n_padded * 32);
     // default: tcgen05 distance GEMM; DD_KNN_FFMA=1 keeps the CUDA-core kernel (A/B comparison, KP=64, k>13)
     static const bool force_ffma = getenv("DD_KNN_FFMA") != nullptr;
+    // large embeddings: cluster-ordered candidate tiles (knn_prune.cu) -- the same exact result from a fraction of the tile pairs
+    if (!force_ffma && h->knn_list_pairs == 0 && dd_knn_clustered_applies(h, k)) return dd_dev_knn_clustered(h, k);
     if (h->KP == 32 && !force_ffma) return run_knn_tc(h, k, TL, cand_d, cand_i);
     if (dd_sharded(h)) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: cell-block sharding needs the tcgen05 path (<= 32 components)");
     if (h->KP == 32)
@@ -863,13 +879,20 @@ int dd_knn_launch_prep(dd_handle *h, const float *emb, int64_t n, int64_t n_pad,
 }
 
 int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
-                           const int *list_off, const int *list_tiles) {
+                           const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
+                           const float *tau_init, float *tau_out) {
     static dd_once_per_device attr_set;  // function attributes are per device
     attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tc::k_knn_tc<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
     DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<16, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
-              n_blocks, cand_i, list_off, list_tiles);
+              n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out);
+    return DD_OK;
+}
+
+int dd_knn_launch_refine32(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
+    DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, (int64_t)0, n, k, idx_out,
+              dist_out);
     return DD_OK;
 }
 

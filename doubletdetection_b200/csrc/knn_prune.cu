@@ -4,11 +4,15 @@
 #include "dd_internal.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 int dd_knn_launch_prep(dd_handle *h, const float *emb, int64_t n, int64_t n_pad, uint8_t *qa, uint8_t *cb);        // knn.cu
 int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
-                           const int *list_off, const int *list_tiles);                                              // knn.cu
+                           const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
+                           const float *tau_init, float *tau_out);                                                   // knn.cu
+int dd_knn_launch_refine32(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
+                           float *dist_out);                                                                         // knn.cu
 int dd_knn_launch_refine16(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 
@@ -146,7 +150,7 @@ __global__ void k_prune_offsets(const int32_t *__restrict__ len, int n_blocks, i
 
 // candidate lists of launch B (permuted numbering, one row per permuted position) -> original numbering and row order
 __global__ void k_prune_translate(const int32_t *__restrict__ perm, const int *__restrict__ cand_p, int64_t n_pad,
-                                  int *__restrict__ cand_o) {
+                                  int *__restrict__ cand_o, int out_stride = 16, int out_col0 = 0) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = t >> 4;
     const int l = (int)(t & 15);
@@ -159,7 +163,7 @@ __global__ void k_prune_translate(const int32_t *__restrict__ perm, const int *_
         const int oc = perm[c];
         if (oc >= 0) out = oc;
     }
-    cand_o[(int64_t)o * 16 + l] = out;
+    cand_o[(int64_t)o * out_stride + out_col0 + l] = out;
 }
 
 template <typename T>
@@ -241,7 +245,8 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
     DD_LAUNCH(h, "prune_boxes", k_prune_boxes, (unsigned)(((int64_t)n_tiles * 32 + 255) / 256), 256, 0, d_emb_p.p, d_perm.p, n_tiles,
               d_lo.p, d_hi.p, d_tile_rows.p);
     // launch A + exact re-ranking in the permuted numbering -> thresholds
-    DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_a.p, d_tiles_a.p));
+    DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_a.p, d_tiles_a.p, nullptr, nullptr, nullptr,
+                                  nullptr));
     DD_TRY(dd_knn_launch_refine16(h, d_emb_p.p, d_cand_p.p, n_pad, (int)k, d_idx_a.p, d_dist_a.p));
     DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)n_blocks, 256, 0, d_perm.p, d_idx_a.p, d_dist_a.p, (int)k, d_thr.p);
     DD_LAUNCH(h, "prune_lists", k_prune_lists, (unsigned)n_blocks, 256, 0, d_lo.p, d_hi.p, d_tile_rows.p, d_thr.p, n_tiles,
@@ -250,9 +255,10 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
     DD_LAUNCH(h, "prune_lists", k_prune_lists, (unsigned)n_blocks, 256, 0, d_lo.p, d_hi.p, d_tile_rows.p, d_thr.p, n_tiles,
               (const int32_t *)d_off_b.p, d_list_b.p, d_len_b.p);
     // launch B, back to the original numbering, exact re-ranking there
-    DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_b.p, d_list_b.p));
+    DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_b.p, d_list_b.p, nullptr, nullptr, nullptr,
+                                  nullptr));
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((n_pad * 16 + 255) / 256), 256, 0, d_perm.p, d_cand_p.p, n_pad,
-              d_cand_o.p);
+              d_cand_o.p, 16, 0);
     // output buffers of the ordinary kNN (sized by an earlier dd_knn call on this embedding, or here)
     if (!h->d_knn_idx || h->cap_knn < n * k + n + 2 * ((n + 255) / 256 * 256) * 32)
         return dd_fail(h, DD_ERR_ARG, "dd_knn_pruned: call dd_knn on this embedding first (it sizes the output buffers)");
@@ -272,5 +278,425 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
         stats_out[2] = n_blocks;
         stats_out[3] = n_tiles;
     }
+    return DD_OK;
+}
+
+// ====================================================================================================================
+// The cluster-ordered exact kNN as the fit loop runs it (dd_dev_knn -> here for >= kClusteredMinRows rows, k <= 13): the
+// ordering itself is found on the device as well, nothing synchronises with the host.
+//
+//   1. groups: kGroups k-means centroids on the embedding, warm-started from the previous call on this handle (the fit
+//      loop's embeddings of consecutive iterations share their leading components); each call is one Lloyd step (five
+//      after a cold start) -- k_km_assign / k_km_update / k_grp_axis.  The grouping only decides how tight the bounds are: any
+//      grouping gives the exact result.
+//   2. order inside a group: along the coordinate axis on which the group varies most (the bounding boxes are axis
+//      aligned, so slabs along an axis are what tightens them), in kBins buckets between mean -/+ 2.5 sigma --
+//      k_grp_axis / k_bucket_count.  Groups are padded to whole 256-row query blocks -- k_bucket_layout / k_bucket_scatter.
+//   3. gather + operand tiles + per-tile boxes of the permuted embedding (kernels above).
+//   4. launch A: every block against the tiles of its own group; exact re-ranking there -> each row's k-th distance, an
+//      upper bound of its true one; the block's threshold is the largest of its rows.
+//   5. launch B: every block against the tiles of the OTHER groups whose box-to-box distance is within the threshold, longest
+//      lists first; a row starts from its launch-A filter threshold (tau) so that only improvements are collected.
+//   6. both candidate lists back to the original numbering, exact float64 re-ranking of the <= 32 candidates there
+//      (ties break by original index, as in the dense kNN).
+namespace {
+
+constexpr int kGroups = 128, kBins = 64, kBuckets = kGroups * kBins;
+
+__global__ void k_km_init(const float *__restrict__ emb, int64_t n, float *__restrict__ cent) {
+    const int g = blockIdx.x, c = threadIdx.x;  // 32 threads
+    const int64_t row = (int64_t)g * n / kGroups + n / (2 * kGroups);
+    cent[g * 32 + c] = emb[min(row, n - 1) * 32 + c];
+}
+
+// one thread per row: nearest centroid (largest x.c - |c|^2 / 2); ACCUM: per-group sums for the centroid update;
+// STATS: per-group sums and sums of squares for the axis choice (final assignment of a call)
+template <bool ACCUM, bool STATS>
+__global__ void __launch_bounds__(256) k_km_assign(const float *__restrict__ emb, int64_t n, const float *__restrict__ cent,
+                                                   int32_t *__restrict__ label, float *__restrict__ acc_sum,
+                                                   float *__restrict__ acc_sq, int32_t *__restrict__ acc_cnt) {
+    __shared__ float s_c[kGroups * 33];  // padded rows: conflict-free when every thread reads another group
+    __shared__ float s_h[kGroups];
+    for (int e = threadIdx.x; e < kGroups * 32; e += 256) s_c[(e >> 5) * 33 + (e & 31)] = cent[e];
+    __syncthreads();
+    if (threadIdx.x < kGroups) {
+        float h = 0.f;
+        for (int c = 0; c < 32; c++) h += s_c[threadIdx.x * 33 + c] * s_c[threadIdx.x * 33 + c];
+        s_h[threadIdx.x] = 0.5f * h;
+    }
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(emb + row * 32 + c);
+        x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
+    }
+    int best = 0;
+    float best_t = -3.0e38f;
+    for (int g = 0; g < kGroups; g++) {
+        float t = -s_h[g];
+#pragma unroll
+        for (int c = 0; c < 32; c++) t = fmaf(x[c], s_c[g * 33 + c], t);  // broadcast reads
+        if (t > best_t) {
+            best_t = t;
+            best = g;
+        }
+    }
+    label[row] = best;
+    if (ACCUM || STATS) {
+        atomicAdd(acc_cnt + best, 1);
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            atomicAdd(acc_sum + best * 32 + c, x[c]);
+            if (STATS) atomicAdd(acc_sq + best * 32 + c, x[c] * x[c]);
+        }
+    }
+}
+
+// new centroid = mean of its rows (an empty group keeps its old centroid); clears the accumulators
+__global__ void k_km_update(float *__restrict__ cent, float *__restrict__ acc_sum, int32_t *__restrict__ acc_cnt) {
+    const int g = blockIdx.x, c = threadIdx.x;  // 32 threads
+    const int cnt = acc_cnt[g];
+    const float s = acc_sum[g * 32 + c];
+    __syncwarp();
+    if (cnt > 0) cent[g * 32 + c] = s / (float)cnt;
+    acc_sum[g * 32 + c] = 0.f;
+    if (c == 0) acc_cnt[g] = 0;
+}
+
+// per group: the coordinate axis with the largest variance, and the affine map of that coordinate onto the kBins buckets
+// (mean -/+ 2.5 sigma; outliers land in the end buckets).  Also moves the centroid to the group's mean for the next call
+// and clears the accumulators.
+__global__ void k_grp_axis(float *__restrict__ cent, float *__restrict__ acc_sum, float *__restrict__ acc_sq,
+                           int32_t *__restrict__ acc_cnt, int32_t *__restrict__ axis, float *__restrict__ bin_lo,
+                           float *__restrict__ bin_scale) {
+    const int g = blockIdx.x, c = threadIdx.x;  // 32 threads
+    const int cnt = acc_cnt[g];
+    const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
+    const float mean = acc_sum[g * 32 + c] * inv;
+    float var = fmaxf(acc_sq[g * 32 + c] * inv - mean * mean, 0.f);
+    __syncwarp();
+    if (cnt > 0) cent[g * 32 + c] = mean;
+    acc_sum[g * 32 + c] = 0.f;
+    acc_sq[g * 32 + c] = 0.f;
+    float best_var = var;
+    int best = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best_var, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ov > best_var || (ov == best_var && ob < best)) {
+            best_var = ov;
+            best = ob;
+        }
+    }
+    const float m_best = __shfl_sync(0xffffffffu, mean, best);
+    if (c == 0) {
+        const float sd = sqrtf(best_var);
+        axis[g] = best;
+        bin_lo[g] = m_best - 2.5f * sd;
+        bin_scale[g] = sd > 0.f ? (float)kBins / (5.f * sd) : 0.f;
+        acc_cnt[g] = 0;
+    }
+}
+
+__global__ void k_bucket_count(const float *__restrict__ emb, int64_t n, const int32_t *__restrict__ label,
+                               const int32_t *__restrict__ axis, const float *__restrict__ bin_lo,
+                               const float *__restrict__ bin_scale, int32_t *__restrict__ bucket, int32_t *__restrict__ hist) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int g = label[row];
+    const float x = emb[row * 32 + axis[g]];
+    const float f = (x - bin_lo[g]) * bin_scale[g];
+    const int b = g * kBins + max(0, min(kBins - 1, (int)f));
+    bucket[row] = b;
+    atomicAdd(hist + b, 1);
+}
+
+// one CTA, kGroups threads... groups padded to whole 256-row blocks; first position of every bucket; per-block group (-1:
+// block unused) and per-group tile range.  info[0] = padded rows in use.
+__global__ void __launch_bounds__(kGroups) k_bucket_layout(const int32_t *__restrict__ hist, int32_t *__restrict__ start,
+                                                           int32_t *__restrict__ cursor, int32_t *__restrict__ block_group,
+                                                           int n_blocks_max, int32_t *__restrict__ group_tile0,
+                                                           int32_t *__restrict__ group_tiles, int32_t *__restrict__ info) {
+    __shared__ int s_pad[kGroups], s_start[kGroups + 1];
+    const int g = threadIdx.x;
+    int size = 0;
+    for (int b = 0; b < kBins; b++) size += hist[g * kBins + b];
+    s_pad[g] = (size + 255) / 256 * 256;
+    __syncthreads();
+    if (g == 0) {
+        int run = 0;
+        for (int i = 0; i < kGroups; i++) {
+            s_start[i] = run;
+            run += s_pad[i];
+        }
+        s_start[kGroups] = run;
+        info[0] = run;
+    }
+    __syncthreads();
+    int run = s_start[g];
+    for (int b = 0; b < kBins; b++) {
+        start[g * kBins + b] = run;
+        cursor[g * kBins + b] = 0;
+        run += hist[g * kBins + b];
+    }
+    group_tile0[g] = s_start[g] / tc::TILE;
+    group_tiles[g] = (size + tc::TILE - 1) / tc::TILE;  // tiles that hold real rows
+    for (int b = s_start[g] / 256; b < s_start[g + 1] / 256; b++) block_group[b] = g;
+    for (int b = s_start[kGroups] / 256 + g; b < n_blocks_max; b += kGroups) block_group[b] = -1;
+}
+
+__global__ void k_bucket_scatter(int64_t n, const int32_t *__restrict__ bucket, const int32_t *__restrict__ start,
+                                 int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int b = bucket[row];
+    perm[start[b] + atomicAdd(cursor + b, 1)] = (int32_t)row;
+}
+
+// launch A lists: the tiles of the block's own group that hold real rows (a contiguous range), at stride n_tiles_max
+__global__ void k_lists_own(const int32_t *__restrict__ block_group, const int32_t *__restrict__ group_tile0,
+                            const int32_t *__restrict__ group_tiles, int n_tiles_max, int32_t *__restrict__ off,
+                            int32_t *__restrict__ list, int32_t *__restrict__ len) {
+    const int b = blockIdx.x;
+    const int g = block_group[b];
+    const int t0 = g >= 0 ? group_tile0[g] : 0, nt = g >= 0 ? group_tiles[g] : 0;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) list[(int64_t)b * n_tiles_max + t] = t0 + t;
+    if (threadIdx.x == 0) {
+        off[b] = b * n_tiles_max;
+        len[b] = nt;
+    }
+}
+
+// launch B lists in ONE pass (fixed stride): the tiles of OTHER groups whose box-to-box distance^2 to the block's box is
+// within the block's threshold.  One CTA (256 threads) per block; order inside the list = tile order.
+__global__ void __launch_bounds__(256) k_lists_other(const float *__restrict__ lo, const float *__restrict__ hi,
+                                                     const int32_t *__restrict__ tile_rows, const double *__restrict__ thr,
+                                                     const int32_t *__restrict__ block_group, int n_tiles_max,
+                                                     int32_t *__restrict__ list, int32_t *__restrict__ len) {
+    __shared__ float q_lo[32], q_hi[32];
+    __shared__ int s_warp[8], s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;
+    const int g = block_group[b];
+    if (g < 0) {  // unused block (uniform)
+        if (tid == 0) len[b] = 0;
+        return;
+    }
+    if (tid < 32) {
+        float mn = 3.0e38f, mx = -3.0e38f;
+        for (int h2 = 0; h2 < tc::QT; h2++) {
+            const int t = b * tc::QT + h2;
+            if (tile_rows[t] > 0) {
+                mn = fminf(mn, lo[(int64_t)t * 32 + tid]);
+                mx = fmaxf(mx, hi[(int64_t)t * 32 + tid]);
+            }
+        }
+        q_lo[tid] = mn;
+        q_hi[tid] = mx;
+    }
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const double limit = thr[b] * (1.0 + 1.0e-5);
+    int32_t *mine = list + (int64_t)b * n_tiles_max;
+    for (int t0 = 0; t0 < n_tiles_max; t0 += 256) {
+        const int t = t0 + tid;
+        bool need = false;
+        if (t < n_tiles_max && tile_rows[t] > 0 && block_group[t / tc::QT] != g) {
+            double lb = 0.0;
+            for (int c = 0; c < 32; c++) {
+                const float gap = fmaxf(0.f, fmaxf(lo[(int64_t)t * 32 + c] - q_hi[c], q_lo[c] - hi[(int64_t)t * 32 + c]));
+                lb += (double)gap * (double)gap;
+            }
+            need = lb <= limit;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) s_warp[wl] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < wl; w++) before += s_warp[w];
+        if (need) mine[before + __popc(m & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (tid == 0) {
+            int total = 0;
+            for (int w = 0; w < 8; w++) total += s_warp[w];
+            s_base += total;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) len[b] = s_base;
+}
+
+// blocks by decreasing list length (rank by counting; ties by block index): order[rank] = block
+__global__ void k_block_order(const int32_t *__restrict__ len, int n_blocks, int32_t *__restrict__ order) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const int mine = len[b];
+    int rank = 0;
+    for (int o = 0; o < n_blocks; o++) {
+        const int l = len[o];
+        rank += (l > mine) || (l == mine && o < b);
+    }
+    order[rank] = b;
+}
+
+struct ClusteredBuffers {
+    int32_t *label, *bucket, *acc_cnt, *axis, *hist, *start, *cursor, *block_group, *group_tile0, *group_tiles, *info, *perm,
+        *tile_rows, *off, *list_a, *len_a, *list_b, *len_b, *order, *idx_a;
+    int *cand_a, *cand_b, *cand_o;
+    float *cent, *acc_sum, *acc_sq, *bin_lo, *bin_scale, *emb_p, *lo, *hi, *tau, *dist_a;
+    double *thr;
+};
+
+}  // namespace
+
+// Smallest embedding for which the ordering pays (clusters must be larger than tiles; measured: DESIGN.md section 5)
+static constexpr int64_t kClusteredMinRows = 50000;
+
+bool dd_knn_clustered_applies(const dd_handle *h, int32_t k) {
+    static const bool off = getenv("DD_KNN_DENSE") != nullptr;
+    if (off || h->knn_mode == 1 || h->KP != 32 || k < 2 || k > 13 || dd_sharded(h)) return false;
+    return h->knn_mode == 2 ? h->emb_rows >= 512 : h->emb_rows >= kClusteredMinRows;
+}
+
+// 0 = choose by size (default), 1 = always the all-tiles kernel, 2 = always the cluster-ordered path (tests, A/B timing)
+extern "C" int dd_set_knn_mode(dd_handle *h, int32_t mode) {
+    if (!h || mode < 0 || mode > 2) return dd_fail(h, DD_ERR_ARG, "dd_set_knn_mode: mode must be 0, 1 or 2");
+    h->knn_mode = mode;
+    return DD_OK;
+}
+
+// Asynchronous on h->stream; result in h->d_knn_idx / h->d_knn_dist (allocated by dd_dev_knn).
+int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
+    const int64_t n = h->emb_rows;
+    const int64_t P = (n + 255) / 256 * 256 + (int64_t)kGroups * 256;  // padded rows: every group wastes < 256
+    const int T = (int)(P / tc::TILE), B = (int)(P / 256);
+    if ((int64_t)B * T >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "clustered knn: list table too large");
+    // ---- one grow-only allocation, carved up
+    size_t bytes = 0;
+    auto take = [&](size_t b) {
+        const size_t at = bytes;
+        bytes += (b + 255) / 256 * 256;
+        return at;
+    };
+    const size_t o_label = take(4 * n), o_bucket = take(4 * n), o_acc_cnt = take(4 * kGroups), o_axis = take(4 * kGroups),
+                 o_hist = take(4 * kBuckets), o_start = take(4 * kBuckets), o_cursor = take(4 * kBuckets), o_bg = take(4 * B),
+                 o_gt0 = take(4 * kGroups), o_gt = take(4 * kGroups), o_info = take(64), o_perm = take(4 * P),
+                 o_trows = take(4 * T), o_off = take(4 * B), o_list_a = take(4 * (size_t)B * T), o_len_a = take(4 * B),
+                 o_list_b = take(4 * (size_t)B * T), o_len_b = take(4 * B), o_order = take(4 * B), o_idx_a = take(4 * P * k),
+                 o_cand_a = take(4 * P * 16), o_cand_b = take(4 * P * 16), o_cand_o = take(4 * n * 32),
+                 o_cent = take(4 * kGroups * 32), o_acc_sum = take(4 * kGroups * 32), o_acc_sq = take(4 * kGroups * 32),
+                 o_bin_lo = take(4 * kGroups), o_bin_scale = take(4 * kGroups), o_emb_p = take(4 * P * 32),
+                 o_lo = take(4 * (size_t)T * 32), o_hi = take(4 * (size_t)T * 32), o_tau = take(4 * P), o_dist_a = take(4 * P * k),
+                 o_thr = take(8 * B);
+    bool cold = false;
+    if ((int64_t)bytes > h->cap_knn_cl || h->knn_cl_rows != n) {
+        if ((int64_t)bytes > h->cap_knn_cl) {
+            if (h->d_knn_cl) cudaFree(h->d_knn_cl);
+            h->d_knn_cl = nullptr;
+            h->cap_knn_cl = 0;
+            DD_CUDA(h, cudaMalloc(&h->d_knn_cl, bytes));
+            h->cap_knn_cl = (int64_t)bytes;
+        }
+        h->knn_cl_rows = n;
+        cold = true;  // no centroids from an earlier call on this problem size
+    }
+    uint8_t *base = h->d_knn_cl;
+    ClusteredBuffers b;
+    b.label = (int32_t *)(base + o_label); b.bucket = (int32_t *)(base + o_bucket); b.acc_cnt = (int32_t *)(base + o_acc_cnt);
+    b.axis = (int32_t *)(base + o_axis); b.hist = (int32_t *)(base + o_hist); b.start = (int32_t *)(base + o_start);
+    b.cursor = (int32_t *)(base + o_cursor); b.block_group = (int32_t *)(base + o_bg); b.group_tile0 = (int32_t *)(base + o_gt0);
+    b.group_tiles = (int32_t *)(base + o_gt); b.info = (int32_t *)(base + o_info); b.perm = (int32_t *)(base + o_perm);
+    b.tile_rows = (int32_t *)(base + o_trows); b.off = (int32_t *)(base + o_off); b.list_a = (int32_t *)(base + o_list_a);
+    b.len_a = (int32_t *)(base + o_len_a); b.list_b = (int32_t *)(base + o_list_b); b.len_b = (int32_t *)(base + o_len_b);
+    b.order = (int32_t *)(base + o_order); b.idx_a = (int32_t *)(base + o_idx_a); b.cand_a = (int *)(base + o_cand_a);
+    b.cand_b = (int *)(base + o_cand_b); b.cand_o = (int *)(base + o_cand_o); b.cent = (float *)(base + o_cent);
+    b.acc_sum = (float *)(base + o_acc_sum); b.acc_sq = (float *)(base + o_acc_sq); b.bin_lo = (float *)(base + o_bin_lo);
+    b.bin_scale = (float *)(base + o_bin_scale); b.emb_p = (float *)(base + o_emb_p); b.lo = (float *)(base + o_lo);
+    b.hi = (float *)(base + o_hi); b.tau = (float *)(base + o_tau); b.dist_a = (float *)(base + o_dist_a);
+    b.thr = (double *)(base + o_thr);
+    const int64_t op_bytes = (int64_t)T * tc::TILE_BYTES;
+    DD_TRY(dd_reserve(h, &h->d_knn_ops, &h->cap_knn_ops, 2 * op_bytes));
+    uint8_t *qa = h->d_knn_ops, *cb = h->d_knn_ops + op_bytes;
+    const unsigned row_ctas = (unsigned)((n + 255) / 256);
+
+    // ---- 1. groups
+    if (cold) {
+        DD_LAUNCH(h, "kcl_init", k_km_init, kGroups, 32, 0, h->d_emb, n, b.cent);
+        DD_CUDA(h, cudaMemsetAsync(b.acc_cnt, 0, 4 * kGroups, h->stream));
+        DD_CUDA(h, cudaMemsetAsync(b.acc_sum, 0, 4 * kGroups * 32, h->stream));
+        DD_CUDA(h, cudaMemsetAsync(b.acc_sq, 0, 4 * kGroups * 32, h->stream));
+    }
+    // warm: the final assignment below is itself one Lloyd step (k_grp_axis moves every centroid to its group's mean)
+    for (int pass = 0; pass < (cold ? 4 : 0); pass++) {
+        DD_LAUNCH(h, "kcl_assign", (k_km_assign<true, false>), row_ctas, 256, 0, h->d_emb, n, b.cent, b.label, b.acc_sum, b.acc_sq,
+                  b.acc_cnt);
+        DD_LAUNCH(h, "kcl_update", k_km_update, kGroups, 32, 0, b.cent, b.acc_sum, b.acc_cnt);
+    }
+    DD_LAUNCH(h, "kcl_assign", (k_km_assign<false, true>), row_ctas, 256, 0, h->d_emb, n, b.cent, b.label, b.acc_sum, b.acc_sq,
+              b.acc_cnt);
+    // ---- 2. order inside the groups, padded layout
+    DD_LAUNCH(h, "kcl_axis", k_grp_axis, kGroups, 32, 0, b.cent, b.acc_sum, b.acc_sq, b.acc_cnt, b.axis, b.bin_lo, b.bin_scale);
+    DD_CUDA(h, cudaMemsetAsync(b.hist, 0, 4 * kBuckets, h->stream));
+    DD_LAUNCH(h, "kcl_bucket", k_bucket_count, row_ctas, 256, 0, h->d_emb, n, b.label, b.axis, b.bin_lo, b.bin_scale, b.bucket, b.hist);
+    DD_LAUNCH(h, "kcl_layout", k_bucket_layout, 1, kGroups, 0, b.hist, b.start, b.cursor, b.block_group, B, b.group_tile0,
+              b.group_tiles, b.info);
+    DD_CUDA(h, cudaMemsetAsync(b.perm, 0xff, 4 * P, h->stream));
+    DD_LAUNCH(h, "kcl_scatter", k_bucket_scatter, row_ctas, 256, 0, n, b.bucket, b.start, b.cursor, b.perm);
+    // ---- 3. permuted embedding, operand tiles, boxes
+    DD_LAUNCH(h, "prune_gather", k_prune_gather, (unsigned)((P * 8 + 255) / 256), 256, 0, h->d_emb, b.perm, P, b.emb_p);
+    DD_TRY(dd_knn_launch_prep(h, b.emb_p, P, P, qa, cb));
+    DD_LAUNCH(h, "prune_boxes", k_prune_boxes, (unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, b.emb_p, b.perm, T, b.lo, b.hi,
+              b.tile_rows);
+    // ---- 4. launch A (own group) -> thresholds
+    DD_LAUNCH(h, "kcl_lists_own", k_lists_own, (unsigned)B, 128, 0, b.block_group, b.group_tile0, b.group_tiles, T, b.off, b.list_a,
+              b.len_a);
+    DD_LAUNCH(h, "kcl_order", k_block_order, (unsigned)((B + 255) / 256), 256, 0, b.len_a, B, b.order);
+    DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
+    DD_CUDA(h, cudaMemsetAsync(b.idx_a, 0xff, sizeof(int32_t) * (size_t)P * k, h->stream));  // -1 = "not found"
+    DD_TRY(dd_knn_launch_refine16(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
+    DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)B, 256, 0, b.perm, b.idx_a, b.dist_a, (int)k, b.thr);
+    // ---- 5. launch B (other groups within the bound), longest lists first, starting from launch A's filter thresholds
+    DD_LAUNCH(h, "kcl_lists_other", k_lists_other, (unsigned)B, 256, 0, b.lo, b.hi, b.tile_rows, b.thr, b.block_group, T, b.list_b,
+              b.len_b);
+    DD_LAUNCH(h, "kcl_order", k_block_order, (unsigned)((B + 255) / 256), 256, 0, b.len_b, B, b.order);
+    DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+    // ---- 6. back to the original numbering, exact re-ranking of both lists together
+    DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * 16 + 255) / 256), 256, 0, b.perm, b.cand_a, P, b.cand_o, 32, 0);
+    DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * 16 + 255) / 256), 256, 0, b.perm, b.cand_b, P, b.cand_o, 32, 16);
+    DD_TRY(dd_knn_launch_refine32(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
+    return DD_OK;
+}
+
+// Inspection: how much of the dense work the last clustered kNN on this handle did.  stats_out[0..3] = block-tile pairs of
+// launch A, of launch B, blocks in use, tiles in use.
+extern "C" int dd_knn_clustered_stats(dd_handle *h, int64_t *stats_out) {
+    if (!h || !stats_out || !h->d_knn_cl || h->knn_cl_rows <= 0) return dd_fail(h, DD_ERR_ARG, "dd_knn_clustered_stats: no clustered kNN ran");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n = h->knn_cl_rows;
+    const int64_t P = (n + 255) / 256 * 256 + (int64_t)kGroups * 256;
+    const int B = (int)(P / 256);
+    // same carving as dd_dev_knn_clustered (offsets recomputed)
+    size_t bytes = 0;
+    auto take = [&](size_t b) { const size_t at = bytes; bytes += (b + 255) / 256 * 256; return at; };
+    const int T = (int)(P / tc::TILE);
+    take(4 * n); take(4 * n); take(4 * kGroups); take(4 * kGroups); take(4 * kBuckets); take(4 * kBuckets); take(4 * kBuckets);
+    take(4 * B); take(4 * kGroups); take(4 * kGroups);
+    const size_t o_info = take(64);
+    take(4 * P); take(4 * T); take(4 * B); take(4 * (size_t)B * T);
+    const size_t o_len_a = take(4 * B);
+    take(4 * (size_t)B * T);
+    const size_t o_len_b = take(4 * B);
+    std::vector<int32_t> la(B), lb(B);
+    int32_t info[16];
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    DD_CUDA(h, cudaMemcpy(la.data(), h->d_knn_cl + o_len_a, 4 * B, cudaMemcpyDeviceToHost));
+    DD_CUDA(h, cudaMemcpy(lb.data(), h->d_knn_cl + o_len_b, 4 * B, cudaMemcpyDeviceToHost));
+    DD_CUDA(h, cudaMemcpy(info, h->d_knn_cl + o_info, 64, cudaMemcpyDeviceToHost));
+    int64_t pa = 0, pb = 0;
+    for (int i = 0; i < B; i++) { pa += la[i]; pb += lb[i]; }
+    stats_out[0] = pa; stats_out[1] = pb; stats_out[2] = info[0] / 256; stats_out[3] = info[0] / tc::TILE;
     return DD_OK;
 }

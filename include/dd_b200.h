@@ -136,6 +136,15 @@ int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const int32_t *list
  * buffers).  stats_out int64[4] (may be NULL): block-tile pairs of launch A, of launch B, blocks, tiles.  k <= 13. */
 int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32_t *perm, const int32_t *block_group, int32_t *idx_out,
                   float *dist_out, int64_t *stats_out);
+/* The fit loop's kNN for large embeddings (>= 50 000 rows, k <= 13; doubletdetection.py:331-336 at BASELINE sizes) is the
+ * cluster-ordered form of the same exact search: rows grouped by a device k-means, groups padded to 256-row blocks, every
+ * block first against its own group, then against the tiles of other groups its bounding box cannot exclude (valid lower
+ * bounds: identical neighbours to the all-tiles kernel).  dd_set_knn_mode: 0 = choose by size, 1 = always all tiles, 2 =
+ * always cluster-ordered.  dd_knn_clustered_stats: block-tile pairs visited by the last such call: [launch A, launch B,
+ * blocks in use, tiles in use]. */
+int dd_set_knn_mode(dd_handle *h, int32_t mode);
+int dd_knn_clustered_stats(dd_handle *h, int64_t *stats_out);
+
 
 /* ---- clustering call, doubletdetection.py:337-343 -----------------------------------------
  * Louvain (RB configuration null model, resolution gamma, unweighted, seeded) on the symmetrised

@@ -1,0 +1,65 @@
+"""The cluster-ordered exact kNN (knn_prune.cu: dd_dev_knn_clustered -- what the fit loop runs from 50 000 rows on) against
+the all-tiles tcgen05 kernel: index for index, distance for distance, on the headline embedding (c3: 125 000 augmented cells),
+on data without any cluster structure, on tiny groups and at ragged sizes.  Needs a B200 (`-m gpu`)."""
+
+import numpy as np
+import pytest
+
+from oracle import datasets, upstream
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(handle, emb, k):
+    handle.upload_embedding(emb)
+    handle.set_knn_mode(1)
+    want_idx, want_dist = handle.knn(k)
+    handle.set_knn_mode(2)
+    try:
+        got_idx, got_dist = handle.knn(k)
+        got_idx2, _ = handle.knn(k)  # second call: warm-started centroids
+        stats = handle.knn_clustered_stats()
+    finally:
+        handle.set_knn_mode(0)
+    return want_idx, want_dist, got_idx, got_dist, got_idx2, stats
+
+
+@pytest.mark.parametrize("n,k,kind", [(60000, 10, "blobs"), (60000, 13, "uniform"), (50001, 2, "blobs"), (5000, 10, "blobs"),
+                                      (777, 6, "uniform"), (30000, 10, "duplicates")])
+def test_clustered_knn_equals_dense(handle, n, k, kind):
+    rs = np.random.default_rng(n + k)
+    if kind == "blobs":
+        emb = (rs.normal(size=(n, 30)) + rs.integers(0, 7, size=(n, 1)) * np.r_[np.full(8, 3.0), np.zeros(22)][None, :])
+    elif kind == "uniform":
+        emb = rs.random(size=(n, 30)) * 10
+    else:  # many exactly equal points: ties must break by index exactly as in the dense kernel
+        emb = rs.normal(size=(n // 10, 30))[rs.integers(0, n // 10, size=n)]
+    emb = emb.astype(np.float32)
+    want_idx, want_dist, got_idx, got_dist, got_idx2, stats = _both(handle, emb, k)
+    np.testing.assert_array_equal(got_idx, want_idx)
+    np.testing.assert_array_equal(got_dist, want_dist)
+    np.testing.assert_array_equal(got_idx2, want_idx)
+    if n <= 5000:  # and against the oracle's brute force where that is quick
+        ref_idx, _ = upstream.knn_brute(emb, k)
+        assert (ref_idx == got_idx).mean() > 0.999  # float64 re-ranking vs sklearn's expanded form: near-ties only
+    print(f"\n[{kind} n={n} k={k}] block-tile pairs visited: {(stats['pairs_a'] + stats['pairs_b']) / max(1, ((n + 255) // 256) * ((n + 127) // 128)):.3f} of the dense kernel's")
+
+
+def test_clustered_knn_on_the_headline_embedding(handle):
+    """c3: one iteration's PCA embedding of 125 000 augmented cells, k = 10 (doubletdetection.py:331-336)."""
+    from doubletdetection_b200.classifier import _pca_plan
+
+    counts = datasets.structured_counts(100000, 3000, seed=1234)
+    n_cells = counts.shape[0]
+    handle.upload_counts(counts)
+    handle.create_doublets(np.random.default_rng(0).choice(n_cells, size=(n_cells // 4, 2), replace=False))
+    handle.normalise_log(handle.median_lib_size(), 0.1)
+    omega, n_power = _pca_plan(n_cells + n_cells // 4, 3000, 30, 0)
+    emb, _ = handle.pca(30, omega, n_power)
+    want_idx, want_dist, got_idx, got_dist, got_idx2, stats = _both(handle, np.ascontiguousarray(emb, dtype=np.float32), 10)
+    np.testing.assert_array_equal(got_idx, want_idx)
+    np.testing.assert_array_equal(got_dist, want_dist)
+    np.testing.assert_array_equal(got_idx2, want_idx)
+    frac = (stats["pairs_a"] + stats["pairs_b"]) / (489 * 977)
+    print(f"\n[c3 embedding] block-tile pairs visited: {frac:.3f} of the dense kernel's ({stats})")
+    assert frac < 0.6
