@@ -890,6 +890,71 @@ int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, i
     return DD_OK;
 }
 
+// the same for lists of 32 (k - 1 > 12: PhenoGraph's 30 neighbours)
+int dd_knn_launch_listed32(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
+                           const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
+                           const float *tau_init, float *tau_out) {
+    static dd_once_per_device attr_set;  // function attributes are per device
+    attr_set.run(h->device, [&] {
+        cudaFuncSetAttribute(tc::k_knn_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+    });
+    DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<32, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
+              n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out);
+    return DD_OK;
+}
+
+// exact re-ranking of 64 candidates per query (two lists of 32 side by side): every lane owns two of them
+__global__ void k_knn_refine64(const float *__restrict__ emb, const int *__restrict__ cand_i, int64_t n, int k,
+                               int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= n) return;
+    int ci[2];
+    double d[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        ci[s] = cand_i[q * 64 + 32 * s + lane];
+        d[s] = INFINITY;
+        if (ci[s] != 0x7fffffff) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(emb + q * 32 + c);
+                const float4 b = *reinterpret_cast<const float4 *>(emb + (int64_t)ci[s] * 32 + c);
+                const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
+                const double dz = (double)a.z - (double)b.z, dw = (double)a.w - (double)b.w;
+                acc += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+            d[s] = acc;
+        }
+    }
+    int rank[2] = {0, 0};
+    for (int l = 0; l < 32; l++) {
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const double od = __shfl_sync(0xffffffffu, d[s], l);
+            const int oi = __shfl_sync(0xffffffffu, ci[s], l);
+#pragma unroll
+            for (int t = 0; t < 2; t++) rank[t] += (od < d[t]) || (od == d[t] && oi < ci[t]);
+        }
+    }
+    if (lane == 0) {
+        idx_out[q * k] = (int32_t)q;
+        dist_out[q * k] = 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+        if (rank[s] < k - 1) {
+            idx_out[q * k + 1 + rank[s]] = ci[s] == 0x7fffffff ? -1 : ci[s];
+            dist_out[q * k + 1 + rank[s]] = (float)sqrt(d[s]);
+        }
+}
+
+int dd_knn_launch_refine64(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
+    DD_LAUNCH(h, "knn_refine", k_knn_refine64, (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, n, k, idx_out, dist_out);
+    return DD_OK;
+}
+
 int dd_knn_launch_refine32(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
     DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, (int64_t)0, n, k, idx_out,
               dist_out);

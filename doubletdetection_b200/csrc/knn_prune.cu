@@ -13,6 +13,11 @@ int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, i
                            const float *tau_init, float *tau_out);                                                   // knn.cu
 int dd_knn_launch_refine32(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
+int dd_knn_launch_listed32(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
+                           const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
+                           const float *tau_init, float *tau_out);                                                   // knn.cu
+int dd_knn_launch_refine64(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
+                           float *dist_out);                                                                         // knn.cu
 int dd_knn_launch_refine16(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 
@@ -45,7 +50,8 @@ __global__ void k_prune_gather(const float *__restrict__ emb, const int32_t *__r
 
 // one warp per 128-row tile, lane = dimension: bounding box over the real rows of the tile
 __global__ void k_prune_boxes(const float *__restrict__ emb_p, const int32_t *__restrict__ perm, int n_tiles,
-                              float *__restrict__ lo, float *__restrict__ hi, int32_t *__restrict__ tile_rows) {
+                              float *__restrict__ lo, float *__restrict__ hi, int32_t *__restrict__ tile_rows,
+                              float *__restrict__ lo_t = nullptr, float *__restrict__ hi_t = nullptr) {
     const int lane = threadIdx.x & 31;
     const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (t >= n_tiles) return;
@@ -61,6 +67,10 @@ __global__ void k_prune_boxes(const float *__restrict__ emb_p, const int32_t *__
     }
     lo[(int64_t)t * 32 + lane] = mn;
     hi[(int64_t)t * 32 + lane] = mx;
+    if (lo_t) {  // dimension-major copies: one thread per tile reads them coalesced (k_lists_other)
+        lo_t[(int64_t)lane * n_tiles + t] = mn;
+        hi_t[(int64_t)lane * n_tiles + t] = mx;
+    }
     if (lane == 0) tile_rows[t] = rows;
 }
 
@@ -150,14 +160,14 @@ __global__ void k_prune_offsets(const int32_t *__restrict__ len, int n_blocks, i
 
 // candidate lists of launch B (permuted numbering, one row per permuted position) -> original numbering and row order
 __global__ void k_prune_translate(const int32_t *__restrict__ perm, const int *__restrict__ cand_p, int64_t n_pad,
-                                  int *__restrict__ cand_o, int out_stride = 16, int out_col0 = 0) {
+                                  int *__restrict__ cand_o, int out_stride = 16, int out_col0 = 0, int list_w = 16) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r = t >> 4;
-    const int l = (int)(t & 15);
+    const int64_t r = t / list_w;
+    const int l = (int)(t % list_w);
     if (r >= n_pad) return;
     const int o = perm[r];
     if (o < 0) return;
-    const int c = cand_p[r * 16 + l];
+    const int c = cand_p[r * list_w + l];
     int out = 0x7fffffff;
     if (c != 0x7fffffff && c >= 0 && c < n_pad) {
         const int oc = perm[c];
@@ -258,7 +268,7 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
     DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_b.p, d_list_b.p, nullptr, nullptr, nullptr,
                                   nullptr));
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((n_pad * 16 + 255) / 256), 256, 0, d_perm.p, d_cand_p.p, n_pad,
-              d_cand_o.p, 16, 0);
+              d_cand_o.p, 16, 0, 16);
     // output buffers of the ordinary kNN (sized by an earlier dd_knn call on this embedding, or here)
     if (!h->d_knn_idx || h->cap_knn < n * k + n + 2 * ((n + 255) / 256 * 256) * 32)
         return dd_fail(h, DD_ERR_ARG, "dd_knn_pruned: call dd_knn on this embedding first (it sizes the output buffers)");
@@ -309,50 +319,78 @@ __global__ void k_km_init(const float *__restrict__ emb, int64_t n, float *__res
     cent[g * 32 + c] = emb[min(row, n - 1) * 32 + c];
 }
 
-// one thread per row: nearest centroid (largest x.c - |c|^2 / 2); ACCUM: per-group sums for the centroid update;
-// STATS: per-group sums and sums of squares for the axis choice (final assignment of a call)
-template <bool ACCUM, bool STATS>
-__global__ void __launch_bounds__(256) k_km_assign(const float *__restrict__ emb, int64_t n, const float *__restrict__ cent,
-                                                   int32_t *__restrict__ label, float *__restrict__ acc_sum,
-                                                   float *__restrict__ acc_sq, int32_t *__restrict__ acc_cnt) {
-    __shared__ float s_c[kGroups * 33];  // padded rows: conflict-free when every thread reads another group
-    __shared__ float s_h[kGroups];
-    for (int e = threadIdx.x; e < kGroups * 32; e += 256) s_c[(e >> 5) * 33 + (e & 31)] = cent[e];
+// one thread per row: nearest centroid (largest x.c - |c|^2 / 2).  Per-group counts, sums (centroid update) and, with STATS,
+// sums of squares (axis choice) are accumulated in shared memory by a persistent grid (each CTA owns a contiguous range of
+// rows) and flushed with one global atomic per touched (group, dimension) and CTA.
+constexpr int kAssignThreads = 256;
+constexpr size_t kAssignSmem = sizeof(float) * (kGroups * 32 * 3 + kGroups) + sizeof(int) * kGroups;
+template <bool STATS>
+__global__ void __launch_bounds__(kAssignThreads, 2) k_km_assign(const float *__restrict__ emb, int64_t n, const float *__restrict__ cent,
+                                                              int32_t *__restrict__ label, float *__restrict__ acc_sum,
+                                                              float *__restrict__ acc_sq, int32_t *__restrict__ acc_cnt) {
+    extern __shared__ __align__(16) float km_sm[];
+    float *s_c = km_sm;                    // kGroups x 32 (every thread reads the same address: broadcast, no padding needed)
+    float *s_sum = s_c + kGroups * 32;
+    float *s_sq = s_sum + kGroups * 32;
+    float *s_h = s_sq + kGroups * 32;      // |c|^2 / 2
+    int *s_cnt = reinterpret_cast<int *>(s_h + kGroups);
+    for (int e = threadIdx.x; e < kGroups * 32; e += kAssignThreads) {
+        s_c[e] = cent[e];
+        s_sum[e] = 0.f;
+        s_sq[e] = 0.f;
+    }
     __syncthreads();
     if (threadIdx.x < kGroups) {
         float h = 0.f;
-        for (int c = 0; c < 32; c++) h += s_c[threadIdx.x * 33 + c] * s_c[threadIdx.x * 33 + c];
+        for (int c = 0; c < 32; c++) h += s_c[threadIdx.x * 32 + c] * s_c[threadIdx.x * 32 + c];
         s_h[threadIdx.x] = 0.5f * h;
+        s_cnt[threadIdx.x] = 0;
     }
     __syncthreads();
-    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (row >= n) return;
-    float x[32];
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+    for (int64_t row = r0 + threadIdx.x; row < r1; row += kAssignThreads) {
+        float x[32];
 #pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(emb + row * 32 + c);
-        x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
-    }
-    int best = 0;
-    float best_t = -3.0e38f;
-    for (int g = 0; g < kGroups; g++) {
-        float t = -s_h[g];
-#pragma unroll
-        for (int c = 0; c < 32; c++) t = fmaf(x[c], s_c[g * 33 + c], t);  // broadcast reads
-        if (t > best_t) {
-            best_t = t;
-            best = g;
+        for (int c = 0; c < 32; c += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(emb + row * 32 + c);
+            x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
         }
-    }
-    label[row] = best;
-    if (ACCUM || STATS) {
-        atomicAdd(acc_cnt + best, 1);
+        int best = 0;
+        float best_t = -3.0e38f;
+#pragma unroll 2
+        for (int g = 0; g < kGroups; g++) {
+            const float4 *c4 = reinterpret_cast<const float4 *>(s_c + g * 32);
+            float t0 = -s_h[g], t1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                const float4 a = c4[q], b = c4[q + 1];
+                t0 = fmaf(x[4 * q], a.x, t0); t0 = fmaf(x[4 * q + 1], a.y, t0);
+                t0 = fmaf(x[4 * q + 2], a.z, t0); t0 = fmaf(x[4 * q + 3], a.w, t0);
+                t1 = fmaf(x[4 * q + 4], b.x, t1); t1 = fmaf(x[4 * q + 5], b.y, t1);
+                t1 = fmaf(x[4 * q + 6], b.z, t1); t1 = fmaf(x[4 * q + 7], b.w, t1);
+            }
+            const float t = t0 + t1;
+            if (t > best_t) {
+                best_t = t;
+                best = g;
+            }
+        }
+        label[row] = best;
+        atomicAdd(s_cnt + best, 1);
 #pragma unroll
         for (int c = 0; c < 32; c++) {
-            atomicAdd(acc_sum + best * 32 + c, x[c]);
-            if (STATS) atomicAdd(acc_sq + best * 32 + c, x[c] * x[c]);
+            atomicAdd(s_sum + best * 32 + c, x[c]);
+            if (STATS) atomicAdd(s_sq + best * 32 + c, x[c] * x[c]);
         }
     }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kGroups * 32; e += kAssignThreads) {
+        if (s_cnt[e >> 5] == 0) continue;
+        atomicAdd(acc_sum + e, s_sum[e]);
+        if (STATS) atomicAdd(acc_sq + e, s_sq[e]);
+    }
+    if (threadIdx.x < kGroups && s_cnt[threadIdx.x] > 0) atomicAdd(acc_cnt + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
 // new centroid = mean of its rows (an empty group keeps its old centroid); clears the accumulators
@@ -474,6 +512,7 @@ __global__ void k_lists_own(const int32_t *__restrict__ block_group, const int32
 // launch B lists in ONE pass (fixed stride): the tiles of OTHER groups whose box-to-box distance^2 to the block's box is
 // within the block's threshold.  One CTA (256 threads) per block; order inside the list = tile order.
 __global__ void __launch_bounds__(256) k_lists_other(const float *__restrict__ lo, const float *__restrict__ hi,
+                                                     const float *__restrict__ lo_t, const float *__restrict__ hi_t,
                                                      const int32_t *__restrict__ tile_rows, const double *__restrict__ thr,
                                                      const int32_t *__restrict__ block_group, int n_tiles_max,
                                                      int32_t *__restrict__ list, int32_t *__restrict__ len) {
@@ -507,7 +546,7 @@ __global__ void __launch_bounds__(256) k_lists_other(const float *__restrict__ l
         if (t < n_tiles_max && tile_rows[t] > 0 && block_group[t / tc::QT] != g) {
             double lb = 0.0;
             for (int c = 0; c < 32; c++) {
-                const float gap = fmaxf(0.f, fmaxf(lo[(int64_t)t * 32 + c] - q_hi[c], q_lo[c] - hi[(int64_t)t * 32 + c]));
+                const float gap = fmaxf(0.f, fmaxf(lo_t[(int64_t)c * n_tiles_max + t] - q_hi[c], q_lo[c] - hi_t[(int64_t)c * n_tiles_max + t]));
                 lb += (double)gap * (double)gap;
             }
             need = lb <= limit;
@@ -546,7 +585,7 @@ struct ClusteredBuffers {
     int32_t *label, *bucket, *acc_cnt, *axis, *hist, *start, *cursor, *block_group, *group_tile0, *group_tiles, *info, *perm,
         *tile_rows, *off, *list_a, *len_a, *list_b, *len_b, *order, *idx_a;
     int *cand_a, *cand_b, *cand_o;
-    float *cent, *acc_sum, *acc_sq, *bin_lo, *bin_scale, *emb_p, *lo, *hi, *tau, *dist_a;
+    float *cent, *acc_sum, *acc_sq, *bin_lo, *bin_scale, *emb_p, *lo, *hi, *lo_t, *hi_t, *tau, *dist_a;
     double *thr;
 };
 
@@ -557,7 +596,7 @@ static constexpr int64_t kClusteredMinRows = 50000;
 
 bool dd_knn_clustered_applies(const dd_handle *h, int32_t k) {
     static const bool off = getenv("DD_KNN_DENSE") != nullptr;
-    if (off || h->knn_mode == 1 || h->KP != 32 || k < 2 || k > 13 || dd_sharded(h)) return false;
+    if (off || h->knn_mode == 1 || h->KP != 32 || k < 2 || k > 31 || dd_sharded(h)) return false;
     return h->knn_mode == 2 ? h->emb_rows >= 512 : h->emb_rows >= kClusteredMinRows;
 }
 
@@ -574,6 +613,7 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     const int64_t P = (n + 255) / 256 * 256 + (int64_t)kGroups * 256;  // padded rows: every group wastes < 256
     const int T = (int)(P / tc::TILE), B = (int)(P / 256);
     if ((int64_t)B * T >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "clustered knn: list table too large");
+    const int TL = (k - 1 <= 12) ? 16 : 32;  // candidates kept per row and launch (as in dd_dev_knn)
     // ---- one grow-only allocation, carved up
     size_t bytes = 0;
     auto take = [&](size_t b) {
@@ -586,13 +626,13 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
                  o_gt0 = take(4 * kGroups), o_gt = take(4 * kGroups), o_info = take(64), o_perm = take(4 * P),
                  o_trows = take(4 * T), o_off = take(4 * B), o_list_a = take(4 * (size_t)B * T), o_len_a = take(4 * B),
                  o_list_b = take(4 * (size_t)B * T), o_len_b = take(4 * B), o_order = take(4 * B), o_idx_a = take(4 * P * k),
-                 o_cand_a = take(4 * P * 16), o_cand_b = take(4 * P * 16), o_cand_o = take(4 * n * 32),
+                 o_cand_a = take(4 * P * TL), o_cand_b = take(4 * P * TL), o_cand_o = take(4 * n * 2 * TL),
                  o_cent = take(4 * kGroups * 32), o_acc_sum = take(4 * kGroups * 32), o_acc_sq = take(4 * kGroups * 32),
                  o_bin_lo = take(4 * kGroups), o_bin_scale = take(4 * kGroups), o_emb_p = take(4 * P * 32),
                  o_lo = take(4 * (size_t)T * 32), o_hi = take(4 * (size_t)T * 32), o_tau = take(4 * P), o_dist_a = take(4 * P * k),
-                 o_thr = take(8 * B);
+                 o_thr = take(8 * B), o_lo_t = take(4 * (size_t)T * 32), o_hi_t = take(4 * (size_t)T * 32);
     bool cold = false;
-    if ((int64_t)bytes > h->cap_knn_cl || h->knn_cl_rows != n) {
+    if ((int64_t)bytes > h->cap_knn_cl || h->knn_cl_rows != n || h->knn_cl_tl != TL) {
         if ((int64_t)bytes > h->cap_knn_cl) {
             if (h->d_knn_cl) cudaFree(h->d_knn_cl);
             h->d_knn_cl = nullptr;
@@ -601,6 +641,7 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
             h->cap_knn_cl = (int64_t)bytes;
         }
         h->knn_cl_rows = n;
+        h->knn_cl_tl = TL;  // the carving depends on it
         cold = true;  // no centroids from an earlier call on this problem size
     }
     uint8_t *base = h->d_knn_cl;
@@ -617,10 +658,17 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     b.bin_scale = (float *)(base + o_bin_scale); b.emb_p = (float *)(base + o_emb_p); b.lo = (float *)(base + o_lo);
     b.hi = (float *)(base + o_hi); b.tau = (float *)(base + o_tau); b.dist_a = (float *)(base + o_dist_a);
     b.thr = (double *)(base + o_thr);
+    b.lo_t = (float *)(base + o_lo_t); b.hi_t = (float *)(base + o_hi_t);
     const int64_t op_bytes = (int64_t)T * tc::TILE_BYTES;
     DD_TRY(dd_reserve(h, &h->d_knn_ops, &h->cap_knn_ops, 2 * op_bytes));
     uint8_t *qa = h->d_knn_ops, *cb = h->d_knn_ops + op_bytes;
     const unsigned row_ctas = (unsigned)((n + 255) / 256);
+    const unsigned assign_grid = (unsigned)std::min<int64_t>(2 * h->num_sms, (n + kAssignThreads - 1) / kAssignThreads);
+    static dd_once_per_device assign_attr;  // function attributes are per device
+    assign_attr.run(h->device, [&] {
+        cudaFuncSetAttribute(k_km_assign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAssignSmem);
+        cudaFuncSetAttribute(k_km_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAssignSmem);
+    });
 
     // ---- 1. groups
     if (cold) {
@@ -631,12 +679,12 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     }
     // warm: the final assignment below is itself one Lloyd step (k_grp_axis moves every centroid to its group's mean)
     for (int pass = 0; pass < (cold ? 4 : 0); pass++) {
-        DD_LAUNCH(h, "kcl_assign", (k_km_assign<true, false>), row_ctas, 256, 0, h->d_emb, n, b.cent, b.label, b.acc_sum, b.acc_sq,
-                  b.acc_cnt);
+        DD_LAUNCH(h, "kcl_assign", k_km_assign<false>, assign_grid, kAssignThreads, kAssignSmem, h->d_emb, n, b.cent, b.label,
+                  b.acc_sum, b.acc_sq, b.acc_cnt);
         DD_LAUNCH(h, "kcl_update", k_km_update, kGroups, 32, 0, b.cent, b.acc_sum, b.acc_cnt);
     }
-    DD_LAUNCH(h, "kcl_assign", (k_km_assign<false, true>), row_ctas, 256, 0, h->d_emb, n, b.cent, b.label, b.acc_sum, b.acc_sq,
-              b.acc_cnt);
+    DD_LAUNCH(h, "kcl_assign", k_km_assign<true>, assign_grid, kAssignThreads, kAssignSmem, h->d_emb, n, b.cent, b.label, b.acc_sum,
+              b.acc_sq, b.acc_cnt);
     // ---- 2. order inside the groups, padded layout
     DD_LAUNCH(h, "kcl_axis", k_grp_axis, kGroups, 32, 0, b.cent, b.acc_sum, b.acc_sq, b.acc_cnt, b.axis, b.bin_lo, b.bin_scale);
     DD_CUDA(h, cudaMemsetAsync(b.hist, 0, 4 * kBuckets, h->stream));
@@ -649,24 +697,38 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     DD_LAUNCH(h, "prune_gather", k_prune_gather, (unsigned)((P * 8 + 255) / 256), 256, 0, h->d_emb, b.perm, P, b.emb_p);
     DD_TRY(dd_knn_launch_prep(h, b.emb_p, P, P, qa, cb));
     DD_LAUNCH(h, "prune_boxes", k_prune_boxes, (unsigned)(((int64_t)T * 32 + 255) / 256), 256, 0, b.emb_p, b.perm, T, b.lo, b.hi,
-              b.tile_rows);
+              b.tile_rows, b.lo_t, b.hi_t);
     // ---- 4. launch A (own group) -> thresholds
     DD_LAUNCH(h, "kcl_lists_own", k_lists_own, (unsigned)B, 128, 0, b.block_group, b.group_tile0, b.group_tiles, T, b.off, b.list_a,
               b.len_a);
     DD_LAUNCH(h, "kcl_order", k_block_order, (unsigned)((B + 255) / 256), 256, 0, b.len_a, B, b.order);
-    DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
+    if (TL == 16)
+        DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
+    else
+        DD_TRY(dd_knn_launch_listed32(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
     DD_CUDA(h, cudaMemsetAsync(b.idx_a, 0xff, sizeof(int32_t) * (size_t)P * k, h->stream));  // -1 = "not found"
-    DD_TRY(dd_knn_launch_refine16(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
+    if (TL == 16)
+        DD_TRY(dd_knn_launch_refine16(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
+    else
+        DD_TRY(dd_knn_launch_refine32(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
     DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)B, 256, 0, b.perm, b.idx_a, b.dist_a, (int)k, b.thr);
     // ---- 5. launch B (other groups within the bound), longest lists first, starting from launch A's filter thresholds
-    DD_LAUNCH(h, "kcl_lists_other", k_lists_other, (unsigned)B, 256, 0, b.lo, b.hi, b.tile_rows, b.thr, b.block_group, T, b.list_b,
-              b.len_b);
+    DD_LAUNCH(h, "kcl_lists_other", k_lists_other, (unsigned)B, 256, 0, b.lo, b.hi, b.lo_t, b.hi_t, b.tile_rows, b.thr, b.block_group,
+              T, b.list_b, b.len_b);
     DD_LAUNCH(h, "kcl_order", k_block_order, (unsigned)((B + 255) / 256), 256, 0, b.len_b, B, b.order);
-    DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+    if (TL == 16)
+        DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+    else
+        DD_TRY(dd_knn_launch_listed32(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
     // ---- 6. back to the original numbering, exact re-ranking of both lists together
-    DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * 16 + 255) / 256), 256, 0, b.perm, b.cand_a, P, b.cand_o, 32, 0);
-    DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * 16 + 255) / 256), 256, 0, b.perm, b.cand_b, P, b.cand_o, 32, 16);
-    DD_TRY(dd_knn_launch_refine32(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
+    DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_a, P, b.cand_o, 2 * TL, 0,
+              TL);
+    DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_b, P, b.cand_o, 2 * TL, TL,
+              TL);
+    if (TL == 16)
+        DD_TRY(dd_knn_launch_refine32(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
+    else
+        DD_TRY(dd_knn_launch_refine64(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
     return DD_OK;
 }
 
