@@ -398,32 +398,36 @@ __global__ void __launch_bounds__(128) k_apply(float *__restrict__ Yf, double *_
 }
 
 // Symmetric eigen-decomposition of the L x L Gram matrix by parallel-ordered cyclic Jacobi (float64),
-// eigenvalues sorted in decreasing order.  One CTA, 256 threads.
-__global__ void __launch_bounds__(256) k_jacobi(const double *__restrict__ gram, int L, int LP,
-                                                double *__restrict__ evec, double *__restrict__ eval) {
+// eigenvalues sorted in decreasing order.  One CTA, kJacobiThreads threads, TWO barriers per round: the n / 2 rotations
+// of a round are computed from the diagonal 2 x 2 blocks, then every 2 x 2 block of A gets its column rotation followed by
+// its row rotation in one go (one thread per block), and the columns of V are rotated alongside.  The round-robin schedule
+// is the closed form of "position 0 stays, positions 1 .. n-1 shift by one per round": pos_r[i] = ((i - 1 - r) mod (n - 1)) + 1.
+constexpr int kJacobiThreads = 512;
+__global__ void __launch_bounds__(kJacobiThreads) k_jacobi(const double *__restrict__ gram, int L, int LP,
+                                                           double *__restrict__ evec, double *__restrict__ eval) {
     extern __shared__ double jac_sm[];
     double (*Am)[kMaxLP + 1] = reinterpret_cast<double (*)[kMaxLP + 1]>(jac_sm);
     double (*Vm)[kMaxLP + 1] = reinterpret_cast<double (*)[kMaxLP + 1]>(jac_sm + kMaxLP * (kMaxLP + 1));
     __shared__ double cs_c[kMaxLP / 2], cs_s[kMaxLP / 2];
     __shared__ int pp[kMaxLP / 2], qq[kMaxLP / 2];
-    __shared__ int pos[kMaxLP];
-    __shared__ double offmax;
+    __shared__ int offmax;
     const int tid = threadIdx.x;
     const int n = (L + 1) & ~1;  // even number of players; index L (if padded) is a bye
-    for (int e = tid; e < n * n; e += blockDim.x) {
+    for (int e = tid; e < n * n; e += kJacobiThreads) {
         const int i = e / n, j = e % n;
         Am[i][j] = (i < L && j < L) ? gram[i * LP + j] : 0.0;
         Vm[i][j] = (i == j) ? 1.0 : 0.0;
     }
-    if (tid < n) pos[tid] = tid;
+    if (tid == 0) offmax = 0;
     __syncthreads();
-    const int half = n / 2;
+    const int half = n / 2, m = n - 1;
     for (int sweep = 0; sweep < 30; sweep++) {
-        if (tid == 0) offmax = 0.0;
-        __syncthreads();
         for (int round = 0; round < n - 1; round++) {
             if (tid < half) {
-                int p = pos[tid], q = pos[n - 1 - tid];
+                // players at positions tid and n - 1 - tid of this round
+                const int i0 = tid, i1 = n - 1 - tid;
+                int p = i0 == 0 ? 0 : ((i0 - 1 - round) % m + m) % m + 1;
+                int q = ((i1 - 1 - round) % m + m) % m + 1;
                 if (p > q) { const int t = p; p = q; q = t; }
                 double c = 1.0, s = 0.0;
                 if (q < L) {
@@ -434,45 +438,41 @@ __global__ void __launch_bounds__(256) k_jacobi(const double *__restrict__ gram,
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                         c = 1.0 / sqrt(1.0 + t * t);
                         s = t * c;
-                        if (fabs(apq) > 1e-14 * scale) offmax = 1.0;  // benign race: any writer sets it
+                        if (fabs(apq) > 1e-14 * scale) offmax = 1;  // benign race: any writer sets it
                     }
                 }
                 pp[tid] = p; qq[tid] = q; cs_c[tid] = c; cs_s[tid] = s;
             }
             __syncthreads();
-            // columns p, q of A and V
-            for (int e = tid; e < half * n; e += blockDim.x) {
+            // A <- J^T A J block by block: columns (p2, q2) first, then rows (p1, q1) -- the arithmetic of two separate passes
+            for (int e = tid; e < half * half; e += kJacobiThreads) {
+                const int t1 = e / half, t2 = e % half;
+                const int p1 = pp[t1], q1 = qq[t1], p2 = pp[t2], q2 = qq[t2];
+                const double c1 = cs_c[t1], s1 = cs_s[t1], c2 = cs_c[t2], s2 = cs_s[t2];
+                const double app = Am[p1][p2], apq = Am[p1][q2], aqp = Am[q1][p2], aqq = Am[q1][q2];
+                const double bpp = c2 * app - s2 * apq, bpq = s2 * app + c2 * apq;
+                const double bqp = c2 * aqp - s2 * aqq, bqq = s2 * aqp + c2 * aqq;
+                Am[p1][p2] = c1 * bpp - s1 * bqp;
+                Am[q1][p2] = s1 * bpp + c1 * bqp;
+                Am[p1][q2] = c1 * bpq - s1 * bqq;
+                Am[q1][q2] = s1 * bpq + c1 * bqq;
+            }
+            // V <- V J
+            for (int e = tid; e < half * n; e += kJacobiThreads) {
                 const int t = e / n, i = e % n;
                 const int p = pp[t], q = qq[t];
                 const double c = cs_c[t], s = cs_s[t];
-                const double aip = Am[i][p], aiq = Am[i][q];
-                Am[i][p] = c * aip - s * aiq;
-                Am[i][q] = s * aip + c * aiq;
                 const double vip = Vm[i][p], viq = Vm[i][q];
                 Vm[i][p] = c * vip - s * viq;
                 Vm[i][q] = s * vip + c * viq;
             }
             __syncthreads();
-            // rows p, q of A
-            for (int e = tid; e < half * n; e += blockDim.x) {
-                const int t = e / n, j = e % n;
-                const int p = pp[t], q = qq[t];
-                const double c = cs_c[t], s = cs_s[t];
-                const double apj = Am[p][j], aqj = Am[q][j];
-                Am[p][j] = c * apj - s * aqj;
-                Am[q][j] = s * apj + c * aqj;
-            }
-            __syncthreads();
-            // rotate the tournament: position 0 stays, the rest shift by one
-            int nxt = 0;
-            if (tid < n && tid > 0) nxt = pos[tid == 1 ? n - 1 : tid - 1];
-            __syncthreads();
-            if (tid < n && tid > 0) pos[tid] = nxt;
-            __syncthreads();
         }
-        const bool done = offmax == 0.0;
+        const bool done = offmax == 0;
         __syncthreads();
         if (done) break;
+        if (tid == 0) offmax = 0;
+        __syncthreads();  // the first round of the next sweep may set it again
     }
     // sort eigenvalues (descending) by rank counting; ties by index
     if (tid < L) {
@@ -680,7 +680,7 @@ int run_pca(dd_handle *h, int n_power_iter) {
         }
     }
     // svd(B) with B^T = Z:  B B^T = Z^T Z = gram
-    DD_LAUNCH(h, "jacobi", k_jacobi, 1, 256, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
+    DD_LAUNCH(h, "jacobi", k_jacobi, 1, kJacobiThreads, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm + OFF_KEYS);
     DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, h->d_Zacc, (const float *)nullptr, 0,
               (int)h->G, L, C, sm + OFF_EVEC, keys);
@@ -763,7 +763,7 @@ int run_pca_transposed(dd_handle *h, int n_power_iter) {
     DD_CUDA(h, cudaMemsetAsync(sm + OFF_GRAM, 0, sizeof(double) * kMaxLP * kMaxLP, h->stream));
     DD_LAUNCH(h, "gram_tall", (k_gram<LP, 0>), tall_grid, 256, 0, h->d_Y, nullptr, A, nullptr, 0.0, nullptr, sm + OFF_GRAM,
               sm + OFF_EVAL /*unused sums*/);
-    DD_LAUNCH(h, "jacobi", k_jacobi, 1, 256, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
+    DD_LAUNCH(h, "jacobi", k_jacobi, 1, kJacobiThreads, kJacobiSmem, sm + OFF_GRAM, L, LP, sm + OFF_EVEC, sm + OFF_EVAL);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sm + OFF_KEYS);
     DD_LAUNCH(h, "signs_w", k_signs_w<LP>, (unsigned)((h->G + 127) / 128), 128, 0, (const double *)nullptr, h->d_Qt, ld,
               (int)h->G, L, C, sm + OFF_EVEC, keys);
