@@ -850,6 +850,36 @@ int grid_for(dd_handle *h, size_t smem_bytes) {
 // ------------------------------------------------------------------------------------------------
 int dd_finish_upload(dd_handle *h);
 
+// a handle that borrowed another handle's count matrix (dd_share_counts) forgets the pointers instead of freeing them
+void dd_drop_borrowed_counts(dd_handle *h) {
+    if (!h->counts_borrowed) return;
+    h->d_indptr = nullptr; h->d_indices = nullptr; h->d_data = nullptr; h->d_lib = nullptr; h->d_l1 = nullptr;
+    h->cap_rows = 0; h->cap_nnz = 0;
+    h->counts_borrowed = false;
+}
+
+// Second (third, ...) pipeline on the same GPU: `dst` works on `src`'s resident count matrix and library sizes (read-only
+// for the fit loop) instead of uploading its own copy.  `src` must stay alive and keep its matrix while `dst` uses it.
+extern "C" int dd_share_counts(dd_handle *dst, const dd_handle *src) {
+    if (!dst || !src || dst == src) return dd_fail(dst, DD_ERR_ARG, "dd_share_counts: two different handles are needed");
+    if (!src->d_indptr) return dd_fail(dst, DD_ERR_ARG, "dd_share_counts: the source handle holds no counts");
+    if (dst->device != src->device) return dd_fail(dst, DD_ERR_ARG, "dd_share_counts: the handles live on different devices");
+    DD_CUDA(dst, cudaSetDevice(dst->device));
+    if (!dst->counts_borrowed) {
+        for (void *p : {(void *)dst->d_indptr, (void *)dst->d_indices, (void *)dst->d_data, (void *)dst->d_lib, (void *)dst->d_l1})
+            if (p) cudaFree(p);
+    }
+    dst->d_indptr = src->d_indptr; dst->d_indices = src->d_indices; dst->d_data = src->d_data;
+    dst->d_lib = src->d_lib; dst->d_l1 = src->d_l1;
+    dst->cap_rows = 0; dst->cap_nnz = 0;
+    dst->counts_borrowed = true;
+    dst->N = src->N; dst->G = src->G; dst->nnz = src->nnz; dst->ld = src->ld;
+    dst->h_lib = src->h_lib;
+    dst->nonneg = src->nonneg;
+    dst->synth_csr_valid = false; dst->dense_valid = false; dst->emb_valid = false; dst->M = 0; dst->A = 0;
+    return DD_OK;
+}
+
 extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32_t *indptr,
                                 const int32_t *indices, const float *data) {
     if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_upload_counts: null handle");
@@ -860,6 +890,7 @@ extern "C" int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, 
     if (indptr[0] != 0 || nnz < 0) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: bad indptr");
     if (nnz > 0 && (!indices || !data)) return dd_fail(h, DD_ERR_ARG, "dd_upload_counts: null indices/data");
     DD_CUDA(h, cudaSetDevice(h->device));
+    dd_drop_borrowed_counts(h);
     h->N = n_cells; h->G = n_genes; h->nnz = nnz;
     h->ld = dd_round_up(n_genes, 32);
     h->synth_csr_valid = false; h->dense_valid = false; h->emb_valid = false; h->M = 0; h->A = 0;

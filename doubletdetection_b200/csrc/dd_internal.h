@@ -80,6 +80,7 @@ struct dd_handle {
     float *d_lib = nullptr;   // float32 row sums (_lib_size)
     double *d_l1 = nullptr;   // double sums of |x| (the L1 normaliser of sklearn)
     std::vector<float> h_lib;
+    bool counts_borrowed = false;  // dd_share_counts: the CSR / library-size buffers belong to another handle of this device
     bool nonneg = true;  // no negative value in the uploaded matrix (then L1 norms of row sums are additive)
 
     // ---- synthetics ----
@@ -276,6 +277,7 @@ int dd_dev_colstats(dd_handle *h, bool with_sq);                    // scale.cu
 int dd_dev_standard_scale(dd_handle *h, float max_value);           // scale.cu
 int dd_dev_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter,
                const float *omega_host);                            // pca.cu
+void dd_drop_borrowed_counts(dd_handle *h);                         // csr.cu
 int dd_dev_knn(dd_handle *h, int32_t k);                            // knn.cu
 bool dd_knn_clustered_applies(const dd_handle *h, int32_t k);        // knn_prune.cu
 int dd_dev_knn_clustered(dd_handle *h, int32_t k);                  // knn_prune.cu

@@ -163,6 +163,7 @@ void dd_lv_lane_free(dd_lv_lane &l) {
 extern "C" void dd_destroy(dd_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    dd_drop_borrowed_counts(h);  // borrowed buffers are freed by their owner
     cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     if (h->stream3) cudaStreamSynchronize(h->stream3);

@@ -233,6 +233,7 @@ extern "C" int dd_select_genes(dd_handle *h, int64_t n_sel, const int64_t *genes
     if (!h) return dd_fail(nullptr, DD_ERR_ARG, "dd_select_genes: null handle");
     if (!h->d_indptr) return dd_fail(h, DD_ERR_ARG, "dd_select_genes: upload the counts first");
     if (n_sel < 1 || !genes) return dd_fail(h, DD_ERR_ARG, "dd_select_genes: empty selection");
+    if (h->counts_borrowed) return dd_fail(h, DD_ERR_ARG, "dd_select_genes: the count matrix belongs to another handle");
     const int64_t N = h->N, G = h->G;
     std::vector<int32_t> new_id((size_t)G, -1);
     for (int64_t j = 0; j < n_sel; j++) {

@@ -50,6 +50,10 @@ int dd_abi_version(void);
  * normalise kernel divides by the row sum on the fly with the same rounding. */
 int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32_t *indptr,
                      const int32_t *indices, const float *data);
+/* A second pipeline on the same GPU (the Python shim runs two fit loops per device, each on half of the iterations, so that
+ * one loop's latency-bound PCA kernels run underneath the other's HBM-bound products): `dst` reads `src`'s resident count
+ * matrix and library sizes instead of holding a copy.  `src` must outlive the use and must not be re-uploaded meanwhile. */
+int dd_share_counts(dd_handle *dst, const dd_handle *src);
 /* `_lib_size` (float32[N]) as computed on the device. */
 int dd_get_lib_size(dd_handle *h, float *lib_size_out);
 

@@ -83,6 +83,9 @@ def test_product_arm_line_with_a_stand_in_handle(monkeypatch, capsys):
         def upload_counts(self, csr):
             self.n_cells, self.n_genes = csr.shape
 
+        def share_counts(self, src):
+            self.n_cells, self.n_genes = src.n_cells, src.n_genes
+
         def fit_iterations(self, parents, omega, **kw):
             n_iters, n_synth = parents.shape[:2]
             self.launches += 100
@@ -130,4 +133,5 @@ def test_product_arm_line_with_a_stand_in_handle(monkeypatch, capsys):
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
-    assert d["gpu_launches"] == 200 and set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert d["config"]["pipelines_per_gpu"] == 2  # two pipelined loops per GPU (DD_PIPELINES), 100 launches per loop and step
+    assert d["gpu_launches"] == 400 and set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])

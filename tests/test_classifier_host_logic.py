@@ -29,6 +29,9 @@ class OracleHandle:
         self.raw = csr.copy()
         self.n_cells, self.n_genes = csr.shape
 
+    def share_counts(self, src):  # a second pipeline on the same GPU reads the first one's matrix
+        self.raw, self.n_cells, self.n_genes = src.raw, src.n_cells, src.n_genes
+
     def hvg_variances(self):  # what hvg.cu reproduces: the reference's own scipy expression (doubletdetection.py:166-169)
         return (np.array(self.raw.power(2).mean(axis=0)) - (np.array(self.raw.mean(axis=0))) ** 2)[0]
 

@@ -235,6 +235,9 @@ def _cells_failure_worker(rank, world, port, q):
             def upload_counts(self, csr):
                 pass
 
+            def share_counts(self, src):
+                pass
+
             def shard_cells(self, on):
                 pass
 

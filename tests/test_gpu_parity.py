@@ -518,3 +518,27 @@ def test_default_constructor_fits():
         labels = clf.fit(counts).predict()
     assert labels.shape == (1200,) and clf.all_scores_.shape == (10, 1200)
     assert np.isin(labels[~np.isnan(labels)], (0.0, 1.0)).all()
+
+
+@pytest.mark.parametrize("algo", ["louvain", "phenograph"])
+def test_pipelines_on_one_gpu_give_the_single_loop_result(monkeypatch, algo):
+    """BoostClassifier.fit runs several pipelined loops per GPU (DD_PIPELINES, default 2; handles sharing one resident count
+    matrix through dd_share_counts), each on a contiguous part of the iterations: the result must not depend on it.  The
+    second fit on the same object re-shares the re-uploaded matrix."""
+    from doubletdetection_b200 import BoostClassifier
+
+    counts = datasets.structured_counts(3000, 600, seed=4)
+    fits = {}
+    for pipes in ("1", "2", "3"):
+        monkeypatch.setenv("DD_PIPELINES", pipes)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            clf = BoostClassifier(n_iters=7, clustering_algorithm=algo, random_state=5, n_jobs=4)
+            first = clf.fit(counts)
+            fits[pipes] = (first.communities_.copy(), first.all_log_p_values_.copy(), first.all_scores_.copy())
+            if pipes == "2":
+                again = clf.fit(counts[:2500])  # new matrix on the same handles; the rng stream continues (Q2)
+                assert again.communities_.shape == (7, 2500) and np.isfinite(again.all_scores_).any()
+    for pipes in ("2", "3"):
+        for a, b in zip(fits["1"], fits[pipes]):
+            np.testing.assert_array_equal(a, b)
