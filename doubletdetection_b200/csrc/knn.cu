@@ -276,6 +276,57 @@ __global__ void k_knn_refine(const float *__restrict__ emb, const int *__restric
 }
 
 
+// exact re-ranking of `width` <= 32 PER candidates per query (one or two lists side by side): every lane owns PER of them
+template <int PER>
+__global__ void k_knn_refine_w(const float *__restrict__ emb, const int *__restrict__ cand_i, int width, int64_t q0, int64_t n,
+                               int k, int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = q0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // queries [q0, n)
+    if (q >= n) return;
+    int ci[PER];
+    double d[PER];
+#pragma unroll
+    for (int s = 0; s < PER; s++) {
+        const int col = 32 * s + lane;
+        ci[s] = col < width ? cand_i[q * width + col] : 0x7fffffff;
+        d[s] = INFINITY;
+        if (ci[s] != 0x7fffffff) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(emb + q * 32 + c);
+                const float4 b = *reinterpret_cast<const float4 *>(emb + (int64_t)ci[s] * 32 + c);
+                const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
+                const double dz = (double)a.z - (double)b.z, dw = (double)a.w - (double)b.w;
+                acc += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+            d[s] = acc;
+        }
+    }
+    int rank[PER];
+#pragma unroll
+    for (int t = 0; t < PER; t++) rank[t] = 0;
+    for (int l = 0; l < 32; l++) {
+#pragma unroll
+        for (int s = 0; s < PER; s++) {
+            const double od = __shfl_sync(0xffffffffu, d[s], l);
+            const int oi = __shfl_sync(0xffffffffu, ci[s], l);
+#pragma unroll
+            for (int t = 0; t < PER; t++) rank[t] += (od < d[t]) || (od == d[t] && oi < ci[t]);
+        }
+    }
+    if (lane == 0) {
+        idx_out[q * k] = (int32_t)q;
+        dist_out[q * k] = 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < PER; s++)
+        if (rank[s] < k - 1) {
+            idx_out[q * k + 1 + rank[s]] = ci[s] == 0x7fffffff ? -1 : ci[s];
+            dist_out[q * k + 1 + rank[s]] = (float)sqrt(d[s]);
+        }
+}
+
 // =================================================================================================
 // Tensor-core path (KP == 32, TL == 16): the distance GEMM on tcgen05 / TMEM.
 //
@@ -709,11 +760,11 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     static dd_once_per_device attr_set;  // function attributes are per device
     attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tc::k_knn_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-        cudaFuncSetAttribute(tc::k_knn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         cudaFuncSetAttribute(tc::k_knn_tc<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
-        cudaFuncSetAttribute(tc::k_knn_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
         cudaFuncSetAttribute(tc::k_knn_tc<16, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
-        cudaFuncSetAttribute(tc::k_knn_tc<32, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
+        cudaFuncSetAttribute(tc::k_knn_tc<40, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes<64>());
     });
     DD_LAUNCH(h, "knn_prep", tc::k_knn_prep, (unsigned)(n_pad / 8), 112, 0, h->d_emb, n, n_pad,
               reinterpret_cast<uint4 *>(qa), reinterpret_cast<uint4 *>(cb));
@@ -731,13 +782,13 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
             DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<16, true>), (unsigned)n_pairs, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
                       0, n_pairs, cand_i, h->d_knn_list_off, h->d_knn_list_tiles);
         else
-            DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<32, true>), (unsigned)n_pairs, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
+            DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<40, true>), (unsigned)n_pairs, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
                       0, n_pairs, cand_i, h->d_knn_list_off, h->d_knn_list_tiles);
         if (TL == 16)
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, (int64_t)0, n, k,
                       h->d_knn_idx, h->d_knn_dist);
         else
-            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, (int64_t)0, n, k,
+            DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, 40, (int64_t)0, n, k,
                       h->d_knn_idx, h->d_knn_dist);
         return DD_OK;
     }
@@ -753,17 +804,17 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);
         } else if (h->knn_narrow) {
-            DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<32, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
+            DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<40, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
                       n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
-            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
+            DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, 40, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);
         } else if (TL == 16) {
             DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);
         } else {
-            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<32>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
-            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 32>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
+            DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<40>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
+            DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, 40, q0, q1,
                       k, h->d_knn_idx, h->d_knn_dist);
         }
     }
@@ -792,7 +843,8 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     if (n >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: too many rows for int32 indices");
     const int TL = (k - 1 <= 12) ? 16 : 32;
     const int64_t n_padded = (n + 255) / 256 * 256;  // the tensor-core path keeps lists for whole 256-row CTAs
-    const int64_t need = n * k + n + 2 * n_padded * 32;
+    // candidate lists: 32 per row on the FFMA fallback, up to 40 per row on the tcgen05 path (k - 1 > 12: lists of 40)
+    const int64_t need = n * k + n + n_padded * 32 + n_padded * 40;
     if (need > h->cap_knn) {
         if (h->d_knn_idx_base) cudaFree(h->d_knn_idx_base);
         if (h->d_knn_dist) cudaFree(h->d_knn_dist);
@@ -890,68 +942,26 @@ int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, i
     return DD_OK;
 }
 
-// the same for lists of 32 (k - 1 > 12: PhenoGraph's 30 neighbours)
-int dd_knn_launch_listed32(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
+// the same for lists of 40 (k - 1 > 12: PhenoGraph's 30 neighbours keep a margin of 10 filter ranks)
+int dd_knn_launch_listed40(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
                            const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
                            const float *tau_init, float *tau_out) {
     static dd_once_per_device attr_set;  // function attributes are per device
     attr_set.run(h->device, [&] {
-        cudaFuncSetAttribute(tc::k_knn_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+        cudaFuncSetAttribute(tc::k_knn_tc<40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
-    DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<32, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
+    DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<40, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
               n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out);
     return DD_OK;
 }
 
-// exact re-ranking of 64 candidates per query (two lists of 32 side by side): every lane owns two of them
-__global__ void k_knn_refine64(const float *__restrict__ emb, const int *__restrict__ cand_i, int64_t n, int k,
-                               int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= n) return;
-    int ci[2];
-    double d[2];
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        ci[s] = cand_i[q * 64 + 32 * s + lane];
-        d[s] = INFINITY;
-        if (ci[s] != 0x7fffffff) {
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-                const float4 a = *reinterpret_cast<const float4 *>(emb + q * 32 + c);
-                const float4 b = *reinterpret_cast<const float4 *>(emb + (int64_t)ci[s] * 32 + c);
-                const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y;
-                const double dz = (double)a.z - (double)b.z, dw = (double)a.w - (double)b.w;
-                acc += dx * dx + dy * dy + dz * dz + dw * dw;
-            }
-            d[s] = acc;
-        }
-    }
-    int rank[2] = {0, 0};
-    for (int l = 0; l < 32; l++) {
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const double od = __shfl_sync(0xffffffffu, d[s], l);
-            const int oi = __shfl_sync(0xffffffffu, ci[s], l);
-#pragma unroll
-            for (int t = 0; t < 2; t++) rank[t] += (od < d[t]) || (od == d[t] && oi < ci[t]);
-        }
-    }
-    if (lane == 0) {
-        idx_out[q * k] = (int32_t)q;
-        dist_out[q * k] = 0.f;
-    }
-#pragma unroll
-    for (int s = 0; s < 2; s++)
-        if (rank[s] < k - 1) {
-            idx_out[q * k + 1 + rank[s]] = ci[s] == 0x7fffffff ? -1 : ci[s];
-            dist_out[q * k + 1 + rank[s]] = (float)sqrt(d[s]);
-        }
+// re-ranking launchers for knn_prune.cu: lists of 40 (one launch's), and two lists of 40 side by side
+int dd_knn_launch_refine40(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
+    DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, 40, (int64_t)0, n, k, idx_out, dist_out);
+    return DD_OK;
 }
-
-int dd_knn_launch_refine64(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
-    DD_LAUNCH(h, "knn_refine", k_knn_refine64, (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, n, k, idx_out, dist_out);
+int dd_knn_launch_refine80(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
+    DD_LAUNCH(h, "knn_refine", k_knn_refine_w<3>, (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, 80, (int64_t)0, n, k, idx_out, dist_out);
     return DD_OK;
 }
 

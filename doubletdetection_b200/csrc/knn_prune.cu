@@ -13,10 +13,12 @@ int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, i
                            const float *tau_init, float *tau_out);                                                   // knn.cu
 int dd_knn_launch_refine32(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
-int dd_knn_launch_listed32(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
+int dd_knn_launch_listed40(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
                            const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
                            const float *tau_init, float *tau_out);                                                   // knn.cu
-int dd_knn_launch_refine64(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
+int dd_knn_launch_refine40(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
+                           float *dist_out);                                                                         // knn.cu
+int dd_knn_launch_refine80(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 int dd_knn_launch_refine16(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
@@ -270,7 +272,7 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((n_pad * 16 + 255) / 256), 256, 0, d_perm.p, d_cand_p.p, n_pad,
               d_cand_o.p, 16, 0, 16);
     // output buffers of the ordinary kNN (sized by an earlier dd_knn call on this embedding, or here)
-    if (!h->d_knn_idx || h->cap_knn < n * k + n + 2 * ((n + 255) / 256 * 256) * 32)
+    if (!h->d_knn_idx || h->cap_knn < n * k + n + ((n + 255) / 256 * 256) * 72)
         return dd_fail(h, DD_ERR_ARG, "dd_knn_pruned: call dd_knn on this embedding first (it sizes the output buffers)");
     DD_TRY(dd_knn_launch_refine16(h, h->d_emb, d_cand_o.p, n, (int)k, h->d_knn_idx, h->d_knn_dist));
     DD_TRY(dd_stage_end(h, "knn"));
@@ -613,7 +615,7 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     const int64_t P = (n + 255) / 256 * 256 + (int64_t)kGroups * 256;  // padded rows: every group wastes < 256
     const int T = (int)(P / tc::TILE), B = (int)(P / 256);
     if ((int64_t)B * T >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "clustered knn: list table too large");
-    const int TL = (k - 1 <= 12) ? 16 : 32;  // candidates kept per row and launch (as in dd_dev_knn)
+    const int TL = (k - 1 <= 12) ? 16 : 40;  // candidates kept per row and launch (as in dd_dev_knn)
     // ---- one grow-only allocation, carved up
     size_t bytes = 0;
     auto take = [&](size_t b) {
@@ -705,12 +707,12 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     if (TL == 16)
         DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
     else
-        DD_TRY(dd_knn_launch_listed32(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
+        DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
     DD_CUDA(h, cudaMemsetAsync(b.idx_a, 0xff, sizeof(int32_t) * (size_t)P * k, h->stream));  // -1 = "not found"
     if (TL == 16)
         DD_TRY(dd_knn_launch_refine16(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
     else
-        DD_TRY(dd_knn_launch_refine32(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
+        DD_TRY(dd_knn_launch_refine40(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
     DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)B, 256, 0, b.perm, b.idx_a, b.dist_a, (int)k, b.thr);
     // ---- 5. launch B (other groups within the bound), longest lists first, starting from launch A's filter thresholds
     DD_LAUNCH(h, "kcl_lists_other", k_lists_other, (unsigned)B, 256, 0, b.lo, b.hi, b.lo_t, b.hi_t, b.tile_rows, b.thr, b.block_group,
@@ -719,7 +721,7 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     if (TL == 16)
         DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
     else
-        DD_TRY(dd_knn_launch_listed32(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+        DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
     // ---- 6. back to the original numbering, exact re-ranking of both lists together
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_a, P, b.cand_o, 2 * TL, 0,
               TL);
@@ -728,7 +730,7 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     if (TL == 16)
         DD_TRY(dd_knn_launch_refine32(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
     else
-        DD_TRY(dd_knn_launch_refine64(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
+        DD_TRY(dd_knn_launch_refine80(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
     return DD_OK;
 }
 
