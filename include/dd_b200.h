@@ -107,8 +107,11 @@ int dd_pca(dd_handle *h, int32_t n_comp, int32_t n_random, int32_t n_power_iter,
            float *emb_out, double *singular_values_out);
 /* ---- sklearn's EXACT PCA branches (svd_solver "covariance_eigh" / "full", picked by "auto" for <= 1000 genes with
  * >= 10x as many augmented cells, for matrices with max(shape) <= 500 and for n_components >= 0.8 min(shape):
- * sklearn/decomposition/_pca.py:524-536, 560-640; reached from doubletdetection.py:309-314).  The device does what scales
- * with the number of cells; the caller eigendecomposes the small Gram matrix in between (numpy.linalg.eigh in the shim).
+ * sklearn/decomposition/_pca.py:524-536, 560-640; reached from doubletdetection.py:309-314) and svd_solver="arpack", which
+ * doubletdetection.py:308 selects when pseudocount == 1 keeps the matrix sparse (:296-297; dd_normalise_log then computes
+ * log1p, and the zeros of the dense matrix are the gaps of the sparse one).  The device does what scales with the number of
+ * cells; the caller solves the small symmetric eigenproblem in between (scipy.linalg.eigh, top n_comp pairs, in the shim).
+ * The Gram side is limited to 16384 rows.
  *   dd_centered_gram  float64 Gram matrix of the centred dense matrix: transposed == 0 -> G x G (sum over cells, i.e.
  *                     (A - 1) x the covariance matrix), else A x A (sum over genes); out: n x n row-major, symmetric
  *   dd_project        X_pca = (D - mean) V for sign-fixed components V (float64[G x n_comp], row-major); leaves the
@@ -120,7 +123,8 @@ int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const floa
 
 /* ---- sc.pp.neighbors(n_neighbors=k) exact kNN, doubletdetection.py:331-336 -------------
  * Exact Euclidean k nearest neighbours of every augmented cell in the embedding; column 0 is
- * the cell itself (distance 0), then the k-1 nearest others by (distance, index).
+ * the cell itself (distance 0), then the k-1 nearest others by (distance, index).  2 <= k <= 31 (PhenoGraph: 30 + self).
+ * A 3xBF16 tcgen05 distance GEMM filters 16 (k <= 13) or 40 candidates per row, which are re-ranked in float64.
  * idx_out int32[A*k], dist_out float32[A*k] (may be NULL). */
 int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
 
