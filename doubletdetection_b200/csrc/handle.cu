@@ -178,6 +178,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     dd_comm_destroy(h);
     if (h->lv_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lv_graph_exec);
     if (h->lvw_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->lvw_graph_exec);
+    if (h->h_knn_cl_pairs) cudaFreeHost(h->h_knn_cl_pairs);
     for (int32_t *p : h->slot_knn) cudaFreeHost(p);
     for (double *p : h->slot_flag) cudaFreeHost(p);
     if (h->h_lv_rounds) cudaFreeHost(h->h_lv_rounds);

@@ -583,6 +583,29 @@ __global__ void k_block_order(const int32_t *__restrict__ len, int n_blocks, int
     order[rank] = b;
 }
 
+// info[2], info[3] = block-tile pairs of launch A and launch B (read back asynchronously: the fit loop uses it to notice
+// embeddings without cluster structure, where the ordering does not pay)
+__global__ void k_sum_pairs(const int32_t *__restrict__ len_a, const int32_t *__restrict__ len_b, int n_blocks,
+                            int32_t *__restrict__ info) {
+    __shared__ long long s_a[256], s_b[256];
+    long long a = 0, b = 0;
+    for (int i = threadIdx.x; i < n_blocks; i += 256) {
+        a += len_a[i];
+        b += len_b[i];
+    }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 256; i++) {
+            a += s_a[i];
+            b += s_b[i];
+        }
+        info[2] = (int32_t)min(a, 0x7fffffffll);
+        info[3] = (int32_t)min(b, 0x7fffffffll);
+    }
+}
+
 struct ClusteredBuffers {
     int32_t *label, *bucket, *acc_cnt, *axis, *hist, *start, *cursor, *block_group, *group_tile0, *group_tiles, *info, *perm,
         *tile_rows, *off, *list_a, *len_a, *list_b, *len_b, *order, *idx_a;
@@ -599,7 +622,17 @@ static constexpr int64_t kClusteredMinRows = 50000;
 bool dd_knn_clustered_applies(const dd_handle *h, int32_t k) {
     static const bool off = getenv("DD_KNN_DENSE") != nullptr;
     if (off || h->knn_mode == 1 || h->KP != 32 || k < 2 || k > 31 || dd_sharded(h)) return false;
-    return h->knn_mode == 2 ? h->emb_rows >= 512 : h->emb_rows >= kClusteredMinRows;
+    if (h->knn_mode == 2) return h->emb_rows >= 512;
+    if (h->emb_rows < kClusteredMinRows) return false;
+    // by size -- unless an earlier call on this problem size reported that the ordering does not pay: on an embedding
+    // without cluster structure the bounds exclude nothing and the padded order visits MORE pairs than the all-tiles kernel
+    // (uniform points: 1.2 x).  The counts arrive asynchronously (pinned host memory), one or two calls late.
+    if (h->h_knn_cl_pairs && h->knn_cl_rows == h->emb_rows) {
+        const int64_t visited = (int64_t)h->h_knn_cl_pairs[0] + h->h_knn_cl_pairs[1];
+        const int64_t dense = ((h->emb_rows + 255) / 256) * ((h->emb_rows + 127) / 128);
+        if (visited > dense * 8 / 10) return false;
+    }
+    return true;
 }
 
 // 0 = choose by size (default), 1 = always the all-tiles kernel, 2 = always the cluster-ordered path (tests, A/B timing)
@@ -644,7 +677,9 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
         }
         h->knn_cl_rows = n;
         h->knn_cl_tl = TL;  // the carving depends on it
-        cold = true;  // no centroids from an earlier call on this problem size
+        cold = true;
+        if (!h->h_knn_cl_pairs && cudaMallocHost(&h->h_knn_cl_pairs, 2 * sizeof(int32_t)) != cudaSuccess) h->h_knn_cl_pairs = nullptr;
+        if (h->h_knn_cl_pairs) h->h_knn_cl_pairs[0] = h->h_knn_cl_pairs[1] = 0;  // nothing known about this problem size yet  // no centroids from an earlier call on this problem size
     }
     uint8_t *base = h->d_knn_cl;
     ClusteredBuffers b;
@@ -722,6 +757,9 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
         DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
     else
         DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+    DD_LAUNCH(h, "kcl_pairs", k_sum_pairs, 1, 256, 0, b.len_a, b.len_b, B, b.info);
+    if (h->h_knn_cl_pairs)
+        DD_CUDA(h, cudaMemcpyAsync(h->h_knn_cl_pairs, b.info + 2, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     // ---- 6. back to the original numbering, exact re-ranking of both lists together
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_a, P, b.cand_o, 2 * TL, 0,
               TL);

@@ -101,3 +101,34 @@ def test_clustered_knn_on_the_headline_embedding(handle):
     np.testing.assert_array_equal(got_idx, want_idx)
     np.testing.assert_array_equal(got_dist, want_dist)
     print(f"[c3 embedding, k = 31] block-tile pairs visited: {(stats['pairs_a'] + stats['pairs_b']) / (489 * 977):.3f}")
+
+
+def test_auto_mode_falls_back_when_the_ordering_does_not_pay(handle):
+    """Uniform points have no cluster structure: the bounds exclude nothing and the padded order visits more pairs than the
+    all-tiles kernel.  In the default mode the handle notices (pair counts read back asynchronously) and later calls on the
+    same problem size use the all-tiles kernel; clustered data keeps the cluster-ordered path."""
+    rs = np.random.default_rng(3)
+    n = 60000
+    for kind, expect_listed in (("uniform", False), ("blobs", True)):
+        if kind == "uniform":
+            emb = (rs.random(size=(n + 256, 30)) * 10).astype(np.float32)  # another size: nothing known about it yet
+        else:
+            emb = (rs.normal(size=(n, 30)) * 0.3 + rs.integers(0, 40, size=(n, 1)) * np.r_[np.full(8, 3.0), np.zeros(22)][None, :]
+                   + rs.integers(0, 5, size=(n, 1)) * np.r_[np.zeros(8), np.full(4, 5.0), np.zeros(18)][None, :]).astype(np.float32)
+        handle.upload_embedding(emb)
+        handle.set_knn_mode(1)
+        want, _ = handle.knn(10)
+        handle.set_knn_mode(0)
+        handle.set_kernel_timing(True)
+        first, _ = handle.knn(10)   # by size: cluster-ordered
+        second, _ = handle.knn(10)  # the counts of the first call are known by now
+        before = handle.kernel_timing_report()
+        third, _ = handle.knn(10)
+        after = handle.kernel_timing_report()
+        handle.set_kernel_timing(False)
+        for got in (first, second, third):
+            np.testing.assert_array_equal(got, want)
+        listed = after.get("knn_tc_listed", (0, 0))[1] - before.get("knn_tc_listed", (0, 0))[1]
+        dense = after.get("knn_tc", (0, 0))[1] - before.get("knn_tc", (0, 0))[1]
+        print(f"\n[{kind}] third call: {listed} list-driven launches, {dense} all-tiles launches")
+        assert (listed > 0) == expect_listed and (dense > 0) == (not expect_listed)
