@@ -108,7 +108,9 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     for (int s = 0; s < n_slots; s++) {
         slots[s].graph = h->slot_knn[s];
         slots[s].flag = h->slot_flag[s];
-        if (cudaEventCreateWithFlags(&slots[s].done, cudaEventDisableTiming) != cudaSuccess) {
+        // blocking sync: a host worker that waits for its iteration sleeps instead of spinning (8 ranks x 2 pipelines share
+        // the box's cores with the issuing threads)
+        if (cudaEventCreateWithFlags(&slots[s].done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
             cleanup();
             return dd_fail(h, DD_ERR_CUDA, "dd_fit_iterations: event creation");
         }
