@@ -84,6 +84,7 @@ SIGNATURES = {
     "dd_knn_listed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p]),
     "dd_set_knn_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "dd_knn_clustered_stats": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
+    "dd_knn_uncertified": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
     "dd_knn_pruned": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_f32p, c_i64p]),
     "dd_louvain_knn": (
         ctypes.c_int,
@@ -492,6 +493,12 @@ class Handle:
     def set_knn_mode(self, mode):
         """0 = cluster-ordered kNN for large embeddings (default), 1 = always the all-tiles kernel, 2 = always cluster-ordered."""
         self._check(self._lib.dd_set_knn_mode(self._h, int(mode)))
+
+    def knn_uncertified(self):
+        """Rows of the last kNN call that the filter's certificate could not clear (re-done by float64 brute force)."""
+        out = ctypes.c_int64(0)
+        self._check(self._lib.dd_knn_uncertified(self._h, ctypes.byref(out)))
+        return int(out.value)
 
     def knn_clustered_stats(self):
         out = np.zeros(4, dtype=np.int64)

@@ -436,6 +436,14 @@ class BoostClassifier:
         self._pending, self._fitted = None, {}
         if cells_dist is not None:
             out = merge_owned_iterations(cells_dist, out, self.device)
+        if self.verbose:
+            # the reference prints these lines while it iterates (:193-194, :350-355); the pipelined loop has no such moment, so
+            # the same lines are printed for the iterations this process ran once they are finished
+            for i in range(it0, it1):
+                full = np.concatenate([out["communities"][i], out["synth_communities"][i]])
+                community_sizes = [int(np.count_nonzero(full == c)) for c in np.unique(full)]
+                print("Iteration {:3}/{}".format(i + 1, self.n_iters))
+                print("Found clusters [{0}, ... {2}], with sizes: {1}\n".format(full.min(), community_sizes, full.max()))
         self.stage_ms_ = out["stage_ms"]
         if dist is not None and self.n_iters > 1:
             # iteration-sharded: the (n_iters, .) rows stay where they were computed until somebody asks for them

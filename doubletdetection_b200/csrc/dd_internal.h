@@ -145,6 +145,9 @@ struct dd_handle {
     uint8_t *d_knn_cl = nullptr;
     int64_t cap_knn_cl = 0, knn_cl_rows = -1;
     int knn_cl_tl = 0;
+    int32_t *d_knn_cert = nullptr;      // [0] rows the filter certificate could not clear, [4..] their indices (knn.cu)
+    int64_t cap_knn_cert = 0;
+    int32_t *h_knn_uncert = nullptr;    // pinned copy of the count of the last kNN call
     int32_t *h_knn_cl_pairs = nullptr;  // pinned: block-tile pairs of launch A / B of the last completed cluster-ordered kNN
     int64_t cap_knn_list_off = 0, cap_knn_list_tiles = 0;
     int knn_list_pairs = 0;

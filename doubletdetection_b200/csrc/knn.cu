@@ -276,10 +276,34 @@ __global__ void k_knn_refine(const float *__restrict__ emb, const int *__restric
 }
 
 
+// ---- certificate of the approximate filter ------------------------------------------------------------------------------
+// The tcgen05 kernels rank candidates by an APPROXIMATE score (3 of the 9 bf16 cross products of q.c, fp32 accumulation):
+//     |approx - exact| <= e(q, c) = 2^-16 |q| |c| + 2^-26 |c|^2        (dropped terms 3 x 2^-18, accumulation, norm term)
+// A row's result is exact iff no candidate the filter EXCLUDED is closer than the reported k-th neighbour.  An excluded y
+// scored at most the filter's last kept candidate, hence at most the kept candidate z with the largest exact distance
+// sqrt(D) plus e(z); if y were closer than the k-th neighbour (distance d_k), then |y| <= |q| + d_k, and
+//     D - d_k^2  >  2 [ e(|q| + d_k) + e(|q| + sqrt(D)) ]
+// contradicts it.  Rows that fail the test (embeddings whose offset from the origin is ~1000 x their local spacing) are
+// appended to `rows` and re-done by brute force in float64 (k_knn_exact_rows): the result is exact either way.
+// Two lists (cluster-ordered kNN): list A = own group, list B = other groups above A's threshold; an excluded candidate is
+// bounded by A's last kept (own group, or B not full) or by B's last kept (B full): D = min(D_A, B full ? D_B : D_A).
+struct KnnCert {
+    int list_w = 0;          // 0: no certification
+    int n_lists = 1;
+    int *count = nullptr;    // number of uncertified rows
+    int *rows = nullptr;     // their indices (capacity `cap`)
+    int cap = 0;
+};
+
+__device__ __forceinline__ double knn_filter_err(double qn, double r) {
+    const double c = qn + r;
+    return 1.52587890625e-05 * qn * c + 1.4901161193847656e-08 * c * c;  // 2^-16, 2^-26
+}
+
 // exact re-ranking of `width` <= 32 PER candidates per query (one or two lists side by side): every lane owns PER of them
 template <int PER>
 __global__ void k_knn_refine_w(const float *__restrict__ emb, const int *__restrict__ cand_i, int width, int64_t q0, int64_t n,
-                               int k, int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+                               int k, int32_t *__restrict__ idx_out, float *__restrict__ dist_out, KnnCert cert = KnnCert()) {
     const int lane = threadIdx.x & 31;
     const int64_t q = q0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // queries [q0, n)
     if (q >= n) return;
@@ -325,6 +349,111 @@ __global__ void k_knn_refine_w(const float *__restrict__ emb, const int *__restr
             idx_out[q * k + 1 + rank[s]] = ci[s] == 0x7fffffff ? -1 : ci[s];
             dist_out[q * k + 1 + rank[s]] = (float)sqrt(d[s]);
         }
+    if (cert.list_w > 0) {  // uniform
+        // per list: is it full (no "none" entry), and the largest exact distance^2 among its entries
+        double dmax[2] = {0.0, 0.0}, dk2 = -1.0;
+        bool hole[2] = {false, false};
+#pragma unroll
+        for (int s = 0; s < PER; s++) {
+            const int col = 32 * s + lane;
+            if (col < width) {
+                const int li = col >= cert.list_w ? 1 : 0;
+                if (ci[s] == 0x7fffffff) hole[li] = true; else dmax[li] = fmax(dmax[li], d[s]);
+                if (rank[s] == k - 2 && ci[s] != 0x7fffffff) dk2 = d[s];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dmax[0] = fmax(dmax[0], __shfl_xor_sync(0xffffffffu, dmax[0], o));
+            dmax[1] = fmax(dmax[1], __shfl_xor_sync(0xffffffffu, dmax[1], o));
+            dk2 = fmax(dk2, __shfl_xor_sync(0xffffffffu, dk2, o));
+        }
+        const bool hole0 = __any_sync(0xffffffffu, hole[0]), hole1 = __any_sync(0xffffffffu, hole[1]);
+        const float x = emb[q * 32 + lane];
+        double qn2 = (double)x * (double)x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qn2 += __shfl_xor_sync(0xffffffffu, qn2, o);
+        const double da = hole0 ? INFINITY : dmax[0];
+        const double db = (cert.n_lists > 1 && !hole1) ? dmax[1] : da;
+        const double D = fmin(da, db);
+        bool ok = true;
+        if (D < INFINITY && dk2 >= 0.0) {  // something was excluded, and k - 1 neighbours were reported
+            const double qn = sqrt(qn2);
+            ok = D - dk2 > 2.0 * (knn_filter_err(qn, sqrt(dk2)) + knn_filter_err(qn, sqrt(D)));
+        }
+        if (!ok && lane == 0) {
+            const int slot = atomicAdd(cert.count, 1);
+            if (slot < cert.cap) cert.rows[slot] = (int)q;
+        }
+    }
+}
+
+// Brute force in float64 for the rows the certificate could not clear: one warp per row, every lane keeps the k - 1 best of
+// its share of the candidates (sorted by (distance, index), the order of the re-ranking kernels), the lanes' lists are merged
+// by repeated warp-wide minimum.  Same distance arithmetic as k_knn_refine_w, so the two paths agree to the bit.
+__global__ void __launch_bounds__(256) k_knn_exact_rows(const float *__restrict__ emb, int64_t n, const int *__restrict__ rows,
+                                                        const int *__restrict__ count, int cap, int k,
+                                                        int32_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = gridDim.x * (blockDim.x >> 5);
+    const int total = min(*count, cap);
+    const int kk = k - 1;
+    for (int it = warp; it < total; it += n_warps) {
+        const int64_t q = rows[it];
+        float4 qa[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) qa[c] = *reinterpret_cast<const float4 *>(emb + q * 32 + 4 * c);
+        double ld[31];
+        int li[31];
+        int cnt = 0;
+        for (int64_t cnd = lane; cnd < n; cnd += 32) {
+            if (cnd == q) continue;
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float4 b = *reinterpret_cast<const float4 *>(emb + cnd * 32 + 4 * c);
+                const double dx = (double)qa[c].x - (double)b.x, dy = (double)qa[c].y - (double)b.y;
+                const double dz = (double)qa[c].z - (double)b.z, dw = (double)qa[c].w - (double)b.w;
+                acc += dx * dx + dy * dy + dz * dz + dw * dw;
+            }
+            if (cnt == kk && !(acc < ld[kk - 1])) continue;  // candidates arrive in increasing index: a tie loses
+            int pos = cnt < kk ? cnt : kk - 1;
+            while (pos > 0 && acc < ld[pos - 1]) {
+                ld[pos] = ld[pos - 1];
+                li[pos] = li[pos - 1];
+                pos--;
+            }
+            ld[pos] = acc;
+            li[pos] = (int)cnd;
+            if (cnt < kk) cnt++;
+        }
+        int head = 0;
+        for (int r = 0; r < kk; r++) {
+            double bd = head < cnt ? ld[head] : INFINITY;
+            int bi = head < cnt ? li[head] : 0x7fffffff;
+            int bl = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                if (od < bd || (od == bd && oi < bi)) {
+                    bd = od;
+                    bi = oi;
+                    bl = ol;
+                }
+            }
+            if (bl == lane && bi != 0x7fffffff) head++;
+            if (lane == 0) {
+                idx_out[q * k + 1 + r] = bi == 0x7fffffff ? -1 : bi;
+                dist_out[q * k + 1 + r] = (float)sqrt(bd);
+            }
+        }
+        if (lane == 0) {
+            idx_out[q * k] = (int32_t)q;
+            dist_out[q * k] = 0.f;
+        }
+    }
 }
 
 // =================================================================================================
@@ -749,6 +878,33 @@ int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     return DD_OK;
 }
 
+// Final re-ranking of a kNN call: exact float64 order of the filter's candidates (`width` per row: n_lists lists of list_w),
+// the filter's certificate, and the float64 brute-force fix-up of the rows it could not clear.  Rows [q0, q1).
+int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int width, int list_w, int n_lists, int64_t q0,
+                        int64_t q1, int64_t n, int k) {
+    DD_TRY(dd_reserve(h, &h->d_knn_cert, &h->cap_knn_cert, n + 4));
+    DD_CUDA(h, cudaMemsetAsync(h->d_knn_cert, 0, sizeof(int32_t), h->stream));
+    KnnCert cert;
+    cert.list_w = list_w;
+    cert.n_lists = n_lists;
+    cert.count = h->d_knn_cert;
+    cert.rows = h->d_knn_cert + 4;
+    cert.cap = (int)n;
+    const unsigned grid = (unsigned)((q1 - q0 + 7) / 8);
+    if (width <= 32)
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<1>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert);
+    else if (width <= 64)
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert);
+    else
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<3>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert);
+    DD_LAUNCH(h, "knn_exact_rows", k_knn_exact_rows, (unsigned)(h->num_sms * 2), 256, 0, emb, n, (const int *)cert.rows,
+              (const int *)cert.count, cert.cap, k, h->d_knn_idx, h->d_knn_dist);
+    if (!h->h_knn_uncert && cudaMallocHost(&h->h_knn_uncert, sizeof(int32_t)) != cudaSuccess) h->h_knn_uncert = nullptr;
+    if (h->h_knn_uncert)
+        DD_CUDA(h, cudaMemcpyAsync(h->h_knn_uncert, h->d_knn_cert, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    return DD_OK;
+}
+
 int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     const int64_t n = h->emb_rows;
     const int n_tiles = (int)((n + tc::TILE - 1) / tc::TILE);
@@ -784,6 +940,7 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
         else
             DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<40, true>), (unsigned)n_pairs, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles,
                       0, n_pairs, cand_i, h->d_knn_list_off, h->d_knn_list_tiles);
+        // (test hook with caller-made lists: candidates outside the lists are not the filter's doing -- no certificate)
         if (TL == 16)
             DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((n + 7) / 8), 256, 0, h->d_emb, cand_i, (int64_t)0, n, k,
                       h->d_knn_idx, h->d_knn_dist);
@@ -801,21 +958,17 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
         if (h->knn_narrow && TL == 16) {
             DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<16, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
                       n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
-            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
-                      k, h->d_knn_idx, h->d_knn_dist);
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 16, 16, 1, q0, q1, n, k));
         } else if (h->knn_narrow) {
             DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<40, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
                       n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
-            DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, 40, q0, q1,
-                      k, h->d_knn_idx, h->d_knn_dist);
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 40, 40, 1, q0, q1, n, k));
         } else if (TL == 16) {
             DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
-            DD_LAUNCH(h, "knn_refine", (k_knn_refine<32, 16>), (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, q0, q1,
-                      k, h->d_knn_idx, h->d_knn_dist);
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 16, 16, 1, q0, q1, n, k));
         } else {
             DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<40>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
-            DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((q1 - q0 + 7) / 8), 256, 0, h->d_emb, cand_i, 40, q0, q1,
-                      k, h->d_knn_idx, h->d_knn_dist);
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 40, 40, 1, q0, q1, n, k));
         }
     }
     if (W > 1) {
@@ -882,6 +1035,17 @@ extern "C" int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out
     if (dist_out)
         DD_CUDA(h, cudaMemcpyAsync(dist_out, h->d_knn_dist, sizeof(float) * n * k, cudaMemcpyDeviceToHost, h->stream));
     DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+// How many rows of the last dd_knn / fit-loop kNN on this handle the filter's certificate could not clear (they were re-done by
+// float64 brute force: the result is exact either way; a large number means the embedding sits far from the origin
+// relative to its local spacing and the kNN runs at brute-force speed).
+extern "C" int dd_knn_uncertified(dd_handle *h, int64_t *count_out) {
+    if (!h || !count_out) return dd_fail(h, DD_ERR_ARG, "dd_knn_uncertified: null argument");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    *count_out = h->h_knn_uncert ? (int64_t)*h->h_knn_uncert : 0;
     return DD_OK;
 }
 
@@ -955,13 +1119,9 @@ int dd_knn_launch_listed40(dd_handle *h, const uint8_t *qa, const uint8_t *cb, i
     return DD_OK;
 }
 
-// re-ranking launchers for knn_prune.cu: lists of 40 (one launch's), and two lists of 40 side by side
+// re-ranking launcher for knn_prune.cu: lists of 40 (one launch's)
 int dd_knn_launch_refine40(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
     DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, 40, (int64_t)0, n, k, idx_out, dist_out);
-    return DD_OK;
-}
-int dd_knn_launch_refine80(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out, float *dist_out) {
-    DD_LAUNCH(h, "knn_refine", k_knn_refine_w<3>, (unsigned)((n + 7) / 8), 256, 0, emb, cand_i, 80, (int64_t)0, n, k, idx_out, dist_out);
     return DD_OK;
 }
 

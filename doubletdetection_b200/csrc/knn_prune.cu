@@ -18,8 +18,8 @@ int dd_knn_launch_listed40(dd_handle *h, const uint8_t *qa, const uint8_t *cb, i
                            const float *tau_init, float *tau_out);                                                   // knn.cu
 int dd_knn_launch_refine40(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
-int dd_knn_launch_refine80(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
-                           float *dist_out);                                                                         // knn.cu
+int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int width, int list_w, int n_lists, int64_t q0,
+                        int64_t q1, int64_t n, int k);                                                               // knn.cu
 int dd_knn_launch_refine16(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 
@@ -765,10 +765,8 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
               TL);
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_b, P, b.cand_o, 2 * TL, TL,
               TL);
-    if (TL == 16)
-        DD_TRY(dd_knn_launch_refine32(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
-    else
-        DD_TRY(dd_knn_launch_refine80(h, h->d_emb, b.cand_o, n, (int)k, h->d_knn_idx, h->d_knn_dist));
+    // (with the filter's certificate over both lists, and the float64 fix-up of the rows it cannot clear)
+    DD_TRY(dd_knn_refine_final(h, h->d_emb, b.cand_o, 2 * TL, TL, 2, 0, n, n, (int)k));
     return DD_OK;
 }
 

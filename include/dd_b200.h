@@ -151,6 +151,10 @@ int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32_t *perm, c
  * always cluster-ordered.  dd_knn_clustered_stats: block-tile pairs visited by the last such call: [launch A, launch B,
  * blocks in use, tiles in use]. */
 int dd_set_knn_mode(dd_handle *h, int32_t mode);
+/* Exactness: the tcgen05 filter's scores carry an error of at most 2^-16 |q| |c|; the re-ranking kernel certifies every row
+ * (no excluded candidate can be closer than the reported k-th neighbour) and the rows it cannot clear are re-done by float64
+ * brute force on the device.  dd_knn_uncertified: how many rows of the last kNN call took that route. */
+int dd_knn_uncertified(dd_handle *h, int64_t *count_out);
 int dd_knn_clustered_stats(dd_handle *h, int64_t *stats_out);
 
 

@@ -94,7 +94,8 @@ def test_clustered_knn_on_the_headline_embedding(handle):
     np.testing.assert_array_equal(got_dist, want_dist)
     np.testing.assert_array_equal(got_idx2, want_idx)
     frac = (stats["pairs_a"] + stats["pairs_b"]) / (489 * 977)
-    print(f"\n[c3 embedding] block-tile pairs visited: {frac:.3f} of the dense kernel's ({stats})")
+    print(f"\n[c3 embedding] block-tile pairs visited: {frac:.3f} of the dense kernel's ({stats}); rows the filter certificate "
+          f"could not clear: {handle.knn_uncertified()} of {emb.shape[0]}")
     assert frac < 0.6
     # PhenoGraph's neighbourhood (30 + self): lists of 32 per launch, 64 candidates re-ranked
     want_idx, want_dist, got_idx, got_dist, got_idx2, stats = _both(handle, np.ascontiguousarray(emb, dtype=np.float32), 31)
@@ -132,3 +133,36 @@ def test_auto_mode_falls_back_when_the_ordering_does_not_pay(handle):
         dense = after.get("knn_tc", (0, 0))[1] - before.get("knn_tc", (0, 0))[1]
         print(f"\n[{kind}] third call: {listed} list-driven launches, {dense} all-tiles launches")
         assert (listed > 0) == expect_listed and (dense > 0) == (not expect_listed)
+
+
+@pytest.mark.parametrize("offset", [3.0, 300.0, 30000.0])
+def test_filter_certificate_and_exact_fixup(handle, offset):
+    """The tcgen05 filter's error grows with |q| |c| (2^-16 relative): clusters that sit `offset` away from the origin with a
+    local spacing of ~1 make it useless from offset ~ 1e3 on.  The re-ranking kernel certifies every row and the rows it
+    cannot clear are re-done by float64 brute force, so BOTH kernels must equal the host's float64 brute force at any
+    offset -- and the certificate must clear (almost) everything at ordinary scales."""
+    rs = np.random.default_rng(int(offset))
+    n, k = 20000, 10
+    emb = (rs.normal(size=(n, 30)) + rs.integers(0, 6, size=(n, 1)) * np.r_[np.full(4, offset), np.zeros(26)][None, :]).astype(np.float32)
+    e64 = emb.astype(np.float64)
+    rows = rs.choice(n, size=300, replace=False)
+    truth = np.empty((rows.size, k), dtype=np.int64)
+    for i, r in enumerate(rows):
+        d2 = ((e64[r][None, :] - e64) ** 2).sum(1)
+        d2[r] = -1.0
+        truth[i] = np.lexsort((np.arange(n), d2))[:k]
+    handle.upload_embedding(emb)
+    counts = {}
+    for mode in (1, 2):
+        handle.set_knn_mode(mode)
+        try:
+            idx, dist = handle.knn(k)
+            counts[mode] = handle.knn_uncertified()
+        finally:
+            handle.set_knn_mode(0)
+        np.testing.assert_array_equal(idx[rows], truth, err_msg=f"mode {mode}, offset {offset}")
+    print(f"\n[offset {offset}] rows the certificate could not clear: all-tiles {counts[1]}, cluster-ordered {counts[2]} of {n}")
+    if offset <= 3.0:
+        assert counts[1] <= n // 100 and counts[2] <= n // 100
+    if offset >= 30000.0:
+        assert counts[1] > 0 and counts[2] > 0
