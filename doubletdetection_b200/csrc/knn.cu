@@ -878,6 +878,8 @@ int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
     return DD_OK;
 }
 
+}  // namespace
+
 // Final re-ranking of a kNN call: exact float64 order of the filter's candidates (`width` per row: n_lists lists of list_w),
 // the filter's certificate, and the float64 brute-force fix-up of the rows it could not clear.  Rows [q0, q1).
 int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int width, int list_w, int n_lists, int64_t q0,
@@ -904,6 +906,8 @@ int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int w
         DD_CUDA(h, cudaMemcpyAsync(h->h_knn_uncert, h->d_knn_cert, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     return DD_OK;
 }
+
+namespace {
 
 int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
     const int64_t n = h->emb_rows;
