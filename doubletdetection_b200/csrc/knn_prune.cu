@@ -497,14 +497,30 @@ __global__ void k_bucket_scatter(int64_t n, const int32_t *__restrict__ bucket, 
     perm[start[b] + atomicAdd(cursor + b, 1)] = (int32_t)row;
 }
 
-// launch A lists: the tiles of the block's own group that hold real rows (a contiguous range), at stride n_tiles_max
+// launch A lists: the tiles of the block's own group that hold real rows, at stride n_tiles_max -- starting with the block's
+// own two tiles and moving outwards (the group is ordered in slabs: the nearest slabs come first, so a row's list fills
+// with near-final candidates at once and the later tiles rarely pass its threshold)
 __global__ void k_lists_own(const int32_t *__restrict__ block_group, const int32_t *__restrict__ group_tile0,
                             const int32_t *__restrict__ group_tiles, int n_tiles_max, int32_t *__restrict__ off,
                             int32_t *__restrict__ list, int32_t *__restrict__ len) {
     const int b = blockIdx.x;
     const int g = block_group[b];
     const int t0 = g >= 0 ? group_tile0[g] : 0, nt = g >= 0 ? group_tiles[g] : 0;
-    for (int t = threadIdx.x; t < nt; t += blockDim.x) list[(int64_t)b * n_tiles_max + t] = t0 + t;
+    // position of the block's first tile inside the group's real tiles (the group's last block may hold fewer real tiles)
+    const int own = min(max(b * tc::QT - t0, 0), max(nt - 1, 0));
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        // i-th entry: own, own + 1, own - 1, own + 2, own - 2, ... folded back into [0, nt)
+        const int step = (i + 1) / 2;
+        int t = (i & 1) ? own + step : own - step;
+        // once one side runs out the other side continues
+        const int left = own, right = nt - 1 - own;  // tiles available on either side
+        if (step > min(left, right)) {
+            const int m = min(left, right);
+            const int rest = i - 2 * m;  // entries after the symmetric part (i >= 2 m + 1)
+            t = left < right ? own + m + rest : own - m - rest;
+        }
+        list[(int64_t)b * n_tiles_max + i] = t0 + t;
+    }
     if (threadIdx.x == 0) {
         off[b] = b * n_tiles_max;
         len[b] = nt;

@@ -166,3 +166,36 @@ def test_filter_certificate_and_exact_fixup(handle, offset):
         assert counts[1] <= n // 100 and counts[2] <= n // 100
     if offset >= 30000.0:
         assert counts[1] > 0 and counts[2] > 0
+
+
+def test_building_block_hooks_listed_and_pruned(handle):
+    """The two test hooks the cluster-ordered path grew out of: ``dd_knn_listed`` (caller-made tile lists per 256-row block)
+    and ``dd_knn_pruned`` (caller-made padded permutation; boxes, launch A, thresholds, lists, launch B on the device)."""
+    rs = np.random.default_rng(12)
+    n, k = 6000, 10
+    emb = (rs.normal(size=(n, 30)) + rs.integers(0, 3, size=(n, 1)) * np.r_[np.full(8, 6.0), np.zeros(22)][None, :]).astype(np.float32)
+    handle.upload_embedding(emb)
+    handle.set_knn_mode(1)
+    try:
+        want, want_dist = handle.knn(k)
+        n_tiles, n_blocks = -(-n // 128), -(-(-(-n // 128)) // 2)
+        # every block visits every tile: the list-driven kernel must reproduce the all-tiles kernel
+        off = np.arange(n_blocks + 1, dtype=np.int32) * n_tiles
+        tiles = np.tile(np.arange(n_tiles, dtype=np.int32), n_blocks)
+        got, got_dist = handle.knn_listed(k, off, tiles)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(got_dist, want_dist)
+        # three groups by the planted offset, padded to whole blocks
+        group = np.rint(emb[:, 0] / 6.0).clip(0, 2).astype(int)
+        perm, block_group = [], []
+        for g in range(3):
+            ids = np.nonzero(group == g)[0]
+            pad = (-ids.size) % 256
+            perm.append(np.concatenate([ids, np.full(pad, -1, dtype=ids.dtype)]))
+            block_group += [g] * ((ids.size + pad) // 256)
+        idx, dist, stats = handle.knn_pruned(k, np.concatenate(perm), np.asarray(block_group), n)
+        np.testing.assert_array_equal(idx, want)
+        np.testing.assert_array_equal(dist, want_dist)
+        assert stats["pairs_a"] > 0
+    finally:
+        handle.set_knn_mode(0)
