@@ -87,6 +87,7 @@ def shim(monkeypatch):
     from doubletdetection_b200 import _capi, classifier
 
     monkeypatch.setattr(_capi, "Handle", OracleHandle)
+    monkeypatch.setenv("DD_PIPELINES", "1")  # the stand-in calls BLAS: keep it on one thread (see test_gpu_test_logic_dryrun.py)
     OracleHandle.calls = []
     return classifier.BoostClassifier
 
@@ -223,3 +224,38 @@ def test_exact_pca_branches_match_sklearn(shape, solver):
     lead = slice(0, 3)
     assert np.abs(want[:, lead] - truth[:, lead]).max() / np.abs(truth[:, lead]).max() < 1e-3
     np.testing.assert_array_equal(h.emb, emb)
+
+
+def test_fit_iterations_pipelined_merges_the_pieces():
+    """``_capi.fit_iterations_pipelined``: contiguous pieces of the iteration range, one per handle, run in threads; result rows
+    merged, stage times summed except wall / device_total (longest loop); errors re-raised on the caller's thread."""
+    from doubletdetection_b200 import _capi
+
+    class Piece:
+        def __init__(self, tag, fail=False):
+            self.tag, self.fail, self.seen = tag, fail, None
+
+        def fit_iterations(self, parents, omega, *, iter_begin, iter_end, n_host_threads, **kw):
+            if self.fail:
+                raise NotImplementedError("boom")
+            self.seen = (iter_begin, iter_end, n_host_threads)
+            n_iters = parents.shape[0]
+            out = dict(scores=np.zeros((n_iters, 5)), log_p=np.zeros((n_iters, 5)), communities=np.zeros((n_iters, 5), np.int32),
+                       synth_communities=np.zeros((n_iters, 2), np.int32),
+                       stage_ms=dict(pca=1.0, wall=10.0 + self.tag, device_total=9.0 + self.tag))
+            for key in ("scores", "log_p", "communities", "synth_communities"):
+                out[key][iter_begin:iter_end] = self.tag + 1
+            return out
+
+    parents = np.zeros((7, 2, 2), dtype=np.int64)
+    hs = [Piece(0), Piece(1), Piece(2)]
+    out = _capi.fit_iterations_pipelined(hs, parents, None, iter_begin=1, iter_end=7, n_host_threads=7)
+    assert [h.seen for h in hs] == [(1, 3, 2), (3, 5, 2), (5, 7, 2)]
+    np.testing.assert_array_equal(out["communities"][:, 0], [0, 1, 1, 2, 2, 3, 3])
+    np.testing.assert_array_equal(out["scores"][:, 0], [0, 1, 1, 2, 2, 3, 3])
+    assert out["stage_ms"] == dict(pca=3.0, wall=12.0, device_total=11.0, pipelines=3.0)
+    # fewer iterations than handles: one loop per iteration at most; a single handle takes the plain path
+    out = _capi.fit_iterations_pipelined(hs, parents, None, iter_begin=2, iter_end=3, n_host_threads=4)
+    assert hs[0].seen == (2, 3, 4) and "pipelines" not in out["stage_ms"]
+    with pytest.raises(NotImplementedError):
+        _capi.fit_iterations_pipelined([Piece(0), Piece(1, fail=True)], parents, None, n_host_threads=2)

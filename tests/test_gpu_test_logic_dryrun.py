@@ -15,6 +15,10 @@ def oracle_backed(monkeypatch):
     from doubletdetection_b200 import _capi
 
     monkeypatch.setattr(_capi, "Handle", OracleHandle)
+    # one pipelined loop: the stand-in runs the oracle's sklearn / BLAS calls, and two Python threads inside OpenBLAS at the
+    # same time change the rounding of its LATER calls in this process (the float32 goldens of test_oracle_golden.py are
+    # bit-exact only for an undisturbed BLAS); the product's two loops run CUDA work, not BLAS
+    monkeypatch.setenv("DD_PIPELINES", "1")
     OracleHandle.calls = []
     return _capi
 
