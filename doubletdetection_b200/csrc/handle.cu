@@ -107,10 +107,17 @@ extern "C" int dd_create(int device, dd_handle **out) {
     // highest priority its CTAs are placed first whenever an SM frees resources, so it keeps pace with the main stream
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+    // A/B switches (levels above the lowest priority, clamped to the device's range): DD_PRIO_MAIN (PCA), DD_PRIO_BUILD (dense
+    // build), DD_PRIO_KNN
+    auto prio_of = [&](const char *name) {
+        const char *e = getenv(name);
+        const int up = e ? atoi(e) : 0;
+        return std::max(prio_greatest, prio_least - std::max(0, up));
+    };
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_of("DD_PRIO_MAIN")) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
-        cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_of("DD_PRIO_BUILD")) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, prio_of("DD_PRIO_KNN")) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_pca_done[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_pca_done[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_emb_free[0], cudaEventDisableTiming) != cudaSuccess ||
