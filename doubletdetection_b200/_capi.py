@@ -60,6 +60,7 @@ SIGNATURES = {
     "dd_upload_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, c_i32p, c_i32p, c_f32p]),
     "dd_get_lib_size": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
     "dd_share_counts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dd_counts_all_finite": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]),
     "dd_hvg_variances": (ctypes.c_int, [ctypes.c_void_p, c_f32p]),
     "dd_select_genes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i64p]),
     "dd_counts_nnz": (ctypes.c_int, [ctypes.c_void_p, c_i64p]),
@@ -363,6 +364,11 @@ class Handle:
         self.n_cells, self.n_genes = csr.shape
         self._check(self._lib.dd_upload_counts(self._h, self.n_cells, self.n_genes, _ptr(indptr, ctypes.c_int32),
                                                _ptr(indices, ctypes.c_int32), _ptr(data, ctypes.c_float)))
+
+    def counts_all_finite(self):
+        out = ctypes.c_int32(1)
+        self._check(self._lib.dd_counts_all_finite(self._h, ctypes.byref(out)))
+        return bool(out.value)
 
     def share_counts(self, src):
         """Work on ``src``'s resident count matrix (another handle on the same GPU) instead of uploading a copy."""

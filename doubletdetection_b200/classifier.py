@@ -326,8 +326,13 @@ class BoostClassifier:
         import time as _time
 
         _t = [_time.perf_counter()]
-        raw_counts = check_array(  # :149-155
-            raw_counts, accept_sparse="csr", ensure_all_finite=True, ensure_2d=True, dtype="float32"
+        # :149-155.  For sparse input the finiteness scan (a full pass over the values on one host core) is left to the
+        # device, which looks at every value anyway while it sums the rows; if it finds NaN / inf the reference's own call
+        # is repeated below to raise sklearn's error.
+        sparse_in = sp_sparse.issparse(raw_counts)
+        counts_in = raw_counts
+        raw_counts = check_array(
+            raw_counts, accept_sparse="csr", ensure_all_finite=not sparse_in, ensure_2d=True, dtype="float32"
         )
         if sp_sparse.issparse(raw_counts) is not True:  # :157-160
             if self.verbose:
@@ -383,6 +388,9 @@ class BoostClassifier:
             for i in range(self.n_iters):
                 parents[i] = self.rng.choice(num_cells, size=(num_synths, 2), replace=self.replace)
             upload.result()  # re-raises what the upload raised
+        if sparse_in and not h.counts_all_finite():
+            check_array(counts_in, accept_sparse="csr", ensure_all_finite=True, ensure_2d=True, dtype="float32")  # raises
+            raise ValueError("Input contains NaN or infinity.")
         _t.append(_time.perf_counter())
 
         it0, it1 = 0, self.n_iters

@@ -47,7 +47,8 @@ __global__ void k_row_sums(const int32_t *__restrict__ indptr, const float *__re
             const float v = __ldg(data + p);
             acc += v;
             acc1 += fabs((double)v);
-            if (v < 0.f) *any_negative = 1;
+            if (v < 0.f) any_negative[0] = 1;
+            if (!isfinite(v)) any_negative[1] = 1;  // NaN / inf: what check_array(ensure_all_finite=True) looks for (:149-155)
         }
         acc = warp_sum_f(acc);
         acc1 = warp_sum_d(acc1);
@@ -876,6 +877,7 @@ extern "C" int dd_share_counts(dd_handle *dst, const dd_handle *src) {
     dst->N = src->N; dst->G = src->G; dst->nnz = src->nnz; dst->ld = src->ld;
     dst->h_lib = src->h_lib;
     dst->nonneg = src->nonneg;
+    dst->all_finite = src->all_finite;
     dst->synth_csr_valid = false; dst->dense_valid = false; dst->emb_valid = false; dst->M = 0; dst->A = 0;
     return DD_OK;
 }
@@ -926,14 +928,23 @@ int dd_finish_upload(dd_handle *h) {
     const int64_t n_cells = h->N;
     const int grid = h->num_sms * 8;
     int *d_neg = reinterpret_cast<int *>(h->d_l1 + n_cells);  // one spare slot behind the L1 sums
-    DD_CUDA(h, cudaMemsetAsync(d_neg, 0, sizeof(int), h->stream));
+    DD_CUDA(h, cudaMemsetAsync(d_neg, 0, 2 * sizeof(int), h->stream));
     DD_LAUNCH(h, "row_sums", k_row_sums, grid, 256, 0, h->d_indptr, h->d_data, n_cells, h->d_lib, h->d_l1, d_neg);
-    int neg = 0;
-    DD_CUDA(h, cudaMemcpyAsync(&neg, d_neg, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int neg[2] = {0, 0};
+    DD_CUDA(h, cudaMemcpyAsync(neg, d_neg, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->h_lib.resize(n_cells);
     DD_CUDA(h, cudaMemcpyAsync(h->h_lib.data(), h->d_lib, sizeof(float) * n_cells, cudaMemcpyDeviceToHost, h->stream));
     DD_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->nonneg = neg == 0;
+    h->nonneg = neg[0] == 0;
+    h->all_finite = neg[1] == 0;
+    return DD_OK;
+}
+
+// 1 if the uploaded matrix holds only finite values (the device looked at every entry while summing the rows): lets the
+// caller skip the host-side finiteness scan of check_array (:149-155) and run it only to produce sklearn's error message.
+extern "C" int dd_counts_all_finite(dd_handle *h, int32_t *out) {
+    if (!h || !out || !h->d_indptr) return dd_fail(h, DD_ERR_ARG, "dd_counts_all_finite: upload the counts first");
+    *out = h->all_finite ? 1 : 0;
     return DD_OK;
 }
 

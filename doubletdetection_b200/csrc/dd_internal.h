@@ -80,6 +80,7 @@ struct dd_handle {
     float *d_lib = nullptr;   // float32 row sums (_lib_size)
     double *d_l1 = nullptr;   // double sums of |x| (the L1 normaliser of sklearn)
     std::vector<float> h_lib;
+    bool all_finite = true;  // no NaN / inf among the uploaded values (k_row_sums)
     bool counts_borrowed = false;  // dd_share_counts: the CSR / library-size buffers belong to another handle of this device
     bool nonneg = true;  // no negative value in the uploaded matrix (then L1 norms of row sums are additive)
 

@@ -54,6 +54,9 @@ int dd_upload_counts(dd_handle *h, int64_t n_cells, int64_t n_genes, const int32
  * one loop's latency-bound PCA kernels run underneath the other's HBM-bound products): `dst` reads `src`'s resident count
  * matrix and library sizes instead of holding a copy.  `src` must outlive the use and must not be re-uploaded meanwhile. */
 int dd_share_counts(dd_handle *dst, const dd_handle *src);
+/* 1 if every uploaded value is finite (checked on the device while the library sizes are summed): the shim then skips the
+ * host-side scan of check_array(ensure_all_finite=True) (:149-155) and only runs it to raise sklearn's own error. */
+int dd_counts_all_finite(dd_handle *h, int32_t *all_finite_out);
 /* `_lib_size` (float32[N]) as computed on the device. */
 int dd_get_lib_size(dd_handle *h, float *lib_size_out);
 

@@ -86,6 +86,9 @@ def test_product_arm_line_with_a_stand_in_handle(monkeypatch, capsys):
         def share_counts(self, src):
             self.n_cells, self.n_genes = src.n_cells, src.n_genes
 
+        def counts_all_finite(self):
+            return True
+
         def fit_iterations(self, parents, omega, **kw):
             n_iters, n_synth = parents.shape[:2]
             self.launches += 100

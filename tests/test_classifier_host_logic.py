@@ -29,6 +29,9 @@ class OracleHandle:
         self.raw = csr.copy()
         self.n_cells, self.n_genes = csr.shape
 
+    def counts_all_finite(self):
+        return bool(np.isfinite(self.raw.data).all())
+
     def share_counts(self, src):  # a second pipeline on the same GPU reads the first one's matrix
         self.raw, self.n_cells, self.n_genes = src.raw, src.n_cells, src.n_genes
 
@@ -259,3 +262,16 @@ def test_fit_iterations_pipelined_merges_the_pieces():
     assert hs[0].seen == (2, 3, 4) and "pipelines" not in out["stage_ms"]
     with pytest.raises(NotImplementedError):
         _capi.fit_iterations_pipelined([Piece(0), Piece(1, fail=True)], parents, None, n_host_threads=2)
+
+
+def test_sparse_input_with_nan_raises_sklearns_error(shim):
+    """Sparse input skips check_array's host-side finiteness scan (the device checks while it sums the rows); a matrix with
+    NaN / inf must still end in sklearn's ValueError (doubletdetection.py:149-155)."""
+    import scipy.sparse as sp_sparse
+
+    x = sp_sparse.csr_matrix(np.random.default_rng(0).poisson(1.0, (600, 120)).astype(np.float32))
+    x.data[17] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(ValueError, match="NaN"):
+            shim(n_iters=2, clustering_algorithm="louvain").fit(x)

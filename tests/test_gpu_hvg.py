@@ -87,3 +87,16 @@ def test_classifier_hvg_on_device_equals_host_prologue(monkeypatch):
     np.testing.assert_array_equal(dev.top_var_genes_, host.top_var_genes_)
     np.testing.assert_array_equal(dev.communities_, host.communities_)
     np.testing.assert_array_equal(dev.all_log_p_values_, host.all_log_p_values_)
+
+
+def test_sparse_input_with_nan_or_inf_raises_like_check_array():
+    """The finiteness check of check_array (:149-155) runs on the device for sparse input; the error is sklearn's."""
+    from doubletdetection_b200 import BoostClassifier
+
+    for bad in (np.nan, np.inf):
+        x = sp_sparse.csr_matrix(np.random.default_rng(0).poisson(1.0, (600, 120)).astype(np.float32))
+        x.data[1234] = bad
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with pytest.raises(ValueError):
+                BoostClassifier(n_iters=2, clustering_algorithm="louvain").fit(x)
