@@ -832,6 +832,143 @@ __global__ void __launch_bounds__(kV4MaxWarps * 32, 1)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all rows have landed before the CTA retires
 }
 
+// DD_DENSE_V=5: variant 4 with the gathers taken off the row's critical path.  Variant 4 loads a row's index / value lists
+// inside the scatter loops, four at a time: with 16-18 warps per SM that is ~5 KB of CSR reads in flight per SM, a
+// fraction of what HBM's latency x bandwidth product asks for (~70 KB per SM) -- the kernel waits for its own gathers
+// (0.85 ms).  Here a warp issues ALL loads of its next row (up to kV5PF entries per lane and parent, i.e. 384 per list) into
+// registers before it does anything else with the current one, so 18 warps keep ~60 KB in flight per SM; rows with longer lists
+// finish from global memory.  Same row algorithm (constant fill, scatter, tag merge of the two parents in the shared-memory
+// row buffer, one bulk store per row).
+constexpr int kV5PF = 12, kV5MaxWarps = 16;
+struct V5Regs {
+    int ia[kV5PF], ib[kV5PF];
+    float va[kV5PF], vb[kV5PF];
+};
+
+__global__ void __launch_bounds__(kV5MaxWarps * 32, 1)
+    k_dense_rows_v5(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
+                    const double *__restrict__ l1_rows, const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
+                    int64_t m0, int64_t m_loc, int n_genes, int ld, float median, float pc, float *__restrict__ dense) {
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)ld * 4u;  // multiple of 128
+    float *buf = reinterpret_cast<float *>(tma_smem + (size_t)wl * row_bytes);
+    uint32_t *bits = reinterpret_cast<uint32_t *>(buf);
+    const int64_t gw = (int64_t)blockIdx.x * nw + wl, n_warps = (int64_t)gridDim.x * nw;
+    const int64_t n_rows = n_loc + m_loc;
+    const int64_t my_rows = gw < n_rows ? (n_rows - gw + n_warps - 1) / n_warps : 0;
+    const float logpc = logf(pc);
+
+    auto load_desc = [&](int64_t k) {
+        V4Desc d;
+        const int64_t w = gw + k * n_warps;
+        d.synth = w < m_loc;
+        d.row = d.synth ? n_loc + w : w - m_loc;
+        d.sb = 0;
+        d.nb = 0;
+        if (!d.synth) {
+            const int64_t src = n0 + d.row;
+            d.sa = __ldg(indptr + src);
+            d.na = __ldg(indptr + src + 1) - d.sa;
+            d.l1 = __ldg(l1_rows + src);
+        } else {
+            const int64_t r = m0 + w;
+            const int64_t pa = __ldg(parents + 2 * r), pb = __ldg(parents + 2 * r + 1);
+            d.sa = __ldg(indptr + pa);
+            d.na = __ldg(indptr + pa + 1) - d.sa;
+            d.sb = __ldg(indptr + pb);
+            d.nb = __ldg(indptr + pb + 1) - d.sb;
+            d.l1 = __ldg(l1_rows + pa) + __ldg(l1_rows + pb);
+        }
+        return d;
+    };
+    auto load_lists = [&](const V4Desc &d, V5Regs &r) {
+#pragma unroll
+        for (int j = 0; j < kV5PF; j++) {
+            const int p = lane + 32 * j;
+            const bool ina = p < d.na, inb = p < d.nb;
+            r.ia[j] = ina ? __ldg(indices + d.sa + p) : -1;
+            r.va[j] = ina ? __ldg(data + d.sa + p) : 0.f;
+            r.ib[j] = inb ? __ldg(indices + d.sb + p) : -1;
+            r.vb[j] = inb ? __ldg(data + d.sb + p) : 0.f;
+        }
+    };
+
+    V4Desc cur = my_rows > 0 ? load_desc(0) : V4Desc{};
+    V5Regs r;
+    if (my_rows > 0) load_lists(cur, r);
+    for (int64_t k = 0; k < my_rows; k++) {
+        V4Desc nxt = cur;
+        if (k + 1 < my_rows) nxt = load_desc(k + 1);  // consumed at the end of this iteration
+        // the bulk store of the previous row must have finished READING the buffer before it is refilled
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        for (int j = 4 * lane; j < ld; j += 128) {
+            float4 v;
+            v.x = j < n_genes ? logpc : 0.f;
+            v.y = j + 1 < n_genes ? logpc : 0.f;
+            v.z = j + 2 < n_genes ? logpc : 0.f;
+            v.w = j + 3 < n_genes ? logpc : 0.f;
+            *reinterpret_cast<float4 *>(buf + j) = v;
+        }
+        __syncwarp();
+        const double l1 = cur.l1;
+        const int32_t *ia = indices + cur.sa, *ib = indices + cur.sb;
+        const float *da = data + cur.sa, *db = data + cur.sb;
+        if (!cur.synth) {
+#pragma unroll
+            for (int j = 0; j < kV5PF; j++)
+                if (r.ia[j] >= 0 && r.va[j] != 0.f) buf[r.ia[j]] = norm_log(r.va[j], l1, median, pc);
+            for (int p = lane + 32 * kV5PF; p < cur.na; p += 32) {
+                const float v = da[p];
+                if (v != 0.f) buf[ia[p]] = norm_log(v, l1, median, pc);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kV5PF; j++)
+                if (r.ia[j] >= 0) bits[r.ia[j]] = kTagBits | (uint32_t)(lane + 32 * j + 1);
+            for (int p = lane + 32 * kV5PF; p < cur.na; p += 32) bits[ia[p]] = kTagBits | (uint32_t)(p + 1);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kV5PF; j++)
+                if (r.ib[j] >= 0) {
+                    float v = r.vb[j];
+                    const uint32_t x = bits[r.ib[j]];
+                    if (is_tag(x)) v += da[(int)(x & kTagPayload) - 1];
+                    buf[r.ib[j]] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+                }
+            for (int p = lane + 32 * kV5PF; p < cur.nb; p += 32) {
+                const int col = ib[p];
+                float v = db[p];
+                const uint32_t x = bits[col];
+                if (is_tag(x)) v += da[(int)(x & kTagPayload) - 1];
+                buf[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kV5PF; j++)
+                if (r.ia[j] >= 0 && is_tag(bits[r.ia[j]])) buf[r.ia[j]] = r.va[j] != 0.f ? norm_log(r.va[j], l1, median, pc) : logpc;
+            for (int p = lane + 32 * kV5PF; p < cur.na; p += 32) {
+                const int col = ia[p];
+                const float v = da[p];
+                if (is_tag(bits[col])) buf[col] = v != 0.f ? norm_log(v, l1, median, pc) : logpc;
+            }
+        }
+        __syncwarp();  // the row is complete in shared memory
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy read
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dense + cur.row * (int64_t)ld),
+                         "r"(csr_smem_u32(buf)), "r"(row_bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+        cur = nxt;
+        if (k + 1 < my_rows) load_lists(cur, r);  // every gather of the next row goes out now
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all rows have landed before the CTA retires
+}
+
 int pick_chunk(int64_t ld) { return (int)std::min<int64_t>(ld, kMaxChunk); }
 
 // The dense build is latency-bound with one 12 KB row buffer per warp (16 warps / SM); staging 1024 columns
@@ -1116,6 +1253,23 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
                     cudaFuncSetAttribute(k_dense_rows_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 });
                 DD_LAUNCH(h, "dense_rows", k_dense_rows_v4, h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
+                          h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
+                          pseudocount, h->d_dense);
+                h->dense_valid = true;
+                h->emb_valid = false;
+                return DD_OK;
+            }
+        }
+        if (variant == 5) {  // variant 4 + the next row's gathers issued into registers a row ahead
+            static const int v5_warps = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 16;
+            const size_t row_bytes = (size_t)h->ld * 4;
+            const int nw = (int)std::min<size_t>(std::min(std::max(v5_warps, 1), kV5MaxWarps), (224 * 1024) / row_bytes);
+            if (nw >= 4) {
+                static dd_once_per_device attr5;  // function attributes are per device
+                attr5.run(h->device, [&] {
+                    cudaFuncSetAttribute(k_dense_rows_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                });
+                DD_LAUNCH(h, "dense_rows", k_dense_rows_v5, h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
                           h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
                           pseudocount, h->d_dense);
                 h->dense_valid = true;
