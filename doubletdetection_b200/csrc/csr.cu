@@ -839,12 +839,14 @@ __global__ void __launch_bounds__(kV4MaxWarps * 32, 1)
 // registers before it does anything else with the current one, so 18 warps keep ~60 KB in flight per SM; rows with longer lists
 // finish from global memory.  Same row algorithm (constant fill, scatter, tag merge of the two parents in the shared-memory
 // row buffer, one bulk store per row).
-constexpr int kV5PF = 12, kV5MaxWarps = 16;
+template <int kV5PF>
 struct V5Regs {
     int ia[kV5PF], ib[kV5PF];
     float va[kV5PF], vb[kV5PF];
 };
 
+// <12, 16>: lists up to 384 entries from registers, 16 warps (121 registers); <10, 18>: 320 entries, 18 warps
+template <int kV5PF, int kV5MaxWarps>
 __global__ void __launch_bounds__(kV5MaxWarps * 32, 1)
     k_dense_rows_v5(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ data,
                     const double *__restrict__ l1_rows, const int64_t *__restrict__ parents, int64_t n0, int64_t n_loc,
@@ -882,7 +884,7 @@ __global__ void __launch_bounds__(kV5MaxWarps * 32, 1)
         }
         return d;
     };
-    auto load_lists = [&](const V4Desc &d, V5Regs &r) {
+    auto load_lists = [&](const V4Desc &d, V5Regs<kV5PF> &r) {
 #pragma unroll
         for (int j = 0; j < kV5PF; j++) {
             const int p = lane + 32 * j;
@@ -895,7 +897,7 @@ __global__ void __launch_bounds__(kV5MaxWarps * 32, 1)
     };
 
     V4Desc cur = my_rows > 0 ? load_desc(0) : V4Desc{};
-    V5Regs r;
+    V5Regs<kV5PF> r;
     if (my_rows > 0) load_lists(cur, r);
     for (int64_t k = 0; k < my_rows; k++) {
         V4Desc nxt = cur;
@@ -1219,7 +1221,9 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
     DD_TRY(dd_reserve(h, &h->d_dense, &h->cap_dense, need));
     // DD_DENSE_V=0 keeps the shared-memory row-buffer kernel (A/B comparison; also used when the merge-through-
     // the-row trick does not apply: negative values, or rows too long for the tag payload)
-    static const int variant = getenv("DD_DENSE_V") ? atoi(getenv("DD_DENSE_V")) : 1;
+    // default 5: rows assembled in shared memory from register-prefetched lists (0.49 ms at c3 = 59 % of the HBM peak); rows too
+    // long for >= 8 row buffers per SM (more than ~7000 genes) fall through to variant 1 (fill + scatter through L2, 0.76 ms)
+    static const int variant = getenv("DD_DENSE_V") ? atoi(getenv("DD_DENSE_V")) : 5;
     const bool sharded = dd_sharded(h);
     if ((variant != 0 && h->nonneg && h->G < (int64_t)kTagPayload) || sharded) {
         if (!h->nonneg || h->G >= (int64_t)kTagPayload)
@@ -1260,18 +1264,24 @@ int dd_dev_build_dense(dd_handle *h, float median, float pseudocount) {
                 return DD_OK;
             }
         }
-        if (variant == 5) {  // variant 4 + the next row's gathers issued into registers a row ahead
+        if (variant == 5) {  // variant 4 + the next row's gathers issued into registers a row ahead (the default, see below)
             static const int v5_warps = getenv("DD_DENSE_WARPS") ? atoi(getenv("DD_DENSE_WARPS")) : 16;
             const size_t row_bytes = (size_t)h->ld * 4;
-            const int nw = (int)std::min<size_t>(std::min(std::max(v5_warps, 1), kV5MaxWarps), (224 * 1024) / row_bytes);
-            if (nw >= 4) {
+            const int nw = (int)std::min<size_t>(std::min(std::max(v5_warps, 1), 18), (224 * 1024) / row_bytes);
+            if (nw >= 8) {
                 static dd_once_per_device attr5;  // function attributes are per device
                 attr5.run(h->device, [&] {
-                    cudaFuncSetAttribute(k_dense_rows_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                    cudaFuncSetAttribute(k_dense_rows_v5<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                    cudaFuncSetAttribute(k_dense_rows_v5<10, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 });
-                DD_LAUNCH(h, "dense_rows", k_dense_rows_v5, h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
-                          h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld, median,
-                          pseudocount, h->d_dense);
+                if (nw > 16)
+                    DD_LAUNCH(h, "dense_rows", (k_dense_rows_v5<10, 18>), h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
+                              h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld,
+                              median, pseudocount, h->d_dense);
+                else
+                    DD_LAUNCH(h, "dense_rows", (k_dense_rows_v5<12, 16>), h->num_sms, nw * 32, row_bytes * nw, h->d_indptr, h->d_indices,
+                              h->d_data, h->d_l1, h->d_parents, h->blk_n0, h->blk_n, h->blk_m0, h->blk_m, (int)h->G, (int)h->ld,
+                              median, pseudocount, h->d_dense);
                 h->dense_valid = true;
                 h->emb_valid = false;
                 return DD_OK;
