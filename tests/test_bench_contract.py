@@ -89,6 +89,22 @@ def test_product_arm_line_with_a_stand_in_handle(monkeypatch, capsys):
         def counts_all_finite(self):
             return True
 
+        # stage-wise calls of the "rooflines_alone" leg
+        def create_doublets(self, parents):
+            pass
+
+        def median_lib_size(self):
+            return 1.0
+
+        def normalise_log(self, median, pseudocount):
+            pass
+
+        def pca(self, n_comp, omega, n_power_iter):
+            pass
+
+        def knn(self, k):
+            pass
+
         def fit_iterations(self, parents, omega, **kw):
             n_iters, n_synth = parents.shape[:2]
             self.launches += 100
@@ -136,5 +152,6 @@ def test_product_arm_line_with_a_stand_in_handle(monkeypatch, capsys):
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+    assert d["rooflines_alone"] is not None
     assert d["config"]["pipelines_per_gpu"] == 2  # two pipelined loops per GPU (DD_PIPELINES), 100 launches per loop and step
     assert d["gpu_launches"] == 400 and set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
