@@ -223,7 +223,10 @@ class OracleClassifier:
         st["aug_lib_size"] = aug_lib
         if self.standard_scaling is True:
             if sp_sparse.issparse(aug):
-                raise NotImplementedError("oracle: sparse (pseudocount==1) + standard_scaling")
+                # sc.pp.scale zero-centres, and zero-centring a sparse matrix densifies it first (scanpy >= 1.10:
+                # "... as `zero_center=True`, sparse input is densified"): from here on the pseudocount == 1 branch is dense,
+                # and :308 picks svd_solver="auto" for it.  [upstream, absent -- restated from scanpy's behaviour]
+                aug = np.asarray(aug.toarray(), dtype=np.float32)
             aug, _, _ = upstream.pp_scale(aug, max_value=15)
         if self.keep_stages:
             st["aug"] = aug

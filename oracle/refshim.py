@@ -13,6 +13,8 @@ import os
 import sys
 import types
 
+import numpy as np
+
 from . import upstream
 
 REFERENCE_FILE = "/root/reference/doubletdetection/doubletdetection.py"
@@ -38,7 +40,10 @@ def _make_stub_modules(louvain_fn=None, record=None, phenograph_seed=0):
     tl = types.SimpleNamespace()
 
     def scale(adata, max_value=None):
-        adata.X, _, _ = upstream.pp_scale(adata.X, max_value=max_value)
+        X = adata.X
+        if hasattr(X, "toarray"):  # sc.pp.scale(zero_center=True) densifies sparse input (the pseudocount == 1 branch)
+            X = np.asarray(X.toarray(), dtype=np.float32)
+        adata.X, _, _ = upstream.pp_scale(X, max_value=max_value)
         rec("scaled", adata.X)
 
     def pca(adata, n_comps=None, random_state=0, svd_solver="auto"):

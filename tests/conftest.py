@@ -53,6 +53,10 @@ def golden_case(name):
     if name == "structured_1200x260_pc1":
         st = datasets.structured_counts(1200, 260, seed=5)
         return st, dict(n_iters=2, clustering_algorithm="louvain", pseudocount=1), dict(p_thresh=1e-3, voter_thresh=0.5)
+    if name == "structured_1200x260_pc1_scaled":
+        st = datasets.structured_counts(1200, 260, seed=5)
+        return (st, dict(n_iters=2, clustering_algorithm="louvain", pseudocount=1, standard_scaling=True),
+                dict(p_thresh=1e-3, voter_thresh=0.5))
     raise KeyError(name)
 
 
@@ -60,7 +64,7 @@ GOLDEN_NAMES = ["c1_louvain", "c1_louvain_scaled", "hvg_replace", "single_iter",
 # goldens of the other two clustering branches (same generator: the reference's real code over the restated calls)
 CLUSTER_GOLDEN_NAMES = ["c1_phenograph_scaled", "c1_leiden_scaled", "structured_900x200_phenograph"]
 # the sparse branch (pseudocount == 1 -> np.log1p on the sparse matrix, svd_solver="arpack"; doubletdetection.py:296-297, 308)
-SPARSE_GOLDEN_NAMES = ["structured_1200x260_pc1"]
+SPARSE_GOLDEN_NAMES = ["structured_1200x260_pc1", "structured_1200x260_pc1_scaled"]
 
 
 @pytest.fixture(scope="session")

@@ -105,6 +105,9 @@ def main():
     st3 = datasets.structured_counts(1200, 260, seed=5)
     run_case("structured_1200x260_pc1", st3, dict(p_thresh=1e-3, voter_thresh=0.5), n_iters=2, clustering_algorithm="louvain",
              pseudocount=1)
+    # ... and with standard_scaling: sc.pp.scale densifies the sparse matrix, :308 then picks svd_solver="auto"
+    run_case("structured_1200x260_pc1_scaled", st3, dict(p_thresh=1e-3, voter_thresh=0.5), n_iters=2,
+             clustering_algorithm="louvain", pseudocount=1, standard_scaling=True)
 
 
 if __name__ == "__main__":

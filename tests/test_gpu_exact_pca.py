@@ -173,15 +173,62 @@ def test_classifier_pseudocount1_chain_vs_oracle(handle, shape, n_top):
     assert min(ari) > 0.8
 
 
-def test_pseudocount1_with_scaling_takes_the_dense_solver():
+def test_pseudocount1_with_scaling_takes_the_dense_solver(handle):
     """standard_scaling densifies the matrix (sc.pp.scale zero-centres), so :308 picks "auto" again: the pipelined loop with
-    the log1p build.  The oracle does not restate scanpy's sparse pp.scale, so this checks the path runs and is deterministic."""
+    the log1p build.  Chain check against the oracle (scaled log1p matrix, randomized PCA on the GPU embedding's stages) and
+    determinism."""
     from doubletdetection_b200 import BoostClassifier
 
     counts = datasets.structured_counts(1500, 600, seed=9)
+    kw = dict(n_iters=2, clustering_algorithm="louvain", pseudocount=1, standard_scaling=True, random_state=0)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        a = BoostClassifier(n_iters=2, clustering_algorithm="louvain", pseudocount=1, standard_scaling=True).fit(counts)
-        b = BoostClassifier(n_iters=2, clustering_algorithm="louvain", pseudocount=1, standard_scaling=True).fit(counts)
+        a = BoostClassifier(**kw).fit(counts)
+        b = BoostClassifier(**kw).fit(counts)
+        ora = reference_path.OracleClassifier(louvain_fn=louvain_c.louvain, keep_stages=True, **kw).fit(counts)
     np.testing.assert_array_equal(a.communities_, b.communities_)
     assert np.isfinite(a.all_scores_).all()
+    np.testing.assert_array_equal(np.asarray(a.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    n, g_ = counts.shape
+    omega = pca_f64.omega(g_, 30, 0).astype(np.float32)
+    n_iter = pca_f64.auto_n_iter(n + n // 4, g_, 30)
+    handle.upload_counts(reference_path.prologue(counts, 10000)["raw"])
+    for i in range(2):
+        handle.create_doublets(np.asarray(a._parents_array[i]))
+        handle.normalise_log(handle.median_lib_size(), 1.0)
+        handle.standard_scale(15.0)
+        if i == 0:  # the scaled log1p matrix against the oracle's
+            np.testing.assert_allclose(handle.download_dense(), ora.stages[0]["aug"], rtol=2e-5, atol=2e-5)
+        emb, _ = handle.pca(30, omega, n_iter)
+        idx, _ = upstream.knn_brute(emb, 10)
+        gph = upstream.knn_pattern_graph(idx)
+        labels = louvain_c.louvain(gph.indptr, gph.indices, None, resolution=4.0, seed=0, level0="parallel")
+        np.testing.assert_array_equal(a.communities_[i], labels[:n])
+
+
+@pytest.mark.parametrize("name", ["structured_1200x260_pc1", "structured_1200x260_pc1_scaled"])
+def test_classifier_pseudocount1_vs_reference_golden(name):
+    """The sparse branch end to end against goldens produced by the reference's REAL control flow (doubletdetection.py:296-297,
+    302-303, 308; tests/golden/make_golden.py): parents bit-exact, final labels identical, communities up to the drift of the
+    reference's float32 PCA (ARPACK resp. randomized) against the GPU's."""
+    from conftest import golden_case, load_golden
+    from sklearn.metrics import adjusted_rand_score
+
+    from doubletdetection_b200 import BoostClassifier
+
+    g = load_golden(name)
+    counts, kw, pkw = golden_case(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(**kw).fit(counts)
+        labels = np.asarray(clf.predict(**pkw), dtype=np.float64)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), g["parents"])
+    same = (clf.communities_ == g["communities"]).all(axis=1)
+    ari = [adjusted_rand_score(clf.communities_[i], g["communities"][i]) for i in range(same.size)]
+    print(f"\n[{name}] iterations with identical communities: {int(same.sum())}/{same.size}; adjusted Rand {np.round(ari, 4)}")
+    assert min(ari) >= 0.9
+    agree = np.mean((labels == g["labels"]) | (np.isnan(labels) & np.isnan(g["labels"])))
+    assert agree >= 0.99, agree
+    for i in np.nonzero(same)[0]:
+        np.testing.assert_array_equal(clf.all_scores_[i], g["all_scores"][i])
+        np.testing.assert_allclose(clf.all_log_p_values_[i], g["all_log_p_values"][i], rtol=1e-4, atol=1e-12)
