@@ -144,21 +144,31 @@ void dd_comm_destroy(dd_handle *h) {
     h->nccl_comm = nullptr;
 }
 
+// The collectives are booked in the per-kernel timing report (dd_set_kernel_timing) under "nccl_*" -- CUDA events around the
+// NCCL call on the handle's stream, i.e. including the wait for the slowest rank -- but not in the launch counter (they are
+// not this library's kernels).
 int dd_comm_allreduce_f64(dd_handle *h, double *buf, int64_t count) {
     if (!dd_sharded(h) || count <= 0) return DD_OK;
+    dd_launch_begin(h);
     DD_NCCL(h, g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    DD_TRY(dd_launch_end(h, "nccl_allreduce"));
+    h->launches--;
     return DD_OK;
 }
 
 int dd_comm_bcast(dd_handle *h, void *buf, int64_t bytes, int root) {
     if (!dd_sharded(h) || bytes <= 0) return DD_OK;
+    dd_launch_begin(h);
     DD_NCCL(h, g_nccl.Broadcast(buf, buf, (size_t)bytes, ncclUint8, root, (ncclComm_t)h->nccl_comm, h->stream));
+    DD_TRY(dd_launch_end(h, "nccl_bcast"));
+    h->launches--;
     return DD_OK;
 }
 
 int dd_comm_gather_ranges(dd_handle *h, void *base, int64_t row_bytes, int n_ranges, const int64_t *begin,
                           const int64_t *count, const int *owner) {
     if (!dd_sharded(h)) return DD_OK;
+    dd_launch_begin(h);
     DD_NCCL(h, g_nccl.GroupStart());
     for (int r = 0; r < n_ranges; r++) {
         if (count[r] <= 0) continue;
@@ -171,5 +181,7 @@ int dd_comm_gather_ranges(dd_handle *h, void *base, int64_t row_bytes, int n_ran
         }
     }
     DD_NCCL(h, g_nccl.GroupEnd());
+    DD_TRY(dd_launch_end(h, "nccl_allgather"));
+    h->launches--;
     return DD_OK;
 }
