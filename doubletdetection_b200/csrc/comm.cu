@@ -156,6 +156,17 @@ int dd_comm_allreduce_f64(dd_handle *h, double *buf, int64_t count) {
     return DD_OK;
 }
 
+// sum of int32 words: used to merge buffers in which every word is written by exactly one rank and zero elsewhere (exact for
+// any bit pattern, float32 included)
+int dd_comm_allreduce_i32(dd_handle *h, int32_t *buf, int64_t count) {
+    if (!dd_sharded(h) || count <= 0) return DD_OK;
+    dd_launch_begin(h);
+    DD_NCCL(h, g_nccl.AllReduce(buf, buf, (size_t)count, ncclInt32, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    DD_TRY(dd_launch_end(h, "nccl_allreduce"));
+    h->launches--;
+    return DD_OK;
+}
+
 int dd_comm_bcast(dd_handle *h, void *buf, int64_t bytes, int root) {
     if (!dd_sharded(h) || bytes <= 0) return DD_OK;
     dd_launch_begin(h);

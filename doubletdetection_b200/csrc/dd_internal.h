@@ -269,6 +269,7 @@ static inline bool dd_sharded(const dd_handle *h) { return h->shard_cells && h->
 void dd_set_block(dd_handle *h);  // derive blk_* / A / A_glob from N, M, rank, world
 int dd_comm_allreduce_f64(dd_handle *h, double *buf, int64_t count);
 int dd_comm_bcast(dd_handle *h, void *buf, int64_t bytes, int root);
+int dd_comm_allreduce_i32(dd_handle *h, int32_t *buf, int64_t count);
 // "all-gather" of row ranges that already sit at their final place in a replicated buffer: range r of `begin` /
 // `count` (in rows of row_bytes bytes) is owned by rank owner[r] and broadcast from there in one NCCL group
 int dd_comm_gather_ranges(dd_handle *h, void *base, int64_t row_bytes, int n_ranges, const int64_t *begin,

@@ -303,10 +303,18 @@ __device__ __forceinline__ double knn_filter_err(double qn, double r) {
 // exact re-ranking of `width` <= 32 PER candidates per query (one or two lists side by side): every lane owns PER of them
 template <int PER>
 __global__ void k_knn_refine_w(const float *__restrict__ emb, const int *__restrict__ cand_i, int width, int64_t q0, int64_t n,
-                               int k, int32_t *__restrict__ idx_out, float *__restrict__ dist_out, KnnCert cert = KnnCert()) {
+                               int k, int32_t *__restrict__ idx_out, float *__restrict__ dist_out, KnnCert cert = KnnCert(),
+                               const int32_t *__restrict__ row_map = nullptr, int shard_world = 1, int shard_rank = 0) {
     const int lane = threadIdx.x & 31;
-    const int64_t q = q0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // queries [q0, n)
+    int64_t q = q0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // queries [q0, n)
     if (q >= n) return;
+    // cell-block sharding of the cluster-ordered kNN: the 256-row blocks of the PERMUTED order are dealt round-robin; row_map
+    // (the permutation) turns a permuted position into the original row whose candidates and output these are
+    if (shard_world > 1 && ((q >> 8) % shard_world) != shard_rank) return;
+    if (row_map) {
+        q = row_map[q];
+        if (q < 0) return;  // padding position
+    }
     int ci[PER];
     double d[PER];
 #pragma unroll
@@ -674,7 +682,7 @@ __global__ void __launch_bounds__(THREADS, 1)
              int n_full, int *__restrict__ cand_i, const int *__restrict__ list_off = nullptr,
              const int *__restrict__ list_tiles = nullptr, const int *__restrict__ list_len = nullptr,
              const int *__restrict__ block_order = nullptr, const float *__restrict__ tau_init = nullptr,
-             float *__restrict__ tau_out = nullptr) {
+             float *__restrict__ tau_out = nullptr, int shard_world = 1, int shard_rank = 0) {
     constexpr int SUB = TILE / TN;                     // pipeline steps per 128-row candidate tile
     constexpr int STAGE_BYTES = TN * KC * 16;
     constexpr uint32_t TMEM_COLS = 4 * TN;             // 2 buffers x 2 query tiles x TN accumulator columns
@@ -702,6 +710,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         // order, so the tail of the launch is made of the short lists).  list_len: lists at fixed strides (list_off[p]) with
         // explicit lengths, instead of packed lists delimited by list_off[p + 1]
         const int blk = pair0 + (block_order ? block_order[blockIdx.x] : (int)blockIdx.x);
+        // cell-block sharding: the query blocks are dealt to the ranks round-robin (whole CTA leaves, before any barrier)
+        if (shard_world > 1 && (blk % shard_world) != shard_rank) return;
         const int off = list_off[blk];
         n_tiles = list_len ? list_len[blk] : list_off[blk + 1] - off;
         my_list = list_tiles + off;
@@ -883,7 +893,7 @@ int run_knn(dd_handle *h, int k, float *norms, float *cand_d, int *cand_i) {
 // Final re-ranking of a kNN call: exact float64 order of the filter's candidates (`width` per row: n_lists lists of list_w),
 // the filter's certificate, and the float64 brute-force fix-up of the rows it could not clear.  Rows [q0, q1).
 int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int width, int list_w, int n_lists, int64_t q0,
-                        int64_t q1, int64_t n, int k) {
+                        int64_t q1, int64_t n, int k, const int32_t *row_map, int shard_world, int shard_rank) {
     DD_TRY(dd_reserve(h, &h->d_knn_cert, &h->cap_knn_cert, n + 4));
     DD_CUDA(h, cudaMemsetAsync(h->d_knn_cert, 0, sizeof(int32_t), h->stream));
     KnnCert cert;
@@ -894,11 +904,14 @@ int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int w
     cert.cap = (int)n;
     const unsigned grid = (unsigned)((q1 - q0 + 7) / 8);
     if (width <= 32)
-        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<1>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert);
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<1>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert,
+                  row_map, shard_world, shard_rank);
     else if (width <= 64)
-        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert);
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert,
+                  row_map, shard_world, shard_rank);
     else
-        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<3>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert);
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<3>, grid, 256, 0, emb, cand_i, width, q0, q1, k, h->d_knn_idx, h->d_knn_dist, cert,
+                  row_map, shard_world, shard_rank);
     DD_LAUNCH(h, "knn_exact_rows", k_knn_exact_rows, (unsigned)(h->num_sms * 2), 256, 0, emb, n, (const int *)cert.rows,
               (const int *)cert.count, cert.cap, k, h->d_knn_idx, h->d_knn_dist);
     if (!h->h_knn_uncert && cudaMallocHost(&h->h_knn_uncert, sizeof(int32_t)) != cudaSuccess) h->h_knn_uncert = nullptr;
@@ -962,17 +975,17 @@ int run_knn_tc(dd_handle *h, int k, int TL, float *cand_t, int *cand_i) {
         if (h->knn_narrow && TL == 16) {
             DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<16, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
                       n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
-            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 16, 16, 1, q0, q1, n, k));
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 16, 16, 1, q0, q1, n, k, nullptr, 1, 0));
         } else if (h->knn_narrow) {
             DD_LAUNCH(h, "knn_tc", (tc::k_knn_tc<40, false, 64>), grid, tc::THREADS, tc::smem_bytes<64>(), qa, cb, n, n_tiles, pair0,
                       n_full, cand_i, (const int *)nullptr, (const int *)nullptr);
-            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 40, 40, 1, q0, q1, n, k));
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 40, 40, 1, q0, q1, n, k, nullptr, 1, 0));
         } else if (TL == 16) {
             DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<16>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
-            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 16, 16, 1, q0, q1, n, k));
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 16, 16, 1, q0, q1, n, k, nullptr, 1, 0));
         } else {
             DD_LAUNCH(h, "knn_tc", tc::k_knn_tc<40>, grid, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, pair0, n_full, cand_i);
-            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 40, 40, 1, q0, q1, n, k));
+            DD_TRY(dd_knn_refine_final(h, h->d_emb, cand_i, 40, 40, 1, q0, q1, n, k, nullptr, 1, 0));
         }
     }
     if (W > 1) {
@@ -1100,26 +1113,39 @@ int dd_knn_launch_prep(dd_handle *h, const float *emb, int64_t n, int64_t n_pad,
 
 int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
                            const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
-                           const float *tau_init, float *tau_out) {
+                           const float *tau_init, float *tau_out, int shard_world, int shard_rank) {
     static dd_once_per_device attr_set;  // function attributes are per device
     attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tc::k_knn_tc<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
     DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<16, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
-              n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out);
+              n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out, shard_world, shard_rank);
     return DD_OK;
 }
 
 // the same for lists of 40 (k - 1 > 12: PhenoGraph's 30 neighbours keep a margin of 10 filter ranks)
 int dd_knn_launch_listed40(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
                            const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
-                           const float *tau_init, float *tau_out) {
+                           const float *tau_init, float *tau_out, int shard_world, int shard_rank) {
     static dd_once_per_device attr_set;  // function attributes are per device
     attr_set.run(h->device, [&] {
         cudaFuncSetAttribute(tc::k_knn_tc<40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     });
     DD_LAUNCH(h, "knn_tc_listed", (tc::k_knn_tc<40, true>), (unsigned)n_blocks, tc::THREADS, tc::SMEM_BYTES, qa, cb, n, n_tiles, 0,
-              n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out);
+              n_blocks, cand_i, list_off, list_tiles, list_len, block_order, tau_init, tau_out, shard_world, shard_rank);
+    return DD_OK;
+}
+
+// re-ranking of ONE launch's lists (16 or 40 wide) over the permuted rows, for the blocks this rank owns
+int dd_knn_launch_refine_lists(dd_handle *h, const float *emb, const int *cand_i, int width, int64_t n, int k, int32_t *idx_out,
+                               float *dist_out, int shard_world, int shard_rank) {
+    const unsigned grid = (unsigned)((n + 7) / 8);
+    if (width <= 32)
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<1>, grid, 256, 0, emb, cand_i, width, (int64_t)0, n, k, idx_out, dist_out, KnnCert(),
+                  (const int32_t *)nullptr, shard_world, shard_rank);
+    else
+        DD_LAUNCH(h, "knn_refine", k_knn_refine_w<2>, grid, 256, 0, emb, cand_i, width, (int64_t)0, n, k, idx_out, dist_out, KnnCert(),
+                  (const int32_t *)nullptr, shard_world, shard_rank);
     return DD_OK;
 }
 

@@ -10,16 +10,18 @@
 int dd_knn_launch_prep(dd_handle *h, const float *emb, int64_t n, int64_t n_pad, uint8_t *qa, uint8_t *cb);        // knn.cu
 int dd_knn_launch_listed16(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
                            const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
-                           const float *tau_init, float *tau_out);                                                   // knn.cu
+                           const float *tau_init, float *tau_out, int shard_world, int shard_rank);                  // knn.cu
+int dd_knn_launch_refine_lists(dd_handle *h, const float *emb, const int *cand_i, int width, int64_t n, int k, int32_t *idx_out,
+                               float *dist_out, int shard_world, int shard_rank);                                   // knn.cu
 int dd_knn_launch_refine32(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 int dd_knn_launch_listed40(dd_handle *h, const uint8_t *qa, const uint8_t *cb, int64_t n, int n_tiles, int n_blocks, int *cand_i,
                            const int *list_off, const int *list_tiles, const int *list_len, const int *block_order,
-                           const float *tau_init, float *tau_out);                                                   // knn.cu
+                           const float *tau_init, float *tau_out, int shard_world, int shard_rank);                  // knn.cu
 int dd_knn_launch_refine40(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 int dd_knn_refine_final(dd_handle *h, const float *emb, const int *cand_i, int width, int list_w, int n_lists, int64_t q0,
-                        int64_t q1, int64_t n, int k);                                                               // knn.cu
+                        int64_t q1, int64_t n, int k, const int32_t *row_map, int shard_world, int shard_rank);      // knn.cu
 int dd_knn_launch_refine16(dd_handle *h, const float *emb, const int *cand_i, int64_t n, int k, int32_t *idx_out,
                            float *dist_out);                                                                         // knn.cu
 
@@ -79,8 +81,13 @@ __global__ void k_prune_boxes(const float *__restrict__ emb_p, const int32_t *__
 // one CTA (256 threads) per 256-row block: the largest k-th distance^2 launch A found for its real rows (inf if a row
 // found fewer than k - 1 neighbours in its own group)
 __global__ void __launch_bounds__(256) k_prune_threshold(const int32_t *__restrict__ perm, const int32_t *__restrict__ idx_a,
-                                                         const float *__restrict__ dist_a, int k, double *__restrict__ thr) {
+                                                         const float *__restrict__ dist_a, int k, double *__restrict__ thr,
+                                                         int shard_world = 1, int shard_rank = 0) {
     __shared__ double s_max[8];
+    if (shard_world > 1 && ((int)blockIdx.x % shard_world) != shard_rank) {  // another rank's block (uniform)
+        if (threadIdx.x == 0) thr[blockIdx.x] = 0.0;
+        return;
+    }
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double v = 0.0;
     if (perm[row] >= 0) {
@@ -162,11 +169,13 @@ __global__ void k_prune_offsets(const int32_t *__restrict__ len, int n_blocks, i
 
 // candidate lists of launch B (permuted numbering, one row per permuted position) -> original numbering and row order
 __global__ void k_prune_translate(const int32_t *__restrict__ perm, const int *__restrict__ cand_p, int64_t n_pad,
-                                  int *__restrict__ cand_o, int out_stride = 16, int out_col0 = 0, int list_w = 16) {
+                                  int *__restrict__ cand_o, int out_stride = 16, int out_col0 = 0, int list_w = 16,
+                                  int shard_world = 1, int shard_rank = 0) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = t / list_w;
     const int l = (int)(t % list_w);
     if (r >= n_pad) return;
+    if (shard_world > 1 && ((r >> 8) % shard_world) != shard_rank) return;  // another rank's block
     const int o = perm[r];
     if (o < 0) return;
     const int c = cand_p[r * list_w + l];
@@ -258,7 +267,7 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
               d_lo.p, d_hi.p, d_tile_rows.p);
     // launch A + exact re-ranking in the permuted numbering -> thresholds
     DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_a.p, d_tiles_a.p, nullptr, nullptr, nullptr,
-                                  nullptr));
+                                  nullptr, 1, 0));
     DD_TRY(dd_knn_launch_refine16(h, d_emb_p.p, d_cand_p.p, n_pad, (int)k, d_idx_a.p, d_dist_a.p));
     DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)n_blocks, 256, 0, d_perm.p, d_idx_a.p, d_dist_a.p, (int)k, d_thr.p);
     DD_LAUNCH(h, "prune_lists", k_prune_lists, (unsigned)n_blocks, 256, 0, d_lo.p, d_hi.p, d_tile_rows.p, d_thr.p, n_tiles,
@@ -268,7 +277,7 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
               (const int32_t *)d_off_b.p, d_list_b.p, d_len_b.p);
     // launch B, back to the original numbering, exact re-ranking there
     DD_TRY(dd_knn_launch_listed16(h, qa, cb, n_pad, n_tiles, n_blocks, d_cand_p.p, d_off_b.p, d_list_b.p, nullptr, nullptr, nullptr,
-                                  nullptr));
+                                  nullptr, 1, 0));
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((n_pad * 16 + 255) / 256), 256, 0, d_perm.p, d_cand_p.p, n_pad,
               d_cand_o.p, 16, 0, 16);
     // output buffers of the ordinary kNN (sized by an earlier dd_knn call on this embedding, or here)
@@ -533,12 +542,13 @@ __global__ void __launch_bounds__(256) k_lists_other(const float *__restrict__ l
                                                      const float *__restrict__ lo_t, const float *__restrict__ hi_t,
                                                      const int32_t *__restrict__ tile_rows, const double *__restrict__ thr,
                                                      const int32_t *__restrict__ block_group, int n_tiles_max,
-                                                     int32_t *__restrict__ list, int32_t *__restrict__ len) {
+                                                     int32_t *__restrict__ list, int32_t *__restrict__ len,
+                                                     int shard_world = 1, int shard_rank = 0) {
     __shared__ float q_lo[32], q_hi[32];
     __shared__ int s_warp[8], s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;
     const int g = block_group[b];
-    if (g < 0) {  // unused block (uniform)
+    if (g < 0 || (shard_world > 1 && (b % shard_world) != shard_rank)) {  // unused block, or another rank's (uniform)
         if (tid == 0) len[b] = 0;
         return;
     }
@@ -637,9 +647,12 @@ static constexpr int64_t kClusteredMinRows = 50000;
 
 bool dd_knn_clustered_applies(const dd_handle *h, int32_t k) {
     static const bool off = getenv("DD_KNN_DENSE") != nullptr;
-    if (off || h->knn_mode == 1 || h->KP != 32 || k < 2 || k > 31 || dd_sharded(h)) return false;
+    if (off || h->knn_mode == 1 || h->KP != 32 || k < 2 || k > 31) return false;
     if (h->knn_mode == 2) return h->emb_rows >= 512;
     if (h->emb_rows < kClusteredMinRows) return false;
+    // cell-block sharding: every rank must take the same branch (the calls below contain collectives), so the choice depends
+    // on the size only -- no feedback from the pair counts, which differ from rank to rank
+    if (dd_sharded(h)) return true;
     // by size -- unless an earlier call on this problem size reported that the ordering does not pay: on an embedding
     // without cluster structure the bounds exclude nothing and the padded order visits MORE pairs than the all-tiles kernel
     // (uniform points: 1.2 x).  The counts arrive asynchronously (pinned host memory), one or two calls late.
@@ -665,6 +678,11 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
     const int T = (int)(P / tc::TILE), B = (int)(P / 256);
     if ((int64_t)B * T >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "clustered knn: list table too large");
     const int TL = (k - 1 <= 12) ? 16 : 40;  // candidates kept per row and launch (as in dd_dev_knn)
+    // Cell-block sharding: every rank holds the whole (all-gathered) embedding and runs the pre-pass; rank 0's ordering is
+    // broadcast (the k-means sums and the bucket cursors are atomics: their rounding / order differs between ranks), the
+    // 256-row blocks of the permuted order are dealt to the ranks round-robin, every rank re-ranks the rows of its blocks
+    // into a zeroed result buffer, and the buffers are summed (one writer per word).
+    const int W = dd_sharded(h) ? h->world : 1, R = dd_sharded(h) ? h->rank : 0;
     // ---- one grow-only allocation, carved up
     size_t bytes = 0;
     auto take = [&](size_t b) {
@@ -746,6 +764,12 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
               b.group_tiles, b.info);
     DD_CUDA(h, cudaMemsetAsync(b.perm, 0xff, 4 * P, h->stream));
     DD_LAUNCH(h, "kcl_scatter", k_bucket_scatter, row_ctas, 256, 0, n, b.bucket, b.start, b.cursor, b.perm);
+    if (W > 1) {
+        DD_TRY(dd_comm_bcast(h, b.perm, 4 * P, 0));
+        DD_TRY(dd_comm_bcast(h, b.block_group, 4 * (int64_t)B, 0));
+        DD_TRY(dd_comm_bcast(h, b.group_tile0, 4 * kGroups, 0));
+        DD_TRY(dd_comm_bcast(h, b.group_tiles, 4 * kGroups, 0));
+    }
     // ---- 3. permuted embedding, operand tiles, boxes
     DD_LAUNCH(h, "prune_gather", k_prune_gather, (unsigned)((P * 8 + 255) / 256), 256, 0, h->d_emb, b.perm, P, b.emb_p);
     DD_TRY(dd_knn_launch_prep(h, b.emb_p, P, P, qa, cb));
@@ -756,33 +780,40 @@ int dd_dev_knn_clustered(dd_handle *h, int32_t k) {
               b.len_a);
     DD_LAUNCH(h, "kcl_order", k_block_order, (unsigned)((B + 255) / 256), 256, 0, b.len_a, B, b.order);
     if (TL == 16)
-        DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
+        DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau, W, R));
     else
-        DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau));
+        DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_a, b.off, b.list_a, b.len_a, b.order, nullptr, b.tau, W, R));
     DD_CUDA(h, cudaMemsetAsync(b.idx_a, 0xff, sizeof(int32_t) * (size_t)P * k, h->stream));  // -1 = "not found"
-    if (TL == 16)
-        DD_TRY(dd_knn_launch_refine16(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
-    else
-        DD_TRY(dd_knn_launch_refine40(h, b.emb_p, b.cand_a, P, (int)k, b.idx_a, b.dist_a));
-    DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)B, 256, 0, b.perm, b.idx_a, b.dist_a, (int)k, b.thr);
+    DD_TRY(dd_knn_launch_refine_lists(h, b.emb_p, b.cand_a, TL, P, (int)k, b.idx_a, b.dist_a, W, R));
+    DD_LAUNCH(h, "prune_threshold", k_prune_threshold, (unsigned)B, 256, 0, b.perm, b.idx_a, b.dist_a, (int)k, b.thr, W, R);
     // ---- 5. launch B (other groups within the bound), longest lists first, starting from launch A's filter thresholds
     DD_LAUNCH(h, "kcl_lists_other", k_lists_other, (unsigned)B, 256, 0, b.lo, b.hi, b.lo_t, b.hi_t, b.tile_rows, b.thr, b.block_group,
-              T, b.list_b, b.len_b);
+              T, b.list_b, b.len_b, W, R);
     DD_LAUNCH(h, "kcl_order", k_block_order, (unsigned)((B + 255) / 256), 256, 0, b.len_b, B, b.order);
     if (TL == 16)
-        DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+        DD_TRY(dd_knn_launch_listed16(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr, W, R));
     else
-        DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr));
+        DD_TRY(dd_knn_launch_listed40(h, qa, cb, P, T, B, b.cand_b, b.off, b.list_b, b.len_b, b.order, b.tau, nullptr, W, R));
     DD_LAUNCH(h, "kcl_pairs", k_sum_pairs, 1, 256, 0, b.len_a, b.len_b, B, b.info);
     if (h->h_knn_cl_pairs)
         DD_CUDA(h, cudaMemcpyAsync(h->h_knn_cl_pairs, b.info + 2, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     // ---- 6. back to the original numbering, exact re-ranking of both lists together
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_a, P, b.cand_o, 2 * TL, 0,
-              TL);
+              TL, W, R);
     DD_LAUNCH(h, "prune_translate", k_prune_translate, (unsigned)((P * TL + 255) / 256), 256, 0, b.perm, b.cand_b, P, b.cand_o, 2 * TL, TL,
-              TL);
+              TL, W, R);
     // (with the filter's certificate over both lists, and the float64 fix-up of the rows it cannot clear)
-    DD_TRY(dd_knn_refine_final(h, h->d_emb, b.cand_o, 2 * TL, TL, 2, 0, n, n, (int)k));
+    if (W == 1) {
+        DD_TRY(dd_knn_refine_final(h, h->d_emb, b.cand_o, 2 * TL, TL, 2, 0, n, n, (int)k, nullptr, 1, 0));
+    } else {
+        // this rank's rows = the real rows of its blocks of the permuted order: iterate over permuted positions, perm maps them
+        // to original rows; everything else stays zero and the ranks' buffers are summed
+        DD_CUDA(h, cudaMemsetAsync(h->d_knn_idx, 0, sizeof(int32_t) * (size_t)n * k, h->stream));
+        DD_CUDA(h, cudaMemsetAsync(h->d_knn_dist, 0, sizeof(float) * (size_t)n * k, h->stream));
+        DD_TRY(dd_knn_refine_final(h, h->d_emb, b.cand_o, 2 * TL, TL, 2, 0, P, n, (int)k, b.perm, W, R));
+        DD_TRY(dd_comm_allreduce_i32(h, h->d_knn_idx, n * k));
+        DD_TRY(dd_comm_allreduce_i32(h, reinterpret_cast<int32_t *>(h->d_knn_dist), n * k));
+    }
     return DD_OK;
 }
 

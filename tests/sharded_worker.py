@@ -83,6 +83,19 @@ def main():
     idx_ref, dd_ref = ref.knn(10)
     assert np.array_equal(idx, idx_ref), "sharded kNN lists differ from the single-GPU kNN of the same embedding"
     assert np.array_equal(dd, dd_ref)
+    # the cluster-ordered form under sharding (what the fit loop runs from 50 000 rows on): rank 0's ordering is broadcast, the
+    # 256-row blocks of the permuted order are dealt round-robin, the ranks' result buffers are summed
+    for k in (10, 31):
+        h.set_knn_mode(1)
+        ref.set_knn_mode(1)
+        idx_ref, dd_ref = ref.knn(k)
+        h.set_knn_mode(2)
+        idx2, dd2 = h.knn(k)
+        idx3, dd3 = h.knn(k)  # warm-started centroids
+        h.set_knn_mode(0)
+        ref.set_knn_mode(0)
+        assert np.array_equal(idx2, idx_ref) and np.array_equal(idx3, idx_ref), f"sharded cluster-ordered kNN differs (k = {k})"
+        assert np.array_equal(dd2, dd_ref) and np.array_equal(dd3, dd_ref)
 
     # scaled variant: the column statistics are all-reduced
     ref.create_doublets(parents)
@@ -105,6 +118,13 @@ def main():
         sharded = BoostClassifier(distributed="cells", **kw).fit(counts)
         lab_single = single.predict(p_thresh=1e-3, voter_thresh=0.5)
         lab = sharded.predict(p_thresh=1e-3, voter_thresh=0.5)
+        # the same fit with the cluster-ordered kNN forced (it is the default only from 50 000 rows on): identical results
+        forced = BoostClassifier(distributed="cells", **kw)
+        forced._native().set_knn_mode(2)
+        forced.fit(counts)
+        forced._native().set_knn_mode(0)
+    assert np.array_equal(forced.communities_, sharded.communities_), "cluster-ordered kNN changed the sharded fit"
+    assert np.array_equal(forced.all_log_p_values_, sharded.all_log_p_values_)
     assert np.array_equal(np.asarray(single.parents_), np.asarray(sharded.parents_))
     agree = float(np.mean(lab == lab_single))
     assert agree >= 0.995, f"sharded fit labels agree with the single-GPU fit on only {agree:.4f} of the cells"
