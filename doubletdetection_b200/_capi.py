@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdd_b200.so")
 
 DD_OK, DD_ERR_ARG, DD_ERR_CUDA, DD_ERR_UNSUPPORTED, DD_ERR_NOMEM = 0, 1, 2, 3, 4
-ABI_VERSION = 6
+ABI_VERSION = 7
 COMM_ID_BYTES = 128
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -106,6 +106,14 @@ SIGNATURES = {
     "dd_umap_connectivities": (
         ctypes.c_int,
         [ctypes.c_int64, ctypes.c_int32, c_i32p, c_f32p, c_i64p, c_i32p, c_f32p, ctypes.c_int64, c_i64p],
+    ),
+    "dd_umap_graph": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int32, c_i64p, c_i32p, c_f32p, ctypes.c_int64, c_i64p],
+    ),
+    "dd_leiden_device_graph": (
+        ctypes.c_int,
+        [ctypes.c_int64, c_i32p, c_i32p, c_f64p, ctypes.c_double, ctypes.c_uint64, c_i32p, c_i32p],
     ),
     "dd_leiden_knn": (
         ctypes.c_int,
@@ -287,6 +295,23 @@ def leiden_csr(indptr, indices, weights=None, resolution=1.0, seed=0):
     ncomm = ctypes.c_int32(0)
     rc = lib.dd_leiden_csr(n, _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int64), _ptr(w, ctypes.c_double),
                            float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
+    if rc != DD_OK:
+        _raise(lib, None, rc)
+    return labels[:n]
+
+
+def leiden_device_graph(off, adj, weights, resolution=4.0, seed=0):
+    """Leiden labels of a graph in the layout the device leaves for the fit loop's host workers (int32 offsets, rows in any
+    order, float64 weights with 0 = no edge)."""
+    lib = load()
+    off = np.ascontiguousarray(off, dtype=np.int32)
+    adj = np.ascontiguousarray(adj, dtype=np.int32)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    n = off.size - 1
+    labels = np.empty(max(n, 1), dtype=np.int32)
+    ncomm = ctypes.c_int32(0)
+    rc = lib.dd_leiden_device_graph(n, _ptr(off, ctypes.c_int32), _ptr(adj, ctypes.c_int32), _ptr(w, ctypes.c_double),
+                                    float(resolution), int(seed) & (2**64 - 1), _ptr(labels, ctypes.c_int32), ctypes.byref(ncomm))
     if rc != DD_OK:
         _raise(lib, None, rc)
     return labels[:n]
@@ -512,7 +537,7 @@ class Handle:
         return dict(pairs_a=int(out[0]), pairs_b=int(out[1]), blocks=int(out[2]), tiles=int(out[3]))
 
     def knn_listed(self, k, list_off, list_tiles, with_dist=True):
-        """Experimental: exact kNN in which 256-row query block p only visits the 128-row candidate tiles
+        """Test hook: exact kNN in which 256-row query block p only visits the 128-row candidate tiles
         ``list_tiles[list_off[p]:list_off[p + 1]]`` (scripts/knn_listed_experiment.py)."""
         n = self._emb_rows
         list_off = np.ascontiguousarray(list_off, dtype=np.int32)
@@ -525,7 +550,7 @@ class Handle:
         return idx, dist
 
     def louvain_level0_weighted(self, indptr, indices, weights, resolution=1.0, seed=0):
-        """Experimental: weighted first Louvain level on the device (fixed-point weights).  Returns (comm, rounds)."""
+        """Test hook: weighted first Louvain level on the device (fixed-point weights).  Returns (comm, rounds)."""
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int64)
         weights = np.ascontiguousarray(weights, dtype=np.float64)
@@ -538,7 +563,7 @@ class Handle:
         return comm, rounds.value
 
     def knn_pruned(self, k, perm, block_group, n_rows, with_dist=True):
-        """Experimental: cluster-ordered exact kNN, pre-pass and both launches on the device.  ``perm``: padded position ->
+        """Test hook: cluster-ordered exact kNN, pre-pass and both launches on the device.  ``perm``: padded position ->
         original row or -1; ``block_group``: group of every 256-row block.  Returns (idx, dist, stats)."""
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         block_group = np.ascontiguousarray(block_group, dtype=np.int32)
@@ -568,6 +593,21 @@ class Handle:
         g.eliminate_zeros()
         g.sort_indices()
         return g
+
+    def umap_graph(self, k):
+        """umap's connectivities of the last ``knn(k)`` (lists + distances) as built on the device: scipy CSR (float32,
+        sorted rows, zeros dropped) -- the device twin of :func:`umap_connectivities`."""
+        import scipy.sparse as sp_sparse
+
+        n = self._emb_rows
+        nnz = ctypes.c_int64(0)
+        self._check(self._lib.dd_umap_graph(self._h, int(k), None, None, None, 0, ctypes.byref(nnz)))
+        indptr = np.zeros(n + 1, dtype=np.int64)
+        indices = np.empty(max(nnz.value, 1), dtype=np.int32)
+        weights = np.empty(max(nnz.value, 1), dtype=np.float32)
+        self._check(self._lib.dd_umap_graph(self._h, int(k), _ptr(indptr, ctypes.c_int64), _ptr(indices, ctypes.c_int32),
+                                            _ptr(weights, ctypes.c_float), max(nnz.value, 1), ctypes.byref(nnz)))
+        return sp_sparse.csr_matrix((weights[: nnz.value], indices[: nnz.value], indptr), shape=(n, n))
 
     # the loop
     def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10,

@@ -12,7 +12,7 @@
 
 #include "../../include/dd_b200.h"
 
-#define DD_ABI_VERSION 6
+#define DD_ABI_VERSION 7
 
 // padded leading dimension of the dense A x G matrix: rows start on 128-byte boundaries
 static inline int64_t dd_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -139,7 +139,7 @@ struct dd_handle {
     int64_t cap_knn = 0;
     uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout
     int64_t cap_knn_ops = 0;
-    // experimental (dd_knn_listed): candidate-tile lists per 256-row query block; knn_list_pairs > 0 while such a call runs
+    // list-driven kernel (dd_knn_listed, cluster-ordered kNN): candidate-tile lists per 256-row query block; knn_list_pairs > 0 while such a call runs
     int32_t *d_knn_list_off = nullptr, *d_knn_list_tiles = nullptr;
     // cluster-ordered kNN (knn_prune.cu: dd_dev_knn_clustered): one carved allocation; the k-means centroids inside it are
     // carried from call to call while the number of rows stays the same
@@ -160,7 +160,9 @@ struct dd_handle {
     double *d_lv_tot = nullptr;
     double *d_lv_w = nullptr;  // Jaccard edge weights of the PhenoGraph graph (one per adjacency entry)
     int64_t cap_lv_n = 0, cap_lv_nnz = 0, cap_lv_w = 0;
-    // experimental weighted first level (louvain_gpu_w.cu): fixed-point weights, int64 degrees / totals, buckets, state
+    float *d_umap_w = nullptr;  // Leiden branch: umap's directed membership strengths, one per kNN list entry
+    int64_t cap_umap_w = 0;
+    // weighted first level (louvain_gpu_w.cu): fixed-point weights, int64 degrees / totals, buckets, state
     long long *d_lvw_wq = nullptr, *d_lvw_i64 = nullptr;  // wq[nnz]; k | tot | two_m (2 n + 1)
     int32_t *d_lvw_i32 = nullptr;                          // csize | desired | bucket (n each) + counters
     int64_t cap_lvw_nnz = 0, cap_lvw_n = 0, lvw_bucket_n = -1;
@@ -301,11 +303,17 @@ int dd_host_louvain_from_level0(int64_t n, const int32_t *off, const int32_t *ad
                                 double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
 // PhenoGraph on the host from the device-built weighted graph (rows in any order, zero weights = pruned edges):
 // Louvain at resolution 1 on the weighted graph, labels by decreasing size, communities <= min_cluster_size -> -1
-// comm0 (may be NULL): the first level already done on the device (experimental, DD_PHENO_LEVEL0)
+// comm0 (may be NULL): the first level already done on the device (default; DD_PHENO_LEVEL0=0 turns it off)
 int dd_host_phenograph_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, uint64_t seed,
                                   int32_t min_cluster_size, int32_t *labels_out, int32_t *n_comm_out, const int32_t *comm0);
-int dd_dev_louvain_level0_weighted(dd_handle *h, double gamma, uint64_t seed);  // louvain_gpu_w.cu (experimental)
+int dd_dev_louvain_level0_weighted(dd_handle *h, double gamma, uint64_t seed);  // louvain_gpu_w.cu
 // Leiden on the umap-weighted neighbour graph (leiden.cpp): kNN lists with self in column 0 + float32 distances
 int dd_host_leiden_knn(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist, double resolution,
                        uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
+// the same from the umap graph built on the device (dd_dev_umap_graph: rows in any order, zero weights = no edge)
+int dd_dev_umap_graph(dd_handle *h, int32_t k);  // louvain_gpu.cu
+int dd_host_leiden_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, double resolution,
+                              uint64_t seed, int32_t *labels_out, int32_t *n_comm_out);
+int dd_host_umap_canonical(int64_t n, const int32_t *off, const int32_t *adj, const double *w, int64_t *indptr_out,
+                           int32_t *indices_out, float *weights_out, int64_t capacity, int64_t *nnz_out);
 float dd_host_median(std::vector<float> &v);

@@ -21,8 +21,7 @@ int dd_pca_flag_copy(dd_handle *h, double *host_flag);                      // p
 namespace {
 
 struct Slot {
-    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1)) | PhenoGraph: weights (f64)];
-                               // Leiden: [kNN idx (A * k) | kNN dist (A * k, float32)]
+    int32_t *graph = nullptr;  // pinned: [off (A + 1) | comm (A) | adj (<= A * 2 (k - 1)) | PhenoGraph / Leiden: weights (f64)]
     double *flag = nullptr;    // pinned, PCA breakdown flag
     cudaEvent_t done = nullptr;
 };
@@ -51,9 +50,11 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     if (p->clustering != DD_CLUSTER_LOUVAIN && p->clustering != DD_CLUSTER_PHENOGRAPH && p->clustering != DD_CLUSTER_LEIDEN)
         return dd_fail(h, DD_ERR_ARG, "dd_fit_iterations: unknown clustering");
     const bool pheno = p->clustering == DD_CLUSTER_PHENOGRAPH;
-    // Leiden works on umap's weighted graph, whose weights come from the kNN DISTANCES: the lists + distances of every
-    // iteration go to the host workers, which build the fuzzy simplicial set and partition it (leiden.cpp)
+    // Leiden works on umap's weighted graph, whose weights come from the kNN DISTANCES: the fuzzy simplicial set of every
+    // iteration is built on the device right behind its kNN (dd_dev_umap_graph) and the host workers partition it (leiden.cpp)
     const bool leiden = p->clustering == DD_CLUSTER_LEIDEN;
+    // DD_UMAP_HOST=1 (A/B timing only): the round-1 split -- lists + distances go to the workers, which build the graph too
+    static const bool umap_host = getenv("DD_UMAP_HOST") && atoi(getenv("DD_UMAP_HOST")) != 0;
     // PhenoGraph's first Louvain level on the device, in fixed point (louvain_gpu_w.cu); DD_PHENO_LEVEL0=0: the host twin
     // of that level runs on the workers instead (same communities, A/B timing only)
     static const bool pheno_level0 = !(getenv("DD_PHENO_LEVEL0") && atoi(getenv("DD_PHENO_LEVEL0")) == 0);
@@ -72,7 +73,7 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     const int n_slots = n_threads + 2;
     const int64_t max_nnz = A * 2 * (k - 1);
     const int64_t w_off = ((A + 1) + A + max_nnz + 1) / 2 * 2;  // weights start 8-byte aligned
-    const int64_t slot_elems = pheno ? w_off + 2 * max_nnz : leiden ? 2 * A * k : (A + 1) + A + max_nnz;
+    const int64_t slot_elems = (pheno || leiden) ? std::max<int64_t>(w_off + 2 * max_nnz, 2 * A * k) : (A + 1) + A + max_nnz;
     const int n_run = p->iter_end - p->iter_begin;
     if (stage_ms_out) std::fill(stage_ms_out, stage_ms_out + 8, 0.0);
     if (n_run == 0) return DD_OK;
@@ -158,9 +159,12 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
                 const auto t0 = now();
                 int32_t n_comm = 0;
                 const int32_t *off = s.graph, *comm0 = s.graph + (A + 1), *adj = s.graph + (A + 1) + A;
-                if (leiden)
+                if (leiden && umap_host)
                     wrc = dd_host_leiden_knn(A, k, s.graph, reinterpret_cast<const float *>(s.graph + A * k), p->resolution,
                                              p->seed, labels.data(), &n_comm);
+                else if (leiden)
+                    wrc = dd_host_leiden_from_graph(A, off, adj, reinterpret_cast<const double *>(s.graph + w_off), p->resolution,
+                                                    p->seed, labels.data(), &n_comm);
                 else if (pheno)
                     wrc = dd_host_phenograph_from_graph(A, off, adj, reinterpret_cast<const double *>(s.graph + w_off), p->seed,
                                                         p->pheno_min_cluster_size, labels.data(), &n_comm,
@@ -295,11 +299,18 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
             h->d_knn_idx = h->d_knn_idx_base + eb * h->knn_idx_stride;
         cudaEventRecord(ev[4], knn_stream);
         if (rc == DD_OK && leiden && cluster_here) {
-            // no device clustering stage: the lists and their distances leave on the kNN stream (the distance buffer is
-            // not double-buffered, and the next kNN is ordered behind these copies on the same stream)
+            // no clustering lane: umap's graph is built on the kNN stream right behind the search (the distance buffer and
+            // the graph buffers are not double-buffered: the next kNN / graph build is ordered behind these kernels and
+            // copies on the same stream)
             Slot &s = slots[slot];
-            cudaMemcpyAsync(s.graph, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, knn_stream);
-            cudaMemcpyAsync(s.graph + A * k, h->d_knn_dist, sizeof(float) * A * k, cudaMemcpyDeviceToHost, knn_stream);
+            if (umap_host) {
+                cudaMemcpyAsync(s.graph, h->d_knn_idx, sizeof(int32_t) * A * k, cudaMemcpyDeviceToHost, knn_stream);
+                cudaMemcpyAsync(s.graph + A * k, h->d_knn_dist, sizeof(float) * A * k, cudaMemcpyDeviceToHost, knn_stream);
+            } else if ((rc = dd_dev_umap_graph(h, k)) == DD_OK) {
+                cudaMemcpyAsync(s.graph, h->d_lv_off, sizeof(int32_t) * (A + 1), cudaMemcpyDeviceToHost, knn_stream);
+                cudaMemcpyAsync(s.graph + (A + 1) + A, h->d_lv_adj, sizeof(int32_t) * max_nnz, cudaMemcpyDeviceToHost, knn_stream);
+                cudaMemcpyAsync(s.graph + w_off, h->d_lv_w, sizeof(double) * max_nnz, cudaMemcpyDeviceToHost, knn_stream);
+            }
         }
         cudaEventRecord(h->ev_emb_free[eb], knn_stream);
         cudaEventRecord(h->ev_knn_done, knn_stream);

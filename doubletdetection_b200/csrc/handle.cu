@@ -177,7 +177,7 @@ extern "C" void dd_destroy(dd_handle *h) {
     if (h->stream4) cudaStreamSynchronize(h->stream4);
     void *bufs[] = {h->d_indptr, h->d_indices, h->d_data,   h->d_lib,   h->d_l1,      h->d_parents, h->d_sindptr,
                     h->d_scount, h->d_sindices, h->d_sdata, h->d_slib,  h->d_dense,   h->d_colsum,  h->d_colsumsq,
-                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb_base, h->d_knn_idx_base, h->d_knn_dist, h->d_knn_ops, h->d_knn_list_off, h->d_knn_list_tiles, h->d_knn_cl, h->d_knn_cert, h->d_lvw_wq, h->d_lvw_i64, h->d_lvw_i32, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w};
+                    h->d_Qt,     h->d_Y,        h->d_Zacc,  h->d_small, h->d_emb_base, h->d_knn_idx_base, h->d_knn_dist, h->d_knn_ops, h->d_knn_list_off, h->d_knn_list_tiles, h->d_knn_cl, h->d_knn_cert, h->d_lvw_wq, h->d_lvw_i64, h->d_lvw_i32, h->d_qb, h->d_yb, h->d_omega_b, h->d_mu, h->d_lv_off, h->d_lv_adj, h->d_lv_comm, h->d_lv_tot, h->d_lv_i32, h->d_lv_w, h->d_umap_w};
     for (void *p : bufs)
         if (p) cudaFree(p);
     for (dd_lv_lane &l : h->lv_lanes) dd_lv_lane_free(l);

@@ -1066,7 +1066,7 @@ extern "C" int dd_knn_uncertified(dd_handle *h, int64_t *count_out) {
     return DD_OK;
 }
 
-// Experimental test hook ("next lever"): exact kNN in which the 256-row query block p only visits the
+// Test hook of the list-driven kernel: exact kNN in which the 256-row query block p only visits the
 // candidate tiles (128 rows each) list_tiles[list_off[p] .. list_off[p + 1]).  The caller is responsible for the lists being
 // sufficient (scripts/knn_listed_experiment.py derives them from bounding boxes); rows whose lists hold fewer than k - 1
 // other points get -1 entries.  Same outputs as dd_knn.

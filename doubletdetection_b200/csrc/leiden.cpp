@@ -4,9 +4,10 @@
 // (use_weights=True, RB-configuration quality, n_iterations=-1).  umap-learn and leidenalg are absent from the
 // image; the arithmetic of the weights is pinned by oracle/upstream.py (smooth_knn_dist, membership_strengths,
 // fuzzy_connectivities) and the move order of the partitioning by oracle/leiden_ref.py -- this file reproduces
-// both bit for bit / label for label.  Host code: the kNN lists come from the GPU (dd_fit_iterations copies
-// idx + dist of every iteration into a pinned slot), the graph has ~15 weighted edges per cell, and iterations
-// are clustered concurrently on the host workers while the GPU runs ahead.
+// both bit for bit / label for label.  In the fit loop the graph itself is built on the GPU (louvain_gpu.cu:
+// dd_dev_umap_graph, the device twin of umap_weights / umap_graph below) and arrives in a pinned slot; the host workers
+// partition it (dd_host_leiden_from_graph) concurrently while the GPU runs ahead.  The host graph builder serves the
+// stage-wise entry points and is what the device graph is tested against.
 #include <stdint.h>
 
 #include <algorithm>
@@ -423,9 +424,76 @@ int umap_graph(int64_t n, int32_t k, const int32_t *idx, const float *dist, Grap
     return DD_OK;
 }
 
+// The umap graph as the device builds it (louvain_gpu.cu: symmetric pattern with rows in arbitrary order, float32 union
+// weights widened to double, 0 = no edge) in the form umap_graph() produces: rows ascending, zeros dropped.
+int graph_from_device(int64_t n, const int32_t *off, const int32_t *adj, const double *w, Graph &g) {
+    if (n > 0 && (!off || off[0] != 0)) return DD_ERR_ARG;
+    const int64_t raw = n > 0 ? off[n] : 0;
+    if (raw < 0 || (raw > 0 && (!adj || !w))) return DD_ERR_ARG;
+    g.n = (int32_t)n;
+    g.indptr.assign((size_t)n + 1, 0);
+    g.indices.clear();
+    g.weights.clear();
+    g.indices.reserve((size_t)raw);
+    g.weights.reserve((size_t)raw);
+    std::vector<std::pair<int32_t, double>> row;
+    for (int64_t i = 0; i < n; i++) {
+        if (off[i + 1] < off[i] || off[i + 1] > raw) return DD_ERR_ARG;
+        row.clear();
+        for (int64_t e = off[i]; e < off[i + 1]; e++) {
+            if (adj[e] < 0 || adj[e] >= n) return DD_ERR_ARG;
+            if (w[e] != 0.0) row.emplace_back(adj[e], w[e]);
+        }
+        std::sort(row.begin(), row.end());
+        for (const auto &e : row) {
+            g.indices.push_back(e.first);
+            g.weights.push_back(e.second);
+        }
+        g.indptr[i + 1] = (int64_t)g.indices.size();
+    }
+    g.selfw.assign((size_t)n, 0.0);
+    if (g.weights.empty()) g.weights.push_back(0.0);  // keep "empty == unit weights" unambiguous
+    return DD_OK;
+}
+
 }  // namespace
 
-// The pipeline's path and the host entry: kNN lists (self in column 0) + float32 distances -> labels.
+// The pipeline's path: the umap graph built on the device -> labels.
+int dd_host_leiden_from_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *w, double resolution,
+                              uint64_t seed, int32_t *labels_out, int32_t *n_comm_out) {
+    if (n < 0 || (n > 0 && !labels_out) || n >= (1ll << 31) - 1) return DD_ERR_ARG;
+    Graph g;
+    const int rc = graph_from_device(n, off, adj, w, g);
+    if (rc != DD_OK) return rc;
+    return run_leiden(g, resolution, seed, labels_out, n_comm_out);
+}
+
+int dd_host_umap_canonical(int64_t n, const int32_t *off, const int32_t *adj, const double *w, int64_t *indptr_out,
+                           int32_t *indices_out, float *weights_out, int64_t capacity, int64_t *nnz_out) {
+    Graph g;
+    const int rc = graph_from_device(n, off, adj, w, g);
+    if (rc != DD_OK) return rc;
+    const int64_t nnz = (int64_t)g.indices.size();
+    *nnz_out = nnz;
+    if (capacity < nnz) return DD_OK;  // size query
+    if (!indptr_out || (nnz > 0 && (!indices_out || !weights_out))) return DD_ERR_ARG;
+    std::copy(g.indptr.begin(), g.indptr.end(), indptr_out);
+    for (int64_t e = 0; e < nnz; e++) {
+        indices_out[e] = g.indices[e];
+        weights_out[e] = (float)g.weights[e];
+    }
+    return DD_OK;
+}
+
+// Host-callable form of the pipeline's second half (tests: the slot layout of dd_fit_iterations without a GPU).
+extern "C" int dd_leiden_device_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *weights, double resolution,
+                                      uint64_t seed, int32_t *labels_out, int32_t *n_communities_out) {
+    const int rc = dd_host_leiden_from_graph(n, off, adj, weights, resolution, seed, labels_out, n_communities_out);
+    if (rc != DD_OK) dd_set_global_error("dd_leiden_device_graph: bad arguments or malformed graph (offsets, neighbour index out of range)");
+    return rc;
+}
+
+// The host entry: kNN lists (self in column 0) + float32 distances -> labels.
 int dd_host_leiden_knn(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist, double resolution,
                        uint64_t seed, int32_t *labels_out, int32_t *n_comm_out) {
     if (n < 0 || k < 2 || (n > 0 && (!knn_idx || !knn_dist || !labels_out))) return DD_ERR_ARG;

@@ -10,8 +10,10 @@
 #include "dd_internal.h"
 
 #include <cooperative_groups.h>
+#include <math_constants.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -606,7 +608,98 @@ __global__ void __launch_bounds__(256) k_jaccard_weights(const int32_t *__restri
         }
     }
 }
+// umap's smooth_knn_dist + compute_membership_strengths (sc.pp.neighbors(method="umap"), doubletdetection.py:331-336;
+// local_connectivity = 1, bandwidth = 1) for the Leiden branch: one thread per cell.  rho = the nearest positive distance,
+// sigma by bisection in float64 so that the memberships of the k - 1 neighbours sum to log2(k), directed weight
+// exp(-(d - rho) / sigma) stored as float32.  Same operations in the same order as the host twin (leiden.cpp:umap_weights,
+// specification oracle/upstream.py): float32 differences, float64 quotient / exp / sequential sum; explicit _rn
+// intrinsics keep the compiler from contracting anything.  (The host's global mean distance only floors sigma of rows
+// whose distances are all zero, and those rows' weights are 1 whatever sigma is: it is not needed here.)
+__global__ void __launch_bounds__(128) k_umap_rows(const int32_t *__restrict__ knn, const float *__restrict__ dist, int n,
+                                                   int k, double target, float *__restrict__ wdir) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *di = dist + (int64_t)i * k;
+    float rho = 0.f;
+    for (int c = 0; c < k; c++)
+        if (di[c] > 0.f) {
+            rho = di[c];
+            break;
+        }
+    double row_sum = 0.0;
+    for (int c = 0; c < k; c++) row_sum = __dadd_rn(row_sum, (double)di[c]);
+    double lo = 0.0, hi = CUDART_INF, mid = 1.0;
+    for (int it = 0; it < 64; it++) {
+        double psum = 0.0;
+        for (int c = 1; c < k; c++) {
+            const double d = (double)__fsub_rn(di[c], rho);
+            psum = __dadd_rn(psum, d > 0.0 ? exp(-__ddiv_rn(d, mid)) : 1.0);
+        }
+        if (fabs(__dsub_rn(psum, target)) < 1e-5) break;
+        if (psum > target) {
+            hi = mid;
+            mid = __ddiv_rn(__dadd_rn(lo, hi), 2.0);
+        } else {
+            lo = mid;
+            if (hi == CUDART_INF)
+                mid = __dmul_rn(mid, 2.0);
+            else
+                mid = __ddiv_rn(__dadd_rn(lo, hi), 2.0);
+        }
+    }
+    float sigma = __double2float_rn(mid);
+    const double floor_ = rho > 0.f ? __dmul_rn(1e-3, __ddiv_rn(row_sum, (double)k)) : 0.0;
+    if ((double)sigma < floor_) sigma = __double2float_rn(floor_);
+    for (int c = 0; c < k; c++) {
+        const int j = knn[(int64_t)i * k + c];
+        const float diff = __fsub_rn(di[c], rho);
+        float v;
+        if (j == i || j < 0)
+            v = 0.f;
+        else if (diff <= 0.f || sigma == 0.f)
+            v = 1.f;
+        else
+            v = __double2float_rn(exp(-__ddiv_rn((double)diff, (double)sigma)));
+        wdir[(int64_t)i * k + c] = v;
+    }
+}
+
+// umap's fuzzy union on the symmetric pattern: entry (i, j) carries a + b - a b in float32, a = w(i -> j), b = w(j -> i)
+// (0 where the list does not hold the other cell).  One warp per cell, lanes over its entries.  Entries whose union is 0
+// (underflowed memberships) stay in the pattern with weight 0; the host drops them.
+__global__ void __launch_bounds__(256) k_umap_union(const int32_t *__restrict__ knn, const float *__restrict__ wdir, int n, int k,
+                                                    const int32_t *__restrict__ off, const int32_t *__restrict__ adj,
+                                                    double *__restrict__ w_out) {
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= n) return;
+    for (int p = off[i] + lane; p < off[i + 1]; p += 32) {
+        const int j = adj[p];
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < k; c++) {
+            if (knn[(int64_t)i * k + c] == j) a = wdir[(int64_t)i * k + c];
+            if (knn[(int64_t)j * k + c] == i) b = wdir[(int64_t)j * k + c];
+        }
+        w_out[p] = (double)__fsub_rn(__fadd_rn(a, b), __fmul_rn(a, b));
+    }
+}
 }  // namespace
+
+// Symmetric pattern of the kNN lists (k columns, self in column 0) + umap's connectivities (Leiden branch):
+// h->d_lv_off / d_lv_adj / d_lv_w on the device, from h->d_knn_idx and h->d_knn_dist (asynchronous on h->stream).
+int dd_dev_umap_graph(dd_handle *h, int32_t k) {
+    if (k < 2) return dd_fail(h, DD_ERR_ARG, "umap graph: k < 2");
+    if (!h->d_knn_dist) return dd_fail(h, DD_ERR_ARG, "umap graph: no kNN distances on the device");
+    LvBuffers b;
+    DD_TRY(lv_build_graph(h, k, b));
+    DD_TRY(dd_reserve(h, &h->d_lv_w, &h->cap_lv_w, h->cap_lv_nnz));
+    DD_TRY(dd_reserve(h, &h->d_umap_w, &h->cap_umap_w, (int64_t)b.n * k));
+    DD_LAUNCH(h, "umap_rows", k_umap_rows, (unsigned)((b.n + 127) / 128), 128, 0, h->d_knn_idx, h->d_knn_dist, b.n, (int)k,
+              std::log2((double)k), h->d_umap_w);
+    DD_LAUNCH(h, "umap_union", k_umap_union, (unsigned)(((int64_t)b.n * 32 + 255) / 256), 256, 0, h->d_knn_idx, h->d_umap_w, b.n,
+              (int)k, h->d_lv_off, h->d_lv_adj, h->d_lv_w);
+    return DD_OK;
+}
 
 // Symmetric pattern of the kNN lists (k columns, self in column 0) + Jaccard weights: h->d_lv_off / d_lv_adj /
 // d_lv_w on the device (asynchronous on h->stream).
@@ -791,5 +884,29 @@ extern "C" int dd_jaccard_graph(dd_handle *h, int32_t k, int32_t prune, int32_t 
     DD_CUDA(h, cudaMemcpyAsync(indices_out, h->d_lv_adj, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, h->stream));
     DD_CUDA(h, cudaMemcpyAsync(weights_out, h->d_lv_w, sizeof(double) * nnz, cudaMemcpyDeviceToHost, h->stream));
     DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    return DD_OK;
+}
+
+// Test / inspection hook: umap's connectivities of the kNN lists + distances computed last (dd_knn with k neighbours incl.
+// self) as built on the device, in the canonical form the Leiden workers use (rows ascending, zero weights dropped) -- the
+// same format as the host twin dd_umap_connectivities.  Call with capacity 0 to get nnz_out.
+extern "C" int dd_umap_graph(dd_handle *h, int32_t k, int64_t *indptr_out, int32_t *indices_out, float *weights_out,
+                             int64_t capacity, int64_t *nnz_out) {
+    if (!h || !nnz_out) return dd_fail(h, DD_ERR_ARG, "dd_umap_graph: null argument");
+    if (!h->emb_valid || !h->d_knn_idx || !h->d_knn_dist) return dd_fail(h, DD_ERR_ARG, "dd_umap_graph: call dd_knn first");
+    DD_CUDA(h, cudaSetDevice(h->device));
+    DD_TRY(dd_dev_umap_graph(h, k));
+    const int64_t n = h->emb_rows;
+    std::vector<int32_t> off((size_t)n + 1);
+    DD_CUDA(h, cudaMemcpyAsync(off.data(), h->d_lv_off, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int64_t raw = off[n];
+    std::vector<int32_t> adj((size_t)std::max<int64_t>(raw, 1));
+    std::vector<double> w((size_t)std::max<int64_t>(raw, 1));
+    DD_CUDA(h, cudaMemcpyAsync(adj.data(), h->d_lv_adj, sizeof(int32_t) * raw, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaMemcpyAsync(w.data(), h->d_lv_w, sizeof(double) * raw, cudaMemcpyDeviceToHost, h->stream));
+    DD_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int rc = dd_host_umap_canonical(n, off.data(), adj.data(), w.data(), indptr_out, indices_out, weights_out, capacity, nnz_out);
+    if (rc != DD_OK) return dd_fail(h, rc, "dd_umap_graph: the device graph is malformed or an output pointer is null");
     return DD_OK;
 }

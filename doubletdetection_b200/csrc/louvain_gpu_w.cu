@@ -1,6 +1,6 @@
-// louvain_gpu_w.cu -- EXPERIMENTAL: the first Louvain level by synchronous coloured rounds for WEIGHTED graphs (PhenoGraph's
-// Jaccard graph, Leiden's umap graph).  Written after round 1's GPU budget was spent: it has never run on hardware and
-// nothing in dd_fit_iterations calls it yet; tests/gpu_weighted_level_check.py compares it with the specification.
+// louvain_gpu_w.cu -- the first Louvain level by synchronous coloured rounds for WEIGHTED graphs: what dd_fit_iterations
+// runs for PhenoGraph's Jaccard graph (the reference's default clustering, doubletdetection.py:317-325).  Measured and
+// parity-green on B200 (tests/test_gpu_pheno_level0.py, profiles/r2a_weighted_level.log, r2z_ncu_clustering_summary.md).
 //
 // Specification: oracle/louvain_ref.py:level0_parallel(..., weights); host twin: louvain.cpp:level0_parallel_host_w.  The
 // level works on fixed-point weights wq = rint(w * 2^32) held in int64: w(i, c), k_i, tot[c] and two_m are exact integer
@@ -8,9 +8,8 @@
 // the result is still bit-reproducible (the float64 atomics of the unweighted kernel are exact only because degrees are
 // integers).  The gain is the unweighted formula evaluated in double on those integers (explicit _rn intrinsics: no
 // contraction), candidates are compared by (gain, smaller id), singletons never move into a larger-id singleton.
-//
-// Kept deliberately simple (one launch per step, no CUDA graph, temporary buffers): correctness first, then fold it into
-// louvain_gpu.cu's machinery.
+// The device-built rows are compacted in place first (pruned entries to the tail) and the 32 x 17 steps are one CUDA-graph
+// replay on a clustering lane.
 #include "dd_internal.h"
 
 #include <algorithm>

@@ -131,7 +131,7 @@ int dd_upload_embedding(dd_handle *h, int64_t n_rows, int32_t n_comp, const floa
  * idx_out int32[A*k], dist_out float32[A*k] (may be NULL). */
 int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
 
-/* Experimental test hook (no counterpart in the reference): the same exact kNN, but the 256-row query block p only visits
+/* Test hook of the list-driven kernel (no counterpart in the reference): the same exact kNN, but the 256-row query block p only visits
  * the 128-row candidate tiles list_tiles[list_off[p] .. list_off[p + 1]) (host arrays, n_blocks = ceil(ceil(A / 128) / 2)
  * lists).  The caller guarantees that the lists are sufficient -- scripts/knn_listed_experiment.py derives them from
  * bounding boxes of a cluster-ordered embedding; neighbours missing from a list are simply not
@@ -139,7 +139,7 @@ int dd_knn(dd_handle *h, int32_t k, int32_t *idx_out, float *dist_out);
 int dd_knn_listed(dd_handle *h, int32_t k, int64_t n_blocks, const int32_t *list_off, const int32_t *list_tiles,
                   int32_t *idx_out, float *dist_out);
 
-/* Experimental test hook, one step further: the whole cluster-ordered kNN on the device.  perm int32[n_pad] maps a padded
+/* Test hook, one step further: both launches of the cluster-ordered kNN on the device with a caller-made ordering.  perm int32[n_pad] maps a padded
  * position to an original row or -1 (n_pad a multiple of 256; rows of a group contiguous, every group padded to whole
  * 256-row blocks), block_group int32[n_pad / 256] names the group of every block.  Launch A (own group) bounds every
  * query's k-th distance, launch B visits the tiles whose bounding boxes the bound cannot exclude, the result is re-ranked
@@ -189,13 +189,12 @@ int dd_louvain_csr(int64_t n, const int64_t *indptr, const int64_t *indices, con
                    double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 /* The same graph partitioned the way the kNN pipeline does it: first level by synchronous coloured rounds (the host twin
  * of the device level), the levels above sequentially.  With weights the first level works in fixed point (multiples of
- * 2^-32 summed in int64: exact, hence order-independent sums) -- the specification a device level for PhenoGraph's and
- * Leiden's weighted graphs will follow (oracle/louvain_ref.py; not yet used by dd_fit_iterations). */
+ * 2^-32 summed in int64: exact, hence order-independent sums) -- the specification of the device level that
+ * dd_fit_iterations runs for PhenoGraph's weighted graph (oracle/louvain_ref.py). */
 int dd_louvain_csr_level0(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                           double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 
-/* Experimental test hook (never run on hardware yet, not used by dd_fit_iterations): the weighted first level of
- * dd_louvain_csr_level0 on the DEVICE -- fixed-point weights, 64-bit integer atomics -- for an explicit symmetric CSR graph
+/* Test hook: the weighted first level of dd_louvain_csr_level0 on the DEVICE (what dd_fit_iterations runs for PhenoGraph) -- fixed-point weights, 64-bit integer atomics -- for an explicit symmetric CSR graph
  * (host arrays, positive weights, no self-loops).  comm_out int32[n] = community (a node id) of every node after the level,
  * to be compared with oracle/louvain_ref.py:level0_parallel (tests/gpu_weighted_level_check.py). */
 int dd_louvain_level0_weighted(dd_handle *h, int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
@@ -212,7 +211,8 @@ int dd_louvain_level0_weighted(dd_handle *h, int64_t n, const int64_t *indptr, c
  * edge weights used, iterated until stable like leidenalg's n_iterations=-1), labels by decreasing community
  * size.  umap-learn / leidenalg are absent from the image: the arithmetic of the weights is pinned by
  * oracle/upstream.py, the move order by oracle/leiden_ref.py (parity with leidenalg itself is unpinned).  This is
- * what dd_fit_iterations runs on its host workers for DD_CLUSTER_LEIDEN, fed by the device kNN.
+ * what dd_fit_iterations runs on its host workers for DD_CLUSTER_LEIDEN; the GRAPH of every iteration is built on the
+ * device (dd_umap_graph below is that stage's test hook), dd_umap_connectivities is its host twin.
  * dd_leiden_csr: the same partitioning of an explicit symmetric CSR graph (weights may be NULL = unweighted).
  * No handle: pure host code, thread-safe. */
 int dd_umap_connectivities(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn_dist,
@@ -222,6 +222,17 @@ int dd_leiden_knn(int64_t n, int32_t k, const int32_t *knn_idx, const float *knn
                   uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 int dd_leiden_csr(int64_t n, const int64_t *indptr, const int64_t *indices, const double *weights,
                   double resolution, uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
+/* umap's connectivities of the lists + distances of the last dd_knn(h, k, ...) as built on the DEVICE (one thread per
+ * cell runs smooth_knn_dist's bisection and the membership strengths, one warp per cell the fuzzy union on the symmetric
+ * pattern), returned in dd_umap_connectivities' format (ascending rows, zeros dropped, indptr_out int64[n + 1]).  Call
+ * with capacity 0 to get nnz_out, then with buffers of that size. */
+int dd_umap_graph(dd_handle *h, int32_t k, int64_t *indptr_out, int32_t *indices_out, float *weights_out,
+                  int64_t capacity, int64_t *nnz_out);
+/* The second half of the fit loop's Leiden stage on its own (host): the graph in the layout the device leaves in the
+ * pinned slot -- off int32[n + 1], adj int32[off[n]] with the rows in ANY order, weights float64 with 0 = no edge -- is
+ * put into canonical form (rows ascending, zeros dropped) and partitioned like dd_leiden_knn. */
+int dd_leiden_device_graph(int64_t n, const int32_t *off, const int32_t *adj, const double *weights, double resolution,
+                           uint64_t seed, int32_t *labels_out, int32_t *n_communities_out);
 
 /* ---- scoring, doubletdetection.py:344-383 (host) ----------------------------------------
  * labels int32[n_cells + n_synth]; scores_out / log_p_out float64[n_cells]:

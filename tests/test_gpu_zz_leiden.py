@@ -1,9 +1,7 @@
-"""clustering_algorithm="leiden" on the B200 path (doubletdetection.py:331-342): the exact kNN lists + distances
-of every iteration go from the GPU to the native host workers, which build umap's connectivities and run the
-in-repo Leiden.  Every test needs a B200 (`-m gpu`); nothing here reads /root/reference.
-
-(The file sorts last on purpose: this path was added after the round's GPU budget was spent, so it is the one part
-of the suite that has not yet run on hardware -- its host side is covered bit for bit by tests/test_host_native.py.)
+"""clustering_algorithm="leiden" on the B200 path (doubletdetection.py:331-342): umap's connectivities of every
+iteration's exact kNN lists + distances are built on the GPU (smooth_knn_dist bisection, membership strengths, fuzzy
+union) and the native host workers run the in-repo Leiden on them.  Every test needs a B200 (`-m gpu`); nothing here
+reads /root/reference.  The host side is covered bit for bit by tests/test_host_native.py.
 """
 
 import warnings
@@ -16,9 +14,54 @@ from oracle import datasets, pca_f64, reference_path, upstream
 pytestmark = pytest.mark.gpu
 
 
+def _blobs(n, dim, seed, spread=2.5, n_types=5):
+    rs = np.random.default_rng(seed)
+    return (rs.normal(size=(n, dim)) + rs.integers(0, n_types, size=(n, 1)) * spread).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,k", [(400, 10), (3000, 10), (20000, 10), (5000, 15), (60000, 10)])
+def test_device_umap_graph_matches_host_twin(handle, native, n, k):
+    """dd_umap_graph (device: one thread per cell for smooth_knn_dist + strengths, one warp per cell for the fuzzy union
+    on the symmetric pattern) against the host twin and the oracle's restatement on the device's own lists and
+    distances: same pattern, same float32 weights.  The device's float64 exp may differ from libm's in the last bit; that
+    survives the rounding to float32 with probability 2^-29 per edge and flips a bisection branch only if the membership
+    sum lands within 1e-15 of its target, so bit equality is asserted."""
+    emb = _blobs(n, 30, n + k, spread=1.5)
+    handle.upload_embedding(emb)
+    idx, dist = handle.knn(k)
+    got = handle.umap_graph(k)
+    want = native.umap_connectivities(idx, dist)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    differ = int(np.count_nonzero(got.data != want.data))
+    print(f"\n[umap graph n={n} k={k}] nnz {got.nnz}, weights that differ from the host twin: {differ}, "
+          f"max relative difference {float(np.max(np.abs(got.data - want.data) / want.data)):.2e}")
+    np.testing.assert_array_equal(got.data, want.data)
+    if n <= 5000:
+        ora = upstream.fuzzy_connectivities(idx, dist)
+        np.testing.assert_array_equal(got.indices, ora.indices)
+        np.testing.assert_array_equal(got.data, ora.data)
+
+
+def test_device_umap_graph_duplicates_and_far_neighbours(handle, native):
+    """Coincident cells (rho = 0 rows, distance 0 -> strength 1), and an outlier whose memberships underflow to 0 (entries
+    that stay in the device pattern with weight 0 and are dropped by the canonical form)."""
+    emb = _blobs(300, 4, 5)
+    emb[10:16] = emb[10]
+    emb[200] += 1.0e4
+    handle.upload_embedding(emb)
+    idx, dist = handle.knn(4)
+    got = handle.umap_graph(4)
+    want = native.umap_connectivities(idx, dist)
+    np.testing.assert_array_equal(got.indptr, want.indptr)
+    np.testing.assert_array_equal(got.indices, want.indices)
+    np.testing.assert_array_equal(got.data, want.data)
+
+
 def test_pipeline_leiden_matches_stagewise_calls(handle, native):
-    """dd_fit_iterations(clustering=leiden) == stage-by-stage entry points + dd_leiden_knn on the device's own lists
-    and distances (checks the pinned-slot layout and the ordering of the copies against the next iteration's kNN)."""
+    """dd_fit_iterations(clustering=leiden) == stage-by-stage entry points + Leiden on the device-built umap graph of the
+    device's own lists and distances (checks the pinned-slot layout and the ordering of the graph kernels and copies
+    against the next iteration's kNN), and that graph == the host twin's == the oracle's, so == dd_leiden_knn."""
     raw = datasets.structured_counts(3000, 400, seed=7)
     n_cells, n_iters, n_synth = 3000, 4, 750
     rng = np.random.default_rng(5)
@@ -34,7 +77,8 @@ def test_pipeline_leiden_matches_stagewise_calls(handle, native):
         handle.normalise_log(handle.median_lib_size(), 0.1)
         handle.pca(C, omega, n_power)
         idx, dist = handle.knn(10)
-        labels = native.leiden_knn(idx, dist, resolution=4.0, seed=0)
+        dev = handle.umap_graph(10)
+        labels = native.leiden_csr(dev.indptr, dev.indices, dev.data.astype(np.float64), resolution=4.0, seed=0)
         np.testing.assert_array_equal(out["communities"][i], labels[:n_cells])
         np.testing.assert_array_equal(out["synth_communities"][i], labels[n_cells:])
         s, lp, _, _ = reference_path.score_communities(labels, n_cells)
@@ -42,9 +86,10 @@ def test_pipeline_leiden_matches_stagewise_calls(handle, native):
         np.testing.assert_allclose(out["log_p"][i], lp, rtol=1e-9, atol=1e-12)
         # the device graph against the oracle's restatement on the device's own lists: same bits
         want = upstream.fuzzy_connectivities(idx, dist)
-        got = native.umap_connectivities(idx, dist)
-        np.testing.assert_array_equal(got.indices, want.indices)
-        np.testing.assert_array_equal(got.data, want.data)
+        for got in (native.umap_connectivities(idx, dist), dev):
+            np.testing.assert_array_equal(got.indices, want.indices)
+            np.testing.assert_array_equal(got.data, want.data)
+        np.testing.assert_array_equal(native.leiden_knn(idx, dist, resolution=4.0, seed=0), labels)
 
 
 def test_classifier_leiden_vs_oracle():

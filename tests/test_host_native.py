@@ -249,6 +249,36 @@ def test_leiden_matches_python_spec(native, n, k, gamma, seed):
         assert ncomp == 1, f"community {c} is disconnected"
 
 
+@pytest.mark.parametrize("n,k,seed", [(400, 10, 0), (1500, 10, 21)])
+def test_leiden_from_device_layout_graph(native, n, k, seed):
+    """dd_fit_iterations hands its Leiden workers the umap graph as the DEVICE builds it: the symmetric pattern with int32
+    offsets, rows in arbitrary order, float64 weights and 0 for "no edge".  The host half (dd_leiden_device_graph) must put
+    that into the canonical form and partition it exactly like dd_leiden_knn."""
+    idx, dist = upstream.knn_brute(_blobs(n, 6, n + k), k)
+    C = upstream.fuzzy_connectivities(idx, dist)
+    rs = np.random.default_rng(seed)
+    off, adj, w = [0], [], []
+    for i in range(n):
+        cols = C.indices[C.indptr[i]:C.indptr[i + 1]].tolist()
+        vals = C.data[C.indptr[i]:C.indptr[i + 1]].astype(np.float64).tolist()
+        for _ in range(int(rs.integers(0, 3))):  # pattern entries whose union underflowed: weight 0
+            j = int(rs.integers(0, n))
+            if j != i and j not in cols:
+                cols.append(j)
+                vals.append(0.0)
+        order = rs.permutation(len(cols))
+        adj += [cols[t] for t in order]
+        w += [vals[t] for t in order]
+        off.append(len(adj))
+    want = native.leiden_knn(idx, dist, resolution=4.0, seed=seed)
+    got = native.leiden_device_graph(off, adj, w, resolution=4.0, seed=seed)
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        native.leiden_device_graph([0, 1, 2], [1, 5], [1.0, 1.0])  # neighbour out of range
+    with pytest.raises(ValueError):
+        native.leiden_device_graph([0, 2, 1], [1, 0], [1.0, 1.0])  # offsets not monotone
+
+
 def test_leiden_degenerate_inputs(native):
     # no edges: every node its own community
     np.testing.assert_array_equal(native.leiden_csr(np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int64)), np.arange(5))
