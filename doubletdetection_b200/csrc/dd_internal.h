@@ -137,6 +137,7 @@ struct dd_handle {
     int64_t knn_idx_stride = 0;
     float *d_knn_dist = nullptr;
     int64_t cap_knn = 0;
+    int32_t knn_last_k = 0;  // row stride of the lists / distances written last (the graph hooks refuse another k)
     uint8_t *d_knn_ops = nullptr;  // tcgen05 operand tiles (queries, candidates) in UMMA canonical layout
     int64_t cap_knn_ops = 0;
     // list-driven kernel (dd_knn_listed, cluster-ordered kNN): candidate-tile lists per 256-row query block; knn_list_pairs > 0 while such a call runs

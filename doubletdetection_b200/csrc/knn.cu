@@ -1011,6 +1011,7 @@ int dd_dev_knn(dd_handle *h, int32_t k) {
     if (k < 2 || k > 31) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: k must be in [2, 31]");
     if (k > n) return dd_fail(h, DD_ERR_ARG, "knn: k exceeds the number of rows");
     if (n >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_UNSUPPORTED, "knn: too many rows for int32 indices");
+    h->knn_last_k = k;
     const int TL = (k - 1 <= 12) ? 16 : 32;
     const int64_t n_padded = (n + 255) / 256 * 256;  // the tensor-core path keeps lists for whole 256-row CTAs
     // candidate lists: 32 per row on the FFMA fallback, up to 40 per row on the tcgen05 path (k - 1 > 12: lists of 40)

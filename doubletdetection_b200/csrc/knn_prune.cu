@@ -205,6 +205,7 @@ extern "C" int dd_knn_pruned(dd_handle *h, int32_t k, int64_t n_pad, const int32
     if (!perm || !block_group || !idx_out) return dd_fail(h, DD_ERR_ARG, "dd_knn_pruned: null argument");
     if (!h->emb_valid || h->KP != 32) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_knn_pruned: needs an embedding of <= 32 components");
     if (k < 2 || k > 13) return dd_fail(h, DD_ERR_UNSUPPORTED, "dd_knn_pruned: k must be in [2, 13]");
+    h->knn_last_k = k;
     const int64_t n = h->emb_rows;
     if (n_pad < n || n_pad % 256 != 0 || n_pad >= (1ll << 31) - 1) return dd_fail(h, DD_ERR_ARG, "dd_knn_pruned: bad padded size");
     const int n_blocks = (int)(n_pad / 256), n_tiles = (int)(n_pad / tc::TILE);

@@ -873,6 +873,7 @@ extern "C" int dd_jaccard_graph(dd_handle *h, int32_t k, int32_t prune, int32_t 
                                 double *weights_out, int64_t capacity, int64_t *nnz_out) {
     if (!h || !indptr_out || !nnz_out) return dd_fail(h, DD_ERR_ARG, "dd_jaccard_graph: null argument");
     if (!h->emb_valid || !h->d_knn_idx) return dd_fail(h, DD_ERR_ARG, "dd_jaccard_graph: call dd_knn first");
+    if (k != h->knn_last_k) return dd_fail(h, DD_ERR_ARG, "dd_jaccard_graph: k differs from the k of the last kNN on this handle");
     DD_CUDA(h, cudaSetDevice(h->device));
     DD_TRY(dd_dev_jaccard_graph(h, k, prune));
     const int64_t n = h->emb_rows;
@@ -894,6 +895,7 @@ extern "C" int dd_umap_graph(dd_handle *h, int32_t k, int64_t *indptr_out, int32
                              int64_t capacity, int64_t *nnz_out) {
     if (!h || !nnz_out) return dd_fail(h, DD_ERR_ARG, "dd_umap_graph: null argument");
     if (!h->emb_valid || !h->d_knn_idx || !h->d_knn_dist) return dd_fail(h, DD_ERR_ARG, "dd_umap_graph: call dd_knn first");
+    if (k != h->knn_last_k) return dd_fail(h, DD_ERR_ARG, "dd_umap_graph: k differs from the k of the last kNN on this handle");
     DD_CUDA(h, cudaSetDevice(h->device));
     DD_TRY(dd_dev_umap_graph(h, k));
     const int64_t n = h->emb_rows;
