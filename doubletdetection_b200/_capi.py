@@ -612,7 +612,9 @@ class Handle:
     # the loop
     def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10,
                        resolution=4.0, seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0,
-                       clustering="louvain", pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10):
+                       clustering="louvain", pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10, out=None):
+        """``out``: result arrays of a previous / concurrent call on the same parents (``fit_iterations_pipelined``): the
+        loop writes the rows of ITS iterations into them instead of allocating its own."""
         parents = np.ascontiguousarray(parents, dtype=np.int64)
         n_iters, n_synth = parents.shape[0], parents.shape[1]
         omega = _f32(omega)
@@ -623,10 +625,12 @@ class Handle:
                       {"louvain": CLUSTER_LOUVAIN, "phenograph": CLUSTER_PHENOGRAPH, "leiden": CLUSTER_LEIDEN}[clustering], int(pheno_k),
                       int(bool(pheno_prune)), int(pheno_min_cluster_size))
         N = self.n_cells
-        scores = np.zeros((n_iters, N), dtype=np.float64)
-        logp = np.zeros((n_iters, N), dtype=np.float64)
-        comm = np.zeros((n_iters, N), dtype=np.int32)
-        synth_comm = np.zeros((n_iters, max(n_synth, 1)), dtype=np.int32)
+        if out is None:
+            out = alloc_fit_outputs(n_iters, N, n_synth)
+        scores, logp, comm, synth_comm = out
+        if (scores.shape != (n_iters, N) or logp.shape != (n_iters, N) or comm.shape != (n_iters, N)
+                or synth_comm.shape != (n_iters, max(n_synth, 1))):
+            raise ValueError("fit_iterations: `out` arrays do not match (n_iters, n_cells, n_synth)")
         stage_ms = np.zeros(8, dtype=np.float64)
         self._check(self._lib.dd_fit_iterations(
             self._h, ctypes.byref(p), _ptr(parents, ctypes.c_int64), _ptr(omega, ctypes.c_float),
@@ -681,6 +685,12 @@ class Handle:
         return ms.value, n.value
 
 
+def alloc_fit_outputs(n_iters, n_cells, n_synth):
+    """(scores, log_p, communities, synth_communities) of ``n_iters`` iterations, zero-filled (lazily: calloc pages)."""
+    return (np.zeros((n_iters, n_cells), dtype=np.float64), np.zeros((n_iters, n_cells), dtype=np.float64),
+            np.zeros((n_iters, n_cells), dtype=np.int32), np.zeros((n_iters, max(n_synth, 1)), dtype=np.int32))
+
+
 def fit_iterations_pipelined(handles, parents, omega, *, iter_begin=0, iter_end=None, n_host_threads=1, **kw):
     """``Handle.fit_iterations`` over several handles of ONE GPU that share the count matrix: the iteration range is cut into
     contiguous pieces, one pipelined loop (and host thread; ctypes releases the GIL) per handle.  The loops interleave on the
@@ -698,11 +708,15 @@ def fit_iterations_pipelined(handles, parents, omega, *, iter_begin=0, iter_end=
     bounds = [iter_begin + (n_run * i) // pipes for i in range(pipes + 1)]
     outs, errors = [None] * pipes, [None] * pipes
     threads_each = max(1, n_host_threads // pipes)
+    # ONE set of result arrays: every loop writes the rows of its own iterations (no per-loop copies to merge afterwards)
+    n_cells = getattr(handles[0], "n_cells", None)
+    shared = alloc_fit_outputs(n_iters, n_cells, parents.shape[1]) if n_cells else None
+    extra = {} if shared is None else {"out": shared}
 
     def work(i):
         try:
             outs[i] = handles[i].fit_iterations(parents, omega, iter_begin=bounds[i], iter_end=bounds[i + 1],
-                                                n_host_threads=threads_each, **kw)
+                                                n_host_threads=threads_each, **extra, **kw)
         except Exception as e:  # noqa: BLE001 -- re-raised on the calling thread
             errors[i] = e
 
@@ -717,7 +731,8 @@ def fit_iterations_pipelined(handles, parents, omega, *, iter_begin=0, iter_end=
     out = outs[0]
     for i in range(1, pipes):
         for key in ("scores", "log_p", "communities", "synth_communities"):
-            out[key][bounds[i]:bounds[i + 1]] = outs[i][key][bounds[i]:bounds[i + 1]]
+            if not np.may_share_memory(out[key], outs[i][key]):  # a handle that allocated its own arrays
+                out[key][bounds[i]:bounds[i + 1]] = outs[i][key][bounds[i]:bounds[i + 1]]
     stage = {k: sum(o["stage_ms"][k] for o in outs) for k in out["stage_ms"]}
     # the loops run side by side: what the caller waited for is the longest of them
     for key in ("wall", "device_total"):

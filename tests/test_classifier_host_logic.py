@@ -44,7 +44,7 @@ class OracleHandle:
 
     def fit_iterations(self, parents, omega, *, pseudocount, standard_scaling, n_comp, n_power_iter, knn_k=10, resolution=4.0,
                        seed=0, n_host_threads=1, iter_begin=0, iter_end=None, scale_max_value=15.0, clustering="louvain",
-                       pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10):
+                       pheno_k=30, pheno_prune=True, pheno_min_cluster_size=10, out=None):
         OracleHandle.calls.append(dict(n_comp=n_comp, n_power_iter=n_power_iter, omega_shape=omega.shape, seed=seed,
                                        clustering=clustering, resolution=resolution, n_host_threads=n_host_threads,
                                        iter_begin=iter_begin, iter_end=iter_end, standard_scaling=standard_scaling))
@@ -56,8 +56,11 @@ class OracleHandle:
         from sklearn.utils.sparsefuncs_fast import inplace_csr_row_normalize_l1
 
         inplace_csr_row_normalize_l1(normed)
-        out = dict(scores=np.zeros((n_iters, n)), log_p=np.zeros((n_iters, n)), communities=np.zeros((n_iters, n), np.int32),
-                   synth_communities=np.zeros((n_iters, n_synth), np.int32), stage_ms={"wall": 0.0})
+        if out is not None:  # the pipelined wrapper's shared result arrays
+            out = dict(scores=out[0], log_p=out[1], communities=out[2], synth_communities=out[3][:, :n_synth], stage_ms={"wall": 0.0})
+        else:
+            out = dict(scores=np.zeros((n_iters, n)), log_p=np.zeros((n_iters, n)), communities=np.zeros((n_iters, n), np.int32),
+                       synth_communities=np.zeros((n_iters, n_synth), np.int32), stage_ms={"wall": 0.0})
         for i in range(iter_begin, iter_end):
             synth = reference_path.create_doublets(self.raw, parents[i])
             aug, _, _ = reference_path.normalise(synth, lib, normed, pseudocount)
@@ -262,6 +265,20 @@ def test_fit_iterations_pipelined_merges_the_pieces():
     assert hs[0].seen == (2, 3, 4) and "pipelines" not in out["stage_ms"]
     with pytest.raises(NotImplementedError):
         _capi.fit_iterations_pipelined([Piece(0), Piece(1, fail=True)], parents, None, n_host_threads=2)
+
+    class SharedPiece(Piece):  # what Handle.fit_iterations does: the wrapper's ONE set of result arrays, own rows only
+        n_cells = 5
+
+        def fit_iterations(self, parents, omega, *, iter_begin, iter_end, n_host_threads, out, **kw):
+            for a in out:
+                a[iter_begin:iter_end] = self.tag + 1
+            return dict(scores=out[0], log_p=out[1], communities=out[2], synth_communities=out[3][:, :2],
+                        stage_ms=dict(pca=1.0, wall=10.0 + self.tag, device_total=9.0 + self.tag))
+
+    out = _capi.fit_iterations_pipelined([SharedPiece(0), SharedPiece(1)], parents, None, iter_begin=1, iter_end=7, n_host_threads=2)
+    np.testing.assert_array_equal(out["communities"][:, 0], [0, 1, 1, 1, 2, 2, 2])
+    np.testing.assert_array_equal(out["log_p"][:, 4], [0, 1, 1, 1, 2, 2, 2])
+    assert out["synth_communities"].shape == (7, 2) and out["scores"].shape == (7, 5)
 
 
 def test_sparse_input_with_nan_raises_sklearns_error(shim):
