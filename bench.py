@@ -541,8 +541,9 @@ def run_ours(args, wl, counts):
     my_iters = it1 - it0
     h2d = (counts.indptr.nbytes + counts.indices.nbytes + counts.data.nbytes + omega.nbytes + my_iters * n_synth * 2 * 8)
     # per iteration: the pattern graph (offsets, first-level communities, adjacency upper bound) + PCA flag; N > 1:
-    # predict() all-reduces three N-vectors (votes, valid counts, log-p sums) instead of gathering the (n_iters, N) arrays
-    d2h = my_iters * (((n_aug + 1) + n_aug + n_aug * 18) * 4 + 8) + n_cells * 4 + (3 * 8 * n_cells if world > 1 else 0)
+    # predict() all-reduces two int64 N-vectors (votes, valid counts; doublet_score() would add the log-p sums) instead of
+    # gathering the (n_iters, N) arrays
+    d2h = my_iters * (((n_aug + 1) + n_aug + n_aug * 18) * 4 + 8) + n_cells * 4 + (2 * 8 * n_cells if world > 1 else 0)
     n_doublets = int(np.nansum(labels))
 
     line = {

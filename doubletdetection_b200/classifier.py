@@ -237,9 +237,10 @@ class BoostClassifier:
     synth_communities_ = property(lambda self: self._get_fitted("synth_communities_"),
                                   lambda self, v: self._fitted.__setitem__("synth_communities_", v))
 
-    def _reduced_log_p_stats(self, log_p_thresh):
-        """(votes, valid count, sum of valid log p) per cell over ALL iterations.  Pending sharded fit: from this rank's
-        rows, summed over the ranks (integers exactly; the float64 sums in rank order instead of iteration order)."""
+    def _reduced_log_p_stats(self, log_p_thresh, want_total=True):
+        """(votes, valid count, sum of valid log p) per cell over ALL iterations (votes / the sum only if asked for: the sum
+        is two thirds of the work and predict does not need it).  Pending sharded fit: from this rank's rows, summed over
+        the ranks (integers exactly; the float64 sums in rank order instead of iteration order)."""
         if self._pending is None:
             log_p = np.asarray(self.all_log_p_values_)
         else:
@@ -248,17 +249,20 @@ class BoostClassifier:
         with np.errstate(invalid="ignore"):
             votes = np.count_nonzero((log_p <= log_p_thresh) & valid, axis=0) if log_p_thresh is not None else None
         count = np.count_nonzero(valid, axis=0)
-        total = np.where(valid, log_p, 0.0).sum(axis=0)
+        total = np.where(valid, log_p, 0.0).sum(axis=0) if want_total else None
         if self._pending is not None:
             import torch
 
             dist = self._pending["dist"]
             dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
             ints = np.stack([votes if votes is not None else np.zeros_like(count), count]).astype(np.int64)
-            t_i, t_f = torch.from_numpy(ints).to(dev), torch.from_numpy(np.ascontiguousarray(total)).to(dev)
+            t_i = torch.from_numpy(ints).to(dev)
             dist.all_reduce(t_i, op=dist.ReduceOp.SUM)
-            dist.all_reduce(t_f, op=dist.ReduceOp.SUM)
-            ints, total = t_i.cpu().numpy(), t_f.cpu().numpy()
+            ints = t_i.cpu().numpy()
+            if want_total:
+                t_f = torch.from_numpy(np.ascontiguousarray(total)).to(dev)
+                dist.all_reduce(t_f, op=dist.ReduceOp.SUM)
+                total = t_f.cpu().numpy()
             votes, count = (ints[0] if votes is not None else None), ints[1]
         return votes, count, total
 
@@ -513,7 +517,7 @@ class BoostClassifier:
             # :232-241 -- np.mean(np.ma.masked_invalid(log_p) <= thresh, axis=0), the vote >= voter_thresh, both filled
             # with NaN where every iteration is masked.  Same values without the masked-array machinery (42 -> 6 ms at
             # 25 x 100k): a masked mean is (number of valid votes) * 1.0 / (number of valid entries) in float64.
-            votes, count, _ = self._reduced_log_p_stats(log_p_thresh)
+            votes, count, _ = self._reduced_log_p_stats(log_p_thresh, want_total=False)
             with np.errstate(invalid="ignore", divide="ignore"):
                 average = votes * 1.0 / count
                 labels = (average >= voter_thresh).astype(float)
