@@ -216,17 +216,21 @@ class BoostClassifier:
         self._store(merged)
 
     def _store(self, out):
+        # the reference stores the communities in float arrays (:188); the native loop returns int32: converted when read
+        # (20 MB per fit at 25 x 100k that predict / doublet_score never look at)
         self._fitted = dict(
             all_scores_=out["scores"], all_log_p_values_=out["log_p"],
-            communities_=out["communities"].astype(np.float64),  # the reference stores them in float arrays (:188)
-            synth_communities_=out["synth_communities"].astype(np.float64))
+            communities_=out["communities"], synth_communities_=out["synth_communities"])
 
     def _get_fitted(self, name):
         self._collect()
         try:
-            return self._fitted[name]
+            value = self._fitted[name]
         except KeyError:
             raise AttributeError(f"{name} is set by fit()") from None
+        if name in ("communities_", "synth_communities_") and isinstance(value, np.ndarray) and value.dtype != np.float64:
+            value = self._fitted[name] = value.astype(np.float64)
+        return value
 
     all_scores_ = property(lambda self: self._get_fitted("all_scores_"),
                            lambda self, v: self._fitted.__setitem__("all_scores_", v))
