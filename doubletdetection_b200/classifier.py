@@ -8,8 +8,8 @@ where ``_one_fit`` (:274-383) executes: synthetic doublets, normalise/log, optio
 randomized PCA and the exact kNN graph are CUDA kernels, clustering (Louvain) and scoring are native
 host code overlapped with the GPU.  ``clustering_algorithm="phenograph"`` (the reference's default) builds
 PhenoGraph's Jaccard graph of the 30 nearest neighbours on the GPU and partitions it with the in-repo Louvain
-(one seeded run; the phenograph package with its time-seeded binaries is not available); ``"leiden"`` takes the
-exact kNN lists and distances from the GPU and builds umap's fuzzy-simplicial-set weights and the Leiden partition
+(one seeded run; the phenograph package with its time-seeded binaries is not available); ``"leiden"`` builds
+umap's fuzzy-simplicial-set weights of the exact kNN lists and distances on the GPU as well and partitions that graph
 on the native host workers (in-repo Leiden; leidenalg is not available).  There is no CPU fallback: without the built library or without a B200 ``fit`` raises.
 
 Keyword-only extensions (not in the reference): ``device`` (CUDA device index; default
@@ -205,7 +205,7 @@ class BoostClassifier:
     # ------------------------------------------------------------------ fitted (n_iters, .) arrays (:186-214)
     # Plain arrays after a single-process fit.  After an ITERATION-SHARDED fit (distributed=True / "allgather") every rank
     # holds the rows of its own iterations only: predict() and doublet_score() need per-cell sums over the iterations, so
-    # they all-reduce three N-vectors (votes, valid counts, log-p sums) instead of moving the (n_iters x N) arrays; the
+    # they all-reduce N-vectors (votes and valid counts; log-p sums for doublet_score) instead of moving the (n_iters x N) arrays; the
     # arrays themselves are gathered on first access (a collective: every rank must touch them, or none).
     def _collect(self):
         if self._pending is None:
@@ -503,8 +503,10 @@ class BoostClassifier:
                 labels = _capi.phenograph_knn(idx, prune=cluster_kw["pheno_prune"],
                                               min_cluster_size=cluster_kw["pheno_min_cluster_size"], seed=seed)
             elif algo == "leiden":
-                idx, dist = h.knn(10)
-                labels = _capi.leiden_knn(idx, dist, resolution=cluster_kw["resolution"], seed=seed)
+                h.knn(10, with_dist=False)  # the distances stay on the device, where umap's graph is built
+                g = h.umap_graph(10)
+                labels = _capi.leiden_csr(g.indptr, g.indices, g.data.astype(np.float64), resolution=cluster_kw["resolution"],
+                                          seed=seed)
             else:
                 idx, _ = h.knn(10, with_dist=False)
                 labels = _capi.louvain_knn(idx, resolution=cluster_kw["resolution"], seed=seed)

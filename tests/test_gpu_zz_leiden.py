@@ -184,3 +184,32 @@ def test_classifier_phenograph_vs_reference_golden(name):
     np.testing.assert_array_equal(clf.all_scores_, g["all_scores"])
     np.testing.assert_allclose(clf.all_log_p_values_, g["all_log_p_values"], rtol=1e-4, atol=1e-12, equal_nan=True)
     np.testing.assert_array_equal(labels, g["labels"])
+
+
+def test_classifier_leiden_on_the_exact_pca_route(handle, native):
+    """``clustering_algorithm="leiden"`` with a shape for which sklearn's PCA is exact (<= 1000 genes, >= 10x as many
+    augmented cells -> covariance_eigh): the iteration-by-iteration route of the shim, which also takes umap's graph from
+    the device.  The host twin (``dd_leiden_knn``: graph AND partition on the host) run on the device's own lists and
+    distances must reproduce the classifier's communities and scores exactly."""
+    from doubletdetection_b200 import BoostClassifier
+    from doubletdetection_b200.classifier import _exact_pca, _pca_solver
+
+    counts = datasets.structured_counts(2400, 200, seed=33)
+    n = counts.shape[0]
+    assert _pca_solver(n + n // 4, 200, 30) == "covariance_eigh"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(n_iters=2, clustering_algorithm="leiden", random_state=0, n_jobs=2).fit(counts)
+    handle.upload_counts(reference_path.prologue(counts, 10000)["raw"])
+    for i in range(2):
+        handle.create_doublets(np.asarray(clf._parents_array[i]))
+        handle.normalise_log(handle.median_lib_size(), 0.1)
+        _exact_pca(handle, 30)
+        idx, dist = handle.knn(10)
+        labels = native.leiden_knn(idx, dist, resolution=4.0, seed=0)
+        np.testing.assert_array_equal(clf.communities_[i], labels[:n])
+        np.testing.assert_array_equal(clf.synth_communities_[i], labels[n:])
+        s, lp, _, _ = reference_path.score_communities(labels, n)
+        np.testing.assert_array_equal(clf.all_scores_[i], s)
+        np.testing.assert_allclose(clf.all_log_p_values_[i], lp, rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert clf.communities_.dtype == np.float64  # converted on access (the reference keeps float arrays, :188)
