@@ -91,6 +91,13 @@ bool move_nodes(const Graph &g, double gamma, double two_m, SplitMix64 &rng, std
     int64_t n_moves = 0;
     while (count > 0) {
         const int32_t i = w.queue[head];
+        if (count > 8) {  // entries further down the ring are valid node ids even where they are stale
+            int32_t a = head + 8, b = head + 4;
+            if (a >= n) a -= n;
+            if (b >= n) b -= n;
+            g.prefetch_offset(w.queue[a]);
+            g.prefetch_row(w.queue[b]);
+        }
         head = (head + 1 == n) ? 0 : head + 1;
         count--;
         w.inq[i] = 0;
@@ -171,7 +178,12 @@ void refine(const Graph &g, double gamma, double two_m, SplitMix64 &rng, const s
     w.seen.assign(n, 0);
     w.cands.resize(std::max<int32_t>(n, 1));
     permutation(n, rng, w.order);
-    for (int32_t v : w.order) {
+    for (int32_t t = 0; t < n; t++) {
+        const int32_t v = w.order[t];
+        if (t + 8 < n) {
+            g.prefetch_offset(w.order[t + 8]);
+            g.prefetch_row(w.order[t + 4]);
+        }
         if (w.rsize[w.refined[v]] != 1) continue;
         const int32_t C = part[v];
         const double kv = w.k[v];

@@ -209,6 +209,10 @@ void ddlv::aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &ou
         touched.clear();
         for (int64_t p = mstart[a]; p < mstart[a + 1]; p++) {
             const int32_t i = members[p];
+            if (p + 8 < n) {  // members[] is one array over all communities: the look-ahead crosses their boundaries
+                g.prefetch_offset(members[p + 8]);
+                g.prefetch_row(members[p + 4]);
+            }
             s += g.selfw[i];
             for (int64_t e = g.indptr[i]; e < g.indptr[i + 1]; e++) {
                 const int32_t b = node2new[g.indices[e]];
