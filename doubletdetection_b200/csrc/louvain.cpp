@@ -195,18 +195,22 @@ void ddlv::aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &ou
     }
     out.n = nc;
     out.indptr.assign(nc + 1, 0);
-    out.indices.clear();
-    out.weights.clear();
     out.selfw.assign(nc, 0.0);
-    out.indices.reserve(g.indices.size());
-    out.weights.reserve(g.indices.size());
+    // the aggregate has at most as many entries as g: written by position, trimmed at the end
+    out.indices.resize(g.indices.size());
+    out.weights.resize(g.indices.size());
+    int32_t *const oi = out.indices.data();
+    double *const ow = out.weights.data();
+    int64_t pos = 0;
     std::vector<double> acc(nc, 0.0);
-    std::vector<uint8_t> seen(nc, 0);
-    std::vector<int32_t> touched;
-    touched.reserve(nc);
+    // The neighbour communities of `a` must come out in ASCENDING order (the sweeps above add weights in adjacency order).
+    // A two-level bit set (one bit per community, one summary bit per 64-bit word) replaces "collect + std::sort": marking
+    // is one OR, the ordered walk visits only the set words -- the comparison sort of ~40 random ids per community was
+    // the largest single item of the aggregation (50 of 120 ms at 125 k nodes).
+    const int32_t n_words = (nc + 63) >> 6, n_summary = (n_words + 63) >> 6;
+    std::vector<uint64_t> bits(std::max(n_words, 1), 0), summary(std::max(n_summary, 1), 0);
     for (int32_t a = 0; a < nc; a++) {
         double s = 0.0;
-        touched.clear();
         for (int64_t p = mstart[a]; p < mstart[a + 1]; p++) {
             const int32_t i = members[p];
             if (p + 8 < n) {  // members[] is one array over all communities: the look-ahead crosses their boundaries
@@ -220,24 +224,40 @@ void ddlv::aggregate(const Graph &g, const std::vector<int32_t> &comm, Graph &ou
                 if (b == a) {
                     s += w;
                 } else {
-                    if (!seen[b]) {
-                        seen[b] = 1;
+                    uint64_t &word = bits[b >> 6];
+                    const uint64_t m = 1ull << (b & 63);
+                    if (!(word & m)) {
+                        word |= m;
+                        summary[b >> 12] |= 1ull << ((b >> 6) & 63);
                         acc[b] = 0.0;
-                        touched.push_back(b);
                     }
                     acc[b] += w;
                 }
             }
         }
         out.selfw[a] = s;
-        std::sort(touched.begin(), touched.end());
-        for (int32_t b : touched) {
-            out.indices.push_back(b);
-            out.weights.push_back(acc[b]);
-            seen[b] = 0;
+        for (int32_t si = 0; si < n_summary; si++) {
+            uint64_t sw = summary[si];
+            if (!sw) continue;
+            summary[si] = 0;
+            while (sw) {
+                const int32_t wi = (si << 6) + __builtin_ctzll(sw);
+                sw &= sw - 1;
+                uint64_t bw = bits[wi];
+                bits[wi] = 0;
+                while (bw) {
+                    const int32_t b = (wi << 6) + __builtin_ctzll(bw);
+                    bw &= bw - 1;
+                    oi[pos] = b;
+                    ow[pos] = acc[b];
+                    pos++;
+                }
+            }
         }
-        out.indptr[a + 1] = (int64_t)out.indices.size();
+        out.indptr[a + 1] = pos;
     }
+    out.indices.resize((size_t)pos);
+    out.weights.resize((size_t)pos);
     if (out.weights.empty()) out.weights.push_back(0.0);  // keep "empty == unit weights" unambiguous
 }
 
