@@ -183,6 +183,11 @@ void refine(const Graph &g, double gamma, double two_m, SplitMix64 &rng, const s
         if (t + 8 < n) {
             g.prefetch_offset(w.order[t + 8]);
             g.prefetch_row(w.order[t + 4]);
+            const int32_t v2 = w.order[t + 2];  // its row has arrived: the per-neighbour state it will look at
+            for (int64_t e = g.indptr[v2]; e < g.indptr[v2 + 1]; e++) {
+                __builtin_prefetch(part.data() + g.indices[e]);
+                __builtin_prefetch(w.refined.data() + g.indices[e]);
+            }
         }
         if (w.rsize[w.refined[v]] != 1) continue;
         const int32_t C = part[v];
