@@ -485,6 +485,10 @@ def run_ours(args, wl, counts):
     by_time = sorted(report.items(), key=lambda kv: -kv[1][0])
     dominant = next((k_ for k_, _ in by_time if k_ in roofs), None)
     unmodelled = [k_ for k_, _ in by_time[:3] if k_ not in roofs]
+    # ... and among the kernels of the streams that bound the loop (PCA / dense build / kNN): the clustering lanes' kernels
+    # (lv_*, lvw_*, jaccard_*, umap_*) run underneath them
+    lanes = ("lv_", "lvw_", "jaccard", "umap_")
+    critical = next((k_ for k_, _ in by_time if k_ in roofs and not k_.startswith(lanes)), None)
     if "knn_tc_listed" in roofs and knn_stats:
         n_blk, n_til = -(-n_aug // 256), -(-n_aug // 128)
         roofs["knn_tc_listed"].update(
@@ -568,6 +572,8 @@ def run_ours(args, wl, counts):
         "roofline_note": ("roofline = the kernel with the most summed CUDA-event time; `traffic` values are per-launch DRAM bytes from "
                           "the committed ncu --set full captures of this workload (profiles/), not measured in this run"
                           + (f"; top kernels without a model: {unmodelled}" if unmodelled else "")),
+        "roofline_critical_path": (dict(roofs[critical], kernel=critical,
+                                        frac_alone=((roofs_alone or {}).get(critical) or {}).get("frac")) if critical else None),
         "rooflines": roofs,
         "rooflines_alone": roofs_alone,
         "peaks": {k_: peaks.get(k_) for k_ in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained", "source")},
