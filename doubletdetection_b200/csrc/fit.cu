@@ -65,15 +65,17 @@ extern "C" int dd_fit_iterations(dd_handle *h, const dd_fit_params *p, const int
     const int64_t N = h->N, M = p->n_synth, A = N + M;
     // PhenoGraph looks at its own neighbourhood size (k nearest + self), not sc.pp.neighbors' 10
     const int k = pheno ? p->pheno_k + 1 : p->knn_k;
-    // the host side of a Louvain iteration (aggregate ~10^2 communities, upper levels, scoring) is a few milliseconds, so
-    // a few workers keep up with the GPU; PhenoGraph and Leiden partition the whole graph on the host (0.2 s and more per
-    // iteration at 100k cells) and are host-bound: they may use more workers
-    // (each worker owns a pinned result slot -- 90 MB for PhenoGraph at 125 k cells -- hence the upper bounds)
-    const int n_threads = std::max(1, std::min(p->n_host_threads, (pheno || leiden) ? 32 : 16));
-    const int n_slots = n_threads + 2;
     const int64_t max_nnz = A * 2 * (k - 1);
     const int64_t w_off = ((A + 1) + A + max_nnz + 1) / 2 * 2;  // weights start 8-byte aligned
     const int64_t slot_elems = (pheno || leiden) ? std::max<int64_t>(w_off + 2 * max_nnz, 2 * A * k) : (A + 1) + A + max_nnz;
+    // Host workers: as many as the caller allows (n_jobs).  The host side of a Louvain iteration (aggregate ~10^2 communities,
+    // upper levels, scoring) is a few milliseconds, so a few workers keep up with the GPU; PhenoGraph and Leiden partition
+    // much more on the host and are host-bound.  Every worker owns a pinned result slot (10 MB for Louvain, 90 MB for
+    // PhenoGraph at 125 k cells, 0.9 GB at 1.25 M), so the count is bounded by 8 GB of pinned memory per loop, and by 64.
+    const int64_t slot_budget = (8ll << 30) / (int64_t)sizeof(int32_t);
+    const int by_memory = (int)std::max<int64_t>(1, std::min<int64_t>(64, slot_budget / std::max<int64_t>(slot_elems, 1) - 2));
+    const int n_threads = std::max(1, std::min(std::min(p->n_host_threads, 64), by_memory));
+    const int n_slots = n_threads + 2;
     const int n_run = p->iter_end - p->iter_begin;
     if (stage_ms_out) std::fill(stage_ms_out, stage_ms_out + 8, 0.0);
     if (n_run == 0) return DD_OK;
