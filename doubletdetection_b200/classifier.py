@@ -370,6 +370,13 @@ class BoostClassifier:
         num_synths = int(self.boost_rate * num_cells)  # :391
         n_aug = num_cells + num_synths
         omega, n_power_iter = _pca_plan(n_aug, num_genes, self.n_components, self.random_state, arpack=arpack)
+        # sklearn's own argument check (PCA._fit_full / _fit_truncated), which is where the reference fails for such shapes
+        n_min = min(n_aug, num_genes)
+        if self.n_components > n_min or (arpack and self.n_components >= n_min):
+            raise ValueError(f"n_components={self.n_components} must be {'strictly less than' if arpack else 'between 0 and'} "
+                             f"min(n_samples, n_features)={n_min} for the PCA of the {n_aug} x {num_genes} augmented matrix")
+        if omega is not None and num_genes <= 50 and self.clustering_algorithm != "phenograph":  # unreachable: see _pca_solver
+            raise NotImplementedError("at most 50 genes (sc.pp.neighbors then works on X, not X_pca) outside the exact-PCA route")
         if omega is None and min(n_aug, num_genes) > 16384:
             raise NotImplementedError(
                 f"exact PCA (pseudocount=1 selects svd_solver='arpack') of a {n_aug} x {num_genes} matrix: the float64 Gram "
@@ -491,13 +498,20 @@ class BoostClassifier:
         synth_comm = np.zeros((self.n_iters, n_synth), dtype=np.int32)
         algo = cluster_kw["clustering"]
         seed = int(self.random_state)
+        # sc.pp.neighbors (:331-336) looks at adata.X itself, not at X_pca, when there are at most 50 genes (scanpy's
+        # settings.N_PCS) -- such matrices always land on this route (sklearn's "auto" is exact for them), and the
+        # device kNN then runs on the (<= 50-column) normalised matrix.  phenograph.cluster (:320) is handed X_pca regardless.
+        knn_on_x = self._num_genes <= 50 and algo != "phenograph"
         t0 = _time.perf_counter()
         for i in range(it0, it1):
             h.create_doublets(parents[i])
             h.normalise_log(h.median_lib_size(), self.pseudocount)
             if self.standard_scaling is True:
                 h.standard_scale(15.0)
-            _exact_pca(h, self.n_components)
+            if knn_on_x:
+                h.upload_embedding(h.download_dense())
+            else:
+                _exact_pca(h, self.n_components)
             if algo == "phenograph":
                 idx, _ = h.knn(cluster_kw["pheno_k"] + 1, with_dist=False)
                 labels = _capi.phenograph_knn(idx, prune=cluster_kw["pheno_prune"],

@@ -232,3 +232,49 @@ def test_classifier_pseudocount1_vs_reference_golden(name):
     for i in np.nonzero(same)[0]:
         np.testing.assert_array_equal(clf.all_scores_[i], g["all_scores"][i])
         np.testing.assert_allclose(clf.all_log_p_values_[i], g["all_log_p_values"][i], rtol=1e-4, atol=1e-12)
+
+
+@pytest.mark.parametrize("algo,n_genes", [("louvain", 40), ("leiden", 24)])
+def test_at_most_50_genes_neighbours_on_x(handle, algo, n_genes):
+    """with at most 50 genes ``sc.pp.neighbors`` (doubletdetection.py:331-336) takes its neighbours from adata.X
+    itself instead of X_pca (scanpy's N_PCS).  The classifier must do the same: the oracle's downstream stages run on the
+    DEVICE's normalised matrix reproduce its communities and scores exactly, and no PCA is involved any more, so the
+    oracle's own end-to-end run agrees as well (up to near-ties among 2-ulp different log values)."""
+    from sklearn.metrics import adjusted_rand_score
+
+    from doubletdetection_b200 import BoostClassifier, _capi
+    from oracle import leiden_ref
+
+    rs = np.random.default_rng(77)
+    n = 1500
+    prof = 25.0 * np.exp(rs.normal(0.0, 0.7, size=(6, n_genes)))  # deep counts: no two cells get identical rows
+    counts = rs.poisson(prof[rs.integers(0, 6, n)] * rs.lognormal(0.0, 0.25, size=(n, 1))).astype(np.float32)
+    kw = dict(n_iters=2, clustering_algorithm=algo, random_state=0, n_components=min(30, n_genes // 2))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clf = BoostClassifier(n_jobs=2, **kw).fit(counts)
+        ora = reference_path.OracleClassifier(louvain_fn=louvain_c.louvain, **kw).fit(counts)
+        with pytest.raises(ValueError):  # sklearn's check inside sc.tl.pca: more components than genes
+            BoostClassifier(n_iters=2, clustering_algorithm=algo, n_components=n_genes + 1).fit(counts)
+    np.testing.assert_array_equal(np.asarray(clf.parents_, dtype=np.int64), np.asarray(ora.parents_, dtype=np.int64))
+    handle.upload_counts(reference_path.prologue(counts, 10000)["raw"])
+    for i in range(2):
+        handle.create_doublets(np.asarray(clf._parents_array[i]))
+        handle.normalise_log(handle.median_lib_size(), 0.1)
+        idx, dist = upstream.knn_brute(handle.download_dense(), 10)
+        if algo == "leiden":
+            C = upstream.fuzzy_connectivities(idx, dist)
+            labels = leiden_ref.leiden(C.indptr, C.indices, C.data.astype(np.float64), resolution=4.0, seed=0)
+        else:
+            g = upstream.knn_pattern_graph(idx)
+            labels = louvain_c.louvain(g.indptr, g.indices, None, resolution=4.0, seed=0, level0="parallel")
+        labels = np.asarray(labels)
+        if algo == "louvain":  # the pattern graph depends on the neighbour SETS only
+            np.testing.assert_array_equal(clf.communities_[i], labels[:n])
+            s, lp, _, _ = reference_path.score_communities(labels, n)
+            np.testing.assert_array_equal(clf.all_scores_[i], s)
+        else:  # umap's weights see the float32 distances: sklearn's and the device's differ in the last bits
+            assert adjusted_rand_score(clf.communities_[i], labels[:n]) > 0.5
+    ari = [adjusted_rand_score(clf.communities_[i], ora.communities_[i]) for i in range(2)]
+    print(f"\\n[{algo}, {n_genes} genes] adjusted Rand vs the oracle's end-to-end run: {np.round(ari, 4)}")
+    assert min(ari) > (0.9 if algo == "louvain" else 0.5)
