@@ -276,5 +276,5 @@ def test_at_most_50_genes_neighbours_on_x(handle, algo, n_genes):
         else:  # umap's weights see the float32 distances: sklearn's and the device's differ in the last bits
             assert adjusted_rand_score(clf.communities_[i], labels[:n]) > 0.5
     ari = [adjusted_rand_score(clf.communities_[i], ora.communities_[i]) for i in range(2)]
-    print(f"\\n[{algo}, {n_genes} genes] adjusted Rand vs the oracle's end-to-end run: {np.round(ari, 4)}")
+    print(f"\n[{algo}, {n_genes} genes] adjusted Rand vs the oracle's end-to-end run: {np.round(ari, 4)}")
     assert min(ari) > (0.9 if algo == "louvain" else 0.5)
