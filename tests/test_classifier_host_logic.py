@@ -12,7 +12,7 @@ import pytest
 import scipy.sparse as sp_sparse
 
 from conftest import golden_case, load_golden
-from oracle import louvain_c, reference_path, upstream
+from oracle import datasets, louvain_c, reference_path, upstream
 
 
 class OracleHandle:
@@ -292,3 +292,17 @@ def test_sparse_input_with_nan_raises_sklearns_error(shim):
         warnings.simplefilter("ignore")
         with pytest.raises(ValueError, match="NaN"):
             shim(n_iters=2, clustering_algorithm="louvain").fit(x)
+
+
+def test_more_components_than_the_matrix_allows_raises_sklearns_value_error(shim):
+    """``sc.tl.pca(n_comps=...)`` ends in sklearn's range check (PCA._fit_full / _fit_truncated): more components than
+    min(augmented cells, genes) is a ValueError in the reference, and for its sparse ``pseudocount == 1`` branch
+    (``svd_solver="arpack"``) the bound is strict.  The shim raises before anything is uploaded."""
+    counts = datasets.poisson_counts(300, 24, seed=3) + 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(ValueError, match="n_components=25"):
+            shim(n_iters=2, clustering_algorithm="louvain", n_components=25).fit(counts)
+        with pytest.raises(ValueError, match="strictly less"):
+            shim(n_iters=2, clustering_algorithm="louvain", n_components=24, pseudocount=1).fit(counts)
+    assert OracleHandle.calls == []
